@@ -1,0 +1,195 @@
+/*
+ * dsc.h -- C ABI of the B200-native deformable two-view hot path.
+ *
+ * One library (libdsc_b200.so, hand-written sm_100a CUDA) behind plain-C entry
+ * points.  Every entry point names the reference code it replaces (paths are
+ * relative to the reference repository, luicalrob/Triangulation-in-Deformable-Scenes):
+ *
+ *   dsc_triangulate*        Modules/Utils/Geometry.cc:216-230 useTriangulationMethod and the four
+ *                           triangulators (:62-214), called per match from
+ *                           Modules/Mapping/Mapping.cc:294-343 (+ gate :351-364) and
+ *                           Modules/Mapping/MonocularMapInitializer.cc:303-368 (+ gates :315-360);
+ *                           KannalaBrandt8::unproject/project Modules/Calibration/KannalaBrandt8.cc:32-83
+ *   dsc_depth_scale_init    Modules/Map/KeyFrame.cc:131-153 setInitialDepthScaleInSimulationImages
+ *   dsc_problem_upload      the Map -> g2o graph gather of arapOptimization,
+ *                           Modules/Optimization/g2oBundleAdjustment.cc:640-957
+ *   dsc_set_graph           mesh adjacency + cot weights + area + triangle count,
+ *                           g2oBundleAdjustment.cc:657-662,883-948 (Utils/Geometry.cc:272-368)
+ *   dsc_compute_rotations   Modules/Utils/Geometry.cc:549-604 computeR (called :687-688)
+ *   dsc_cost                g2o computeActiveErrors + activeRobustChi2 over the edges of
+ *                           Modules/Optimization/g2oTypes.h:267-349,390-421
+ *   dsc_optimize            optimizer.optimize(nOptIterations), g2oBundleAdjustment.cc:959-962
+ *                           (g2o Levenberg-Marquardt + BlockSolverX + LinearSolverEigen, :619-628)
+ *   dsc_download            the write-back :967-1007 (points cast to float, depth scales, T_global,
+ *                           optimizationUpdate)
+ *   dsc_pixel_sigma         Modules/Utils/Geometry.cc:370-498 calculatePixelsStandDev
+ *
+ * Conventions: every function returns an int status (DSC_OK == 0, negative = error, see
+ * dsc_status); nothing throws across the boundary; all pointers are HOST pointers unless the
+ * name says _dev; the caller keeps ownership of everything it passes in.  One context owns one
+ * CUDA stream and must be driven by one host thread at a time; several contexts may run
+ * concurrently.  There is NO CPU fallback: without a CUDA device dsc_create fails.
+ */
+#ifndef DSC_H_
+#define DSC_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct dsc_ctx dsc_ctx;
+
+typedef enum {
+    DSC_OK = 0,
+    DSC_ERR_INVALID_ARG = -1,
+    DSC_ERR_CUDA = -2,
+    DSC_ERR_NO_DEVICE = -3,
+    DSC_ERR_STATE = -4,          /* call order violated (e.g. optimize before set_graph)   */
+    DSC_ERR_NONFINITE = -5,      /* cost became NaN/inf                                      */
+    DSC_ERR_PCG_BREAKDOWN = -6,  /* p.Ap <= 0 or non-finite inside the linear solve          */
+    DSC_ERR_GRAPH = -7,          /* neighbour graph is not symmetric / has bad indices       */
+    DSC_ERR_ALLOC = -8
+} dsc_status;
+
+/* camera models: Modules/Calibration/{KannalaBrandt8,PinHole}.cc */
+enum { DSC_CAM_KB8 = 0, DSC_CAM_PINHOLE = 1 };
+/* Triangulation.method (Geometry.cc:220-228): unknown strings select NRSLAM */
+enum { DSC_TRI_CLASSIC = 0, DSC_TRI_NRSLAM = 1, DSC_TRI_ORBSLAM = 2, DSC_TRI_DEPTH = 3 };
+/* Triangulation.seed.location */
+enum { DSC_LOC_INRAYS = 0, DSC_LOC_TWOPOINTS = 1, DSC_LOC_FARPOINTS = 2 };
+/* validity gates */
+enum { DSC_GATE_NONE = 0, DSC_GATE_SIM = 1 /* Mapping.cc:351-364 */, DSC_GATE_REAL = 2 /* MonocularMapInitializer.cc:315-360 */ };
+
+typedef struct {
+    int   model;        /* DSC_CAM_*                                  */
+    float params[8];    /* fx fy cx cy k0 k1 k2 k3 (Settings.cc:38-50) */
+} dsc_camera;
+
+/* A key-frame pair.  Tcw are row-major 3x4 [R|t] float matrices (Sophus::SE3f KeyFrame::getPose()). */
+typedef struct {
+    dsc_camera cam1, cam2;
+    float T1w[12];
+    float T2w[12];
+} dsc_pair;
+
+typedef struct {
+    int   method;          /* DSC_TRI_*                                               */
+    int   location;        /* DSC_LOC_*                                               */
+    int   gate;            /* DSC_GATE_*                                              */
+    float min_cos;         /* Triangulation.minCos                                    */
+    float depth_limit;     /* Triangulation.depthLimit (GATE_REAL)                    */
+    int   check_reproj;    /* Triangulation.checks: reprojection^2 <= 5.991 (GATE_REAL) */
+} dsc_tri_params;
+
+/* the balance weights of arapOptimization(Map*, rep, global, arap, alpha, beta, DepthError, nIter, update) */
+typedef struct {
+    double rep;
+    double global;         /* accepted, unused -- as in the reference body   */
+    double arap;
+    double alpha;          /* stored on the edge, unused (g2oTypes.h:346-347) */
+    double beta;
+    float  depth_sigma;    /* DepthError (metres); information = 1/sigma^2    */
+} dsc_weights;
+
+typedef struct {
+    double rtol;           /* stop when sqrt(r.z / r0.z0) <= rtol  (default 1e-10)      */
+    int    max_iters;      /* per linear solve                      (default 4000)       */
+    int    check_every;    /* host polls convergence every this many iterations (32)    */
+} dsc_pcg_params;
+
+/* per LM iteration record (one per outer g2o iteration) */
+typedef struct {
+    double chi2_before;    /* activeRobustChi2 at the start of the iteration */
+    double chi2_after;     /* after the accepted step (== before if none)    */
+    double lambda;         /* lambda at the start of the iteration           */
+    int    trials;         /* lambda trials                                   */
+    int    accepted;
+    int    pcg_iters;      /* summed over the trials                          */
+} dsc_iter_record;
+
+typedef struct {
+    int    iterations;         /* LM iterations executed                       */
+    int    total_trials;
+    int    total_pcg_iters;
+    int    terminated;         /* 1 if g2o's Terminate condition fired         */
+    double final_chi2;
+    double device_ms;          /* CUDA-event time of the whole call            */
+    double linearize_ms, pcg_ms, trial_ms;   /* CUDA-event breakdown           */
+    int    kernel_launches;
+} dsc_opt_stats;
+
+/* ---- context --------------------------------------------------------------------------- */
+int  dsc_create(int device, dsc_ctx** out);
+void dsc_destroy(dsc_ctx* ctx);
+const char* dsc_last_error(const dsc_ctx* ctx);
+const char* dsc_status_string(int status);
+int  dsc_version(void);
+int  dsc_synchronize(dsc_ctx* ctx);
+/* CUDA-event stopwatch on the context's stream (bench.py times kernels with it) */
+int  dsc_timer_start(dsc_ctx* ctx);
+int  dsc_timer_stop(dsc_ctx* ctx, double* ms);
+/* number of kernels this context has launched so far */
+int  dsc_launch_count(const dsc_ctx* ctx, long long* count);
+
+/* ---- K1: batched two-view triangulation -------------------------------------------------
+ * Host arrays of n matches: uv1/uv2 [n][2] pixels, depth1/depth2 [n] (may be NULL unless
+ * method == DSC_TRI_DEPTH).  Outputs X1/X2 [n][3] world points, valid[n], cos_parallax[n]
+ * (any output may be NULL).  dsc_triangulate = upload + kernel + download (end-to-end);
+ * the three-step form keeps data resident for repeated kernel timing. */
+int dsc_triangulate(dsc_ctx* ctx, const dsc_pair* pair, const dsc_tri_params* prm, int n,
+                    const float* uv1, const float* uv2, const float* depth1, const float* depth2,
+                    float* X1, float* X2, uint8_t* valid, float* cos_parallax, int* n_valid);
+int dsc_tri_upload(dsc_ctx* ctx, const dsc_pair* pair, int n, const float* uv1, const float* uv2,
+                   const float* depth1, const float* depth2);
+int dsc_tri_run(dsc_ctx* ctx, const dsc_tri_params* prm);
+int dsc_tri_download(dsc_ctx* ctx, float* X1, float* X2, uint8_t* valid, float* cos_parallax, int* n_valid);
+/* mean of depth/z_c over valid points with non-zero depth (KeyFrame.cc:131-153); which = 1|2 */
+int dsc_depth_scale_init(dsc_ctx* ctx, int which, double* scale);
+
+/* ---- the refinement problem ---------------------------------------------------------------
+ * n compact correspondences (every one has both map points and both observations):
+ * X1/X2 [n][3] float map-point positions, uv1/uv2 [n][2], depth1/depth2 [n] (metres, as returned
+ * by KeyFrame::getDepthMeasure(..., false)), inv_sigma2_1/2 [n] (KeyFrame::getInvSigma2(octave),
+ * NULL = 1), initial depth scales, T_global as (qx,qy,qz,qw,tx,ty,tz) (NULL = identity). */
+int dsc_problem_upload(dsc_ctx* ctx, const dsc_pair* pair, int n,
+                       const float* X1, const float* X2, const float* uv1, const float* uv2,
+                       const double* depth1, const double* depth2,
+                       const float* inv_sigma2_1, const float* inv_sigma2_2,
+                       double scale1, double scale2, const double* Tg7);
+/* symmetric CSR neighbour graph over the n correspondences: rowptr[n+1], col[E], w[E]
+ * (w[i->j] == w[j->i]), mesh area, triangle count (ARAP information = arap * n_triangles^2).
+ * reorder != 0 lets the library renumber the correspondences along a space-filling curve
+ * internally; all results come back in the caller's numbering. */
+int dsc_set_graph(dsc_ctx* ctx, int n, const int32_t* rowptr, const int32_t* col, const double* w,
+                  double area, long long n_triangles, int reorder);
+int dsc_compute_rotations(dsc_ctx* ctx);
+/* rotations as unit quaternions (x,y,z,w) [n][4] */
+int dsc_get_rotations(dsc_ctx* ctx, double* quat);
+int dsc_set_rotations(dsc_ctx* ctx, const double* quat);
+/* back to the uploaded points / scales / T_global (replaces Map::clone() for the weight search) */
+int dsc_reset_state(dsc_ctx* ctx);
+int dsc_set_pcg(dsc_ctx* ctx, const dsc_pcg_params* prm);
+/* total robust chi2 of the current state; parts[3] = reprojection, depth, ARAP (may be NULL) */
+int dsc_cost(dsc_ctx* ctx, const dsc_weights* w, double* chi2, double* parts);
+/* n_iters LM iterations; records[n_iters] and stats may be NULL */
+int dsc_optimize(dsc_ctx* ctx, const dsc_weights* w, int n_iters, dsc_iter_record* records, dsc_opt_stats* stats);
+/* X1/X2 [n][3] float (cast like the reference), fp64 copies X1d/X2d [n][3] (may be NULL),
+ * scales[2], Tg7, update = sum |p_uploaded - p_now| over all 2n points (float norm, double sum) */
+int dsc_download(dsc_ctx* ctx, float* X1, float* X2, double* X1d, double* X2d,
+                 double* scales, double* Tg7, double* update);
+/* calculatePixelsStandDev on the current state: sigma[2] = C1, C2 */
+int dsc_pixel_sigma(dsc_ctx* ctx, double* sigma);
+
+/* gradient b (8 + 6n, oracle layout [T(6) s1 s2 | X1_0 X2_0 ...]) and diagonal of H for the current
+ * state -- test hook for the assembly kernels */
+int dsc_debug_linearize(dsc_ctx* ctx, const dsc_weights* w, double* b, double* hdiag, double* chi2);
+/* y = (H + lambda I) x with the matrix-free operator the PCG uses -- test hook */
+int dsc_debug_matvec(dsc_ctx* ctx, const dsc_weights* w, double lambda, const double* x, double* y);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DSC_H_ */

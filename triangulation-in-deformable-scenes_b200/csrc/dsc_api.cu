@@ -1,0 +1,856 @@
+// dsc_api.cu -- context, C ABI (include/dsc.h) and the Levenberg-Marquardt host loop.
+//
+// The LM control flow restates g2o::OptimizationAlgorithmLevenberg::solve as configured by the
+// reference at Modules/Optimization/g2oBundleAdjustment.cc:619-628,959-962 (upstream g2o
+// core/optimization_algorithm_levenberg.cpp; the library itself is not vendored by the reference):
+// lambda_0 = 1e-5 max|diag H|, rho = (chi - chi_new) / (dx.(lambda dx + b) + 1e-3), good step
+// lambda *= max(1/3, min(2/3, 1 - (2 rho - 1)^3)), bad step lambda *= ni, ni *= 2, <= 10 trials.
+// All state stays in HBM; per trial the host reads back two scalars.
+#include "../../include/dsc.h"
+#include "dsc_kernels.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <string>
+#include <vector>
+
+using namespace dsc;
+
+#define DSC_VERSION 100
+
+struct dsc_ctx {
+    int device = 0;
+    int sms = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, evA = nullptr, evB = nullptr;
+    std::string err;
+    long long launches = 0;
+
+    // ---- triangulation stage
+    int tn = 0, tcap = 0;
+    bool t_has_depth = false;
+    PairDev tpair{};
+    float2 *t_uv1 = nullptr, *t_uv2 = nullptr;
+    float *t_d1 = nullptr, *t_d2 = nullptr, *t_X1 = nullptr, *t_X2 = nullptr, *t_cos = nullptr;
+    uint8_t* t_valid = nullptr;
+    bool t_done = false;
+
+    // ---- refinement problem
+    int n = 0, cap = 0;
+    long long E = 0, ecap = 0;
+    bool have_problem = false, have_graph = false, have_rot = false;
+    PairDev pair{};
+    double area = 1.0;
+    long long ntri = 0;
+    Globals g0{};                         // uploaded globals
+    std::vector<int> perm;                // internal index -> caller index
+    std::vector<float> hX1, hX2, huv1, huv2, hisg1, hisg2;
+    std::vector<double> hd1, hd2;
+    float *X1f = nullptr, *X2f = nullptr;         // staging (caller order)
+    int* d_perm = nullptr;
+    double *P = nullptr, *Ptrial = nullptr, *P0 = nullptr, *Q = nullptr;
+    float4* uv = nullptr;
+    double2* dm = nullptr;
+    float2* isg = nullptr;
+    int *rowptr = nullptr, *col = nullptr;
+    double* wgt = nullptr;
+    double *b = nullptr, *D = nullptr, *U = nullptr, *Minv = nullptr;
+    double* vec[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // x r z w p s
+    double* small = nullptr;              // 6 x 8 global vectors + Ginv(64)
+    Globals *Gcur = nullptr, *Gtrial = nullptr;
+    LinGlobal* lin = nullptr;
+    CgControl* ctl = nullptr;
+    int* errflag = nullptr;
+    double* part = nullptr;               // partial-sum scratch
+    double *gpart[2] = {nullptr, nullptr}, *dpart = nullptr, *bpart = nullptr;
+    double* h_pinned = nullptr;           // pinned host scratch
+    dsc_pcg_params pcg{1e-10, 4000, 32};
+};
+
+namespace {
+
+const char* status_str(int s) {
+    switch (s) {
+        case DSC_OK: return "ok";
+        case DSC_ERR_INVALID_ARG: return "invalid argument";
+        case DSC_ERR_CUDA: return "CUDA error";
+        case DSC_ERR_NO_DEVICE: return "no CUDA device (there is no CPU fallback)";
+        case DSC_ERR_STATE: return "call order violated";
+        case DSC_ERR_NONFINITE: return "non-finite cost";
+        case DSC_ERR_PCG_BREAKDOWN: return "PCG breakdown";
+        case DSC_ERR_GRAPH: return "neighbour graph invalid (must be symmetric, in range, no self loops)";
+        case DSC_ERR_ALLOC: return "allocation failed";
+    }
+    return "unknown";
+}
+
+int fail(dsc_ctx* c, int code, const std::string& what) {
+    if (c) c->err = std::string(status_str(code)) + ": " + what;
+    return code;
+}
+
+#define CK(call)                                                                              \
+    do {                                                                                      \
+        cudaError_t e_ = (call);                                                              \
+        if (e_ != cudaSuccess)                                                                \
+            return fail(ctx, DSC_ERR_CUDA, std::string(#call) + " -> " + cudaGetErrorString(e_)); \
+    } while (0)
+
+template <typename T>
+cudaError_t dev_alloc(T*& p, size_t count) {
+    if (p) { cudaFree(p); p = nullptr; }
+    if (count == 0) return cudaSuccess;
+    return cudaMalloc(reinterpret_cast<void**>(&p), count * sizeof(T));
+}
+template <typename T>
+void dev_free(T*& p) { if (p) { cudaFree(p); p = nullptr; } }
+
+int grid_threads(const dsc_ctx* c, long long n) {           // thread-per-item kernels
+    long long nb = (n + kThreads - 1) / kThreads;
+    long long cap = (long long)c->sms * 8;
+    return (int)std::max(1LL, std::min(nb, cap));
+}
+int grid_groups(const dsc_ctx* c, long long n) {            // 8-lanes-per-item kernels
+    long long nb = (n + kGroups - 1) / kGroups;
+    long long cap = (long long)c->sms * 8;
+    return (int)std::max(1LL, std::min(nb, cap));
+}
+
+void fill_pair(const dsc_pair* in, PairDev& o) {
+    o.cam1.model = in->cam1.model; o.cam2.model = in->cam2.model;
+    for (int k = 0; k < 8; ++k) { o.cam1.p[k] = in->cam1.params[k]; o.cam2.p[k] = in->cam2.params[k]; }
+    for (int cam = 0; cam < 2; ++cam) {
+        const float* T = cam == 0 ? in->T1w : in->T2w;
+        PoseF& pf = cam == 0 ? o.T1f : o.T2f;
+        double* Rd = cam == 0 ? o.R1 : o.R2;
+        double* td = cam == 0 ? o.t1 : o.t2;
+        double R64[9];
+        for (int r = 0; r < 3; ++r) {
+            for (int cc = 0; cc < 3; ++cc) { pf.R[r * 3 + cc] = T[r * 4 + cc]; R64[r * 3 + cc] = (double)T[r * 4 + cc]; }
+            pf.t[r] = T[r * 4 + 3];
+            td[r] = (double)T[r * 4 + 3];
+        }
+        // g2o::SE3Quat(kfPose.unit_quaternion().cast<double>(), ...): quaternion, normalised, back to a matrix
+        double q[4];
+        rot_to_quat(R64, q);
+        quat_to_rot(q, Rd);
+    }
+}
+
+WeightsDev make_weights(const dsc_ctx* c, const dsc_weights* w) {
+    WeightsDev o;
+    o.rep = w->rep;
+    o.arap_info = w->arap * (double)c->ntri * (double)c->ntri;
+    double sd = (double)w->depth_sigma;
+    o.depth_info = 1.0 / (sd * sd);
+    o.inv_area = 1.0 / c->area;
+    o.huber = (double)(float)std::sqrt(100.991);
+    return o;
+}
+
+// spread the low 16 bits of v so that there is a zero between every bit
+uint32_t part1by1(uint32_t v) {
+    v &= 0x0000ffffu;
+    v = (v | (v << 8)) & 0x00ff00ffu;
+    v = (v | (v << 4)) & 0x0f0f0f0fu;
+    v = (v | (v << 2)) & 0x33333333u;
+    v = (v | (v << 1)) & 0x55555555u;
+    return v;
+}
+
+double host_sum(const double* p, int n, int stride = 1, int off = 0) {
+    double s = 0.0;
+    for (int i = 0; i < n; ++i) s += p[(size_t)i * stride + off];
+    return s;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------ context
+extern "C" int dsc_version(void) { return DSC_VERSION; }
+extern "C" const char* dsc_status_string(int s) { return status_str(s); }
+extern "C" const char* dsc_last_error(const dsc_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+extern "C" int dsc_create(int device, dsc_ctx** out) {
+    if (!out) return DSC_ERR_INVALID_ARG;
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) return DSC_ERR_NO_DEVICE;
+    if (device < 0 || device >= count) return DSC_ERR_INVALID_ARG;
+    dsc_ctx* ctx = new dsc_ctx();
+    ctx->device = device;
+    auto bail = [&](int code) { dsc_destroy(ctx); return code; };
+    if (cudaSetDevice(device) != cudaSuccess) return bail(DSC_ERR_CUDA);
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return bail(DSC_ERR_CUDA);
+    ctx->sms = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(DSC_ERR_CUDA);
+    cudaEventCreate(&ctx->ev0); cudaEventCreate(&ctx->ev1); cudaEventCreate(&ctx->evA); cudaEventCreate(&ctx->evB);
+    if (cudaMalloc(&ctx->Gcur, sizeof(Globals)) != cudaSuccess) return bail(DSC_ERR_ALLOC);
+    if (cudaMalloc(&ctx->Gtrial, sizeof(Globals)) != cudaSuccess) return bail(DSC_ERR_ALLOC);
+    if (cudaMalloc(&ctx->lin, sizeof(LinGlobal)) != cudaSuccess) return bail(DSC_ERR_ALLOC);
+    if (cudaMalloc(&ctx->ctl, sizeof(CgControl)) != cudaSuccess) return bail(DSC_ERR_ALLOC);
+    if (cudaMalloc(&ctx->errflag, sizeof(int)) != cudaSuccess) return bail(DSC_ERR_ALLOC);
+    if (cudaMalloc(&ctx->small, sizeof(double) * (6 * 8 + 64)) != cudaSuccess) return bail(DSC_ERR_ALLOC);
+    if (cudaMalloc(&ctx->part, sizeof(double) * kMaxBlocks * kLinPart) != cudaSuccess) return bail(DSC_ERR_ALLOC);
+    if (cudaMalloc(&ctx->gpart[0], sizeof(double) * kMaxBlocks) != cudaSuccess) return bail(DSC_ERR_ALLOC);
+    if (cudaMalloc(&ctx->gpart[1], sizeof(double) * kMaxBlocks) != cudaSuccess) return bail(DSC_ERR_ALLOC);
+    if (cudaMalloc(&ctx->dpart, sizeof(double) * kMaxBlocks) != cudaSuccess) return bail(DSC_ERR_ALLOC);
+    if (cudaMalloc(&ctx->bpart, sizeof(double) * kMaxBlocks * 8) != cudaSuccess) return bail(DSC_ERR_ALLOC);
+    if (cudaMallocHost(&ctx->h_pinned, sizeof(double) * kMaxBlocks * kLinPart) != cudaSuccess) return bail(DSC_ERR_ALLOC);
+    cudaMemset(ctx->errflag, 0, sizeof(int));
+    *out = ctx;
+    return DSC_OK;
+}
+
+extern "C" void dsc_destroy(dsc_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    dev_free(ctx->t_uv1); dev_free(ctx->t_uv2); dev_free(ctx->t_d1); dev_free(ctx->t_d2);
+    dev_free(ctx->t_X1); dev_free(ctx->t_X2); dev_free(ctx->t_cos); dev_free(ctx->t_valid);
+    dev_free(ctx->X1f); dev_free(ctx->X2f); dev_free(ctx->d_perm);
+    dev_free(ctx->P); dev_free(ctx->Ptrial); dev_free(ctx->P0); dev_free(ctx->Q);
+    dev_free(ctx->uv); dev_free(ctx->dm); dev_free(ctx->isg);
+    dev_free(ctx->rowptr); dev_free(ctx->col); dev_free(ctx->wgt);
+    dev_free(ctx->b); dev_free(ctx->D); dev_free(ctx->U); dev_free(ctx->Minv);
+    for (auto& v : ctx->vec) dev_free(v);
+    dev_free(ctx->small); dev_free(ctx->Gcur); dev_free(ctx->Gtrial); dev_free(ctx->lin); dev_free(ctx->ctl);
+    dev_free(ctx->errflag); dev_free(ctx->part); dev_free(ctx->gpart[0]); dev_free(ctx->gpart[1]);
+    dev_free(ctx->dpart); dev_free(ctx->bpart);
+    if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->evA) cudaEventDestroy(ctx->evA);
+    if (ctx->evB) cudaEventDestroy(ctx->evB);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+extern "C" int dsc_synchronize(dsc_ctx* ctx) {
+    if (!ctx) return DSC_ERR_INVALID_ARG;
+    CK(cudaStreamSynchronize(ctx->stream));
+    return DSC_OK;
+}
+extern "C" int dsc_timer_start(dsc_ctx* ctx) {
+    if (!ctx) return DSC_ERR_INVALID_ARG;
+    CK(cudaEventRecord(ctx->ev0, ctx->stream));
+    return DSC_OK;
+}
+extern "C" int dsc_timer_stop(dsc_ctx* ctx, double* ms) {
+    if (!ctx || !ms) return DSC_ERR_INVALID_ARG;
+    CK(cudaEventRecord(ctx->ev1, ctx->stream));
+    CK(cudaEventSynchronize(ctx->ev1));
+    float f = 0.f;
+    CK(cudaEventElapsedTime(&f, ctx->ev0, ctx->ev1));
+    *ms = (double)f;
+    return DSC_OK;
+}
+extern "C" int dsc_launch_count(const dsc_ctx* ctx, long long* count) {
+    if (!ctx || !count) return DSC_ERR_INVALID_ARG;
+    *count = ctx->launches;
+    return DSC_OK;
+}
+
+// ------------------------------------------------------------------ K1 triangulation
+extern "C" int dsc_tri_upload(dsc_ctx* ctx, const dsc_pair* pair, int n, const float* uv1, const float* uv2,
+                              const float* depth1, const float* depth2) {
+    if (!ctx || !pair || n < 0 || (n > 0 && (!uv1 || !uv2))) return fail(ctx, DSC_ERR_INVALID_ARG, "dsc_tri_upload");
+    CK(cudaSetDevice(ctx->device));
+    if (n > ctx->tcap) {
+        CK(dev_alloc(ctx->t_uv1, (size_t)n)); CK(dev_alloc(ctx->t_uv2, (size_t)n));
+        CK(dev_alloc(ctx->t_d1, (size_t)n)); CK(dev_alloc(ctx->t_d2, (size_t)n));
+        CK(dev_alloc(ctx->t_X1, (size_t)3 * n)); CK(dev_alloc(ctx->t_X2, (size_t)3 * n));
+        CK(dev_alloc(ctx->t_cos, (size_t)n)); CK(dev_alloc(ctx->t_valid, (size_t)n));
+        ctx->tcap = n;
+    }
+    ctx->tn = n;
+    fill_pair(pair, ctx->tpair);
+    ctx->t_has_depth = depth1 && depth2;
+    ctx->t_done = false;
+    if (n == 0) return DSC_OK;
+    CK(cudaMemcpyAsync(ctx->t_uv1, uv1, sizeof(float2) * n, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->t_uv2, uv2, sizeof(float2) * n, cudaMemcpyHostToDevice, ctx->stream));
+    if (ctx->t_has_depth) {
+        CK(cudaMemcpyAsync(ctx->t_d1, depth1, sizeof(float) * n, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->t_d2, depth2, sizeof(float) * n, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    return DSC_OK;
+}
+
+extern "C" int dsc_tri_run(dsc_ctx* ctx, const dsc_tri_params* prm) {
+    if (!ctx || !prm) return fail(ctx, DSC_ERR_INVALID_ARG, "dsc_tri_run");
+    if (prm->method == DSC_TRI_DEPTH && !ctx->t_has_depth) return fail(ctx, DSC_ERR_INVALID_ARG, "DepthMeasurement needs depths");
+    if (prm->method < 0 || prm->method > 3 || prm->location < 0 || prm->location > 2 || prm->gate < 0 || prm->gate > 2)
+        return fail(ctx, DSC_ERR_INVALID_ARG, "triangulation parameters");
+    CK(cudaSetDevice(ctx->device));
+    ctx->t_done = true;
+    if (ctx->tn == 0) return DSC_OK;
+    TriParams tp{prm->method, prm->location, prm->gate, prm->min_cos, prm->depth_limit, prm->check_reproj};
+    triangulate_kernel<<<grid_threads(ctx, ctx->tn), kThreads, 0, ctx->stream>>>(
+        ctx->tn, ctx->t_uv1, ctx->t_uv2, ctx->t_d1, ctx->t_d2, ctx->tpair, tp, ctx->t_X1, ctx->t_X2, ctx->t_valid, ctx->t_cos);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return DSC_OK;
+}
+
+extern "C" int dsc_tri_download(dsc_ctx* ctx, float* X1, float* X2, uint8_t* valid, float* cos_parallax, int* n_valid) {
+    if (!ctx) return DSC_ERR_INVALID_ARG;
+    if (!ctx->t_done) return fail(ctx, DSC_ERR_STATE, "dsc_tri_download before dsc_tri_run");
+    CK(cudaSetDevice(ctx->device));
+    int n = ctx->tn;
+    std::vector<uint8_t> hv;
+    if (n > 0) {
+        if (X1) CK(cudaMemcpyAsync(X1, ctx->t_X1, sizeof(float) * 3 * n, cudaMemcpyDeviceToHost, ctx->stream));
+        if (X2) CK(cudaMemcpyAsync(X2, ctx->t_X2, sizeof(float) * 3 * n, cudaMemcpyDeviceToHost, ctx->stream));
+        if (cos_parallax) CK(cudaMemcpyAsync(cos_parallax, ctx->t_cos, sizeof(float) * n, cudaMemcpyDeviceToHost, ctx->stream));
+        uint8_t* dst = valid;
+        if (!dst && n_valid) { hv.resize(n); dst = hv.data(); }
+        if (dst) CK(cudaMemcpyAsync(dst, ctx->t_valid, n, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        if (n_valid) { int c = 0; for (int i = 0; i < n; ++i) c += dst[i] ? 1 : 0; *n_valid = c; }
+    } else if (n_valid) *n_valid = 0;
+    return DSC_OK;
+}
+
+extern "C" int dsc_triangulate(dsc_ctx* ctx, const dsc_pair* pair, const dsc_tri_params* prm, int n,
+                               const float* uv1, const float* uv2, const float* depth1, const float* depth2,
+                               float* X1, float* X2, uint8_t* valid, float* cos_parallax, int* n_valid) {
+    int s = dsc_tri_upload(ctx, pair, n, uv1, uv2, depth1, depth2);
+    if (s) return s;
+    s = dsc_tri_run(ctx, prm);
+    if (s) return s;
+    return dsc_tri_download(ctx, X1, X2, valid, cos_parallax, n_valid);
+}
+
+extern "C" int dsc_depth_scale_init(dsc_ctx* ctx, int which, double* scale) {
+    if (!ctx || !scale || (which != 1 && which != 2)) return fail(ctx, DSC_ERR_INVALID_ARG, "dsc_depth_scale_init");
+    if (!ctx->t_done || !ctx->t_has_depth) return fail(ctx, DSC_ERR_STATE, "needs a triangulation run with depths");
+    CK(cudaSetDevice(ctx->device));
+    int nb = grid_threads(ctx, ctx->tn);
+    if (ctx->tn == 0) { *scale = std::numeric_limits<double>::quiet_NaN(); return DSC_OK; }
+    depth_scale_kernel<<<nb, kThreads, 0, ctx->stream>>>(ctx->tn, which == 1 ? ctx->t_X1 : ctx->t_X2,
+                                                        which == 1 ? ctx->t_d1 : ctx->t_d2, ctx->t_valid,
+                                                        which == 1 ? ctx->tpair.T1f : ctx->tpair.T2f, ctx->part);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(ctx->h_pinned, ctx->part, sizeof(double) * 2 * nb, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    double s = host_sum(ctx->h_pinned, nb, 2, 0), c = host_sum(ctx->h_pinned, nb, 2, 1);
+    *scale = s / (double)(float)c;
+    return DSC_OK;
+}
+
+// ------------------------------------------------------------------ refinement problem
+static int upload_state(dsc_ctx* ctx) {            // (re)build device state from the host copies, in internal order
+    int n = ctx->n;
+    if (n == 0) return DSC_OK;
+    const int* pm = ctx->perm.empty() ? nullptr : ctx->perm.data();
+    std::vector<float4> uv(n);
+    std::vector<double2> dm(n);
+    std::vector<float2> sg(n);
+    for (int i = 0; i < n; ++i) {
+        int s = pm ? pm[i] : i;
+        uv[i] = make_float4(ctx->huv1[2 * s], ctx->huv1[2 * s + 1], ctx->huv2[2 * s], ctx->huv2[2 * s + 1]);
+        dm[i] = make_double2(ctx->hd1[s], ctx->hd2[s]);
+        sg[i] = make_float2(ctx->hisg1[s], ctx->hisg2[s]);
+    }
+    CK(cudaMemcpyAsync(ctx->uv, uv.data(), sizeof(float4) * n, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->dm, dm.data(), sizeof(double2) * n, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->isg, sg.data(), sizeof(float2) * n, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->X1f, ctx->hX1.data(), sizeof(float) * 3 * n, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->X2f, ctx->hX2.data(), sizeof(float) * 3 * n, cudaMemcpyHostToDevice, ctx->stream));
+    if (pm) CK(cudaMemcpyAsync(ctx->d_perm, pm, sizeof(int) * n, cudaMemcpyHostToDevice, ctx->stream));
+    init_state_kernel<<<grid_threads(ctx, n), kThreads, 0, ctx->stream>>>(n, ctx->X1f, ctx->X2f, pm ? ctx->d_perm : nullptr, ctx->P0);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(ctx->P, ctx->P0, sizeof(double) * 8 * n, cudaMemcpyDeviceToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->Gcur, &ctx->g0, sizeof(Globals), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));       // host staging vectors go out of scope
+    return DSC_OK;
+}
+
+extern "C" int dsc_problem_upload(dsc_ctx* ctx, const dsc_pair* pair, int n,
+                                  const float* X1, const float* X2, const float* uv1, const float* uv2,
+                                  const double* depth1, const double* depth2,
+                                  const float* inv_sigma2_1, const float* inv_sigma2_2,
+                                  double scale1, double scale2, const double* Tg7) {
+    if (!ctx || !pair || n < 0 || (n > 0 && (!X1 || !X2 || !uv1 || !uv2 || !depth1 || !depth2)))
+        return fail(ctx, DSC_ERR_INVALID_ARG, "dsc_problem_upload");
+    CK(cudaSetDevice(ctx->device));
+    if (n > ctx->cap) {
+        size_t N = (size_t)n;
+        CK(dev_alloc(ctx->X1f, 3 * N)); CK(dev_alloc(ctx->X2f, 3 * N)); CK(dev_alloc(ctx->d_perm, N));
+        CK(dev_alloc(ctx->P, 8 * N)); CK(dev_alloc(ctx->Ptrial, 8 * N)); CK(dev_alloc(ctx->P0, 8 * N)); CK(dev_alloc(ctx->Q, 4 * N));
+        CK(dev_alloc(ctx->uv, N)); CK(dev_alloc(ctx->dm, N)); CK(dev_alloc(ctx->isg, N));
+        CK(dev_alloc(ctx->rowptr, N + 1));
+        CK(dev_alloc(ctx->b, 6 * N)); CK(dev_alloc(ctx->D, 21 * N)); CK(dev_alloc(ctx->U, 16 * N)); CK(dev_alloc(ctx->Minv, 21 * N));
+        for (auto& v : ctx->vec) CK(dev_alloc(v, 6 * N));
+        ctx->cap = n;
+    }
+    ctx->n = n;
+    fill_pair(pair, ctx->pair);
+    ctx->hX1.assign(X1, X1 + 3 * (size_t)n); ctx->hX2.assign(X2, X2 + 3 * (size_t)n);
+    ctx->huv1.assign(uv1, uv1 + 2 * (size_t)n); ctx->huv2.assign(uv2, uv2 + 2 * (size_t)n);
+    ctx->hd1.assign(depth1, depth1 + n); ctx->hd2.assign(depth2, depth2 + n);
+    if (inv_sigma2_1) ctx->hisg1.assign(inv_sigma2_1, inv_sigma2_1 + n); else ctx->hisg1.assign(n, 1.0f);
+    if (inv_sigma2_2) ctx->hisg2.assign(inv_sigma2_2, inv_sigma2_2 + n); else ctx->hisg2.assign(n, 1.0f);
+    Globals g{};
+    if (Tg7) {
+        double nq = std::sqrt(Tg7[0] * Tg7[0] + Tg7[1] * Tg7[1] + Tg7[2] * Tg7[2] + Tg7[3] * Tg7[3]);
+        if (!(nq > 0.0)) return fail(ctx, DSC_ERR_INVALID_ARG, "T_global quaternion has zero norm");
+        double s = (Tg7[3] < 0 ? -1.0 : 1.0) / nq;
+        for (int k = 0; k < 4; ++k) g.Tg[k] = Tg7[k] * s;
+        for (int k = 4; k < 7; ++k) g.Tg[k] = Tg7[k];
+    } else { g.Tg[3] = 1.0; }
+    g.s1 = scale1; g.s2 = scale2;
+    quat_to_rot(g.Tg, g.Rg);
+    ctx->g0 = g;
+    ctx->perm.clear();
+    ctx->have_problem = true; ctx->have_graph = false; ctx->have_rot = false;
+    return upload_state(ctx);
+}
+
+extern "C" int dsc_set_graph(dsc_ctx* ctx, int n, const int32_t* rowptr, const int32_t* col, const double* w,
+                             double area, long long n_triangles, int reorder) {
+    if (!ctx || !rowptr || n < 0) return fail(ctx, DSC_ERR_INVALID_ARG, "dsc_set_graph");
+    if (!ctx->have_problem || n != ctx->n) return fail(ctx, DSC_ERR_STATE, "dsc_set_graph: upload a problem of the same size first");
+    const bool validate = !(reorder & 2);
+    reorder &= 1;
+    if (!(area > 0.0) || n_triangles < 0) return fail(ctx, DSC_ERR_INVALID_ARG, "area must be > 0, n_triangles >= 0");
+    CK(cudaSetDevice(ctx->device));
+    long long E = n > 0 ? rowptr[n] : 0;
+    if (rowptr[0] != 0 || E < 0 || (E > 0 && (!col || !w))) return fail(ctx, DSC_ERR_GRAPH, "rowptr");
+    for (int i = 0; i < n; ++i) if (rowptr[i + 1] < rowptr[i]) return fail(ctx, DSC_ERR_GRAPH, "rowptr not monotone");
+    // symmetric, in range, no self loops, symmetric weights (the reference's mesh adjacency always is)
+    if (validate) {
+        std::vector<long long> key((size_t)E);
+        for (int i = 0; i < n; ++i)
+            for (int e = rowptr[i]; e < rowptr[i + 1]; ++e) {
+                int j = col[e];
+                if (j < 0 || j >= n || j == i) return fail(ctx, DSC_ERR_GRAPH, "column index out of range or self loop");
+                key[e] = (long long)i * n + j;
+            }
+        std::vector<size_t> order((size_t)E);
+        for (size_t e = 0; e < (size_t)E; ++e) order[e] = e;
+        std::sort(order.begin(), order.end(), [&](size_t a, size_t b2) { return key[a] < key[b2]; });
+        for (size_t k = 1; k < (size_t)E; ++k)
+            if (key[order[k]] == key[order[k - 1]]) return fail(ctx, DSC_ERR_GRAPH, "duplicate edge");
+        for (int i = 0; i < n; ++i)
+            for (int e = rowptr[i]; e < rowptr[i + 1]; ++e) {
+                long long rk = (long long)col[e] * n + i;
+                size_t lo = 0, hi = (size_t)E;
+                while (lo < hi) { size_t mid = (lo + hi) / 2; if (key[order[mid]] < rk) lo = mid + 1; else hi = mid; }
+                if (lo >= (size_t)E || key[order[lo]] != rk) return fail(ctx, DSC_ERR_GRAPH, "graph is not symmetric");
+                if (w[order[lo]] != w[e]) return fail(ctx, DSC_ERR_GRAPH, "edge weights are not symmetric");
+            }
+    }
+    // internal numbering: Morton order of KF1's world (x,y) -- the plane the reference triangulates in
+    std::vector<int> perm(n), inv(n);
+    for (int i = 0; i < n; ++i) perm[i] = i;
+    if (reorder && n > 1) {
+        float xmin = 1e30f, xmax = -1e30f, ymin = 1e30f, ymax = -1e30f;
+        for (int i = 0; i < n; ++i) {
+            float x = ctx->hX1[3 * (size_t)i], y = ctx->hX1[3 * (size_t)i + 1];
+            if (std::isfinite(x) && std::isfinite(y)) { xmin = std::min(xmin, x); xmax = std::max(xmax, x); ymin = std::min(ymin, y); ymax = std::max(ymax, y); }
+        }
+        float sx = xmax > xmin ? 65535.0f / (xmax - xmin) : 0.f, sy = ymax > ymin ? 65535.0f / (ymax - ymin) : 0.f;
+        std::vector<uint64_t> code(n);
+        for (int i = 0; i < n; ++i) {
+            float x = ctx->hX1[3 * (size_t)i], y = ctx->hX1[3 * (size_t)i + 1];
+            uint32_t qx = std::isfinite(x) ? (uint32_t)std::min(65535.0f, std::max(0.0f, (x - xmin) * sx)) : 0u;
+            uint32_t qy = std::isfinite(y) ? (uint32_t)std::min(65535.0f, std::max(0.0f, (y - ymin) * sy)) : 0u;
+            code[i] = ((uint64_t)(part1by1(qx) | (part1by1(qy) << 1)) << 32) | (uint32_t)i;
+        }
+        std::sort(code.begin(), code.end());
+        for (int i = 0; i < n; ++i) perm[i] = (int)(code[i] & 0xffffffffu);
+    }
+    for (int i = 0; i < n; ++i) inv[perm[i]] = i;
+    std::vector<int> rp(n + 1, 0), cl((size_t)E);
+    std::vector<double> ww((size_t)E);
+    for (int i = 0; i < n; ++i) rp[i + 1] = rp[i] + (rowptr[perm[i] + 1] - rowptr[perm[i]]);
+    for (int i = 0; i < n; ++i) {
+        int s = perm[i], o = rp[i];
+        std::vector<std::pair<int, double>> row;
+        row.reserve(rowptr[s + 1] - rowptr[s]);
+        for (int e = rowptr[s]; e < rowptr[s + 1]; ++e) row.emplace_back(inv[col[e]], w[e]);
+        std::sort(row.begin(), row.end());
+        for (auto& pr2 : row) { cl[o] = pr2.first; ww[o] = pr2.second; ++o; }
+    }
+    if (E > ctx->ecap) {
+        CK(dev_alloc(ctx->col, (size_t)E)); CK(dev_alloc(ctx->wgt, (size_t)E));
+        ctx->ecap = E;
+    }
+    ctx->E = E;
+    ctx->area = area; ctx->ntri = n_triangles;
+    CK(cudaMemcpyAsync(ctx->rowptr, rp.data(), sizeof(int) * (n + 1), cudaMemcpyHostToDevice, ctx->stream));
+    if (E > 0) {
+        CK(cudaMemcpyAsync(ctx->col, cl.data(), sizeof(int) * E, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->wgt, ww.data(), sizeof(double) * E, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    bool identity = true;
+    for (int i = 0; i < n; ++i) if (perm[i] != i) { identity = false; break; }
+    if (identity) ctx->perm.clear(); else ctx->perm = perm;
+    ctx->have_graph = true; ctx->have_rot = false;
+    return upload_state(ctx);
+}
+
+extern "C" int dsc_compute_rotations(dsc_ctx* ctx) {
+    if (!ctx) return DSC_ERR_INVALID_ARG;
+    if (!ctx->have_graph) return fail(ctx, DSC_ERR_STATE, "dsc_compute_rotations before dsc_set_graph");
+    CK(cudaSetDevice(ctx->device));
+    if (ctx->n > 0) {
+        rotations_kernel<<<grid_groups(ctx, ctx->n), kThreads, 0, ctx->stream>>>(ctx->n, ctx->P, ctx->rowptr, ctx->col, ctx->wgt, ctx->Q);
+        ctx->launches++;
+        CK(cudaGetLastError());
+    }
+    ctx->have_rot = true;
+    return DSC_OK;
+}
+
+extern "C" int dsc_get_rotations(dsc_ctx* ctx, double* quat) {
+    if (!ctx || !quat) return DSC_ERR_INVALID_ARG;
+    if (!ctx->have_rot) return fail(ctx, DSC_ERR_STATE, "no rotations yet");
+    CK(cudaSetDevice(ctx->device));
+    int n = ctx->n;
+    std::vector<double> tmp(4 * (size_t)n);
+    if (n) CK(cudaMemcpyAsync(tmp.data(), ctx->Q, sizeof(double) * 4 * n, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < n; ++i) {
+        int d = ctx->perm.empty() ? i : ctx->perm[i];
+        for (int k = 0; k < 4; ++k) quat[4 * (size_t)d + k] = tmp[4 * (size_t)i + k];
+    }
+    return DSC_OK;
+}
+
+extern "C" int dsc_set_rotations(dsc_ctx* ctx, const double* quat) {
+    if (!ctx || !quat) return DSC_ERR_INVALID_ARG;
+    if (!ctx->have_graph) return fail(ctx, DSC_ERR_STATE, "dsc_set_rotations before dsc_set_graph");
+    CK(cudaSetDevice(ctx->device));
+    int n = ctx->n;
+    std::vector<double> tmp(4 * (size_t)n);
+    for (int i = 0; i < n; ++i) {
+        int s = ctx->perm.empty() ? i : ctx->perm[i];
+        for (int k = 0; k < 4; ++k) tmp[4 * (size_t)i + k] = quat[4 * (size_t)s + k];
+    }
+    if (n) CK(cudaMemcpyAsync(ctx->Q, tmp.data(), sizeof(double) * 4 * n, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->have_rot = true;
+    return DSC_OK;
+}
+
+extern "C" int dsc_reset_state(dsc_ctx* ctx) {
+    if (!ctx) return DSC_ERR_INVALID_ARG;
+    if (!ctx->have_problem) return fail(ctx, DSC_ERR_STATE, "no problem uploaded");
+    CK(cudaSetDevice(ctx->device));
+    if (ctx->n) CK(cudaMemcpyAsync(ctx->P, ctx->P0, sizeof(double) * 8 * ctx->n, cudaMemcpyDeviceToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->Gcur, &ctx->g0, sizeof(Globals), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return DSC_OK;
+}
+
+extern "C" int dsc_set_pcg(dsc_ctx* ctx, const dsc_pcg_params* prm) {
+    if (!ctx || !prm || !(prm->rtol > 0.0) || prm->max_iters < 1 || prm->check_every < 1) return fail(ctx, DSC_ERR_INVALID_ARG, "dsc_set_pcg");
+    ctx->pcg = *prm;
+    return DSC_OK;
+}
+
+static int ready(dsc_ctx* ctx, const dsc_weights* w) {
+    if (!ctx || !w) return DSC_ERR_INVALID_ARG;
+    if (!ctx->have_problem || !ctx->have_graph || !ctx->have_rot)
+        return fail(ctx, DSC_ERR_STATE, "need dsc_problem_upload, dsc_set_graph and rotations first");
+    if (!(w->depth_sigma > 0.f) || !std::isfinite(w->depth_sigma))
+        return fail(ctx, DSC_ERR_INVALID_ARG, "depth_sigma must be finite and > 0 (the reference divides by it, g2oBundleAdjustment.cc:824)");
+    return DSC_OK;
+}
+
+static int eval_cost(dsc_ctx* ctx, const WeightsDev& W, const double* P, const Globals* G, double* chi2, double* parts) {
+    int nb = grid_groups(ctx, ctx->n);
+    cost_kernel<<<nb, kThreads, 0, ctx->stream>>>(ctx->n, P, ctx->Q, ctx->uv, ctx->dm, ctx->isg, ctx->rowptr, ctx->col, ctx->wgt,
+                                                 G, ctx->pair, W, ctx->part);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(ctx->h_pinned, ctx->part, sizeof(double) * 3 * nb, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    double p0 = host_sum(ctx->h_pinned, nb, 3, 0), p1 = host_sum(ctx->h_pinned, nb, 3, 1), p2 = host_sum(ctx->h_pinned, nb, 3, 2);
+    if (parts) { parts[0] = p0; parts[1] = p1; parts[2] = p2; }
+    *chi2 = p0 + p1 + p2;
+    return DSC_OK;
+}
+
+extern "C" int dsc_cost(dsc_ctx* ctx, const dsc_weights* w, double* chi2, double* parts) {
+    int s = ready(ctx, w);
+    if (s) return s;
+    if (!chi2) return DSC_ERR_INVALID_ARG;
+    CK(cudaSetDevice(ctx->device));
+    if (ctx->n == 0) { *chi2 = 0.0; if (parts) parts[0] = parts[1] = parts[2] = 0.0; return DSC_OK; }
+    return eval_cost(ctx, make_weights(ctx, w), ctx->P, ctx->Gcur, chi2, parts);
+}
+
+static CgVecs make_vecs(dsc_ctx* ctx) {
+    CgVecs v;
+    v.x = ctx->vec[0]; v.r = ctx->vec[1]; v.z = ctx->vec[2]; v.w = ctx->vec[3]; v.p = ctx->vec[4]; v.s = ctx->vec[5];
+    v.xg = ctx->small; v.rg = ctx->small + 8; v.zg = ctx->small + 16; v.wg = ctx->small + 24; v.pg = ctx->small + 32; v.sg = ctx->small + 40;
+    return v;
+}
+
+static int run_linearize(dsc_ctx* ctx, const WeightsDev& W, LinGlobal* hlin) {
+    int nb = grid_groups(ctx, ctx->n);
+    linearize_kernel<<<nb, kThreads, 0, ctx->stream>>>(ctx->n, ctx->P, ctx->Q, ctx->uv, ctx->dm, ctx->isg, ctx->rowptr, ctx->col,
+                                                      ctx->wgt, ctx->Gcur, ctx->pair, W, ctx->b, ctx->D, ctx->U, ctx->part);
+    finalize_linearize_kernel<<<1, kThreads, 0, ctx->stream>>>(nb, ctx->part, ctx->lin);
+    ctx->launches += 2;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(hlin, ctx->lin, sizeof(LinGlobal), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return DSC_OK;
+}
+
+// PCG solve of (H + lambda I) dx = b; returns iterations, status DSC_OK / DSC_ERR_PCG_BREAKDOWN
+static int run_pcg(dsc_ctx* ctx, const WeightsDev& W, double lambda, int* iters_out) {
+    int n = ctx->n;
+    int nbv = grid_threads(ctx, (long long)n);
+    int nbs = grid_groups(ctx, n);
+    CgVecs v = make_vecs(ctx);
+    double* Ginv = ctx->small + 48;
+    CK(cudaMemsetAsync(ctx->errflag, 0, sizeof(int), ctx->stream));
+    precond_kernel<<<nbv, kThreads, 0, ctx->stream>>>(n, ctx->D, lambda, ctx->lin, ctx->Minv, Ginv, ctx->errflag);
+    cg_init_kernel<<<nbv, kThreads, 0, ctx->stream>>>(n, ctx->b, ctx->lin, ctx->Minv, Ginv, v, ctx->gpart[0], ctx->ctl);
+    cg_spmv_kernel<<<nbs, kThreads, 0, ctx->stream>>>(n, ctx->P, ctx->Q, ctx->U, ctx->rowptr, ctx->col, ctx->wgt, ctx->Gcur, ctx->pair, W,
+                                                     lambda, v.z, v.zg, v.w, ctx->dpart, ctx->bpart, ctx->lin, ctx->ctl);
+    ctx->launches += 3;
+    double rtol2 = ctx->pcg.rtol * ctx->pcg.rtol;
+    int k = 0;
+    CgControl hc{};
+    while (k < ctx->pcg.max_iters) {
+        int chunk = std::min(ctx->pcg.check_every, ctx->pcg.max_iters - k);
+        for (int c = 0; c < chunk; ++c, ++k) {
+            cg_update_kernel<<<nbv, kThreads, 0, ctx->stream>>>(n, k & 1, k == 0 ? 1 : 0, ctx->Minv, Ginv, ctx->lin, lambda, v,
+                                                               ctx->gpart[k & 1], ctx->gpart[(k + 1) & 1], ctx->dpart, ctx->bpart, nbs,
+                                                               ctx->ctl, rtol2);
+            cg_spmv_kernel<<<nbs, kThreads, 0, ctx->stream>>>(n, ctx->P, ctx->Q, ctx->U, ctx->rowptr, ctx->col, ctx->wgt, ctx->Gcur, ctx->pair, W,
+                                                             lambda, v.z, v.zg, v.w, ctx->dpart, ctx->bpart, ctx->lin, ctx->ctl);
+            ctx->launches += 2;
+        }
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(&hc, ctx->ctl, sizeof(CgControl), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        if (hc.converged || hc.breakdown) break;
+    }
+    if (iters_out) *iters_out = hc.iters;
+    if (hc.breakdown) return DSC_ERR_PCG_BREAKDOWN;
+    return DSC_OK;
+}
+
+static double ev_ms(cudaEvent_t a, cudaEvent_t b2) { float f = 0.f; cudaEventElapsedTime(&f, a, b2); return (double)f; }
+
+extern "C" int dsc_optimize(dsc_ctx* ctx, const dsc_weights* w, int n_iters, dsc_iter_record* records, dsc_opt_stats* stats) {
+    int s = ready(ctx, w);
+    if (s) return s;
+    if (n_iters < 0) return fail(ctx, DSC_ERR_INVALID_ARG, "n_iters");
+    CK(cudaSetDevice(ctx->device));
+    dsc_opt_stats st{};
+    long long launches0 = ctx->launches;
+    if (ctx->n == 0) { if (stats) *stats = st; return DSC_OK; }
+    WeightsDev W = make_weights(ctx, w);
+    cudaEvent_t e_begin, e_end, e_a, e_b;
+    cudaEventCreate(&e_begin); cudaEventCreate(&e_end); cudaEventCreate(&e_a); cudaEventCreate(&e_b);
+    auto cleanup = [&]() { cudaEventDestroy(e_begin); cudaEventDestroy(e_end); cudaEventDestroy(e_a); cudaEventDestroy(e_b); };
+    cudaEventRecord(e_begin, ctx->stream);
+    double lambda = 0.0, ni = 2.0;
+    double current = 0.0;
+    int rc = DSC_OK;
+    int nbv = grid_threads(ctx, ctx->n);
+    CgVecs v = make_vecs(ctx);
+    for (int it = 0; it < n_iters; ++it) {
+        LinGlobal hl;
+        cudaEventRecord(e_a, ctx->stream);
+        rc = run_linearize(ctx, W, &hl);
+        if (rc) break;
+        cudaEventRecord(e_b, ctx->stream); cudaEventSynchronize(e_b);
+        st.linearize_ms += ev_ms(e_a, e_b);
+        current = hl.chi2[0] + hl.chi2[1] + hl.chi2[2];
+        if (!std::isfinite(current)) { rc = fail(ctx, DSC_ERR_NONFINITE, "cost is not finite at linearisation"); break; }
+        if (it == 0) { lambda = 1e-5 * hl.maxdiag; ni = 2.0; }          // computeLambdaInit, tau = 1e-5
+        dsc_iter_record rec{};
+        rec.chi2_before = current; rec.lambda = lambda;
+        double rho = 0.0;
+        int q = 0;
+        bool accepted = false;
+        do {
+            int its = 0;
+            cudaEventRecord(e_a, ctx->stream);
+            int prc = run_pcg(ctx, W, lambda, &its);
+            cudaEventRecord(e_b, ctx->stream); cudaEventSynchronize(e_b);
+            st.pcg_ms += ev_ms(e_a, e_b);
+            rec.pcg_iters += its; st.total_pcg_iters += its;
+            if (prc != DSC_OK && prc != DSC_ERR_PCG_BREAKDOWN) { rc = prc; break; }
+            double temp = std::numeric_limits<double>::max(), scale = 1e-3;
+            cudaEventRecord(e_a, ctx->stream);
+            if (prc == DSC_OK) {
+                apply_update_kernel<<<nbv, kThreads, 0, ctx->stream>>>(ctx->n, ctx->P, v.x, v.xg, ctx->b, ctx->lin, lambda, ctx->Gcur,
+                                                                      ctx->Ptrial, ctx->Gtrial, ctx->gpart[0]);
+                ctx->launches++;
+                cudaMemcpyAsync(ctx->h_pinned + 3 * kMaxBlocks, ctx->gpart[0], sizeof(double) * nbv, cudaMemcpyDeviceToHost, ctx->stream);
+                double t2 = 0.0;
+                rc = eval_cost(ctx, W, ctx->Ptrial, ctx->Gtrial, &t2, nullptr);
+                if (rc) break;
+                temp = t2;
+                scale = host_sum(ctx->h_pinned + 3 * kMaxBlocks, nbv) + 1e-3;
+            }
+            cudaEventRecord(e_b, ctx->stream); cudaEventSynchronize(e_b);
+            st.trial_ms += ev_ms(e_a, e_b);
+            rho = (current - temp) / scale;
+            if (rho > 0 && std::isfinite(temp)) {
+                double alpha = 1.0 - std::pow(2.0 * rho - 1.0, 3);
+                alpha = std::min(alpha, 2.0 / 3.0);
+                lambda *= std::max(1.0 / 3.0, alpha);
+                ni = 2.0;
+                current = temp;
+                std::swap(ctx->P, ctx->Ptrial);
+                std::swap(ctx->Gcur, ctx->Gtrial);
+                accepted = true;
+            } else {
+                lambda *= ni;
+                ni *= 2.0;
+            }
+            ++q;
+        } while (rho < 0 && q < 10);
+        if (rc) break;
+        rec.trials = q; rec.accepted = accepted ? 1 : 0; rec.chi2_after = current;
+        st.total_trials += q; st.iterations = it + 1;
+        if (records) records[it] = rec;
+        if (q == 10 || rho == 0) { st.terminated = 1; break; }
+    }
+    cudaEventRecord(e_end, ctx->stream); cudaEventSynchronize(e_end);
+    st.device_ms = ev_ms(e_begin, e_end);
+    st.final_chi2 = current;
+    st.kernel_launches = (int)(ctx->launches - launches0);
+    cleanup();
+    if (stats) *stats = st;
+    return rc;
+}
+
+extern "C" int dsc_download(dsc_ctx* ctx, float* X1, float* X2, double* X1d, double* X2d,
+                            double* scales, double* Tg7, double* update) {
+    if (!ctx) return DSC_ERR_INVALID_ARG;
+    if (!ctx->have_problem) return fail(ctx, DSC_ERR_STATE, "no problem uploaded");
+    CK(cudaSetDevice(ctx->device));
+    int n = ctx->n;
+    Globals g;
+    CK(cudaMemcpyAsync(&g, ctx->Gcur, sizeof(Globals), cudaMemcpyDeviceToHost, ctx->stream));
+    double upd = 0.0;
+    if (n > 0) {
+        int nb = grid_threads(ctx, n);
+        double *dX1 = nullptr, *dX2 = nullptr;
+        if (X1d) CK(cudaMalloc(&dX1, sizeof(double) * 3 * n));
+        if (X2d) CK(cudaMalloc(&dX2, sizeof(double) * 3 * n));
+        export_kernel<<<nb, kThreads, 0, ctx->stream>>>(n, ctx->P, ctx->P0, ctx->perm.empty() ? nullptr : ctx->d_perm,
+                                                       ctx->X1f, ctx->X2f, dX1, dX2, ctx->part);
+        ctx->launches++;
+        CK(cudaGetLastError());
+        if (X1) CK(cudaMemcpyAsync(X1, ctx->X1f, sizeof(float) * 3 * n, cudaMemcpyDeviceToHost, ctx->stream));
+        if (X2) CK(cudaMemcpyAsync(X2, ctx->X2f, sizeof(float) * 3 * n, cudaMemcpyDeviceToHost, ctx->stream));
+        if (X1d) CK(cudaMemcpyAsync(X1d, dX1, sizeof(double) * 3 * n, cudaMemcpyDeviceToHost, ctx->stream));
+        if (X2d) CK(cudaMemcpyAsync(X2d, dX2, sizeof(double) * 3 * n, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->h_pinned, ctx->part, sizeof(double) * nb, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        if (dX1) cudaFree(dX1);
+        if (dX2) cudaFree(dX2);
+        upd = host_sum(ctx->h_pinned, nb);
+    } else CK(cudaStreamSynchronize(ctx->stream));
+    if (scales) { scales[0] = g.s1; scales[1] = g.s2; }
+    if (Tg7) for (int k = 0; k < 7; ++k) Tg7[k] = g.Tg[k];
+    if (update) *update = upd;
+    return DSC_OK;
+}
+
+extern "C" int dsc_pixel_sigma(dsc_ctx* ctx, double* sigma) {
+    if (!ctx || !sigma) return DSC_ERR_INVALID_ARG;
+    if (!ctx->have_problem) return fail(ctx, DSC_ERR_STATE, "no problem uploaded");
+    CK(cudaSetDevice(ctx->device));
+    int n = ctx->n;
+    if (n == 0) { sigma[0] = sigma[1] = std::numeric_limits<double>::quiet_NaN(); return DSC_OK; }
+    int nb = grid_threads(ctx, n);
+    pixel_sigma_kernel<<<nb, kThreads, 0, ctx->stream>>>(n, ctx->P, ctx->uv, ctx->pair, ctx->part);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(ctx->h_pinned, ctx->part, sizeof(double) * 4 * nb, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    double s[4];
+    for (int k = 0; k < 4; ++k) s[k] = host_sum(ctx->h_pinned, nb, 4, k);
+    sigma[0] = 0.5 * (std::sqrt(s[0] / n) + std::sqrt(s[1] / n));
+    sigma[1] = 0.5 * (std::sqrt(s[2] / n) + std::sqrt(s[3] / n));
+    return DSC_OK;
+}
+
+// ------------------------------------------------------------------ test hooks
+extern "C" int dsc_debug_linearize(dsc_ctx* ctx, const dsc_weights* w, double* b, double* hdiag, double* chi2) {
+    int s = ready(ctx, w);
+    if (s) return s;
+    CK(cudaSetDevice(ctx->device));
+    int n = ctx->n;
+    WeightsDev W = make_weights(ctx, w);
+    LinGlobal hl;
+    s = run_linearize(ctx, W, &hl);
+    if (s) return s;
+    std::vector<double> hb(6 * (size_t)n), hD(21 * (size_t)n);
+    if (n) {
+        CK(cudaMemcpyAsync(hb.data(), ctx->b, sizeof(double) * 6 * n, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(hD.data(), ctx->D, sizeof(double) * 21 * n, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (chi2) *chi2 = hl.chi2[0] + hl.chi2[1] + hl.chi2[2];
+    for (int k = 0; k < 8; ++k) { if (b) b[k] = hl.bg[k]; if (hdiag) hdiag[k] = hl.C[k * 8 + k]; }
+    for (int i = 0; i < n; ++i) {
+        size_t d = ctx->perm.empty() ? (size_t)i : (size_t)ctx->perm[i];
+        for (int k = 0; k < 6; ++k) {
+            if (b) b[8 + 6 * d + k] = hb[6 * (size_t)i + k];
+            if (hdiag) hdiag[8 + 6 * d + k] = hD[21 * (size_t)i + pk<6>(k, k)];
+        }
+    }
+    return DSC_OK;
+}
+
+extern "C" int dsc_debug_matvec(dsc_ctx* ctx, const dsc_weights* w, double lambda, const double* x, double* y) {
+    int s = ready(ctx, w);
+    if (s) return s;
+    if (!x || !y) return DSC_ERR_INVALID_ARG;
+    CK(cudaSetDevice(ctx->device));
+    int n = ctx->n;
+    WeightsDev W = make_weights(ctx, w);
+    LinGlobal hl;
+    s = run_linearize(ctx, W, &hl);
+    if (s) return s;
+    CgVecs v = make_vecs(ctx);
+    std::vector<double> hz(6 * (size_t)n);
+    for (int i = 0; i < n; ++i) {
+        size_t sidx = ctx->perm.empty() ? (size_t)i : (size_t)ctx->perm[i];
+        for (int k = 0; k < 6; ++k) hz[6 * (size_t)i + k] = x[8 + 6 * sidx + k];
+    }
+    if (n) CK(cudaMemcpyAsync(v.z, hz.data(), sizeof(double) * 6 * n, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(v.zg, x, sizeof(double) * 8, cudaMemcpyHostToDevice, ctx->stream));
+    int nbs = grid_groups(ctx, n);
+    cg_spmv_kernel<<<nbs, kThreads, 0, ctx->stream>>>(n, ctx->P, ctx->Q, ctx->U, ctx->rowptr, ctx->col, ctx->wgt, ctx->Gcur, ctx->pair, W,
+                                                     lambda, v.z, v.zg, v.w, ctx->dpart, ctx->bpart, ctx->lin, nullptr);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    std::vector<double> hw(6 * (size_t)n), hbp(8 * (size_t)nbs);
+    if (n) CK(cudaMemcpyAsync(hw.data(), v.w, sizeof(double) * 6 * n, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(hbp.data(), ctx->bpart, sizeof(double) * 8 * nbs, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (int k = 0; k < 8; ++k) {
+        double sum = 0.0;
+        for (int bk = 0; bk < nbs; ++bk) sum += hbp[8 * (size_t)bk + k];
+        y[k] = sum + ((k >= 6 ? hl.C[k * 8 + k] : 0.0) + lambda) * x[k];
+    }
+    for (int i = 0; i < n; ++i) {
+        size_t d = ctx->perm.empty() ? (size_t)i : (size_t)ctx->perm[i];
+        for (int k = 0; k < 6; ++k) y[8 + 6 * d + k] = hw[6 * (size_t)i + k];
+    }
+    return DSC_OK;
+}

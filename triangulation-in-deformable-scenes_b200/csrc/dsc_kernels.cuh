@@ -1,0 +1,987 @@
+// dsc_kernels.cuh -- hand-written sm_100a kernels of the deformable two-view hot path.
+//
+// Layout in HBM (n correspondences in the library's internal, space-filling-curve order; E directed
+// neighbour edges in CSR):
+//   P      double[n][8]  {X1.xyz, 0, X2.xyz, 0}      64 B records: one neighbour gather = 2 aligned sectors
+//   Q      double[n][4]  per-vertex ARAP rotation as unit quaternion (computeR)   32 B = 1 sector
+//   uv     float4[n]     {u1, v1, u2, v2}
+//   dm     double2[n]    depth measurements (KF1, KF2)
+//   isg    float2[n]     KeyFrame::getInvSigma2(octave) of the two observations
+//   U      double[n][16] unary Hessian record {U1[6], U2[6], kd1, kd2, 0, 0}      128 B = 1 line
+//   D      double[n][21] packed upper 6x6 diagonal block of H (block-Jacobi preconditioner source)
+//   Minv   double[n][21] packed inverse of D + lambda I
+//   vectors b, x, r, z, w, p, s: double[n][6] {d/dX1, d/dX2}; the 8 global unknowns
+//   (T_g omega/upsilon, s1, s2) live in separate 8-vectors.
+//
+// Work decomposition of the gather kernels: 8 lanes per correspondence (4 correspondences per warp);
+// lane l walks the directed edges rowptr[i]+l, +8, ... of vertex i, and the per-vertex sums are
+// combined with warp-shuffle segmented reductions -- no global atomics anywhere.  The neighbour graph
+// is symmetric and the reference adds one EdgeARAP per *directed* pair with identical residual
+// (g2oBundleAdjustment.cc:883-953), so vertex i's row of J^T W J is 2x the sum over its own CSR row.
+// Grid = persistent blocks (multiple of the SM count) with a grid-stride loop; every reduction is
+// two-stage and deterministic (per-block partials, summed in a fixed order by the consumer).
+#pragma once
+#include "dsc_math.cuh"
+
+namespace dsc {
+
+constexpr int kThreads = 256;
+constexpr int kLanes = 8;                       // lanes per correspondence
+constexpr int kGroups = kThreads / kLanes;      // correspondences per block-iteration
+constexpr int kMaxBlocks = 2048;
+
+struct PairDev {
+    CamF cam1, cam2;
+    PoseF T1f, T2f;
+    double R1[9], t1[3], R2[9], t2[3];          // g2o::SE3Quat(unit_quaternion().cast<double>(), ...)
+};
+
+struct WeightsDev {
+    double rep;          // repBalanceWeight
+    double arap_info;    // arapBalanceWeight * n_triangles^2   (g2oBundleAdjustment.cc:946)
+    double depth_info;   // 1 / DepthError^2                    (:822-825)
+    double inv_area;     // 1 / mesh area                       (:942-943, g2oTypes.h:333-334)
+    double huber;        // deltaMono = (float)sqrt(100.991)    (:631)
+};
+
+struct Globals {         // the 8 global unknowns + derived rotation
+    double Tg[7];        // qx qy qz qw tx ty tz
+    double s1, s2;
+    double Rg[9];
+};
+
+struct LinGlobal {       // reduced by finalize_linearize
+    double chi2[3];      // reprojection (robust), depth, ARAP
+    double maxdiag;
+    double bg[8];        // gradient of the global unknowns (b = -J^T W e)
+    double C[64];        // 8x8 global block of H
+};
+
+struct CgScalars { double gamma_prev, alpha_prev; };
+struct CgControl {
+    CgScalars sc[2];
+    double gamma0;
+    int iters;
+    int converged;
+    int breakdown;
+};
+
+// ------------------------------------------------------------------ helpers
+DSC_D D3 qrot(const double* q, D3 v) {              // Eigen::Quaternion::_transformVector
+    D3 qv = d3(q[0], q[1], q[2]);
+    D3 t = 2.0 * cross(qv, v);
+    return v + q[3] * t + cross(qv, t);
+}
+DSC_D D3 qrotT(const double* q, D3 v) {
+    D3 qv = d3(-q[0], -q[1], -q[2]);
+    D3 t = 2.0 * cross(qv, v);
+    return v + q[3] * t + cross(qv, t);
+}
+DSC_D double group_sum(double v) {                  // sum over the 8 lanes of a correspondence
+    v += __shfl_xor_sync(0xffffffffu, v, 4);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    return v;
+}
+DSC_D double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+// deterministic block reduction of K values held per thread; result valid in thread 0
+template <int K>
+DSC_D void block_reduce(double (&v)[K], double* smem /* [K][kThreads/32] */) {
+    int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        double s = warp_sum(v[k]);
+        if (lane == 0) smem[k * (kThreads / 32) + warp] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            double s = 0.0;
+            for (int w = 0; w < kThreads / 32; ++w) s += smem[k * (kThreads / 32) + w];
+            v[k] = s;
+        }
+    }
+    __syncthreads();
+}
+// every thread of the block gets the fixed-order sum of part[0..nb) (stride `stride`)
+DSC_D double sum_partials(const double* part, int nb, int stride, double* smem32) {
+    double s = 0.0;
+    for (int i = threadIdx.x; i < nb; i += blockDim.x) s += part[(size_t)i * stride];
+    s = warp_sum(s);
+    int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) smem32[warp] = s;
+    __syncthreads();
+    double t = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += smem32[w];
+    return t;
+}
+
+// 256-bit read-only global load (sm_100: ld.global.nc.v4.f64 -> one LDG.E.256; p must be 32-byte aligned)
+DSC_D double4 ldg256(const double4* p) {
+    double4 r;
+    asm("ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w) : "l"(p));
+    return r;
+}
+struct P8 { D3 a, b; };                             // X1, X2 of one correspondence
+DSC_D P8 load_P(const double* __restrict__ P, int i) {
+    const double4* p = reinterpret_cast<const double4*>(P) + 2 * (size_t)i;
+    double4 u = ldg256(p), v = ldg256(p + 1);
+    P8 r; r.a = d3(u.x, u.y, u.z); r.b = d3(v.x, v.y, v.z);
+    return r;
+}
+DSC_D void load6(const double* __restrict__ V, int i, D3& a, D3& b) {
+    const double2* p = reinterpret_cast<const double2*>(V) + 3 * (size_t)i;
+    double2 u = p[0], v = p[1], w = p[2];
+    a = d3(u.x, u.y, v.x); b = d3(v.y, w.x, w.y);
+}
+DSC_D void store6(double* __restrict__ V, int i, D3 a, D3 b) {
+    double2* p = reinterpret_cast<double2*>(V) + 3 * (size_t)i;
+    p[0] = make_double2(a.x, a.y); p[1] = make_double2(a.z, b.x); p[2] = make_double2(b.y, b.z);
+}
+DSC_D void load_q(const double* __restrict__ Q, int i, double* q) {
+    const double4* p = reinterpret_cast<const double4*>(Q) + (size_t)i;
+    double4 u = ldg256(p);
+    q[0] = u.x; q[1] = u.y; q[2] = u.z; q[3] = u.w;
+}
+
+// One directed ARAP edge (i -> j).  EdgeARAP::computeError, g2oTypes.h:310-339:
+//   e = w (|(d2 - Ri d1)/A|^2 + |(-d2 + Rj d1)/A|^2) + |Rg (X2i + X2j) - 2 t - (X1i + X1j)|^2
+// and its analytic gradient (the reference differentiates numerically, g2o central differences).
+struct ArapGrad { D3 gi1, gi2, gj1, gj2, gw, gv; double e; };
+template <bool kGrad>
+DSC_D void arap_edge(const P8& Pi, const P8& Pj, const double* qi, const double* qj, double w, double inv_area,
+                     const Globals& G, ArapGrad& o) {
+    D3 d1 = Pi.a - Pj.a, d2 = Pi.b - Pj.b;
+    D3 a = inv_area * (d2 - qrot(qi, d1));
+    D3 b = inv_area * (d2 - qrot(qj, d1));
+    D3 S2 = Pi.b + Pj.b, S1 = Pi.a + Pj.a;
+    D3 tg = d3(G.Tg[4], G.Tg[5], G.Tg[6]);
+    D3 qt = mul(G.Rg, S2) - 2.0 * tg;
+    D3 g = qt - S1;
+    o.e = w * (dot(a, a) + dot(b, b)) + dot(g, g);
+    if (kGrad) {
+        double c2 = 2.0 * w * inv_area;
+        D3 u = c2 * (a + b);
+        D3 m = c2 * (qrotT(qi, a) + qrotT(qj, b));
+        D3 v2 = 2.0 * mulT(G.Rg, g);
+        D3 g2 = 2.0 * g;
+        o.gi1 = d3(-m.x - g2.x, -m.y - g2.y, -m.z - g2.z);
+        o.gi2 = u + v2;
+        o.gj1 = m - g2;
+        o.gj2 = v2 - u;
+        o.gw = 2.0 * cross(qt, g);
+        o.gv = d3(-4.0 * g.x, -4.0 * g.y, -4.0 * g.z);
+    }
+}
+
+// Reprojection edge EdgeSE3ProjectXYZPerKeyFrameOnlyPoints (g2oTypes.h:277-291, g2oTypes.cc:270-283):
+// e = obs - (double)project((float)(R X + t)),  J = -(double)projectJac((float)Xc) R.
+DSC_D void reproj_residual(const CamF& cam, const double* R, const double* t, D3 X, float u, float v,
+                           double& e0, double& e1, F3& Xcf) {
+    D3 Xc = mul(R, X);
+    Xc = d3(Xc.x + t[0], Xc.y + t[1], Xc.z + t[2]);
+    Xcf = mk3((float)Xc.x, (float)Xc.y, (float)Xc.z);
+    float pu, pv;
+    cam_project(cam, Xcf, pu, pv);
+    e0 = (double)u - (double)pu;
+    e1 = (double)v - (double)pv;
+}
+DSC_D void huber(double chi2, double delta, double& rho0, double& rho1) {   // g2o::RobustKernelHuber
+    double d2 = delta * delta;
+    if (chi2 <= d2) { rho0 = chi2; rho1 = 1.0; }
+    else { double s = sqrt(chi2); rho0 = 2.0 * s * delta - d2; rho1 = delta / s; }
+}
+
+// ================================================================== K1: triangulation
+struct TriParams { int method, location, gate; float min_cos, depth_limit; int check_reproj; };
+
+DSC_D void tri_nrslam(F3 xn1, F3 xn2, const PoseF& T21, int loc, F3& p1, F3& p2) {   // Geometry.cc:103-153
+    F3 f0 = normalize3(xn1), f1 = normalize3(xn2);
+    F3 t = mk3(T21.t[0], T21.t[1], T21.t[2]);
+    F3 Rf0 = rot(T21.R, f0);
+    F3 p = cross3(Rf0, f1), q = cross3(Rf0, t), r = cross3(f1, t);
+    float np_ = norm3(p), nq = norm3(q), nr = norm3(r);
+    float l0 = fdv(nr, np_), l1 = fdv(nq, np_);
+    F3 point0 = scale3(l0, Rf0), point1 = scale3(l1, f1);
+    F3 x1 = scale3(fdv(nq, fa(nq, nr)), add3(t, scale3(l0, add3(Rf0, f1))));
+    if (loc == 1) { p1 = x1; p2 = x1; }
+    else if (loc == 2) {
+        point0 = add3(t, point0);
+        p1 = add3(point0, sub3(point0, x1));
+        p2 = add3(point1, sub3(point1, x1));
+    } else { p1 = add3(t, point0); p2 = point1; }
+}
+DSC_D void tri_classic(F3 xn1, F3 xn2, const PoseF& T21, int loc, F3& p1, F3& p2) {  // Geometry.cc:62-101
+    F3 m0 = rot(T21.R, xn1), m1 = xn2;
+    F3 tt = mk3(T21.t[0], T21.t[1], T21.t[2]);
+    F3 t = normalize3(tt), M0 = normalize3(m0), M1 = normalize3(m1);
+    F3 a0 = sub3(M0, scale3(dot3(M0, t), t)), a1 = sub3(M1, scale3(dot3(M1, t), t));
+    // V.col(1) of the 2x3 SVD: right singular vector of the smaller singular value (double, rounded)
+    double g00 = (double)a0.x * a0.x + (double)a0.y * a0.y + (double)a0.z * a0.z;
+    double g11 = (double)a1.x * a1.x + (double)a1.y * a1.y + (double)a1.z * a1.z;
+    double g01 = (double)a0.x * a1.x + (double)a0.y * a1.y + (double)a0.z * a1.z;
+    double th = 0.5 * atan2(2.0 * g01, g00 - g11);
+    double ux = -sin(th), uy = cos(th);
+    double nx = ux * a0.x + uy * a1.x, ny = ux * a0.y + uy * a1.y, nz = ux * a0.z + uy * a1.z;
+    double nn = sqrt(nx * nx + ny * ny + nz * nz);
+    F3 n = mk3((float)(nx / nn), (float)(ny / nn), (float)(nz / nn));
+    F3 m0_ = sub3(m0, scale3(dot3(m0, n), n)), m1_ = sub3(m1, scale3(dot3(m1, n), n));
+    F3 z = cross3(m1_, m0_);
+    float zz = dot3(z, z);
+    float l0 = fdv(dot3(z, cross3(tt, m1_)), zz), l1 = fdv(dot3(z, cross3(tt, m0_)), zz);
+    if (loc == 1) { p1 = add3(tt, scale3(l0, m0_)); p2 = p1; }
+    else { p1 = add3(tt, scale3(l0, m0)); p2 = scale3(l1, m1); }
+}
+DSC_D void tri_dlt(F3 xn1, F3 xn2, const PoseF& T1, const PoseF& T2, F3& X) {         // Geometry.cc:155-186 (intended)
+    double A[4][4], V[4][4], sig[4];
+    for (int k = 0; k < 4; ++k) {
+        float r10 = k < 3 ? T1.R[0 + k] : T1.t[0], r11 = k < 3 ? T1.R[3 + k] : T1.t[1], r12 = k < 3 ? T1.R[6 + k] : T1.t[2];
+        float r20 = k < 3 ? T2.R[0 + k] : T2.t[0], r21 = k < 3 ? T2.R[3 + k] : T2.t[1], r22 = k < 3 ? T2.R[6 + k] : T2.t[2];
+        A[0][k] = (double)fs(fm(xn1.x, r12), r10);
+        A[1][k] = (double)fs(fm(xn1.y, r12), r11);
+        A[2][k] = (double)fs(fm(xn2.x, r22), r20);
+        A[3][k] = (double)fs(fm(xn2.y, r22), r21);
+    }
+    jacobi_svd<4>(A, V, sig);
+    float x0 = (float)V[0][3], x1 = (float)V[1][3], x2 = (float)V[2][3], x3 = (float)V[3][3];
+    if (x3 != 0.f) X = mk3(fdv(x0, x3), fdv(x1, x3), fdv(x2, x3)); else X = mk3(0.f, 0.f, 0.f);
+}
+
+__global__ void __launch_bounds__(kThreads)
+triangulate_kernel(int n, const float2* __restrict__ uv1, const float2* __restrict__ uv2,
+                   const float* __restrict__ dep1, const float* __restrict__ dep2,
+                   const __grid_constant__ PairDev pr, const __grid_constant__ TriParams tp,
+                   float* __restrict__ X1, float* __restrict__ X2, uint8_t* __restrict__ valid,
+                   float* __restrict__ cosp) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        float2 a = uv1[i], b = uv2[i];
+        F3 ray1 = cam_unproject(pr.cam1, a.x, a.y), ray2 = cam_unproject(pr.cam2, b.x, b.y);
+        F3 xn1 = normalize3(ray1), xn2 = normalize3(ray2);
+        PoseF T21 = compose(pr.T2f, inverse(pr.T1f));
+        PoseF Tw2 = inverse(pr.T2f);
+        F3 w1, w2;
+        if (tp.method == 2) {
+            F3 X; tri_dlt(xn1, xn2, pr.T1f, pr.T2f, X);
+            w1 = X; w2 = X;
+        } else {
+            F3 p1, p2;
+            if (tp.method == 3) {                        // Geometry.cc:189-214
+                float s1 = fdv(dep1[i], ray1.z), s2 = fdv(dep2[i], ray2.z);
+                F3 c1 = mk3(fm(ray1.x, s1), fm(ray1.y, s1), fm(ray1.z, s1));
+                F3 c2 = mk3(fm(ray2.x, s2), fm(ray2.y, s2), fm(ray2.z, s2));
+                F3 point0 = apply(T21, c1), point1 = c2;
+                F3 xm = div3(add3(point0, point1), 2.0f);
+                if (tp.location == 1) { p1 = xm; p2 = xm; }
+                else if (tp.location == 2) { p1 = add3(point0, sub3(point0, xm)); p2 = add3(point1, sub3(point1, xm)); }
+                else { p1 = point0; p2 = point1; }
+            } else if (tp.method == 0) tri_classic(xn1, xn2, T21, tp.location, p1, p2);
+            else tri_nrslam(xn1, xn2, T21, tp.location, p1, p2);
+            w1 = apply(Tw2, p1); w2 = apply(Tw2, p2);
+        }
+        F3 c1 = apply(pr.T1f, w1), c2 = apply(pr.T2f, w2);
+        F3 r1 = normalize3(rotT(pr.T1f.R, xn1)), r2 = normalize3(rotT(pr.T2f.R, xn2));
+        float cp = fdv(dot3(r1, r2), fm(norm3(r1), norm3(r2)));
+        bool ok = true;
+        if (tp.gate == 1) {                              // Mapping::isValidParallax, Mapping.cc:351-364
+            if (c1.z < 0.f || c2.z < 0.f) ok = false;
+            if (!(cp <= tp.min_cos)) ok = false;
+        } else if (tp.gate == 2) {                       // MonocularMapInitializer.cc:315-360
+            bool fin = isfinite(w1.x) && isfinite(w1.y) && isfinite(w1.z) && isfinite(w2.x) && isfinite(w2.y) && isfinite(w2.z);
+            bool z1 = (w1.x == 0.f && w1.y == 0.f && w1.z == 0.f), z2 = (w2.x == 0.f && w2.y == 0.f && w2.z == 0.f);
+            if (!fin || z1 || z2) ok = false;
+            if (c1.z < 0.f || c1.z > tp.depth_limit) ok = false;
+            if (c2.z < 0.f || c2.z > tp.depth_limit) ok = false;
+            if (tp.check_reproj) {
+                float pu, pv;
+                cam_project(pr.cam1, c1, pu, pv);
+                float ex = fs(a.x, pu), ey = fs(a.y, pv);
+                if ((double)fa(fm(ex, ex), fm(ey, ey)) > 5.991) ok = false;
+                cam_project(pr.cam2, c2, pu, pv);
+                ex = fs(b.x, pu); ey = fs(b.y, pv);
+                if ((double)fa(fm(ex, ex), fm(ey, ey)) > 5.991) ok = false;
+            }
+        }
+        X1[3 * (size_t)i + 0] = w1.x; X1[3 * (size_t)i + 1] = w1.y; X1[3 * (size_t)i + 2] = w1.z;
+        X2[3 * (size_t)i + 0] = w2.x; X2[3 * (size_t)i + 1] = w2.y; X2[3 * (size_t)i + 2] = w2.z;
+        valid[i] = ok ? 1 : 0;
+        cosp[i] = cp;
+    }
+}
+
+// KeyFrame::setInitialDepthScaleInSimulationImages (KeyFrame.cc:131-153): sum of d / z_c, count
+__global__ void __launch_bounds__(kThreads)
+depth_scale_kernel(int n, const float* __restrict__ X, const float* __restrict__ dep, const uint8_t* __restrict__ valid,
+                   const __grid_constant__ PoseF T, double* __restrict__ part /* [grid][2] */) {
+    __shared__ double sm[2 * (kThreads / 32)];
+    double v[2] = {0.0, 0.0};
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        float d = dep[i];
+        if (!valid[i] || d == 0.f) continue;
+        F3 c = apply(T, mk3(X[3 * (size_t)i], X[3 * (size_t)i + 1], X[3 * (size_t)i + 2]));
+        v[0] += (double)fdv(d, c.z);
+        v[1] += 1.0;
+    }
+    block_reduce<2>(v, sm);
+    if (threadIdx.x == 0) { part[2 * blockIdx.x] = v[0]; part[2 * blockIdx.x + 1] = v[1]; }
+}
+
+// ================================================================== state set-up
+__global__ void __launch_bounds__(kThreads)
+init_state_kernel(int n, const float* __restrict__ X1, const float* __restrict__ X2, const int* __restrict__ perm,
+                  double* __restrict__ P) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        size_t s = perm ? (size_t)perm[i] : (size_t)i;
+        double4* p = reinterpret_cast<double4*>(P) + 2 * (size_t)i;
+        p[0] = make_double4((double)X1[3 * s], (double)X1[3 * s + 1], (double)X1[3 * s + 2], 0.0);
+        p[1] = make_double4((double)X2[3 * s], (double)X2[3 * s + 1], (double)X2[3 * s + 2], 0.0);
+    }
+}
+
+// computeR (Geometry.cc:549-604): S_i = sum_j w_ij (p1i - p1j)(p2i - p2j)^T -> R_i = V U^T (det fix) -> quaternion
+__global__ void __launch_bounds__(kThreads)
+rotations_kernel(int n, const double* __restrict__ P, const int* __restrict__ rowptr, const int* __restrict__ col,
+                 const double* __restrict__ wgt, double* __restrict__ Q) {
+    int lane = threadIdx.x & (kLanes - 1);
+    int nround = (n + kGroups - 1) / kGroups;
+    for (int rd = blockIdx.x; rd < nround; rd += gridDim.x) {
+        int i = rd * kGroups + threadIdx.x / kLanes;
+        bool act = i < n;
+        double S[9];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) S[k] = 0.0;
+        int e0 = 0, e1 = 0;
+        if (act) {
+            e0 = rowptr[i]; e1 = rowptr[i + 1];
+            P8 Pi = load_P(P, i);
+            for (int e = e0 + lane; e < e1; e += kLanes) {
+                int j = col[e];
+                double w = wgt[e];
+                P8 Pj = load_P(P, j);
+                D3 d1 = Pi.a - Pj.a, d2 = Pi.b - Pj.b;
+                S[0] += w * d1.x * d2.x; S[1] += w * d1.x * d2.y; S[2] += w * d1.x * d2.z;
+                S[3] += w * d1.y * d2.x; S[4] += w * d1.y * d2.y; S[5] += w * d1.y * d2.z;
+                S[6] += w * d1.z * d2.x; S[7] += w * d1.z * d2.y; S[8] += w * d1.z * d2.z;
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 9; ++k) S[k] = group_sum(S[k]);
+        if (act && lane == 0) {
+            double q[4] = {0.0, 0.0, 0.0, 1.0};
+            if (e1 > e0) {
+                double R[9];
+                rotation_from_covariance(S, R);
+                rot_to_quat(R, q);
+            }
+            reinterpret_cast<double4*>(Q)[i] = make_double4(q[0], q[1], q[2], q[3]);
+        }
+    }
+}
+
+// ================================================================== K6: cost
+// activeRobustChi2 = sum_reproj Huber(w e.e) + sum_depth W_d e^2 + sum_arap W_a e^2.
+// part: [grid][3]
+__global__ void __launch_bounds__(kThreads)
+cost_kernel(int n, const double* __restrict__ P, const double* __restrict__ Q, const float4* __restrict__ uv,
+            const double2* __restrict__ dm, const float2* __restrict__ isg, const int* __restrict__ rowptr,
+            const int* __restrict__ col, const double* __restrict__ wgt, const Globals* __restrict__ Gp,
+            const __grid_constant__ PairDev pr, const __grid_constant__ WeightsDev W, double* __restrict__ part) {
+    __shared__ double sm[3 * (kThreads / 32)];
+    __shared__ Globals G;
+    if (threadIdx.x == 0) G = *Gp;
+    __syncthreads();
+    int lane = threadIdx.x & (kLanes - 1);
+    double acc[3] = {0.0, 0.0, 0.0};
+    int nround = (n + kGroups - 1) / kGroups;
+    for (int rd = blockIdx.x; rd < nround; rd += gridDim.x) {
+        int i = rd * kGroups + threadIdx.x / kLanes;
+        if (i >= n) continue;
+        P8 Pi = load_P(P, i);
+        double qi[4];
+        load_q(Q, i, qi);
+        int e1 = rowptr[i + 1];
+        double ea = 0.0;
+        for (int e = rowptr[i] + lane; e < e1; e += kLanes) {
+            int j = col[e];
+            P8 Pj = load_P(P, j);
+            double qj[4];
+            load_q(Q, j, qj);
+            ArapGrad g;
+            arap_edge<false>(Pi, Pj, qi, qj, wgt[e], W.inv_area, G, g);
+            ea += g.e * g.e;
+        }
+        acc[2] += W.arap_info * ea;
+        if (lane < 2) {                                  // lane 0: KF1 observation, lane 1: KF2 observation
+            float4 o = uv[i];
+            float2 sg = isg[i];
+            double2 d = dm[i];
+            double e0, e1r, r0, r1;
+            F3 xcf;
+            if (lane == 0) {
+                reproj_residual(pr.cam1, pr.R1, pr.t1, Pi.a, o.x, o.y, e0, e1r, xcf);
+                huber((double)sg.x * W.rep * (e0 * e0 + e1r * e1r), W.huber, r0, r1);
+                D3 xc = mul(pr.R1, Pi.a);
+                double rr = d.x / G.s1 - (xc.z + pr.t1[2]);
+                double ed = rr * rr * (G.s1 <= 0.0 ? 500.0 : 1.0);
+                acc[0] += r0; acc[1] += W.depth_info * ed * ed;
+            } else {
+                reproj_residual(pr.cam2, pr.R2, pr.t2, Pi.b, o.z, o.w, e0, e1r, xcf);
+                huber((double)sg.y * W.rep * (e0 * e0 + e1r * e1r), W.huber, r0, r1);
+                D3 xc = mul(pr.R2, Pi.b);
+                double rr = d.y / G.s2 - (xc.z + pr.t2[2]);
+                double ed = rr * rr * (G.s2 <= 0.0 ? 500.0 : 1.0);
+                acc[0] += r0; acc[1] += W.depth_info * ed * ed;
+            }
+        }
+    }
+    block_reduce<3>(acc, sm);
+    if (threadIdx.x == 0) { part[3 * blockIdx.x] = acc[0]; part[3 * blockIdx.x + 1] = acc[1]; part[3 * blockIdx.x + 2] = acc[2]; }
+}
+
+// ================================================================== K2 + K3: linearise and assemble
+// Per correspondence: gradient b (6), packed 6x6 diagonal block D (21), unary record U (16).
+// Per block: partial sums of chi2[3], max diagonal, global gradient bg[8], global block C (T-T 21 packed, s1, s2).
+constexpr int kLinPart = 3 + 1 + 8 + 21 + 2;   // 35
+__global__ void __launch_bounds__(kThreads)
+linearize_kernel(int n, const double* __restrict__ P, const double* __restrict__ Q, const float4* __restrict__ uv,
+                 const double2* __restrict__ dm, const float2* __restrict__ isg, const int* __restrict__ rowptr,
+                 const int* __restrict__ col, const double* __restrict__ wgt, const Globals* __restrict__ Gp,
+                 const __grid_constant__ PairDev pr, const __grid_constant__ WeightsDev W,
+                 double* __restrict__ b, double* __restrict__ D, double* __restrict__ U, double* __restrict__ part) {
+    __shared__ double sm[kLinPart * (kThreads / 32)];
+    __shared__ Globals G;
+    if (threadIdx.x == 0) G = *Gp;
+    __syncthreads();
+    int lane = threadIdx.x & (kLanes - 1);
+    double acc[kLinPart];
+#pragma unroll
+    for (int k = 0; k < kLinPart; ++k) acc[k] = 0.0;
+    double maxdiag = 0.0;
+    int nround = (n + kGroups - 1) / kGroups;
+    for (int rd = blockIdx.x; rd < nround; rd += gridDim.x) {
+        int i = rd * kGroups + threadIdx.x / kLanes;
+        bool act = i < n;
+        double gb[6], Dk[21];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) gb[k] = 0.0;
+#pragma unroll
+        for (int k = 0; k < 21; ++k) Dk[k] = 0.0;
+        P8 Pi;
+        if (act) {
+            Pi = load_P(P, i);
+            double qi[4];
+            load_q(Q, i, qi);
+            int e1 = rowptr[i + 1];
+            for (int e = rowptr[i] + lane; e < e1; e += kLanes) {
+                int j = col[e];
+                P8 Pj = load_P(P, j);
+                double qj[4];
+                load_q(Q, j, qj);
+                ArapGrad g;
+                arap_edge<true>(Pi, Pj, qi, qj, wgt[e], W.inv_area, G, g);
+                double gi[6] = {g.gi1.x, g.gi1.y, g.gi1.z, g.gi2.x, g.gi2.y, g.gi2.z};
+                double gt[6] = {g.gw.x, g.gw.y, g.gw.z, g.gv.x, g.gv.y, g.gv.z};
+                double we = W.arap_info * g.e;
+                acc[2] += we * g.e;
+                // vertex rows: the directed twin (j -> i) has the same residual and gradient => factor 2
+#pragma unroll
+                for (int r = 0; r < 6; ++r) {
+                    gb[r] -= 2.0 * we * gi[r];
+                    double s = 2.0 * W.arap_info * gi[r];
+#pragma unroll
+                    for (int c = r; c < 6; ++c) Dk[pk<6>(r, c)] += s * gi[c];
+                }
+                // global rows: every directed edge once
+#pragma unroll
+                for (int r = 0; r < 6; ++r) {
+                    acc[4 + r] -= we * gt[r];
+                    double s = W.arap_info * gt[r];
+#pragma unroll
+                    for (int c = r; c < 6; ++c) acc[12 + pk<6>(r, c)] += s * gt[c];
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 6; ++k) gb[k] = group_sum(gb[k]);
+#pragma unroll
+        for (int k = 0; k < 21; ++k) Dk[k] = group_sum(Dk[k]);
+        if (act && lane == 0) {
+            float4 o = uv[i];
+            float2 sg = isg[i];
+            double2 d = dm[i];
+            double Urec[16];
+#pragma unroll
+            for (int k = 0; k < 16; ++k) Urec[k] = 0.0;
+#pragma unroll
+            for (int cam = 0; cam < 2; ++cam) {
+                const CamF& cm = cam == 0 ? pr.cam1 : pr.cam2;
+                const double* R = cam == 0 ? pr.R1 : pr.R2;
+                const double* t = cam == 0 ? pr.t1 : pr.t2;
+                D3 X = cam == 0 ? Pi.a : Pi.b;
+                double e0, e1r, rho0, rho1;
+                F3 xcf;
+                reproj_residual(cm, R, t, X, cam == 0 ? o.x : o.z, cam == 0 ? o.y : o.w, e0, e1r, xcf);
+                double om = (double)(cam == 0 ? sg.x : sg.y) * W.rep;
+                huber(om * (e0 * e0 + e1r * e1r), W.huber, rho0, rho1);
+                acc[0] += rho0;
+                float Jf[6];
+                cam_project_jac(cm, xcf, Jf);
+                double J[6];                               // J = -Jproj * R   (2x3)
+#pragma unroll
+                for (int r = 0; r < 2; ++r)
+#pragma unroll
+                    for (int c = 0; c < 3; ++c)
+                        J[r * 3 + c] = -((double)Jf[r * 3] * R[c] + (double)Jf[r * 3 + 1] * R[3 + c] + (double)Jf[r * 3 + 2] * R[6 + c]);
+                double wr = rho1 * om;
+                double Uu[6];
+#pragma unroll
+                for (int r = 0; r < 3; ++r) {
+                    gb[cam * 3 + r] -= wr * (J[r] * e0 + J[3 + r] * e1r);
+#pragma unroll
+                    for (int c = r; c < 3; ++c) Uu[pk<3>(r, c)] = wr * (J[r] * J[c] + J[3 + r] * J[3 + c]);
+                }
+                // depth edge EdgeDepthCorrection (g2oTypes.h:400-416): e = (d/s - z_c)^2 (x500 if s<=0)
+                double s = cam == 0 ? G.s1 : G.s2;
+                double dd = cam == 0 ? d.x : d.y;
+                double kf = s <= 0.0 ? 500.0 : 1.0;
+                D3 xc = mul(R, X);
+                double rr = dd / s - (xc.z + t[2]);
+                double ed = kf * rr * rr;
+                double alpha = -2.0 * kf * rr;             // de/dX = alpha * R[2,:]
+                double Js = 2.0 * kf * rr * (-dd / (s * s));
+                acc[1] += W.depth_info * ed * ed;
+                double nrm[3] = {R[6], R[7], R[8]};
+#pragma unroll
+                for (int r = 0; r < 3; ++r) {
+                    gb[cam * 3 + r] -= W.depth_info * ed * alpha * nrm[r];
+#pragma unroll
+                    for (int c = r; c < 3; ++c) Uu[pk<3>(r, c)] += W.depth_info * alpha * alpha * nrm[r] * nrm[c];
+                }
+                acc[10 + cam] -= W.depth_info * ed * Js;           // bg[6 + cam]
+                acc[33 + cam] += W.depth_info * Js * Js;           // C[s s]
+                Urec[12 + cam] = W.depth_info * alpha * Js;        // kd: coupling X <-> s along R[2,:]
+#pragma unroll
+                for (int k = 0; k < 6; ++k) Urec[cam * 6 + k] = Uu[k];
+#pragma unroll
+                for (int r = 0; r < 3; ++r)
+#pragma unroll
+                    for (int c = r; c < 3; ++c) Dk[pk<6>(cam * 3 + r, cam * 3 + c)] += Uu[pk<3>(r, c)];
+            }
+            store6(b, i, d3(gb[0], gb[1], gb[2]), d3(gb[3], gb[4], gb[5]));
+            double* Dp = D + 21 * (size_t)i;
+#pragma unroll
+            for (int k = 0; k < 21; ++k) Dp[k] = Dk[k];
+            double2* Up = reinterpret_cast<double2*>(U + 16 * (size_t)i);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) Up[k] = make_double2(Urec[2 * k], Urec[2 * k + 1]);
+#pragma unroll
+            for (int r = 0; r < 6; ++r) maxdiag = fmax(maxdiag, fabs(Dk[pk<6>(r, r)]));
+        }
+    }
+    // max-reduce maxdiag separately, sums through block_reduce
+    for (int o = 16; o > 0; o >>= 1) maxdiag = fmax(maxdiag, __shfl_xor_sync(0xffffffffu, maxdiag, o));
+    __shared__ double smax[kThreads / 32];
+    if ((threadIdx.x & 31) == 0) smax[threadIdx.x >> 5] = maxdiag;
+    block_reduce<kLinPart>(acc, sm);
+    if (threadIdx.x == 0) {
+        double m = 0.0;
+        for (int w = 0; w < kThreads / 32; ++w) m = fmax(m, smax[w]);
+        acc[3] = m;
+        double* o = part + (size_t)kLinPart * blockIdx.x;
+        for (int k = 0; k < kLinPart; ++k) o[k] = acc[k];
+    }
+}
+
+__global__ void __launch_bounds__(kThreads)
+finalize_linearize_kernel(int nb, const double* __restrict__ part, LinGlobal* __restrict__ out) {
+    __shared__ double sm[kThreads / 32];
+    for (int k = 0; k < kLinPart; ++k) {
+        double v;
+        if (k == 3) {
+            double m = 0.0;
+            for (int i = threadIdx.x; i < nb; i += blockDim.x) m = fmax(m, part[(size_t)i * kLinPart + 3]);
+            for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+            __syncthreads();
+            if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = m;
+            __syncthreads();
+            v = 0.0;
+            for (int w = 0; w < kThreads / 32; ++w) v = fmax(v, sm[w]);
+        } else {
+            v = sum_partials(part + k, nb, kLinPart, sm);
+        }
+        if (threadIdx.x == 0) {
+            if (k < 3) out->chi2[k] = v;
+            else if (k == 3) out->maxdiag = v;
+            else if (k < 12) out->bg[k - 4] = v;
+            else if (k < 33) {
+                int idx = k - 12, r = 0;
+                while (idx >= 6 - r) { idx -= 6 - r; ++r; }
+                int c = r + idx;
+                out->C[r * 8 + c] = v; out->C[c * 8 + r] = v;
+            } else { int s = 6 + (k - 33); out->C[s * 8 + s] = v; }
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        for (int r = 0; r < 6; ++r) for (int s = 6; s < 8; ++s) { out->C[r * 8 + s] = 0.0; out->C[s * 8 + r] = 0.0; }
+        out->C[6 * 8 + 7] = 0.0; out->C[7 * 8 + 6] = 0.0;
+        double m = out->maxdiag;
+        for (int r = 0; r < 8; ++r) m = fmax(m, fabs(out->C[r * 8 + r]));
+        out->maxdiag = m;                                 // computeLambdaInit: max over ALL vertices' diagonals
+    }
+}
+
+// block-Jacobi preconditioner: Minv_i = (D_i + lambda I)^-1 (packed), Ginv = (C + lambda I)^-1
+__global__ void __launch_bounds__(kThreads)
+precond_kernel(int n, const double* __restrict__ D, double lambda, const LinGlobal* __restrict__ lin,
+               double* __restrict__ Minv, double* __restrict__ Ginv, int* __restrict__ err) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const double* Dp = D + 21 * (size_t)i;
+        double A[36], Ai[36];
+#pragma unroll
+        for (int r = 0; r < 6; ++r)
+#pragma unroll
+            for (int c = r; c < 6; ++c) {
+                double v = Dp[pk<6>(r, c)] + (r == c ? lambda : 0.0);
+                A[r * 6 + c] = v; A[c * 6 + r] = v;
+            }
+        if (!spd_inverse<6>(A, Ai)) {
+            atomicExch(err, 1);
+#pragma unroll
+            for (int k = 0; k < 36; ++k) Ai[k] = 0.0;
+#pragma unroll
+            for (int r = 0; r < 6; ++r) Ai[r * 6 + r] = 1.0 / fmax(fabs(A[r * 6 + r]), 1e-300);
+        }
+        double* Mp = Minv + 21 * (size_t)i;
+#pragma unroll
+        for (int r = 0; r < 6; ++r)
+#pragma unroll
+            for (int c = r; c < 6; ++c) Mp[pk<6>(r, c)] = Ai[r * 6 + c];
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        double A[64], Ai[64];
+        for (int k = 0; k < 64; ++k) A[k] = lin->C[k];
+        for (int r = 0; r < 8; ++r) A[r * 8 + r] += lambda;
+        if (!spd_inverse<8>(A, Ai)) {
+            atomicExch(err, 1);
+            for (int k = 0; k < 64; ++k) Ai[k] = 0.0;
+            for (int r = 0; r < 8; ++r) Ai[r * 8 + r] = 1.0 / fmax(fabs(A[r * 8 + r]), 1e-300);
+        }
+        for (int k = 0; k < 64; ++k) Ginv[k] = Ai[k];
+    }
+}
+
+DSC_D void apply_minv(const double* __restrict__ Mp, const double* r, double* z) {
+    double M[21];
+#pragma unroll
+    for (int k = 0; k < 21; ++k) M[k] = Mp[k];
+#pragma unroll
+    for (int a = 0; a < 6; ++a) {
+        double s = 0.0;
+#pragma unroll
+        for (int c = 0; c < 6; ++c) s += (a <= c ? M[pk<6>(a, c)] : M[pk<6>(c, a)]) * r[c];
+        z[a] = s;
+    }
+}
+
+// ================================================================== K4: PCG (Chronopoulos-Gear form)
+//   z = M^-1 r ; w = A z ; gamma = r.z ; delta = z.w
+//   beta = gamma/gamma_prev ; alpha = gamma / (delta - beta gamma / alpha_prev)
+//   p = z + beta p ; s = w + beta s ; x += alpha p ; r -= alpha s
+// Two kernels per iteration (update, spmv); all scalars stay on the device.
+struct CgVecs {
+    double *x, *r, *z, *w, *p, *s;          // [n][6]
+    double *xg, *rg, *zg, *wg, *pg, *sg;    // [8]
+};
+
+__global__ void __launch_bounds__(kThreads)
+cg_init_kernel(int n, const double* __restrict__ b, const LinGlobal* __restrict__ lin, const double* __restrict__ Minv,
+               const double* __restrict__ Ginv, CgVecs v, double* __restrict__ gpart, CgControl* __restrict__ ctl) {
+    __shared__ double sm[kThreads / 32];
+    double g[1] = {0.0};
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        double r[6], z[6];
+        D3 a, c;
+        load6(b, i, a, c);
+        r[0] = a.x; r[1] = a.y; r[2] = a.z; r[3] = c.x; r[4] = c.y; r[5] = c.z;
+        apply_minv(Minv + 21 * (size_t)i, r, z);
+        store6(v.r, i, a, c);
+        store6(v.z, i, d3(z[0], z[1], z[2]), d3(z[3], z[4], z[5]));
+        D3 zero = d3(0, 0, 0);
+        store6(v.x, i, zero, zero); store6(v.p, i, zero, zero); store6(v.s, i, zero, zero);
+#pragma unroll
+        for (int k = 0; k < 6; ++k) g[0] += r[k] * z[k];
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        for (int a = 0; a < 8; ++a) {
+            double s = 0.0;
+            for (int c = 0; c < 8; ++c) s += Ginv[a * 8 + c] * lin->bg[c];
+            v.rg[a] = lin->bg[a]; v.zg[a] = s; v.xg[a] = 0.0; v.pg[a] = 0.0; v.sg[a] = 0.0;
+            g[0] += lin->bg[a] * s;
+        }
+        ctl->iters = 0; ctl->converged = 0; ctl->breakdown = 0;
+        ctl->sc[0].gamma_prev = 1.0; ctl->sc[0].alpha_prev = 1.0;
+        ctl->sc[1].gamma_prev = 1.0; ctl->sc[1].alpha_prev = 1.0;
+    }
+    block_reduce<1>(g, sm);
+    if (threadIdx.x == 0) gpart[blockIdx.x] = g[0];
+}
+
+// w = (H + lambda I) z, matrix-free.  dpart[grid]: partial z.w (global rows included), bpart[grid][8]: partial
+// global rows of H z (T_g rows from the ARAP edges, s1/s2 rows from the depth edges).
+__global__ void __launch_bounds__(kThreads)
+cg_spmv_kernel(int n, const double* __restrict__ P, const double* __restrict__ Q, const double* __restrict__ U,
+               const int* __restrict__ rowptr, const int* __restrict__ col, const double* __restrict__ wgt,
+               const Globals* __restrict__ Gp, const __grid_constant__ PairDev pr, const __grid_constant__ WeightsDev W,
+               double lambda, const double* __restrict__ z, const double* __restrict__ zg, double* __restrict__ w,
+               double* __restrict__ dpart, double* __restrict__ bpart,
+               const LinGlobal* __restrict__ lin, const CgControl* __restrict__ ctl) {
+    __shared__ double sm[9 * (kThreads / 32)];
+    __shared__ Globals G;
+    __shared__ double zgs[8];
+    if (ctl && (ctl->converged || ctl->breakdown)) return;   // flags are only written by an EARLIER launch
+    if (threadIdx.x == 0) G = *Gp;
+    if (threadIdx.x < 8) zgs[threadIdx.x] = zg[threadIdx.x];
+    __syncthreads();
+    int lane = threadIdx.x & (kLanes - 1);
+    double acc[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) acc[k] = 0.0;
+    D3 zw = d3(zgs[0], zgs[1], zgs[2]), zv = d3(zgs[3], zgs[4], zgs[5]);
+    int nround = (n + kGroups - 1) / kGroups;
+    for (int rd = blockIdx.x; rd < nround; rd += gridDim.x) {
+        int i = rd * kGroups + threadIdx.x / kLanes;
+        bool act = i < n;
+        double o[6];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) o[k] = 0.0;
+        D3 zi1 = d3(0, 0, 0), zi2 = d3(0, 0, 0);
+        if (act) {
+            P8 Pi = load_P(P, i);
+            double qi[4];
+            load_q(Q, i, qi);
+            load6(z, i, zi1, zi2);
+            int e1 = rowptr[i + 1];
+            for (int e = rowptr[i] + lane; e < e1; e += kLanes) {
+                int j = col[e];
+                P8 Pj = load_P(P, j);
+                double qj[4];
+                load_q(Q, j, qj);
+                D3 zj1, zj2;
+                load6(z, j, zj1, zj2);
+                ArapGrad g;
+                arap_edge<true>(Pi, Pj, qi, qj, wgt[e], W.inv_area, G, g);
+                double s = dot(g.gi1, zi1) + dot(g.gi2, zi2) + dot(g.gj1, zj1) + dot(g.gj2, zj2) + dot(g.gw, zw) + dot(g.gv, zv);
+                double ws = W.arap_info * s;
+                double w2 = 2.0 * ws;
+                o[0] += w2 * g.gi1.x; o[1] += w2 * g.gi1.y; o[2] += w2 * g.gi1.z;
+                o[3] += w2 * g.gi2.x; o[4] += w2 * g.gi2.y; o[5] += w2 * g.gi2.z;
+                acc[0] += ws * g.gw.x; acc[1] += ws * g.gw.y; acc[2] += ws * g.gw.z;
+                acc[3] += ws * g.gv.x; acc[4] += ws * g.gv.y; acc[5] += ws * g.gv.z;
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 6; ++k) o[k] = group_sum(o[k]);
+        if (act && lane == 0) {
+            const double2* Up = reinterpret_cast<const double2*>(U + 16 * (size_t)i);
+            double u[16];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) { double2 t = __ldg(Up + k); u[2 * k] = t.x; u[2 * k + 1] = t.y; }
+            double zi[6] = {zi1.x, zi1.y, zi1.z, zi2.x, zi2.y, zi2.z};
+#pragma unroll
+            for (int cam = 0; cam < 2; ++cam) {
+                const double* R = cam == 0 ? pr.R1 : pr.R2;
+                double nz = R[6] * zi[cam * 3] + R[7] * zi[cam * 3 + 1] + R[8] * zi[cam * 3 + 2];
+                double kd = u[12 + cam];
+#pragma unroll
+                for (int r = 0; r < 3; ++r) {
+                    double s = 0.0;
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) s += (r <= c ? u[cam * 6 + pk<3>(r, c)] : u[cam * 6 + pk<3>(c, r)]) * zi[cam * 3 + c];
+                    o[cam * 3 + r] += s + kd * R[6 + r] * zgs[6 + cam];
+                }
+                acc[6 + cam] += kd * nz;
+            }
+            double dl = 0.0;
+#pragma unroll
+            for (int k = 0; k < 6; ++k) { o[k] += lambda * zi[k]; dl += zi[k] * o[k]; }
+            acc[8] += dl;
+            store6(w, i, d3(o[0], o[1], o[2]), d3(o[3], o[4], o[5]));
+        }
+    }
+    block_reduce<9>(acc, sm);
+    if (threadIdx.x == 0) {
+        double dl = acc[8];
+        for (int k = 0; k < 8; ++k) { bpart[8 * (size_t)blockIdx.x + k] = acc[k]; dl += zgs[k] * acc[k]; }
+        if (blockIdx.x == 0)     // diagonal of the global rows that is not inside the edge sums: (C_ss + lambda)
+            for (int k = 0; k < 8; ++k) dl += zgs[k] * ((k >= 6 ? lin->C[k * 8 + k] : 0.0) + lambda) * zgs[k];
+        dpart[blockIdx.x] = dl;
+    }
+}
+
+// One CG step.  par = iteration parity (double-buffered scalars and gamma partials).
+__global__ void __launch_bounds__(kThreads)
+cg_update_kernel(int n, int par, int first, const double* __restrict__ Minv, const double* __restrict__ Ginv,
+                 const LinGlobal* __restrict__ lin, double lambda, CgVecs v,
+                 const double* __restrict__ gpart_in, double* __restrict__ gpart_out,
+                 const double* __restrict__ dpart, const double* __restrict__ bpart, int nspmv,
+                 CgControl* __restrict__ ctl, double rtol2) {
+    __shared__ double sm[kThreads / 32];
+    if (ctl->converged || ctl->breakdown) return;            // set by an earlier launch
+    double gamma = sum_partials(gpart_in, gridDim.x, 1, sm);
+    double delta = sum_partials(dpart, nspmv, 1, sm);
+    if (first && blockIdx.x == 0 && threadIdx.x == 0) ctl->gamma0 = gamma;
+    double gamma0 = first ? gamma : ctl->gamma0;
+    if (!first && gamma <= rtol2 * gamma0) {                  // same fixed-order sums in every block => same decision
+        if (blockIdx.x == 0 && threadIdx.x == 0) ctl->converged = 1;
+        return;
+    }
+    CgScalars prev = ctl->sc[par ^ 1];
+    double beta = first ? 0.0 : gamma / prev.gamma_prev;
+    double denom = first ? delta : delta - beta * gamma / prev.alpha_prev;
+    double alpha = gamma / denom;
+    bool bad = !(denom > 0.0) || !isfinite(alpha);
+    if (bad) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) ctl->breakdown = 1;
+        return;
+    }
+    double g[1] = {0.0};
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        D3 z1, z2, w1, w2, p1, p2, s1, s2, x1, x2, r1, r2;
+        load6(v.z, i, z1, z2); load6(v.w, i, w1, w2); load6(v.p, i, p1, p2);
+        load6(v.s, i, s1, s2); load6(v.x, i, x1, x2); load6(v.r, i, r1, r2);
+        p1 = z1 + beta * p1; p2 = z2 + beta * p2;
+        s1 = w1 + beta * s1; s2 = w2 + beta * s2;
+        x1 = x1 + alpha * p1; x2 = x2 + alpha * p2;
+        r1 = r1 - alpha * s1; r2 = r2 - alpha * s2;
+        double r[6] = {r1.x, r1.y, r1.z, r2.x, r2.y, r2.z}, zn[6];
+        apply_minv(Minv + 21 * (size_t)i, r, zn);
+        store6(v.p, i, p1, p2); store6(v.s, i, s1, s2); store6(v.x, i, x1, x2); store6(v.r, i, r1, r2);
+        store6(v.z, i, d3(zn[0], zn[1], zn[2]), d3(zn[3], zn[4], zn[5]));
+#pragma unroll
+        for (int k = 0; k < 6; ++k) g[0] += r[k] * zn[k];
+    }
+    if (blockIdx.x == 0) {
+        __shared__ double wg[8], rgn[8];
+        __syncthreads();
+        if (threadIdx.x < 8) {
+            int k = threadIdx.x;
+            double s = 0.0;
+            for (int bk = 0; bk < nspmv; ++bk) s += bpart[8 * (size_t)bk + k];
+            double d = (k >= 6 ? lin->C[k * 8 + k] : 0.0) + lambda;
+            wg[k] = s + d * v.zg[k];
+            double pg = v.zg[k] + beta * v.pg[k];
+            double sg = wg[k] + beta * v.sg[k];
+            v.pg[k] = pg; v.sg[k] = sg;
+            v.xg[k] += alpha * pg;
+            double rr = v.rg[k] - alpha * sg;
+            v.rg[k] = rr; rgn[k] = rr;
+        }
+        __syncthreads();
+        if (threadIdx.x < 8) {
+            int k = threadIdx.x;
+            double s = 0.0;
+            for (int c = 0; c < 8; ++c) s += Ginv[k * 8 + c] * rgn[c];
+            v.zg[k] = s;
+            wg[k] = s * rgn[k];
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int k = 0; k < 8; ++k) g[0] += wg[k];
+            ctl->sc[par].gamma_prev = gamma; ctl->sc[par].alpha_prev = alpha;
+            ctl->iters = ctl->iters + 1;
+        }
+    }
+    block_reduce<1>(g, sm);
+    if (threadIdx.x == 0) gpart_out[blockIdx.x] = g[0];
+}
+
+// ================================================================== LM trial: x_new = x (+) dx
+// Ptrial = P + dx (points), trial globals = exp(dx_T) * T_g, s + ds; scale partial = sum dx (lambda dx + b)
+__global__ void __launch_bounds__(kThreads)
+apply_update_kernel(int n, const double* __restrict__ P, const double* __restrict__ x, const double* __restrict__ xg,
+                    const double* __restrict__ b, const LinGlobal* __restrict__ lin, double lambda,
+                    const Globals* __restrict__ Gcur, double* __restrict__ Ptrial, Globals* __restrict__ Gtrial,
+                    double* __restrict__ part) {
+    __shared__ double sm[kThreads / 32];
+    double acc[1] = {0.0};
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        D3 x1, x2, b1, b2;
+        load6(x, i, x1, x2); load6(b, i, b1, b2);
+        P8 Pi = load_P(P, i);
+        double4* o = reinterpret_cast<double4*>(Ptrial) + 2 * (size_t)i;
+        o[0] = make_double4(Pi.a.x + x1.x, Pi.a.y + x1.y, Pi.a.z + x1.z, 0.0);
+        o[1] = make_double4(Pi.b.x + x2.x, Pi.b.y + x2.y, Pi.b.z + x2.z, 0.0);
+        acc[0] += dot(x1, lambda * x1 + b1) + dot(x2, lambda * x2 + b2);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        Globals g = *Gcur;
+        double upd[6];
+        for (int k = 0; k < 6; ++k) upd[k] = xg[k];
+        double T[7];
+        se3_oplus(g.Tg, upd, T);
+        Globals o;
+        for (int k = 0; k < 7; ++k) o.Tg[k] = T[k];
+        o.s1 = g.s1 + xg[6]; o.s2 = g.s2 + xg[7];
+        quat_to_rot(o.Tg, o.Rg);
+        *Gtrial = o;
+        for (int k = 0; k < 8; ++k) acc[0] += xg[k] * (lambda * xg[k] + lin->bg[k]);
+    }
+    block_reduce<1>(acc, sm);
+    if (threadIdx.x == 0) part[blockIdx.x] = acc[0];
+}
+
+// ================================================================== write-back helpers
+// points cast to float in the caller's order; update = sum |p_old - p_new| (float norm, g2oBundleAdjustment.cc:978-990)
+__global__ void __launch_bounds__(kThreads)
+export_kernel(int n, const double* __restrict__ P, const double* __restrict__ P0, const int* __restrict__ perm,
+              float* __restrict__ X1, float* __restrict__ X2, double* __restrict__ X1d, double* __restrict__ X2d,
+              double* __restrict__ part) {
+    __shared__ double sm[kThreads / 32];
+    double acc[1] = {0.0};
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        size_t d = perm ? (size_t)perm[i] : (size_t)i;
+        P8 a = load_P(P, i), o = load_P(P0, i);
+        float n1[3] = {(float)a.a.x, (float)a.a.y, (float)a.a.z}, n2[3] = {(float)a.b.x, (float)a.b.y, (float)a.b.z};
+        float o1[3] = {(float)o.a.x, (float)o.a.y, (float)o.a.z}, o2[3] = {(float)o.b.x, (float)o.b.y, (float)o.b.z};
+        for (int k = 0; k < 3; ++k) {
+            X1[3 * d + k] = n1[k]; X2[3 * d + k] = n2[k];
+        }
+        if (X1d) { X1d[3 * d] = a.a.x; X1d[3 * d + 1] = a.a.y; X1d[3 * d + 2] = a.a.z; }
+        if (X2d) { X2d[3 * d] = a.b.x; X2d[3 * d + 1] = a.b.y; X2d[3 * d + 2] = a.b.z; }
+        float e1 = fsq(fa(fa(fm(fs(o1[0], n1[0]), fs(o1[0], n1[0])), fm(fs(o1[1], n1[1]), fs(o1[1], n1[1]))), fm(fs(o1[2], n1[2]), fs(o1[2], n1[2]))));
+        float e2 = fsq(fa(fa(fm(fs(o2[0], n2[0]), fs(o2[0], n2[0])), fm(fs(o2[1], n2[1]), fs(o2[1], n2[1]))), fm(fs(o2[2], n2[2]), fs(o2[2], n2[2]))));
+        acc[0] += (double)e1 + (double)e2;
+    }
+    block_reduce<1>(acc, sm);
+    if (threadIdx.x == 0) part[blockIdx.x] = acc[0];
+}
+
+// calculatePixelsStandDev (Utils/Geometry.cc:409-458): per camera sums of squared |obs - project(T * (float)X)|
+// part: [grid][4] = {su1, sv1, su2, sv2}
+__global__ void __launch_bounds__(kThreads)
+pixel_sigma_kernel(int n, const double* __restrict__ P, const float4* __restrict__ uv,
+                   const __grid_constant__ PairDev pr, double* __restrict__ part) {
+    __shared__ double sm[4 * (kThreads / 32)];
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        P8 a = load_P(P, i);
+        float4 o = uv[i];
+        float pu, pv;
+        cam_project(pr.cam1, apply(pr.T1f, mk3((float)a.a.x, (float)a.a.y, (float)a.a.z)), pu, pv);
+        double eu = fabs((double)o.x - (double)pu), ev = fabs((double)o.y - (double)pv);
+        acc[0] += eu * eu; acc[1] += ev * ev;
+        cam_project(pr.cam2, apply(pr.T2f, mk3((float)a.b.x, (float)a.b.y, (float)a.b.z)), pu, pv);
+        eu = fabs((double)o.z - (double)pu); ev = fabs((double)o.w - (double)pv);
+        acc[2] += eu * eu; acc[3] += ev * ev;
+    }
+    block_reduce<4>(acc, sm);
+    if (threadIdx.x == 0) for (int k = 0; k < 4; ++k) part[4 * (size_t)blockIdx.x + k] = acc[k];
+}
+
+}  // namespace dsc
