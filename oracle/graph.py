@@ -138,4 +138,22 @@ def compute_rotations(g, X1, X2):
     R[neg] = V[neg] @ np.swapaxes(U2[neg], 1, 2)
     deg = np.diff(g.rowptr)
     R[deg == 0] = np.eye(3)
+    # Degenerate covariances.  S == 0 keeps the identity.  Rank 1 (e.g. a hull vertex whose cot weights
+    # are clamped to 0 on all but one edge): V U^T depends on an arbitrary completion of the SVD bases in
+    # the reference; defined here (and in the CUDA kernel) as the minimal rotation taking u1 to v1.
+    sv = np.linalg.svd(S, compute_uv=False)
+    for i in np.nonzero(~(sv[:, 0] > 0.0))[0]:
+        R[i] = np.eye(3)
+    for i in np.nonzero((sv[:, 0] > 0.0) & ~(sv[:, 1] > 1e-12 * sv[:, 0]))[0]:
+        u, v = U[i, :, 0], V[i, :, 0]
+        d = float(u @ v)
+        if d > -1.0 + 1e-12:
+            c = np.cross(u, v)
+            K = np.array([[0, -c[2], c[1]], [c[2], 0, -c[0]], [-c[1], c[0], 0]])
+            R[i] = np.eye(3) + K + (K @ K) / (1.0 + d)
+        else:
+            k = int(np.argmin(np.abs(u)))
+            a = np.cross(u, np.eye(3)[k])
+            a /= np.linalg.norm(a)
+            R[i] = 2.0 * np.outer(a, a) - np.eye(3)
     return R

@@ -1,0 +1,226 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle on identical inputs.
+
+Tolerances (BASELINE.json north_star): float32 triangulation bit-exact for the closed-form
+methods; per-iteration cost and final points within 1e-5 relative in fp64; index bookkeeping exact.
+"""
+import numpy as np
+import pytest
+
+from oracle import scenes, edges, lm, camera, graph as ograph
+from oracle.triangulate import triangulate_pairs, init_depth_scale_sim, GATE_SIM, GATE_REAL, GATE_NONE
+
+pytestmark = pytest.mark.gpu
+
+REF = "/root/reference/Data/"
+
+
+def _pair(pkg, sc):
+    cam = (camera.KB8, sc["cam"])
+    return pkg.make_pair(cam, cam, sc["T1"], sc["T2"]), cam
+
+
+def _upload(pkg, ctx, p, reorder=1):
+    pair = pkg.make_pair(p.cam1, p.cam2, p.T1, p.T2)
+    ctx.problem_upload(pair, p.X1, p.X2, p.uv1, p.uv2, p.d1, p.d2, p.inv_sigma2_1, p.inv_sigma2_2,
+                       scale1=p.s1, scale2=p.s2, Tg7=p.Tg.as7())
+    g = p.graph
+    ctx.set_graph(g.rowptr, g.col, g.w, g.area, g.n_triangles, reorder)
+    ctx.compute_rotations()
+
+
+def _w(pkg, w):
+    return pkg.make_weights(w.rep, w.arap, w.depth_sigma, w.glob, w.alpha, w.beta)
+
+
+@pytest.mark.parametrize("method", ["NRSLAM", "DepthMeasurement"])
+@pytest.mark.parametrize("location", ["InRays", "TwoPoints", "FarPoints"])
+def test_triangulation_closed_form_bit_exact(pkg, ctx, method, location):
+    sc = scenes.sheet_scene(20000, seed=1)
+    pair, cam = _pair(pkg, sc)
+    prm = ctx.tri_params(method, location, GATE_SIM, 0.9998)
+    X1, X2, valid, cosp, nv = ctx.triangulate(pair, prm, sc["uv1"], sc["uv2"], sc["d1"], sc["d2"])
+    oX1, oX2, ovalid, ocos = triangulate_pairs(sc["uv1"], sc["uv2"], cam, cam, sc["T1"], sc["T2"], method, location,
+                                                GATE_SIM, 0.9998, d1=sc["d1"], d2=sc["d2"])
+    assert np.array_equal(valid, ovalid)
+    assert nv == int(ovalid.sum())
+    assert np.array_equal(X1, oX1) and np.array_equal(X2, oX2)
+    assert np.array_equal(cosp, ocos)
+
+
+@pytest.mark.parametrize("method", ["Classic", "ORBSLAM"])
+def test_triangulation_svd_methods(pkg, ctx, method):
+    sc = scenes.sheet_scene(5000, seed=2)
+    pair, cam = _pair(pkg, sc)
+    for location in ("InRays", "TwoPoints"):
+        prm = ctx.tri_params(method, location, GATE_NONE)
+        X1, X2, valid, cosp, nv = ctx.triangulate(pair, prm, sc["uv1"], sc["uv2"])
+        oX1, oX2, ovalid, ocos = triangulate_pairs(sc["uv1"], sc["uv2"], cam, cam, sc["T1"], sc["T2"], method, location, GATE_NONE)
+        # singular vectors: fp64 Jacobi on the device vs LAPACK in the oracle, rounded to float32
+        np.testing.assert_allclose(X1, oX1, rtol=2e-4, atol=2e-6)
+        np.testing.assert_allclose(X2, oX2, rtol=2e-4, atol=2e-6)
+
+
+def test_triangulation_real_gates_and_kb8_distortion(pkg, ctx):
+    sc = scenes.tube_scene(8000, seed=4, cam=scenes.REALCOLON_CAM)
+    pair, cam = _pair(pkg, sc)
+    prm = ctx.tri_params("NRSLAM", "TwoPoints", GATE_REAL, 0.9998, depth_limit=0.25, check_reproj=True)
+    X1, X2, valid, cosp, nv = ctx.triangulate(pair, prm, sc["uv1"], sc["uv2"])
+    oX1, oX2, ovalid, ocos = triangulate_pairs(sc["uv1"], sc["uv2"], cam, cam, sc["T1"], sc["T2"], "NRSLAM", "TwoPoints",
+                                                GATE_REAL, 0.9998, depth_limit=0.25, check_reproj=True)
+    assert 0 < ovalid.sum() < len(ovalid)
+    assert np.array_equal(valid, ovalid)
+    assert np.array_equal(X1, oX1) and np.array_equal(X2, oX2)
+
+
+def test_triangulation_empty_and_single(pkg, ctx):
+    sc = scenes.sheet_scene(1, seed=0)
+    pair, cam = _pair(pkg, sc)
+    prm = ctx.tri_params()
+    X1, X2, valid, cosp, nv = ctx.triangulate(pair, prm, np.zeros((0, 2), np.float32), np.zeros((0, 2), np.float32))
+    assert X1.shape == (0, 3) and nv == 0
+    X1, X2, valid, cosp, nv = ctx.triangulate(pair, prm, sc["uv1"], sc["uv2"])
+    oX1, oX2, ovalid, _ = triangulate_pairs(sc["uv1"], sc["uv2"], cam, cam, sc["T1"], sc["T2"])
+    assert np.array_equal(X1, oX1) and np.array_equal(valid, ovalid)
+    # principal point: unproject is defined as the optical axis
+    uv = np.array([[sc["cam"][2], sc["cam"][3]]], np.float32)
+    X1, X2, valid, cosp, nv = ctx.triangulate(pair, prm, uv, uv)
+    oX1, oX2, ovalid, _ = triangulate_pairs(uv, uv, cam, cam, sc["T1"], sc["T2"])
+    assert np.array_equal(X1, oX1, equal_nan=True)
+
+
+def test_depth_scale_init(pkg, ctx):
+    sc = scenes.sheet_scene(4000, seed=5)
+    pair, cam = _pair(pkg, sc)
+    ctx.tri_upload(pair, sc["uv1"], sc["uv2"], sc["d1"], sc["d2"])
+    ctx.tri_run(ctx.tri_params())
+    X1, X2, valid, _, _ = ctx.tri_download()
+    for which, X, d, T in ((1, X1, sc["d1"], sc["T1"]), (2, X2, sc["d2"], sc["T2"])):
+        s = ctx.depth_scale_init(which)
+        assert s == pytest.approx(init_depth_scale_sim(d, X, T, valid), rel=1e-12)
+
+
+@pytest.mark.parametrize("kind,n", [("knn", 3000), ("delaunay", 1500)])
+def test_rotations_cost_gradient_and_operator(pkg, ctx, kind, n):
+    sc = scenes.sheet_scene(n, seed=7)
+    p, keep = scenes.problem_from_scene(sc, kind, 8)
+    w = edges.Weights(rep=1.0, arap=3.0e3, depth_sigma=0.003)
+    _upload(pkg, ctx, p)
+    # K7 rotations
+    q = ctx.get_rotations()
+    from oracle.se3 import quat_to_rot
+    R = np.stack([quat_to_rot(qq) for qq in q])
+    np.testing.assert_allclose(R, p.R, atol=1e-9)
+    ctx.set_rotations(np.stack([__import__("oracle.se3", fromlist=["x"]).rot_to_quat(r) for r in p.R]))
+    # K6 cost
+    st = edges.state_of(p)
+    chi, parts = edges.total_cost(p, w, st, parts=True)
+    gchi, gparts = ctx.cost(_w(pkg, w))
+    assert gchi == pytest.approx(chi, rel=1e-11)
+    for a, b in zip(gparts, parts):
+        assert a == pytest.approx(b, rel=1e-10)
+    # K2/K3 gradient, Hessian diagonal; K4 operator
+    import scipy.sparse as sp
+    J, wt, e, chi_l = edges.linearize(p, w, st)
+    JW = J.T @ sp.diags(wt)
+    H = (JW @ J).tocsr()
+    b = -(JW @ e)
+    gb, ghd, gchi2 = ctx.debug_linearize(_w(pkg, w))
+    assert gchi2 == pytest.approx(chi, rel=1e-11)
+    np.testing.assert_allclose(gb, b, rtol=1e-9, atol=1e-9 * np.abs(b).max())
+    np.testing.assert_allclose(ghd, H.diagonal(), rtol=1e-9, atol=1e-12 * np.abs(H.diagonal()).max())
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal(H.shape[0])
+    lam = 1e-5 * np.abs(H.diagonal()).max()
+    y = ctx.debug_matvec(_w(pkg, w), lam, x)
+    yo = H @ x + lam * x
+    np.testing.assert_allclose(y, yo, rtol=1e-9, atol=1e-10 * np.abs(yo).max())
+
+
+def _compare_lm(pkg, ctx, p, w, iters, rtol_cost=1e-5, rtol_pts=1e-5, pcg_rtol=1e-12, reorder=1):
+    _upload(pkg, ctx, p, reorder)
+    ctx.set_pcg(rtol=pcg_rtol, max_iters=20000, check_every=64)
+    recs, st = ctx.optimize(_w(pkg, w), iters)
+    out = ctx.download()
+    ost, otr = lm.optimize(p, w, iters)
+    assert st.iterations == len(otr.chi2)
+    for r, c, lam_o, q in zip(recs, otr.chi2, otr.lam, otr.trials):
+        assert r.chi2_before == pytest.approx(c, rel=rtol_cost)
+        assert r.lam == pytest.approx(lam_o, rel=1e-4)
+        assert r.trials == q
+    assert st.final_chi2 == pytest.approx(otr.final_chi2, rel=rtol_cost)
+    scale = np.abs(np.concatenate([ost.X1, ost.X2])).max()
+    assert np.abs(out["X1d"] - ost.X1).max() <= rtol_pts * scale
+    assert np.abs(out["X2d"] - ost.X2).max() <= rtol_pts * scale
+    assert out["scales"][0] == pytest.approx(ost.s1, rel=1e-5) and out["scales"][1] == pytest.approx(ost.s2, rel=1e-5)
+    Tg = ost.Tg.as7()
+    np.testing.assert_allclose(out["Tg"], Tg, atol=1e-5 * max(1.0, np.abs(Tg).max()))
+    n1, n2, upd = lm.write_back(p, ost)
+    assert out["update"] == pytest.approx(upd, rel=1e-4)
+    return recs, st, out
+
+
+def test_lm_config1_simulation(pkg, ctx):
+    """BASELINE.json configs[0]: Data/original_points.csv -> moved_points.csv, Simulation.yaml, Delaunay graph."""
+    import os
+    gold = os.path.join(os.path.dirname(__file__), "golden", "config1_points.npz")
+    z = np.load(gold)
+    fe = scenes.simulation_frontend(z["original"], z["moved"], (-0.10, 0.02, 0.12), (0.14, 0.01, 0.06))
+    p, keep = scenes.build_problem(fe["uv1"], fe["uv2"], fe["d1"], fe["d2"], fe["cam"], fe["T1"], fe["T2"])
+    w = edges.Weights(rep=1.0, arap=200000.0, depth_sigma=0.003, glob=50.0)
+    _compare_lm(pkg, ctx, p, w, 25)
+
+
+@pytest.mark.parametrize("arap", [2.0e5, 1.0e-2])
+def test_lm_sheet_knn(pkg, ctx, arap):
+    sc = scenes.sheet_scene(2500, seed=11)
+    p, keep = scenes.problem_from_scene(sc, "knn", 8)
+    w = edges.Weights(rep=1.0, arap=arap, depth_sigma=0.003)
+    _compare_lm(pkg, ctx, p, w, 6)
+
+
+def test_lm_no_reorder_same_result(pkg, ctx):
+    sc = scenes.sheet_scene(1500, seed=12)
+    p, keep = scenes.problem_from_scene(sc, "knn", 8)
+    w = edges.Weights(rep=1.0, arap=50.0, depth_sigma=0.003)
+    r1, s1, o1 = _compare_lm(pkg, ctx, p, w, 4, reorder=0)
+    r2, s2, o2 = _compare_lm(pkg, ctx, p, w, 4, reorder=1)
+    np.testing.assert_allclose(o1["X1d"], o2["X1d"], rtol=0, atol=1e-9)
+
+
+def test_reset_state_and_pixel_sigma(pkg, ctx):
+    sc = scenes.sheet_scene(1200, seed=13)
+    p, keep = scenes.problem_from_scene(sc, "knn", 8)
+    w = edges.Weights(rep=1.0, arap=10.0, depth_sigma=0.003)
+    _upload(pkg, ctx, p)
+    s0 = ctx.pixel_sigma()
+    assert s0[0] == pytest.approx(scenes.pixel_sigma(p.cam1, p.T1, p.X1, p.uv1), rel=1e-9)
+    assert s0[1] == pytest.approx(scenes.pixel_sigma(p.cam2, p.T2, p.X2, p.uv2), rel=1e-9)
+    c0, _ = ctx.cost(_w(pkg, w))
+    ctx.optimize(_w(pkg, w), 2)
+    c1, _ = ctx.cost(_w(pkg, w))
+    assert c1 < c0
+    ctx.reset_state()
+    c2, _ = ctx.cost(_w(pkg, w))
+    assert c2 == c0
+
+
+def test_error_behaviour(pkg, ctx):
+    sc = scenes.sheet_scene(300, seed=14)
+    p, keep = scenes.problem_from_scene(sc, "knn", 6)
+    w = pkg.make_weights(1.0, 1.0, 0.003)
+    with pytest.raises(pkg.DscError) as e:
+        ctx.cost(w)                      # nothing uploaded
+    assert e.value.status == -4
+    pair = pkg.make_pair(p.cam1, p.cam2, p.T1, p.T2)
+    ctx.problem_upload(pair, p.X1, p.X2, p.uv1, p.uv2, p.d1, p.d2, scale1=p.s1, scale2=p.s2)
+    g = p.graph
+    bad_col = g.col.copy()
+    bad_col[0] = (bad_col[0] + 7) % p.n       # breaks symmetry
+    with pytest.raises(pkg.DscError) as e:
+        ctx.set_graph(g.rowptr, bad_col, g.w, g.area, g.n_triangles)
+    assert e.value.status == -7
+    ctx.set_graph(g.rowptr, g.col, g.w, g.area, g.n_triangles)
+    ctx.compute_rotations()
+    with pytest.raises(pkg.DscError) as e:
+        ctx.optimize(pkg.make_weights(1.0, 1.0, 0.0), 1)    # sigma_depth = 0: 1/0 in the reference
+    assert e.value.status == -1

@@ -1,0 +1,307 @@
+"""ctypes binding of the C ABI in include/dsc.h (libdsc_b200.so).
+
+This is the thin Python face used by tests/ and bench.py; the product is the shared library.
+The binding never falls back to a CPU implementation: if the library is missing or no CUDA
+device is present, it raises.
+"""
+import ctypes as C
+import os
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libdsc_b200.so")
+
+CAM_KB8, CAM_PINHOLE = 0, 1
+TRI_CLASSIC, TRI_NRSLAM, TRI_ORBSLAM, TRI_DEPTH = 0, 1, 2, 3
+LOC_INRAYS, LOC_TWOPOINTS, LOC_FARPOINTS = 0, 1, 2
+GATE_NONE, GATE_SIM, GATE_REAL = 0, 1, 2
+METHODS = {"Classic": 0, "NRSLAM": 1, "ORBSLAM": 2, "DepthMeasurement": 3}
+LOCATIONS = {"InRays": 0, "TwoPoints": 1, "FarPoints": 2}
+
+EXPORTS = [
+    "dsc_create", "dsc_destroy", "dsc_last_error", "dsc_status_string", "dsc_version", "dsc_synchronize",
+    "dsc_timer_start", "dsc_timer_stop", "dsc_launch_count",
+    "dsc_triangulate", "dsc_tri_upload", "dsc_tri_run", "dsc_tri_download", "dsc_depth_scale_init",
+    "dsc_problem_upload", "dsc_set_graph", "dsc_compute_rotations", "dsc_get_rotations", "dsc_set_rotations",
+    "dsc_reset_state", "dsc_set_pcg", "dsc_cost", "dsc_optimize", "dsc_download", "dsc_pixel_sigma",
+    "dsc_debug_linearize", "dsc_debug_matvec",
+]
+
+
+class Camera(C.Structure):
+    _fields_ = [("model", C.c_int), ("params", C.c_float * 8)]
+
+
+class Pair(C.Structure):
+    _fields_ = [("cam1", Camera), ("cam2", Camera), ("T1w", C.c_float * 12), ("T2w", C.c_float * 12)]
+
+
+class TriParams(C.Structure):
+    _fields_ = [("method", C.c_int), ("location", C.c_int), ("gate", C.c_int), ("min_cos", C.c_float),
+                ("depth_limit", C.c_float), ("check_reproj", C.c_int)]
+
+
+class Weights(C.Structure):
+    _fields_ = [("rep", C.c_double), ("glob", C.c_double), ("arap", C.c_double), ("alpha", C.c_double),
+                ("beta", C.c_double), ("depth_sigma", C.c_float)]
+
+
+class PcgParams(C.Structure):
+    _fields_ = [("rtol", C.c_double), ("max_iters", C.c_int), ("check_every", C.c_int)]
+
+
+class IterRecord(C.Structure):
+    _fields_ = [("chi2_before", C.c_double), ("chi2_after", C.c_double), ("lam", C.c_double), ("trials", C.c_int),
+                ("accepted", C.c_int), ("pcg_iters", C.c_int)]
+
+
+class OptStats(C.Structure):
+    _fields_ = [("iterations", C.c_int), ("total_trials", C.c_int), ("total_pcg_iters", C.c_int), ("terminated", C.c_int),
+                ("final_chi2", C.c_double), ("device_ms", C.c_double), ("linearize_ms", C.c_double), ("pcg_ms", C.c_double),
+                ("trial_ms", C.c_double), ("kernel_launches", C.c_int)]
+
+
+class DscError(RuntimeError):
+    def __init__(self, status, msg):
+        super().__init__(f"dsc status {status}: {msg}")
+        self.status = status
+
+
+_lib = None
+
+
+def load_library(path=None):
+    """dlopen libdsc_b200.so; raises if it has not been built (no fallback)."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    path = path or LIB_PATH
+    if not os.path.exists(path):
+        raise FileNotFoundError(f"{path} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                                f"(the hot path has no CPU fallback)")
+    lib = C.CDLL(path)
+    lib.dsc_last_error.restype = C.c_char_p
+    lib.dsc_status_string.restype = C.c_char_p
+    lib.dsc_destroy.restype = None
+    _lib = lib
+    return lib
+
+
+def _fp(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+def _f32(a, shape=None):
+    if a is None:
+        return None
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    if shape is not None:
+        a = a.reshape(shape)
+    return a
+
+
+def _f64(a, shape=None):
+    if a is None:
+        return None
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    if shape is not None:
+        a = a.reshape(shape)
+    return a
+
+
+def make_pair(cam1, cam2, T1w, T2w):
+    """cam = (model, params[8]); Tcw = 3x4 float32 [R|t] (or an object with .as34())."""
+    p = Pair()
+    for dst, cam in ((p.cam1, cam1), (p.cam2, cam2)):
+        dst.model = int(cam[0])
+        prm = np.asarray(cam[1], np.float32).reshape(8)
+        for k in range(8):
+            dst.params[k] = float(prm[k])
+    for dst, T in ((p.T1w, T1w), (p.T2w, T2w)):
+        M = T.as34() if hasattr(T, "as34") else np.asarray(T, np.float32)
+        M = np.asarray(M, np.float32).reshape(12)
+        for k in range(12):
+            dst[k] = float(M[k])
+    return p
+
+
+def make_weights(rep=1.0, arap=1.0, depth_sigma=1.0, glob=0.0, alpha=1.0, beta=1.0):
+    return Weights(float(rep), float(glob), float(arap), float(alpha), float(beta), float(depth_sigma))
+
+
+class Context:
+    """One dsc_ctx: one CUDA stream, driven by one host thread."""
+
+    def __init__(self, device=0):
+        self.lib = load_library()
+        self.h = C.c_void_p()
+        st = self.lib.dsc_create(int(device), C.byref(self.h))
+        if st != 0:
+            raise DscError(st, self.lib.dsc_status_string(st).decode())
+        self.n = 0
+        self.tn = 0
+
+    def close(self):
+        if getattr(self, "h", None) is not None and self.h:
+            self.lib.dsc_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _ck(self, st):
+        if st != 0:
+            raise DscError(st, self.lib.dsc_last_error(self.h).decode())
+
+    # ---- timing / bookkeeping
+    def synchronize(self):
+        self._ck(self.lib.dsc_synchronize(self.h))
+
+    def timer_start(self):
+        self._ck(self.lib.dsc_timer_start(self.h))
+
+    def timer_stop(self):
+        ms = C.c_double()
+        self._ck(self.lib.dsc_timer_stop(self.h, C.byref(ms)))
+        return ms.value
+
+    def launch_count(self):
+        c = C.c_longlong()
+        self._ck(self.lib.dsc_launch_count(self.h, C.byref(c)))
+        return c.value
+
+    # ---- K1
+    @staticmethod
+    def tri_params(method="NRSLAM", location="FarPoints", gate=GATE_SIM, min_cos=0.9998, depth_limit=np.inf,
+                   check_reproj=False):
+        m = METHODS.get(method, 1) if isinstance(method, str) else int(method)
+        loc = LOCATIONS.get(location, 0) if isinstance(location, str) else int(location)
+        return TriParams(m, loc, int(gate), float(min_cos), float(min(depth_limit, 3.0e38)), int(bool(check_reproj)))
+
+    def triangulate(self, pair, prm, uv1, uv2, d1=None, d2=None):
+        uv1, uv2 = _f32(uv1, (-1, 2)), _f32(uv2, (-1, 2))
+        n = uv1.shape[0]
+        d1, d2 = _f32(d1), _f32(d2)
+        X1 = np.empty((n, 3), np.float32)
+        X2 = np.empty((n, 3), np.float32)
+        valid = np.empty(n, np.uint8)
+        cosp = np.empty(n, np.float32)
+        nv = C.c_int()
+        self._ck(self.lib.dsc_triangulate(self.h, C.byref(pair), C.byref(prm), n, _fp(uv1), _fp(uv2), _fp(d1), _fp(d2),
+                                          _fp(X1), _fp(X2), _fp(valid), _fp(cosp), C.byref(nv)))
+        self.tn = n
+        return X1, X2, valid.astype(bool), cosp, nv.value
+
+    def tri_upload(self, pair, uv1, uv2, d1=None, d2=None):
+        uv1, uv2 = _f32(uv1, (-1, 2)), _f32(uv2, (-1, 2))
+        self.tn = uv1.shape[0]
+        self._ck(self.lib.dsc_tri_upload(self.h, C.byref(pair), self.tn, _fp(uv1), _fp(uv2), _fp(_f32(d1)), _fp(_f32(d2))))
+
+    def tri_run(self, prm):
+        self._ck(self.lib.dsc_tri_run(self.h, C.byref(prm)))
+
+    def tri_download(self):
+        n = self.tn
+        X1 = np.empty((n, 3), np.float32)
+        X2 = np.empty((n, 3), np.float32)
+        valid = np.empty(n, np.uint8)
+        cosp = np.empty(n, np.float32)
+        nv = C.c_int()
+        self._ck(self.lib.dsc_tri_download(self.h, _fp(X1), _fp(X2), _fp(valid), _fp(cosp), C.byref(nv)))
+        return X1, X2, valid.astype(bool), cosp, nv.value
+
+    def depth_scale_init(self, which):
+        s = C.c_double()
+        self._ck(self.lib.dsc_depth_scale_init(self.h, int(which), C.byref(s)))
+        return s.value
+
+    # ---- refinement problem
+    def problem_upload(self, pair, X1, X2, uv1, uv2, d1, d2, inv_sigma2_1=None, inv_sigma2_2=None,
+                       scale1=1.0, scale2=1.0, Tg7=None):
+        X1, X2 = _f32(X1, (-1, 3)), _f32(X2, (-1, 3))
+        n = X1.shape[0]
+        uv1, uv2 = _f32(uv1, (-1, 2)), _f32(uv2, (-1, 2))
+        d1, d2 = _f64(d1), _f64(d2)
+        s1, s2 = _f32(inv_sigma2_1), _f32(inv_sigma2_2)
+        tg = _f64(Tg7)
+        self._ck(self.lib.dsc_problem_upload(self.h, C.byref(pair), n, _fp(X1), _fp(X2), _fp(uv1), _fp(uv2), _fp(d1), _fp(d2),
+                                             _fp(s1), _fp(s2), C.c_double(scale1), C.c_double(scale2), _fp(tg)))
+        self.n = n
+
+    def set_graph(self, rowptr, col, w, area, n_triangles, reorder=1):
+        rowptr = np.ascontiguousarray(rowptr, np.int32)
+        col = np.ascontiguousarray(col, np.int32)
+        w = _f64(w)
+        self._ck(self.lib.dsc_set_graph(self.h, len(rowptr) - 1, _fp(rowptr), _fp(col), _fp(w), C.c_double(area),
+                                        C.c_longlong(int(n_triangles)), int(reorder)))
+
+    def compute_rotations(self):
+        self._ck(self.lib.dsc_compute_rotations(self.h))
+
+    def get_rotations(self):
+        q = np.empty((self.n, 4), np.float64)
+        self._ck(self.lib.dsc_get_rotations(self.h, _fp(q)))
+        return q
+
+    def set_rotations(self, quat):
+        q = _f64(quat, (-1, 4))
+        self._ck(self.lib.dsc_set_rotations(self.h, _fp(q)))
+
+    def reset_state(self):
+        self._ck(self.lib.dsc_reset_state(self.h))
+
+    def set_pcg(self, rtol=1e-10, max_iters=4000, check_every=32):
+        p = PcgParams(float(rtol), int(max_iters), int(check_every))
+        self._ck(self.lib.dsc_set_pcg(self.h, C.byref(p)))
+
+    def cost(self, w):
+        chi = C.c_double()
+        parts = (C.c_double * 3)()
+        self._ck(self.lib.dsc_cost(self.h, C.byref(w), C.byref(chi), parts))
+        return chi.value, tuple(parts)
+
+    def optimize(self, w, n_iters):
+        recs = (IterRecord * max(1, n_iters))()
+        st = OptStats()
+        self._ck(self.lib.dsc_optimize(self.h, C.byref(w), int(n_iters), recs, C.byref(st)))
+        return [recs[i] for i in range(st.iterations)], st
+
+    def download(self, doubles=True):
+        n = self.n
+        X1 = np.empty((n, 3), np.float32)
+        X2 = np.empty((n, 3), np.float32)
+        X1d = np.empty((n, 3), np.float64) if doubles else None
+        X2d = np.empty((n, 3), np.float64) if doubles else None
+        scales = np.empty(2, np.float64)
+        tg = np.empty(7, np.float64)
+        upd = C.c_double()
+        self._ck(self.lib.dsc_download(self.h, _fp(X1), _fp(X2), _fp(X1d), _fp(X2d), _fp(scales), _fp(tg), C.byref(upd)))
+        return dict(X1=X1, X2=X2, X1d=X1d, X2d=X2d, scales=scales, Tg=tg, update=upd.value)
+
+    def pixel_sigma(self):
+        s = np.empty(2, np.float64)
+        self._ck(self.lib.dsc_pixel_sigma(self.h, _fp(s)))
+        return s
+
+    def debug_linearize(self, w):
+        nu = 8 + 6 * self.n
+        b = np.empty(nu)
+        hd = np.empty(nu)
+        chi = C.c_double()
+        self._ck(self.lib.dsc_debug_linearize(self.h, C.byref(w), _fp(b), _fp(hd), C.byref(chi)))
+        return b, hd, chi.value
+
+    def debug_matvec(self, w, lam, x):
+        x = _f64(x)
+        y = np.empty_like(x)
+        self._ck(self.lib.dsc_debug_matvec(self.h, C.byref(w), C.c_double(lam), _fp(x), _fp(y)))
+        return y

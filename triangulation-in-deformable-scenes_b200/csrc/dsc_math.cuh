@@ -283,8 +283,33 @@ DSC_HD void rotation_from_covariance(const double* S, double* R) {
     double A[3][3], V[3][3], sig[3];
     for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) A[i][j] = S[i * 3 + j];
     jacobi_svd<3>(A, V, sig);
-    if (!(sig[1] > 1e-300 * fmax(sig[0], 1e-300)) || !(sig[0] > 0.0)) {
-        for (int i = 0; i < 9; ++i) R[i] = (i % 4 == 0) ? 1.0 : 0.0;   // rank < 2: undefined in the reference
+    if (!(sig[0] > 0.0)) {                              // S == 0: Rs stays at its identity initialisation
+        for (int i = 0; i < 9; ++i) R[i] = (i % 4 == 0) ? 1.0 : 0.0;
+        return;
+    }
+    if (!(sig[1] > 1e-12 * sig[0])) {
+        // rank 1 (a vertex whose only non-zero-weight neighbour is one edge): V U^T is not unique in the
+        // reference (any completion of the SVD bases).  Defined here, and in oracle/graph.py, as the minimal
+        // rotation taking u1 to v1.
+        D3 u = (1.0 / sig[0]) * d3(A[0][0], A[1][0], A[2][0]);
+        D3 v = d3(V[0][0], V[1][0], V[2][0]);
+        double d = dot(u, v);
+        if (d > -1.0 + 1e-12) {
+            D3 c = cross(u, v);
+            double k = 1.0 / (1.0 + d);
+            double K[9] = {0, -c.z, c.y, c.z, 0, -c.x, -c.y, c.x, 0};
+            for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) {
+                double k2 = K[i * 3 + 0] * K[0 * 3 + j] + K[i * 3 + 1] * K[1 * 3 + j] + K[i * 3 + 2] * K[2 * 3 + j];
+                R[i * 3 + j] = (i == j ? 1.0 : 0.0) + K[i * 3 + j] + k * k2;
+            }
+        } else {
+            double ax = fabs(u.x), ay = fabs(u.y), az = fabs(u.z);
+            D3 e = (ax <= ay && ax <= az) ? d3(1, 0, 0) : ((ay <= az) ? d3(0, 1, 0) : d3(0, 0, 1));
+            D3 a = cross(u, e);
+            a = (1.0 / sqrt(dot(a, a))) * a;
+            double aa[3] = {a.x, a.y, a.z};
+            for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) R[i * 3 + j] = 2.0 * aa[i] * aa[j] - (i == j ? 1.0 : 0.0);
+        }
         return;
     }
     D3 u1 = (1.0 / sig[0]) * d3(A[0][0], A[1][0], A[2][0]);
