@@ -1,0 +1,292 @@
+#!/usr/bin/env python
+"""bench.py -- the hot path on BASELINE.json's metric: non-rigid LM iterations/s (and triangulated
+points/s, HBM GB/s of the dominant kernel) on a synthetic deformable two-view pair.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--n 1000000] [--k 8]
+
+A step = one arapOptimization call (triangulated pair -> `lm_iters` Levenberg-Marquardt iterations)
+on the workload named in config.workload.  `value` times the refinement with all inputs resident in
+HBM (CUDA events on the library's stream); `e2e` times the same step through the C ABI from host
+buffers (uv -> triangulate -> host; problem + graph upload; rotations; LM; download).  N > 1 runs one
+independent frame-pair problem per rank (no data-path collective): weak scaling.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n", type=int, default=1_000_000)
+    ap.add_argument("--k", type=int, default=8)
+    ap.add_argument("--workload", default="drunkard", choices=["drunkard", "realcolon", "sheet"])
+    ap.add_argument("--lm-iters", type=int, default=0, help="0 = the config's own count")
+    ap.add_argument("--pcg-rtol", type=float, default=1e-10)
+    ap.add_argument("--pcg-max-iters", type=int, default=6000)
+    ap.add_argument("--cpu-sample-n", type=int, default=20000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------------------------- workload
+def make_scene(pkg, args, seed):
+    wl = pkg_workloads(pkg)
+    n_gen = int(args.n * 1.08) + 64
+    if args.workload == "drunkard":
+        sc = wl.tube_scene(n_gen, seed=seed, cam=wl.DRUNKARD_CAM, arap=1.0e7, depth_sigma=0.0003, lm_iters=30)
+        name = "config3: Drunkard.yaml-shaped tube, 1 frame pair"
+    elif args.workload == "realcolon":
+        sc = wl.tube_scene(n_gen, seed=seed, cam=wl.REALCOLON_CAM, arap=0.1, depth_sigma=1e-6, lm_iters=30,
+                           scales=(1.0, 1.0))
+        keep = wl.border_mask_keep(sc["uv1"], 1440, 1080) & wl.border_mask_keep(sc["uv2"], 1440, 1080)
+        for key in ("uv1", "uv2", "d1", "d2"):
+            sc[key] = sc[key][keep]
+        name = "config4: Realcolon.yaml-shaped tube + border mask, 1 frame pair"
+    else:
+        sc = wl.sheet_scene(n_gen, seed=seed)
+        name = "config2: Simulation.yaml sheet, 1 frame pair"
+    sc["name"] = name
+    return sc
+
+
+def pkg_workloads(pkg):
+    import importlib
+    return importlib.import_module(pkg.__name__ + ".workloads")
+
+
+def prepare(pkg, ctx, sc, args):
+    """Triangulate on the GPU, keep exactly n valid correspondences, build the k-NN graph (host, untimed)."""
+    wl = pkg_workloads(pkg)
+    cam = (0, sc["cam"])
+    pair = pkg.make_pair(cam, cam, sc["T1"], sc["T2"])
+    prm = ctx.tri_params("NRSLAM", "FarPoints", 1, sc["min_cos"])
+    X1, X2, valid, cosp, nv = ctx.triangulate(pair, prm, sc["uv1"], sc["uv2"])
+    idx = np.nonzero(valid)[0][: args.n]
+    if len(idx) < args.n:
+        raise RuntimeError(f"only {len(idx)} valid correspondences of {args.n} requested")
+    prob = dict(pair=pair, prm=prm, X1=X1[idx], X2=X2[idx], uv1=sc["uv1"][idx], uv2=sc["uv2"][idx],
+                d1=sc["d1"][idx].astype(np.float64), d2=sc["d2"][idx].astype(np.float64), area=sc["area"])
+    rowptr, col, w = wl.knn_graph(prob["X1"][:, :2].astype(np.float64), args.k)
+    prob.update(rowptr=rowptr, col=col, w=w, ntri=2 * len(idx))
+    # initial depth scales (KeyFrame::setInitialDepthScaleInSimulationImages) from the kept points
+    ctx.tri_upload(pair, prob["uv1"], prob["uv2"], prob["d1"].astype(np.float32), prob["d2"].astype(np.float32))
+    ctx.tri_run(prm)
+    prob["s1"], prob["s2"] = ctx.depth_scale_init(1), ctx.depth_scale_init(2)
+    return prob
+
+
+def upload(ctx, prob, flags=3):
+    ctx.problem_upload(prob["pair"], prob["X1"], prob["X2"], prob["uv1"], prob["uv2"], prob["d1"], prob["d2"],
+                       scale1=prob["s1"], scale2=prob["s2"])
+    ctx.set_graph(prob["rowptr"], prob["col"], prob["w"], prob["area"], prob["ntri"], flags)
+    ctx.compute_rotations()
+
+
+# ---------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows = []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=[])
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+                for nme, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nme)
+            except Exception:
+                pass
+        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None,
+                    reasons=sorted(reasons), samples=len(sm))
+
+
+# ---------------------------------------------------------------------------------------------- CPU arm
+def cpu_reference_run(args, steps, warmup):
+    """The reference's CPU algorithm (oracle port; the reference itself needs g2o/Eigen/Qhull/Open3D and
+    cannot be compiled here) on a bounded sample of the same workload."""
+    from oracle import bench_cpu
+    return bench_cpu.run(args.workload, args.cpu_sample_n, args.k, steps, warmup, args.n)
+
+
+# ---------------------------------------------------------------------------------------------- main
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        res = cpu_reference_run(args, args.steps, args.warmup)
+        line = dict(metric="non-rigid LM iterations/s at 1M correspondences", value=res["value"], unit="LM it/s",
+                    n_gpus=args.gpus, steps=args.steps, warmup=args.warmup, ms_per_step=res["ms_per_step"],
+                    higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64", data="synthetic",
+                    impl="reference", config=res["config"], cpu_baseline=res["cpu_baseline"],
+                    e2e=dict(value=res["value"], unit="LM it/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+                    gpu_launches=0)
+        print(json.dumps(line))
+        return 0
+
+    import __graft_entry__ as g
+    pkg = g.package()
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ctx = pkg.Context(local)
+    sc = make_scene(pkg, args, seed=rank)
+    prob = prepare(pkg, ctx, sc, args)
+    lm_iters = args.lm_iters or sc["lm_iters"]
+    w = pkg.make_weights(**sc["weights"])
+    ctx.set_pcg(rtol=args.pcg_rtol, max_iters=args.pcg_max_iters, check_every=64)
+    upload(ctx, prob)
+    n, E = ctx.problem_size()
+
+    def barrier():
+        if dist is not None:
+            import torch
+            dist.barrier()
+            torch.cuda.synchronize()
+        ctx.synchronize()
+
+    # ---- device-resident arm: inputs already in HBM, one arapOptimization per step
+    for _ in range(args.warmup):
+        ctx.reset_state()
+        ctx.optimize(w, lm_iters)
+    sampler = ClockSampler(local) if rank == 0 else None
+    launches0 = ctx.launch_count()
+    barrier()
+    t0 = time.perf_counter()
+    dev_ms, its, pcg_its, trials, stats_last = 0.0, 0, 0, 0, None
+    for _ in range(args.steps):
+        ctx.reset_state()
+        recs, st = ctx.optimize(w, lm_iters)
+        dev_ms += st.device_ms
+        its += st.iterations
+        pcg_its += st.total_pcg_iters
+        trials += st.total_trials
+        stats_last = st
+    barrier()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    launches = ctx.launch_count() - launches0
+    clocks = sampler.stop() if sampler else None
+
+    # ---- end-to-end arm: host buffers in, host buffers out, every step
+    h2d = (prob["uv1"].nbytes + prob["uv2"].nbytes) * 2 + prob["X1"].nbytes + prob["X2"].nbytes + prob["d1"].nbytes + \
+        prob["d2"].nbytes + prob["rowptr"].nbytes + prob["col"].nbytes + prob["w"].nbytes + 8 * n
+    d2h = 2 * 12 * n * 2 + 5 * n + 2 * 12 * n
+    e2e_ms = 0.0
+    for s in range(1 + args.steps):                       # first pass untimed
+        barrier()
+        t1 = time.perf_counter()
+        ctx.triangulate(prob["pair"], prob["prm"], prob["uv1"], prob["uv2"])
+        upload(ctx, prob)
+        ctx.optimize(w, lm_iters)
+        out = ctx.download(doubles=False)
+        barrier()
+        if s > 0:
+            e2e_ms += (time.perf_counter() - t1) * 1e3
+
+    # ---- kernel roofline (CUDA events on the library's stream) and triangulation throughput
+    kern = ctx.profile_kernels(w, warm=3, reps=20)
+    ctx.tri_upload(prob["pair"], sc["uv1"], sc["uv2"])
+    tri = ctx.profile_triangulate(prob["prm"], warm=3, reps=20)
+    n_tri = len(sc["uv1"])
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    cg_ms = kern["cg_spmv"]["ms"] + kern["cg_update"]["ms"]
+    dom = "cg_spmv" if kern["cg_spmv"]["ms"] >= kern["cg_update"]["ms"] else "cg_update"
+    ach = kern[dom]["bytes"] / (kern[dom]["ms"] * 1e-3) / 1e9
+    roof = dict(bound="hbm", kernel=dom, achieved=ach, peak=peak, unit="GB/s", frac=ach / peak, traffic=None, peak_source=peak_src,
+                kernels={k: dict(ms=v["ms"], gbs=v["bytes"] / (v["ms"] * 1e-3) / 1e9, frac=v["bytes"] / (v["ms"] * 1e-3) / 1e9 / peak)
+                         for k, v in kern.items()},
+                triangulate=dict(ms=tri["ms"], gbs=tri["bytes"] / (tri["ms"] * 1e-3) / 1e9, frac=tri["bytes"] / (tri["ms"] * 1e-3) / 1e9 / peak,
+                                 points_per_s=2.0 * n_tri / (tri["ms"] * 1e-3)))
+
+    # ---- max over ranks, aggregate
+    if dist is not None:
+        import torch
+        t = torch.tensor([dev_ms, wall_ms, e2e_ms], dtype=torch.float64, device=f"cuda:{local}")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_ms, wall_ms, e2e_ms = [float(v) for v in t.tolist()]
+        c = torch.tensor([its, pcg_its, launches], dtype=torch.float64, device=f"cuda:{local}")
+        dist.all_reduce(c, op=dist.ReduceOp.SUM)
+        its, pcg_its, launches = [int(v) for v in c.tolist()]
+    if rank == 0:
+        step_ms = max(dev_ms, 0.0) / args.steps
+        value = its / (dev_ms * 1e-3)
+        e2e_val = (lm_iters * args.steps * world) / (e2e_ms * 1e-3)
+        cpu = None
+        if not args.no_cpu_baseline and world == 1:
+            try:
+                r = cpu_reference_run(args, 1, 0)
+                cpu = r["cpu_baseline"]
+            except Exception as ex:      # the baseline is a report, never a gate
+                cpu = dict(value=None, unit="LM it/s", cores=1, kind="port", sample=f"failed: {ex}")
+        line = dict(metric="non-rigid LM iterations/s at 1M correspondences", value=value, unit="LM it/s", n_gpus=world,
+                    steps=args.steps, warmup=args.warmup, ms_per_step=step_ms, higher_is_better=True, scaling="weak",
+                    vs_baseline=None, dtype="f64", data="synthetic",
+                    config=dict(workload=sc["name"], correspondences=n, directed_edges=E, k=args.k, lm_iters_per_step=lm_iters,
+                                pcg_rtol=args.pcg_rtol, pcg_iters_per_lm_iter=pcg_its / max(1, its),
+                                lm_trials_per_step=trials / args.steps, l2="working set ~1.1 GB/GPU, larger than the 126 MB L2",
+                                frame_pairs=world, parallelism=f"{world} independent frame pairs, one per GPU"),
+                    e2e=dict(value=e2e_val, unit="LM it/s", h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(d2h),
+                             ms_per_step=e2e_ms / args.steps),
+                    gpu_launches=int(launches), clocks=clocks, roofline=roof, cpu_baseline=cpu,
+                    triangulated_points_per_s=roof["triangulate"]["points_per_s"],
+                    cg_iteration_ms=cg_ms, wall_ms_per_step=wall_ms / args.steps)
+        print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+    ctx.close()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -189,6 +189,19 @@ int dsc_debug_linearize(dsc_ctx* ctx, const dsc_weights* w, double* b, double* h
 /* y = (H + lambda I) x with the matrix-free operator the PCG uses -- test hook */
 int dsc_debug_matvec(dsc_ctx* ctx, const dsc_weights* w, double lambda, const double* x, double* y);
 
+/* Per-kernel device times for the roofline: each hot kernel is launched `reps` times back to back on
+ * the current state (after `warm` untimed launches) between two CUDA events on the context's stream.
+ * ms[] receives the average launch duration in milliseconds, indexed by DSC_K_*; bytes[] the algorithmic
+ * bytes one launch moves.  The solver state (points, vectors) is left unchanged
+ * except for the CG scratch vectors. */
+enum { DSC_K_SPMV = 0, DSC_K_UPDATE = 1, DSC_K_LINEARIZE = 2, DSC_K_COST = 3, DSC_K_PRECOND = 4,
+       DSC_K_APPLY = 5, DSC_K_ROTATIONS = 6, DSC_K_COUNT = 7 };
+int dsc_profile_kernels(dsc_ctx* ctx, const dsc_weights* w, int warm, int reps, double* ms, double* bytes);
+/* same for the triangulation kernel (needs dsc_tri_upload first) */
+int dsc_profile_triangulate(dsc_ctx* ctx, const dsc_tri_params* prm, int warm, int reps, double* ms, double* bytes);
+/* problem size as seen by the library: n correspondences, E directed edges */
+int dsc_problem_size(const dsc_ctx* ctx, long long* n, long long* n_edges);
+
 #ifdef __cplusplus
 }
 #endif

@@ -24,8 +24,9 @@ EXPORTS = [
     "dsc_triangulate", "dsc_tri_upload", "dsc_tri_run", "dsc_tri_download", "dsc_depth_scale_init",
     "dsc_problem_upload", "dsc_set_graph", "dsc_compute_rotations", "dsc_get_rotations", "dsc_set_rotations",
     "dsc_reset_state", "dsc_set_pcg", "dsc_cost", "dsc_optimize", "dsc_download", "dsc_pixel_sigma",
-    "dsc_debug_linearize", "dsc_debug_matvec",
+    "dsc_debug_linearize", "dsc_debug_matvec", "dsc_profile_kernels", "dsc_profile_triangulate", "dsc_problem_size",
 ]
+KERNEL_NAMES = ["cg_spmv", "cg_update", "linearize", "cost", "precond", "apply_update", "rotations"]
 
 
 class Camera(C.Structure):
@@ -305,3 +306,21 @@ class Context:
         y = np.empty_like(x)
         self._ck(self.lib.dsc_debug_matvec(self.h, C.byref(w), C.c_double(lam), _fp(x), _fp(y)))
         return y
+
+    def profile_kernels(self, w, warm=3, reps=20):
+        ms = (C.c_double * 7)()
+        by = (C.c_double * 7)()
+        self._ck(self.lib.dsc_profile_kernels(self.h, C.byref(w), int(warm), int(reps), ms, by))
+        return {k: dict(ms=ms[i], bytes=by[i]) for i, k in enumerate(KERNEL_NAMES)}
+
+    def profile_triangulate(self, prm, warm=3, reps=20):
+        ms = C.c_double()
+        by = C.c_double()
+        self._ck(self.lib.dsc_profile_triangulate(self.h, C.byref(prm), int(warm), int(reps), C.byref(ms), C.byref(by)))
+        return dict(ms=ms.value, bytes=by.value)
+
+    def problem_size(self):
+        n = C.c_longlong()
+        e = C.c_longlong()
+        self._ck(self.lib.dsc_problem_size(self.h, C.byref(n), C.byref(e)))
+        return n.value, e.value

@@ -854,3 +854,114 @@ extern "C" int dsc_debug_matvec(dsc_ctx* ctx, const dsc_weights* w, double lambd
     }
     return DSC_OK;
 }
+
+// ------------------------------------------------------------------ per-kernel timing (roofline)
+extern "C" int dsc_problem_size(const dsc_ctx* ctx, long long* n, long long* n_edges) {
+    if (!ctx) return DSC_ERR_INVALID_ARG;
+    if (n) *n = ctx->n;
+    if (n_edges) *n_edges = ctx->E;
+    return DSC_OK;
+}
+
+extern "C" int dsc_profile_kernels(dsc_ctx* ctx, const dsc_weights* w, int warm, int reps, double* ms, double* bytes) {
+    int s = ready(ctx, w);
+    if (s) return s;
+    if (!ms || reps < 1 || warm < 0) return DSC_ERR_INVALID_ARG;
+    CK(cudaSetDevice(ctx->device));
+    int n = ctx->n;
+    if (n == 0) return fail(ctx, DSC_ERR_STATE, "empty problem");
+    WeightsDev W = make_weights(ctx, w);
+    LinGlobal hl;
+    s = run_linearize(ctx, W, &hl);
+    if (s) return s;
+    double lambda = 1e-5 * hl.maxdiag;
+    CgVecs v = make_vecs(ctx);
+    double* Ginv = ctx->small + 48;
+    int nbv = grid_threads(ctx, n), nbs = grid_groups(ctx, n);
+    CK(cudaMemsetAsync(ctx->errflag, 0, sizeof(int), ctx->stream));
+    precond_kernel<<<nbv, kThreads, 0, ctx->stream>>>(n, ctx->D, lambda, ctx->lin, ctx->Minv, Ginv, ctx->errflag);
+    cg_init_kernel<<<nbv, kThreads, 0, ctx->stream>>>(n, ctx->b, ctx->lin, ctx->Minv, Ginv, v, ctx->gpart[0], ctx->ctl);
+    ctx->launches += 2;
+    double N = (double)n, E = (double)ctx->E;
+    double by[DSC_K_COUNT];
+    by[DSC_K_SPMV] = 324.0 * N + 12.0 * E;        // P Q z U rowptr | col w | write w
+    by[DSC_K_UPDATE] = 696.0 * N;                 // read z w p s x r Minv, write p s x r z
+    by[DSC_K_LINEARIZE] = 508.0 * N + 12.0 * E;   // P Q uv dm isg rowptr | col w | write b D U
+    by[DSC_K_COST] = 140.0 * N + 12.0 * E;        // P Q uv dm isg rowptr | col w
+    by[DSC_K_PRECOND] = 336.0 * N;                // D -> Minv
+    by[DSC_K_APPLY] = 224.0 * N;                  // P x b -> Ptrial
+    by[DSC_K_ROTATIONS] = 100.0 * N + 12.0 * E;   // P rowptr | col w | write Q
+    auto time_it = [&](int which, auto&& launch) -> int {
+        for (int i = 0; i < warm; ++i) launch();
+        CK(cudaEventRecord(ctx->evA, ctx->stream));
+        for (int i = 0; i < reps; ++i) launch();
+        CK(cudaEventRecord(ctx->evB, ctx->stream));
+        CK(cudaEventSynchronize(ctx->evB));
+        CK(cudaGetLastError());
+        ms[which] = ev_ms(ctx->evA, ctx->evB) / reps;
+        ctx->launches += warm + reps;
+        return DSC_OK;
+    };
+    s = time_it(DSC_K_SPMV, [&]() {
+        cg_spmv_kernel<<<nbs, kThreads, 0, ctx->stream>>>(n, ctx->P, ctx->Q, ctx->U, ctx->rowptr, ctx->col, ctx->wgt, ctx->Gcur, ctx->pair, W,
+                                                         lambda, v.z, v.zg, v.w, ctx->dpart, ctx->bpart, ctx->lin, nullptr);
+    });
+    if (s) return s;
+    // update: run real CG steps (first=1 keeps beta = 0, so the recurrences stay finite for any reps)
+    s = time_it(DSC_K_UPDATE, [&]() {
+        CgControl z{};
+        cudaMemcpyAsync(ctx->ctl, &z, sizeof(CgControl), cudaMemcpyHostToDevice, ctx->stream);
+        cg_update_kernel<<<nbv, kThreads, 0, ctx->stream>>>(n, 0, 1, ctx->Minv, Ginv, ctx->lin, lambda, v, ctx->gpart[0], ctx->gpart[1],
+                                                           ctx->dpart, ctx->bpart, nbs, ctx->ctl, 0.0);
+    });
+    if (s) return s;
+    s = time_it(DSC_K_LINEARIZE, [&]() {
+        linearize_kernel<<<nbs, kThreads, 0, ctx->stream>>>(n, ctx->P, ctx->Q, ctx->uv, ctx->dm, ctx->isg, ctx->rowptr, ctx->col,
+                                                           ctx->wgt, ctx->Gcur, ctx->pair, W, ctx->b, ctx->D, ctx->U, ctx->part);
+    });
+    if (s) return s;
+    s = time_it(DSC_K_COST, [&]() {
+        cost_kernel<<<nbs, kThreads, 0, ctx->stream>>>(n, ctx->P, ctx->Q, ctx->uv, ctx->dm, ctx->isg, ctx->rowptr, ctx->col, ctx->wgt,
+                                                      ctx->Gcur, ctx->pair, W, ctx->part);
+    });
+    if (s) return s;
+    s = time_it(DSC_K_PRECOND, [&]() {
+        precond_kernel<<<nbv, kThreads, 0, ctx->stream>>>(n, ctx->D, lambda, ctx->lin, ctx->Minv, Ginv, ctx->errflag);
+    });
+    if (s) return s;
+    s = time_it(DSC_K_APPLY, [&]() {
+        apply_update_kernel<<<nbv, kThreads, 0, ctx->stream>>>(n, ctx->P, v.x, v.xg, ctx->b, ctx->lin, lambda, ctx->Gcur,
+                                                              ctx->Ptrial, ctx->Gtrial, ctx->gpart[0]);
+    });
+    if (s) return s;
+    double* Qtmp = ctx->vec[3];                    // scratch: do not disturb the real rotations
+    s = time_it(DSC_K_ROTATIONS, [&]() {
+        rotations_kernel<<<nbs, kThreads, 0, ctx->stream>>>(n, ctx->P, ctx->rowptr, ctx->col, ctx->wgt, Qtmp);
+    });
+    if (s) return s;
+    if (bytes) for (int k = 0; k < DSC_K_COUNT; ++k) bytes[k] = by[k];
+    return DSC_OK;
+}
+
+extern "C" int dsc_profile_triangulate(dsc_ctx* ctx, const dsc_tri_params* prm, int warm, int reps, double* ms, double* bytes) {
+    if (!ctx || !prm || !ms || reps < 1 || warm < 0) return DSC_ERR_INVALID_ARG;
+    if (ctx->tn == 0) return fail(ctx, DSC_ERR_STATE, "dsc_tri_upload first");
+    CK(cudaSetDevice(ctx->device));
+    TriParams tp{prm->method, prm->location, prm->gate, prm->min_cos, prm->depth_limit, prm->check_reproj};
+    int nb = grid_threads(ctx, ctx->tn);
+    auto launch = [&]() {
+        triangulate_kernel<<<nb, kThreads, 0, ctx->stream>>>(ctx->tn, ctx->t_uv1, ctx->t_uv2, ctx->t_d1, ctx->t_d2, ctx->tpair, tp,
+                                                            ctx->t_X1, ctx->t_X2, ctx->t_valid, ctx->t_cos);
+    };
+    for (int i = 0; i < warm; ++i) launch();
+    CK(cudaEventRecord(ctx->evA, ctx->stream));
+    for (int i = 0; i < reps; ++i) launch();
+    CK(cudaEventRecord(ctx->evB, ctx->stream));
+    CK(cudaEventSynchronize(ctx->evB));
+    CK(cudaGetLastError());
+    ctx->launches += warm + reps;
+    ctx->t_done = true;
+    *ms = ev_ms(ctx->evA, ctx->evB) / reps;
+    if (bytes) *bytes = (double)ctx->tn * (16.0 + (prm->method == DSC_TRI_DEPTH ? 8.0 : 0.0) + 24.0 + 1.0 + 4.0);
+    return DSC_OK;
+}
