@@ -57,6 +57,7 @@ struct dsc_ctx {
     float2* isg = nullptr;
     int *rowptr = nullptr, *col = nullptr;
     double* wgt = nullptr;
+    double* Je = nullptr;                 // per directed edge {u, m, g}
     double *b = nullptr, *D = nullptr, *U = nullptr, *Minv = nullptr;
     double* vec[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // x r z w p s
     double* small = nullptr;              // 6 x 8 global vectors + Ginv(64)
@@ -111,6 +112,11 @@ void dev_free(T*& p) { if (p) { cudaFree(p); p = nullptr; } }
 int grid_threads(const dsc_ctx* c, long long n) {           // thread-per-item kernels
     long long nb = (n + kThreads - 1) / kThreads;
     long long cap = (long long)c->sms * 8;
+    return (int)std::max(1LL, std::min(nb, cap));
+}
+int grid_spmv(const dsc_ctx* c, long long n) {              // one block per kTile correspondences, 2 resident per SM
+    long long nb = (n + kTile - 1) / kTile;
+    long long cap = (long long)c->sms * 2;
     return (int)std::max(1LL, std::min(nb, cap));
 }
 int grid_groups(const dsc_ctx* c, long long n) {            // 8-lanes-per-item kernels
@@ -215,7 +221,7 @@ extern "C" void dsc_destroy(dsc_ctx* ctx) {
     dev_free(ctx->X1f); dev_free(ctx->X2f); dev_free(ctx->d_perm);
     dev_free(ctx->P); dev_free(ctx->Ptrial); dev_free(ctx->P0); dev_free(ctx->Q);
     dev_free(ctx->uv); dev_free(ctx->dm); dev_free(ctx->isg);
-    dev_free(ctx->rowptr); dev_free(ctx->col); dev_free(ctx->wgt);
+    dev_free(ctx->rowptr); dev_free(ctx->col); dev_free(ctx->wgt); dev_free(ctx->Je);
     dev_free(ctx->b); dev_free(ctx->D); dev_free(ctx->U); dev_free(ctx->Minv);
     for (auto& v : ctx->vec) dev_free(v);
     dev_free(ctx->small); dev_free(ctx->Gcur); dev_free(ctx->Gtrial); dev_free(ctx->lin); dev_free(ctx->ctl);
@@ -481,7 +487,7 @@ extern "C" int dsc_set_graph(dsc_ctx* ctx, int n, const int32_t* rowptr, const i
         for (auto& pr2 : row) { cl[o] = pr2.first; ww[o] = pr2.second; ++o; }
     }
     if (E > ctx->ecap) {
-        CK(dev_alloc(ctx->col, (size_t)E)); CK(dev_alloc(ctx->wgt, (size_t)E));
+        CK(dev_alloc(ctx->col, (size_t)E)); CK(dev_alloc(ctx->wgt, (size_t)E)); CK(dev_alloc(ctx->Je, 9 * (size_t)E));
         ctx->ecap = E;
     }
     ctx->E = E;
@@ -600,8 +606,8 @@ static CgVecs make_vecs(dsc_ctx* ctx) {
 
 static int run_linearize(dsc_ctx* ctx, const WeightsDev& W, LinGlobal* hlin) {
     int nb = grid_groups(ctx, ctx->n);
-    linearize_kernel<<<nb, kThreads, 0, ctx->stream>>>(ctx->n, ctx->P, ctx->Q, ctx->uv, ctx->dm, ctx->isg, ctx->rowptr, ctx->col,
-                                                      ctx->wgt, ctx->Gcur, ctx->pair, W, ctx->b, ctx->D, ctx->U, ctx->part);
+    linearize_kernel<<<nb, kThreads, 0, ctx->stream>>>(ctx->n, (size_t)ctx->E, ctx->P, ctx->Q, ctx->uv, ctx->dm, ctx->isg, ctx->rowptr, ctx->col,
+                                                      ctx->wgt, ctx->Gcur, ctx->pair, W, ctx->b, ctx->D, ctx->U, ctx->Je, ctx->part);
     finalize_linearize_kernel<<<1, kThreads, 0, ctx->stream>>>(nb, ctx->part, ctx->lin);
     ctx->launches += 2;
     CK(cudaGetLastError());
@@ -614,13 +620,13 @@ static int run_linearize(dsc_ctx* ctx, const WeightsDev& W, LinGlobal* hlin) {
 static int run_pcg(dsc_ctx* ctx, const WeightsDev& W, double lambda, int* iters_out) {
     int n = ctx->n;
     int nbv = grid_threads(ctx, (long long)n);
-    int nbs = grid_groups(ctx, n);
+    int nbs = grid_spmv(ctx, n);
     CgVecs v = make_vecs(ctx);
     double* Ginv = ctx->small + 48;
     CK(cudaMemsetAsync(ctx->errflag, 0, sizeof(int), ctx->stream));
     precond_kernel<<<nbv, kThreads, 0, ctx->stream>>>(n, ctx->D, lambda, ctx->lin, ctx->Minv, Ginv, ctx->errflag);
     cg_init_kernel<<<nbv, kThreads, 0, ctx->stream>>>(n, ctx->b, ctx->lin, ctx->Minv, Ginv, v, ctx->gpart[0], ctx->ctl);
-    cg_spmv_kernel<<<nbs, kThreads, 0, ctx->stream>>>(n, ctx->P, ctx->Q, ctx->U, ctx->rowptr, ctx->col, ctx->wgt, ctx->Gcur, ctx->pair, W,
+    cg_spmv_kernel<<<nbs, kThreads, 0, ctx->stream>>>(n, (size_t)ctx->E, ctx->P, ctx->Je, ctx->U, ctx->rowptr, ctx->col, ctx->Gcur, ctx->pair, W,
                                                      lambda, v.z, v.zg, v.w, ctx->dpart, ctx->bpart, ctx->lin, ctx->ctl);
     ctx->launches += 3;
     double rtol2 = ctx->pcg.rtol * ctx->pcg.rtol;
@@ -632,7 +638,7 @@ static int run_pcg(dsc_ctx* ctx, const WeightsDev& W, double lambda, int* iters_
             cg_update_kernel<<<nbv, kThreads, 0, ctx->stream>>>(n, k & 1, k == 0 ? 1 : 0, ctx->Minv, Ginv, ctx->lin, lambda, v,
                                                                ctx->gpart[k & 1], ctx->gpart[(k + 1) & 1], ctx->dpart, ctx->bpart, nbs,
                                                                ctx->ctl, rtol2);
-            cg_spmv_kernel<<<nbs, kThreads, 0, ctx->stream>>>(n, ctx->P, ctx->Q, ctx->U, ctx->rowptr, ctx->col, ctx->wgt, ctx->Gcur, ctx->pair, W,
+            cg_spmv_kernel<<<nbs, kThreads, 0, ctx->stream>>>(n, (size_t)ctx->E, ctx->P, ctx->Je, ctx->U, ctx->rowptr, ctx->col, ctx->Gcur, ctx->pair, W,
                                                              lambda, v.z, v.zg, v.w, ctx->dpart, ctx->bpart, ctx->lin, ctx->ctl);
             ctx->launches += 2;
         }
@@ -834,8 +840,8 @@ extern "C" int dsc_debug_matvec(dsc_ctx* ctx, const dsc_weights* w, double lambd
     }
     if (n) CK(cudaMemcpyAsync(v.z, hz.data(), sizeof(double) * 6 * n, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(v.zg, x, sizeof(double) * 8, cudaMemcpyHostToDevice, ctx->stream));
-    int nbs = grid_groups(ctx, n);
-    cg_spmv_kernel<<<nbs, kThreads, 0, ctx->stream>>>(n, ctx->P, ctx->Q, ctx->U, ctx->rowptr, ctx->col, ctx->wgt, ctx->Gcur, ctx->pair, W,
+    int nbs = grid_spmv(ctx, n);
+    cg_spmv_kernel<<<nbs, kThreads, 0, ctx->stream>>>(n, (size_t)ctx->E, ctx->P, ctx->Je, ctx->U, ctx->rowptr, ctx->col, ctx->Gcur, ctx->pair, W,
                                                      lambda, v.z, v.zg, v.w, ctx->dpart, ctx->bpart, ctx->lin, nullptr);
     ctx->launches++;
     CK(cudaGetLastError());
@@ -877,16 +883,16 @@ extern "C" int dsc_profile_kernels(dsc_ctx* ctx, const dsc_weights* w, int warm,
     double lambda = 1e-5 * hl.maxdiag;
     CgVecs v = make_vecs(ctx);
     double* Ginv = ctx->small + 48;
-    int nbv = grid_threads(ctx, n), nbs = grid_groups(ctx, n);
+    int nbv = grid_threads(ctx, n), nbs = grid_groups(ctx, n), nbp = grid_spmv(ctx, n);
     CK(cudaMemsetAsync(ctx->errflag, 0, sizeof(int), ctx->stream));
     precond_kernel<<<nbv, kThreads, 0, ctx->stream>>>(n, ctx->D, lambda, ctx->lin, ctx->Minv, Ginv, ctx->errflag);
     cg_init_kernel<<<nbv, kThreads, 0, ctx->stream>>>(n, ctx->b, ctx->lin, ctx->Minv, Ginv, v, ctx->gpart[0], ctx->ctl);
     ctx->launches += 2;
     double N = (double)n, E = (double)ctx->E;
     double by[DSC_K_COUNT];
-    by[DSC_K_SPMV] = 324.0 * N + 12.0 * E;        // P Q z U rowptr | col w | write w
+    by[DSC_K_SPMV] = 260.0 * N + 76.0 * E;        // X1(32) z(48) U(128) rowptr(4) | col(4) Je(72) | write w(48)
     by[DSC_K_UPDATE] = 696.0 * N;                 // read z w p s x r Minv, write p s x r z
-    by[DSC_K_LINEARIZE] = 508.0 * N + 12.0 * E;   // P Q uv dm isg rowptr | col w | write b D U
+    by[DSC_K_LINEARIZE] = 508.0 * N + 84.0 * E;   // P Q uv dm isg rowptr | col w | write b D U Je
     by[DSC_K_COST] = 140.0 * N + 12.0 * E;        // P Q uv dm isg rowptr | col w
     by[DSC_K_PRECOND] = 336.0 * N;                // D -> Minv
     by[DSC_K_APPLY] = 224.0 * N;                  // P x b -> Ptrial
@@ -903,7 +909,7 @@ extern "C" int dsc_profile_kernels(dsc_ctx* ctx, const dsc_weights* w, int warm,
         return DSC_OK;
     };
     s = time_it(DSC_K_SPMV, [&]() {
-        cg_spmv_kernel<<<nbs, kThreads, 0, ctx->stream>>>(n, ctx->P, ctx->Q, ctx->U, ctx->rowptr, ctx->col, ctx->wgt, ctx->Gcur, ctx->pair, W,
+        cg_spmv_kernel<<<nbp, kThreads, 0, ctx->stream>>>(n, (size_t)ctx->E, ctx->P, ctx->Je, ctx->U, ctx->rowptr, ctx->col, ctx->Gcur, ctx->pair, W,
                                                          lambda, v.z, v.zg, v.w, ctx->dpart, ctx->bpart, ctx->lin, nullptr);
     });
     if (s) return s;
@@ -912,12 +918,12 @@ extern "C" int dsc_profile_kernels(dsc_ctx* ctx, const dsc_weights* w, int warm,
         CgControl z{};
         cudaMemcpyAsync(ctx->ctl, &z, sizeof(CgControl), cudaMemcpyHostToDevice, ctx->stream);
         cg_update_kernel<<<nbv, kThreads, 0, ctx->stream>>>(n, 0, 1, ctx->Minv, Ginv, ctx->lin, lambda, v, ctx->gpart[0], ctx->gpart[1],
-                                                           ctx->dpart, ctx->bpart, nbs, ctx->ctl, 0.0);
+                                                           ctx->dpart, ctx->bpart, nbp, ctx->ctl, 0.0);
     });
     if (s) return s;
     s = time_it(DSC_K_LINEARIZE, [&]() {
-        linearize_kernel<<<nbs, kThreads, 0, ctx->stream>>>(n, ctx->P, ctx->Q, ctx->uv, ctx->dm, ctx->isg, ctx->rowptr, ctx->col,
-                                                           ctx->wgt, ctx->Gcur, ctx->pair, W, ctx->b, ctx->D, ctx->U, ctx->part);
+        linearize_kernel<<<nbs, kThreads, 0, ctx->stream>>>(n, (size_t)ctx->E, ctx->P, ctx->Q, ctx->uv, ctx->dm, ctx->isg, ctx->rowptr, ctx->col,
+                                                           ctx->wgt, ctx->Gcur, ctx->pair, W, ctx->b, ctx->D, ctx->U, ctx->Je, ctx->part);
     });
     if (s) return s;
     s = time_it(DSC_K_COST, [&]() {

@@ -2,12 +2,14 @@
 //
 // Layout in HBM (n correspondences in the library's internal, space-filling-curve order; E directed
 // neighbour edges in CSR):
-//   P      double[n][8]  {X1.xyz, 0, X2.xyz, 0}      64 B records: one neighbour gather = 2 aligned sectors
+//   P      double[2][n][4] {X1.xyz, 0} plane then {X2.xyz, 0} plane: 32 B records, one neighbour gather of a
+//                        point = 1 aligned sector (LDG.E.256); the PCG operator only touches the X1 plane
 //   Q      double[n][4]  per-vertex ARAP rotation as unit quaternion (computeR)   32 B = 1 sector
 //   uv     float4[n]     {u1, v1, u2, v2}
 //   dm     double2[n]    depth measurements (KF1, KF2)
 //   isg    float2[n]     KeyFrame::getInvSigma2(octave) of the two observations
 //   U      double[n][16] unary Hessian record {U1[6], U2[6], kd1, kd2, 0, 0}      128 B = 1 line
+//   Je     double[9][E]  per directed edge {u, m, g}: the ARAP Jacobian record streamed by the PCG operator
 //   D      double[n][21] packed upper 6x6 diagonal block of H (block-Jacobi preconditioner source)
 //   Minv   double[n][21] packed inverse of D + lambda I
 //   vectors b, x, r, z, w, p, s: double[n][6] {d/dX1, d/dX2}; the 8 global unknowns
@@ -129,9 +131,9 @@ DSC_D double4 ldg256(const double4* p) {
     return r;
 }
 struct P8 { D3 a, b; };                             // X1, X2 of one correspondence
-DSC_D P8 load_P(const double* __restrict__ P, int i) {
-    const double4* p = reinterpret_cast<const double4*>(P) + 2 * (size_t)i;
-    double4 u = ldg256(p), v = ldg256(p + 1);
+DSC_D P8 load_P(const double* __restrict__ P, int n, int i) {
+    const double4* p = reinterpret_cast<const double4*>(P);
+    double4 u = ldg256(p + (size_t)i), v = ldg256(p + (size_t)n + (size_t)i);
     P8 r; r.a = d3(u.x, u.y, u.z); r.b = d3(v.x, v.y, v.z);
     return r;
 }
@@ -153,7 +155,7 @@ DSC_D void load_q(const double* __restrict__ Q, int i, double* q) {
 // One directed ARAP edge (i -> j).  EdgeARAP::computeError, g2oTypes.h:310-339:
 //   e = w (|(d2 - Ri d1)/A|^2 + |(-d2 + Rj d1)/A|^2) + |Rg (X2i + X2j) - 2 t - (X1i + X1j)|^2
 // and its analytic gradient (the reference differentiates numerically, g2o central differences).
-struct ArapGrad { D3 gi1, gi2, gj1, gj2, gw, gv; double e; };
+struct ArapGrad { D3 gi1, gi2, gj1, gj2, gw, gv; D3 u, m, g; double e; };
 template <bool kGrad>
 DSC_D void arap_edge(const P8& Pi, const P8& Pj, const double* qi, const double* qj, double w, double inv_area,
                      const Globals& G, ArapGrad& o) {
@@ -177,6 +179,7 @@ DSC_D void arap_edge(const P8& Pi, const P8& Pj, const double* qi, const double*
         o.gj2 = v2 - u;
         o.gw = 2.0 * cross(qt, g);
         o.gv = d3(-4.0 * g.x, -4.0 * g.y, -4.0 * g.z);
+        o.u = u; o.m = m; o.g = g;
     }
 }
 
@@ -337,9 +340,9 @@ init_state_kernel(int n, const float* __restrict__ X1, const float* __restrict__
                   double* __restrict__ P) {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         size_t s = perm ? (size_t)perm[i] : (size_t)i;
-        double4* p = reinterpret_cast<double4*>(P) + 2 * (size_t)i;
-        p[0] = make_double4((double)X1[3 * s], (double)X1[3 * s + 1], (double)X1[3 * s + 2], 0.0);
-        p[1] = make_double4((double)X2[3 * s], (double)X2[3 * s + 1], (double)X2[3 * s + 2], 0.0);
+        double4* p = reinterpret_cast<double4*>(P);
+        p[i] = make_double4((double)X1[3 * s], (double)X1[3 * s + 1], (double)X1[3 * s + 2], 0.0);
+        p[(size_t)n + i] = make_double4((double)X2[3 * s], (double)X2[3 * s + 1], (double)X2[3 * s + 2], 0.0);
     }
 }
 
@@ -358,11 +361,11 @@ rotations_kernel(int n, const double* __restrict__ P, const int* __restrict__ ro
         int e0 = 0, e1 = 0;
         if (act) {
             e0 = rowptr[i]; e1 = rowptr[i + 1];
-            P8 Pi = load_P(P, i);
+            P8 Pi = load_P(P, n, i);
             for (int e = e0 + lane; e < e1; e += kLanes) {
                 int j = col[e];
                 double w = wgt[e];
-                P8 Pj = load_P(P, j);
+                P8 Pj = load_P(P, n, j);
                 D3 d1 = Pi.a - Pj.a, d2 = Pi.b - Pj.b;
                 S[0] += w * d1.x * d2.x; S[1] += w * d1.x * d2.y; S[2] += w * d1.x * d2.z;
                 S[3] += w * d1.y * d2.x; S[4] += w * d1.y * d2.y; S[5] += w * d1.y * d2.z;
@@ -401,14 +404,14 @@ cost_kernel(int n, const double* __restrict__ P, const double* __restrict__ Q, c
     for (int rd = blockIdx.x; rd < nround; rd += gridDim.x) {
         int i = rd * kGroups + threadIdx.x / kLanes;
         if (i >= n) continue;
-        P8 Pi = load_P(P, i);
+        P8 Pi = load_P(P, n, i);
         double qi[4];
         load_q(Q, i, qi);
         int e1 = rowptr[i + 1];
         double ea = 0.0;
         for (int e = rowptr[i] + lane; e < e1; e += kLanes) {
             int j = col[e];
-            P8 Pj = load_P(P, j);
+            P8 Pj = load_P(P, n, j);
             double qj[4];
             load_q(Q, j, qj);
             ArapGrad g;
@@ -448,11 +451,12 @@ cost_kernel(int n, const double* __restrict__ P, const double* __restrict__ Q, c
 // Per block: partial sums of chi2[3], max diagonal, global gradient bg[8], global block C (T-T 21 packed, s1, s2).
 constexpr int kLinPart = 3 + 1 + 8 + 21 + 2;   // 35
 __global__ void __launch_bounds__(kThreads)
-linearize_kernel(int n, const double* __restrict__ P, const double* __restrict__ Q, const float4* __restrict__ uv,
+linearize_kernel(int n, size_t nE, const double* __restrict__ P, const double* __restrict__ Q, const float4* __restrict__ uv,
                  const double2* __restrict__ dm, const float2* __restrict__ isg, const int* __restrict__ rowptr,
                  const int* __restrict__ col, const double* __restrict__ wgt, const Globals* __restrict__ Gp,
                  const __grid_constant__ PairDev pr, const __grid_constant__ WeightsDev W,
-                 double* __restrict__ b, double* __restrict__ D, double* __restrict__ U, double* __restrict__ part) {
+                 double* __restrict__ b, double* __restrict__ D, double* __restrict__ U, double* __restrict__ Je,
+                 double* __restrict__ part) {
     __shared__ double sm[kLinPart * (kThreads / 32)];
     __shared__ Globals G;
     if (threadIdx.x == 0) G = *Gp;
@@ -473,17 +477,22 @@ linearize_kernel(int n, const double* __restrict__ P, const double* __restrict__
         for (int k = 0; k < 21; ++k) Dk[k] = 0.0;
         P8 Pi;
         if (act) {
-            Pi = load_P(P, i);
+            Pi = load_P(P, n, i);
             double qi[4];
             load_q(Q, i, qi);
             int e1 = rowptr[i + 1];
             for (int e = rowptr[i] + lane; e < e1; e += kLanes) {
                 int j = col[e];
-                P8 Pj = load_P(P, j);
+                P8 Pj = load_P(P, n, j);
                 double qj[4];
                 load_q(Q, j, qj);
                 ArapGrad g;
                 arap_edge<true>(Pi, Pj, qi, qj, wgt[e], W.inv_area, G, g);
+                {   // per-edge Jacobian record streamed by the PCG operator: u, m, g (72 B)
+                    double* je = Je + (size_t)e;            // 9 planes of nE doubles: coalesced across the lanes
+                    je[0] = g.u.x; je[nE] = g.u.y; je[2 * nE] = g.u.z; je[3 * nE] = g.m.x; je[4 * nE] = g.m.y; je[5 * nE] = g.m.z;
+                    je[6 * nE] = g.g.x; je[7 * nE] = g.g.y; je[8 * nE] = g.g.z;
+                }
                 double gi[6] = {g.gi1.x, g.gi1.y, g.gi1.z, g.gi2.x, g.gi2.y, g.gi2.z};
                 double gt[6] = {g.gw.x, g.gw.y, g.gw.z, g.gv.x, g.gv.y, g.gv.z};
                 double we = W.arap_info * g.e;
@@ -732,95 +741,152 @@ cg_init_kernel(int n, const double* __restrict__ b, const LinGlobal* __restrict_
     if (threadIdx.x == 0) gpart[blockIdx.x] = g[0];
 }
 
-// w = (H + lambda I) z, matrix-free.  dpart[grid]: partial z.w (global rows included), bpart[grid][8]: partial
-// global rows of H z (T_g rows from the ARAP edges, s1/s2 rows from the depth edges).
-__global__ void __launch_bounds__(kThreads)
-cg_spmv_kernel(int n, const double* __restrict__ P, const double* __restrict__ Q, const double* __restrict__ U,
-               const int* __restrict__ rowptr, const int* __restrict__ col, const double* __restrict__ wgt,
+// w = (H + lambda I) z.  The ARAP part streams the per-edge Jacobian record Je = {u, m, g} written by
+// linearize_kernel (gradient of e w.r.t. X1i,X2i,X1j,X2j,T_g is  -m-2g | u+2Rg^T g | m-2g | -u+2Rg^T g |
+// [2 (X1i+X1j) x g, -4 g]), so with dz1 = z1i-z1j, dz2 = z2i-z2j, sz1 = z1i+z1j, sz2 = z2i+z2j:
+//     s_e = u.dz2 - m.dz1 + 2 g.(Rg sz2 - sz1 + z_w x (X1i+X1j) - 2 z_v)
+//     Am = sum_e 2W s_e m, Ag = sum_e 2W s_e g, Au = sum_e 2W s_e u          (per vertex, over its CSR row)
+//     w_i1 = -Am - 2 Ag,   w_i2 = Au + 2 Rg^T Ag
+//     T_g rows: the directed twins carry the same s_e and g, so  w_w = 2 sum_i X1i x Ag_i,  w_v = -2 sum_i Ag_i.
+// A block owns a tile of kTile consecutive correspondences (space-filling-curve order): their z, X1 and
+// row pointers are staged in shared memory with coalesced loads, and a neighbour inside the tile is served
+// from shared memory; only halo neighbours are gathered from L2.  dpart[grid]: partial z.w (global rows
+// included), bpart[grid][8]: partial global rows (T_g from the ARAP edges, s1/s2 from the depth edges).
+constexpr int kTile = 512;
+__global__ void __launch_bounds__(kThreads, 2)
+cg_spmv_kernel(int n, size_t nE, const double* __restrict__ P, const double* __restrict__ Je, const double* __restrict__ U,
+               const int* __restrict__ rowptr, const int* __restrict__ col,
                const Globals* __restrict__ Gp, const __grid_constant__ PairDev pr, const __grid_constant__ WeightsDev W,
                double lambda, const double* __restrict__ z, const double* __restrict__ zg, double* __restrict__ w,
                double* __restrict__ dpart, double* __restrict__ bpart,
                const LinGlobal* __restrict__ lin, const CgControl* __restrict__ ctl) {
-    __shared__ double sm[9 * (kThreads / 32)];
-    __shared__ Globals G;
+    __shared__ double sz[kTile * 6];
+    __shared__ double sx[kTile * 3];
+    __shared__ int srp[kTile + 1];
+    __shared__ double sred[3 * 8 * (kThreads / 32)];
+    __shared__ double Rg[9];
     __shared__ double zgs[8];
     if (ctl && (ctl->converged || ctl->breakdown)) return;   // flags are only written by an EARLIER launch
-    if (threadIdx.x == 0) G = *Gp;
+    if (threadIdx.x < 9) Rg[threadIdx.x] = Gp->Rg[threadIdx.x];
     if (threadIdx.x < 8) zgs[threadIdx.x] = zg[threadIdx.x];
-    __syncthreads();
-    int lane = threadIdx.x & (kLanes - 1);
-    double acc[9];
-#pragma unroll
-    for (int k = 0; k < 9; ++k) acc[k] = 0.0;
-    D3 zw = d3(zgs[0], zgs[1], zgs[2]), zv = d3(zgs[3], zgs[4], zgs[5]);
-    int nround = (n + kGroups - 1) / kGroups;
-    for (int rd = blockIdx.x; rd < nround; rd += gridDim.x) {
-        int i = rd * kGroups + threadIdx.x / kLanes;
-        bool act = i < n;
-        double o[6];
-#pragma unroll
-        for (int k = 0; k < 6; ++k) o[k] = 0.0;
-        D3 zi1 = d3(0, 0, 0), zi2 = d3(0, 0, 0);
-        if (act) {
-            P8 Pi = load_P(P, i);
-            double qi[4];
-            load_q(Q, i, qi);
-            load6(z, i, zi1, zi2);
-            int e1 = rowptr[i + 1];
-            for (int e = rowptr[i] + lane; e < e1; e += kLanes) {
-                int j = col[e];
-                P8 Pj = load_P(P, j);
-                double qj[4];
-                load_q(Q, j, qj);
-                D3 zj1, zj2;
-                load6(z, j, zj1, zj2);
-                ArapGrad g;
-                arap_edge<true>(Pi, Pj, qi, qj, wgt[e], W.inv_area, G, g);
-                double s = dot(g.gi1, zi1) + dot(g.gi2, zi2) + dot(g.gj1, zj1) + dot(g.gj2, zj2) + dot(g.gw, zw) + dot(g.gv, zv);
-                double ws = W.arap_info * s;
-                double w2 = 2.0 * ws;
-                o[0] += w2 * g.gi1.x; o[1] += w2 * g.gi1.y; o[2] += w2 * g.gi1.z;
-                o[3] += w2 * g.gi2.x; o[4] += w2 * g.gi2.y; o[5] += w2 * g.gi2.z;
-                acc[0] += ws * g.gw.x; acc[1] += ws * g.gw.y; acc[2] += ws * g.gw.z;
-                acc[3] += ws * g.gv.x; acc[4] += ws * g.gv.y; acc[5] += ws * g.gv.z;
+    const int lane = threadIdx.x & (kLanes - 1);
+    const int grp = threadIdx.x / kLanes;
+    // epilogue role of this lane: output component `lane` (0..5) = row lane%3 of camera lane/3
+    const int ecam = lane >= 3 ? 1 : 0, erow = lane - 3 * ecam;
+    const double* Rc = ecam == 0 ? pr.R1 : pr.R2;
+    const double nrow = lane < 6 ? Rc[6 + erow] : 0.0;
+    double accb = 0.0, accs = 0.0, accd = 0.0;        // this lane's T_g border component, s border, z.w
+    const int ntiles = (n + kTile - 1) / kTile;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int v0 = tile * kTile;
+        const int nv = min(kTile, n - v0);
+        __syncthreads();
+        {   // stage z, X1, rowptr of the tile (coalesced)
+            const double2* zsrc = reinterpret_cast<const double2*>(z + 6 * (size_t)v0);
+            double2* zdst = reinterpret_cast<double2*>(sz);
+            for (int k = threadIdx.x; k < nv * 3; k += kThreads) zdst[k] = zsrc[k];
+            const double4* psrc = reinterpret_cast<const double4*>(P) + v0;
+            for (int k = threadIdx.x; k < nv; k += kThreads) {
+                double4 x = ldg256(psrc + k);
+                sx[3 * k] = x.x; sx[3 * k + 1] = x.y; sx[3 * k + 2] = x.z;
             }
+            for (int k = threadIdx.x; k <= nv; k += kThreads) srp[k] = rowptr[v0 + k];
         }
-#pragma unroll
-        for (int k = 0; k < 6; ++k) o[k] = group_sum(o[k]);
-        if (act && lane == 0) {
-            const double2* Up = reinterpret_cast<const double2*>(U + 16 * (size_t)i);
-            double u[16];
-#pragma unroll
-            for (int k = 0; k < 8; ++k) { double2 t = __ldg(Up + k); u[2 * k] = t.x; u[2 * k + 1] = t.y; }
-            double zi[6] = {zi1.x, zi1.y, zi1.z, zi2.x, zi2.y, zi2.z};
-#pragma unroll
-            for (int cam = 0; cam < 2; ++cam) {
-                const double* R = cam == 0 ? pr.R1 : pr.R2;
-                double nz = R[6] * zi[cam * 3] + R[7] * zi[cam * 3 + 1] + R[8] * zi[cam * 3 + 2];
-                double kd = u[12 + cam];
-#pragma unroll
-                for (int r = 0; r < 3; ++r) {
-                    double s = 0.0;
-#pragma unroll
-                    for (int c = 0; c < 3; ++c) s += (r <= c ? u[cam * 6 + pk<3>(r, c)] : u[cam * 6 + pk<3>(c, r)]) * zi[cam * 3 + c];
-                    o[cam * 3 + r] += s + kd * R[6 + r] * zgs[6 + cam];
+        __syncthreads();
+        const D3 zw = d3(zgs[0], zgs[1], zgs[2]);
+        const D3 zv2 = d3(2.0 * zgs[3], 2.0 * zgs[4], 2.0 * zgs[5]);
+        for (int il = grp; il < kTile; il += kGroups) {
+            const bool act = il < nv;
+            D3 Am = d3(0, 0, 0), Ag = d3(0, 0, 0), Au = d3(0, 0, 0);
+            D3 zi1 = d3(0, 0, 0), zi2 = d3(0, 0, 0), X1i = d3(0, 0, 0);
+            if (act) {
+                zi1 = d3(sz[6 * il], sz[6 * il + 1], sz[6 * il + 2]);
+                zi2 = d3(sz[6 * il + 3], sz[6 * il + 4], sz[6 * il + 5]);
+                X1i = d3(sx[3 * il], sx[3 * il + 1], sx[3 * il + 2]);
+                const int e1 = srp[il + 1];
+                for (int e = srp[il] + lane; e < e1; e += kLanes) {
+                    const int j = __ldg(col + e);
+                    const double* je = Je + (size_t)e;
+                    D3 u = d3(__ldg(je), __ldg(je + nE), __ldg(je + 2 * nE));
+                    D3 m = d3(__ldg(je + 3 * nE), __ldg(je + 4 * nE), __ldg(je + 5 * nE));
+                    D3 g = d3(__ldg(je + 6 * nE), __ldg(je + 7 * nE), __ldg(je + 8 * nE));
+                    D3 zj1, zj2, X1j;
+                    const unsigned jl = (unsigned)(j - v0);
+                    if (jl < (unsigned)nv) {
+                        zj1 = d3(sz[6 * jl], sz[6 * jl + 1], sz[6 * jl + 2]);
+                        zj2 = d3(sz[6 * jl + 3], sz[6 * jl + 4], sz[6 * jl + 5]);
+                        X1j = d3(sx[3 * jl], sx[3 * jl + 1], sx[3 * jl + 2]);
+                    } else {
+                        load6(z, j, zj1, zj2);
+                        double4 xj = ldg256(reinterpret_cast<const double4*>(P) + (size_t)j);
+                        X1j = d3(xj.x, xj.y, xj.z);
+                    }
+                    D3 S1 = X1i + X1j;
+                    D3 t = mul(Rg, zi2 + zj2) - (zi1 + zj1) + cross(zw, S1) - zv2;
+                    double s = dot(u, zi2 - zj2) - dot(m, zi1 - zj1) + 2.0 * dot(g, t);
+                    double w2 = 2.0 * W.arap_info * s;
+                    Am = Am + w2 * m; Ag = Ag + w2 * g; Au = Au + w2 * u;
                 }
-                acc[6 + cam] += kd * nz;
             }
-            double dl = 0.0;
+            double o[9] = {Am.x, Am.y, Am.z, Ag.x, Ag.y, Ag.z, Au.x, Au.y, Au.z};
 #pragma unroll
-            for (int k = 0; k < 6; ++k) { o[k] += lambda * zi[k]; dl += zi[k] * o[k]; }
-            acc[8] += dl;
-            store6(w, i, d3(o[0], o[1], o[2]), d3(o[3], o[4], o[5]));
+            for (int k = 0; k < 9; ++k) o[k] = group_sum(o[k]);     // xor butterfly: every lane holds the sums
+            if (act && lane < 6) {
+                // lane c computes output component c: [-Am - 2 Ag | Au + 2 Rg^T Ag] + U z + kd n z_s + lambda z
+                const int i = v0 + il;
+                const double* Ui = U + 16 * (size_t)i;
+                const double zc0 = ecam == 0 ? zi1.x : zi2.x, zc1 = ecam == 0 ? zi1.y : zi2.y, zc2 = ecam == 0 ? zi1.z : zi2.z;
+                const double ag_r = erow == 0 ? o[3] : (erow == 1 ? o[4] : o[5]);
+                double base;
+                if (ecam == 0) base = -(erow == 0 ? o[0] : (erow == 1 ? o[1] : o[2])) - 2.0 * ag_r;
+                else base = (erow == 0 ? o[6] : (erow == 1 ? o[7] : o[8])) + 2.0 * (Rg[erow] * o[3] + Rg[3 + erow] * o[4] + Rg[6 + erow] * o[5]);
+                // packed symmetric 3x3 row `erow`: indices (0,1,2) | (1,3,4) | (2,4,5)
+                const int i0 = erow, i1 = erow == 0 ? 1 : (erow == 1 ? 3 : 4), i2 = erow == 0 ? 2 : (erow == 1 ? 4 : 5);
+                const double us = __ldg(Ui + ecam * 6 + i0) * zc0 + __ldg(Ui + ecam * 6 + i1) * zc1 + __ldg(Ui + ecam * 6 + i2) * zc2;
+                const double kd = __ldg(Ui + 12 + ecam);
+                const double zme = erow == 0 ? zc0 : (erow == 1 ? zc1 : zc2);
+                const double out = base + us + kd * nrow * zgs[6 + ecam] + lambda * zme;
+                accs += kd * nrow * zme;                           // s1/s2 rows: kd (n . z)
+                accd += zme * out;
+                // T_g rows from the per-vertex sums: omega: 2 (X1i x Ag), upsilon: -2 Ag
+                if (ecam == 0) {
+                    const double cx = erow == 0 ? X1i.y * o[5] - X1i.z * o[4] : (erow == 1 ? X1i.z * o[3] - X1i.x * o[5] : X1i.x * o[4] - X1i.y * o[3]);
+                    accb += 2.0 * cx;
+                } else accb -= 2.0 * ag_r;
+                w[6 * (size_t)i + lane] = out;
+            }
         }
     }
-    block_reduce<9>(acc, sm);
-    if (threadIdx.x == 0) {
-        double dl = acc[8];
-        for (int k = 0; k < 8; ++k) { bpart[8 * (size_t)blockIdx.x + k] = acc[k]; dl += zgs[k] * acc[k]; }
-        if (blockIdx.x == 0)     // diagonal of the global rows that is not inside the edge sums: (C_ss + lambda)
-            for (int k = 0; k < 8; ++k) dl += zgs[k] * ((k >= 6 ? lin->C[k * 8 + k] : 0.0) + lambda) * zgs[k];
-        dpart[blockIdx.x] = dl;
+    // role-preserving reduction: lanes with equal (lane % 8) across the block
+    {
+        double v3[3] = {accb, accs, accd};
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            double s = v3[k];
+            s += __shfl_xor_sync(0xffffffffu, s, 8);
+            s += __shfl_xor_sync(0xffffffffu, s, 16);
+            if ((threadIdx.x & 31) < 8) sred[(k * 8 + (threadIdx.x & 7)) * (kThreads / 32) + (threadIdx.x >> 5)] = s;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double r[3][8];
+            for (int k = 0; k < 3; ++k)
+                for (int q = 0; q < 8; ++q) {
+                    double s = 0.0;
+                    for (int wv = 0; wv < kThreads / 32; ++wv) s += sred[(k * 8 + q) * (kThreads / 32) + wv];
+                    r[k][q] = s;
+                }
+            double bg[8];
+            for (int q = 0; q < 6; ++q) bg[q] = r[0][q];
+            bg[6] = r[1][0] + r[1][1] + r[1][2];
+            bg[7] = r[1][3] + r[1][4] + r[1][5];
+            double dl = 0.0;
+            for (int q = 0; q < 6; ++q) dl += r[2][q];
+            for (int k = 0; k < 8; ++k) { bpart[8 * (size_t)blockIdx.x + k] = bg[k]; dl += zgs[k] * bg[k]; }
+            if (blockIdx.x == 0)     // diagonal of the global rows that is not inside the edge sums: (C_ss + lambda)
+                for (int k = 0; k < 8; ++k) dl += zgs[k] * ((k >= 6 ? lin->C[k * 8 + k] : 0.0) + lambda) * zgs[k];
+            dpart[blockIdx.x] = dl;
+        }
     }
 }
 
@@ -913,10 +979,10 @@ apply_update_kernel(int n, const double* __restrict__ P, const double* __restric
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         D3 x1, x2, b1, b2;
         load6(x, i, x1, x2); load6(b, i, b1, b2);
-        P8 Pi = load_P(P, i);
-        double4* o = reinterpret_cast<double4*>(Ptrial) + 2 * (size_t)i;
-        o[0] = make_double4(Pi.a.x + x1.x, Pi.a.y + x1.y, Pi.a.z + x1.z, 0.0);
-        o[1] = make_double4(Pi.b.x + x2.x, Pi.b.y + x2.y, Pi.b.z + x2.z, 0.0);
+        P8 Pi = load_P(P, n, i);
+        double4* o = reinterpret_cast<double4*>(Ptrial);
+        o[i] = make_double4(Pi.a.x + x1.x, Pi.a.y + x1.y, Pi.a.z + x1.z, 0.0);
+        o[(size_t)n + i] = make_double4(Pi.b.x + x2.x, Pi.b.y + x2.y, Pi.b.z + x2.z, 0.0);
         acc[0] += dot(x1, lambda * x1 + b1) + dot(x2, lambda * x2 + b2);
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
@@ -946,7 +1012,7 @@ export_kernel(int n, const double* __restrict__ P, const double* __restrict__ P0
     double acc[1] = {0.0};
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         size_t d = perm ? (size_t)perm[i] : (size_t)i;
-        P8 a = load_P(P, i), o = load_P(P0, i);
+        P8 a = load_P(P, n, i), o = load_P(P0, n, i);
         float n1[3] = {(float)a.a.x, (float)a.a.y, (float)a.a.z}, n2[3] = {(float)a.b.x, (float)a.b.y, (float)a.b.z};
         float o1[3] = {(float)o.a.x, (float)o.a.y, (float)o.a.z}, o2[3] = {(float)o.b.x, (float)o.b.y, (float)o.b.z};
         for (int k = 0; k < 3; ++k) {
@@ -970,7 +1036,7 @@ pixel_sigma_kernel(int n, const double* __restrict__ P, const float4* __restrict
     __shared__ double sm[4 * (kThreads / 32)];
     double acc[4] = {0.0, 0.0, 0.0, 0.0};
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        P8 a = load_P(P, i);
+        P8 a = load_P(P, n, i);
         float4 o = uv[i];
         float pu, pv;
         cam_project(pr.cam1, apply(pr.T1f, mk3((float)a.a.x, (float)a.a.y, (float)a.a.z)), pu, pv);
