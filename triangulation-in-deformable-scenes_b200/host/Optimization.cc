@@ -1,0 +1,441 @@
+// Optimization.cc -- host shim: gathers the reference's Map into structure-of-arrays buffers, calls the CUDA
+// library through the C ABI (include/dsc.h) and scatters the result back.  No numerical work of the hot path
+// happens here; there is no CPU fallback (a missing GPU throws).
+#include "Optimization.h"
+
+#include <algorithm>
+#include <array>
+#include <cmath>
+#include <cstdlib>
+#include <fstream>
+#include <iostream>
+#include <limits>
+#include <stdexcept>
+
+#include "../../include/dsc.h"
+#include "Mesh.h"
+
+namespace {
+
+dsc_ctx* g_ctx = nullptr;
+std::vector<dsc_host::LmRecord> g_trace;
+dsc_pcg_params g_pcg{1e-10, 6000, 64};
+
+dsc_ctx* ctx() {
+    if (!g_ctx) {
+        const char* d = std::getenv("DSC_DEVICE");
+        int st = dsc_create(d ? std::atoi(d) : 0, &g_ctx);
+        if (st != DSC_OK) throw std::runtime_error(std::string("dsc_create failed: ") + dsc_status_string(st));
+    }
+    return g_ctx;
+}
+void ck(int st, const char* what) {
+    if (st != DSC_OK) throw std::runtime_error(std::string(what) + ": " + dsc_last_error(g_ctx));
+}
+int method_id(const std::string& m) {        // Geometry.cc:220-228: anything else is NRSLAM
+    if (m == "Classic") return DSC_TRI_CLASSIC;
+    if (m == "ORBSLAM") return DSC_TRI_ORBSLAM;
+    if (m == "DepthMeasurement") return DSC_TRI_DEPTH;
+    return DSC_TRI_NRSLAM;
+}
+int location_id(const std::string& l) {
+    if (l == "TwoPoints") return DSC_LOC_TWOPOINTS;
+    if (l == "FarPoints") return DSC_LOC_FARPOINTS;
+    return DSC_LOC_INRAYS;
+}
+dsc_pair make_pair(KeyFrame& k1, KeyFrame& k2) {
+    dsc_pair p{};
+    auto c1 = k1.getCalibration(), c2 = k2.getCalibration();
+    p.cam1.model = c1->modelId(); p.cam2.model = c2->modelId();
+    for (int i = 0; i < 8; ++i) {
+        p.cam1.params[i] = i < c1->getNumberOfParameters() ? c1->getParameter(i) : 0.f;
+        p.cam2.params[i] = i < c2->getNumberOfParameters() ? c2->getParameter(i) : 0.f;
+    }
+    dsc_host::pose34(k1.getPose(), p.T1w);
+    dsc_host::pose34(k2.getPose(), p.T2w);
+    return p;
+}
+// Sophus::SE3f -> (qx,qy,qz,qw,tx,ty,tz) in double, Eigen's matrix->quaternion rule
+void se3_to_7(const Sophus::SE3f& T, double* o) {
+    auto Rm = T.rotationMatrix();
+    double R[9];
+    for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) R[r * 3 + c] = (double)Rm(r, c);
+    double q[4], t = R[0] + R[4] + R[8];
+    if (t > 0) {
+        t = std::sqrt(t + 1.0); q[3] = 0.5 * t; t = 0.5 / t;
+        q[0] = (R[7] - R[5]) * t; q[1] = (R[2] - R[6]) * t; q[2] = (R[3] - R[1]) * t;
+    } else {
+        int i = 0;
+        if (R[4] > R[0]) i = 1;
+        if (R[8] > R[i * 4]) i = 2;
+        int j = (i + 1) % 3, k = (j + 1) % 3;
+        t = std::sqrt(R[i * 4] - R[j * 4] - R[k * 4] + 1.0); q[i] = 0.5 * t; t = 0.5 / t;
+        q[3] = (R[k * 3 + j] - R[j * 3 + k]) * t; q[j] = (R[j * 3 + i] + R[i * 3 + j]) * t; q[k] = (R[k * 3 + i] + R[i * 3 + k]) * t;
+    }
+    for (int k = 0; k < 4; ++k) o[k] = q[k];
+    auto tr = T.translation();
+    o[4] = tr[0]; o[5] = tr[1]; o[6] = tr[2];
+}
+Sophus::SE3f se3_from_7(const double* v) {
+    double x = v[0], y = v[1], z = v[2], w = v[3];
+    Eigen::Matrix3f R;
+    R(0, 0) = (float)(1 - 2 * (y * y + z * z)); R(0, 1) = (float)(2 * (x * y - z * w)); R(0, 2) = (float)(2 * (x * z + y * w));
+    R(1, 0) = (float)(2 * (x * y + z * w)); R(1, 1) = (float)(1 - 2 * (x * x + z * z)); R(1, 2) = (float)(2 * (y * z - x * w));
+    R(2, 0) = (float)(2 * (x * z - y * w)); R(2, 1) = (float)(2 * (y * z + x * w)); R(2, 2) = (float)(1 - 2 * (x * x + y * y));
+    return Sophus::SE3f(R, Eigen::Vector3f((float)v[4], (float)v[5], (float)v[6]));
+}
+
+// One key-frame pair gathered from the Map (g2oBundleAdjustment.cc:640-957 without the g2o objects)
+struct PairProblem {
+    KeyFrame_ kf1, kf2;
+    ID kf1Id = 0, kf2Id = 0;
+    std::vector<MapPoint_> mp1, mp2;
+    std::vector<float> X1, X2, uv1, uv2, isg1, isg2;
+    std::vector<double> d1, d2;
+    dsc_host::Graph graph;
+    double Tg[7];
+};
+
+bool gather_pair(Map* pMap, KeyFrame_ pKF1, ID kf1ID, KeyFrame_ pKF2, ID kf2ID, PairProblem& pp) {
+    pp.kf1 = pKF1; pp.kf2 = pKF2; pp.kf1Id = kf1ID; pp.kf2Id = kf2ID;
+    auto& v1 = pKF1->getMapPoints();
+    auto& v2 = pKF2->getMapPoints();
+    size_t slots = std::min(v1.size(), v2.size());
+    for (size_t mpIndex = 0; mpIndex < slots; ++mpIndex) {
+        MapPoint_ a = v1[mpIndex], b = v2[mpIndex];
+        if (!a || !b) continue;                                               // :728-729
+        int i1 = pMap->isMapPointInKeyFrame(a->getId(), kf1ID);               // :765-768
+        int i2 = pMap->isMapPointInKeyFrame(b->getId(), kf2ID);
+        if (i1 < 0 || i2 < 0) continue;
+        cv::KeyPoint k1 = pKF1->getKeyPoint((size_t)i1), k2 = pKF2->getKeyPoint((size_t)i2);
+        auto p1 = a->getWorldPosition(), p2 = b->getWorldPosition();
+        pp.mp1.push_back(a); pp.mp2.push_back(b);
+        for (int k = 0; k < 3; ++k) { pp.X1.push_back(p1[k]); pp.X2.push_back(p2[k]); }
+        pp.uv1.push_back(k1.pt.x); pp.uv1.push_back(k1.pt.y);
+        pp.uv2.push_back(k2.pt.x); pp.uv2.push_back(k2.pt.y);
+        pp.isg1.push_back(pKF1->getInvSigma2(k1.octave));                     // :781
+        pp.isg2.push_back(pKF2->getInvSigma2(k2.octave));
+        // :816,846 read the depth image; simulated key frames only carry per-key-point depths
+        pp.d1.push_back(pKF1->hasDepthImage() ? pKF1->getDepthMeasure(k1.pt.x, k1.pt.y, false) : (double)pKF1->getDepthMeasure((size_t)i1));
+        pp.d2.push_back(pKF2->hasDepthImage() ? pKF2->getDepthMeasure(k2.pt.x, k2.pt.y, false) : (double)pKF2->getDepthMeasure((size_t)i2));
+    }
+    int n = (int)pp.mp1.size();
+    if (n < 3) return false;
+    // mesh on KF1's positions: 2-D Delaunay of world (x,y), adjacency, cot weights, area (:653-662)
+    std::vector<double> xy(2 * (size_t)n);
+    std::vector<std::array<double, 3>> V(n);
+    for (int i = 0; i < n; ++i) {
+        xy[2 * i] = (double)pp.X1[3 * i]; xy[2 * i + 1] = (double)pp.X1[3 * i + 1];
+        V[i] = {(double)pp.X1[3 * i], (double)pp.X1[3 * i + 1], (double)pp.X1[3 * i + 2]};
+    }
+    auto tri = dsc_host::Delaunay2D::triangulate(xy.data(), n);
+    pp.graph = dsc_host::mesh_graph(V, tri, 0.0);
+    se3_to_7(pMap->getGlobalKeyFramesTransformation(kf1ID, kf2ID), pp.Tg);    // :664 (identity the first time)
+    return pp.graph.n_triangles > 0 && pp.graph.area > 0.0;
+}
+
+void upload_pair(PairProblem& pp) {
+    dsc_ctx* c = ctx();
+    dsc_pair pr = make_pair(*pp.kf1, *pp.kf2);
+    int n = (int)pp.mp1.size();
+    ck(dsc_problem_upload(c, &pr, n, pp.X1.data(), pp.X2.data(), pp.uv1.data(), pp.uv2.data(), pp.d1.data(), pp.d2.data(),
+                          pp.isg1.data(), pp.isg2.data(), pp.kf1->getEstimatedDepthScale(), pp.kf2->getEstimatedDepthScale(), pp.Tg),
+       "dsc_problem_upload");
+    ck(dsc_set_graph(c, n, pp.graph.rowptr.data(), pp.graph.col.data(), pp.graph.w.data(), pp.graph.area, pp.graph.n_triangles, 1 | 2),
+       "dsc_set_graph");
+    ck(dsc_compute_rotations(c), "dsc_compute_rotations");                    // :687-688 computeR
+    ck(dsc_set_pcg(c, &g_pcg), "dsc_set_pcg");
+}
+
+dsc_weights weights(double rep, double glob, double arap, double alpha, double beta, float depthError) {
+    dsc_weights w{};
+    w.rep = rep; w.global = glob; w.arap = arap; w.alpha = alpha; w.beta = beta; w.depth_sigma = depthError;
+    return w;
+}
+
+void run_lm(const dsc_weights& w, int nIter) {
+    std::vector<dsc_iter_record> rec((size_t)std::max(1, nIter));
+    dsc_opt_stats st{};
+    ck(dsc_optimize(ctx(), &w, nIter, rec.data(), &st), "dsc_optimize");
+    g_trace.clear();
+    for (int i = 0; i < st.iterations; ++i)
+        g_trace.push_back({rec[i].chi2_before, rec[i].chi2_after, rec[i].lambda, rec[i].trials, rec[i].accepted, rec[i].pcg_iters});
+}
+
+void write_back(Map* pMap, PairProblem& pp, double* optimizationUpdate) {
+    int n = (int)pp.mp1.size();
+    std::vector<float> X1(3 * (size_t)n), X2(3 * (size_t)n);
+    double scales[2], Tg[7], upd = 0.0;
+    ck(dsc_download(ctx(), X1.data(), X2.data(), nullptr, nullptr, scales, Tg, &upd), "dsc_download");
+    pp.kf1->setEstimatedDepthScale(scales[0]);                                // :967-972
+    pp.kf2->setEstimatedDepthScale(scales[1]);
+    for (int i = 0; i < n; ++i) {                                             // :978-990
+        Eigen::Vector3f a(X1[3 * i], X1[3 * i + 1], X1[3 * i + 2]), b(X2[3 * i], X2[3 * i + 1], X2[3 * i + 2]);
+        pp.mp1[i]->setWorldPosition(a);
+        pp.mp2[i]->setWorldPosition(b);
+    }
+    if (optimizationUpdate) *optimizationUpdate += upd;
+    pMap->insertGlobalKeyFramesTransformation(0, 1, se3_from_7(Tg));          // :1007 (ids hard-coded upstream)
+}
+
+template <typename F>
+void for_each_pair(Map* pMap, F&& f) {                                        // :640-645 (pKF1 = k2, pKF2 = k1)
+    auto& kfs = pMap->getKeyFrames();
+    for (auto k1 = kfs.begin(); k1 != kfs.end(); ++k1)
+        for (auto k2 = std::next(k1); k2 != kfs.end(); ++k2) f(k2->second, k2->first, k1->second, k1->first);
+}
+
+// Nelder-Mead over the free coordinates of (rep, global, arap) inside box bounds: the stand-in for
+// nlopt::opt(nlopt::LN_NELDERMEAD, 3) (g2oBundleAdjustment.cc:491-515).  NLopt is absent and unpinned; restated:
+// fixed coordinates (lb == ub) are eliminated, initial step = NLopt's default rule, standard coefficients
+// (1, 2, 0.5, 0.5), points clamped to the box, stop on xtol_rel / xtol_abs of the simplex or maxeval.
+template <typename F>
+double nelder_mead(std::vector<double>& x, const std::vector<double>& lb, const std::vector<double>& ub, double xtol_rel,
+                   double xtol_abs, int maxeval, F&& f) {
+    std::vector<int> freeIdx;
+    for (size_t i = 0; i < x.size(); ++i) if (ub[i] > lb[i]) freeIdx.push_back((int)i);
+    int evals = 0;
+    auto eval = [&](const std::vector<double>& y) { std::vector<double> full = x; for (size_t k = 0; k < freeIdx.size(); ++k) full[freeIdx[k]] = y[k]; ++evals; return f(full); };
+    for (size_t i = 0; i < x.size(); ++i) x[i] = std::min(ub[i], std::max(lb[i], x[i]));
+    size_t d = freeIdx.size();
+    if (d == 0) return f(x);
+    std::vector<std::vector<double>> S(d + 1, std::vector<double>(d));
+    std::vector<double> fv(d + 1);
+    for (size_t k = 0; k < d; ++k) S[0][k] = x[freeIdx[k]];
+    for (size_t k = 0; k < d; ++k) {
+        int i = freeIdx[k];
+        double step = (ub[i] - lb[i]) * 0.25;
+        if (ub[i] - x[i] < step && ub[i] > x[i]) step = (ub[i] - x[i]) * 0.75;
+        if (x[i] - lb[i] < step && x[i] > lb[i]) step = (x[i] - lb[i]) * 0.75;
+        if (!(step > 0) || !std::isfinite(step)) step = x[i] != 0 ? std::fabs(x[i]) : 1.0;
+        S[k + 1] = S[0];
+        S[k + 1][k] = (S[0][k] + step <= ub[i]) ? S[0][k] + step : S[0][k] - step;
+    }
+    auto clamp = [&](std::vector<double>& y) { for (size_t k = 0; k < d; ++k) y[k] = std::min(ub[freeIdx[k]], std::max(lb[freeIdx[k]], y[k])); };
+    for (size_t k = 0; k <= d && evals < maxeval; ++k) fv[k] = eval(S[k]);
+    while (evals < maxeval) {
+        std::vector<size_t> o(d + 1);
+        for (size_t k = 0; k <= d; ++k) o[k] = k;
+        std::sort(o.begin(), o.end(), [&](size_t a, size_t b) { return fv[a] < fv[b]; });
+        size_t lo = o[0], hi = o[d], nhi = o[d > 0 ? d - 1 : 0];
+        bool conv = true;
+        for (size_t k = 0; k < d; ++k) {
+            double mn = S[0][k], mx = S[0][k];
+            for (size_t j = 1; j <= d; ++j) { mn = std::min(mn, S[j][k]); mx = std::max(mx, S[j][k]); }
+            if (mx - mn > xtol_abs && mx - mn > xtol_rel * std::fabs(S[lo][k])) conv = false;
+        }
+        if (conv) break;
+        std::vector<double> c(d, 0.0);
+        for (size_t j = 0; j <= d; ++j) if (j != hi) for (size_t k = 0; k < d; ++k) c[k] += S[j][k] / d;
+        auto along = [&](double t) { std::vector<double> y(d); for (size_t k = 0; k < d; ++k) y[k] = c[k] + t * (S[hi][k] - c[k]); clamp(y); return y; };
+        std::vector<double> xr = along(-1.0);
+        double fr = eval(xr);
+        if (fr < fv[lo]) {
+            std::vector<double> xe = along(-2.0);
+            double fe = evals < maxeval ? eval(xe) : std::numeric_limits<double>::infinity();
+            if (fe < fr) { S[hi] = xe; fv[hi] = fe; } else { S[hi] = xr; fv[hi] = fr; }
+        } else if (fr < fv[nhi] || d == 1 && fr < fv[hi]) {
+            S[hi] = xr; fv[hi] = fr;
+        } else {
+            std::vector<double> xc = along(fr < fv[hi] ? -0.5 : 0.5);
+            double fc = evals < maxeval ? eval(xc) : std::numeric_limits<double>::infinity();
+            if (fc < std::min(fr, fv[hi])) { S[hi] = xc; fv[hi] = fc; }
+            else {
+                for (size_t j = 0; j <= d && evals < maxeval; ++j)
+                    if (j != lo) { for (size_t k = 0; k < d; ++k) S[j][k] = S[lo][k] + 0.5 * (S[j][k] - S[lo][k]); fv[j] = eval(S[j]); }
+            }
+        }
+    }
+    size_t best = 0;
+    for (size_t k = 1; k <= d; ++k) if (fv[k] < fv[best]) best = k;
+    for (size_t k = 0; k < d; ++k) x[freeIdx[k]] = S[best][k];
+    return fv[best];
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------ public API
+namespace dsc_host {
+const std::vector<LmRecord>& lastTrace() { return g_trace; }
+void setSolver(double rtol, int maxIters) { g_pcg.rtol = rtol; g_pcg.max_iters = maxIters; }
+
+TriangulationResult triangulateMatches(KeyFrame& refKF, KeyFrame& currKF, const std::vector<int>& matches, const std::string& method,
+                                       const std::string& location, int gate, float minCos, float depthLimit, bool checkReprojection) {
+    size_t nRef = refKF.getKeyPoints().size();
+    std::vector<int> refIdx;
+    std::vector<float> uv1, uv2, d1, d2;
+    bool depth = !refKF.getDepthMeasurements().empty() && !currKF.getDepthMeasurements().empty();
+    for (size_t i = 0; i < nRef && i < matches.size(); ++i) {
+        int j = matches[i];
+        if (j < 0) continue;
+        refIdx.push_back((int)i);
+        cv::Point2f a = refKF.getKeyPoint(i).pt, b = currKF.getKeyPoint((size_t)j).pt;
+        uv1.push_back(a.x); uv1.push_back(a.y); uv2.push_back(b.x); uv2.push_back(b.y);
+        if (depth) { d1.push_back(refKF.getDepthMeasure(i)); d2.push_back(currKF.getDepthMeasure((size_t)j)); }
+    }
+    int n = (int)refIdx.size();
+    dsc_pair pr = make_pair(refKF, currKF);
+    dsc_tri_params tp{method_id(method), location_id(location), gate, minCos, depthLimit, checkReprojection ? 1 : 0};
+    std::vector<float> X1(3 * (size_t)n), X2(3 * (size_t)n), cs(n);
+    std::vector<uint8_t> valid(n);
+    int nv = 0;
+    ck(dsc_triangulate(ctx(), &pr, &tp, n, uv1.data(), uv2.data(), depth ? d1.data() : nullptr, depth ? d2.data() : nullptr, X1.data(),
+                       X2.data(), valid.data(), cs.data(), &nv),
+       "dsc_triangulate");
+    TriangulationResult r;
+    r.x3D_1.assign(nRef, Eigen::Vector3f()); r.x3D_2.assign(nRef, Eigen::Vector3f());
+    r.valid.assign(nRef, 0); r.cosParallax.assign(nRef, 1.f);
+    for (int k = 0; k < n; ++k) {
+        int i = refIdx[k];
+        r.x3D_1[i] = Eigen::Vector3f(X1[3 * k], X1[3 * k + 1], X1[3 * k + 2]);
+        r.x3D_2[i] = Eigen::Vector3f(X2[3 * k], X2[3 * k + 1], X2[3 * k + 2]);
+        r.valid[i] = valid[k]; r.cosParallax[i] = cs[k];
+    }
+    r.nValid = nv;
+    return r;
+}
+
+int triangulateSimulatedMapPoints(Map& map, KeyFrame_ refKF, KeyFrame_ currKF, const std::string& method, const std::string& location, float minCos) {
+    size_t n = std::min(refKF->getKeyPoints().size(), currKF->getKeyPoints().size());
+    std::vector<int> matches(refKF->getKeyPoints().size(), -1);
+    for (size_t i = 0; i < n; ++i) matches[i] = (int)i;                        // Mapping.cc:295-296: ordered pairs
+    TriangulationResult r = triangulateMatches(*refKF, *currKF, matches, method, location, DSC_GATE_SIM, minCos);
+    int created = 0;
+    for (size_t i = 0; i < n; ++i) {
+        if (!r.valid[i]) continue;
+        MapPoint_ a(new MapPoint(r.x3D_1[i])), b(new MapPoint(r.x3D_2[i]));    // Mapping.cc:329-339
+        map.insertMapPoint(a); map.insertMapPoint(b);
+        map.addObservation(refKF->getId(), a->getId(), i);
+        map.addObservation(currKF->getId(), b->getId(), i);
+        refKF->setMapPoint(i, a); currKF->setMapPoint(i, b);
+        created += 2;
+    }
+    // KeyFrame::setInitialDepthScaleInSimulationImages (KeyFrame.cc:131-153), only if the scale is still 0
+    if (!refKF->getEstimatedDepthScale()) { double s = 0; ck(dsc_depth_scale_init(ctx(), 1, &s), "dsc_depth_scale_init"); refKF->setEstimatedDepthScale(s); }
+    if (!currKF->getEstimatedDepthScale()) { double s = 0; ck(dsc_depth_scale_init(ctx(), 2, &s), "dsc_depth_scale_init"); currKF->setEstimatedDepthScale(s); }
+    return created;
+}
+}  // namespace dsc_host
+
+void KeyFrame::setInitialDepthScaleInSimulationImages() {
+    throw std::logic_error("use dsc_host::triangulateSimulatedMapPoints: the initial depth scale is reduced on the GPU");
+}
+
+bool useTriangulationMethod(const Eigen::Vector3f& xn1, const Eigen::Vector3f& xn2, const Sophus::SE3f& T1w, const Sophus::SE3f& T2w,
+                            Eigen::Vector3f& x3D_1, Eigen::Vector3f& x3D_2, std::string TrianMethod, std::string TrianLocation) {
+    // rays in, so the batch kernel is driven through an identity pin-hole: pixel = (x/z, y/z) unprojects to the
+    // same ray direction.  Rays with z <= 0 cannot be expressed that way.
+    if (!(xn1[2] > 0.f) || !(xn2[2] > 0.f)) return false;
+    dsc_pair pr{};
+    pr.cam1.model = pr.cam2.model = DSC_CAM_PINHOLE;
+    pr.cam1.params[0] = pr.cam1.params[1] = pr.cam2.params[0] = pr.cam2.params[1] = 1.f;
+    dsc_host::pose34(T1w, pr.T1w);
+    dsc_host::pose34(T2w, pr.T2w);
+    dsc_tri_params tp{method_id(TrianMethod), location_id(TrianLocation), DSC_GATE_NONE, 1.f, 3.0e38f, 0};
+    float uv1[2] = {xn1[0] / xn1[2], xn1[1] / xn1[2]}, uv2[2] = {xn2[0] / xn2[2], xn2[1] / xn2[2]};
+    float d1 = xn1[2], d2 = xn2[2], X1[3], X2[3];
+    ck(dsc_triangulate(ctx(), &pr, &tp, 1, uv1, uv2, &d1, &d2, X1, X2, nullptr, nullptr, nullptr), "dsc_triangulate");
+    x3D_1 = Eigen::Vector3f(X1[0], X1[1], X1[2]);
+    x3D_2 = Eigen::Vector3f(X2[0], X2[1], X2[2]);
+    return true;                                                               // Geometry.cc:229
+}
+
+void arapOptimization(Map* pMap, double repBalanceWeight, double globalBalanceWeight, double arapBalanceWeight, double alphaWeight,
+                      double betaWeight, float DepthError, int nOptIterations, double* optimizationUpdate) {
+    if (optimizationUpdate) *optimizationUpdate = 0;                            // :974-976
+    dsc_weights w = weights(repBalanceWeight, globalBalanceWeight, arapBalanceWeight, alphaWeight, betaWeight, DepthError);
+    // The reference puts every key-frame pair in one g2o graph; its executables only ever hold two key frames
+    // (the main loops stop after the first mapped pair), so pairs are refined one after the other here.
+    for_each_pair(pMap, [&](KeyFrame_ kf1, ID id1, KeyFrame_ kf2, ID id2) {
+        PairProblem pp;
+        if (!gather_pair(pMap, kf1, id1, kf2, id2, pp)) return;
+        upload_pair(pp);
+        run_lm(w, nOptIterations);
+        write_back(pMap, pp, optimizationUpdate);
+    });
+}
+
+void calculatePixelsStandDev(std::shared_ptr<Map> map, PixelsError& pe) {
+    for_each_pair(map.get(), [&](KeyFrame_ kf1, ID id1, KeyFrame_ kf2, ID id2) {
+        PairProblem pp;
+        if (!gather_pair(map.get(), kf1, id1, kf2, id2, pp)) return;
+        upload_pair(pp);
+        double s[2];
+        ck(dsc_pixel_sigma(ctx(), s), "dsc_pixel_sigma");
+        pe.desvc1 = s[0]; pe.desvc2 = s[1]; pe.desv = 0.5 * (s[0] + s[1]);
+    });
+}
+
+void deformationOptimization(std::shared_ptr<Map> pMap, Settings& settings, std::shared_ptr<MapVisualizer>& mapVisualizer,
+                             const std::vector<Eigen::Vector3f> /*originalPoints*/, const std::vector<Eigen::Vector3f> /*movedPoints*/) {
+    float depthSigma = settings.getSimulatedDepthWeight() / 1000;               // :449
+    double rep = settings.getOptRepWeight(), arap = settings.getOptArapWeight(), glob = settings.getOptGlobalWeight();
+    double alpha = settings.getOptAlphaWeight(), beta = settings.getOptBetaWeight();
+    std::string sel = settings.getOptSelection(), wsel = settings.getOptWeightsSelection();
+    int nOptimizations = settings.getnOptimizations(), nOptIterations = settings.getnOptIterations();
+    bool drawRays = settings.getDrawRaysSelection();
+    size_t nMapPoints = pMap->getMapPoints().size();
+    double optimizationUpdate = 100;
+    for (int i = 1; i <= nOptimizations && optimizationUpdate >= (0.0001 * nMapPoints); i++) {   // :482
+        if (sel == "open3DArap") {
+            throw std::runtime_error("Optimization.selection open3DArap (Open3D DeformAsRigidAsPossible) is outside the accelerated path");
+        } else if (sel == "twoOptimizations" && wsel == "nlopt") {
+            // weight search: every objective evaluation re-runs the refinement from the uploaded state
+            // (dsc_reset_state) instead of cloning the Map (nloptOptimization.cc:5-37)
+            std::vector<double> x = {rep, glob, arap};
+            std::vector<double> lb = {settings.getNloptRepLowerBound(), settings.getNloptGlobalLowerBound(), settings.getNloptArapLowerBound()};
+            std::vector<double> ub = {settings.getNloptRepUpperBound(), settings.getNloptGlobalUpperBound(), settings.getNloptArapUpperBound()};
+            bool uploaded = false;
+            for_each_pair(pMap.get(), [&](KeyFrame_ kf1, ID id1, KeyFrame_ kf2, ID id2) {
+                if (uploaded) return;
+                PairProblem pp;
+                if (!gather_pair(pMap.get(), kf1, id1, kf2, id2, pp)) return;
+                upload_pair(pp);
+                uploaded = true;
+            });
+            if (uploaded) {
+                double minf = nelder_mead(x, lb, ub, settings.getNloptRelTolerance(), settings.getNloptAbsTolerance(),
+                                          settings.getNloptnOptimizations(), [&](const std::vector<double>& y) {
+                                              ck(dsc_reset_state(ctx()), "dsc_reset_state");
+                                              run_lm(weights(y[0], y[1], y[2], alpha, beta, depthSigma), nOptIterations);
+                                              double s[2];
+                                              ck(dsc_pixel_sigma(ctx(), s), "dsc_pixel_sigma");
+                                              return std::pow(std::log(s[0]), 2) + std::pow(std::log(s[1]), 2);
+                                          });
+                std::cout << "\nWEIGHTS OPTIMIZED\nOptimized repBalanceWeight: " << x[0] << "\nOptimized globalBalanceWeight: " << x[1]
+                          << "\nOptimized arapBalanceWeight: " << x[2] << "\nFinal minimized ABSOLUTE error: " << minf << std::endl;
+            }
+            arapOptimization(pMap.get(), x[0], x[1], x[2], alpha, beta, depthSigma, nOptIterations, &optimizationUpdate);   // :525
+            rep = x[0]; glob = x[1]; arap = x[2];
+        } else {
+            // "g2oArap", and "twoOptimizations" with weightsSelection "eigen" (Eigen::LevenbergMarquardt over
+            // NumericalDiff, :532-563, unsupported Eigen module): the refinement runs with the configured weights
+            arapOptimization(pMap.get(), rep, glob, arap, alpha, beta, depthSigma, nOptIterations, &optimizationUpdate);
+        }
+        std::cout << "\nOptimization COMPLETED... " << i << " / " << nOptimizations << " iterations.\nOptimization change: "
+                  << optimizationUpdate << std::endl;
+        if (mapVisualizer) mapVisualizer->update(drawRays);
+    }
+    if (mapVisualizer) mapVisualizer->update(drawRays);
+}
+
+// ------------------------------------------------------------------ C hooks for the tests (ctypes)
+extern "C" int dsch_delaunay(int n, const double* xy, int* tri_out, int max_tri) {
+    auto tri = dsc_host::Delaunay2D::triangulate(xy, n);
+    int m = (int)tri.size();
+    for (int k = 0; k < m && k < max_tri; ++k) { tri_out[3 * k] = tri[k][0]; tri_out[3 * k + 1] = tri[k][1]; tri_out[3 * k + 2] = tri[k][2]; }
+    return m;
+}
+
+extern "C" int dsch_mesh_graph(int n, const double* xyz, int ntri, const int* tri, int* rowptr, int* col, double* w, int max_e, double* area) {
+    std::vector<std::array<double, 3>> V(n);
+    for (int i = 0; i < n; ++i) V[i] = {xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]};
+    std::vector<std::array<int, 3>> T(ntri);
+    for (int k = 0; k < ntri; ++k) T[k] = {tri[3 * k], tri[3 * k + 1], tri[3 * k + 2]};
+    auto g = dsc_host::mesh_graph(V, T, 0.0);
+    for (int i = 0; i <= n; ++i) rowptr[i] = g.rowptr[i];
+    int E = (int)g.col.size();
+    for (int e = 0; e < E && e < max_e; ++e) { col[e] = g.col[e]; w[e] = g.w[e]; }
+    *area = g.area;
+    return E;
+}

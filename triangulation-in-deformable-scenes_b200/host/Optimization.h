@@ -1,0 +1,61 @@
+// Optimization.h -- the reference's optimisation-call API, served by the CUDA library behind include/dsc.h.
+//
+// Same names, argument meaning and order as
+//   Modules/Optimization/g2oBundleAdjustment.h:52-59   deformationOptimization, arapOptimization
+//   Modules/Utils/Geometry.h:66-69                      useTriangulationMethod
+// so Modules/System/SLAM.cc:127,145, Modules/Optimization/nloptOptimization.cc:20, Modules/Mapping/Mapping.cc:311
+// and Modules/Mapping/MonocularMapInitializer.cc:313 compile against this header unchanged.
+#pragma once
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "Map.h"
+#include "Settings.h"
+
+/* Performs an As-Rigid-As-Possible optimization using arapOptimization inside an external loop that optimizes the
+ * balance weights (g2oBundleAdjustment.cc:446-606). */
+void deformationOptimization(std::shared_ptr<Map> pMap, Settings& settings, std::shared_ptr<MapVisualizer>& mapVisualizer,
+                             const std::vector<Eigen::Vector3f> originalPoints = {}, const std::vector<Eigen::Vector3f> movedPoints = {});
+
+/* ARAP + reprojection + depth refinement of the map points of every key-frame pair (g2oBundleAdjustment.cc:608-1008). */
+void arapOptimization(Map* pMap, double repBalanceWeight, double globalBalanceWeight, double arapBalanceWeight, double alphaWeight,
+                      double betaWeight, float DepthError, int nOptIterations, double* optimizationUpdate = nullptr);
+
+/* One correspondence (Geometry.cc:216-230).  Kept for API parity: it launches a 1-element batch; callers with
+ * many matches should use triangulateMatches. */
+bool useTriangulationMethod(const Eigen::Vector3f& xn1, const Eigen::Vector3f& xn2, const Sophus::SE3f& T1w, const Sophus::SE3f& T2w,
+                            Eigen::Vector3f& x3D_1, Eigen::Vector3f& x3D_2, std::string TrianMethod, std::string TrianLocation);
+
+/* Pixel-error standard deviation of the two cameras (Utils/Geometry.cc:370-498). */
+struct PixelsError { double avgc1 = 0, avgc2 = 0, avg = 0, desvc1 = 0, desvc2 = 0, desv = 0; };
+void calculatePixelsStandDev(std::shared_ptr<Map> Map, PixelsError& pixelsErrors);
+
+namespace dsc_host {
+
+struct TriangulationResult {
+    std::vector<Eigen::Vector3f> x3D_1, x3D_2;
+    std::vector<unsigned char> valid;
+    std::vector<float> cosParallax;
+    int nValid = 0;
+};
+
+/* Batched replacement of the per-match loops of Mapping::triangulateSimulatedMapPoints (Mapping.cc:294-343) and
+ * MonocularMapInitializer::reconstructPoints (:303-368): key points in pixels, gates as DSC_GATE_*. */
+TriangulationResult triangulateMatches(KeyFrame& refKF, KeyFrame& currKF, const std::vector<int>& matches /* curr index per ref key point, -1 = none */,
+                                       const std::string& method, const std::string& location, int gate, float minCos,
+                                       float depthLimit = 3.0e38f, bool checkReprojection = false);
+
+/* Mapping::triangulateSimulatedMapPoints end to end: triangulate, create MapPoints/observations for the valid
+ * matches, initial depth scales (KeyFrame.cc:131-153).  Returns the number of MapPoints created. */
+int triangulateSimulatedMapPoints(Map& map, KeyFrame_ refKF, KeyFrame_ currKF, const std::string& method, const std::string& location, float minCos);
+
+/* Per-iteration record of the last arapOptimization call (the reference runs g2o with setVerbose(false); the
+ * parity tests need the trace). */
+struct LmRecord { double chi2_before, chi2_after, lambda; int trials, accepted, pcg_iters; };
+const std::vector<LmRecord>& lastTrace();
+
+/* PCG controls of the linear solve (defaults rtol 1e-10, 6000 iterations). */
+void setSolver(double rtol, int maxIters);
+
+}  // namespace dsc_host

@@ -1,0 +1,114 @@
+// simulation_main.cc -- the flow of the reference's Execution/simulation.cc:7-41 on top of the host shim:
+// SLAM::loadPoints / setCameraPoses / getSimulatedDepthMeasurements / createKeyPoints / processSimulatedImage
+// (Modules/System/SLAM.cc:133-148,172-351) restated without OpenCV/Pangolin.  Prints one JSON object with the
+// triangulation, the LM trace of the last arapOptimization call and the final state.
+//   dsc_simulation <settings.yaml> <original_points.csv> <moved_points.csv> [--single]
+#include <cstdio>
+#include <fstream>
+#include <iostream>
+#include <random>
+#include <sstream>
+
+#include "Optimization.h"
+
+static std::vector<Eigen::Vector3f> loadCsv(const std::string& path) {
+    std::vector<Eigen::Vector3f> out;
+    std::ifstream f(path);
+    std::string line;
+    while (std::getline(f, line)) {
+        std::istringstream iss(line);
+        float x, y, z;
+        if (iss >> x >> y >> z) out.push_back(Eigen::Vector3f(x, y, z));
+    }
+    return out;
+}
+static double roundToDecimals(double value, int decimals) {           // Utils/Conversions.cc:64-67
+    double factor = std::pow(10.0, decimals);
+    return std::round(value * factor) / factor;
+}
+static Eigen::Matrix3f lookAt(const Eigen::Vector3f& c, const Eigen::Vector3f& target, const Eigen::Vector3f& up = Eigen::Vector3f(0, 1, 0)) {
+    Eigen::Vector3f forward = (target - c).normalized();               // SLAM.cc:340-351
+    Eigen::Vector3f right = up.cross(forward).normalized();
+    Eigen::Vector3f upv = forward.cross(right).normalized();
+    Eigen::Matrix3f R;
+    R.setCol(0, right); R.setCol(1, upv); R.setCol(2, forward);
+    return R;
+}
+
+int main(int argc, char** argv) {
+    if (argc < 4) { std::fprintf(stderr, "usage: %s settings.yaml original.csv moved.csv [--single]\n", argv[0]); return 2; }
+    bool single = argc > 4 && std::string(argv[4]) == "--single";
+    try {
+        Settings settings(argv[1]);
+        auto original = loadCsv(argv[2]), moved = loadCsv(argv[3]);
+        size_t n = std::min(original.size(), moved.size());
+        auto calib = settings.getCalibration();
+        // setCameraPoses (SLAM.cc:223-235): the camera centre is stored as the translation of Tcw [sic]
+        Sophus::SE3f T1w(Eigen::Matrix3f::Identity(), settings.getFirstCameraPos());
+        Sophus::SE3f T2w(lookAt(settings.getSecondCameraPos(), moved[0]), settings.getSecondCameraPos());
+        std::vector<cv::KeyPoint> k1(n), k2(n);
+        std::vector<float> d1(n), d2(n);
+        {   // getSimulatedDepthMeasurements (SLAM.cc:321-338)
+            std::default_random_engine generator;
+            std::normal_distribution<float> distribution(0.0f, settings.getSimulatedDepthError() / 1000);
+            for (size_t i = 0; i < n; ++i) {
+                Eigen::Vector3f c1 = T1w * original[i], c2 = T2w * moved[i];
+                d1[i] = c1[2] * settings.getSimulatedDepthScaleC1() + distribution(generator);
+                d2[i] = c2[2] * settings.getSimulatedDepthScaleC2() + distribution(generator);
+            }
+        }
+        {   // createKeyPoints (SLAM.cc:281-319)
+            std::default_random_engine generator;
+            std::normal_distribution<float> distribution(0.0f, settings.getSimulatedRepError());
+            int dec = settings.getDecimalsRepError();
+            for (size_t i = 0; i < n; ++i) {
+                Eigen::Vector3f c1 = T1w * original[i], c2 = T2w * moved[i];
+                cv::Point2f p1 = calib->project(c1), p2 = calib->project(c2);
+                p1.x = (float)roundToDecimals(p1.x + distribution(generator), dec);
+                p1.y = (float)roundToDecimals(p1.y + distribution(generator), dec);
+                p2.x = (float)roundToDecimals(p2.x + distribution(generator), dec);
+                p2.y = (float)roundToDecimals(p2.y + distribution(generator), dec);
+                k1[i] = cv::KeyPoint(p1, 1.0f); k2[i] = cv::KeyPoint(p2, 1.0f);
+            }
+        }
+        auto refKF = std::make_shared<KeyFrame>(k1, T1w, calib), currKF = std::make_shared<KeyFrame>(k2, T2w, calib);
+        for (size_t i = 0; i < n; ++i) { refKF->setDepthMeasure(d1[i], i); currKF->setDepthMeasure(d2[i], i); }
+        auto pMap = std::make_shared<Map>();
+        pMap->insertKeyFrame(refKF); pMap->insertKeyFrame(currKF);
+        // processSimulatedImage (SLAM.cc:133-148)
+        int nMPs = dsc_host::triangulateSimulatedMapPoints(*pMap, refKF, currKF, settings.getTrianMethod(), settings.getTrianLocation(), settings.getMinCos());
+        std::vector<Eigen::Vector3f> tri1, tri2;
+        for (size_t i = 0; i < n; ++i) if (refKF->getMapPoint(i)) { tri1.push_back(refKF->getMapPoint(i)->getWorldPosition()); tri2.push_back(currKF->getMapPoint(i)->getWorldPosition()); }
+        double s1_0 = refKF->getEstimatedDepthScale(), s2_0 = currKF->getEstimatedDepthScale();
+        std::shared_ptr<MapVisualizer> vis = std::make_shared<MapVisualizer>();
+        dsc_host::setSolver(1e-12, 20000);
+        double update = 0;
+        if (single)
+            arapOptimization(pMap.get(), settings.getOptRepWeight(), settings.getOptGlobalWeight(), settings.getOptArapWeight(), settings.getOptAlphaWeight(),
+                             settings.getOptBetaWeight(), settings.getSimulatedDepthWeight() / 1000, settings.getnOptIterations(), &update);
+        else
+            deformationOptimization(pMap, settings, vis, original, moved);
+        PixelsError pe;
+        calculatePixelsStandDev(pMap, pe);
+        std::printf("{\"n\": %zu, \"map_points\": %d, \"s1_init\": %.17g, \"s2_init\": %.17g, \"update\": %.17g, \"sigma_c1\": %.17g, \"sigma_c2\": %.17g,\n",
+                    n, nMPs, s1_0, s2_0, update, pe.desvc1, pe.desvc2);
+        std::printf(" \"s1\": %.17g, \"s2\": %.17g, \"uv1_sum\": %.17g, \"d1_sum\": %.17g,\n", refKF->getEstimatedDepthScale(), currKF->getEstimatedDepthScale(),
+                    [&] { double s = 0; for (auto& k : k1) s += (double)k.pt.x + (double)k.pt.y; return s; }(), [&] { double s = 0; for (float d : d1) s += d; return s; }());
+        std::printf(" \"trace\": [");
+        auto& tr = dsc_host::lastTrace();
+        for (size_t i = 0; i < tr.size(); ++i) std::printf("%s[%.17g, %.17g, %d]", i ? ", " : "", tr[i].chi2_before, tr[i].lambda, tr[i].trials);
+        std::printf("],\n \"tri1\": [");
+        for (size_t i = 0; i < tri1.size(); ++i) std::printf("%s%.9g, %.9g, %.9g", i ? ", " : "", tri1[i][0], tri1[i][1], tri1[i][2]);
+        std::printf("],\n \"X1\": [");
+        bool first = true;
+        for (size_t i = 0; i < n; ++i) if (refKF->getMapPoint(i)) { auto p = refKF->getMapPoint(i)->getWorldPosition(); std::printf("%s%.9g, %.9g, %.9g", first ? "" : ", ", p[0], p[1], p[2]); first = false; }
+        std::printf("],\n \"X2\": [");
+        first = true;
+        for (size_t i = 0; i < n; ++i) if (currKF->getMapPoint(i)) { auto p = currKF->getMapPoint(i)->getWorldPosition(); std::printf("%s%.9g, %.9g, %.9g", first ? "" : ", ", p[0], p[1], p[2]); first = false; }
+        std::printf("]}\n");
+    } catch (const std::exception& e) {
+        std::fprintf(stderr, "dsc_simulation: %s\n", e.what());
+        return 1;
+    }
+    return 0;
+}
