@@ -2,7 +2,7 @@
 """bench.py -- the hot path on BASELINE.json's metric: non-rigid LM iterations/s (and triangulated
 points/s, HBM GB/s of the dominant kernel) on a synthetic deformable two-view pair.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--n 1000000] [--k 8]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--points 1000000] [--k 8]
 
 A step = one arapOptimization call (triangulated pair -> `lm_iters` Levenberg-Marquardt iterations)
 on the workload named in config.workload.  `value` times the refinement with all inputs resident in
@@ -30,9 +30,11 @@ def parse():
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--n", type=int, default=1_000_000)
+    ap.add_argument("--points", dest="n", type=int, default=1_000_000, help="correspondences per frame pair")
     ap.add_argument("--k", type=int, default=8)
-    ap.add_argument("--workload", default="drunkard", choices=["drunkard", "realcolon", "sheet"])
+    ap.add_argument("--workload", default="drunkard", choices=["drunkard", "realcolon", "sheet", "batch"])
+    ap.add_argument("--problems", type=int, default=0, help="batch workload: frame-pair problems per GPU (config 5 has 4096 in total)")
+    ap.add_argument("--streams", type=int, default=8, help="batch workload: concurrent contexts (CUDA streams) per GPU")
     ap.add_argument("--lm-iters", type=int, default=0, help="0 = the config's own count")
     ap.add_argument("--pcg-rtol", type=float, default=1e-10)
     ap.add_argument("--pcg-max-iters", type=int, default=6000)
@@ -152,6 +154,8 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.workload == "batch" and args.impl == "ours":
+        return main_batch(args, rank, world, local)
 
     if args.impl == "reference":
         if rank != 0:
@@ -251,13 +255,11 @@ def main():
 
     # ---- max over ranks, aggregate
     if dist is not None:
-        import torch
-        t = torch.tensor([dev_ms, wall_ms, e2e_ms], dtype=torch.float64, device=f"cuda:{local}")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dev_ms, wall_ms, e2e_ms = [float(v) for v in t.tolist()]
-        c = torch.tensor([its, pcg_its, launches], dtype=torch.float64, device=f"cuda:{local}")
-        dist.all_reduce(c, op=dist.ReduceOp.SUM)
-        its, pcg_its, launches = [int(v) for v in c.tolist()]
+        import importlib
+        sh = importlib.import_module(pkg.__name__ + ".sharding")
+        (dev_ms, wall_ms, e2e_ms), (its, pcg_its, launches) = sh.fold(dist, f"cuda:{local}", [dev_ms, wall_ms, e2e_ms],
+                                                                        [its, pcg_its, launches])
+        its, pcg_its, launches = int(its), int(pcg_its), int(launches)
     if rank == 0:
         step_ms = max(dev_ms, 0.0) / args.steps
         value = its / (dev_ms * 1e-3)
@@ -285,6 +287,107 @@ def main():
     if dist is not None:
         dist.destroy_process_group()
     ctx.close()
+    return 0
+
+
+def main_batch(args, rank, world, local):
+    """Config 5: many independent small frame pairs, sharded by problem index (p % world == rank), several
+    contexts (streams) per GPU fed from a work queue.  No collective on the data path."""
+    import importlib
+    import queue
+    import __graft_entry__ as g
+    pkg = g.package()
+    sh = importlib.import_module(pkg.__name__ + ".sharding")
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    n = args.n if args.n != 1_000_000 else 10_000
+    per_gpu = args.problems or 16
+    mine = sh.shard(per_gpu * world, world, rank)
+    args.n, args.workload = n, "sheet"
+    ctxs = [pkg.Context(local) for _ in range(max(1, args.streams))]
+    probs = []
+    for pidx in mine:                                      # host-side synthesis + graph, untimed
+        sc = make_scene(pkg, args, seed=pidx)
+        probs.append((sc, prepare(pkg, ctxs[0], sc, args)))
+    lm_iters = args.lm_iters or probs[0][0]["lm_iters"]
+    w = pkg.make_weights(**probs[0][0]["weights"])
+    for c in ctxs:
+        c.set_pcg(rtol=args.pcg_rtol, max_iters=args.pcg_max_iters, check_every=64)
+
+    def run_all():
+        q = queue.Queue()
+        for pr in probs:
+            q.put(pr)
+        res = [[0.0, 0, 0, 0] for _ in ctxs]               # device ms, LM its, PCG its, launches
+
+        def worker(k):
+            c = ctxs[k]
+            l0 = c.launch_count()
+            while True:
+                try:
+                    sc, prob = q.get_nowait()
+                except queue.Empty:
+                    break
+                upload(c, prob)
+                recs, st = c.optimize(w, lm_iters)
+                c.download(doubles=False)
+                res[k][0] += st.device_ms
+                res[k][1] += st.iterations
+                res[k][2] += st.total_pcg_iters
+            res[k][3] = c.launch_count() - l0
+        th = [threading.Thread(target=worker, args=(k,)) for k in range(len(ctxs))]
+        t0 = time.perf_counter()
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
+        for c in ctxs:
+            c.synchronize()
+        return res, (time.perf_counter() - t0) * 1e3
+
+    for _ in range(args.warmup):
+        run_all()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if dist is not None:
+        import torch
+        dist.barrier()
+        torch.cuda.synchronize()
+    wall, its, pcg, launches = 0.0, 0, 0, 0
+    for _ in range(args.steps):
+        res, ms = run_all()
+        wall += ms
+        its += sum(r[1] for r in res)
+        pcg += sum(r[2] for r in res)
+        launches += sum(r[3] for r in res)
+    if dist is not None:
+        import torch
+        dist.barrier()
+        torch.cuda.synchronize()
+    clocks = sampler.stop() if sampler else None
+    (wall,), (its, pcg, launches) = sh.fold(dist, f"cuda:{local}" if dist is not None else "cpu", [wall], [its, pcg, launches])
+    if rank == 0:
+        n_c, E = ctxs[0].problem_size()
+        line = dict(metric="non-rigid LM iterations/s, batch of independent 10k-correspondence frame pairs", value=its / (wall * 1e-3),
+                    unit="LM it/s", n_gpus=world, steps=args.steps, warmup=args.warmup, ms_per_step=wall / args.steps,
+                    higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64", data="synthetic",
+                    config=dict(workload="config5: batch of independent config-2 frame pairs, sharded by problem index",
+                                correspondences_per_problem=n_c, directed_edges_per_problem=E, problems_per_gpu=per_gpu,
+                                problems=per_gpu * world, streams_per_gpu=len(ctxs), lm_iters_per_problem=lm_iters,
+                                pcg_rtol=args.pcg_rtol, pcg_iters_per_lm_iter=pcg / max(1, its),
+                                timing="host clock around the synchronised step (concurrent streams), max over ranks; includes "
+                                       "per-problem upload and download", l2="per-problem working set ~10 MB: L2 resident by design"),
+                    e2e=dict(value=its / (wall * 1e-3), unit="LM it/s", h2d_bytes_per_step=int(len(probs) * (n_c * 96 + E * 12)),
+                             d2h_bytes_per_step=int(len(probs) * n_c * 24)),
+                    gpu_launches=int(launches), clocks=clocks, roofline=None, cpu_baseline=None)
+        print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+    for c in ctxs:
+        c.close()
     return 0
 
 
