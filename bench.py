@@ -43,6 +43,20 @@ def parse():
     return ap.parse_args()
 
 
+class _stdout_to_stderr:
+    """keep the one-JSON-line contract: anything a library writes to fd 1 meanwhile goes to stderr"""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+
+    def __exit__(self, *a):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+
+
 # ---------------------------------------------------------------------------------------------- workload
 def make_scene(pkg, args, seed):
     wl = pkg_workloads(pkg)
@@ -177,7 +191,9 @@ def main():
         import torch
         import torch.distributed as dist
         torch.cuda.set_device(local)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        with _stdout_to_stderr():                      # NCCL prints its version banner on stdout
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            dist.barrier()
     ctx = pkg.Context(local)
     sc = make_scene(pkg, args, seed=rank)
     prob = prepare(pkg, ctx, sc, args)
@@ -303,7 +319,9 @@ def main_batch(args, rank, world, local):
         import torch
         import torch.distributed as dist
         torch.cuda.set_device(local)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        with _stdout_to_stderr():                      # NCCL prints its version banner on stdout
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            dist.barrier()
     n = args.n if args.n != 1_000_000 else 10_000
     per_gpu = args.problems or 16
     mine = sh.shard(per_gpu * world, world, rank)
