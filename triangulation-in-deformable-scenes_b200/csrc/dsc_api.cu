@@ -58,6 +58,7 @@ struct dsc_ctx {
     int *rowptr = nullptr, *col = nullptr;
     double* wgt = nullptr;
     double* Je = nullptr;                 // per directed edge {u, m, g}
+    unsigned short* erow = nullptr;       // per directed edge: row index inside its kTile tile
     double *b = nullptr, *D = nullptr, *U = nullptr, *Minv = nullptr;
     double* vec[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // x r z w p s
     double* small = nullptr;              // 6 x 8 global vectors + Ginv(64)
@@ -208,6 +209,7 @@ extern "C" int dsc_create(int device, dsc_ctx** out) {
     if (cudaMalloc(&ctx->bpart, sizeof(double) * kMaxBlocks * 8) != cudaSuccess) return bail(DSC_ERR_ALLOC);
     if (cudaMallocHost(&ctx->h_pinned, sizeof(double) * kMaxBlocks * kLinPart) != cudaSuccess) return bail(DSC_ERR_ALLOC);
     cudaMemset(ctx->errflag, 0, sizeof(int));
+    if (cudaFuncSetAttribute(cg_spmv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSpmvSmem) != cudaSuccess) return bail(DSC_ERR_CUDA);
     *out = ctx;
     return DSC_OK;
 }
@@ -221,7 +223,7 @@ extern "C" void dsc_destroy(dsc_ctx* ctx) {
     dev_free(ctx->X1f); dev_free(ctx->X2f); dev_free(ctx->d_perm);
     dev_free(ctx->P); dev_free(ctx->Ptrial); dev_free(ctx->P0); dev_free(ctx->Q);
     dev_free(ctx->uv); dev_free(ctx->dm); dev_free(ctx->isg);
-    dev_free(ctx->rowptr); dev_free(ctx->col); dev_free(ctx->wgt); dev_free(ctx->Je);
+    dev_free(ctx->rowptr); dev_free(ctx->col); dev_free(ctx->wgt); dev_free(ctx->Je); dev_free(ctx->erow);
     dev_free(ctx->b); dev_free(ctx->D); dev_free(ctx->U); dev_free(ctx->Minv);
     for (auto& v : ctx->vec) dev_free(v);
     dev_free(ctx->small); dev_free(ctx->Gcur); dev_free(ctx->Gtrial); dev_free(ctx->lin); dev_free(ctx->ctl);
@@ -487,7 +489,9 @@ extern "C" int dsc_set_graph(dsc_ctx* ctx, int n, const int32_t* rowptr, const i
         for (auto& pr2 : row) { cl[o] = pr2.first; ww[o] = pr2.second; ++o; }
     }
     if (E > ctx->ecap) {
-        CK(dev_alloc(ctx->col, (size_t)E)); CK(dev_alloc(ctx->wgt, (size_t)E)); CK(dev_alloc(ctx->Je, 9 * (size_t)E));
+        size_t Ep = (((size_t)E + 31) / 32) * 32 + 64;      // padded: the PCG operator reads whole 32-edge blocks
+        CK(dev_alloc(ctx->col, Ep)); CK(dev_alloc(ctx->wgt, Ep)); CK(dev_alloc(ctx->Je, 9 * Ep)); CK(dev_alloc(ctx->erow, Ep));
+        CK(cudaMemset(ctx->col, 0, sizeof(int) * Ep)); CK(cudaMemset(ctx->erow, 0, sizeof(unsigned short) * Ep)); CK(cudaMemset(ctx->Je, 0, sizeof(double) * 9 * Ep));
         ctx->ecap = E;
     }
     ctx->E = E;
@@ -496,6 +500,9 @@ extern "C" int dsc_set_graph(dsc_ctx* ctx, int n, const int32_t* rowptr, const i
     if (E > 0) {
         CK(cudaMemcpyAsync(ctx->col, cl.data(), sizeof(int) * E, cudaMemcpyHostToDevice, ctx->stream));
         CK(cudaMemcpyAsync(ctx->wgt, ww.data(), sizeof(double) * E, cudaMemcpyHostToDevice, ctx->stream));
+        std::vector<unsigned short> er((size_t)E);
+        for (int i = 0; i < n; ++i) for (int e = rp[i]; e < rp[i + 1]; ++e) er[e] = (unsigned short)(i % kTile);
+        CK(cudaMemcpy(ctx->erow, er.data(), sizeof(unsigned short) * E, cudaMemcpyHostToDevice));
     }
     CK(cudaStreamSynchronize(ctx->stream));
     bool identity = true;
@@ -626,7 +633,7 @@ static int run_pcg(dsc_ctx* ctx, const WeightsDev& W, double lambda, int* iters_
     CK(cudaMemsetAsync(ctx->errflag, 0, sizeof(int), ctx->stream));
     precond_kernel<<<nbv, kThreads, 0, ctx->stream>>>(n, ctx->D, lambda, ctx->lin, ctx->Minv, Ginv, ctx->errflag);
     cg_init_kernel<<<nbv, kThreads, 0, ctx->stream>>>(n, ctx->b, ctx->lin, ctx->Minv, Ginv, v, ctx->gpart[0], ctx->ctl);
-    cg_spmv_kernel<<<nbs, kThreads, 0, ctx->stream>>>(n, (size_t)ctx->E, ctx->P, ctx->Je, ctx->U, ctx->rowptr, ctx->col, ctx->Gcur, ctx->pair, W,
+    cg_spmv_kernel<<<nbs, kThreads, kSpmvSmem, ctx->stream>>>(n, (size_t)ctx->E, ctx->P, ctx->Je, ctx->U, ctx->rowptr, ctx->col, ctx->erow, ctx->Gcur, ctx->pair, W,
                                                      lambda, v.z, v.zg, v.w, ctx->dpart, ctx->bpart, ctx->lin, ctx->ctl);
     ctx->launches += 3;
     double rtol2 = ctx->pcg.rtol * ctx->pcg.rtol;
@@ -638,7 +645,7 @@ static int run_pcg(dsc_ctx* ctx, const WeightsDev& W, double lambda, int* iters_
             cg_update_kernel<<<nbv, kThreads, 0, ctx->stream>>>(n, k & 1, k == 0 ? 1 : 0, ctx->Minv, Ginv, ctx->lin, lambda, v,
                                                                ctx->gpart[k & 1], ctx->gpart[(k + 1) & 1], ctx->dpart, ctx->bpart, nbs,
                                                                ctx->ctl, rtol2);
-            cg_spmv_kernel<<<nbs, kThreads, 0, ctx->stream>>>(n, (size_t)ctx->E, ctx->P, ctx->Je, ctx->U, ctx->rowptr, ctx->col, ctx->Gcur, ctx->pair, W,
+            cg_spmv_kernel<<<nbs, kThreads, kSpmvSmem, ctx->stream>>>(n, (size_t)ctx->E, ctx->P, ctx->Je, ctx->U, ctx->rowptr, ctx->col, ctx->erow, ctx->Gcur, ctx->pair, W,
                                                              lambda, v.z, v.zg, v.w, ctx->dpart, ctx->bpart, ctx->lin, ctx->ctl);
             ctx->launches += 2;
         }
@@ -841,7 +848,7 @@ extern "C" int dsc_debug_matvec(dsc_ctx* ctx, const dsc_weights* w, double lambd
     if (n) CK(cudaMemcpyAsync(v.z, hz.data(), sizeof(double) * 6 * n, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(v.zg, x, sizeof(double) * 8, cudaMemcpyHostToDevice, ctx->stream));
     int nbs = grid_spmv(ctx, n);
-    cg_spmv_kernel<<<nbs, kThreads, 0, ctx->stream>>>(n, (size_t)ctx->E, ctx->P, ctx->Je, ctx->U, ctx->rowptr, ctx->col, ctx->Gcur, ctx->pair, W,
+    cg_spmv_kernel<<<nbs, kThreads, kSpmvSmem, ctx->stream>>>(n, (size_t)ctx->E, ctx->P, ctx->Je, ctx->U, ctx->rowptr, ctx->col, ctx->erow, ctx->Gcur, ctx->pair, W,
                                                      lambda, v.z, v.zg, v.w, ctx->dpart, ctx->bpart, ctx->lin, nullptr);
     ctx->launches++;
     CK(cudaGetLastError());
@@ -890,7 +897,7 @@ extern "C" int dsc_profile_kernels(dsc_ctx* ctx, const dsc_weights* w, int warm,
     ctx->launches += 2;
     double N = (double)n, E = (double)ctx->E;
     double by[DSC_K_COUNT];
-    by[DSC_K_SPMV] = 260.0 * N + 76.0 * E;        // X1(32) z(48) U(128) rowptr(4) | col(4) Je(72) | write w(48)
+    by[DSC_K_SPMV] = 260.0 * N + 78.0 * E;        // X1(32) z(48) U(128) rowptr(4) | col(4) erow(2) Je(72) | write w(48)
     by[DSC_K_UPDATE] = 696.0 * N;                 // read z w p s x r Minv, write p s x r z
     by[DSC_K_LINEARIZE] = 508.0 * N + 84.0 * E;   // P Q uv dm isg rowptr | col w | write b D U Je
     by[DSC_K_COST] = 140.0 * N + 12.0 * E;        // P Q uv dm isg rowptr | col w
@@ -909,7 +916,7 @@ extern "C" int dsc_profile_kernels(dsc_ctx* ctx, const dsc_weights* w, int warm,
         return DSC_OK;
     };
     s = time_it(DSC_K_SPMV, [&]() {
-        cg_spmv_kernel<<<nbp, kThreads, 0, ctx->stream>>>(n, (size_t)ctx->E, ctx->P, ctx->Je, ctx->U, ctx->rowptr, ctx->col, ctx->Gcur, ctx->pair, W,
+        cg_spmv_kernel<<<nbp, kThreads, kSpmvSmem, ctx->stream>>>(n, (size_t)ctx->E, ctx->P, ctx->Je, ctx->U, ctx->rowptr, ctx->col, ctx->erow, ctx->Gcur, ctx->pair, W,
                                                          lambda, v.z, v.zg, v.w, ctx->dpart, ctx->bpart, ctx->lin, nullptr);
     });
     if (s) return s;

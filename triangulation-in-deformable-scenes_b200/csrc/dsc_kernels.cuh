@@ -9,7 +9,7 @@
 //   dm     double2[n]    depth measurements (KF1, KF2)
 //   isg    float2[n]     KeyFrame::getInvSigma2(octave) of the two observations
 //   U      double[n][16] unary Hessian record {U1[6], U2[6], kd1, kd2, 0, 0}      128 B = 1 line
-//   Je     double[9][E]  per directed edge {u, m, g}: the ARAP Jacobian record streamed by the PCG operator
+//   Je     double[E/32][9][32] per directed edge {u, m, g}: ARAP Jacobian record streamed by the PCG operator
 //   D      double[n][21] packed upper 6x6 diagonal block of H (block-Jacobi preconditioner source)
 //   Minv   double[n][21] packed inverse of D + lambda I
 //   vectors b, x, r, z, w, p, s: double[n][6] {d/dX1, d/dX2}; the 8 global unknowns
@@ -151,6 +151,10 @@ DSC_D void load_q(const double* __restrict__ Q, int i, double* q) {
     double4 u = ldg256(p);
     q[0] = u.x; q[1] = u.y; q[2] = u.z; q[3] = u.w;
 }
+
+// Je layout: blocks of 32 consecutive edges, 9 planes of 32 doubles inside a block ("AoSoA"): a warp that
+// handles edges 32c..32c+31 reads plane k as one 256-byte line at a compile-time offset.
+DSC_HD size_t je_index(size_t e, int k) { return (e >> 5) * 288 + (size_t)k * 32 + (e & 31); }
 
 // One directed ARAP edge (i -> j).  EdgeARAP::computeError, g2oTypes.h:310-339:
 //   e = w (|(d2 - Ri d1)/A|^2 + |(-d2 + Rj d1)/A|^2) + |Rg (X2i + X2j) - 2 t - (X1i + X1j)|^2
@@ -489,9 +493,9 @@ linearize_kernel(int n, size_t nE, const double* __restrict__ P, const double* _
                 ArapGrad g;
                 arap_edge<true>(Pi, Pj, qi, qj, wgt[e], W.inv_area, G, g);
                 {   // per-edge Jacobian record streamed by the PCG operator: u, m, g (72 B)
-                    double* je = Je + (size_t)e;            // 9 planes of nE doubles: coalesced across the lanes
-                    je[0] = g.u.x; je[nE] = g.u.y; je[2 * nE] = g.u.z; je[3 * nE] = g.m.x; je[4 * nE] = g.m.y; je[5 * nE] = g.m.z;
-                    je[6 * nE] = g.g.x; je[7 * nE] = g.g.y; je[8 * nE] = g.g.z;
+                    const double jv[9] = {g.u.x, g.u.y, g.u.z, g.m.x, g.m.y, g.m.z, g.g.x, g.g.y, g.g.z};
+#pragma unroll
+                    for (int k = 0; k < 9; ++k) Je[je_index((size_t)e, k)] = jv[k];
                 }
                 double gi[6] = {g.gi1.x, g.gi1.y, g.gi1.z, g.gi2.x, g.gi2.y, g.gi2.z};
                 double gt[6] = {g.gw.x, g.gw.y, g.gw.z, g.gv.x, g.gv.y, g.gv.z};
@@ -748,145 +752,187 @@ cg_init_kernel(int n, const double* __restrict__ b, const LinGlobal* __restrict_
 //     Am = sum_e 2W s_e m, Ag = sum_e 2W s_e g, Au = sum_e 2W s_e u          (per vertex, over its CSR row)
 //     w_i1 = -Am - 2 Ag,   w_i2 = Au + 2 Rg^T Ag
 //     T_g rows: the directed twins carry the same s_e and g, so  w_w = 2 sum_i X1i x Ag_i,  w_v = -2 sum_i Ag_i.
-// A block owns a tile of kTile consecutive correspondences (space-filling-curve order): their z, X1 and
-// row pointers are staged in shared memory with coalesced loads, and a neighbour inside the tile is served
-// from shared memory; only halo neighbours are gathered from L2.  dpart[grid]: partial z.w (global rows
-// included), bpart[grid][8]: partial global rows (T_g from the ARAP edges, s1/s2 from the depth edges).
+// Work decomposition: a block owns a tile of kTile consecutive correspondences (space-filling-curve order); their
+// z, X1 and row pointers are staged in shared memory with coalesced loads and a neighbour inside the tile is
+// served from shared memory (only halo neighbours are gathered from L2).  Edge phase: each warp owns 64 rows of
+// the tile and walks the 32-edge blocks that hold THEIR edges, one edge per lane (coalesced Je/col/erow streams,
+// every lane busy, the loads of two blocks issued before any arithmetic).  The 9 partial sums of a block are
+// folded per row by a SEGMENTED reduction: lanes park their values in a per-warp shared-memory slab, the heads
+// of the row segments are found with one ballot, and lane p sums (segment p/9, component p%9) into the row's
+// accumulator (rows never leave their warp, so no atomics).  Vertex phase: thread (vertex, component) forms the
+// output row, coalesced w store.   dpart[grid]: partial z.w (global rows included), bpart[grid][8]: global rows.
 constexpr int kTile = 512;
+constexpr int kWarps = kThreads / 32;
+constexpr int kRowsPerWarp = kTile / kWarps;
+constexpr int kStage = 9 * 33 + 1;     // per-warp slab: 9 components x (32 lanes + 1 pad)
+constexpr size_t kSpmvSmem = sizeof(double) * (kTile * 6 + kTile * 4 + kTile * 9 + kWarps * kStage) + sizeof(int) * (kTile + 4 + kWarps * 72);
+
 __global__ void __launch_bounds__(kThreads, 2)
 cg_spmv_kernel(int n, size_t nE, const double* __restrict__ P, const double* __restrict__ Je, const double* __restrict__ U,
-               const int* __restrict__ rowptr, const int* __restrict__ col,
+               const int* __restrict__ rowptr, const int* __restrict__ col, const unsigned short* __restrict__ erow,
                const Globals* __restrict__ Gp, const __grid_constant__ PairDev pr, const __grid_constant__ WeightsDev W,
                double lambda, const double* __restrict__ z, const double* __restrict__ zg, double* __restrict__ w,
                double* __restrict__ dpart, double* __restrict__ bpart,
                const LinGlobal* __restrict__ lin, const CgControl* __restrict__ ctl) {
-    __shared__ double sz[kTile * 6];
-    __shared__ double sx[kTile * 3];
-    __shared__ int srp[kTile + 1];
-    __shared__ double sred[3 * 8 * (kThreads / 32)];
+    extern __shared__ double smem_d[];
+    double* sz = smem_d;                       // [kTile][6]
+    double* sx = sz + kTile * 6;               // [kTile][4]  (X1.xyz, pad)
+    double* sacc = sx + kTile * 4;             // [kTile][9]  Am | Ag | Au
+    double* sstage = sacc + kTile * 9;         // [kWarps][kStage]
+    int* srp = reinterpret_cast<int*>(sstage + kWarps * kStage);   // [kTile + 4]
+    int* sseg = srp + kTile + 4;               // [kWarps][72]: 0..32 segment starts, 36..67 row of lane
+    __shared__ double sred[kThreads * 3];
     __shared__ double Rg[9];
     __shared__ double zgs[8];
     if (ctl && (ctl->converged || ctl->breakdown)) return;   // flags are only written by an EARLIER launch
     if (threadIdx.x < 9) Rg[threadIdx.x] = Gp->Rg[threadIdx.x];
     if (threadIdx.x < 8) zgs[threadIdx.x] = zg[threadIdx.x];
-    const int lane = threadIdx.x & (kLanes - 1);
-    const int grp = threadIdx.x / kLanes;
-    // epilogue role of this lane: output component `lane` (0..5) = row lane%3 of camera lane/3
-    const int ecam = lane >= 3 ? 1 : 0, erow = lane - 3 * ecam;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double* stg = sstage + warp * kStage;
+    int* seg = sseg + warp * 72;
+    // vertex-phase role: output component `role` of vertex tid / 6 (+ 42 per trip); threads 252..255 idle there
+    const int role = threadIdx.x % 6, ecam = role >= 3 ? 1 : 0, er = role - 3 * ecam;
     const double* Rc = ecam == 0 ? pr.R1 : pr.R2;
-    const double nrow = lane < 6 ? Rc[6 + erow] : 0.0;
-    double accb = 0.0, accs = 0.0, accd = 0.0;        // this lane's T_g border component, s border, z.w
+    const double nrow = Rc[6 + er];
+    double accb = 0.0, accs = 0.0, accd = 0.0;        // this thread's T_g border component, s border, z.w
     const int ntiles = (n + kTile - 1) / kTile;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int v0 = tile * kTile;
         const int nv = min(kTile, n - v0);
         __syncthreads();
-        {   // stage z, X1, rowptr of the tile (coalesced)
+        {   // stage z, X1, rowptr of the tile (coalesced), clear the accumulators
             const double2* zsrc = reinterpret_cast<const double2*>(z + 6 * (size_t)v0);
             double2* zdst = reinterpret_cast<double2*>(sz);
             for (int k = threadIdx.x; k < nv * 3; k += kThreads) zdst[k] = zsrc[k];
             const double4* psrc = reinterpret_cast<const double4*>(P) + v0;
-            for (int k = threadIdx.x; k < nv; k += kThreads) {
-                double4 x = ldg256(psrc + k);
-                sx[3 * k] = x.x; sx[3 * k + 1] = x.y; sx[3 * k + 2] = x.z;
-            }
+            double4* xdst = reinterpret_cast<double4*>(sx);
+            for (int k = threadIdx.x; k < nv; k += kThreads) xdst[k] = ldg256(psrc + k);
             for (int k = threadIdx.x; k <= nv; k += kThreads) srp[k] = rowptr[v0 + k];
+            for (int k = threadIdx.x; k < nv * 9; k += kThreads) sacc[k] = 0.0;
         }
         __syncthreads();
         const D3 zw = d3(zgs[0], zgs[1], zgs[2]);
         const D3 zv2 = d3(2.0 * zgs[3], 2.0 * zgs[4], 2.0 * zgs[5]);
-        for (int il = grp; il < kTile; il += kGroups) {
-            const bool act = il < nv;
-            D3 Am = d3(0, 0, 0), Ag = d3(0, 0, 0), Au = d3(0, 0, 0);
-            D3 zi1 = d3(0, 0, 0), zi2 = d3(0, 0, 0), X1i = d3(0, 0, 0);
-            if (act) {
-                zi1 = d3(sz[6 * il], sz[6 * il + 1], sz[6 * il + 2]);
-                zi2 = d3(sz[6 * il + 3], sz[6 * il + 4], sz[6 * il + 5]);
-                X1i = d3(sx[3 * il], sx[3 * il + 1], sx[3 * il + 2]);
-                const int e1 = srp[il + 1];
-                for (int e = srp[il] + lane; e < e1; e += kLanes) {
-                    const int j = __ldg(col + e);
-                    const double* je = Je + (size_t)e;
-                    D3 u = d3(__ldg(je), __ldg(je + nE), __ldg(je + 2 * nE));
-                    D3 m = d3(__ldg(je + 3 * nE), __ldg(je + 4 * nE), __ldg(je + 5 * nE));
-                    D3 g = d3(__ldg(je + 6 * nE), __ldg(je + 7 * nE), __ldg(je + 8 * nE));
+        const double2* sz2 = reinterpret_cast<const double2*>(sz);
+        const double2* sx2 = reinterpret_cast<const double2*>(sx);
+        // ---- edge phase
+        const int r0 = warp * kRowsPerWarp, r1 = min(r0 + kRowsPerWarp, nv);
+        if (r0 < nv) {
+            const int ebeg = srp[r0], eend = srp[r1];
+            for (int blk = ebeg >> 5; blk * 32 < eend; blk += 2) {
+                int jn[2], rw[2];
+                double je[2][9];
+                bool ok[2];
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {            // every streaming load of both 32-edge blocks first
+                    const int e = (blk + h) * 32 + lane;
+                    ok[h] = e >= ebeg && e < eend;
+                    const bool ld = (blk + h) * 32 < eend;       // warp-uniform: block exists for this warp
+                    jn[h] = ld ? __ldg(col + e) : 0;
+                    rw[h] = ld ? (int)__ldg(erow + e) : 0;
+                    const double* jb = Je + (size_t)(blk + h) * 288 + lane;
+#pragma unroll
+                    for (int k = 0; k < 9; ++k) je[h][k] = ld ? __ldg(jb + k * 32) : 0.0;
+                }
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    if ((blk + h) * 32 >= eend) break;   // warp-uniform
+                    const int il = ok[h] ? rw[h] : r0;
+                    const double2 a0 = sz2[3 * il], a1 = sz2[3 * il + 1], a2 = sz2[3 * il + 2];
+                    const D3 zi1 = d3(a0.x, a0.y, a1.x), zi2 = d3(a1.y, a2.x, a2.y);
+                    const double2 xa = sx2[2 * il], xb = sx2[2 * il + 1];
+                    const D3 X1i = d3(xa.x, xa.y, xb.x);
                     D3 zj1, zj2, X1j;
+                    const int j = ok[h] ? jn[h] : v0 + r0;
                     const unsigned jl = (unsigned)(j - v0);
                     if (jl < (unsigned)nv) {
-                        zj1 = d3(sz[6 * jl], sz[6 * jl + 1], sz[6 * jl + 2]);
-                        zj2 = d3(sz[6 * jl + 3], sz[6 * jl + 4], sz[6 * jl + 5]);
-                        X1j = d3(sx[3 * jl], sx[3 * jl + 1], sx[3 * jl + 2]);
+                        const double2 b0 = sz2[3 * jl], b1 = sz2[3 * jl + 1], b2 = sz2[3 * jl + 2];
+                        zj1 = d3(b0.x, b0.y, b1.x); zj2 = d3(b1.y, b2.x, b2.y);
+                        const double2 ya = sx2[2 * jl], yb = sx2[2 * jl + 1];
+                        X1j = d3(ya.x, ya.y, yb.x);
                     } else {
                         load6(z, j, zj1, zj2);
                         double4 xj = ldg256(reinterpret_cast<const double4*>(P) + (size_t)j);
                         X1j = d3(xj.x, xj.y, xj.z);
                     }
-                    D3 S1 = X1i + X1j;
-                    D3 t = mul(Rg, zi2 + zj2) - (zi1 + zj1) + cross(zw, S1) - zv2;
-                    double s = dot(u, zi2 - zj2) - dot(m, zi1 - zj1) + 2.0 * dot(g, t);
-                    double w2 = 2.0 * W.arap_info * s;
-                    Am = Am + w2 * m; Ag = Ag + w2 * g; Au = Au + w2 * u;
+                    const D3 u = d3(je[h][0], je[h][1], je[h][2]), m = d3(je[h][3], je[h][4], je[h][5]), g = d3(je[h][6], je[h][7], je[h][8]);
+                    const D3 S1 = X1i + X1j;
+                    const D3 t = mul(Rg, zi2 + zj2) - (zi1 + zj1) + cross(zw, S1) - zv2;
+                    const double s = dot(u, zi2 - zj2) - dot(m, zi1 - zj1) + 2.0 * dot(g, t);
+                    const double w2 = ok[h] ? 2.0 * W.arap_info * s : 0.0;
+                    // park the 9 contributions, find the row segments (CSR order => rows ascend along the lanes)
+                    stg[0 * 33 + lane] = w2 * m.x; stg[1 * 33 + lane] = w2 * m.y; stg[2 * 33 + lane] = w2 * m.z;
+                    stg[3 * 33 + lane] = w2 * g.x; stg[4 * 33 + lane] = w2 * g.y; stg[5 * 33 + lane] = w2 * g.z;
+                    stg[6 * 33 + lane] = w2 * u.x; stg[7 * 33 + lane] = w2 * u.y; stg[8 * 33 + lane] = w2 * u.z;
+                    const int key = ok[h] ? il : -1 - lane;
+                    const int kprev = __shfl_up_sync(0xffffffffu, key, 1);
+                    const bool head = ok[h] && (lane == 0 || kprev != key);
+                    const unsigned hmask = __ballot_sync(0xffffffffu, head);
+                    const unsigned omask = __ballot_sync(0xffffffffu, ok[h]);
+                    const int nseg = __popc(hmask);
+                    if (head) { const int r = __popc(hmask & ((1u << lane) - 1u)); seg[r] = lane; seg[36 + r] = il; }
+                    if (lane == 0) seg[nseg] = 32 - __clz(omask);          // one past the last valid lane
+                    __syncwarp();
+                    for (int p = lane; p < nseg * 9; p += 32) {
+                        const int r = p / 9, k = p - 9 * r;
+                        const int ta = seg[r], tb = seg[r + 1];
+                        double sum = 0.0;
+                        for (int t = ta; t < tb; ++t) sum += stg[k * 33 + t];
+                        sacc[9 * seg[36 + r] + k] += sum;
+                    }
+                    __syncwarp();
                 }
             }
-            double o[9] = {Am.x, Am.y, Am.z, Ag.x, Ag.y, Ag.z, Au.x, Au.y, Au.z};
-#pragma unroll
-            for (int k = 0; k < 9; ++k) o[k] = group_sum(o[k]);     // xor butterfly: every lane holds the sums
-            if (act && lane < 6) {
-                // lane c computes output component c: [-Am - 2 Ag | Au + 2 Rg^T Ag] + U z + kd n z_s + lambda z
+        }
+        __syncthreads();
+        // ---- vertex phase: thread = (vertex, output component)
+        if (threadIdx.x < 252) {
+            for (int il = threadIdx.x / 6; il < nv; il += 42) {
                 const int i = v0 + il;
                 const double* Ui = U + 16 * (size_t)i;
-                const double zc0 = ecam == 0 ? zi1.x : zi2.x, zc1 = ecam == 0 ? zi1.y : zi2.y, zc2 = ecam == 0 ? zi1.z : zi2.z;
-                const double ag_r = erow == 0 ? o[3] : (erow == 1 ? o[4] : o[5]);
-                double base;
-                if (ecam == 0) base = -(erow == 0 ? o[0] : (erow == 1 ? o[1] : o[2])) - 2.0 * ag_r;
-                else base = (erow == 0 ? o[6] : (erow == 1 ? o[7] : o[8])) + 2.0 * (Rg[erow] * o[3] + Rg[3 + erow] * o[4] + Rg[6 + erow] * o[5]);
-                // packed symmetric 3x3 row `erow`: indices (0,1,2) | (1,3,4) | (2,4,5)
-                const int i0 = erow, i1 = erow == 0 ? 1 : (erow == 1 ? 3 : 4), i2 = erow == 0 ? 2 : (erow == 1 ? 4 : 5);
-                const double us = __ldg(Ui + ecam * 6 + i0) * zc0 + __ldg(Ui + ecam * 6 + i1) * zc1 + __ldg(Ui + ecam * 6 + i2) * zc2;
+                const int i1 = er == 0 ? 1 : (er == 1 ? 3 : 4), i2 = er == 0 ? 2 : (er == 1 ? 4 : 5);
+                const double uu0 = __ldg(Ui + ecam * 6 + er), uu1 = __ldg(Ui + ecam * 6 + i1), uu2 = __ldg(Ui + ecam * 6 + i2);
                 const double kd = __ldg(Ui + 12 + ecam);
-                const double zme = erow == 0 ? zc0 : (erow == 1 ? zc1 : zc2);
-                const double out = base + us + kd * nrow * zgs[6 + ecam] + lambda * zme;
+                const double* a = sacc + 9 * il;
+                const double ag0 = a[3], ag1 = a[4], ag2 = a[5];
+                const double zc0 = sz[6 * il + 3 * ecam], zc1 = sz[6 * il + 3 * ecam + 1], zc2 = sz[6 * il + 3 * ecam + 2];
+                const double ag_r = er == 0 ? ag0 : (er == 1 ? ag1 : ag2);
+                double base;
+                if (ecam == 0) base = -a[er] - 2.0 * ag_r;
+                else base = a[6 + er] + 2.0 * (Rg[er] * ag0 + Rg[3 + er] * ag1 + Rg[6 + er] * ag2);
+                const double zme = er == 0 ? zc0 : (er == 1 ? zc1 : zc2);
+                const double out = base + uu0 * zc0 + uu1 * zc1 + uu2 * zc2 + kd * nrow * zgs[6 + ecam] + lambda * zme;
                 accs += kd * nrow * zme;                           // s1/s2 rows: kd (n . z)
                 accd += zme * out;
-                // T_g rows from the per-vertex sums: omega: 2 (X1i x Ag), upsilon: -2 Ag
-                if (ecam == 0) {
-                    const double cx = erow == 0 ? X1i.y * o[5] - X1i.z * o[4] : (erow == 1 ? X1i.z * o[3] - X1i.x * o[5] : X1i.x * o[4] - X1i.y * o[3]);
+                if (ecam == 0) {                                   // T_g rows: omega 2 (X1i x Ag), upsilon -2 Ag
+                    const double x0 = sx[4 * il], x1 = sx[4 * il + 1], x2 = sx[4 * il + 2];
+                    const double cx = er == 0 ? x1 * ag2 - x2 * ag1 : (er == 1 ? x2 * ag0 - x0 * ag2 : x0 * ag1 - x1 * ag0);
                     accb += 2.0 * cx;
                 } else accb -= 2.0 * ag_r;
-                w[6 * (size_t)i + lane] = out;
+                w[6 * (size_t)i + role] = out;
             }
         }
     }
-    // role-preserving reduction: lanes with equal (lane % 8) across the block
-    {
-        double v3[3] = {accb, accs, accd};
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            double s = v3[k];
-            s += __shfl_xor_sync(0xffffffffu, s, 8);
-            s += __shfl_xor_sync(0xffffffffu, s, 16);
-            if ((threadIdx.x & 31) < 8) sred[(k * 8 + (threadIdx.x & 7)) * (kThreads / 32) + (threadIdx.x >> 5)] = s;
+    // role-preserving block reduction (roles repeat every 6 threads)
+    sred[threadIdx.x * 3] = accb; sred[threadIdx.x * 3 + 1] = accs; sred[threadIdx.x * 3 + 2] = accd;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double r[3][6];
+        for (int q = 0; q < 6; ++q) {
+            double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+            for (int t = q; t < 252; t += 6) { s0 += sred[t * 3]; s1 += sred[t * 3 + 1]; s2 += sred[t * 3 + 2]; }
+            r[0][q] = s0; r[1][q] = s1; r[2][q] = s2;
         }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            double r[3][8];
-            for (int k = 0; k < 3; ++k)
-                for (int q = 0; q < 8; ++q) {
-                    double s = 0.0;
-                    for (int wv = 0; wv < kThreads / 32; ++wv) s += sred[(k * 8 + q) * (kThreads / 32) + wv];
-                    r[k][q] = s;
-                }
-            double bg[8];
-            for (int q = 0; q < 6; ++q) bg[q] = r[0][q];
-            bg[6] = r[1][0] + r[1][1] + r[1][2];
-            bg[7] = r[1][3] + r[1][4] + r[1][5];
-            double dl = 0.0;
-            for (int q = 0; q < 6; ++q) dl += r[2][q];
-            for (int k = 0; k < 8; ++k) { bpart[8 * (size_t)blockIdx.x + k] = bg[k]; dl += zgs[k] * bg[k]; }
-            if (blockIdx.x == 0)     // diagonal of the global rows that is not inside the edge sums: (C_ss + lambda)
-                for (int k = 0; k < 8; ++k) dl += zgs[k] * ((k >= 6 ? lin->C[k * 8 + k] : 0.0) + lambda) * zgs[k];
-            dpart[blockIdx.x] = dl;
-        }
+        double bg[8];
+        for (int q = 0; q < 6; ++q) bg[q] = r[0][q];
+        bg[6] = r[1][0] + r[1][1] + r[1][2];
+        bg[7] = r[1][3] + r[1][4] + r[1][5];
+        double dl = 0.0;
+        for (int q = 0; q < 6; ++q) dl += r[2][q];
+        for (int k = 0; k < 8; ++k) { bpart[8 * (size_t)blockIdx.x + k] = bg[k]; dl += zgs[k] * bg[k]; }
+        if (blockIdx.x == 0)     // diagonal of the global rows that is not inside the edge sums: (C_ss + lambda)
+            for (int k = 0; k < 8; ++k) dl += zgs[k] * ((k >= 6 ? lin->C[k * 8 + k] : 0.0) + lambda) * zgs[k];
+        dpart[blockIdx.x] = dl;
     }
 }
 
