@@ -9,7 +9,7 @@ import __graft_entry__ as g
 
 pkg = g.package()
 args = bench.parse.__wrapped__() if hasattr(bench.parse, "__wrapped__") else None
-sys.argv = [sys.argv[0], "--points", sys.argv[1] if len(sys.argv) > 1 else "1000000"]
+sys.argv = [sys.argv[0], "--points", sys.argv[1] if len(sys.argv) > 1 else "1000000", "--k", sys.argv[2] if len(sys.argv) > 2 else "8"]
 args = bench.parse()
 ctx = pkg.Context(0)
 sc = bench.make_scene(pkg, args, 0)

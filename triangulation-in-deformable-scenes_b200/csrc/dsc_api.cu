@@ -58,7 +58,9 @@ struct dsc_ctx {
     int *rowptr = nullptr, *col = nullptr;
     double* wgt = nullptr;
     double* Je = nullptr;                 // per directed edge {u, m, g}
-    unsigned short* erow = nullptr;       // per directed edge: row index inside its kTile tile
+    int *ecol = nullptr, *sliceptr = nullptr;   // sliced ELL of the PCG operator (see dsc_set_graph)
+    long long nblk = 0, blkcap = 0;
+    int slcap = 0;
     double *b = nullptr, *D = nullptr, *U = nullptr, *Minv = nullptr;
     double* vec[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // x r z w p s
     double* small = nullptr;              // 6 x 8 global vectors + Ginv(64)
@@ -115,8 +117,8 @@ int grid_threads(const dsc_ctx* c, long long n) {           // thread-per-item k
     long long cap = (long long)c->sms * 8;
     return (int)std::max(1LL, std::min(nb, cap));
 }
-int grid_spmv(const dsc_ctx* c, long long n) {              // one block per kTile correspondences, 2 resident per SM
-    long long nb = (n + kTile - 1) / kTile;
+int grid_spmv(const dsc_ctx* c, long long n) {              // one block per tile of kSortGroup rows, persistent blocks
+    long long nb = (n + kSortGroup - 1) / kSortGroup;
     long long cap = (long long)c->sms * 2;
     return (int)std::max(1LL, std::min(nb, cap));
 }
@@ -209,7 +211,6 @@ extern "C" int dsc_create(int device, dsc_ctx** out) {
     if (cudaMalloc(&ctx->bpart, sizeof(double) * kMaxBlocks * 8) != cudaSuccess) return bail(DSC_ERR_ALLOC);
     if (cudaMallocHost(&ctx->h_pinned, sizeof(double) * kMaxBlocks * kLinPart) != cudaSuccess) return bail(DSC_ERR_ALLOC);
     cudaMemset(ctx->errflag, 0, sizeof(int));
-    if (cudaFuncSetAttribute(cg_spmv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSpmvSmem) != cudaSuccess) return bail(DSC_ERR_CUDA);
     *out = ctx;
     return DSC_OK;
 }
@@ -223,7 +224,7 @@ extern "C" void dsc_destroy(dsc_ctx* ctx) {
     dev_free(ctx->X1f); dev_free(ctx->X2f); dev_free(ctx->d_perm);
     dev_free(ctx->P); dev_free(ctx->Ptrial); dev_free(ctx->P0); dev_free(ctx->Q);
     dev_free(ctx->uv); dev_free(ctx->dm); dev_free(ctx->isg);
-    dev_free(ctx->rowptr); dev_free(ctx->col); dev_free(ctx->wgt); dev_free(ctx->Je); dev_free(ctx->erow);
+    dev_free(ctx->rowptr); dev_free(ctx->col); dev_free(ctx->wgt); dev_free(ctx->Je); dev_free(ctx->ecol); dev_free(ctx->sliceptr);
     dev_free(ctx->b); dev_free(ctx->D); dev_free(ctx->U); dev_free(ctx->Minv);
     for (auto& v : ctx->vec) dev_free(v);
     dev_free(ctx->small); dev_free(ctx->Gcur); dev_free(ctx->Gtrial); dev_free(ctx->lin); dev_free(ctx->ctl);
@@ -476,6 +477,16 @@ extern "C" int dsc_set_graph(dsc_ctx* ctx, int n, const int32_t* rowptr, const i
         std::sort(code.begin(), code.end());
         for (int i = 0; i < n; ++i) perm[i] = (int)(code[i] & 0xffffffffu);
     }
+    if (reorder && n > 1) {
+        // sliced-ELL friendliness: inside every group of kSortGroup Morton-consecutive rows, order by degree
+        // (descending, stable) so that the 32 rows of a warp slice have nearly equal length
+        for (int g0 = 0; g0 < n; g0 += kSortGroup) {
+            int g1 = std::min(n, g0 + kSortGroup);
+            std::stable_sort(perm.begin() + g0, perm.begin() + g1, [&](int a, int b2) {
+                return (rowptr[a + 1] - rowptr[a]) > (rowptr[b2 + 1] - rowptr[b2]);
+            });
+        }
+    }
     for (int i = 0; i < n; ++i) inv[perm[i]] = i;
     std::vector<int> rp(n + 1, 0), cl((size_t)E);
     std::vector<double> ww((size_t)E);
@@ -488,21 +499,44 @@ extern "C" int dsc_set_graph(dsc_ctx* ctx, int n, const int32_t* rowptr, const i
         std::sort(row.begin(), row.end());
         for (auto& pr2 : row) { cl[o] = pr2.first; ww[o] = pr2.second; ++o; }
     }
+    // sliced ELL of the PCG operator: slice = 32 consecutive rows (one warp), width = longest row of the slice;
+    // column k of slice s is "block" sliceptr[s] + k: 32 column indices and 9 x 32 Jacobian doubles (Je).
+    // Padding entries point at the row itself and keep an all-zero Jacobian record, so they add exactly 0.
+    int nslices = (n + 31) / 32;
+    std::vector<int> sp(nslices + 1, 0);
+    for (int sl = 0; sl < nslices; ++sl) {
+        int wmax = 0;
+        for (int i = sl * 32; i < std::min(n, sl * 32 + 32); ++i) wmax = std::max(wmax, rp[i + 1] - rp[i]);
+        sp[sl + 1] = sp[sl] + wmax;
+    }
+    size_t nblk = (size_t)sp[nslices];
+    std::vector<int> ecol(nblk * 32);
+    for (int sl = 0; sl < nslices; ++sl)
+        for (int k = 0; k < sp[sl + 1] - sp[sl]; ++k)
+            for (int l = 0; l < 32; ++l) {
+                int i = sl * 32 + l;
+                int v = i < n ? i : 0;
+                if (i < n && k < rp[i + 1] - rp[i]) v = cl[rp[i] + k];
+                ecol[((size_t)sp[sl] + k) * 32 + l] = v;
+            }
     if (E > ctx->ecap) {
-        size_t Ep = (((size_t)E + 31) / 32) * 32 + 64;      // padded: the PCG operator reads whole 32-edge blocks
-        CK(dev_alloc(ctx->col, Ep)); CK(dev_alloc(ctx->wgt, Ep)); CK(dev_alloc(ctx->Je, 9 * Ep)); CK(dev_alloc(ctx->erow, Ep));
-        CK(cudaMemset(ctx->col, 0, sizeof(int) * Ep)); CK(cudaMemset(ctx->erow, 0, sizeof(unsigned short) * Ep)); CK(cudaMemset(ctx->Je, 0, sizeof(double) * 9 * Ep));
+        CK(dev_alloc(ctx->col, (size_t)E)); CK(dev_alloc(ctx->wgt, (size_t)E));
         ctx->ecap = E;
     }
-    ctx->E = E;
+    if ((long long)nblk > ctx->blkcap) {
+        CK(dev_alloc(ctx->ecol, nblk * 32)); CK(dev_alloc(ctx->Je, nblk * 288));
+        ctx->blkcap = (long long)nblk;
+    }
+    if (nslices + 1 > ctx->slcap) { CK(dev_alloc(ctx->sliceptr, (size_t)nslices + 1)); ctx->slcap = nslices + 1; }
+    ctx->E = E; ctx->nblk = (long long)nblk;
     ctx->area = area; ctx->ntri = n_triangles;
     CK(cudaMemcpyAsync(ctx->rowptr, rp.data(), sizeof(int) * (n + 1), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->sliceptr, sp.data(), sizeof(int) * (nslices + 1), cudaMemcpyHostToDevice, ctx->stream));
     if (E > 0) {
         CK(cudaMemcpyAsync(ctx->col, cl.data(), sizeof(int) * E, cudaMemcpyHostToDevice, ctx->stream));
         CK(cudaMemcpyAsync(ctx->wgt, ww.data(), sizeof(double) * E, cudaMemcpyHostToDevice, ctx->stream));
-        std::vector<unsigned short> er((size_t)E);
-        for (int i = 0; i < n; ++i) for (int e = rp[i]; e < rp[i + 1]; ++e) er[e] = (unsigned short)(i % kTile);
-        CK(cudaMemcpy(ctx->erow, er.data(), sizeof(unsigned short) * E, cudaMemcpyHostToDevice));
+        CK(cudaMemcpyAsync(ctx->ecol, ecol.data(), sizeof(int) * nblk * 32, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemsetAsync(ctx->Je, 0, sizeof(double) * nblk * 288, ctx->stream));
     }
     CK(cudaStreamSynchronize(ctx->stream));
     bool identity = true;
@@ -613,7 +647,7 @@ static CgVecs make_vecs(dsc_ctx* ctx) {
 
 static int run_linearize(dsc_ctx* ctx, const WeightsDev& W, LinGlobal* hlin) {
     int nb = grid_groups(ctx, ctx->n);
-    linearize_kernel<<<nb, kThreads, 0, ctx->stream>>>(ctx->n, (size_t)ctx->E, ctx->P, ctx->Q, ctx->uv, ctx->dm, ctx->isg, ctx->rowptr, ctx->col,
+    linearize_kernel<<<nb, kThreads, 0, ctx->stream>>>(ctx->n, ctx->sliceptr, ctx->P, ctx->Q, ctx->uv, ctx->dm, ctx->isg, ctx->rowptr, ctx->col,
                                                       ctx->wgt, ctx->Gcur, ctx->pair, W, ctx->b, ctx->D, ctx->U, ctx->Je, ctx->part);
     finalize_linearize_kernel<<<1, kThreads, 0, ctx->stream>>>(nb, ctx->part, ctx->lin);
     ctx->launches += 2;
@@ -633,7 +667,7 @@ static int run_pcg(dsc_ctx* ctx, const WeightsDev& W, double lambda, int* iters_
     CK(cudaMemsetAsync(ctx->errflag, 0, sizeof(int), ctx->stream));
     precond_kernel<<<nbv, kThreads, 0, ctx->stream>>>(n, ctx->D, lambda, ctx->lin, ctx->Minv, Ginv, ctx->errflag);
     cg_init_kernel<<<nbv, kThreads, 0, ctx->stream>>>(n, ctx->b, ctx->lin, ctx->Minv, Ginv, v, ctx->gpart[0], ctx->ctl);
-    cg_spmv_kernel<<<nbs, kThreads, kSpmvSmem, ctx->stream>>>(n, (size_t)ctx->E, ctx->P, ctx->Je, ctx->U, ctx->rowptr, ctx->col, ctx->erow, ctx->Gcur, ctx->pair, W,
+    cg_spmv_kernel<<<nbs, kThreads, 0, ctx->stream>>>(n, ctx->P, ctx->Je, ctx->U, ctx->sliceptr, ctx->ecol, ctx->Gcur, ctx->pair, W,
                                                      lambda, v.z, v.zg, v.w, ctx->dpart, ctx->bpart, ctx->lin, ctx->ctl);
     ctx->launches += 3;
     double rtol2 = ctx->pcg.rtol * ctx->pcg.rtol;
@@ -645,7 +679,7 @@ static int run_pcg(dsc_ctx* ctx, const WeightsDev& W, double lambda, int* iters_
             cg_update_kernel<<<nbv, kThreads, 0, ctx->stream>>>(n, k & 1, k == 0 ? 1 : 0, ctx->Minv, Ginv, ctx->lin, lambda, v,
                                                                ctx->gpart[k & 1], ctx->gpart[(k + 1) & 1], ctx->dpart, ctx->bpart, nbs,
                                                                ctx->ctl, rtol2);
-            cg_spmv_kernel<<<nbs, kThreads, kSpmvSmem, ctx->stream>>>(n, (size_t)ctx->E, ctx->P, ctx->Je, ctx->U, ctx->rowptr, ctx->col, ctx->erow, ctx->Gcur, ctx->pair, W,
+            cg_spmv_kernel<<<nbs, kThreads, 0, ctx->stream>>>(n, ctx->P, ctx->Je, ctx->U, ctx->sliceptr, ctx->ecol, ctx->Gcur, ctx->pair, W,
                                                              lambda, v.z, v.zg, v.w, ctx->dpart, ctx->bpart, ctx->lin, ctx->ctl);
             ctx->launches += 2;
         }
@@ -848,7 +882,7 @@ extern "C" int dsc_debug_matvec(dsc_ctx* ctx, const dsc_weights* w, double lambd
     if (n) CK(cudaMemcpyAsync(v.z, hz.data(), sizeof(double) * 6 * n, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(v.zg, x, sizeof(double) * 8, cudaMemcpyHostToDevice, ctx->stream));
     int nbs = grid_spmv(ctx, n);
-    cg_spmv_kernel<<<nbs, kThreads, kSpmvSmem, ctx->stream>>>(n, (size_t)ctx->E, ctx->P, ctx->Je, ctx->U, ctx->rowptr, ctx->col, ctx->erow, ctx->Gcur, ctx->pair, W,
+    cg_spmv_kernel<<<nbs, kThreads, 0, ctx->stream>>>(n, ctx->P, ctx->Je, ctx->U, ctx->sliceptr, ctx->ecol, ctx->Gcur, ctx->pair, W,
                                                      lambda, v.z, v.zg, v.w, ctx->dpart, ctx->bpart, ctx->lin, nullptr);
     ctx->launches++;
     CK(cudaGetLastError());
@@ -897,7 +931,7 @@ extern "C" int dsc_profile_kernels(dsc_ctx* ctx, const dsc_weights* w, int warm,
     ctx->launches += 2;
     double N = (double)n, E = (double)ctx->E;
     double by[DSC_K_COUNT];
-    by[DSC_K_SPMV] = 260.0 * N + 78.0 * E;        // X1(32) z(48) U(128) rowptr(4) | col(4) erow(2) Je(72) | write w(48)
+    by[DSC_K_SPMV] = 256.0 * N + 76.0 * (double)ctx->nblk * 32.0;   // X1 z U | ELL blocks: col(4) Je(72) per slot (padding included) | write w
     by[DSC_K_UPDATE] = 696.0 * N;                 // read z w p s x r Minv, write p s x r z
     by[DSC_K_LINEARIZE] = 508.0 * N + 84.0 * E;   // P Q uv dm isg rowptr | col w | write b D U Je
     by[DSC_K_COST] = 140.0 * N + 12.0 * E;        // P Q uv dm isg rowptr | col w
@@ -916,7 +950,7 @@ extern "C" int dsc_profile_kernels(dsc_ctx* ctx, const dsc_weights* w, int warm,
         return DSC_OK;
     };
     s = time_it(DSC_K_SPMV, [&]() {
-        cg_spmv_kernel<<<nbp, kThreads, kSpmvSmem, ctx->stream>>>(n, (size_t)ctx->E, ctx->P, ctx->Je, ctx->U, ctx->rowptr, ctx->col, ctx->erow, ctx->Gcur, ctx->pair, W,
+        cg_spmv_kernel<<<nbp, kThreads, 0, ctx->stream>>>(n, ctx->P, ctx->Je, ctx->U, ctx->sliceptr, ctx->ecol, ctx->Gcur, ctx->pair, W,
                                                          lambda, v.z, v.zg, v.w, ctx->dpart, ctx->bpart, ctx->lin, nullptr);
     });
     if (s) return s;
@@ -929,7 +963,7 @@ extern "C" int dsc_profile_kernels(dsc_ctx* ctx, const dsc_weights* w, int warm,
     });
     if (s) return s;
     s = time_it(DSC_K_LINEARIZE, [&]() {
-        linearize_kernel<<<nbs, kThreads, 0, ctx->stream>>>(n, (size_t)ctx->E, ctx->P, ctx->Q, ctx->uv, ctx->dm, ctx->isg, ctx->rowptr, ctx->col,
+        linearize_kernel<<<nbs, kThreads, 0, ctx->stream>>>(n, ctx->sliceptr, ctx->P, ctx->Q, ctx->uv, ctx->dm, ctx->isg, ctx->rowptr, ctx->col,
                                                            ctx->wgt, ctx->Gcur, ctx->pair, W, ctx->b, ctx->D, ctx->U, ctx->Je, ctx->part);
     });
     if (s) return s;

@@ -31,6 +31,7 @@ constexpr int kThreads = 256;
 constexpr int kLanes = 8;                       // lanes per correspondence
 constexpr int kGroups = kThreads / kLanes;      // correspondences per block-iteration
 constexpr int kMaxBlocks = 2048;
+constexpr int kSortGroup = 512;                 // rows are degree-sorted inside groups of this many (host, dsc_set_graph)
 
 struct PairDev {
     CamF cam1, cam2;
@@ -130,6 +131,7 @@ DSC_D double4 ldg256(const double4* p) {
     asm("ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w) : "l"(p));
     return r;
 }
+DSC_D void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 struct P8 { D3 a, b; };                             // X1, X2 of one correspondence
 DSC_D P8 load_P(const double* __restrict__ P, int n, int i) {
     const double4* p = reinterpret_cast<const double4*>(P);
@@ -455,7 +457,7 @@ cost_kernel(int n, const double* __restrict__ P, const double* __restrict__ Q, c
 // Per block: partial sums of chi2[3], max diagonal, global gradient bg[8], global block C (T-T 21 packed, s1, s2).
 constexpr int kLinPart = 3 + 1 + 8 + 21 + 2;   // 35
 __global__ void __launch_bounds__(kThreads)
-linearize_kernel(int n, size_t nE, const double* __restrict__ P, const double* __restrict__ Q, const float4* __restrict__ uv,
+linearize_kernel(int n, const int* __restrict__ sliceptr, const double* __restrict__ P, const double* __restrict__ Q, const float4* __restrict__ uv,
                  const double2* __restrict__ dm, const float2* __restrict__ isg, const int* __restrict__ rowptr,
                  const int* __restrict__ col, const double* __restrict__ wgt, const Globals* __restrict__ Gp,
                  const __grid_constant__ PairDev pr, const __grid_constant__ WeightsDev W,
@@ -485,7 +487,8 @@ linearize_kernel(int n, size_t nE, const double* __restrict__ P, const double* _
             double qi[4];
             load_q(Q, i, qi);
             int e1 = rowptr[i + 1];
-            for (int e = rowptr[i] + lane; e < e1; e += kLanes) {
+            const int e_first = rowptr[i];
+            for (int e = e_first + lane; e < e1; e += kLanes) {
                 int j = col[e];
                 P8 Pj = load_P(P, n, j);
                 double qj[4];
@@ -493,9 +496,11 @@ linearize_kernel(int n, size_t nE, const double* __restrict__ P, const double* _
                 ArapGrad g;
                 arap_edge<true>(Pi, Pj, qi, qj, wgt[e], W.inv_area, G, g);
                 {   // per-edge Jacobian record streamed by the PCG operator: u, m, g (72 B)
+                    // sliced-ELL slot of (row i, k-th edge): block sliceptr[i/32] + k, lane i%32
+                    const size_t jblk = ((size_t)__ldg(sliceptr + (i >> 5)) + (size_t)(e - e_first)) * 288 + (i & 31);
                     const double jv[9] = {g.u.x, g.u.y, g.u.z, g.m.x, g.m.y, g.m.z, g.g.x, g.g.y, g.g.z};
 #pragma unroll
-                    for (int k = 0; k < 9; ++k) Je[je_index((size_t)e, k)] = jv[k];
+                    for (int k = 0; k < 9; ++k) Je[jblk + k * 32] = jv[k];
                 }
                 double gi[6] = {g.gi1.x, g.gi1.y, g.gi1.z, g.gi2.x, g.gi2.y, g.gi2.z};
                 double gt[6] = {g.gw.x, g.gw.y, g.gw.z, g.gv.x, g.gv.y, g.gv.z};
@@ -752,184 +757,127 @@ cg_init_kernel(int n, const double* __restrict__ b, const LinGlobal* __restrict_
 //     Am = sum_e 2W s_e m, Ag = sum_e 2W s_e g, Au = sum_e 2W s_e u          (per vertex, over its CSR row)
 //     w_i1 = -Am - 2 Ag,   w_i2 = Au + 2 Rg^T Ag
 //     T_g rows: the directed twins carry the same s_e and g, so  w_w = 2 sum_i X1i x Ag_i,  w_v = -2 sum_i Ag_i.
-// Work decomposition: a block owns a tile of kTile consecutive correspondences (space-filling-curve order); their
-// z, X1 and row pointers are staged in shared memory with coalesced loads and a neighbour inside the tile is
-// served from shared memory (only halo neighbours are gathered from L2).  Edge phase: each warp owns 64 rows of
-// the tile and walks the 32-edge blocks that hold THEIR edges, one edge per lane (coalesced Je/col/erow streams,
-// every lane busy, the loads of two blocks issued before any arithmetic).  The 9 partial sums of a block are
-// folded per row by a SEGMENTED reduction: lanes park their values in a per-warp shared-memory slab, the heads
-// of the row segments are found with one ballot, and lane p sums (segment p/9, component p%9) into the row's
-// accumulator (rows never leave their warp, so no atomics).  Vertex phase: thread (vertex, component) forms the
-// output row, coalesced w store.   dpart[grid]: partial z.w (global rows included), bpart[grid][8]: global rows.
-constexpr int kTile = 512;
-constexpr int kWarps = kThreads / 32;
-constexpr int kRowsPerWarp = kTile / kWarps;
-constexpr int kStage = 9 * 33 + 1;     // per-warp slab: 9 components x (32 lanes + 1 pad)
-constexpr size_t kSpmvSmem = sizeof(double) * (kTile * 6 + kTile * 4 + kTile * 9 + kWarps * kStage) + sizeof(int) * (kTile + 4 + kWarps * 72);
-
+// Layout / work decomposition: sliced ELL.  A slice is 32 consecutive rows (correspondences) = one warp, lane l
+// owns row 32 s + l for the whole slice: its z_i / X1_i stay in registers, its three sums Am/Ag/Au accumulate in
+// registers, and NO cross-lane reduction is needed.  Column k of the slice is block sliceptr[s] + k: one coalesced
+// 128-byte line of neighbour indices and nine coalesced 256-byte lines of Jacobian records.  Rows are degree-sorted
+// inside groups of 512 on the host, so the 32 rows of a slice have (almost) the same length; padding slots point
+// at the row itself and carry an all-zero record.  Only z_j (48 B) and X1_j (32 B) are gathered (L1/L2: the
+// space-filling-curve order keeps neighbours close).  dpart[grid]: partial z.w (global rows included),
+// bpart[grid][8]: partial global rows (T_g from the ARAP sums, s1/s2 from the depth edges).
 __global__ void __launch_bounds__(kThreads, 2)
-cg_spmv_kernel(int n, size_t nE, const double* __restrict__ P, const double* __restrict__ Je, const double* __restrict__ U,
-               const int* __restrict__ rowptr, const int* __restrict__ col, const unsigned short* __restrict__ erow,
+cg_spmv_kernel(int n, const double* __restrict__ P, const double* __restrict__ Je, const double* __restrict__ U,
+               const int* __restrict__ sliceptr, const int* __restrict__ ecol,
                const Globals* __restrict__ Gp, const __grid_constant__ PairDev pr, const __grid_constant__ WeightsDev W,
                double lambda, const double* __restrict__ z, const double* __restrict__ zg, double* __restrict__ w,
                double* __restrict__ dpart, double* __restrict__ bpart,
                const LinGlobal* __restrict__ lin, const CgControl* __restrict__ ctl) {
-    extern __shared__ double smem_d[];
-    double* sz = smem_d;                       // [kTile][6]
-    double* sx = sz + kTile * 6;               // [kTile][4]  (X1.xyz, pad)
-    double* sacc = sx + kTile * 4;             // [kTile][9]  Am | Ag | Au
-    double* sstage = sacc + kTile * 9;         // [kWarps][kStage]
-    int* srp = reinterpret_cast<int*>(sstage + kWarps * kStage);   // [kTile + 4]
-    int* sseg = srp + kTile + 4;               // [kWarps][72]: 0..32 segment starts, 36..67 row of lane
-    __shared__ double sred[kThreads * 3];
+    __shared__ double sm[9 * (kThreads / 32)];
     __shared__ double Rg[9];
     __shared__ double zgs[8];
+    __shared__ double2 sz[kSortGroup * 3];             // z of the tile: 3 double2 per row
+    __shared__ double4 sx[kSortGroup];                 // X1 of the tile
     if (ctl && (ctl->converged || ctl->breakdown)) return;   // flags are only written by an EARLIER launch
     if (threadIdx.x < 9) Rg[threadIdx.x] = Gp->Rg[threadIdx.x];
     if (threadIdx.x < 8) zgs[threadIdx.x] = zg[threadIdx.x];
+    __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    double* stg = sstage + warp * kStage;
-    int* seg = sseg + warp * 72;
-    // vertex-phase role: output component `role` of vertex tid / 6 (+ 42 per trip); threads 252..255 idle there
-    const int role = threadIdx.x % 6, ecam = role >= 3 ? 1 : 0, er = role - 3 * ecam;
-    const double* Rc = ecam == 0 ? pr.R1 : pr.R2;
-    const double nrow = Rc[6 + er];
-    double accb = 0.0, accs = 0.0, accd = 0.0;        // this thread's T_g border component, s border, z.w
-    const int ntiles = (n + kTile - 1) / kTile;
+    const int wpb = kThreads / 32;
+    const D3 zw = d3(zgs[0], zgs[1], zgs[2]);
+    const D3 zv2 = d3(2.0 * zgs[3], 2.0 * zgs[4], 2.0 * zgs[5]);
+    double acc[9];                                     // T_g border (6), s1, s2 border, z.w
+#pragma unroll
+    for (int k = 0; k < 9; ++k) acc[k] = 0.0;
+    // A block owns a tile = one degree-sorted group of kSortGroup rows; the tile's z and X1 are staged in shared
+    // memory (coalesced) and a neighbour inside the tile is read from there; halo neighbours come from L2.
+    const int ntiles = (n + kSortGroup - 1) / kSortGroup;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int v0 = tile * kTile;
-        const int nv = min(kTile, n - v0);
+        const int v0 = tile * kSortGroup;
+        const int nv = min(kSortGroup, n - v0);
         __syncthreads();
-        {   // stage z, X1, rowptr of the tile (coalesced), clear the accumulators
+        {
             const double2* zsrc = reinterpret_cast<const double2*>(z + 6 * (size_t)v0);
-            double2* zdst = reinterpret_cast<double2*>(sz);
-            for (int k = threadIdx.x; k < nv * 3; k += kThreads) zdst[k] = zsrc[k];
+            for (int k = threadIdx.x; k < nv * 3; k += kThreads) sz[k] = zsrc[k];
             const double4* psrc = reinterpret_cast<const double4*>(P) + v0;
-            double4* xdst = reinterpret_cast<double4*>(sx);
-            for (int k = threadIdx.x; k < nv; k += kThreads) xdst[k] = ldg256(psrc + k);
-            for (int k = threadIdx.x; k <= nv; k += kThreads) srp[k] = rowptr[v0 + k];
-            for (int k = threadIdx.x; k < nv * 9; k += kThreads) sacc[k] = 0.0;
+            for (int k = threadIdx.x; k < nv; k += kThreads) sx[k] = ldg256(psrc + k);
         }
         __syncthreads();
-        const D3 zw = d3(zgs[0], zgs[1], zgs[2]);
-        const D3 zv2 = d3(2.0 * zgs[3], 2.0 * zgs[4], 2.0 * zgs[5]);
-        const double2* sz2 = reinterpret_cast<const double2*>(sz);
-        const double2* sx2 = reinterpret_cast<const double2*>(sx);
-        // ---- edge phase
-        const int r0 = warp * kRowsPerWarp, r1 = min(r0 + kRowsPerWarp, nv);
-        if (r0 < nv) {
-            const int ebeg = srp[r0], eend = srp[r1];
-            for (int blk = ebeg >> 5; blk * 32 < eend; blk += 2) {
-                int jn[2], rw[2];
-                double je[2][9];
-                bool ok[2];
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {            // every streaming load of both 32-edge blocks first
-                    const int e = (blk + h) * 32 + lane;
-                    ok[h] = e >= ebeg && e < eend;
-                    const bool ld = (blk + h) * 32 < eend;       // warp-uniform: block exists for this warp
-                    jn[h] = ld ? __ldg(col + e) : 0;
-                    rw[h] = ld ? (int)__ldg(erow + e) : 0;
-                    const double* jb = Je + (size_t)(blk + h) * 288 + lane;
-#pragma unroll
-                    for (int k = 0; k < 9; ++k) je[h][k] = ld ? __ldg(jb + k * 32) : 0.0;
-                }
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    if ((blk + h) * 32 >= eend) break;   // warp-uniform
-                    const int il = ok[h] ? rw[h] : r0;
-                    const double2 a0 = sz2[3 * il], a1 = sz2[3 * il + 1], a2 = sz2[3 * il + 2];
-                    const D3 zi1 = d3(a0.x, a0.y, a1.x), zi2 = d3(a1.y, a2.x, a2.y);
-                    const double2 xa = sx2[2 * il], xb = sx2[2 * il + 1];
-                    const D3 X1i = d3(xa.x, xa.y, xb.x);
-                    D3 zj1, zj2, X1j;
-                    const int j = ok[h] ? jn[h] : v0 + r0;
-                    const unsigned jl = (unsigned)(j - v0);
-                    if (jl < (unsigned)nv) {
-                        const double2 b0 = sz2[3 * jl], b1 = sz2[3 * jl + 1], b2 = sz2[3 * jl + 2];
-                        zj1 = d3(b0.x, b0.y, b1.x); zj2 = d3(b1.y, b2.x, b2.y);
-                        const double2 ya = sx2[2 * jl], yb = sx2[2 * jl + 1];
-                        X1j = d3(ya.x, ya.y, yb.x);
-                    } else {
-                        load6(z, j, zj1, zj2);
-                        double4 xj = ldg256(reinterpret_cast<const double4*>(P) + (size_t)j);
-                        X1j = d3(xj.x, xj.y, xj.z);
-                    }
-                    const D3 u = d3(je[h][0], je[h][1], je[h][2]), m = d3(je[h][3], je[h][4], je[h][5]), g = d3(je[h][6], je[h][7], je[h][8]);
-                    const D3 S1 = X1i + X1j;
-                    const D3 t = mul(Rg, zi2 + zj2) - (zi1 + zj1) + cross(zw, S1) - zv2;
-                    const double s = dot(u, zi2 - zj2) - dot(m, zi1 - zj1) + 2.0 * dot(g, t);
-                    const double w2 = ok[h] ? 2.0 * W.arap_info * s : 0.0;
-                    // park the 9 contributions, find the row segments (CSR order => rows ascend along the lanes)
-                    stg[0 * 33 + lane] = w2 * m.x; stg[1 * 33 + lane] = w2 * m.y; stg[2 * 33 + lane] = w2 * m.z;
-                    stg[3 * 33 + lane] = w2 * g.x; stg[4 * 33 + lane] = w2 * g.y; stg[5 * 33 + lane] = w2 * g.z;
-                    stg[6 * 33 + lane] = w2 * u.x; stg[7 * 33 + lane] = w2 * u.y; stg[8 * 33 + lane] = w2 * u.z;
-                    const int key = ok[h] ? il : -1 - lane;
-                    const int kprev = __shfl_up_sync(0xffffffffu, key, 1);
-                    const bool head = ok[h] && (lane == 0 || kprev != key);
-                    const unsigned hmask = __ballot_sync(0xffffffffu, head);
-                    const unsigned omask = __ballot_sync(0xffffffffu, ok[h]);
-                    const int nseg = __popc(hmask);
-                    if (head) { const int r = __popc(hmask & ((1u << lane) - 1u)); seg[r] = lane; seg[36 + r] = il; }
-                    if (lane == 0) seg[nseg] = 32 - __clz(omask);          // one past the last valid lane
-                    __syncwarp();
-                    for (int p = lane; p < nseg * 9; p += 32) {
-                        const int r = p / 9, k = p - 9 * r;
-                        const int ta = seg[r], tb = seg[r + 1];
-                        double sum = 0.0;
-                        for (int t = ta; t < tb; ++t) sum += stg[k * 33 + t];
-                        sacc[9 * seg[36 + r] + k] += sum;
-                    }
-                    __syncwarp();
-                }
+      for (int ls = warp; ls * 32 < nv; ls += wpb) {
+        const int sl = (v0 >> 5) + ls;
+        const int il = ls * 32 + lane;
+        const int i = v0 + il;
+        const bool act = il < nv;
+        const int ilc = act ? il : nv - 1;
+        const double2 a0 = sz[3 * ilc], a1 = sz[3 * ilc + 1], a2 = sz[3 * ilc + 2];
+        const D3 zi1 = d3(a0.x, a0.y, a1.x), zi2 = d3(a1.y, a2.x, a2.y);
+        const double4 xi = sx[ilc];
+        const D3 X1i = d3(xi.x, xi.y, xi.z);
+        const int b0 = __ldg(sliceptr + sl), b1 = __ldg(sliceptr + sl + 1);
+        D3 Am = d3(0, 0, 0), Ag = d3(0, 0, 0), Au = d3(0, 0, 0);
+        for (int bk = b0; bk < b1; ++bk) {
+            const int j = __ldg(ecol + (size_t)bk * 32 + lane);
+            const double* jb = Je + (size_t)bk * 288 + lane;
+            const D3 u = d3(__ldg(jb), __ldg(jb + 32), __ldg(jb + 64));
+            const D3 m = d3(__ldg(jb + 96), __ldg(jb + 128), __ldg(jb + 160));
+            const D3 g = d3(__ldg(jb + 192), __ldg(jb + 224), __ldg(jb + 256));
+            D3 zj1, zj2, X1j;
+            const unsigned jl = (unsigned)(j - v0);
+            if (jl < (unsigned)nv) {
+                const double2 c0 = sz[3 * jl], c1 = sz[3 * jl + 1], c2 = sz[3 * jl + 2];
+                zj1 = d3(c0.x, c0.y, c1.x); zj2 = d3(c1.y, c2.x, c2.y);
+                const double4 xj = sx[jl];
+                X1j = d3(xj.x, xj.y, xj.z);
+            } else {
+                load6(z, j, zj1, zj2);
+                const double4 xj = ldg256(reinterpret_cast<const double4*>(P) + (size_t)j);
+                X1j = d3(xj.x, xj.y, xj.z);
             }
+            const D3 S1 = X1i + X1j;
+            const D3 t = mul(Rg, zi2 + zj2) - (zi1 + zj1) + cross(zw, S1) - zv2;
+            const double s = dot(u, zi2 - zj2) - dot(m, zi1 - zj1) + 2.0 * dot(g, t);
+            const double w2 = 2.0 * W.arap_info * s;
+            Am = Am + w2 * m; Ag = Ag + w2 * g; Au = Au + w2 * u;
         }
-        __syncthreads();
-        // ---- vertex phase: thread = (vertex, output component)
-        if (threadIdx.x < 252) {
-            for (int il = threadIdx.x / 6; il < nv; il += 42) {
-                const int i = v0 + il;
-                const double* Ui = U + 16 * (size_t)i;
-                const int i1 = er == 0 ? 1 : (er == 1 ? 3 : 4), i2 = er == 0 ? 2 : (er == 1 ? 4 : 5);
-                const double uu0 = __ldg(Ui + ecam * 6 + er), uu1 = __ldg(Ui + ecam * 6 + i1), uu2 = __ldg(Ui + ecam * 6 + i2);
-                const double kd = __ldg(Ui + 12 + ecam);
-                const double* a = sacc + 9 * il;
-                const double ag0 = a[3], ag1 = a[4], ag2 = a[5];
-                const double zc0 = sz[6 * il + 3 * ecam], zc1 = sz[6 * il + 3 * ecam + 1], zc2 = sz[6 * il + 3 * ecam + 2];
-                const double ag_r = er == 0 ? ag0 : (er == 1 ? ag1 : ag2);
-                double base;
-                if (ecam == 0) base = -a[er] - 2.0 * ag_r;
-                else base = a[6 + er] + 2.0 * (Rg[er] * ag0 + Rg[3 + er] * ag1 + Rg[6 + er] * ag2);
-                const double zme = er == 0 ? zc0 : (er == 1 ? zc1 : zc2);
-                const double out = base + uu0 * zc0 + uu1 * zc1 + uu2 * zc2 + kd * nrow * zgs[6 + ecam] + lambda * zme;
-                accs += kd * nrow * zme;                           // s1/s2 rows: kd (n . z)
-                accd += zme * out;
-                if (ecam == 0) {                                   // T_g rows: omega 2 (X1i x Ag), upsilon -2 Ag
-                    const double x0 = sx[4 * il], x1 = sx[4 * il + 1], x2 = sx[4 * il + 2];
-                    const double cx = er == 0 ? x1 * ag2 - x2 * ag1 : (er == 1 ? x2 * ag0 - x0 * ag2 : x0 * ag1 - x1 * ag0);
-                    accb += 2.0 * cx;
-                } else accb -= 2.0 * ag_r;
-                w[6 * (size_t)i + role] = out;
+        if (act) {
+            // output rows: [-Am - 2 Ag | Au + 2 Rg^T Ag] + U z + kd n z_s + lambda z
+            const double2* Up = reinterpret_cast<const double2*>(U + 16 * (size_t)i);
+            double uu[14];
+#pragma unroll
+            for (int k = 0; k < 7; ++k) { const double2 t2 = __ldg(Up + k); uu[2 * k] = t2.x; uu[2 * k + 1] = t2.y; }
+            const D3 rg = mulT(Rg, Ag);
+            double out[6] = {-Am.x - 2.0 * Ag.x, -Am.y - 2.0 * Ag.y, -Am.z - 2.0 * Ag.z,
+                             Au.x + 2.0 * rg.x, Au.y + 2.0 * rg.y, Au.z + 2.0 * rg.z};
+            const double zi[6] = {zi1.x, zi1.y, zi1.z, zi2.x, zi2.y, zi2.z};
+#pragma unroll
+            for (int cam = 0; cam < 2; ++cam) {
+                const double* R = cam == 0 ? pr.R1 : pr.R2;
+                const double nz = R[6] * zi[cam * 3] + R[7] * zi[cam * 3 + 1] + R[8] * zi[cam * 3 + 2];
+                const double kd = uu[12 + cam];
+#pragma unroll
+                for (int r = 0; r < 3; ++r) {
+                    double sum = 0.0;
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) sum += (r <= c ? uu[cam * 6 + pk<3>(r, c)] : uu[cam * 6 + pk<3>(c, r)]) * zi[cam * 3 + c];
+                    out[cam * 3 + r] += sum + kd * R[6 + r] * zgs[6 + cam];
+                }
+                acc[6 + cam] += kd * nz;                           // s1/s2 rows: kd (n . z)
             }
+            double dl = 0.0;
+#pragma unroll
+            for (int k = 0; k < 6; ++k) { out[k] += lambda * zi[k]; dl += zi[k] * out[k]; }
+            acc[8] += dl;
+            // T_g rows (the directed twins carry the same s_e and g): omega 2 (X1i x Ag), upsilon -2 Ag
+            const D3 cx = cross(X1i, Ag);
+            acc[0] += 2.0 * cx.x; acc[1] += 2.0 * cx.y; acc[2] += 2.0 * cx.z;
+            acc[3] -= 2.0 * Ag.x; acc[4] -= 2.0 * Ag.y; acc[5] -= 2.0 * Ag.z;
+            store6(w, i, d3(out[0], out[1], out[2]), d3(out[3], out[4], out[5]));
         }
     }
-    // role-preserving block reduction (roles repeat every 6 threads)
-    sred[threadIdx.x * 3] = accb; sred[threadIdx.x * 3 + 1] = accs; sred[threadIdx.x * 3 + 2] = accd;
-    __syncthreads();
+    }
+    block_reduce<9>(acc, sm);
     if (threadIdx.x == 0) {
-        double r[3][6];
-        for (int q = 0; q < 6; ++q) {
-            double s0 = 0.0, s1 = 0.0, s2 = 0.0;
-            for (int t = q; t < 252; t += 6) { s0 += sred[t * 3]; s1 += sred[t * 3 + 1]; s2 += sred[t * 3 + 2]; }
-            r[0][q] = s0; r[1][q] = s1; r[2][q] = s2;
-        }
-        double bg[8];
-        for (int q = 0; q < 6; ++q) bg[q] = r[0][q];
-        bg[6] = r[1][0] + r[1][1] + r[1][2];
-        bg[7] = r[1][3] + r[1][4] + r[1][5];
-        double dl = 0.0;
-        for (int q = 0; q < 6; ++q) dl += r[2][q];
-        for (int k = 0; k < 8; ++k) { bpart[8 * (size_t)blockIdx.x + k] = bg[k]; dl += zgs[k] * bg[k]; }
+        double dl = acc[8];
+        for (int k = 0; k < 8; ++k) { bpart[8 * (size_t)blockIdx.x + k] = acc[k]; dl += zgs[k] * acc[k]; }
         if (blockIdx.x == 0)     // diagonal of the global rows that is not inside the edge sums: (C_ss + lambda)
             for (int k = 0; k < 8; ++k) dl += zgs[k] * ((k >= 6 ? lin->C[k * 8 + k] : 0.0) + lambda) * zgs[k];
         dpart[blockIdx.x] = dl;
