@@ -224,3 +224,87 @@ def test_error_behaviour(pkg, ctx):
     with pytest.raises(pkg.DscError) as e:
         ctx.optimize(pkg.make_weights(1.0, 1.0, 0.0), 1)    # sigma_depth = 0: 1/0 in the reference
     assert e.value.status == -1
+
+
+def test_lm_tube_distorted_camera_and_ragged_size(pkg, ctx):
+    """Config-3/4 shape at oracle size: Kannala-Brandt distortion, n not a multiple of the 32-row slices."""
+    sc = scenes.tube_scene(1237, seed=21, cam=scenes.REALCOLON_CAM, depth_sigma=0.0003, scales=(1.3, 0.8))
+    p, keep = scenes.problem_from_scene(sc, "knn", 8, min_cos=0.99999)
+    assert p.n % 32 != 0
+    w = edges.Weights(rep=1.0, arap=1.0e7, depth_sigma=0.0003)
+    _compare_lm(pkg, ctx, p, w, 5)
+
+
+def test_lm_k16_graph(pkg, ctx):
+    sc = scenes.sheet_scene(900, seed=22)
+    p, keep = scenes.problem_from_scene(sc, "knn", 16)
+    w = edges.Weights(rep=1.0, arap=0.1, depth_sigma=0.003)
+    _compare_lm(pkg, ctx, p, w, 4)
+
+
+def test_isolated_vertices_and_tiny_problems(pkg, ctx):
+    """Rows without neighbours (sliced-ELL width 0 / padding), a 3-correspondence problem, and an empty one."""
+    sc = scenes.sheet_scene(70, seed=23)
+    p, keep = scenes.problem_from_scene(sc, "knn", 4)
+    g = p.graph
+    # cut vertices 5 and 40 out of the graph (symmetrically)
+    row = g.rows()
+    keep_e = ~np.isin(row, [5, 40]) & ~np.isin(g.col, [5, 40])
+    rp = np.zeros(p.n + 1, np.int32)
+    np.add.at(rp, row[keep_e] + 1, 1)
+    p.graph = ograph.Graph(np.cumsum(rp).astype(np.int32), g.col[keep_e], g.w[keep_e], g.area, g.n_triangles)
+    p.R = ograph.compute_rotations(p.graph, p.X1, p.X2)
+    w = edges.Weights(rep=1.0, arap=3.0, depth_sigma=0.003)
+    _compare_lm(pkg, ctx, p, w, 3)
+    # three correspondences, one triangle
+    sc = scenes.sheet_scene(3, seed=24)
+    p3, _ = scenes.problem_from_scene(sc, "knn", 2, gate=GATE_NONE)
+    _compare_lm(pkg, ctx, p3, w, 2)
+    # empty problem: every call is a no-op, nothing crashes
+    pair = pkg.make_pair(p3.cam1, p3.cam2, p3.T1, p3.T2)
+    z3, z2 = np.zeros((0, 3), np.float32), np.zeros((0, 2), np.float32)
+    ctx.problem_upload(pair, z3, z3, z2, z2, np.zeros(0), np.zeros(0))
+    ctx.set_graph(np.zeros(1, np.int32), np.zeros(0, np.int32), np.zeros(0), 1.0, 0)
+    ctx.compute_rotations()
+    recs, st = ctx.optimize(pkg.make_weights(1.0, 1.0, 0.003), 3)
+    assert st.iterations == 0
+    out = ctx.download()
+    assert out["X1"].shape == (0, 3) and out["update"] == 0.0
+
+
+def test_full_size_properties_1m(pkg, ctx):
+    """BASELINE config 3 size (1M correspondences): size-independent properties -- the operator is symmetric
+    (x.Ay == y.Ax), z.(A z) > 0, the cost of the triangulated state is reproduced by two independent kernels
+    (cost_kernel vs linearize_kernel), one LM iteration does not increase the cost, reset restores it exactly."""
+    import importlib
+    wl = importlib.import_module(pkg.__name__ + ".workloads")
+    n = 1_000_000
+    sc = wl.tube_scene(int(n * 1.08), seed=0, cam=wl.DRUNKARD_CAM, arap=1.0e7, depth_sigma=0.0003)
+    cam = (0, sc["cam"])
+    pair = pkg.make_pair(cam, cam, sc["T1"], sc["T2"])
+    prm = ctx.tri_params("NRSLAM", "FarPoints", 1, sc["min_cos"])
+    X1, X2, valid, cosp, nv = ctx.triangulate(pair, prm, sc["uv1"], sc["uv2"])
+    idx = np.nonzero(valid)[0][:n]
+    assert len(idx) == n
+    rowptr, col, wts = wl.knn_graph(X1[idx][:, :2].astype(np.float64), 8)
+    ctx.problem_upload(pair, X1[idx], X2[idx], sc["uv1"][idx], sc["uv2"][idx], sc["d1"][idx].astype(np.float64),
+                       sc["d2"][idx].astype(np.float64), scale1=1.3, scale2=0.8)
+    ctx.set_graph(rowptr, col, wts, sc["area"], 2 * n, 1)
+    ctx.compute_rotations()
+    w = pkg.make_weights(**sc["weights"])
+    chi, parts = ctx.cost(w)
+    b, hd, chi_lin = ctx.debug_linearize(w)
+    assert chi_lin == pytest.approx(chi, rel=1e-12) and np.isfinite(chi)
+    assert np.all(hd >= 0)
+    rng = np.random.default_rng(1)
+    x, y = rng.standard_normal(8 + 6 * n), rng.standard_normal(8 + 6 * n)
+    lam = 1e-5 * hd.max()
+    Ax, Ay = ctx.debug_matvec(w, lam, x), ctx.debug_matvec(w, lam, y)
+    assert float(y @ Ax) == pytest.approx(float(x @ Ay), rel=1e-9)
+    assert float(x @ Ax) > 0
+    ctx.set_pcg(rtol=1e-10, max_iters=6000, check_every=64)
+    recs, st = ctx.optimize(w, 1)
+    assert st.final_chi2 <= chi and recs[0].chi2_before == pytest.approx(chi, rel=1e-12)
+    ctx.reset_state()
+    chi2, _ = ctx.cost(w)
+    assert chi2 == chi

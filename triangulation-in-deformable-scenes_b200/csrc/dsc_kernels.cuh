@@ -9,13 +9,14 @@
 //   dm     double2[n]    depth measurements (KF1, KF2)
 //   isg    float2[n]     KeyFrame::getInvSigma2(octave) of the two observations
 //   U      double[n][16] unary Hessian record {U1[6], U2[6], kd1, kd2, 0, 0}      128 B = 1 line
-//   Je     double[E/32][9][32] per directed edge {u, m, g}: ARAP Jacobian record streamed by the PCG operator
+//   Je     double[nblk][9][32] sliced ELL of the ARAP Jacobian records {u, m, g}: block b = column k of a 32-row
+//                        slice (b = sliceptr[slice] + k), lane = row inside the slice; ecol int[nblk][32] the neighbour
 //   D      double[n][21] packed upper 6x6 diagonal block of H (block-Jacobi preconditioner source)
 //   Minv   double[n][21] packed inverse of D + lambda I
 //   vectors b, x, r, z, w, p, s: double[n][6] {d/dX1, d/dX2}; the 8 global unknowns
 //   (T_g omega/upsilon, s1, s2) live in separate 8-vectors.
 //
-// Work decomposition of the gather kernels: 8 lanes per correspondence (4 correspondences per warp);
+// Work decomposition of the CSR gather kernels (linearise, cost, rotations): 8 lanes per correspondence;
 // lane l walks the directed edges rowptr[i]+l, +8, ... of vertex i, and the per-vertex sums are
 // combined with warp-shuffle segmented reductions -- no global atomics anywhere.  The neighbour graph
 // is symmetric and the reference adds one EdgeARAP per *directed* pair with identical residual
@@ -131,7 +132,6 @@ DSC_D double4 ldg256(const double4* p) {
     asm("ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w) : "l"(p));
     return r;
 }
-DSC_D void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 struct P8 { D3 a, b; };                             // X1, X2 of one correspondence
 DSC_D P8 load_P(const double* __restrict__ P, int n, int i) {
     const double4* p = reinterpret_cast<const double4*>(P);
@@ -153,10 +153,6 @@ DSC_D void load_q(const double* __restrict__ Q, int i, double* q) {
     double4 u = ldg256(p);
     q[0] = u.x; q[1] = u.y; q[2] = u.z; q[3] = u.w;
 }
-
-// Je layout: blocks of 32 consecutive edges, 9 planes of 32 doubles inside a block ("AoSoA"): a warp that
-// handles edges 32c..32c+31 reads plane k as one 256-byte line at a compile-time offset.
-DSC_HD size_t je_index(size_t e, int k) { return (e >> 5) * 288 + (size_t)k * 32 + (e & 31); }
 
 // One directed ARAP edge (i -> j).  EdgeARAP::computeError, g2oTypes.h:310-339:
 //   e = w (|(d2 - Ri d1)/A|^2 + |(-d2 + Rj d1)/A|^2) + |Rg (X2i + X2j) - 2 t - (X1i + X1j)|^2
