@@ -119,6 +119,7 @@ typedef struct {
     double device_ms;          /* CUDA-event time of the whole call            */
     double linearize_ms, pcg_ms, trial_ms;   /* CUDA-event breakdown           */
     int    kernel_launches;
+    int    early_rejects;      /* trials rejected at the loose tolerance (dsc_set_early_reject) */
 } dsc_opt_stats;
 
 /* ---- context --------------------------------------------------------------------------- */
@@ -172,6 +173,11 @@ int dsc_set_rotations(dsc_ctx* ctx, const double* quat);
 /* back to the uploaded points / scales / T_global (replaces Map::clone() for the weight search) */
 int dsc_reset_state(dsc_ctx* ctx);
 int dsc_set_pcg(dsc_ctx* ctx, const dsc_pcg_params* prm);
+/* Optional (off by default): pause every linear solve at rtol_loose, evaluate the trial step, and reject it at once
+ * when rho < -rho_margin; otherwise resume to the tight tolerance and evaluate again.  A rejected step only uses the
+ * sign of rho (lambda *= ni either way), so the LM trace is unchanged unless rho flips sign between the two
+ * tolerances, which the margin guards against.  rtol_loose <= 0 switches it off. */
+int dsc_set_early_reject(dsc_ctx* ctx, double rtol_loose, double rho_margin);
 /* total robust chi2 of the current state; parts[3] = reprojection, depth, ARAP (may be NULL) */
 int dsc_cost(dsc_ctx* ctx, const dsc_weights* w, double* chi2, double* parts);
 /* n_iters LM iterations; records[n_iters] and stats may be NULL */

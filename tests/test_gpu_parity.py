@@ -308,3 +308,28 @@ def test_full_size_properties_1m(pkg, ctx):
     ctx.reset_state()
     chi2, _ = ctx.cost(w)
     assert chi2 == chi
+
+
+def test_early_reject_keeps_the_trace(pkg, ctx):
+    """dsc_set_early_reject pauses the solve at a loose tolerance and rejects clearly bad steps there; accepted
+    steps are still solved to the tight tolerance, so the LM trace and the result must not change."""
+    gold = np.load(__import__("os").path.join(__import__("os").path.dirname(__file__), "golden", "config1_points.npz"))
+    fe = scenes.simulation_frontend(gold["original"], gold["moved"], (-0.10, 0.02, 0.12), (0.14, 0.01, 0.06))
+    p, keep = scenes.build_problem(fe["uv1"], fe["uv2"], fe["d1"], fe["d2"], fe["cam"], fe["T1"], fe["T2"])
+    w = _w(pkg, edges.Weights(rep=1.0, arap=200000.0, depth_sigma=0.003))
+    _upload(pkg, ctx, p)
+    ctx.set_pcg(rtol=1e-12, max_iters=20000, check_every=64)
+    r0, s0 = ctx.optimize(w, 25)
+    o0 = ctx.download()
+    ctx.reset_state()
+    ctx.set_early_reject(1e-4, 0.25)
+    r1, s1 = ctx.optimize(w, 25)
+    o1 = ctx.download()
+    assert s1.early_rejects > 0 and s1.total_pcg_iters < s0.total_pcg_iters
+    assert [r.trials for r in r1] == [r.trials for r in r0]
+    assert [r.chi2_before for r in r1] == [r.chi2_before for r in r0]          # bit-identical accepted steps
+    assert np.array_equal(o0["X1d"], o1["X1d"]) and np.array_equal(o0["X2d"], o1["X2d"])
+    ctx.set_early_reject(0.0, 0.25)
+    ctx.reset_state()
+    r2, s2 = ctx.optimize(w, 25)
+    assert s2.early_rejects == 0 and s2.total_pcg_iters == s0.total_pcg_iters

@@ -23,7 +23,7 @@ EXPORTS = [
     "dsc_timer_start", "dsc_timer_stop", "dsc_launch_count",
     "dsc_triangulate", "dsc_tri_upload", "dsc_tri_run", "dsc_tri_download", "dsc_depth_scale_init",
     "dsc_problem_upload", "dsc_set_graph", "dsc_compute_rotations", "dsc_get_rotations", "dsc_set_rotations",
-    "dsc_reset_state", "dsc_set_pcg", "dsc_cost", "dsc_optimize", "dsc_download", "dsc_pixel_sigma",
+    "dsc_reset_state", "dsc_set_pcg", "dsc_set_early_reject", "dsc_cost", "dsc_optimize", "dsc_download", "dsc_pixel_sigma",
     "dsc_debug_linearize", "dsc_debug_matvec", "dsc_profile_kernels", "dsc_profile_triangulate", "dsc_problem_size",
 ]
 KERNEL_NAMES = ["cg_spmv", "cg_update", "linearize", "cost", "precond", "apply_update", "rotations"]
@@ -59,7 +59,7 @@ class IterRecord(C.Structure):
 class OptStats(C.Structure):
     _fields_ = [("iterations", C.c_int), ("total_trials", C.c_int), ("total_pcg_iters", C.c_int), ("terminated", C.c_int),
                 ("final_chi2", C.c_double), ("device_ms", C.c_double), ("linearize_ms", C.c_double), ("pcg_ms", C.c_double),
-                ("trial_ms", C.c_double), ("kernel_launches", C.c_int)]
+                ("trial_ms", C.c_double), ("kernel_launches", C.c_int), ("early_rejects", C.c_int)]
 
 
 class DscError(RuntimeError):
@@ -263,6 +263,9 @@ class Context:
     def set_pcg(self, rtol=1e-10, max_iters=4000, check_every=32):
         p = PcgParams(float(rtol), int(max_iters), int(check_every))
         self._ck(self.lib.dsc_set_pcg(self.h, C.byref(p)))
+
+    def set_early_reject(self, rtol_loose=1e-4, rho_margin=0.25):
+        self._ck(self.lib.dsc_set_early_reject(self.h, C.c_double(rtol_loose), C.c_double(rho_margin)))
 
     def cost(self, w):
         chi = C.c_double()

@@ -72,6 +72,7 @@ struct dsc_ctx {
     double *gpart[2] = {nullptr, nullptr}, *dpart = nullptr, *bpart = nullptr;
     double* h_pinned = nullptr;           // pinned host scratch
     dsc_pcg_params pcg{1e-10, 4000, 32};
+    double early_rtol = 0.0, early_margin = 0.25;   // early rejection of clearly bad LM trials (off by default)
 };
 
 namespace {
@@ -491,13 +492,15 @@ extern "C" int dsc_set_graph(dsc_ctx* ctx, int n, const int32_t* rowptr, const i
     std::vector<int> rp(n + 1, 0), cl((size_t)E);
     std::vector<double> ww((size_t)E);
     for (int i = 0; i < n; ++i) rp[i + 1] = rp[i] + (rowptr[perm[i] + 1] - rowptr[perm[i]]);
+#pragma omp parallel for schedule(static, 4096)
     for (int i = 0; i < n; ++i) {
-        int s = perm[i], o = rp[i];
-        std::vector<std::pair<int, double>> row;
-        row.reserve(rowptr[s + 1] - rowptr[s]);
-        for (int e = rowptr[s]; e < rowptr[s + 1]; ++e) row.emplace_back(inv[col[e]], w[e]);
-        std::sort(row.begin(), row.end());
-        for (auto& pr2 : row) { cl[o] = pr2.first; ww[o] = pr2.second; ++o; }
+        int s = perm[i], o = rp[i], deg = rowptr[s + 1] - rowptr[s];
+        for (int k = 0; k < deg; ++k) { cl[o + k] = inv[col[rowptr[s] + k]]; ww[o + k] = w[rowptr[s] + k]; }
+        for (int a = 1; a < deg; ++a) {            // insertion sort of the (short) row by new column index
+            int cj = cl[o + a]; double wj = ww[o + a]; int b2 = a - 1;
+            while (b2 >= 0 && cl[o + b2] > cj) { cl[o + b2 + 1] = cl[o + b2]; ww[o + b2 + 1] = ww[o + b2]; --b2; }
+            cl[o + b2 + 1] = cj; ww[o + b2 + 1] = wj;
+        }
     }
     // sliced ELL of the PCG operator: slice = 32 consecutive rows (one warp), width = longest row of the slice;
     // column k of slice s is "block" sliceptr[s] + k: 32 column indices and 9 x 32 Jacobian doubles (Je).
@@ -511,6 +514,7 @@ extern "C" int dsc_set_graph(dsc_ctx* ctx, int n, const int32_t* rowptr, const i
     }
     size_t nblk = (size_t)sp[nslices];
     std::vector<int> ecol(nblk * 32);
+#pragma omp parallel for schedule(static, 256)
     for (int sl = 0; sl < nslices; ++sl)
         for (int k = 0; k < sp[sl + 1] - sp[sl]; ++k)
             for (int l = 0; l < 32; ++l) {
@@ -606,6 +610,13 @@ extern "C" int dsc_set_pcg(dsc_ctx* ctx, const dsc_pcg_params* prm) {
     return DSC_OK;
 }
 
+extern "C" int dsc_set_early_reject(dsc_ctx* ctx, double rtol_loose, double rho_margin) {
+    if (!ctx || !(rho_margin >= 0.0) || !std::isfinite(rtol_loose)) return fail(ctx, DSC_ERR_INVALID_ARG, "dsc_set_early_reject");
+    ctx->early_rtol = rtol_loose > 0.0 ? rtol_loose : 0.0;
+    ctx->early_margin = rho_margin;
+    return DSC_OK;
+}
+
 static int ready(dsc_ctx* ctx, const dsc_weights* w) {
     if (!ctx || !w) return DSC_ERR_INVALID_ARG;
     if (!ctx->have_problem || !ctx->have_graph || !ctx->have_rot)
@@ -658,7 +669,10 @@ static int run_linearize(dsc_ctx* ctx, const WeightsDev& W, LinGlobal* hlin) {
 }
 
 // PCG solve of (H + lambda I) dx = b; returns iterations, status DSC_OK / DSC_ERR_PCG_BREAKDOWN
-static int run_pcg(dsc_ctx* ctx, const WeightsDev& W, double lambda, int* iters_out) {
+// PCG solve of (H + lambda I) dx = b in two entry points so that a solve can be paused at a loose tolerance,
+// inspected (trial cost) and resumed to the tight one: begin = preconditioner + r0/z0 + first operator
+// application; resume = iterate until sqrt(r.z / r0.z0) <= rtol, breakdown or max_iters.
+static int pcg_begin(dsc_ctx* ctx, const WeightsDev& W, double lambda) {
     int n = ctx->n;
     int nbv = grid_threads(ctx, (long long)n);
     int nbs = grid_spmv(ctx, n);
@@ -670,11 +684,27 @@ static int run_pcg(dsc_ctx* ctx, const WeightsDev& W, double lambda, int* iters_
     cg_spmv_kernel<<<nbs, kThreads, 0, ctx->stream>>>(n, ctx->P, ctx->Je, ctx->U, ctx->sliceptr, ctx->ecol, ctx->Gcur, ctx->pair, W,
                                                      lambda, v.z, v.zg, v.w, ctx->dpart, ctx->bpart, ctx->lin, ctx->ctl);
     ctx->launches += 3;
-    double rtol2 = ctx->pcg.rtol * ctx->pcg.rtol;
-    int k = 0;
+    CK(cudaGetLastError());
+    return DSC_OK;
+}
+
+static int pcg_resume(dsc_ctx* ctx, const WeightsDev& W, double lambda, double rtol, int* k_io) {
+    int n = ctx->n;
+    int nbv = grid_threads(ctx, (long long)n);
+    int nbs = grid_spmv(ctx, n);
+    CgVecs v = make_vecs(ctx);
+    double* Ginv = ctx->small + 48;
+    double rtol2 = rtol * rtol;
+    int k = *k_io;
+    if (k > 0) {        // resuming after a pause: the converged latch belongs to the looser tolerance
+        int zero = 0;
+        CK(cudaMemcpyAsync(&ctx->ctl->converged, &zero, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    }
     CgControl hc{};
+    int poll = std::min(16, ctx->pcg.check_every);      // first polls early (well-damped solves need ~10 iterations)
     while (k < ctx->pcg.max_iters) {
-        int chunk = std::min(ctx->pcg.check_every, ctx->pcg.max_iters - k);
+        int chunk = std::min(poll, ctx->pcg.max_iters - k);
+        poll = std::min(2 * poll, ctx->pcg.check_every);
         for (int c = 0; c < chunk; ++c, ++k) {
             cg_update_kernel<<<nbv, kThreads, 0, ctx->stream>>>(n, k & 1, k == 0 ? 1 : 0, ctx->Minv, Ginv, ctx->lin, lambda, v,
                                                                ctx->gpart[k & 1], ctx->gpart[(k + 1) & 1], ctx->dpart, ctx->bpart, nbs,
@@ -686,10 +716,25 @@ static int run_pcg(dsc_ctx* ctx, const WeightsDev& W, double lambda, int* iters_
         CK(cudaGetLastError());
         CK(cudaMemcpyAsync(&hc, ctx->ctl, sizeof(CgControl), cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
+        k = hc.iters;       // updates actually executed: kernels launched after convergence were no-ops
         if (hc.converged || hc.breakdown) break;
     }
-    if (iters_out) *iters_out = hc.iters;
+    *k_io = hc.iters;
     if (hc.breakdown) return DSC_ERR_PCG_BREAKDOWN;
+    return DSC_OK;
+}
+
+// trial state x (+) dx, its robust chi2 and the rho denominator dx.(lambda dx + b) + 1e-3
+static int eval_trial(dsc_ctx* ctx, const WeightsDev& W, double lambda, double* temp, double* scale) {
+    int nbv = grid_threads(ctx, ctx->n);
+    CgVecs v = make_vecs(ctx);
+    apply_update_kernel<<<nbv, kThreads, 0, ctx->stream>>>(ctx->n, ctx->P, v.x, v.xg, ctx->b, ctx->lin, lambda, ctx->Gcur,
+                                                          ctx->Ptrial, ctx->Gtrial, ctx->part);
+    ctx->launches++;
+    CK(cudaMemcpyAsync(ctx->h_pinned + 3 * kMaxBlocks, ctx->part, sizeof(double) * nbv, cudaMemcpyDeviceToHost, ctx->stream));
+    int rc = eval_cost(ctx, W, ctx->Ptrial, ctx->Gtrial, temp, nullptr);
+    if (rc) return rc;
+    *scale = host_sum(ctx->h_pinned + 3 * kMaxBlocks, nbv) + 1e-3;
     return DSC_OK;
 }
 
@@ -731,26 +776,40 @@ extern "C" int dsc_optimize(dsc_ctx* ctx, const dsc_weights* w, int n_iters, dsc
         do {
             int its = 0;
             cudaEventRecord(e_a, ctx->stream);
-            int prc = run_pcg(ctx, W, lambda, &its);
+            int prc = pcg_begin(ctx, W, lambda);
+            const bool early = ctx->early_rtol > ctx->pcg.rtol;
+            if (prc == DSC_OK) prc = pcg_resume(ctx, W, lambda, early ? ctx->early_rtol : ctx->pcg.rtol, &its);
             cudaEventRecord(e_b, ctx->stream); cudaEventSynchronize(e_b);
             st.pcg_ms += ev_ms(e_a, e_b);
-            rec.pcg_iters += its; st.total_pcg_iters += its;
             if (prc != DSC_OK && prc != DSC_ERR_PCG_BREAKDOWN) { rc = prc; break; }
             double temp = std::numeric_limits<double>::max(), scale = 1e-3;
-            cudaEventRecord(e_a, ctx->stream);
             if (prc == DSC_OK) {
-                apply_update_kernel<<<nbv, kThreads, 0, ctx->stream>>>(ctx->n, ctx->P, v.x, v.xg, ctx->b, ctx->lin, lambda, ctx->Gcur,
-                                                                      ctx->Ptrial, ctx->Gtrial, ctx->gpart[0]);
-                ctx->launches++;
-                cudaMemcpyAsync(ctx->h_pinned + 3 * kMaxBlocks, ctx->gpart[0], sizeof(double) * nbv, cudaMemcpyDeviceToHost, ctx->stream);
-                double t2 = 0.0;
-                rc = eval_cost(ctx, W, ctx->Ptrial, ctx->Gtrial, &t2, nullptr);
+                cudaEventRecord(e_a, ctx->stream);
+                rc = eval_trial(ctx, W, lambda, &temp, &scale);
                 if (rc) break;
-                temp = t2;
-                scale = host_sum(ctx->h_pinned + 3 * kMaxBlocks, nbv) + 1e-3;
+                cudaEventRecord(e_b, ctx->stream); cudaEventSynchronize(e_b);
+                st.trial_ms += ev_ms(e_a, e_b);
+                // Early rejection: a step whose loosely converged solution already fails the gain test by a wide
+                // margin is rejected without finishing the solve (only the SIGN of rho matters for a rejected
+                // step: lambda *= ni either way).  Anything else is solved to the tight tolerance and re-evaluated.
+                bool clearly_bad = early && std::isfinite(temp) && (current - temp) / scale < -ctx->early_margin;
+                if (early && !clearly_bad) {
+                    cudaEventRecord(e_a, ctx->stream);
+                    prc = pcg_resume(ctx, W, lambda, ctx->pcg.rtol, &its);
+                    cudaEventRecord(e_b, ctx->stream); cudaEventSynchronize(e_b);
+                    st.pcg_ms += ev_ms(e_a, e_b);
+                    if (prc != DSC_OK && prc != DSC_ERR_PCG_BREAKDOWN) { rc = prc; break; }
+                    temp = std::numeric_limits<double>::max(); scale = 1e-3;
+                    if (prc == DSC_OK) {
+                        cudaEventRecord(e_a, ctx->stream);
+                        rc = eval_trial(ctx, W, lambda, &temp, &scale);
+                        if (rc) break;
+                        cudaEventRecord(e_b, ctx->stream); cudaEventSynchronize(e_b);
+                        st.trial_ms += ev_ms(e_a, e_b);
+                    }
+                } else if (clearly_bad) st.early_rejects++;
             }
-            cudaEventRecord(e_b, ctx->stream); cudaEventSynchronize(e_b);
-            st.trial_ms += ev_ms(e_a, e_b);
+            rec.pcg_iters += its; st.total_pcg_iters += its;
             rho = (current - temp) / scale;
             if (rho > 0 && std::isfinite(temp)) {
                 double alpha = 1.0 - std::pow(2.0 * rho - 1.0, 3);
