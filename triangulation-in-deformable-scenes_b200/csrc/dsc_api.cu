@@ -10,6 +10,7 @@
 #include "dsc_kernels.cuh"
 
 #include <algorithm>
+#include <parallel/algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -469,18 +470,20 @@ extern "C" int dsc_set_graph(dsc_ctx* ctx, int n, const int32_t* rowptr, const i
         }
         float sx = xmax > xmin ? 65535.0f / (xmax - xmin) : 0.f, sy = ymax > ymin ? 65535.0f / (ymax - ymin) : 0.f;
         std::vector<uint64_t> code(n);
+#pragma omp parallel for schedule(static)
         for (int i = 0; i < n; ++i) {
             float x = ctx->hX1[3 * (size_t)i], y = ctx->hX1[3 * (size_t)i + 1];
             uint32_t qx = std::isfinite(x) ? (uint32_t)std::min(65535.0f, std::max(0.0f, (x - xmin) * sx)) : 0u;
             uint32_t qy = std::isfinite(y) ? (uint32_t)std::min(65535.0f, std::max(0.0f, (y - ymin) * sy)) : 0u;
             code[i] = ((uint64_t)(part1by1(qx) | (part1by1(qy) << 1)) << 32) | (uint32_t)i;
         }
-        std::sort(code.begin(), code.end());
+        __gnu_parallel::sort(code.begin(), code.end());
         for (int i = 0; i < n; ++i) perm[i] = (int)(code[i] & 0xffffffffu);
     }
     if (reorder && n > 1) {
         // sliced-ELL friendliness: inside every group of kSortGroup Morton-consecutive rows, order by degree
         // (descending, stable) so that the 32 rows of a warp slice have nearly equal length
+#pragma omp parallel for schedule(static, 16)
         for (int g0 = 0; g0 < n; g0 += kSortGroup) {
             int g1 = std::min(n, g0 + kSortGroup);
             std::stable_sort(perm.begin() + g0, perm.begin() + g1, [&](int a, int b2) {
