@@ -282,7 +282,13 @@ def main():
     cg_ms = kern["cg_spmv"]["ms"] + kern["cg_update"]["ms"]
     dom = "cg_spmv" if kern["cg_spmv"]["ms"] >= kern["cg_update"]["ms"] else "cg_update"
     ach = kern[dom]["bytes"] / (kern[dom]["ms"] * 1e-3) / 1e9
-    roof = dict(bound="hbm", kernel=dom, achieved=ach, peak=peak, unit="GB/s", frac=ach / peak, traffic=None, peak_source=peak_src,
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(f"{args.workload}_{n}_k{args.k}", {}).get(dom)
+    except Exception:
+        pass
+    roof = dict(bound="hbm", kernel=dom, achieved=ach, peak=peak, unit="GB/s", frac=ach / peak, traffic=traffic,
+                algorithmic_bytes=kern[dom]["bytes"], peak_source=peak_src,
                 kernels={k: dict(ms=v["ms"], gbs=v["bytes"] / (v["ms"] * 1e-3) / 1e9, frac=v["bytes"] / (v["ms"] * 1e-3) / 1e9 / peak)
                          for k, v in kern.items()},
                 triangulate=dict(ms=tri["ms"], gbs=tri["bytes"] / (tri["ms"] * 1e-3) / 1e9, frac=tri["bytes"] / (tri["ms"] * 1e-3) / 1e9 / peak,
