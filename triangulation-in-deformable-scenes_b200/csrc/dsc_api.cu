@@ -8,6 +8,7 @@
 // All state stays in HBM; per trial the host reads back two scalars.
 #include "../../include/dsc.h"
 #include "dsc_kernels.cuh"
+#include "dsc_kernels_ell.cuh"
 
 #include <algorithm>
 #include <parallel/algorithm>
@@ -59,7 +60,8 @@ struct dsc_ctx {
     int *rowptr = nullptr, *col = nullptr;
     double* wgt = nullptr;
     double* Je = nullptr;                 // per directed edge {u, m, g}
-    int *ecol = nullptr, *sliceptr = nullptr;   // sliced ELL of the PCG operator (see dsc_set_graph)
+    int *ecol = nullptr, *sliceptr = nullptr;   // sliced ELL of the gather kernels (see dsc_set_graph)
+    double* ewgt = nullptr;                     // ELL edge weights
     long long nblk = 0, blkcap = 0;
     int slcap = 0;
     double *b = nullptr, *D = nullptr, *U = nullptr, *Minv = nullptr;
@@ -123,6 +125,10 @@ int grid_spmv(const dsc_ctx* c, long long n) {              // one block per til
     long long nb = (n + kSortGroup - 1) / kSortGroup;
     long long cap = (long long)c->sms * 2;
     return (int)std::max(1LL, std::min(nb, cap));
+}
+int grid_tiles(const dsc_ctx* c, long long n, int per_sm) {  // one block per tile of kSortGroup rows, persistent
+    long long nb = (n + kSortGroup - 1) / kSortGroup;
+    return (int)std::max(1LL, std::min(nb, (long long)c->sms * per_sm));
 }
 int grid_groups(const dsc_ctx* c, long long n) {            // 8-lanes-per-item kernels
     long long nb = (n + kGroups - 1) / kGroups;
@@ -213,6 +219,9 @@ extern "C" int dsc_create(int device, dsc_ctx** out) {
     if (cudaMalloc(&ctx->bpart, sizeof(double) * kMaxBlocks * 8) != cudaSuccess) return bail(DSC_ERR_ALLOC);
     if (cudaMallocHost(&ctx->h_pinned, sizeof(double) * kMaxBlocks * kLinPart) != cudaSuccess) return bail(DSC_ERR_ALLOC);
     cudaMemset(ctx->errflag, 0, sizeof(int));
+    if (cudaFuncSetAttribute(rotations_ell_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWinBytes) != cudaSuccess ||
+        cudaFuncSetAttribute(cost_ell_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWinBytes) != cudaSuccess ||
+        cudaFuncSetAttribute(linearize_ell_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWinBytes) != cudaSuccess) return bail(DSC_ERR_CUDA);
     *out = ctx;
     return DSC_OK;
 }
@@ -226,7 +235,7 @@ extern "C" void dsc_destroy(dsc_ctx* ctx) {
     dev_free(ctx->X1f); dev_free(ctx->X2f); dev_free(ctx->d_perm);
     dev_free(ctx->P); dev_free(ctx->Ptrial); dev_free(ctx->P0); dev_free(ctx->Q);
     dev_free(ctx->uv); dev_free(ctx->dm); dev_free(ctx->isg);
-    dev_free(ctx->rowptr); dev_free(ctx->col); dev_free(ctx->wgt); dev_free(ctx->Je); dev_free(ctx->ecol); dev_free(ctx->sliceptr);
+    dev_free(ctx->rowptr); dev_free(ctx->col); dev_free(ctx->wgt); dev_free(ctx->Je); dev_free(ctx->ecol); dev_free(ctx->ewgt); dev_free(ctx->sliceptr);
     dev_free(ctx->b); dev_free(ctx->D); dev_free(ctx->U); dev_free(ctx->Minv);
     for (auto& v : ctx->vec) dev_free(v);
     dev_free(ctx->small); dev_free(ctx->Gcur); dev_free(ctx->Gtrial); dev_free(ctx->lin); dev_free(ctx->ctl);
@@ -517,13 +526,14 @@ extern "C" int dsc_set_graph(dsc_ctx* ctx, int n, const int32_t* rowptr, const i
     }
     size_t nblk = (size_t)sp[nslices];
     std::vector<int> ecol(nblk * 32);
+    std::vector<double> ewgt(nblk * 32, 0.0);
 #pragma omp parallel for schedule(static, 256)
     for (int sl = 0; sl < nslices; ++sl)
         for (int k = 0; k < sp[sl + 1] - sp[sl]; ++k)
             for (int l = 0; l < 32; ++l) {
                 int i = sl * 32 + l;
                 int v = i < n ? i : 0;
-                if (i < n && k < rp[i + 1] - rp[i]) v = cl[rp[i] + k];
+                if (i < n && k < rp[i + 1] - rp[i]) { v = cl[rp[i] + k]; ewgt[((size_t)sp[sl] + k) * 32 + l] = ww[rp[i] + k]; }
                 ecol[((size_t)sp[sl] + k) * 32 + l] = v;
             }
     if (E > ctx->ecap) {
@@ -531,7 +541,7 @@ extern "C" int dsc_set_graph(dsc_ctx* ctx, int n, const int32_t* rowptr, const i
         ctx->ecap = E;
     }
     if ((long long)nblk > ctx->blkcap) {
-        CK(dev_alloc(ctx->ecol, nblk * 32)); CK(dev_alloc(ctx->Je, nblk * 288));
+        CK(dev_alloc(ctx->ecol, nblk * 32)); CK(dev_alloc(ctx->ewgt, nblk * 32)); CK(dev_alloc(ctx->Je, nblk * 288));
         ctx->blkcap = (long long)nblk;
     }
     if (nslices + 1 > ctx->slcap) { CK(dev_alloc(ctx->sliceptr, (size_t)nslices + 1)); ctx->slcap = nslices + 1; }
@@ -543,6 +553,7 @@ extern "C" int dsc_set_graph(dsc_ctx* ctx, int n, const int32_t* rowptr, const i
         CK(cudaMemcpyAsync(ctx->col, cl.data(), sizeof(int) * E, cudaMemcpyHostToDevice, ctx->stream));
         CK(cudaMemcpyAsync(ctx->wgt, ww.data(), sizeof(double) * E, cudaMemcpyHostToDevice, ctx->stream));
         CK(cudaMemcpyAsync(ctx->ecol, ecol.data(), sizeof(int) * nblk * 32, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->ewgt, ewgt.data(), sizeof(double) * nblk * 32, cudaMemcpyHostToDevice, ctx->stream));
         CK(cudaMemsetAsync(ctx->Je, 0, sizeof(double) * nblk * 288, ctx->stream));
     }
     CK(cudaStreamSynchronize(ctx->stream));
@@ -558,7 +569,7 @@ extern "C" int dsc_compute_rotations(dsc_ctx* ctx) {
     if (!ctx->have_graph) return fail(ctx, DSC_ERR_STATE, "dsc_compute_rotations before dsc_set_graph");
     CK(cudaSetDevice(ctx->device));
     if (ctx->n > 0) {
-        rotations_kernel<<<grid_groups(ctx, ctx->n), kThreads, 0, ctx->stream>>>(ctx->n, ctx->P, ctx->rowptr, ctx->col, ctx->wgt, ctx->Q);
+        rotations_ell_kernel<<<grid_tiles(ctx, ctx->n, 2), kEllThreads, kWinBytes, ctx->stream>>>(ctx->n, ctx->P, ctx->sliceptr, ctx->ecol, ctx->ewgt, ctx->Q);
         ctx->launches++;
         CK(cudaGetLastError());
     }
@@ -630,9 +641,9 @@ static int ready(dsc_ctx* ctx, const dsc_weights* w) {
 }
 
 static int eval_cost(dsc_ctx* ctx, const WeightsDev& W, const double* P, const Globals* G, double* chi2, double* parts) {
-    int nb = grid_groups(ctx, ctx->n);
-    cost_kernel<<<nb, kThreads, 0, ctx->stream>>>(ctx->n, P, ctx->Q, ctx->uv, ctx->dm, ctx->isg, ctx->rowptr, ctx->col, ctx->wgt,
-                                                 G, ctx->pair, W, ctx->part);
+    int nb = grid_tiles(ctx, ctx->n, 2);
+    cost_ell_kernel<<<nb, kEllThreads, kWinBytes, ctx->stream>>>(ctx->n, P, ctx->Q, ctx->uv, ctx->dm, ctx->isg, ctx->sliceptr, ctx->ecol,
+                                                               ctx->ewgt, G, ctx->pair, W, ctx->part);
     ctx->launches++;
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(ctx->h_pinned, ctx->part, sizeof(double) * 3 * nb, cudaMemcpyDeviceToHost, ctx->stream));
@@ -660,9 +671,9 @@ static CgVecs make_vecs(dsc_ctx* ctx) {
 }
 
 static int run_linearize(dsc_ctx* ctx, const WeightsDev& W, LinGlobal* hlin) {
-    int nb = grid_groups(ctx, ctx->n);
-    linearize_kernel<<<nb, kThreads, 0, ctx->stream>>>(ctx->n, ctx->sliceptr, ctx->P, ctx->Q, ctx->uv, ctx->dm, ctx->isg, ctx->rowptr, ctx->col,
-                                                      ctx->wgt, ctx->Gcur, ctx->pair, W, ctx->b, ctx->D, ctx->U, ctx->Je, ctx->part);
+    int nb = grid_tiles(ctx, ctx->n, 1);
+    linearize_ell_kernel<<<nb, kEllThreads, kWinBytes, ctx->stream>>>(ctx->n, ctx->P, ctx->Q, ctx->uv, ctx->dm, ctx->isg, ctx->sliceptr, ctx->ecol,
+                                                                    ctx->ewgt, ctx->Gcur, ctx->pair, W, ctx->b, ctx->D, ctx->U, ctx->Je, ctx->part);
     finalize_linearize_kernel<<<1, kThreads, 0, ctx->stream>>>(nb, ctx->part, ctx->lin);
     ctx->launches += 2;
     CK(cudaGetLastError());
@@ -995,11 +1006,12 @@ extern "C" int dsc_profile_kernels(dsc_ctx* ctx, const dsc_weights* w, int warm,
     double by[DSC_K_COUNT];
     by[DSC_K_SPMV] = 256.0 * N + 76.0 * (double)ctx->nblk * 32.0;   // X1 z U | ELL blocks: col(4) Je(72) per slot (padding included) | write w
     by[DSC_K_UPDATE] = 696.0 * N;                 // read z w p s x r Minv, write p s x r z
-    by[DSC_K_LINEARIZE] = 508.0 * N + 84.0 * E;   // P Q uv dm isg rowptr | col w | write b D U Je
-    by[DSC_K_COST] = 140.0 * N + 12.0 * E;        // P Q uv dm isg rowptr | col w
+    double S = (double)ctx->nblk * 32.0;            // ELL slots (padding included)
+    by[DSC_K_LINEARIZE] = 504.0 * N + 12.0 * S + 72.0 * E;   // P Q uv dm isg | ecol ewgt per slot | write b D U, Je per edge
+    by[DSC_K_COST] = 136.0 * N + 12.0 * S;         // P Q uv dm isg | ecol ewgt per slot
     by[DSC_K_PRECOND] = 336.0 * N;                // D -> Minv
     by[DSC_K_APPLY] = 224.0 * N;                  // P x b -> Ptrial
-    by[DSC_K_ROTATIONS] = 100.0 * N + 12.0 * E;   // P rowptr | col w | write Q
+    by[DSC_K_ROTATIONS] = 96.0 * N + 12.0 * S;     // P | ecol ewgt per slot | write Q
     auto time_it = [&](int which, auto&& launch) -> int {
         for (int i = 0; i < warm; ++i) launch();
         CK(cudaEventRecord(ctx->evA, ctx->stream));
@@ -1025,13 +1037,14 @@ extern "C" int dsc_profile_kernels(dsc_ctx* ctx, const dsc_weights* w, int warm,
     });
     if (s) return s;
     s = time_it(DSC_K_LINEARIZE, [&]() {
-        linearize_kernel<<<nbs, kThreads, 0, ctx->stream>>>(n, ctx->sliceptr, ctx->P, ctx->Q, ctx->uv, ctx->dm, ctx->isg, ctx->rowptr, ctx->col,
-                                                           ctx->wgt, ctx->Gcur, ctx->pair, W, ctx->b, ctx->D, ctx->U, ctx->Je, ctx->part);
+        linearize_ell_kernel<<<grid_tiles(ctx, n, 1), kEllThreads, kWinBytes, ctx->stream>>>(n, ctx->P, ctx->Q, ctx->uv, ctx->dm, ctx->isg, ctx->sliceptr,
+                                                                                       ctx->ecol, ctx->ewgt, ctx->Gcur, ctx->pair, W, ctx->b, ctx->D,
+                                                                                       ctx->U, ctx->Je, ctx->part);
     });
     if (s) return s;
     s = time_it(DSC_K_COST, [&]() {
-        cost_kernel<<<nbs, kThreads, 0, ctx->stream>>>(n, ctx->P, ctx->Q, ctx->uv, ctx->dm, ctx->isg, ctx->rowptr, ctx->col, ctx->wgt,
-                                                      ctx->Gcur, ctx->pair, W, ctx->part);
+        cost_ell_kernel<<<grid_tiles(ctx, n, 2), kEllThreads, kWinBytes, ctx->stream>>>(n, ctx->P, ctx->Q, ctx->uv, ctx->dm, ctx->isg, ctx->sliceptr, ctx->ecol,
+                                                                                  ctx->ewgt, ctx->Gcur, ctx->pair, W, ctx->part);
     });
     if (s) return s;
     s = time_it(DSC_K_PRECOND, [&]() {
@@ -1045,7 +1058,7 @@ extern "C" int dsc_profile_kernels(dsc_ctx* ctx, const dsc_weights* w, int warm,
     if (s) return s;
     double* Qtmp = ctx->vec[3];                    // scratch: do not disturb the real rotations
     s = time_it(DSC_K_ROTATIONS, [&]() {
-        rotations_kernel<<<nbs, kThreads, 0, ctx->stream>>>(n, ctx->P, ctx->rowptr, ctx->col, ctx->wgt, Qtmp);
+        rotations_ell_kernel<<<grid_tiles(ctx, n, 2), kEllThreads, kWinBytes, ctx->stream>>>(n, ctx->P, ctx->sliceptr, ctx->ecol, ctx->ewgt, Qtmp);
     });
     if (s) return s;
     if (bytes) for (int k = 0; k < DSC_K_COUNT; ++k) bytes[k] = by[k];

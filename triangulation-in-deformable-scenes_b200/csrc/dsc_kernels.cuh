@@ -16,7 +16,7 @@
 //   vectors b, x, r, z, w, p, s: double[n][6] {d/dX1, d/dX2}; the 8 global unknowns
 //   (T_g omega/upsilon, s1, s2) live in separate 8-vectors.
 //
-// Work decomposition of the CSR gather kernels (linearise, cost, rotations): 8 lanes per correspondence;
+// Work decomposition of the gather kernels: sliced ELL, one warp per 32-row slice, lane = row (dsc_kernels_ell.cuh);
 // lane l walks the directed edges rowptr[i]+l, +8, ... of vertex i, and the per-vertex sums are
 // combined with warp-shuffle segmented reductions -- no global atomics anywhere.  The neighbour graph
 // is symmetric and the reference adds one EdgeARAP per *directed* pair with identical residual
@@ -348,269 +348,9 @@ init_state_kernel(int n, const float* __restrict__ X1, const float* __restrict__
     }
 }
 
-// computeR (Geometry.cc:549-604): S_i = sum_j w_ij (p1i - p1j)(p2i - p2j)^T -> R_i = V U^T (det fix) -> quaternion
-__global__ void __launch_bounds__(kThreads)
-rotations_kernel(int n, const double* __restrict__ P, const int* __restrict__ rowptr, const int* __restrict__ col,
-                 const double* __restrict__ wgt, double* __restrict__ Q) {
-    int lane = threadIdx.x & (kLanes - 1);
-    int nround = (n + kGroups - 1) / kGroups;
-    for (int rd = blockIdx.x; rd < nround; rd += gridDim.x) {
-        int i = rd * kGroups + threadIdx.x / kLanes;
-        bool act = i < n;
-        double S[9];
-#pragma unroll
-        for (int k = 0; k < 9; ++k) S[k] = 0.0;
-        int e0 = 0, e1 = 0;
-        if (act) {
-            e0 = rowptr[i]; e1 = rowptr[i + 1];
-            P8 Pi = load_P(P, n, i);
-            for (int e = e0 + lane; e < e1; e += kLanes) {
-                int j = col[e];
-                double w = wgt[e];
-                P8 Pj = load_P(P, n, j);
-                D3 d1 = Pi.a - Pj.a, d2 = Pi.b - Pj.b;
-                S[0] += w * d1.x * d2.x; S[1] += w * d1.x * d2.y; S[2] += w * d1.x * d2.z;
-                S[3] += w * d1.y * d2.x; S[4] += w * d1.y * d2.y; S[5] += w * d1.y * d2.z;
-                S[6] += w * d1.z * d2.x; S[7] += w * d1.z * d2.y; S[8] += w * d1.z * d2.z;
-            }
-        }
-#pragma unroll
-        for (int k = 0; k < 9; ++k) S[k] = group_sum(S[k]);
-        if (act && lane == 0) {
-            double q[4] = {0.0, 0.0, 0.0, 1.0};
-            if (e1 > e0) {
-                double R[9];
-                rotation_from_covariance(S, R);
-                rot_to_quat(R, q);
-            }
-            reinterpret_cast<double4*>(Q)[i] = make_double4(q[0], q[1], q[2], q[3]);
-        }
-    }
-}
-
-// ================================================================== K6: cost
-// activeRobustChi2 = sum_reproj Huber(w e.e) + sum_depth W_d e^2 + sum_arap W_a e^2.
-// part: [grid][3]
-__global__ void __launch_bounds__(kThreads)
-cost_kernel(int n, const double* __restrict__ P, const double* __restrict__ Q, const float4* __restrict__ uv,
-            const double2* __restrict__ dm, const float2* __restrict__ isg, const int* __restrict__ rowptr,
-            const int* __restrict__ col, const double* __restrict__ wgt, const Globals* __restrict__ Gp,
-            const __grid_constant__ PairDev pr, const __grid_constant__ WeightsDev W, double* __restrict__ part) {
-    __shared__ double sm[3 * (kThreads / 32)];
-    __shared__ Globals G;
-    if (threadIdx.x == 0) G = *Gp;
-    __syncthreads();
-    int lane = threadIdx.x & (kLanes - 1);
-    double acc[3] = {0.0, 0.0, 0.0};
-    int nround = (n + kGroups - 1) / kGroups;
-    for (int rd = blockIdx.x; rd < nround; rd += gridDim.x) {
-        int i = rd * kGroups + threadIdx.x / kLanes;
-        if (i >= n) continue;
-        P8 Pi = load_P(P, n, i);
-        double qi[4];
-        load_q(Q, i, qi);
-        int e1 = rowptr[i + 1];
-        double ea = 0.0;
-        for (int e = rowptr[i] + lane; e < e1; e += kLanes) {
-            int j = col[e];
-            P8 Pj = load_P(P, n, j);
-            double qj[4];
-            load_q(Q, j, qj);
-            ArapGrad g;
-            arap_edge<false>(Pi, Pj, qi, qj, wgt[e], W.inv_area, G, g);
-            ea += g.e * g.e;
-        }
-        acc[2] += W.arap_info * ea;
-        if (lane < 2) {                                  // lane 0: KF1 observation, lane 1: KF2 observation
-            float4 o = uv[i];
-            float2 sg = isg[i];
-            double2 d = dm[i];
-            double e0, e1r, r0, r1;
-            F3 xcf;
-            if (lane == 0) {
-                reproj_residual(pr.cam1, pr.R1, pr.t1, Pi.a, o.x, o.y, e0, e1r, xcf);
-                huber((double)sg.x * W.rep * (e0 * e0 + e1r * e1r), W.huber, r0, r1);
-                D3 xc = mul(pr.R1, Pi.a);
-                double rr = d.x / G.s1 - (xc.z + pr.t1[2]);
-                double ed = rr * rr * (G.s1 <= 0.0 ? 500.0 : 1.0);
-                acc[0] += r0; acc[1] += W.depth_info * ed * ed;
-            } else {
-                reproj_residual(pr.cam2, pr.R2, pr.t2, Pi.b, o.z, o.w, e0, e1r, xcf);
-                huber((double)sg.y * W.rep * (e0 * e0 + e1r * e1r), W.huber, r0, r1);
-                D3 xc = mul(pr.R2, Pi.b);
-                double rr = d.y / G.s2 - (xc.z + pr.t2[2]);
-                double ed = rr * rr * (G.s2 <= 0.0 ? 500.0 : 1.0);
-                acc[0] += r0; acc[1] += W.depth_info * ed * ed;
-            }
-        }
-    }
-    block_reduce<3>(acc, sm);
-    if (threadIdx.x == 0) { part[3 * blockIdx.x] = acc[0]; part[3 * blockIdx.x + 1] = acc[1]; part[3 * blockIdx.x + 2] = acc[2]; }
-}
-
-// ================================================================== K2 + K3: linearise and assemble
-// Per correspondence: gradient b (6), packed 6x6 diagonal block D (21), unary record U (16).
-// Per block: partial sums of chi2[3], max diagonal, global gradient bg[8], global block C (T-T 21 packed, s1, s2).
+// ================================================================== K2 + K3 reductions (the kernels are in dsc_kernels_ell.cuh)
+// per-block partial layout of the linearisation: chi2[3], max diagonal, global gradient bg[8], C_TT packed (21), C_ss (2)
 constexpr int kLinPart = 3 + 1 + 8 + 21 + 2;   // 35
-__global__ void __launch_bounds__(kThreads)
-linearize_kernel(int n, const int* __restrict__ sliceptr, const double* __restrict__ P, const double* __restrict__ Q, const float4* __restrict__ uv,
-                 const double2* __restrict__ dm, const float2* __restrict__ isg, const int* __restrict__ rowptr,
-                 const int* __restrict__ col, const double* __restrict__ wgt, const Globals* __restrict__ Gp,
-                 const __grid_constant__ PairDev pr, const __grid_constant__ WeightsDev W,
-                 double* __restrict__ b, double* __restrict__ D, double* __restrict__ U, double* __restrict__ Je,
-                 double* __restrict__ part) {
-    __shared__ double sm[kLinPart * (kThreads / 32)];
-    __shared__ Globals G;
-    if (threadIdx.x == 0) G = *Gp;
-    __syncthreads();
-    int lane = threadIdx.x & (kLanes - 1);
-    double acc[kLinPart];
-#pragma unroll
-    for (int k = 0; k < kLinPart; ++k) acc[k] = 0.0;
-    double maxdiag = 0.0;
-    int nround = (n + kGroups - 1) / kGroups;
-    for (int rd = blockIdx.x; rd < nround; rd += gridDim.x) {
-        int i = rd * kGroups + threadIdx.x / kLanes;
-        bool act = i < n;
-        double gb[6], Dk[21];
-#pragma unroll
-        for (int k = 0; k < 6; ++k) gb[k] = 0.0;
-#pragma unroll
-        for (int k = 0; k < 21; ++k) Dk[k] = 0.0;
-        P8 Pi;
-        if (act) {
-            Pi = load_P(P, n, i);
-            double qi[4];
-            load_q(Q, i, qi);
-            int e1 = rowptr[i + 1];
-            const int e_first = rowptr[i];
-            for (int e = e_first + lane; e < e1; e += kLanes) {
-                int j = col[e];
-                P8 Pj = load_P(P, n, j);
-                double qj[4];
-                load_q(Q, j, qj);
-                ArapGrad g;
-                arap_edge<true>(Pi, Pj, qi, qj, wgt[e], W.inv_area, G, g);
-                {   // per-edge Jacobian record streamed by the PCG operator: u, m, g (72 B)
-                    // sliced-ELL slot of (row i, k-th edge): block sliceptr[i/32] + k, lane i%32
-                    const size_t jblk = ((size_t)__ldg(sliceptr + (i >> 5)) + (size_t)(e - e_first)) * 288 + (i & 31);
-                    const double jv[9] = {g.u.x, g.u.y, g.u.z, g.m.x, g.m.y, g.m.z, g.g.x, g.g.y, g.g.z};
-#pragma unroll
-                    for (int k = 0; k < 9; ++k) Je[jblk + k * 32] = jv[k];
-                }
-                double gi[6] = {g.gi1.x, g.gi1.y, g.gi1.z, g.gi2.x, g.gi2.y, g.gi2.z};
-                double gt[6] = {g.gw.x, g.gw.y, g.gw.z, g.gv.x, g.gv.y, g.gv.z};
-                double we = W.arap_info * g.e;
-                acc[2] += we * g.e;
-                // vertex rows: the directed twin (j -> i) has the same residual and gradient => factor 2
-#pragma unroll
-                for (int r = 0; r < 6; ++r) {
-                    gb[r] -= 2.0 * we * gi[r];
-                    double s = 2.0 * W.arap_info * gi[r];
-#pragma unroll
-                    for (int c = r; c < 6; ++c) Dk[pk<6>(r, c)] += s * gi[c];
-                }
-                // global rows: every directed edge once
-#pragma unroll
-                for (int r = 0; r < 6; ++r) {
-                    acc[4 + r] -= we * gt[r];
-                    double s = W.arap_info * gt[r];
-#pragma unroll
-                    for (int c = r; c < 6; ++c) acc[12 + pk<6>(r, c)] += s * gt[c];
-                }
-            }
-        }
-#pragma unroll
-        for (int k = 0; k < 6; ++k) gb[k] = group_sum(gb[k]);
-#pragma unroll
-        for (int k = 0; k < 21; ++k) Dk[k] = group_sum(Dk[k]);
-        if (act && lane == 0) {
-            float4 o = uv[i];
-            float2 sg = isg[i];
-            double2 d = dm[i];
-            double Urec[16];
-#pragma unroll
-            for (int k = 0; k < 16; ++k) Urec[k] = 0.0;
-#pragma unroll
-            for (int cam = 0; cam < 2; ++cam) {
-                const CamF& cm = cam == 0 ? pr.cam1 : pr.cam2;
-                const double* R = cam == 0 ? pr.R1 : pr.R2;
-                const double* t = cam == 0 ? pr.t1 : pr.t2;
-                D3 X = cam == 0 ? Pi.a : Pi.b;
-                double e0, e1r, rho0, rho1;
-                F3 xcf;
-                reproj_residual(cm, R, t, X, cam == 0 ? o.x : o.z, cam == 0 ? o.y : o.w, e0, e1r, xcf);
-                double om = (double)(cam == 0 ? sg.x : sg.y) * W.rep;
-                huber(om * (e0 * e0 + e1r * e1r), W.huber, rho0, rho1);
-                acc[0] += rho0;
-                float Jf[6];
-                cam_project_jac(cm, xcf, Jf);
-                double J[6];                               // J = -Jproj * R   (2x3)
-#pragma unroll
-                for (int r = 0; r < 2; ++r)
-#pragma unroll
-                    for (int c = 0; c < 3; ++c)
-                        J[r * 3 + c] = -((double)Jf[r * 3] * R[c] + (double)Jf[r * 3 + 1] * R[3 + c] + (double)Jf[r * 3 + 2] * R[6 + c]);
-                double wr = rho1 * om;
-                double Uu[6];
-#pragma unroll
-                for (int r = 0; r < 3; ++r) {
-                    gb[cam * 3 + r] -= wr * (J[r] * e0 + J[3 + r] * e1r);
-#pragma unroll
-                    for (int c = r; c < 3; ++c) Uu[pk<3>(r, c)] = wr * (J[r] * J[c] + J[3 + r] * J[3 + c]);
-                }
-                // depth edge EdgeDepthCorrection (g2oTypes.h:400-416): e = (d/s - z_c)^2 (x500 if s<=0)
-                double s = cam == 0 ? G.s1 : G.s2;
-                double dd = cam == 0 ? d.x : d.y;
-                double kf = s <= 0.0 ? 500.0 : 1.0;
-                D3 xc = mul(R, X);
-                double rr = dd / s - (xc.z + t[2]);
-                double ed = kf * rr * rr;
-                double alpha = -2.0 * kf * rr;             // de/dX = alpha * R[2,:]
-                double Js = 2.0 * kf * rr * (-dd / (s * s));
-                acc[1] += W.depth_info * ed * ed;
-                double nrm[3] = {R[6], R[7], R[8]};
-#pragma unroll
-                for (int r = 0; r < 3; ++r) {
-                    gb[cam * 3 + r] -= W.depth_info * ed * alpha * nrm[r];
-#pragma unroll
-                    for (int c = r; c < 3; ++c) Uu[pk<3>(r, c)] += W.depth_info * alpha * alpha * nrm[r] * nrm[c];
-                }
-                acc[10 + cam] -= W.depth_info * ed * Js;           // bg[6 + cam]
-                acc[33 + cam] += W.depth_info * Js * Js;           // C[s s]
-                Urec[12 + cam] = W.depth_info * alpha * Js;        // kd: coupling X <-> s along R[2,:]
-#pragma unroll
-                for (int k = 0; k < 6; ++k) Urec[cam * 6 + k] = Uu[k];
-#pragma unroll
-                for (int r = 0; r < 3; ++r)
-#pragma unroll
-                    for (int c = r; c < 3; ++c) Dk[pk<6>(cam * 3 + r, cam * 3 + c)] += Uu[pk<3>(r, c)];
-            }
-            store6(b, i, d3(gb[0], gb[1], gb[2]), d3(gb[3], gb[4], gb[5]));
-            double* Dp = D + 21 * (size_t)i;
-#pragma unroll
-            for (int k = 0; k < 21; ++k) Dp[k] = Dk[k];
-            double2* Up = reinterpret_cast<double2*>(U + 16 * (size_t)i);
-#pragma unroll
-            for (int k = 0; k < 8; ++k) Up[k] = make_double2(Urec[2 * k], Urec[2 * k + 1]);
-#pragma unroll
-            for (int r = 0; r < 6; ++r) maxdiag = fmax(maxdiag, fabs(Dk[pk<6>(r, r)]));
-        }
-    }
-    // max-reduce maxdiag separately, sums through block_reduce
-    for (int o = 16; o > 0; o >>= 1) maxdiag = fmax(maxdiag, __shfl_xor_sync(0xffffffffu, maxdiag, o));
-    __shared__ double smax[kThreads / 32];
-    if ((threadIdx.x & 31) == 0) smax[threadIdx.x >> 5] = maxdiag;
-    block_reduce<kLinPart>(acc, sm);
-    if (threadIdx.x == 0) {
-        double m = 0.0;
-        for (int w = 0; w < kThreads / 32; ++w) m = fmax(m, smax[w]);
-        acc[3] = m;
-        double* o = part + (size_t)kLinPart * blockIdx.x;
-        for (int k = 0; k < kLinPart; ++k) o[k] = acc[k];
-    }
-}
-
 __global__ void __launch_bounds__(kThreads)
 finalize_linearize_kernel(int nb, const double* __restrict__ part, LinGlobal* __restrict__ out) {
     __shared__ double sm[kThreads / 32];
