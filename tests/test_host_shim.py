@@ -112,3 +112,78 @@ def test_simulation_flow_outer_loop_runs():
     assert "WEIGHTS OPTIMIZED" in out.stdout
     assert np.isfinite(js["sigma_c1"]) and np.isfinite(js["sigma_c2"]) and js["s1"] > 0 and js["s2"] > 0
     assert len(js["trace"]) > 0
+
+
+@pytest.mark.gpu
+def test_real_pair_flow_with_permuted_matches(tmp_path):
+    """Mapping::monocularMapInitialization after matching + arapOptimization through the C++ shim, on key points whose
+    curr index is a permutation of the ref index, with unmatched key points, octaves > 0 and depth images: the
+    slot / observation-index conventions of Mapping.cc:205-209 and g2oBundleAdjustment.cc:765-770 must be exact."""
+    from oracle import realpath, camera
+    from oracle.se3 import SE3
+    rng = np.random.default_rng(5)
+    sc = scenes.tube_scene(700, seed=31, cam=scenes.DRUNKARD_CAM, depth_sigma=0.0003, scales=(1.0, 1.0))
+    n1 = 700
+    W = H = 320
+    inside = (sc["uv1"] > 1).all(1) & (sc["uv1"] < W - 2).all(1) & (sc["uv2"] > 1).all(1) & (sc["uv2"] < H - 2).all(1)
+    kp1 = sc["uv1"].copy()
+    perm = rng.permutation(n1)                      # curr key point index of ref key point i
+    kp2 = np.zeros_like(sc["uv2"])
+    kp2[perm] = sc["uv2"]
+    matches = perm.astype(np.int64)
+    matches[~inside] = -1
+    matches[rng.random(n1) < 0.1] = -1              # unmatched key points leave null slots in the middle
+    oct1 = rng.integers(0, 3, n1)
+    oct2 = rng.integers(0, 3, n1)
+    # depth images (value = 100 * depth in metres): smooth ramps so that the bilinear sample is meaningful
+    yy, xx = np.mgrid[0:H, 0:W].astype(np.float32)
+    im1 = (100 * (0.10 + 0.0004 * xx + 0.0002 * yy)).astype(np.float32)
+    im2 = (100 * (0.12 + 0.0003 * xx + 0.0003 * yy)).astype(np.float32)
+    ids1, ids2 = 1.3, 0.8
+    (tmp_path / "d1.f32").write_bytes(im1.tobytes())
+    (tmp_path / "d2.f32").write_bytes(im2.tobytes())
+    with open(tmp_path / "pair.txt", "w") as f:
+        f.write(f"{n1} {n1} {W} {H} {ids1} {ids2}\n")
+        f.write(" ".join(repr(float(v)) for v in sc["cam"]) + "\n")
+        for T in (sc["T1"], sc["T2"]):
+            f.write(" ".join(repr(float(v)) for v in T.as34().reshape(-1)) + "\n")
+        for kp, oc in ((kp1, oct1), (kp2, oct2)):
+            for (x, y), o in zip(kp, oc):
+                f.write(f"{float(x)!r} {float(y)!r} {int(o)}\n")
+        f.write(" ".join(str(int(m)) for m in matches) + "\n")
+    yaml = (tmp_path / "s.yaml")
+    yaml.write_text('%YAML:1.0\nTriangulation.method: "NRSLAM"\nTriangulation.seed.location: "TwoPoints"\nTriangulation.minCos: 0.5\n'
+                    'Triangulation.depthLimit: 1.0\nTriangulation.checks: "false"\nOptimization.rep: 1\nOptimization.global: 1\n'
+                    'Optimization.arap: 1000\nOptimization.alpha: 1\nOptimization.beta: 1\nOptimization.numberOfIterations: 4\n'
+                    'Measurements.DepthWeight: 0.3\n')
+    exe = os.path.join(LIB, "dsc_realpair")
+    out = subprocess.run([exe, str(yaml), str(tmp_path / "pair.txt"), str(tmp_path / "d1.f32"), str(tmp_path / "d2.f32")],
+                         stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    assert out.returncode == 0, out.stderr
+    js = json.loads(out.stdout[out.stdout.index("{"):])
+    # oracle
+    r = realpath.init_from_matches(kp1, kp2, matches, sc["cam"], sc["T1"], sc["T2"], im1, im2, ids1, ids2, "NRSLAM", "TwoPoints",
+                                   depth_limit=1.0, check_reproj=False, min_cos=0.5)
+    assert js["slots"] == r["slots"].tolist()                                   # index bookkeeping: exact
+    assert js["created"] == 2 * len(r["slots"])
+    np.testing.assert_allclose(np.array(js["tri1"]).reshape(-1, 3), r["X1"], rtol=0, atol=2e-6)   # host libm vs emulated unprojection
+    assert js["s1_init"] == pytest.approx(r["s1"], rel=1e-5) and js["s2_init"] == pytest.approx(r["s2"], rel=1e-5)
+    # refinement of exactly those correspondences, with the shim's own triangulated points (float) as the start
+    X1 = np.array(js["tri1"], np.float32).reshape(-1, 3).astype(np.float64)
+    X2 = np.array(js["tri2"], np.float32).reshape(-1, 3).astype(np.float64)
+    g = ograph.delaunay_graph(X1)
+    slots = r["slots"]
+    sig = lambda o: (1.0 / (np.float32(1.2) ** o.astype(np.float32)) ** 2).astype(np.float64)     # Frame.cc:65-75
+    camt = (camera.KB8, sc["cam"])
+    p = edges.Problem(cam1=camt, cam2=camt, T1=sc["T1"], T2=sc["T2"], uv1=r["uv1"], uv2=r["uv2"],
+                      inv_sigma2_1=sig(oct1[slots]), inv_sigma2_2=sig(oct2[matches[slots]]), d1=r["d1"], d2=r["d2"], graph=g,
+                      X1=X1, X2=X2, Tg=SE3(), s1=js["s1_init"], s2=js["s2_init"])
+    p.R = ograph.compute_rotations(g, X1, X2)
+    w = edges.Weights(rep=1.0, arap=1000.0, depth_sigma=0.0003)
+    st, tr = lm.optimize(p, w, 4)
+    chi = [t[0] for t in js["trace"]]
+    np.testing.assert_allclose(chi, tr.chi2, rtol=1e-5)
+    scale = np.abs(st.X1).max()
+    assert np.abs(np.array(js["X1"]).reshape(-1, 3) - st.X1).max() <= 1e-5 * scale + 1e-7      # float write-back
+    assert np.abs(np.array(js["X2"]).reshape(-1, 3) - st.X2).max() <= 1e-5 * scale + 1e-7
+    assert js["s1"] == pytest.approx(st.s1, rel=1e-5) and js["s2"] == pytest.approx(st.s2, rel=1e-5)

@@ -315,6 +315,45 @@ int triangulateSimulatedMapPoints(Map& map, KeyFrame_ refKF, KeyFrame_ currKF, c
     if (!currKF->getEstimatedDepthScale()) { double s = 0; ck(dsc_depth_scale_init(ctx(), 2, &s), "dsc_depth_scale_init"); currKF->setEstimatedDepthScale(s); }
     return created;
 }
+int initializeMapFromMatches(Map& map, KeyFrame_ refKF, KeyFrame_ currKF, const std::vector<int>& matches, Settings& settings,
+                             float* parallaxDegrees) {
+    TriangulationResult r = triangulateMatches(*refKF, *currKF, matches, settings.getTrianMethod(), settings.getTrianLocation(), DSC_GATE_REAL,
+                                               1.0f, settings.getDepthLimit(), settings.getCheckingSelection());
+    std::vector<float> par;
+    for (size_t i = 0; i < r.valid.size(); ++i) if (r.valid[i]) par.push_back(r.cosParallax[i]);
+    if (par.empty()) return 0;
+    std::sort(par.begin(), par.end());                                        // MonocularMapInitializer.cc:375-386
+    float cosp = par[std::min<size_t>(50, par.size() - 1)];
+    if (parallaxDegrees) *parallaxDegrees = std::acos(cosp) * (float)(180.0 / M_PI);
+    Sophus::SE3f T1w = refKF->getPose(), T2w = currKF->getPose();
+    int created = 0;
+    double scale1 = 0, scale2 = 0;
+    float n_points = 0;
+    for (size_t i = 0; i < r.valid.size(); ++i) {
+        if (!r.valid[i]) continue;
+        cv::Point2f x1 = refKF->getKeyPoint(i).pt, x2 = currKF->getKeyPoint((size_t)matches[i]).pt;
+        double d1 = refKF->getDepthMeasure(x1.x, x1.y), d2 = currKF->getDepthMeasure(x2.x, x2.y);
+        if (d1 <= 0.0 || d2 <= 0.0) continue;                                 // Mapping.cc:194-200
+        if (x1.x <= 0.1 || x1.x >= 1500 || x1.y <= 0.1 || x1.y >= 1500) continue;
+        if (x2.x <= 0.1 || x2.x >= 1500 || x2.y <= 0.1 || x2.y >= 1500) continue;
+        MapPoint_ a(new MapPoint(r.x3D_1[i])), b(new MapPoint(r.x3D_2[i]));
+        map.insertMapPoint(a); map.insertMapPoint(b);
+        map.addObservation(refKF->getId(), a->getId(), i);                    // :205-209
+        map.addObservation(currKF->getId(), b->getId(), (size_t)matches[i]);
+        refKF->setMapPoint(i, a); currKF->setMapPoint(i, b);
+        float degrees = std::acos(r.cosParallax[i]) * (float)(180.0 / M_PI);
+        if (degrees > settings.getMinCos()) {                                 // :220-233 (sic: degrees against minCos)
+            Eigen::Vector3f c1 = T1w * r.x3D_1[i], c2 = T2w * r.x3D_2[i];
+            scale1 += refKF->getDepthMeasure(x1.x, x1.y, false) / c1[2];
+            scale2 += currKF->getDepthMeasure(x2.x, x2.y, false) / c2[2];
+            n_points++;
+        }
+        created += 2;
+    }
+    refKF->setEstimatedDepthScale(scale1 / n_points);                         // :250-254
+    currKF->setEstimatedDepthScale(scale2 / n_points);
+    return created;
+}
 }  // namespace dsc_host
 
 void KeyFrame::setInitialDepthScaleInSimulationImages() {

@@ -50,6 +50,16 @@ TriangulationResult triangulateMatches(KeyFrame& refKF, KeyFrame& currKF, const 
  * matches, initial depth scales (KeyFrame.cc:131-153).  Returns the number of MapPoints created. */
 int triangulateSimulatedMapPoints(Map& map, KeyFrame_ refKF, KeyFrame_ currKF, const std::string& method, const std::string& location, float minCos);
 
+/* Real-image map initialisation, Mapping::monocularMapInitialization after the matching step (Mapping.cc:159-257):
+ * MonocularMapInitializer::reconstructPoints (:303-368: triangulate every match with the given poses, gates
+ * finite/non-zero, 0 <= z <= depthLimit in both cameras, optional reprojection^2 <= 5.991), then MapPoints and
+ * observations for the matches whose depth measurements are positive and whose key points lie in (0.1, 1500)
+ * (:183-209; the curr MapPoint is stored at the REF slot, its observation at the matched index), and the initial
+ * depth scales = mean d_measured / z over the points whose parallax in degrees exceeds Triangulation.minCos
+ * (:211-254).  Needs depth images on both key frames.  Returns the number of MapPoints created. */
+int initializeMapFromMatches(Map& map, KeyFrame_ refKF, KeyFrame_ currKF, const std::vector<int>& matches, Settings& settings,
+                             float* parallaxDegrees = nullptr);
+
 /* Per-iteration record of the last arapOptimization call (the reference runs g2o with setVerbose(false); the
  * parity tests need the trace). */
 struct LmRecord { double chi2_before, chi2_after, lambda; int trials, accepted, pcg_iters; };
