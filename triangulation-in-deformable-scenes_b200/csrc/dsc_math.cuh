@@ -331,35 +331,61 @@ template <int N> DSC_HD int pk(int i, int j) { return i * N - (i * (i - 1)) / 2 
 // in: full symmetric A (row-major NxN); out: Ainv full.  Returns false if not positive definite.
 template <int N>
 DSC_HD bool spd_inverse(const double* A, double* Ainv) {
+    // every loop has compile-time bounds and is fully unrolled so that L and its inverse stay in registers
     double L[N][N];
-    for (int i = 0; i < N; ++i) for (int j = 0; j < N; ++j) L[i][j] = 0.0;
+#pragma unroll
+    for (int i = 0; i < N; ++i)
+#pragma unroll
+        for (int j = 0; j < N; ++j) L[i][j] = 0.0;
+    bool ok = true;
+#pragma unroll
     for (int j = 0; j < N; ++j) {
         double d = A[j * N + j];
-        for (int k = 0; k < j; ++k) d -= L[j][k] * L[j][k];
-        if (!(d > 0.0)) return false;
+#pragma unroll
+        for (int k = 0; k < N; ++k) if (k < j) d -= L[j][k] * L[j][k];
+        if (!(d > 0.0)) { ok = false; d = 1.0; }
         d = sqrt(d);
         L[j][j] = d;
-        for (int i = j + 1; i < N; ++i) {
-            double s = A[i * N + j];
-            for (int k = 0; k < j; ++k) s -= L[i][k] * L[j][k];
-            L[i][j] = s / d;
+        const double inv = 1.0 / d;
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            if (i > j) {
+                double s = A[i * N + j];
+#pragma unroll
+                for (int k = 0; k < N; ++k) if (k < j) s -= L[i][k] * L[j][k];
+                L[i][j] = s * inv;
+            }
         }
     }
+    if (!ok) return false;
     double Li[N][N];                                  // inverse of L (lower)
-    for (int i = 0; i < N; ++i) for (int j = 0; j < N; ++j) Li[i][j] = 0.0;
+#pragma unroll
+    for (int i = 0; i < N; ++i)
+#pragma unroll
+        for (int j = 0; j < N; ++j) Li[i][j] = 0.0;
+#pragma unroll
     for (int j = 0; j < N; ++j) {
         Li[j][j] = 1.0 / L[j][j];
-        for (int i = j + 1; i < N; ++i) {
-            double s = 0.0;
-            for (int k = j; k < i; ++k) s -= L[i][k] * Li[k][j];
-            Li[i][j] = s / L[i][i];
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            if (i > j) {
+                double s = 0.0;
+#pragma unroll
+                for (int k = 0; k < N; ++k) if (k >= j && k < i) s -= L[i][k] * Li[k][j];
+                Li[i][j] = s / L[i][i];
+            }
         }
     }
+#pragma unroll
     for (int i = 0; i < N; ++i)
-        for (int j = 0; j <= i; ++j) {
-            double s = 0.0;
-            for (int k = i; k < N; ++k) s += Li[k][i] * Li[k][j];
-            Ainv[i * N + j] = s; Ainv[j * N + i] = s;
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+            if (j <= i) {
+                double s = 0.0;
+#pragma unroll
+                for (int k = 0; k < N; ++k) if (k >= i) s += Li[k][i] * Li[k][j];
+                Ainv[i * N + j] = s; Ainv[j * N + i] = s;
+            }
         }
     return true;
 }
