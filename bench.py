@@ -38,8 +38,8 @@ def parse():
     ap.add_argument("--lm-iters", type=int, default=0, help="0 = the config's own count")
     ap.add_argument("--pcg-rtol", type=float, default=1e-10)
     ap.add_argument("--pcg-max-iters", type=int, default=6000)
-    ap.add_argument("--early-rtol", type=float, default=1e-4, help="loose tolerance of the early-reject check (0 = off)")
-    ap.add_argument("--early-margin", type=float, default=0.25)
+    ap.add_argument("--early-rtol", type=float, nargs="*", default=[1e-3, 1e-4], help="loose tolerances of the early-reject check (none = off)")
+    ap.add_argument("--early-margin", type=float, nargs="*", default=[1.0, 0.5])
     ap.add_argument("--cpu-sample-n", type=int, default=20000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -224,14 +224,15 @@ def main():
         tr = [(r.chi2_before, r.chi2_after, r.trials, r.accepted) for r in recs]
         if k == 0:
             ref_trace = tr
-            if args.early_rtol > 0 and args.warmup > 1:
+            early["lm_it_per_s_full_solves"] = st.iterations / (st.device_ms * 1e-3)   # first warm-up step, no shortcut
+            if len(args.early_rtol) > 0 and args.warmup > 1:
                 ctx.set_early_reject(args.early_rtol, args.early_margin)
                 early["used"] = True
         elif early["used"] and early["trace_identical"] is None:
             early["trace_identical"] = (tr == ref_trace)
             early["early_rejects_per_step"] = st.early_rejects
             if not early["trace_identical"]:
-                ctx.set_early_reject(0.0, args.early_margin)
+                ctx.set_early_reject((), ())
                 early["used"] = False
     sampler = ClockSampler(local) if rank == 0 else None
     launches0 = ctx.launch_count()

@@ -173,11 +173,12 @@ int dsc_set_rotations(dsc_ctx* ctx, const double* quat);
 /* back to the uploaded points / scales / T_global (replaces Map::clone() for the weight search) */
 int dsc_reset_state(dsc_ctx* ctx);
 int dsc_set_pcg(dsc_ctx* ctx, const dsc_pcg_params* prm);
-/* Optional (off by default): pause every linear solve at rtol_loose, evaluate the trial step, and reject it at once
- * when rho < -rho_margin; otherwise resume to the tight tolerance and evaluate again.  A rejected step only uses the
- * sign of rho (lambda *= ni either way), so the LM trace is unchanged unless rho flips sign between the two
- * tolerances, which the margin guards against.  rtol_loose <= 0 switches it off. */
-int dsc_set_early_reject(dsc_ctx* ctx, double rtol_loose, double rho_margin);
+/* Optional (off by default): pause every linear solve at up to 4 loose tolerances rtol_loose[0] > rtol_loose[1] > ...,
+ * evaluate the trial step there, and reject it at once when rho < -rho_margin[level]; otherwise resume the same CG.
+ * The last pass always runs to the tight tolerance of dsc_set_pcg, so accepted steps are unchanged.  A rejected step
+ * only uses the sign of rho (lambda *= ni either way), so the LM trace is unchanged unless rho changes sign between
+ * a loose and the tight tolerance, which the margins guard against.  n_levels = 0 switches it off. */
+int dsc_set_early_reject(dsc_ctx* ctx, int n_levels, const double* rtol_loose, const double* rho_margin);
 /* total robust chi2 of the current state; parts[3] = reprojection, depth, ARAP (may be NULL) */
 int dsc_cost(dsc_ctx* ctx, const dsc_weights* w, double* chi2, double* parts);
 /* n_iters LM iterations; records[n_iters] and stats may be NULL */

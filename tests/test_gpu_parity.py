@@ -322,14 +322,14 @@ def test_early_reject_keeps_the_trace(pkg, ctx):
     r0, s0 = ctx.optimize(w, 25)
     o0 = ctx.download()
     ctx.reset_state()
-    ctx.set_early_reject(1e-4, 0.25)
+    ctx.set_early_reject((1e-3, 1e-4), (1.0, 0.5))
     r1, s1 = ctx.optimize(w, 25)
     o1 = ctx.download()
     assert s1.early_rejects > 0 and s1.total_pcg_iters < s0.total_pcg_iters
     assert [r.trials for r in r1] == [r.trials for r in r0]
     assert [r.chi2_before for r in r1] == [r.chi2_before for r in r0]          # bit-identical accepted steps
     assert np.array_equal(o0["X1d"], o1["X1d"]) and np.array_equal(o0["X2d"], o1["X2d"])
-    ctx.set_early_reject(0.0, 0.25)
+    ctx.set_early_reject((), ())
     ctx.reset_state()
     r2, s2 = ctx.optimize(w, 25)
     assert s2.early_rejects == 0 and s2.total_pcg_iters == s0.total_pcg_iters

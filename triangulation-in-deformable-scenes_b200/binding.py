@@ -264,8 +264,13 @@ class Context:
         p = PcgParams(float(rtol), int(max_iters), int(check_every))
         self._ck(self.lib.dsc_set_pcg(self.h, C.byref(p)))
 
-    def set_early_reject(self, rtol_loose=1e-4, rho_margin=0.25):
-        self._ck(self.lib.dsc_set_early_reject(self.h, C.c_double(rtol_loose), C.c_double(rho_margin)))
+    def set_early_reject(self, rtol_loose=(1e-3, 1e-4), rho_margin=(1.0, 0.5)):
+        """levels of (loose tolerance, rho margin); empty sequences switch the shortcut off"""
+        r = np.ascontiguousarray(np.atleast_1d(rtol_loose), np.float64)
+        m = np.ascontiguousarray(np.atleast_1d(rho_margin), np.float64)
+        if len(r) != len(m):
+            raise ValueError("one margin per tolerance")
+        self._ck(self.lib.dsc_set_early_reject(self.h, len(r), _fp(r), _fp(m)))
 
     def cost(self, w):
         chi = C.c_double()

@@ -75,7 +75,8 @@ struct dsc_ctx {
     double *gpart[2] = {nullptr, nullptr}, *dpart = nullptr, *bpart = nullptr;
     double* h_pinned = nullptr;           // pinned host scratch
     dsc_pcg_params pcg{1e-10, 4000, 32};
-    double early_rtol = 0.0, early_margin = 0.25;   // early rejection of clearly bad LM trials (off by default)
+    int early_levels = 0;                            // early rejection of clearly bad LM trials (off by default)
+    double early_rtol[4] = {0, 0, 0, 0}, early_margin[4] = {0, 0, 0, 0};
 };
 
 namespace {
@@ -624,10 +625,15 @@ extern "C" int dsc_set_pcg(dsc_ctx* ctx, const dsc_pcg_params* prm) {
     return DSC_OK;
 }
 
-extern "C" int dsc_set_early_reject(dsc_ctx* ctx, double rtol_loose, double rho_margin) {
-    if (!ctx || !(rho_margin >= 0.0) || !std::isfinite(rtol_loose)) return fail(ctx, DSC_ERR_INVALID_ARG, "dsc_set_early_reject");
-    ctx->early_rtol = rtol_loose > 0.0 ? rtol_loose : 0.0;
-    ctx->early_margin = rho_margin;
+extern "C" int dsc_set_early_reject(dsc_ctx* ctx, int n_levels, const double* rtol_loose, const double* rho_margin) {
+    if (!ctx || n_levels < 0 || n_levels > 4 || (n_levels > 0 && (!rtol_loose || !rho_margin)))
+        return fail(ctx, DSC_ERR_INVALID_ARG, "dsc_set_early_reject");
+    for (int l = 0; l < n_levels; ++l) {
+        if (!(rtol_loose[l] > 0.0) || !(rho_margin[l] >= 0.0) || (l > 0 && !(rtol_loose[l] < rtol_loose[l - 1])))
+            return fail(ctx, DSC_ERR_INVALID_ARG, "dsc_set_early_reject: tolerances must be positive and strictly decreasing, margins >= 0");
+    }
+    ctx->early_levels = n_levels;
+    for (int l = 0; l < n_levels; ++l) { ctx->early_rtol[l] = rtol_loose[l]; ctx->early_margin[l] = rho_margin[l]; }
     return DSC_OK;
 }
 
@@ -791,38 +797,35 @@ extern "C" int dsc_optimize(dsc_ctx* ctx, const dsc_weights* w, int n_iters, dsc
             int its = 0;
             cudaEventRecord(e_a, ctx->stream);
             int prc = pcg_begin(ctx, W, lambda);
-            const bool early = ctx->early_rtol > ctx->pcg.rtol;
-            if (prc == DSC_OK) prc = pcg_resume(ctx, W, lambda, early ? ctx->early_rtol : ctx->pcg.rtol, &its);
-            cudaEventRecord(e_b, ctx->stream); cudaEventSynchronize(e_b);
-            st.pcg_ms += ev_ms(e_a, e_b);
-            if (prc != DSC_OK && prc != DSC_ERR_PCG_BREAKDOWN) { rc = prc; break; }
+            cudaEventRecord(e_b, ctx->stream);
             double temp = std::numeric_limits<double>::max(), scale = 1e-3;
-            if (prc == DSC_OK) {
+            // Early rejection: the solve is paused at each loose tolerance, the trial is evaluated, and a step that
+            // already fails the gain test by that level's margin is rejected without finishing the solve (only the
+            // SIGN of rho matters for a rejected step: lambda *= ni either way).  Otherwise the same CG is resumed;
+            // the last pass is always the tight tolerance, so accepted steps are computed exactly as without it.
+            bool rejected_early = false;
+            for (int level = 0; level <= ctx->early_levels && prc == DSC_OK && !rejected_early; ++level) {
+                const bool last = level == ctx->early_levels;
+                const double tol = last ? ctx->pcg.rtol : ctx->early_rtol[level];
+                if (!last && !(tol > ctx->pcg.rtol)) continue;
+                cudaEventRecord(e_a, ctx->stream);
+                prc = pcg_resume(ctx, W, lambda, tol, &its);
+                cudaEventRecord(e_b, ctx->stream); cudaEventSynchronize(e_b);
+                st.pcg_ms += ev_ms(e_a, e_b);
+                if (prc != DSC_OK) break;
                 cudaEventRecord(e_a, ctx->stream);
                 rc = eval_trial(ctx, W, lambda, &temp, &scale);
                 if (rc) break;
                 cudaEventRecord(e_b, ctx->stream); cudaEventSynchronize(e_b);
                 st.trial_ms += ev_ms(e_a, e_b);
-                // Early rejection: a step whose loosely converged solution already fails the gain test by a wide
-                // margin is rejected without finishing the solve (only the SIGN of rho matters for a rejected
-                // step: lambda *= ni either way).  Anything else is solved to the tight tolerance and re-evaluated.
-                bool clearly_bad = early && std::isfinite(temp) && (current - temp) / scale < -ctx->early_margin;
-                if (early && !clearly_bad) {
-                    cudaEventRecord(e_a, ctx->stream);
-                    prc = pcg_resume(ctx, W, lambda, ctx->pcg.rtol, &its);
-                    cudaEventRecord(e_b, ctx->stream); cudaEventSynchronize(e_b);
-                    st.pcg_ms += ev_ms(e_a, e_b);
-                    if (prc != DSC_OK && prc != DSC_ERR_PCG_BREAKDOWN) { rc = prc; break; }
-                    temp = std::numeric_limits<double>::max(); scale = 1e-3;
-                    if (prc == DSC_OK) {
-                        cudaEventRecord(e_a, ctx->stream);
-                        rc = eval_trial(ctx, W, lambda, &temp, &scale);
-                        if (rc) break;
-                        cudaEventRecord(e_b, ctx->stream); cudaEventSynchronize(e_b);
-                        st.trial_ms += ev_ms(e_a, e_b);
-                    }
-                } else if (clearly_bad) st.early_rejects++;
+                if (!last && std::isfinite(temp) && (current - temp) / scale < -ctx->early_margin[level]) {
+                    rejected_early = true;
+                    st.early_rejects++;
+                }
             }
+            if (rc) break;
+            if (prc != DSC_OK && prc != DSC_ERR_PCG_BREAKDOWN) { rc = prc; break; }
+            if (prc == DSC_ERR_PCG_BREAKDOWN) { temp = std::numeric_limits<double>::max(); scale = 1e-3; }
             rec.pcg_iters += its; st.total_pcg_iters += its;
             rho = (current - temp) / scale;
             if (rho > 0 && std::isfinite(temp)) {
