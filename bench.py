@@ -34,7 +34,7 @@ def parse():
     ap.add_argument("--k", type=int, default=8)
     ap.add_argument("--workload", default="drunkard", choices=["drunkard", "realcolon", "sheet", "batch"])
     ap.add_argument("--problems", type=int, default=0, help="batch workload: frame-pair problems per GPU (config 5 has 4096 in total)")
-    ap.add_argument("--streams", type=int, default=8, help="batch workload: concurrent contexts (CUDA streams) per GPU")
+    ap.add_argument("--streams", type=int, default=32, help="batch workload: concurrent contexts (CUDA streams) per GPU")
     ap.add_argument("--lm-iters", type=int, default=0, help="0 = the config's own count")
     ap.add_argument("--pcg-rtol", type=float, default=1e-10)
     ap.add_argument("--pcg-max-iters", type=int, default=6000)
@@ -361,6 +361,8 @@ def main_batch(args, rank, world, local):
     w = pkg.make_weights(**probs[0][0]["weights"])
     for c in ctxs:
         c.set_pcg(rtol=args.pcg_rtol, max_iters=args.pcg_max_iters, check_every=64)
+        if len(args.early_rtol) > 0:
+            c.set_early_reject(args.early_rtol, args.early_margin)
 
     def run_all():
         q = queue.Queue()

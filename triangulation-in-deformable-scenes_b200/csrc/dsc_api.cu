@@ -14,6 +14,7 @@
 #include <parallel/algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <string>
@@ -75,6 +76,8 @@ struct dsc_ctx {
     double *gpart[2] = {nullptr, nullptr}, *dpart = nullptr, *bpart = nullptr;
     double* h_pinned = nullptr;           // pinned host scratch
     dsc_pcg_params pcg{1e-10, 4000, 32};
+    struct IterGraph { cudaGraphExec_t exec = nullptr; const double* P = nullptr; WeightsDev W{}; } graphs[2];   // per state buffer
+    bool use_graphs = true;
     int early_levels = 0;                            // early rejection of clearly bad LM trials (off by default)
     double early_rtol[4] = {0, 0, 0, 0}, early_margin[4] = {0, 0, 0, 0};
 };
@@ -158,6 +161,10 @@ void fill_pair(const dsc_pair* in, PairDev& o) {
     }
 }
 
+void drop_graphs(dsc_ctx* c) {
+    for (auto& g : c->graphs) { if (g.exec) cudaGraphExecDestroy(g.exec); g.exec = nullptr; g.P = nullptr; }
+}
+
 WeightsDev make_weights(const dsc_ctx* c, const dsc_weights* w) {
     WeightsDev o;
     o.rep = w->rep;
@@ -220,6 +227,7 @@ extern "C" int dsc_create(int device, dsc_ctx** out) {
     if (cudaMalloc(&ctx->bpart, sizeof(double) * kMaxBlocks * 8) != cudaSuccess) return bail(DSC_ERR_ALLOC);
     if (cudaMallocHost(&ctx->h_pinned, sizeof(double) * kMaxBlocks * kLinPart) != cudaSuccess) return bail(DSC_ERR_ALLOC);
     cudaMemset(ctx->errflag, 0, sizeof(int));
+    ctx->use_graphs = std::getenv("DSC_NO_GRAPHS") == nullptr;
     if (cudaFuncSetAttribute(rotations_ell_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWinBytes) != cudaSuccess ||
         cudaFuncSetAttribute(cost_ell_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWinBytes) != cudaSuccess ||
         cudaFuncSetAttribute(linearize_ell_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWinBytes) != cudaSuccess) return bail(DSC_ERR_CUDA);
@@ -231,6 +239,7 @@ extern "C" void dsc_destroy(dsc_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    drop_graphs(ctx);
     dev_free(ctx->t_uv1); dev_free(ctx->t_uv2); dev_free(ctx->t_d1); dev_free(ctx->t_d2);
     dev_free(ctx->t_X1); dev_free(ctx->t_X2); dev_free(ctx->t_cos); dev_free(ctx->t_valid);
     dev_free(ctx->X1f); dev_free(ctx->X2f); dev_free(ctx->d_perm);
@@ -432,6 +441,7 @@ extern "C" int dsc_problem_upload(dsc_ctx* ctx, const dsc_pair* pair, int n,
     ctx->g0 = g;
     ctx->perm.clear();
     ctx->have_problem = true; ctx->have_graph = false; ctx->have_rot = false;
+    drop_graphs(ctx);
     return upload_state(ctx);
 }
 
@@ -562,6 +572,7 @@ extern "C" int dsc_set_graph(dsc_ctx* ctx, int n, const int32_t* rowptr, const i
     for (int i = 0; i < n; ++i) if (perm[i] != i) { identity = false; break; }
     if (identity) ctx->perm.clear(); else ctx->perm = perm;
     ctx->have_graph = true; ctx->have_rot = false;
+    drop_graphs(ctx);
     return upload_state(ctx);
 }
 
@@ -683,8 +694,10 @@ static int run_linearize(dsc_ctx* ctx, const WeightsDev& W, LinGlobal* hlin) {
     finalize_linearize_kernel<<<1, kThreads, 0, ctx->stream>>>(nb, ctx->part, ctx->lin);
     ctx->launches += 2;
     CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(hlin, ctx->lin, sizeof(LinGlobal), cudaMemcpyDeviceToHost, ctx->stream));
+    LinGlobal* hp = reinterpret_cast<LinGlobal*>(ctx->h_pinned + 6 * kMaxBlocks);
+    CK(cudaMemcpyAsync(hp, ctx->lin, sizeof(LinGlobal), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    *hlin = *hp;
     return DSC_OK;
 }
 
@@ -699,12 +712,43 @@ static int pcg_begin(dsc_ctx* ctx, const WeightsDev& W, double lambda) {
     CgVecs v = make_vecs(ctx);
     double* Ginv = ctx->small + 48;
     CK(cudaMemsetAsync(ctx->errflag, 0, sizeof(int), ctx->stream));
+    ctl_set_kernel<<<1, 1, 0, ctx->stream>>>(ctx->ctl, lambda, 1, 0.0, 0, 0);
     precond_kernel<<<nbv, kThreads, 0, ctx->stream>>>(n, ctx->D, lambda, ctx->lin, ctx->Minv, Ginv, ctx->errflag);
     cg_init_kernel<<<nbv, kThreads, 0, ctx->stream>>>(n, ctx->b, ctx->lin, ctx->Minv, Ginv, v, ctx->gpart[0], ctx->ctl);
     cg_spmv_kernel<<<nbs, kThreads, 0, ctx->stream>>>(n, ctx->P, ctx->Je, ctx->U, ctx->sliceptr, ctx->ecol, ctx->Gcur, ctx->pair, W,
                                                      lambda, v.z, v.zg, v.w, ctx->dpart, ctx->bpart, ctx->lin, ctx->ctl);
     ctx->launches += 3;
     CK(cudaGetLastError());
+    return DSC_OK;
+}
+
+// kGraphIters PCG iterations (first = 0, parity starting even) captured once per state buffer and replayed:
+// lambda and the tolerance live in CgControl, every other argument is fixed for the uploaded problem.
+constexpr int kGraphIters = 16;
+static int iteration_graph(dsc_ctx* ctx, const WeightsDev& W, cudaGraphExec_t* out) {
+    dsc_ctx::IterGraph* slot = nullptr;
+    for (auto& g : ctx->graphs) if (g.exec && g.P == ctx->P && std::memcmp(&g.W, &W, sizeof(WeightsDev)) == 0) { *out = g.exec; return DSC_OK; }
+    for (auto& g : ctx->graphs) if (!g.exec || g.P == ctx->P) { slot = &g; break; }
+    if (!slot) slot = &ctx->graphs[0];
+    if (slot->exec) { cudaGraphExecDestroy(slot->exec); slot->exec = nullptr; }
+    int n = ctx->n, nbv = grid_threads(ctx, (long long)n), nbs = grid_spmv(ctx, n);
+    CgVecs v = make_vecs(ctx);
+    double* Ginv = ctx->small + 48;
+    cudaGraph_t graph = nullptr;
+    CK(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+    for (int k = 2; k < 2 + kGraphIters; ++k) {
+        cg_update_kernel<<<nbv, kThreads, 0, ctx->stream>>>(n, k & 1, 0, ctx->Minv, Ginv, ctx->lin, 0.0, v, ctx->gpart[k & 1],
+                                                           ctx->gpart[(k + 1) & 1], ctx->dpart, ctx->bpart, nbs, ctx->ctl, 0.0);
+        cg_spmv_kernel<<<nbs, kThreads, 0, ctx->stream>>>(n, ctx->P, ctx->Je, ctx->U, ctx->sliceptr, ctx->ecol, ctx->Gcur, ctx->pair, W,
+                                                         0.0, v.z, v.zg, v.w, ctx->dpart, ctx->bpart, ctx->lin, ctx->ctl);
+    }
+    cudaError_t e = cudaStreamEndCapture(ctx->stream, &graph);
+    if (e != cudaSuccess) return fail(ctx, DSC_ERR_CUDA, std::string("graph capture -> ") + cudaGetErrorString(e));
+    e = cudaGraphInstantiate(&slot->exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) { slot->exec = nullptr; return fail(ctx, DSC_ERR_CUDA, std::string("graph instantiate -> ") + cudaGetErrorString(e)); }
+    slot->P = ctx->P; slot->W = W;
+    *out = slot->exec;
     return DSC_OK;
 }
 
@@ -716,26 +760,36 @@ static int pcg_resume(dsc_ctx* ctx, const WeightsDev& W, double lambda, double r
     double* Ginv = ctx->small + 48;
     double rtol2 = rtol * rtol;
     int k = *k_io;
-    if (k > 0) {        // resuming after a pause: the converged latch belongs to the looser tolerance
-        int zero = 0;
-        CK(cudaMemcpyAsync(&ctx->ctl->converged, &zero, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-    }
+    // resuming after a pause (k > 0): the converged latch belongs to the looser tolerance
+    ctl_set_kernel<<<1, 1, 0, ctx->stream>>>(ctx->ctl, 0.0, 0, rtol2, 1, k > 0 ? 1 : 0);
     CgControl hc{};
-    int poll = std::min(16, ctx->pcg.check_every);      // first polls early (well-damped solves need ~10 iterations)
+    int poll = std::min(k == 0 ? 18 : 16, ctx->pcg.check_every);   // first poll early (well-damped solves need ~10 iterations): 2 direct + one graph
     while (k < ctx->pcg.max_iters) {
         int chunk = std::min(poll, ctx->pcg.max_iters - k);
         poll = std::min(2 * poll, ctx->pcg.check_every);
-        for (int c = 0; c < chunk; ++c, ++k) {
+        for (int c = 0; c < chunk;) {
+            if (ctx->use_graphs && k >= 2 && (k & 1) == 0 && chunk - c >= kGraphIters) {
+                cudaGraphExec_t exec = nullptr;
+                int grc = iteration_graph(ctx, W, &exec);
+                if (grc) return grc;
+                CK(cudaGraphLaunch(exec, ctx->stream));
+                k += kGraphIters; c += kGraphIters;
+                ctx->launches += 2 * kGraphIters;
+                continue;
+            }
             cg_update_kernel<<<nbv, kThreads, 0, ctx->stream>>>(n, k & 1, k == 0 ? 1 : 0, ctx->Minv, Ginv, ctx->lin, lambda, v,
                                                                ctx->gpart[k & 1], ctx->gpart[(k + 1) & 1], ctx->dpart, ctx->bpart, nbs,
                                                                ctx->ctl, rtol2);
             cg_spmv_kernel<<<nbs, kThreads, 0, ctx->stream>>>(n, ctx->P, ctx->Je, ctx->U, ctx->sliceptr, ctx->ecol, ctx->Gcur, ctx->pair, W,
                                                              lambda, v.z, v.zg, v.w, ctx->dpart, ctx->bpart, ctx->lin, ctx->ctl);
             ctx->launches += 2;
+            ++k; ++c;
         }
         CK(cudaGetLastError());
-        CK(cudaMemcpyAsync(&hc, ctx->ctl, sizeof(CgControl), cudaMemcpyDeviceToHost, ctx->stream));
+        CgControl* hp = reinterpret_cast<CgControl*>(ctx->h_pinned + 5 * kMaxBlocks);      // pinned: no staging, no device-wide lock
+        CK(cudaMemcpyAsync(hp, ctx->ctl, sizeof(CgControl), cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
+        hc = *hp;
         k = hc.iters;       // updates actually executed: kernels launched after convergence were no-ops
         if (hc.converged || hc.breakdown) break;
     }

@@ -65,6 +65,8 @@ struct CgScalars { double gamma_prev, alpha_prev; };
 struct CgControl {
     CgScalars sc[2];
     double gamma0;
+    double lambda;       // damping of the running solve  } read by the iteration kernels from device memory so that a
+    double rtol2;        // squared stopping tolerance     } captured CUDA graph of iterations can be replayed unchanged
     int iters;
     int converged;
     int breakdown;
@@ -514,6 +516,7 @@ cg_spmv_kernel(int n, const double* __restrict__ P, const double* __restrict__ J
     __shared__ double2 sz[kSortGroup * 3];             // z of the tile: 3 double2 per row
     __shared__ double4 sx[kSortGroup];                 // X1 of the tile
     if (ctl && (ctl->converged || ctl->breakdown)) return;   // flags are only written by an EARLIER launch
+    if (ctl) lambda = ctl->lambda;
     if (threadIdx.x < 9) Rg[threadIdx.x] = Gp->Rg[threadIdx.x];
     if (threadIdx.x < 8) zgs[threadIdx.x] = zg[threadIdx.x];
     __syncthreads();
@@ -629,6 +632,8 @@ cg_update_kernel(int n, int par, int first, const double* __restrict__ Minv, con
                  CgControl* __restrict__ ctl, double rtol2) {
     __shared__ double sm[kThreads / 32];
     if (ctl->converged || ctl->breakdown) return;            // set by an earlier launch
+    lambda = ctl->lambda;
+    rtol2 = ctl->rtol2;
     double gamma = sum_partials(gpart_in, gridDim.x, 1, sm);
     double delta = sum_partials(dpart, nspmv, 1, sm);
     if (first && blockIdx.x == 0 && threadIdx.x == 0) ctl->gamma0 = gamma;
@@ -695,6 +700,13 @@ cg_update_kernel(int n, int par, int first, const double* __restrict__ Minv, con
     }
     block_reduce<1>(g, sm);
     if (threadIdx.x == 0) gpart_out[blockIdx.x] = g[0];
+}
+
+// host -> CgControl without a (pageable, stream-serialising) memcpy: one thread writes the fields that are >= 0 / set
+__global__ void ctl_set_kernel(CgControl* ctl, double lambda, int set_lambda, double rtol2, int set_rtol, int clear_converged) {
+    if (set_lambda) ctl->lambda = lambda;
+    if (set_rtol) ctl->rtol2 = rtol2;
+    if (clear_converged) ctl->converged = 0;
 }
 
 // ================================================================== LM trial: x_new = x (+) dx
