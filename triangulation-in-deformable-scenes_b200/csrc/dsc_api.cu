@@ -11,6 +11,7 @@
 #include "dsc_kernels_ell.cuh"
 
 #include <algorithm>
+#include <chrono>
 #include <parallel/algorithm>
 #include <cmath>
 #include <cstdio>
@@ -75,6 +76,11 @@ struct dsc_ctx {
     double* part = nullptr;               // partial-sum scratch
     double *gpart[2] = {nullptr, nullptr}, *dpart = nullptr, *bpart = nullptr;
     double* h_pinned = nullptr;           // pinned host scratch
+    // pinned, persistent host staging of the graph / observation uploads (grown on demand)
+    int *hs_rp = nullptr, *hs_cl = nullptr, *hs_ecol = nullptr, *hs_sp = nullptr;
+    double *hs_ww = nullptr, *hs_ewgt = nullptr;
+    float4* hs_uv = nullptr; double2* hs_dm = nullptr; float2* hs_isg = nullptr;
+    size_t hc_rp = 0, hc_cl = 0, hc_ecol = 0, hc_sp = 0, hc_ww = 0, hc_ewgt = 0, hc_uv = 0, hc_dm = 0, hc_isg = 0;
     dsc_pcg_params pcg{1e-10, 4000, 32};
     struct IterGraph { cudaGraphExec_t exec = nullptr; const double* P = nullptr; WeightsDev W{}; } graphs[2];   // per state buffer
     bool use_graphs = true;
@@ -119,6 +125,15 @@ cudaError_t dev_alloc(T*& p, size_t count) {
 }
 template <typename T>
 void dev_free(T*& p) { if (p) { cudaFree(p); p = nullptr; } }
+template <typename T>
+cudaError_t pin_reserve(T*& p, size_t& cap, size_t count) {       // pinned host buffer with at least `count` elements
+    if (count <= cap) return cudaSuccess;
+    if (p) { cudaFreeHost(p); p = nullptr; cap = 0; }
+    size_t want = count + count / 8 + 64;
+    cudaError_t e = cudaMallocHost(reinterpret_cast<void**>(&p), want * sizeof(T));
+    if (e == cudaSuccess) cap = want;
+    return e;
+}
 
 int grid_threads(const dsc_ctx* c, long long n) {           // thread-per-item kernels
     long long nb = (n + kThreads - 1) / kThreads;
@@ -252,6 +267,8 @@ extern "C" void dsc_destroy(dsc_ctx* ctx) {
     dev_free(ctx->errflag); dev_free(ctx->part); dev_free(ctx->gpart[0]); dev_free(ctx->gpart[1]);
     dev_free(ctx->dpart); dev_free(ctx->bpart);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+    for (void* q : {(void*)ctx->hs_rp, (void*)ctx->hs_cl, (void*)ctx->hs_ecol, (void*)ctx->hs_sp, (void*)ctx->hs_ww, (void*)ctx->hs_ewgt,
+                    (void*)ctx->hs_uv, (void*)ctx->hs_dm, (void*)ctx->hs_isg}) if (q) cudaFreeHost(q);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->evA) cudaEventDestroy(ctx->evA);
@@ -379,18 +396,18 @@ static int upload_state(dsc_ctx* ctx) {            // (re)build device state fro
     int n = ctx->n;
     if (n == 0) return DSC_OK;
     const int* pm = ctx->perm.empty() ? nullptr : ctx->perm.data();
-    std::vector<float4> uv(n);
-    std::vector<double2> dm(n);
-    std::vector<float2> sg(n);
+    CK(pin_reserve(ctx->hs_uv, ctx->hc_uv, (size_t)n)); CK(pin_reserve(ctx->hs_dm, ctx->hc_dm, (size_t)n)); CK(pin_reserve(ctx->hs_isg, ctx->hc_isg, (size_t)n));
+    float4* uv = ctx->hs_uv; double2* dm = ctx->hs_dm; float2* sg = ctx->hs_isg;
+#pragma omp parallel for schedule(static)
     for (int i = 0; i < n; ++i) {
         int s = pm ? pm[i] : i;
         uv[i] = make_float4(ctx->huv1[2 * s], ctx->huv1[2 * s + 1], ctx->huv2[2 * s], ctx->huv2[2 * s + 1]);
         dm[i] = make_double2(ctx->hd1[s], ctx->hd2[s]);
         sg[i] = make_float2(ctx->hisg1[s], ctx->hisg2[s]);
     }
-    CK(cudaMemcpyAsync(ctx->uv, uv.data(), sizeof(float4) * n, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(ctx->dm, dm.data(), sizeof(double2) * n, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(ctx->isg, sg.data(), sizeof(float2) * n, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->uv, uv, sizeof(float4) * n, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->dm, dm, sizeof(double2) * n, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->isg, sg, sizeof(float2) * n, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->X1f, ctx->hX1.data(), sizeof(float) * 3 * n, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->X2f, ctx->hX2.data(), sizeof(float) * 3 * n, cudaMemcpyHostToDevice, ctx->stream));
     if (pm) CK(cudaMemcpyAsync(ctx->d_perm, pm, sizeof(int) * n, cudaMemcpyHostToDevice, ctx->stream));
@@ -451,6 +468,14 @@ extern "C" int dsc_set_graph(dsc_ctx* ctx, int n, const int32_t* rowptr, const i
     if (!ctx->have_problem || n != ctx->n) return fail(ctx, DSC_ERR_STATE, "dsc_set_graph: upload a problem of the same size first");
     const bool validate = !(reorder & 2);
     reorder &= 1;
+    const bool timing = std::getenv("DSC_TIMING") != nullptr;
+    auto t_last = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) {
+        if (!timing) return;
+        auto t = std::chrono::steady_clock::now();
+        std::fprintf(stderr, "[dsc_set_graph] %-18s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(t - t_last).count());
+        t_last = t;
+    };
     if (!(area > 0.0) || n_triangles < 0) return fail(ctx, DSC_ERR_INVALID_ARG, "area must be > 0, n_triangles >= 0");
     CK(cudaSetDevice(ctx->device));
     long long E = n > 0 ? rowptr[n] : 0;
@@ -511,9 +536,11 @@ extern "C" int dsc_set_graph(dsc_ctx* ctx, int n, const int32_t* rowptr, const i
             });
         }
     }
+    lap("validate+sort");
     for (int i = 0; i < n; ++i) inv[perm[i]] = i;
-    std::vector<int> rp(n + 1, 0), cl((size_t)E);
-    std::vector<double> ww((size_t)E);
+    CK(pin_reserve(ctx->hs_rp, ctx->hc_rp, (size_t)n + 1)); CK(pin_reserve(ctx->hs_cl, ctx->hc_cl, (size_t)E + 1)); CK(pin_reserve(ctx->hs_ww, ctx->hc_ww, (size_t)E + 1));
+    int* rp = ctx->hs_rp; int* cl = ctx->hs_cl; double* ww = ctx->hs_ww;
+    rp[0] = 0;
     for (int i = 0; i < n; ++i) rp[i + 1] = rp[i] + (rowptr[perm[i] + 1] - rowptr[perm[i]]);
 #pragma omp parallel for schedule(static, 4096)
     for (int i = 0; i < n; ++i) {
@@ -525,28 +552,34 @@ extern "C" int dsc_set_graph(dsc_ctx* ctx, int n, const int32_t* rowptr, const i
             cl[o + b2 + 1] = cj; ww[o + b2 + 1] = wj;
         }
     }
+    lap("csr permute");
     // sliced ELL of the PCG operator: slice = 32 consecutive rows (one warp), width = longest row of the slice;
     // column k of slice s is "block" sliceptr[s] + k: 32 column indices and 9 x 32 Jacobian doubles (Je).
     // Padding entries point at the row itself and keep an all-zero Jacobian record, so they add exactly 0.
     int nslices = (n + 31) / 32;
-    std::vector<int> sp(nslices + 1, 0);
+    CK(pin_reserve(ctx->hs_sp, ctx->hc_sp, (size_t)nslices + 1));
+    int* sp = ctx->hs_sp;
+    sp[0] = 0;
     for (int sl = 0; sl < nslices; ++sl) {
         int wmax = 0;
         for (int i = sl * 32; i < std::min(n, sl * 32 + 32); ++i) wmax = std::max(wmax, rp[i + 1] - rp[i]);
         sp[sl + 1] = sp[sl] + wmax;
     }
     size_t nblk = (size_t)sp[nslices];
-    std::vector<int> ecol(nblk * 32);
-    std::vector<double> ewgt(nblk * 32, 0.0);
+    CK(pin_reserve(ctx->hs_ecol, ctx->hc_ecol, nblk * 32 + 1)); CK(pin_reserve(ctx->hs_ewgt, ctx->hc_ewgt, nblk * 32 + 1));
+    int* ecol = ctx->hs_ecol; double* ewgt = ctx->hs_ewgt;
 #pragma omp parallel for schedule(static, 256)
     for (int sl = 0; sl < nslices; ++sl)
         for (int k = 0; k < sp[sl + 1] - sp[sl]; ++k)
             for (int l = 0; l < 32; ++l) {
                 int i = sl * 32 + l;
                 int v = i < n ? i : 0;
-                if (i < n && k < rp[i + 1] - rp[i]) { v = cl[rp[i] + k]; ewgt[((size_t)sp[sl] + k) * 32 + l] = ww[rp[i] + k]; }
+                double wv = 0.0;
+                if (i < n && k < rp[i + 1] - rp[i]) { v = cl[rp[i] + k]; wv = ww[rp[i] + k]; }
                 ecol[((size_t)sp[sl] + k) * 32 + l] = v;
+                ewgt[((size_t)sp[sl] + k) * 32 + l] = wv;
             }
+    lap("ell build");
     if (E > ctx->ecap) {
         CK(dev_alloc(ctx->col, (size_t)E)); CK(dev_alloc(ctx->wgt, (size_t)E));
         ctx->ecap = E;
@@ -558,22 +591,25 @@ extern "C" int dsc_set_graph(dsc_ctx* ctx, int n, const int32_t* rowptr, const i
     if (nslices + 1 > ctx->slcap) { CK(dev_alloc(ctx->sliceptr, (size_t)nslices + 1)); ctx->slcap = nslices + 1; }
     ctx->E = E; ctx->nblk = (long long)nblk;
     ctx->area = area; ctx->ntri = n_triangles;
-    CK(cudaMemcpyAsync(ctx->rowptr, rp.data(), sizeof(int) * (n + 1), cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(ctx->sliceptr, sp.data(), sizeof(int) * (nslices + 1), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->rowptr, rp, sizeof(int) * (n + 1), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->sliceptr, sp, sizeof(int) * (nslices + 1), cudaMemcpyHostToDevice, ctx->stream));
     if (E > 0) {
-        CK(cudaMemcpyAsync(ctx->col, cl.data(), sizeof(int) * E, cudaMemcpyHostToDevice, ctx->stream));
-        CK(cudaMemcpyAsync(ctx->wgt, ww.data(), sizeof(double) * E, cudaMemcpyHostToDevice, ctx->stream));
-        CK(cudaMemcpyAsync(ctx->ecol, ecol.data(), sizeof(int) * nblk * 32, cudaMemcpyHostToDevice, ctx->stream));
-        CK(cudaMemcpyAsync(ctx->ewgt, ewgt.data(), sizeof(double) * nblk * 32, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->col, cl, sizeof(int) * E, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->wgt, ww, sizeof(double) * E, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->ecol, ecol, sizeof(int) * nblk * 32, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->ewgt, ewgt, sizeof(double) * nblk * 32, cudaMemcpyHostToDevice, ctx->stream));
         CK(cudaMemsetAsync(ctx->Je, 0, sizeof(double) * nblk * 288, ctx->stream));
     }
     CK(cudaStreamSynchronize(ctx->stream));
+    lap("uploads");
     bool identity = true;
     for (int i = 0; i < n; ++i) if (perm[i] != i) { identity = false; break; }
     if (identity) ctx->perm.clear(); else ctx->perm = perm;
     ctx->have_graph = true; ctx->have_rot = false;
     drop_graphs(ctx);
-    return upload_state(ctx);
+    int urc = upload_state(ctx);
+    lap("upload_state");
+    return urc;
 }
 
 extern "C" int dsc_compute_rotations(dsc_ctx* ctx) {
