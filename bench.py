@@ -186,6 +186,9 @@ def main():
         print(json.dumps(line))
         return 0
 
+    # torchrun pins OMP_NUM_THREADS=1; the library's host-side graph renumbering is OpenMP-parallel, so give every
+    # rank its share of the host cores (must be set before libgomp is loaded with the library)
+    os.environ["OMP_NUM_THREADS"] = str(max(1, (os.cpu_count() or 8) // max(1, world)))
     import __graft_entry__ as g
     pkg = g.package()
     dist = None
