@@ -97,8 +97,9 @@ def prepare(pkg, ctx, sc, args):
         raise RuntimeError(f"only {len(idx)} valid correspondences of {args.n} requested")
     prob = dict(pair=pair, prm=prm, X1=X1[idx], X2=X2[idx], uv1=sc["uv1"][idx], uv2=sc["uv2"][idx],
                 d1=sc["d1"][idx].astype(np.float64), d2=sc["d2"][idx].astype(np.float64), area=sc["area"])
-    rowptr, col, w = wl.knn_graph(prob["X1"][:, :2].astype(np.float64), args.k)
-    prob.update(rowptr=rowptr, col=col, w=w, ntri=2 * len(idx))
+    t0 = time.perf_counter()
+    rowptr, col, w = ctx.knn_graph(prob["X1"], args.k)          # symmetrised k-NN graph built on the GPU (dsc_knn_build)
+    prob.update(rowptr=rowptr, col=col, w=w, ntri=2 * len(idx), graph_build_ms=(time.perf_counter() - t0) * 1e3)
     # initial depth scales (KeyFrame::setInitialDepthScaleInSimulationImages) from the kept points
     ctx.tri_upload(pair, prob["uv1"], prob["uv2"], prob["d1"].astype(np.float32), prob["d2"].astype(np.float32))
     ctx.tri_run(prm)
@@ -326,7 +327,7 @@ def main():
                     e2e=dict(value=e2e_val, unit="LM it/s", h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(d2h),
                              ms_per_step=e2e_ms / args.steps),
                     gpu_launches=int(launches), clocks=clocks, roofline=roof, cpu_baseline=cpu,
-                    triangulated_points_per_s=roof["triangulate"]["points_per_s"],
+                    triangulated_points_per_s=roof["triangulate"]["points_per_s"], knn_graph_build_ms=prob["graph_build_ms"],
                     cg_iteration_ms=cg_ms, wall_ms_per_step=wall_ms / args.steps)
         print(json.dumps(line))
     if dist is not None:

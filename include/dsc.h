@@ -206,6 +206,13 @@ enum { DSC_K_SPMV = 0, DSC_K_UPDATE = 1, DSC_K_LINEARIZE = 2, DSC_K_COST = 3, DS
 int dsc_profile_kernels(dsc_ctx* ctx, const dsc_weights* w, int warm, int reps, double* ms, double* bytes);
 /* same for the triangulation kernel (needs dsc_tri_upload first) */
 int dsc_profile_triangulate(dsc_ctx* ctx, const dsc_tri_params* prm, int warm, int reps, double* ms, double* bytes);
+/* ---- graph set-up on the GPU ----------------------------------------------------------------
+ * Symmetrised k-nearest-neighbour graph in the plane (x, y) of n points X[n][3] (host, float), k <= 32: uniform grid +
+ * ring search, rows ascending.  This is the adjacency the synthetic 100k / 1M configurations use in place of the
+ * reference's Delaunay mesh (Modules/Utils/Geometry.cc:317-368).  dsc_knn_build leaves the CSR on the device and
+ * reports the number of directed edges; dsc_knn_download copies rowptr[n+1] / col[E] out (feed them to dsc_set_graph). */
+int dsc_knn_build(dsc_ctx* ctx, int n, const float* X, int k, long long* n_edges);
+int dsc_knn_download(dsc_ctx* ctx, int32_t* rowptr, int32_t* col);
 /* problem size as seen by the library: n correspondences, E directed edges */
 int dsc_problem_size(const dsc_ctx* ctx, long long* n, long long* n_edges);
 

@@ -333,3 +333,33 @@ def test_early_reject_keeps_the_trace(pkg, ctx):
     ctx.reset_state()
     r2, s2 = ctx.optimize(w, 25)
     assert s2.early_rejects == 0 and s2.total_pcg_iters == s0.total_pcg_iters
+
+
+@pytest.mark.parametrize("n,k,seed", [(1, 4, 0), (5, 8, 1), (3000, 8, 2), (20000, 16, 3)])
+def test_gpu_knn_graph_matches_kdtree(pkg, ctx, n, k, seed):
+    """Neighbour-graph indexing must be bit-exact: the GPU grid search against the oracle's k-d tree graph."""
+    rng = np.random.default_rng(seed)
+    X = np.stack([rng.normal(0, 0.03, n), rng.normal(0, 0.01, n), rng.normal(0.2, 0.01, n)], 1).astype(np.float32)
+    if n >= 3000:
+        X[7] = X[11]                                   # a duplicate position (zero distance) must not break anything
+    rowptr, col, w = ctx.knn_graph(X, k)
+    if n <= k:
+        # fewer points than neighbours: everybody is everybody's neighbour
+        assert rowptr[-1] == n * (n - 1)
+        return
+    g = ograph.knn_graph(X.astype(np.float64), k, 1.0)
+    assert np.array_equal(rowptr, g.rowptr)
+    assert np.array_equal(col, g.col)
+
+
+def test_gpu_knn_graph_on_a_clustered_tube(pkg, ctx):
+    import importlib
+    wl = importlib.import_module(pkg.__name__ + ".workloads")
+    sc = wl.tube_scene(60000, seed=5)
+    cam = (0, sc["cam"])
+    pair = pkg.make_pair(cam, cam, sc["T1"], sc["T2"])
+    X1, X2, valid, cosp, nv = ctx.triangulate(pair, ctx.tri_params("NRSLAM", "FarPoints", 1, sc["min_cos"]), sc["uv1"], sc["uv2"])
+    X = X1[valid]
+    rowptr, col, w = ctx.knn_graph(X, 8)
+    r2, c2, _ = wl.knn_graph(X[:, :2].astype(np.float64), 8)
+    assert np.array_equal(rowptr, r2) and np.array_equal(col, c2)

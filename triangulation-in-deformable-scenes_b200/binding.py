@@ -24,7 +24,7 @@ EXPORTS = [
     "dsc_triangulate", "dsc_tri_upload", "dsc_tri_run", "dsc_tri_download", "dsc_depth_scale_init",
     "dsc_problem_upload", "dsc_set_graph", "dsc_compute_rotations", "dsc_get_rotations", "dsc_set_rotations",
     "dsc_reset_state", "dsc_set_pcg", "dsc_set_early_reject", "dsc_cost", "dsc_optimize", "dsc_download", "dsc_pixel_sigma",
-    "dsc_debug_linearize", "dsc_debug_matvec", "dsc_profile_kernels", "dsc_profile_triangulate", "dsc_problem_size",
+    "dsc_debug_linearize", "dsc_debug_matvec", "dsc_profile_kernels", "dsc_profile_triangulate", "dsc_problem_size", "dsc_knn_build", "dsc_knn_download",
 ]
 KERNEL_NAMES = ["cg_spmv", "cg_update", "linearize", "cost", "precond", "apply_update", "rotations"]
 
@@ -332,3 +332,15 @@ class Context:
         e = C.c_longlong()
         self._ck(self.lib.dsc_problem_size(self.h, C.byref(n), C.byref(e)))
         return n.value, e.value
+
+    def knn_graph(self, X, k):
+        """symmetrised k-NN graph in (x, y) built on the GPU -> (rowptr, col, unit weights)"""
+        X = _f32(X, (-1, 3))
+        n = X.shape[0]
+        E = C.c_longlong()
+        self._ck(self.lib.dsc_knn_build(self.h, n, _fp(X), int(k), C.byref(E)))
+        rowptr = np.empty(n + 1, np.int32)
+        col = np.empty(max(E.value, 1), np.int32)
+        self._ck(self.lib.dsc_knn_download(self.h, _fp(rowptr), _fp(col)))
+        col = col[:E.value]
+        return rowptr, col, np.ones(E.value, np.float64)

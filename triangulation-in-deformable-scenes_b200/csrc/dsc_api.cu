@@ -9,6 +9,7 @@
 #include "../../include/dsc.h"
 #include "dsc_kernels.cuh"
 #include "dsc_kernels_ell.cuh"
+#include "dsc_knn.cuh"
 
 #include <algorithm>
 #include <chrono>
@@ -81,6 +82,9 @@ struct dsc_ctx {
     double *hs_ww = nullptr, *hs_ewgt = nullptr;
     float4* hs_uv = nullptr; double2* hs_dm = nullptr; float2* hs_isg = nullptr;
     size_t hc_rp = 0, hc_cl = 0, hc_ecol = 0, hc_sp = 0, hc_ww = 0, hc_ewgt = 0, hc_uv = 0, hc_dm = 0, hc_isg = 0;
+    // ---- kNN graph builder (device CSR of the last dsc_knn_build)
+    int knn_n = 0; long long knn_E = 0;
+    int *knn_rowptr = nullptr, *knn_col = nullptr;
     dsc_pcg_params pcg{1e-10, 4000, 32};
     struct IterGraph { cudaGraphExec_t exec = nullptr; const double* P = nullptr; WeightsDev W{}; } graphs[2];   // per state buffer
     bool use_graphs = true;
@@ -263,6 +267,7 @@ extern "C" void dsc_destroy(dsc_ctx* ctx) {
     dev_free(ctx->rowptr); dev_free(ctx->col); dev_free(ctx->wgt); dev_free(ctx->Je); dev_free(ctx->ecol); dev_free(ctx->ewgt); dev_free(ctx->sliceptr);
     dev_free(ctx->b); dev_free(ctx->D); dev_free(ctx->U); dev_free(ctx->Minv);
     for (auto& v : ctx->vec) dev_free(v);
+    dev_free(ctx->knn_rowptr); dev_free(ctx->knn_col);
     dev_free(ctx->small); dev_free(ctx->Gcur); dev_free(ctx->Gtrial); dev_free(ctx->lin); dev_free(ctx->ctl);
     dev_free(ctx->errflag); dev_free(ctx->part); dev_free(ctx->gpart[0]); dev_free(ctx->gpart[1]);
     dev_free(ctx->dpart); dev_free(ctx->bpart);
@@ -1178,5 +1183,88 @@ extern "C" int dsc_profile_triangulate(dsc_ctx* ctx, const dsc_tri_params* prm, 
     ctx->t_done = true;
     *ms = ev_ms(ctx->evA, ctx->evB) / reps;
     if (bytes) *bytes = (double)ctx->tn * (16.0 + (prm->method == DSC_TRI_DEPTH ? 8.0 : 0.0) + 24.0 + 1.0 + 4.0);
+    return DSC_OK;
+}
+
+// ------------------------------------------------------------------ kNN graph on the GPU
+extern "C" int dsc_knn_build(dsc_ctx* ctx, int n, const float* X, int k, long long* n_edges) {
+    if (!ctx || n < 0 || (n > 0 && !X) || k < 1 || k > kKnnMax) return fail(ctx, DSC_ERR_INVALID_ARG, "dsc_knn_build");
+    CK(cudaSetDevice(ctx->device));
+    dev_free(ctx->knn_rowptr); dev_free(ctx->knn_col);
+    ctx->knn_n = n; ctx->knn_E = 0;
+    if (n_edges) *n_edges = 0;
+    CK(dev_alloc(ctx->knn_rowptr, (size_t)n + 1));
+    if (n == 0) { CK(cudaMemset(ctx->knn_rowptr, 0, sizeof(int))); return DSC_OK; }
+    double x0 = 1e300, x1 = -1e300, y0 = 1e300, y1 = -1e300;
+    for (int i = 0; i < n; ++i) {
+        double x = X[3 * (size_t)i], y = X[3 * (size_t)i + 1];
+        if (!std::isfinite(x) || !std::isfinite(y)) return fail(ctx, DSC_ERR_INVALID_ARG, "dsc_knn_build: non-finite coordinate");
+        x0 = std::min(x0, x); x1 = std::max(x1, x); y0 = std::min(y0, y); y1 = std::max(y1, y);
+    }
+    double w = x1 - x0, h = y1 - y0;
+    KnnGrid g{x0, y0, 1.0, 1, 1};
+    if (w > 0 || h > 0) {
+        double cell = std::sqrt(std::max(w, 1e-300) * std::max(h, 1e-300) / std::max(1.0, n / 2.0));
+        cell = std::max(cell, std::max(w, h) / 4096.0);
+        g.inv_cell = 1.0 / cell;
+        g.nx = std::max(1, (int)std::ceil(w / cell) + 1);
+        g.ny = std::max(1, (int)std::ceil(h / cell) + 1);
+    }
+    int ncells = g.nx * g.ny;
+    float* dX = nullptr;
+    int *cell = nullptr, *cnt = nullptr, *start = nullptr, *cursor = nullptr, *order = nullptr, *nbr = nullptr, *sums = nullptr, *deg = nullptr;
+    auto release = [&]() { dev_free(dX); dev_free(cell); dev_free(cnt); dev_free(start); dev_free(cursor); dev_free(order); dev_free(nbr); dev_free(sums); dev_free(deg); };
+    auto scan = [&](int m, const int* in, int* out) -> int {      // exclusive scan of m ints
+        int nb = (m + kScanBlock - 1) / kScanBlock;
+        scan_block_kernel<<<nb, kScanBlock, 0, ctx->stream>>>(m, in, out, sums);
+        scan_sums_kernel<<<1, kScanBlock, 0, ctx->stream>>>(nb, sums);
+        scan_add_kernel<<<nb, kScanBlock, 0, ctx->stream>>>(m, out, sums);
+        ctx->launches += 3;
+        return DSC_OK;
+    };
+    int m = std::max(ncells, n) + 1;
+    cudaError_t e = cudaSuccess;
+    if ((e = dev_alloc(dX, 3 * (size_t)n)) || (e = dev_alloc(cell, (size_t)n)) || (e = dev_alloc(cnt, (size_t)m)) || (e = dev_alloc(start, (size_t)m)) ||
+        (e = dev_alloc(cursor, (size_t)m)) || (e = dev_alloc(order, (size_t)n)) || (e = dev_alloc(nbr, (size_t)n * k)) ||
+        (e = dev_alloc(sums, (size_t)(m / kScanBlock + 2))) || (e = dev_alloc(deg, (size_t)n + 1))) {
+        release();
+        return fail(ctx, DSC_ERR_ALLOC, cudaGetErrorString(e));
+    }
+    int nbt = grid_threads(ctx, n);
+    CK(cudaMemcpyAsync(dX, X, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemsetAsync(cnt, 0, sizeof(int) * m, ctx->stream));
+    CK(cudaMemsetAsync(cursor, 0, sizeof(int) * m, ctx->stream));
+    knn_cell_kernel<<<nbt, kThreads, 0, ctx->stream>>>(n, dX, g, cell, cnt);
+    scan(ncells, cnt, start);
+    knn_scatter_kernel<<<nbt, kThreads, 0, ctx->stream>>>(n, cell, start, cursor, order);
+    knn_search_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(n, k, dX, g, start, order, ncells, nbr);
+    knn_owncount_kernel<<<nbt, kThreads, 0, ctx->stream>>>(n, k, nbr, deg);
+    knn_extra_kernel<<<nbt, kThreads, 0, ctx->stream>>>(n, k, nbr, deg);
+    CK(cudaMemsetAsync(deg + n, 0, sizeof(int), ctx->stream));
+    scan(n + 1, deg, ctx->knn_rowptr);
+    ctx->launches += 5;
+    int E = 0;
+    CK(cudaMemcpyAsync(&E, ctx->knn_rowptr + n, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if ((e = dev_alloc(ctx->knn_col, (size_t)std::max(E, 1)))) { release(); return fail(ctx, DSC_ERR_ALLOC, cudaGetErrorString(e)); }
+    CK(cudaMemsetAsync(cursor, 0, sizeof(int) * m, ctx->stream));
+    knn_fill_kernel<<<nbt, kThreads, 0, ctx->stream>>>(n, k, nbr, ctx->knn_rowptr, cursor, ctx->knn_col);
+    knn_sortrows_kernel<<<nbt, kThreads, 0, ctx->stream>>>(n, ctx->knn_rowptr, ctx->knn_col);
+    ctx->launches += 2;
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(ctx->stream));
+    release();
+    ctx->knn_E = E;
+    if (n_edges) *n_edges = E;
+    return DSC_OK;
+}
+
+extern "C" int dsc_knn_download(dsc_ctx* ctx, int32_t* rowptr, int32_t* col) {
+    if (!ctx || !rowptr) return DSC_ERR_INVALID_ARG;
+    if (!ctx->knn_rowptr) return fail(ctx, DSC_ERR_STATE, "dsc_knn_download before dsc_knn_build");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpyAsync(rowptr, ctx->knn_rowptr, sizeof(int) * ((size_t)ctx->knn_n + 1), cudaMemcpyDeviceToHost, ctx->stream));
+    if (col && ctx->knn_E > 0) CK(cudaMemcpyAsync(col, ctx->knn_col, sizeof(int) * (size_t)ctx->knn_E, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
     return DSC_OK;
 }
