@@ -249,6 +249,7 @@ extern "C" int dsc_create(int device, dsc_ctx** out) {
     ctx->use_graphs = std::getenv("DSC_NO_GRAPHS") == nullptr;
     if (cudaFuncSetAttribute(rotations_ell_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWinBytes) != cudaSuccess ||
         cudaFuncSetAttribute(cost_ell_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWinBytes) != cudaSuccess ||
+        cudaFuncSetAttribute(cg_spmv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSpmvSmem) != cudaSuccess ||
         cudaFuncSetAttribute(linearize_ell_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWinBytes) != cudaSuccess) return bail(DSC_ERR_CUDA);
     *out = ctx;
     return DSC_OK;
@@ -756,7 +757,7 @@ static int pcg_begin(dsc_ctx* ctx, const WeightsDev& W, double lambda) {
     ctl_set_kernel<<<1, 1, 0, ctx->stream>>>(ctx->ctl, lambda, 1, 0.0, 0, 0);
     precond_kernel<<<nbv, kThreads, 0, ctx->stream>>>(n, ctx->D, lambda, ctx->lin, ctx->Minv, Ginv, ctx->errflag);
     cg_init_kernel<<<nbv, kThreads, 0, ctx->stream>>>(n, ctx->b, ctx->lin, ctx->Minv, Ginv, v, ctx->gpart[0], ctx->ctl);
-    cg_spmv_kernel<<<nbs, kThreads, 0, ctx->stream>>>(n, ctx->P, ctx->Je, ctx->U, ctx->sliceptr, ctx->ecol, ctx->Gcur, ctx->pair, W,
+    cg_spmv_kernel<<<nbs, kThreads, kSpmvSmem, ctx->stream>>>(n, ctx->P, ctx->Je, ctx->U, ctx->sliceptr, ctx->ecol, ctx->Gcur, ctx->pair, W,
                                                      lambda, v.z, v.zg, v.w, ctx->dpart, ctx->bpart, ctx->lin, ctx->ctl);
     ctx->launches += 3;
     CK(cudaGetLastError());
@@ -780,7 +781,7 @@ static int iteration_graph(dsc_ctx* ctx, const WeightsDev& W, cudaGraphExec_t* o
     for (int k = 2; k < 2 + kGraphIters; ++k) {
         cg_update_kernel<<<nbv, kThreads, 0, ctx->stream>>>(n, k & 1, 0, ctx->Minv, Ginv, ctx->lin, 0.0, v, ctx->gpart[k & 1],
                                                            ctx->gpart[(k + 1) & 1], ctx->dpart, ctx->bpart, nbs, ctx->ctl, 0.0);
-        cg_spmv_kernel<<<nbs, kThreads, 0, ctx->stream>>>(n, ctx->P, ctx->Je, ctx->U, ctx->sliceptr, ctx->ecol, ctx->Gcur, ctx->pair, W,
+        cg_spmv_kernel<<<nbs, kThreads, kSpmvSmem, ctx->stream>>>(n, ctx->P, ctx->Je, ctx->U, ctx->sliceptr, ctx->ecol, ctx->Gcur, ctx->pair, W,
                                                          0.0, v.z, v.zg, v.w, ctx->dpart, ctx->bpart, ctx->lin, ctx->ctl);
     }
     cudaError_t e = cudaStreamEndCapture(ctx->stream, &graph);
@@ -821,7 +822,7 @@ static int pcg_resume(dsc_ctx* ctx, const WeightsDev& W, double lambda, double r
             cg_update_kernel<<<nbv, kThreads, 0, ctx->stream>>>(n, k & 1, k == 0 ? 1 : 0, ctx->Minv, Ginv, ctx->lin, lambda, v,
                                                                ctx->gpart[k & 1], ctx->gpart[(k + 1) & 1], ctx->dpart, ctx->bpart, nbs,
                                                                ctx->ctl, rtol2);
-            cg_spmv_kernel<<<nbs, kThreads, 0, ctx->stream>>>(n, ctx->P, ctx->Je, ctx->U, ctx->sliceptr, ctx->ecol, ctx->Gcur, ctx->pair, W,
+            cg_spmv_kernel<<<nbs, kThreads, kSpmvSmem, ctx->stream>>>(n, ctx->P, ctx->Je, ctx->U, ctx->sliceptr, ctx->ecol, ctx->Gcur, ctx->pair, W,
                                                              lambda, v.z, v.zg, v.w, ctx->dpart, ctx->bpart, ctx->lin, ctx->ctl);
             ctx->launches += 2;
             ++k; ++c;
@@ -1053,7 +1054,7 @@ extern "C" int dsc_debug_matvec(dsc_ctx* ctx, const dsc_weights* w, double lambd
     if (n) CK(cudaMemcpyAsync(v.z, hz.data(), sizeof(double) * 6 * n, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(v.zg, x, sizeof(double) * 8, cudaMemcpyHostToDevice, ctx->stream));
     int nbs = grid_spmv(ctx, n);
-    cg_spmv_kernel<<<nbs, kThreads, 0, ctx->stream>>>(n, ctx->P, ctx->Je, ctx->U, ctx->sliceptr, ctx->ecol, ctx->Gcur, ctx->pair, W,
+    cg_spmv_kernel<<<nbs, kThreads, kSpmvSmem, ctx->stream>>>(n, ctx->P, ctx->Je, ctx->U, ctx->sliceptr, ctx->ecol, ctx->Gcur, ctx->pair, W,
                                                      lambda, v.z, v.zg, v.w, ctx->dpart, ctx->bpart, ctx->lin, nullptr);
     ctx->launches++;
     CK(cudaGetLastError());
@@ -1122,7 +1123,7 @@ extern "C" int dsc_profile_kernels(dsc_ctx* ctx, const dsc_weights* w, int warm,
         return DSC_OK;
     };
     s = time_it(DSC_K_SPMV, [&]() {
-        cg_spmv_kernel<<<nbp, kThreads, 0, ctx->stream>>>(n, ctx->P, ctx->Je, ctx->U, ctx->sliceptr, ctx->ecol, ctx->Gcur, ctx->pair, W,
+        cg_spmv_kernel<<<nbp, kThreads, kSpmvSmem, ctx->stream>>>(n, ctx->P, ctx->Je, ctx->U, ctx->sliceptr, ctx->ecol, ctx->Gcur, ctx->pair, W,
                                                          lambda, v.z, v.zg, v.w, ctx->dpart, ctx->bpart, ctx->lin, nullptr);
     });
     if (s) return s;

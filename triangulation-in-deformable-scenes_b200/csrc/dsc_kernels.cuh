@@ -503,6 +503,35 @@ cg_init_kernel(int n, const double* __restrict__ b, const LinGlobal* __restrict_
 // at the row itself and carry an all-zero record.  Only z_j (48 B) and X1_j (32 B) are gathered (L1/L2: the
 // space-filling-curve order keeps neighbours close).  dpart[grid]: partial z.w (global rows included),
 // bpart[grid][8]: partial global rows (T_g from the ARAP sums, s1/s2 from the depth edges).
+// Bulk asynchronous copies (cp.async.bulk, the non-tensor TMA path) + mbarrier completion, used by cg_spmv_kernel to
+// stream the ELL blocks into a per-warp shared-memory ring: the bytes in flight no longer depend on registers.
+DSC_D unsigned smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+DSC_D void mbar_init(unsigned long long* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+}
+DSC_D void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+DSC_D void bulk_load(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_addr(dst)), "l"(src), "r"(bytes), "r"(smem_addr(bar)) : "memory");
+}
+DSC_D void mbar_wait(unsigned long long* bar, unsigned parity) {
+    asm volatile("{\n"
+                 ".reg .pred p;\n"
+                 "MBAR_WAIT:\n"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+                 "@p bra MBAR_DONE;\n"
+                 "bra MBAR_WAIT;\n"
+                 "MBAR_DONE:\n"
+                 "}" ::"r"(smem_addr(bar)), "r"(parity) : "memory");
+}
+
+constexpr int kSpmvStages = 3;                                   // ring depth per warp (ELL blocks in flight)
+constexpr int kSpmvStageBytes = 9 * 32 * 8 + 32 * 4;             // one ELL block: Je[9][32] doubles + ecol[32] ints
+constexpr int kSpmvWinBytes = kSortGroup * (48 + 32);            // z (6 doubles) and X1 (double4) of the tile
+constexpr int kSpmvSmem = kSpmvWinBytes + (kThreads / 32) * kSpmvStages * kSpmvStageBytes;
+
 __global__ void __launch_bounds__(kThreads, 2)
 cg_spmv_kernel(int n, const double* __restrict__ P, const double* __restrict__ Je, const double* __restrict__ U,
                const int* __restrict__ sliceptr, const int* __restrict__ ecol,
@@ -510,40 +539,75 @@ cg_spmv_kernel(int n, const double* __restrict__ P, const double* __restrict__ J
                double lambda, const double* __restrict__ z, const double* __restrict__ zg, double* __restrict__ w,
                double* __restrict__ dpart, double* __restrict__ bpart,
                const LinGlobal* __restrict__ lin, const CgControl* __restrict__ ctl) {
+    extern __shared__ __align__(128) unsigned char dyn[];
     __shared__ double sm[9 * (kThreads / 32)];
     __shared__ double Rg[9];
     __shared__ double zgs[8];
-    __shared__ double2 sz[kSortGroup * 3];             // z of the tile: 3 double2 per row
-    __shared__ double4 sx[kSortGroup];                 // X1 of the tile
+    __shared__ unsigned long long bars[(kThreads / 32) * kSpmvStages + 1];
+    double2* sz = reinterpret_cast<double2*>(dyn);                               // z of the tile: 3 double2 per row
+    double4* sx = reinterpret_cast<double4*>(dyn + kSortGroup * 48);             // X1 of the tile
     if (ctl && (ctl->converged || ctl->breakdown)) return;   // flags are only written by an EARLIER launch
     if (ctl) lambda = ctl->lambda;
-    if (threadIdx.x < 9) Rg[threadIdx.x] = Gp->Rg[threadIdx.x];
-    if (threadIdx.x < 8) zgs[threadIdx.x] = zg[threadIdx.x];
-    __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int wpb = kThreads / 32;
+    if (threadIdx.x < 9) Rg[threadIdx.x] = Gp->Rg[threadIdx.x];
+    if (threadIdx.x < 8) zgs[threadIdx.x] = zg[threadIdx.x];
+    if (threadIdx.x <= wpb * kSpmvStages) mbar_init(bars + threadIdx.x, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    unsigned long long* wbar = bars + wpb * kSpmvStages;                         // window barrier
+    unsigned long long* rbar = bars + warp * kSpmvStages;                        // this warp's ring barriers
+    unsigned char* ring = dyn + kSpmvWinBytes + warp * kSpmvStages * kSpmvStageBytes;
     const D3 zw = d3(zgs[0], zgs[1], zgs[2]);
     const D3 zv2 = d3(2.0 * zgs[3], 2.0 * zgs[4], 2.0 * zgs[5]);
     double acc[9];                                     // T_g border (6), s1, s2 border, z.w
 #pragma unroll
     for (int k = 0; k < 9; ++k) acc[k] = 0.0;
     // A block owns a tile = one degree-sorted group of kSortGroup rows; the tile's z and X1 are staged in shared
-    // memory (coalesced) and a neighbour inside the tile is read from there; halo neighbours come from L2.
+    // memory (two bulk copies) and a neighbour inside the tile is read from there; halo neighbours come from L2.
+    // Warp w walks slices w and 15 - w of the tile (balanced: the slices are degree-sorted); their ELL blocks form
+    // one stream of kSpmvStageBytes records that lane 0 keeps kSpmvStages deep in flight.
     const int ntiles = (n + kSortGroup - 1) / kSortGroup;
+    unsigned cons = 0;                                 // ring slots consumed so far by this warp (stage, phase)
+    unsigned wphase = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int v0 = tile * kSortGroup;
         const int nv = min(kSortGroup, n - v0);
-        __syncthreads();
-        {
-            const double2* zsrc = reinterpret_cast<const double2*>(z + 6 * (size_t)v0);
-            for (int k = threadIdx.x; k < nv * 3; k += kThreads) sz[k] = zsrc[k];
-            const double4* psrc = reinterpret_cast<const double4*>(P) + v0;
-            for (int k = threadIdx.x; k < nv; k += kThreads) sx[k] = ldg256(psrc + k);
+        const int lsv[2] = {warp, 2 * wpb - 1 - warp};
+        int rb[2], rl[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const bool ok = lsv[h] * 32 < nv;
+            const int sl = (v0 >> 5) + lsv[h];
+            rb[h] = ok ? __ldg(sliceptr + sl) : 0;
+            rl[h] = ok ? __ldg(sliceptr + sl + 1) - rb[h] : 0;
         }
-        __syncthreads();
-      for (int ls = warp; ls * 32 < nv; ls += wpb) {
-        const int sl = (v0 >> 5) + ls;
-        const int il = ls * 32 + lane;
+        const int total = rl[0] + rl[1];
+        auto issue = [&](int q, unsigned slot, int dep) {   // lane 0: fetch stream element q into ring slot
+            if (dep == 0x7ff4d5c1) q = 0;              // never taken for a finite s; keeps the dependency alive
+            const int bk = q < rl[0] ? rb[0] + q : rb[1] + (q - rl[0]);
+            unsigned char* dst = ring + (slot % kSpmvStages) * kSpmvStageBytes;
+            unsigned long long* bar = rbar + (slot % kSpmvStages);
+            mbar_expect_tx(bar, kSpmvStageBytes);
+            bulk_load(dst, Je + (size_t)bk * 288, 2304, bar);
+            bulk_load(dst + 2304, ecol + (size_t)bk * 32, 128, bar);
+        };
+        __syncthreads();                               // everyone is done with the previous window
+        if (threadIdx.x == 0) {
+            mbar_expect_tx(wbar, (unsigned)nv * 80u);
+            bulk_load(sz, z + 6 * (size_t)v0, (unsigned)nv * 48u, wbar);
+            bulk_load(sx, reinterpret_cast<const double4*>(P) + v0, (unsigned)nv * 32u, wbar);
+        }
+        if (lane == 0)
+            for (int q = 0; q < kSpmvStages && q < total; ++q) issue(q, cons + q, 0);
+        mbar_wait(wbar, wphase);
+        wphase ^= 1u;
+        int q = 0;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        if (rl[h] == 0) continue;
+        const int il = lsv[h] * 32 + lane;
         const int i = v0 + il;
         const bool act = il < nv;
         const int ilc = act ? il : nv - 1;
@@ -551,14 +615,16 @@ cg_spmv_kernel(int n, const double* __restrict__ P, const double* __restrict__ J
         const D3 zi1 = d3(a0.x, a0.y, a1.x), zi2 = d3(a1.y, a2.x, a2.y);
         const double4 xi = sx[ilc];
         const D3 X1i = d3(xi.x, xi.y, xi.z);
-        const int b0 = __ldg(sliceptr + sl), b1 = __ldg(sliceptr + sl + 1);
         D3 Am = d3(0, 0, 0), Ag = d3(0, 0, 0), Au = d3(0, 0, 0);
-        for (int bk = b0; bk < b1; ++bk) {
-            const int j = __ldg(ecol + (size_t)bk * 32 + lane);
-            const double* jb = Je + (size_t)bk * 288 + lane;
-            const D3 u = d3(__ldg(jb), __ldg(jb + 32), __ldg(jb + 64));
-            const D3 m = d3(__ldg(jb + 96), __ldg(jb + 128), __ldg(jb + 160));
-            const D3 g = d3(__ldg(jb + 192), __ldg(jb + 224), __ldg(jb + 256));
+        for (int e = 0; e < rl[h]; ++e, ++q, ++cons) {
+            const unsigned st = cons % kSpmvStages;
+            mbar_wait(rbar + st, (cons / kSpmvStages) & 1u);
+            const unsigned char* sb = ring + st * kSpmvStageBytes;
+            const double* jb = reinterpret_cast<const double*>(sb) + lane;
+            const int j = reinterpret_cast<const int*>(sb + 2304)[lane];
+            const D3 u = d3(jb[0], jb[32], jb[64]);
+            const D3 m = d3(jb[96], jb[128], jb[160]);
+            const D3 g = d3(jb[192], jb[224], jb[256]);
             D3 zj1, zj2, X1j;
             const unsigned jl = (unsigned)(j - v0);
             if (jl < (unsigned)nv) {
@@ -576,6 +642,11 @@ cg_spmv_kernel(int n, const double* __restrict__ P, const double* __restrict__ J
             const double s = dot(u, zi2 - zj2) - dot(m, zi1 - zj1) + 2.0 * dot(g, t);
             const double w2 = 2.0 * W.arap_info * s;
             Am = Am + w2 * m; Ag = Ag + w2 * g; Au = Au + w2 * u;
+            // The slot is free once every lane holds its record in registers: refill it with element q + kSpmvStages.
+            // The copy is issued by the async proxy, which is not ordered after this warp's shared-memory loads by
+            // program order alone, so the issue carries a true data dependency on s (= on all ten loads of the slot).
+            const int dep = __shfl_sync(0xffffffffu, __double2hiint(s), 0);
+            if (lane == 0 && q + kSpmvStages < total) issue(q + kSpmvStages, cons + kSpmvStages, dep);
         }
         if (act) {
             // output rows: [-Am - 2 Ag | Au + 2 Rg^T Ag] + U z + kd n z_s + lambda z
@@ -611,7 +682,7 @@ cg_spmv_kernel(int n, const double* __restrict__ P, const double* __restrict__ J
             acc[3] -= 2.0 * Ag.x; acc[4] -= 2.0 * Ag.y; acc[5] -= 2.0 * Ag.z;
             store6(w, i, d3(out[0], out[1], out[2]), d3(out[3], out[4], out[5]));
         }
-    }
+      }
     }
     block_reduce<9>(acc, sm);
     if (threadIdx.x == 0) {
