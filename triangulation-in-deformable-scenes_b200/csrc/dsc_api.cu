@@ -767,6 +767,7 @@ static int pcg_begin(dsc_ctx* ctx, const WeightsDev& W, double lambda) {
 // kGraphIters PCG iterations (first = 0, parity starting even) captured once per state buffer and replayed:
 // lambda and the tolerance live in CgControl, every other argument is fixed for the uploaded problem.
 constexpr int kGraphIters = 16;
+constexpr int kEarlyWorthIters = 16;     // early-reject pauses are skipped while full solves take no more than this
 static int iteration_graph(dsc_ctx* ctx, const WeightsDev& W, cudaGraphExec_t* out) {
     dsc_ctx::IterGraph* slot = nullptr;
     for (auto& g : ctx->graphs) if (g.exec && g.P == ctx->P && std::memcmp(&g.W, &W, sizeof(WeightsDev)) == 0) { *out = g.exec; return DSC_OK; }
@@ -871,6 +872,7 @@ extern "C" int dsc_optimize(dsc_ctx* ctx, const dsc_weights* w, int n_iters, dsc
     cudaEventRecord(e_begin, ctx->stream);
     double lambda = 0.0, ni = 2.0;
     double current = 0.0;
+    bool expect_long = true;
     int rc = DSC_OK;
     int nbv = grid_threads(ctx, ctx->n);
     CgVecs v = make_vecs(ctx);
@@ -903,7 +905,7 @@ extern "C" int dsc_optimize(dsc_ctx* ctx, const dsc_weights* w, int n_iters, dsc
             for (int level = 0; level <= ctx->early_levels && prc == DSC_OK && !rejected_early; ++level) {
                 const bool last = level == ctx->early_levels;
                 const double tol = last ? ctx->pcg.rtol : ctx->early_rtol[level];
-                if (!last && !(tol > ctx->pcg.rtol)) continue;
+                if (!last && (!(tol > ctx->pcg.rtol) || !expect_long)) continue;
                 cudaEventRecord(e_a, ctx->stream);
                 prc = pcg_resume(ctx, W, lambda, tol, &its);
                 cudaEventRecord(e_b, ctx->stream); cudaEventSynchronize(e_b);
@@ -923,6 +925,9 @@ extern "C" int dsc_optimize(dsc_ctx* ctx, const dsc_weights* w, int n_iters, dsc
             if (prc != DSC_OK && prc != DSC_ERR_PCG_BREAKDOWN) { rc = prc; break; }
             if (prc == DSC_ERR_PCG_BREAKDOWN) { temp = std::numeric_limits<double>::max(); scale = 1e-3; }
             rec.pcg_iters += its; st.total_pcg_iters += its;
+            // A pause costs about one PCG iteration (trial evaluation + a host round trip): worth it only while
+            // solves are long.  Predictor: the previous solve that ran to the tight tolerance.
+            if (!rejected_early && prc == DSC_OK) expect_long = its > kEarlyWorthIters;
             rho = (current - temp) / scale;
             if (rho > 0 && std::isfinite(temp)) {
                 double alpha = 1.0 - std::pow(2.0 * rho - 1.0, 3);
