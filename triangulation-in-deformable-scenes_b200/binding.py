@@ -76,7 +76,7 @@ def load_library(path=None):
     global _lib
     if _lib is not None and path is None:
         return _lib
-    path = path or LIB_PATH
+    path = path or os.environ.get("DSC_B200_LIB") or LIB_PATH      # the override serves kernel experiments
     if not os.path.exists(path):
         raise FileNotFoundError(f"{path} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
                                 f"(the hot path has no CPU fallback)")

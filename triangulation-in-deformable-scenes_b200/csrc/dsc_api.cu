@@ -63,6 +63,8 @@ struct dsc_ctx {
     int *rowptr = nullptr, *col = nullptr;
     double* wgt = nullptr;
     double* Je = nullptr;                 // per directed edge {u, m, g}
+    int* spmv_part = nullptr;                   // [spmv_units + 1] slice ranges = work units of cg_spmv_kernel
+    int spmv_units = 0, spmv_cap = 0;
     int *ecol = nullptr, *sliceptr = nullptr;   // sliced ELL of the gather kernels (see dsc_set_graph)
     double* ewgt = nullptr;                     // ELL edge weights
     long long nblk = 0, blkcap = 0;
@@ -144,8 +146,8 @@ int grid_threads(const dsc_ctx* c, long long n) {           // thread-per-item k
     long long cap = (long long)c->sms * 8;
     return (int)std::max(1LL, std::min(nb, cap));
 }
-int grid_spmv(const dsc_ctx* c, long long n) {              // one block per tile of kSortGroup rows, persistent blocks
-    long long nb = (n + kSortGroup - 1) / kSortGroup;
+int grid_spmv(const dsc_ctx* c, long long n) {              // persistent blocks over work units of >= 4 slices (see dsc_set_graph)
+    long long nb = ((n + 31) / 32 + 3) / 4;
     long long cap = (long long)c->sms * 2;
     return (int)std::max(1LL, std::min(nb, cap));
 }
@@ -265,7 +267,7 @@ extern "C" void dsc_destroy(dsc_ctx* ctx) {
     dev_free(ctx->X1f); dev_free(ctx->X2f); dev_free(ctx->d_perm);
     dev_free(ctx->P); dev_free(ctx->Ptrial); dev_free(ctx->P0); dev_free(ctx->Q);
     dev_free(ctx->uv); dev_free(ctx->dm); dev_free(ctx->isg);
-    dev_free(ctx->rowptr); dev_free(ctx->col); dev_free(ctx->wgt); dev_free(ctx->Je); dev_free(ctx->ecol); dev_free(ctx->ewgt); dev_free(ctx->sliceptr);
+    dev_free(ctx->rowptr); dev_free(ctx->col); dev_free(ctx->wgt); dev_free(ctx->Je); dev_free(ctx->ecol); dev_free(ctx->ewgt); dev_free(ctx->sliceptr); dev_free(ctx->spmv_part);
     dev_free(ctx->b); dev_free(ctx->D); dev_free(ctx->U); dev_free(ctx->Minv);
     for (auto& v : ctx->vec) dev_free(v);
     dev_free(ctx->knn_rowptr); dev_free(ctx->knn_col);
@@ -440,7 +442,7 @@ extern "C" int dsc_problem_upload(dsc_ctx* ctx, const dsc_pair* pair, int n,
         CK(dev_alloc(ctx->P, 8 * N)); CK(dev_alloc(ctx->Ptrial, 8 * N)); CK(dev_alloc(ctx->P0, 8 * N)); CK(dev_alloc(ctx->Q, 4 * N));
         CK(dev_alloc(ctx->uv, N)); CK(dev_alloc(ctx->dm, N)); CK(dev_alloc(ctx->isg, N));
         CK(dev_alloc(ctx->rowptr, N + 1));
-        CK(dev_alloc(ctx->b, 6 * N)); CK(dev_alloc(ctx->D, 21 * N)); CK(dev_alloc(ctx->U, 16 * N)); CK(dev_alloc(ctx->Minv, 21 * N));
+        CK(dev_alloc(ctx->b, 6 * N)); CK(dev_alloc(ctx->D, 21 * N)); CK(dev_alloc(ctx->U, (size_t)kURec * 32 * ((N + 31) / 32))); CK(dev_alloc(ctx->Minv, 21 * N));
         for (auto& v : ctx->vec) CK(dev_alloc(v, 6 * N));
         ctx->cap = n;
     }
@@ -572,19 +574,76 @@ extern "C" int dsc_set_graph(dsc_ctx* ctx, int n, const int32_t* rowptr, const i
         sp[sl + 1] = sp[sl] + wmax;
     }
     size_t nblk = (size_t)sp[nslices];
+    // Work units of the PCG operator (cg_spmv_kernel): full rounds of 16-slice tiles, then the partial last round cut
+    // into one equal-work unit per block; a slice costs its ELL blocks (2432 B each) + its 32 rows (256 B each).
+    int nbs = grid_spmv(ctx, n);
+    std::vector<int> hpart;
+    {
+        const int tsl = kSortGroup / 32;
+        const int ntiles = (nslices + tsl - 1) / tsl;
+        const int full = (ntiles / nbs) * nbs;                 // tiles in complete rounds
+        for (int t = 0; t < full; ++t) hpart.push_back(t * tsl);
+        int sl = std::min(nslices, full * tsl);
+        if (sl < nslices) {
+            const double row_cost = 32.0 * 256.0 / 2432.0;
+            const double total = (double)(sp[nslices] - sp[sl]) + row_cost * (nslices - sl);
+            double acc = 0.0;
+            for (int b = 0; b < nbs; ++b) {                     // a unit may be empty (the kernel skips it)
+                hpart.push_back(sl);
+                const double target = total * (b + 1) / nbs;
+                while (sl < nslices) {
+                    const double c = (sp[sl + 1] - sp[sl]) + row_cost;
+                    if (acc + 0.5 * c > target) break;
+                    acc += c; ++sl;
+                }
+            }
+        }
+        hpart.push_back(nslices);
+    }
+    ctx->spmv_units = (int)hpart.size() - 1;
     CK(pin_reserve(ctx->hs_ecol, ctx->hc_ecol, nblk * 32 + 1)); CK(pin_reserve(ctx->hs_ewgt, ctx->hc_ewgt, nblk * 32 + 1));
     int* ecol = ctx->hs_ecol; double* ewgt = ctx->hs_ewgt;
+    // Slot order inside a row: neighbours inside the row's own tile (the shared-memory window of the gather kernels)
+    // first, halo neighbours last, each part ascending.  Rows of a slice have about the same length, so the halo
+    // gathers (global loads, divergent) concentrate in the last columns of a slice instead of touching every column.
 #pragma omp parallel for schedule(static, 256)
-    for (int sl = 0; sl < nslices; ++sl)
-        for (int k = 0; k < sp[sl + 1] - sp[sl]; ++k)
-            for (int l = 0; l < 32; ++l) {
-                int i = sl * 32 + l;
-                int v = i < n ? i : 0;
-                double wv = 0.0;
-                if (i < n && k < rp[i + 1] - rp[i]) { v = cl[rp[i] + k]; wv = ww[rp[i] + k]; }
-                ecol[((size_t)sp[sl] + k) * 32 + l] = v;
-                ewgt[((size_t)sp[sl] + k) * 32 + l] = wv;
+    for (int sl = 0; sl < nslices; ++sl) {
+        const int width = sp[sl + 1] - sp[sl];
+        for (int l = 0; l < 32; ++l) {
+            const int i = sl * 32 + l;
+            const int deg = i < n ? rp[i + 1] - rp[i] : 0;
+            const int t0 = (i / kSortGroup) * kSortGroup, t1 = t0 + kSortGroup;
+            int k = 0;
+            for (int pass = 0; pass < 2; ++pass)
+                for (int a = 0; a < deg; ++a) {
+                    const int v = cl[rp[i] + a];
+                    const bool inside = v >= t0 && v < t1;
+                    if (inside != (pass == 0)) continue;
+                    ecol[((size_t)sp[sl] + k) * 32 + l] = v;
+                    ewgt[((size_t)sp[sl] + k) * 32 + l] = ww[rp[i] + a];
+                    ++k;
+                }
+            for (; k < width; ++k) {
+                ecol[((size_t)sp[sl] + k) * 32 + l] = i < n ? i : 0;
+                ewgt[((size_t)sp[sl] + k) * 32 + l] = 0.0;
             }
+        }
+    }
+    if (getenv("DSC_TIMING")) {
+        long long halo_lanes = 0, halo_blocks = 0;
+        for (int sl = 0; sl < nslices; ++sl)
+            for (int k = 0; k < sp[sl + 1] - sp[sl]; ++k) {
+                int any = 0;
+                for (int l = 0; l < 32; ++l) {
+                    int i = sl * 32 + l;
+                    int v = ecol[((size_t)sp[sl] + k) * 32 + l];
+                    int t0 = (i / kSortGroup) * kSortGroup;
+                    if (i < n && (v < t0 || v >= t0 + kSortGroup)) { ++halo_lanes; any = 1; }
+                }
+                halo_blocks += any;
+            }
+        fprintf(stderr, "[dsc] ELL: %zu blocks, %lld with a halo lane, %lld halo lanes of %lld edges\n", nblk, halo_blocks, halo_lanes, (long long)E);
+    }
     lap("ell build");
     if (E > ctx->ecap) {
         CK(dev_alloc(ctx->col, (size_t)E)); CK(dev_alloc(ctx->wgt, (size_t)E));
@@ -594,11 +653,13 @@ extern "C" int dsc_set_graph(dsc_ctx* ctx, int n, const int32_t* rowptr, const i
         CK(dev_alloc(ctx->ecol, nblk * 32)); CK(dev_alloc(ctx->ewgt, nblk * 32)); CK(dev_alloc(ctx->Je, nblk * 288));
         ctx->blkcap = (long long)nblk;
     }
+    if ((int)hpart.size() > ctx->spmv_cap) { CK(dev_alloc(ctx->spmv_part, hpart.size())); ctx->spmv_cap = (int)hpart.size(); }
     if (nslices + 1 > ctx->slcap) { CK(dev_alloc(ctx->sliceptr, (size_t)nslices + 1)); ctx->slcap = nslices + 1; }
     ctx->E = E; ctx->nblk = (long long)nblk;
     ctx->area = area; ctx->ntri = n_triangles;
     CK(cudaMemcpyAsync(ctx->rowptr, rp, sizeof(int) * (n + 1), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->sliceptr, sp, sizeof(int) * (nslices + 1), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->spmv_part, hpart.data(), sizeof(int) * hpart.size(), cudaMemcpyHostToDevice, ctx->stream));
     if (E > 0) {
         CK(cudaMemcpyAsync(ctx->col, cl, sizeof(int) * E, cudaMemcpyHostToDevice, ctx->stream));
         CK(cudaMemcpyAsync(ctx->wgt, ww, sizeof(double) * E, cudaMemcpyHostToDevice, ctx->stream));
@@ -757,7 +818,7 @@ static int pcg_begin(dsc_ctx* ctx, const WeightsDev& W, double lambda) {
     ctl_set_kernel<<<1, 1, 0, ctx->stream>>>(ctx->ctl, lambda, 1, 0.0, 0, 0);
     precond_kernel<<<nbv, kThreads, 0, ctx->stream>>>(n, ctx->D, lambda, ctx->lin, ctx->Minv, Ginv, ctx->errflag);
     cg_init_kernel<<<nbv, kThreads, 0, ctx->stream>>>(n, ctx->b, ctx->lin, ctx->Minv, Ginv, v, ctx->gpart[0], ctx->ctl);
-    cg_spmv_kernel<<<nbs, kThreads, kSpmvSmem, ctx->stream>>>(n, ctx->P, ctx->Je, ctx->U, ctx->sliceptr, ctx->ecol, ctx->Gcur, ctx->pair, W,
+    cg_spmv_kernel<<<nbs, kThreads, kSpmvSmem, ctx->stream>>>(n, ctx->P, ctx->Je, ctx->U, ctx->sliceptr, ctx->ecol, ctx->spmv_part, ctx->spmv_units, ctx->Gcur, ctx->pair, W,
                                                      lambda, v.z, v.zg, v.w, ctx->dpart, ctx->bpart, ctx->lin, ctx->ctl);
     ctx->launches += 3;
     CK(cudaGetLastError());
@@ -782,7 +843,7 @@ static int iteration_graph(dsc_ctx* ctx, const WeightsDev& W, cudaGraphExec_t* o
     for (int k = 2; k < 2 + kGraphIters; ++k) {
         cg_update_kernel<<<nbv, kThreads, 0, ctx->stream>>>(n, k & 1, 0, ctx->Minv, Ginv, ctx->lin, 0.0, v, ctx->gpart[k & 1],
                                                            ctx->gpart[(k + 1) & 1], ctx->dpart, ctx->bpart, nbs, ctx->ctl, 0.0);
-        cg_spmv_kernel<<<nbs, kThreads, kSpmvSmem, ctx->stream>>>(n, ctx->P, ctx->Je, ctx->U, ctx->sliceptr, ctx->ecol, ctx->Gcur, ctx->pair, W,
+        cg_spmv_kernel<<<nbs, kThreads, kSpmvSmem, ctx->stream>>>(n, ctx->P, ctx->Je, ctx->U, ctx->sliceptr, ctx->ecol, ctx->spmv_part, ctx->spmv_units, ctx->Gcur, ctx->pair, W,
                                                          0.0, v.z, v.zg, v.w, ctx->dpart, ctx->bpart, ctx->lin, ctx->ctl);
     }
     cudaError_t e = cudaStreamEndCapture(ctx->stream, &graph);
@@ -823,7 +884,7 @@ static int pcg_resume(dsc_ctx* ctx, const WeightsDev& W, double lambda, double r
             cg_update_kernel<<<nbv, kThreads, 0, ctx->stream>>>(n, k & 1, k == 0 ? 1 : 0, ctx->Minv, Ginv, ctx->lin, lambda, v,
                                                                ctx->gpart[k & 1], ctx->gpart[(k + 1) & 1], ctx->dpart, ctx->bpart, nbs,
                                                                ctx->ctl, rtol2);
-            cg_spmv_kernel<<<nbs, kThreads, kSpmvSmem, ctx->stream>>>(n, ctx->P, ctx->Je, ctx->U, ctx->sliceptr, ctx->ecol, ctx->Gcur, ctx->pair, W,
+            cg_spmv_kernel<<<nbs, kThreads, kSpmvSmem, ctx->stream>>>(n, ctx->P, ctx->Je, ctx->U, ctx->sliceptr, ctx->ecol, ctx->spmv_part, ctx->spmv_units, ctx->Gcur, ctx->pair, W,
                                                              lambda, v.z, v.zg, v.w, ctx->dpart, ctx->bpart, ctx->lin, ctx->ctl);
             ctx->launches += 2;
             ++k; ++c;
@@ -1059,7 +1120,7 @@ extern "C" int dsc_debug_matvec(dsc_ctx* ctx, const dsc_weights* w, double lambd
     if (n) CK(cudaMemcpyAsync(v.z, hz.data(), sizeof(double) * 6 * n, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(v.zg, x, sizeof(double) * 8, cudaMemcpyHostToDevice, ctx->stream));
     int nbs = grid_spmv(ctx, n);
-    cg_spmv_kernel<<<nbs, kThreads, kSpmvSmem, ctx->stream>>>(n, ctx->P, ctx->Je, ctx->U, ctx->sliceptr, ctx->ecol, ctx->Gcur, ctx->pair, W,
+    cg_spmv_kernel<<<nbs, kThreads, kSpmvSmem, ctx->stream>>>(n, ctx->P, ctx->Je, ctx->U, ctx->sliceptr, ctx->ecol, ctx->spmv_part, ctx->spmv_units, ctx->Gcur, ctx->pair, W,
                                                      lambda, v.z, v.zg, v.w, ctx->dpart, ctx->bpart, ctx->lin, nullptr);
     ctx->launches++;
     CK(cudaGetLastError());
@@ -1108,10 +1169,10 @@ extern "C" int dsc_profile_kernels(dsc_ctx* ctx, const dsc_weights* w, int warm,
     ctx->launches += 2;
     double N = (double)n, E = (double)ctx->E;
     double by[DSC_K_COUNT];
-    by[DSC_K_SPMV] = 256.0 * N + 76.0 * (double)ctx->nblk * 32.0;   // X1 z U | ELL blocks: col(4) Je(72) per slot (padding included) | write w
+    by[DSC_K_SPMV] = 240.0 * N + 76.0 * (double)ctx->nblk * 32.0;   // X1(32) z(48) U(112) | ELL blocks: col(4) Je(72) per slot (padding included) | write w
     by[DSC_K_UPDATE] = 696.0 * N;                 // read z w p s x r Minv, write p s x r z
     double S = (double)ctx->nblk * 32.0;            // ELL slots (padding included)
-    by[DSC_K_LINEARIZE] = 504.0 * N + 12.0 * S + 72.0 * E;   // P Q uv dm isg | ecol ewgt per slot | write b D U, Je per edge
+    by[DSC_K_LINEARIZE] = 488.0 * N + 12.0 * S + 72.0 * E;   // P Q uv dm isg | ecol ewgt per slot | write b D U, Je per edge
     by[DSC_K_COST] = 136.0 * N + 12.0 * S;         // P Q uv dm isg | ecol ewgt per slot
     by[DSC_K_PRECOND] = 336.0 * N;                // D -> Minv
     by[DSC_K_APPLY] = 224.0 * N;                  // P x b -> Ptrial
@@ -1128,7 +1189,7 @@ extern "C" int dsc_profile_kernels(dsc_ctx* ctx, const dsc_weights* w, int warm,
         return DSC_OK;
     };
     s = time_it(DSC_K_SPMV, [&]() {
-        cg_spmv_kernel<<<nbp, kThreads, kSpmvSmem, ctx->stream>>>(n, ctx->P, ctx->Je, ctx->U, ctx->sliceptr, ctx->ecol, ctx->Gcur, ctx->pair, W,
+        cg_spmv_kernel<<<nbp, kThreads, kSpmvSmem, ctx->stream>>>(n, ctx->P, ctx->Je, ctx->U, ctx->sliceptr, ctx->ecol, ctx->spmv_part, ctx->spmv_units, ctx->Gcur, ctx->pair, W,
                                                          lambda, v.z, v.zg, v.w, ctx->dpart, ctx->bpart, ctx->lin, nullptr);
     });
     if (s) return s;

@@ -527,14 +527,21 @@ DSC_D void mbar_wait(unsigned long long* bar, unsigned parity) {
                  "}" ::"r"(smem_addr(bar)), "r"(parity) : "memory");
 }
 
-constexpr int kSpmvStages = 3;                                   // ring depth per warp (ELL blocks in flight)
+#ifndef DSC_EXP
+#define DSC_EXP 0
+#endif
+#ifndef DSC_STAGES
+#define DSC_STAGES 3
+#endif
+constexpr int kSpmvStages = DSC_STAGES;                                   // ring depth per warp (ELL blocks in flight)
+constexpr int kURec = 14;                                        // unary record {U1[6], U2[6], kd1, kd2}, stored [slice][kURec][32]
 constexpr int kSpmvStageBytes = 9 * 32 * 8 + 32 * 4;             // one ELL block: Je[9][32] doubles + ecol[32] ints
 constexpr int kSpmvWinBytes = kSortGroup * (48 + 32);            // z (6 doubles) and X1 (double4) of the tile
 constexpr int kSpmvSmem = kSpmvWinBytes + (kThreads / 32) * kSpmvStages * kSpmvStageBytes;
 
 __global__ void __launch_bounds__(kThreads, 2)
 cg_spmv_kernel(int n, const double* __restrict__ P, const double* __restrict__ Je, const double* __restrict__ U,
-               const int* __restrict__ sliceptr, const int* __restrict__ ecol,
+               const int* __restrict__ sliceptr, const int* __restrict__ ecol, const int* __restrict__ part, int nunits,
                const Globals* __restrict__ Gp, const __grid_constant__ PairDev pr, const __grid_constant__ WeightsDev W,
                double lambda, const double* __restrict__ z, const double* __restrict__ zg, double* __restrict__ w,
                double* __restrict__ dpart, double* __restrict__ bpart,
@@ -564,22 +571,27 @@ cg_spmv_kernel(int n, const double* __restrict__ P, const double* __restrict__ J
     double acc[9];                                     // T_g border (6), s1, s2 border, z.w
 #pragma unroll
     for (int k = 0; k < 9; ++k) acc[k] = 0.0;
-    // A block owns a tile = one degree-sorted group of kSortGroup rows; the tile's z and X1 are staged in shared
-    // memory (two bulk copies) and a neighbour inside the tile is read from there; halo neighbours come from L2.
-    // Warp w walks slices w and 15 - w of the tile (balanced: the slices are degree-sorted); their ELL blocks form
-    // one stream of kSpmvStageBytes records that lane 0 keeps kSpmvStages deep in flight.
-    const int ntiles = (n + kSortGroup - 1) / kSortGroup;
+    // Work units: slice ranges part[u] .. part[u+1], taken round-robin (unit u by block u mod grid, so that at any
+    // time the blocks work on neighbouring rows: halo gathers hit L2 and the DRAM streams stay close).  Full rounds
+    // are tiles of kSortGroup rows = 16 slices; the host cuts the last, partial round into one equal-work unit per
+    // block, so there is no tail round with idle SMs.  The tile's z and X1 are staged in shared memory (two bulk
+    // copies) and a neighbour inside the tile is read from there; halo neighbours come from L2.  Warp w walks
+    // slices w and 15 - w of the tile (balanced: the slices are degree-sorted inside groups of kSortGroup rows);
+    // their ELL blocks form one stream of kSpmvStageBytes records that lane 0 keeps kSpmvStages deep in flight.
     unsigned cons = 0;                                 // ring slots consumed so far by this warp (stage, phase)
     unsigned wphase = 0;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int v0 = tile * kSortGroup;
-        const int nv = min(kSortGroup, n - v0);
+    for (int unit = blockIdx.x; unit < nunits; unit += gridDim.x) {
+    const int s_begin = __ldg(part + unit), s_end = __ldg(part + unit + 1);
+    for (int ts = s_begin; ts < s_end; ts += kSortGroup / 32) {
+        const int nsl = min(kSortGroup / 32, s_end - ts);
+        const int v0 = ts * 32;
+        const int nv = min(nsl * 32, n - v0);
         const int lsv[2] = {warp, 2 * wpb - 1 - warp};
         int rb[2], rl[2];
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-            const bool ok = lsv[h] * 32 < nv;
-            const int sl = (v0 >> 5) + lsv[h];
+            const bool ok = lsv[h] < nsl;
+            const int sl = ts + lsv[h];
             rb[h] = ok ? __ldg(sliceptr + sl) : 0;
             rl[h] = ok ? __ldg(sliceptr + sl + 1) - rb[h] : 0;
         }
@@ -626,7 +638,15 @@ cg_spmv_kernel(int n, const double* __restrict__ P, const double* __restrict__ J
             const D3 m = d3(jb[96], jb[128], jb[160]);
             const D3 g = d3(jb[192], jb[224], jb[256]);
             D3 zj1, zj2, X1j;
+#if DSC_EXP == 1
+            const unsigned jl = (unsigned)ilc;
+#elif DSC_EXP == 3
+            const unsigned jl = (unsigned)(j - v0) < (unsigned)nv ? (unsigned)(j - v0) : (unsigned)ilc;
+#elif DSC_EXP == 4
+            const unsigned jl = (unsigned)(j - v0) < (unsigned)nv ? (unsigned)ilc : (unsigned)(j - v0);
+#else
             const unsigned jl = (unsigned)(j - v0);
+#endif
             if (jl < (unsigned)nv) {
                 const double2 c0 = sz[3 * jl], c1 = sz[3 * jl + 1], c2 = sz[3 * jl + 2];
                 zj1 = d3(c0.x, c0.y, c1.x); zj2 = d3(c1.y, c2.x, c2.y);
@@ -648,12 +668,12 @@ cg_spmv_kernel(int n, const double* __restrict__ P, const double* __restrict__ J
             const int dep = __shfl_sync(0xffffffffu, __double2hiint(s), 0);
             if (lane == 0 && q + kSpmvStages < total) issue(q + kSpmvStages, cons + kSpmvStages, dep);
         }
-        if (act) {
+        if (act && (DSC_EXP != 2 || Am.x == 1.2345)) {
             // output rows: [-Am - 2 Ag | Au + 2 Rg^T Ag] + U z + kd n z_s + lambda z
-            const double2* Up = reinterpret_cast<const double2*>(U + 16 * (size_t)i);
-            double uu[14];
+            const double* Up = U + ((size_t)(i >> 5) * kURec) * 32 + lane;
+            double uu[kURec];
 #pragma unroll
-            for (int k = 0; k < 7; ++k) { const double2 t2 = __ldg(Up + k); uu[2 * k] = t2.x; uu[2 * k + 1] = t2.y; }
+            for (int k = 0; k < kURec; ++k) uu[k] = __ldg(Up + k * 32);
             const D3 rg = mulT(Rg, Ag);
             double out[6] = {-Am.x - 2.0 * Ag.x, -Am.y - 2.0 * Ag.y, -Am.z - 2.0 * Ag.z,
                              Au.x + 2.0 * rg.x, Au.y + 2.0 * rg.y, Au.z + 2.0 * rg.z};
@@ -683,6 +703,7 @@ cg_spmv_kernel(int n, const double* __restrict__ P, const double* __restrict__ J
             store6(w, i, d3(out[0], out[1], out[2]), d3(out[3], out[4], out[5]));
         }
       }
+    }
     }
     block_reduce<9>(acc, sm);
     if (threadIdx.x == 0) {

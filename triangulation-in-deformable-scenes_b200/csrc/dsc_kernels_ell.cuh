@@ -298,9 +298,9 @@ linearize_ell_kernel(int n, const double* __restrict__ P, const double* __restri
                 double* Dp = D + 21 * (size_t)i;
 #pragma unroll
                 for (int k = 0; k < 21; ++k) Dp[k] = Dk[k];
-                double2* Up = reinterpret_cast<double2*>(U + 16 * (size_t)i);
+                double* Up = U + ((size_t)(i >> 5) * kURec) * 32 + (i & 31);     // slice-major: component k of 32 rows is one 256 B line pair
 #pragma unroll
-                for (int k = 0; k < 8; ++k) Up[k] = make_double2(Urec[2 * k], Urec[2 * k + 1]);
+                for (int k = 0; k < kURec; ++k) Up[k * 32] = Urec[k];
 #pragma unroll
                 for (int r = 0; r < 6; ++r) mx = fmax(mx, fabs(Dk[pk<6>(r, r)]));
                 glob[2] = chi_a;
