@@ -442,7 +442,7 @@ extern "C" int dsc_problem_upload(dsc_ctx* ctx, const dsc_pair* pair, int n,
         CK(dev_alloc(ctx->P, 8 * N)); CK(dev_alloc(ctx->Ptrial, 8 * N)); CK(dev_alloc(ctx->P0, 8 * N)); CK(dev_alloc(ctx->Q, 4 * N));
         CK(dev_alloc(ctx->uv, N)); CK(dev_alloc(ctx->dm, N)); CK(dev_alloc(ctx->isg, N));
         CK(dev_alloc(ctx->rowptr, N + 1));
-        CK(dev_alloc(ctx->b, 6 * N)); CK(dev_alloc(ctx->D, 21 * N)); CK(dev_alloc(ctx->U, (size_t)kURec * 32 * ((N + 31) / 32))); CK(dev_alloc(ctx->Minv, 21 * N));
+        CK(dev_alloc(ctx->b, 6 * N)); CK(dev_alloc(ctx->D, 21 * 32 * ((N + 31) / 32))); CK(dev_alloc(ctx->U, (size_t)kURec * 32 * ((N + 31) / 32))); CK(dev_alloc(ctx->Minv, 21 * 32 * ((N + 31) / 32)));
         for (auto& v : ctx->vec) CK(dev_alloc(v, 6 * N));
         ctx->cap = n;
     }
@@ -1083,10 +1083,10 @@ extern "C" int dsc_debug_linearize(dsc_ctx* ctx, const dsc_weights* w, double* b
     LinGlobal hl;
     s = run_linearize(ctx, W, &hl);
     if (s) return s;
-    std::vector<double> hb(6 * (size_t)n), hD(21 * (size_t)n);
+    std::vector<double> hb(6 * (size_t)n), hD(21 * 32 * (((size_t)n + 31) / 32));
     if (n) {
         CK(cudaMemcpyAsync(hb.data(), ctx->b, sizeof(double) * 6 * n, cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaMemcpyAsync(hD.data(), ctx->D, sizeof(double) * 21 * n, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(hD.data(), ctx->D, sizeof(double) * hD.size(), cudaMemcpyDeviceToHost, ctx->stream));
     }
     CK(cudaStreamSynchronize(ctx->stream));
     if (chi2) *chi2 = hl.chi2[0] + hl.chi2[1] + hl.chi2[2];
@@ -1095,7 +1095,7 @@ extern "C" int dsc_debug_linearize(dsc_ctx* ctx, const dsc_weights* w, double* b
         size_t d = ctx->perm.empty() ? (size_t)i : (size_t)ctx->perm[i];
         for (int k = 0; k < 6; ++k) {
             if (b) b[8 + 6 * d + k] = hb[6 * (size_t)i + k];
-            if (hdiag) hdiag[8 + 6 * d + k] = hD[21 * (size_t)i + pk<6>(k, k)];
+            if (hdiag) hdiag[8 + 6 * d + k] = hD[((size_t)(i >> 5) * 21 + pk<6>(k, k)) * 32 + (i & 31)];
         }
     }
     return DSC_OK;

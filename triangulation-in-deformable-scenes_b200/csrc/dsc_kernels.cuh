@@ -12,7 +12,7 @@
 //   Je     double[nblk][9][32] sliced ELL of the ARAP Jacobian records {u, m, g}: block b = column k of a 32-row
 //                        slice (b = sliceptr[slice] + k), lane = row inside the slice; ecol int[nblk][32] the neighbour
 //   D      double[n][21] packed upper 6x6 diagonal block of H (block-Jacobi preconditioner source)
-//   Minv   double[n][21] packed inverse of D + lambda I
+//   Minv   double[n/32][21][32] packed inverse of D + lambda I (slice-major)
 //   vectors b, x, r, z, w, p, s: double[n][6] {d/dX1, d/dX2}; the 8 global unknowns
 //   (T_g omega/upsilon, s1, s2) live in separate 8-vectors.
 //
@@ -392,18 +392,23 @@ finalize_linearize_kernel(int nb, const double* __restrict__ part, LinGlobal* __
     }
 }
 
+// Packed 6x6 blocks (D, Minv) are stored slice-major, [slice of 32 rows][21][32]: entry k of row i sits at
+// blk21(base, i)[k * 32], so a warp reads entry k of its 32 rows as one 256-byte run.
+template <typename T>
+DSC_D T* blk21(T* base, int i) { return base + ((size_t)(i >> 5) * 21) * 32 + (i & 31); }
+
 // block-Jacobi preconditioner: Minv_i = (D_i + lambda I)^-1 (packed), Ginv = (C + lambda I)^-1
 __global__ void __launch_bounds__(kThreads)
 precond_kernel(int n, const double* __restrict__ D, double lambda, const LinGlobal* __restrict__ lin,
                double* __restrict__ Minv, double* __restrict__ Ginv, int* __restrict__ err) {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const double* Dp = D + 21 * (size_t)i;
+        const double* Dp = blk21(D, i);
         double A[36], Ai[36];
 #pragma unroll
         for (int r = 0; r < 6; ++r)
 #pragma unroll
             for (int c = r; c < 6; ++c) {
-                double v = Dp[pk<6>(r, c)] + (r == c ? lambda : 0.0);
+                double v = Dp[pk<6>(r, c) * 32] + (r == c ? lambda : 0.0);
                 A[r * 6 + c] = v; A[c * 6 + r] = v;
             }
         if (!spd_inverse<6>(A, Ai)) {
@@ -413,11 +418,11 @@ precond_kernel(int n, const double* __restrict__ D, double lambda, const LinGlob
 #pragma unroll
             for (int r = 0; r < 6; ++r) Ai[r * 6 + r] = 1.0 / fmax(fabs(A[r * 6 + r]), 1e-300);
         }
-        double* Mp = Minv + 21 * (size_t)i;
+        double* Mp = blk21(Minv, i);
 #pragma unroll
         for (int r = 0; r < 6; ++r)
 #pragma unroll
-            for (int c = r; c < 6; ++c) Mp[pk<6>(r, c)] = Ai[r * 6 + c];
+            for (int c = r; c < 6; ++c) Mp[pk<6>(r, c) * 32] = Ai[r * 6 + c];
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         double A[64], Ai[64];
@@ -435,7 +440,7 @@ precond_kernel(int n, const double* __restrict__ D, double lambda, const LinGlob
 DSC_D void apply_minv(const double* __restrict__ Mp, const double* r, double* z) {
     double M[21];
 #pragma unroll
-    for (int k = 0; k < 21; ++k) M[k] = Mp[k];
+    for (int k = 0; k < 21; ++k) M[k] = Mp[k * 32];
 #pragma unroll
     for (int a = 0; a < 6; ++a) {
         double s = 0.0;
@@ -465,7 +470,7 @@ cg_init_kernel(int n, const double* __restrict__ b, const LinGlobal* __restrict_
         D3 a, c;
         load6(b, i, a, c);
         r[0] = a.x; r[1] = a.y; r[2] = a.z; r[3] = c.x; r[4] = c.y; r[5] = c.z;
-        apply_minv(Minv + 21 * (size_t)i, r, z);
+        apply_minv(blk21(Minv, i), r, z);
         store6(v.r, i, a, c);
         store6(v.z, i, d3(z[0], z[1], z[2]), d3(z[3], z[4], z[5]));
         D3 zero = d3(0, 0, 0);
@@ -527,9 +532,6 @@ DSC_D void mbar_wait(unsigned long long* bar, unsigned parity) {
                  "}" ::"r"(smem_addr(bar)), "r"(parity) : "memory");
 }
 
-#ifndef DSC_EXP
-#define DSC_EXP 0
-#endif
 #ifndef DSC_STAGES
 #define DSC_STAGES 3
 #endif
@@ -597,7 +599,7 @@ cg_spmv_kernel(int n, const double* __restrict__ P, const double* __restrict__ J
         }
         const int total = rl[0] + rl[1];
         auto issue = [&](int q, unsigned slot, int dep) {   // lane 0: fetch stream element q into ring slot
-            if (dep == 0x7ff4d5c1) q = 0;              // never taken for a finite s; keeps the dependency alive
+            if (dep == 0x7ff4d5c1) q = 0;              // (practically) never taken; keeps the dependency alive
             const int bk = q < rl[0] ? rb[0] + q : rb[1] + (q - rl[0]);
             unsigned char* dst = ring + (slot % kSpmvStages) * kSpmvStageBytes;
             unsigned long long* bar = rbar + (slot % kSpmvStages);
@@ -618,7 +620,7 @@ cg_spmv_kernel(int n, const double* __restrict__ P, const double* __restrict__ J
         int q = 0;
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
-        if (rl[h] == 0) continue;
+        if (lsv[h] >= nsl) continue;                   // (a slice without edges still owns its rows)
         const int il = lsv[h] * 32 + lane;
         const int i = v0 + il;
         const bool act = il < nv;
@@ -638,15 +640,7 @@ cg_spmv_kernel(int n, const double* __restrict__ P, const double* __restrict__ J
             const D3 m = d3(jb[96], jb[128], jb[160]);
             const D3 g = d3(jb[192], jb[224], jb[256]);
             D3 zj1, zj2, X1j;
-#if DSC_EXP == 1
-            const unsigned jl = (unsigned)ilc;
-#elif DSC_EXP == 3
-            const unsigned jl = (unsigned)(j - v0) < (unsigned)nv ? (unsigned)(j - v0) : (unsigned)ilc;
-#elif DSC_EXP == 4
-            const unsigned jl = (unsigned)(j - v0) < (unsigned)nv ? (unsigned)ilc : (unsigned)(j - v0);
-#else
             const unsigned jl = (unsigned)(j - v0);
-#endif
             if (jl < (unsigned)nv) {
                 const double2 c0 = sz[3 * jl], c1 = sz[3 * jl + 1], c2 = sz[3 * jl + 2];
                 zj1 = d3(c0.x, c0.y, c1.x); zj2 = d3(c1.y, c2.x, c2.y);
@@ -665,10 +659,11 @@ cg_spmv_kernel(int n, const double* __restrict__ P, const double* __restrict__ J
             // The slot is free once every lane holds its record in registers: refill it with element q + kSpmvStages.
             // The copy is issued by the async proxy, which is not ordered after this warp's shared-memory loads by
             // program order alone, so the issue carries a true data dependency on s (= on all ten loads of the slot).
+            // (Issuing it earlier, right after the loads, serialises them with the gathers and is 15 % slower.)
             const int dep = __shfl_sync(0xffffffffu, __double2hiint(s), 0);
             if (lane == 0 && q + kSpmvStages < total) issue(q + kSpmvStages, cons + kSpmvStages, dep);
         }
-        if (act && (DSC_EXP != 2 || Am.x == 1.2345)) {
+        if (act) {
             // output rows: [-Am - 2 Ag | Au + 2 Rg^T Ag] + U z + kd n z_s + lambda z
             const double* Up = U + ((size_t)(i >> 5) * kURec) * 32 + lane;
             double uu[kURec];
@@ -753,7 +748,7 @@ cg_update_kernel(int n, int par, int first, const double* __restrict__ Minv, con
         x1 = x1 + alpha * p1; x2 = x2 + alpha * p2;
         r1 = r1 - alpha * s1; r2 = r2 - alpha * s2;
         double r[6] = {r1.x, r1.y, r1.z, r2.x, r2.y, r2.z}, zn[6];
-        apply_minv(Minv + 21 * (size_t)i, r, zn);
+        apply_minv(blk21(Minv, i), r, zn);
         store6(v.p, i, p1, p2); store6(v.s, i, s1, s2); store6(v.x, i, x1, x2); store6(v.r, i, r1, r2);
         store6(v.z, i, d3(zn[0], zn[1], zn[2]), d3(zn[3], zn[4], zn[5]));
 #pragma unroll

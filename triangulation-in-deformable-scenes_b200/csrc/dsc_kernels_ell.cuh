@@ -295,9 +295,9 @@ linearize_ell_kernel(int n, const double* __restrict__ P, const double* __restri
                         for (int c = r; c < 3; ++c) Dk[pk<6>(cam * 3 + r, cam * 3 + c)] += Uu[pk<3>(r, c)];
                 }
                 store6(b, i, d3(gb[0], gb[1], gb[2]), d3(gb[3], gb[4], gb[5]));
-                double* Dp = D + 21 * (size_t)i;
+                double* Dp = blk21(D, i);
 #pragma unroll
-                for (int k = 0; k < 21; ++k) Dp[k] = Dk[k];
+                for (int k = 0; k < 21; ++k) Dp[k * 32] = Dk[k];
                 double* Up = U + ((size_t)(i >> 5) * kURec) * 32 + (i & 31);     // slice-major: component k of 32 rows is one 256 B line pair
 #pragma unroll
                 for (int k = 0; k < kURec; ++k) Up[k * 32] = Urec[k];
