@@ -792,7 +792,7 @@ static CgVecs make_vecs(dsc_ctx* ctx) {
 
 static int run_linearize(dsc_ctx* ctx, const WeightsDev& W, LinGlobal* hlin) {
     int nb = grid_tiles(ctx, ctx->n, 1);
-    linearize_ell_kernel<<<nb, kEllThreads, kWinBytes, ctx->stream>>>(ctx->n, ctx->P, ctx->Q, ctx->uv, ctx->dm, ctx->isg, ctx->sliceptr, ctx->ecol,
+    linearize_ell_kernel<<<nb, kLinThreads, kWinBytes, ctx->stream>>>(ctx->n, ctx->P, ctx->Q, ctx->uv, ctx->dm, ctx->isg, ctx->sliceptr, ctx->ecol,
                                                                     ctx->ewgt, ctx->Gcur, ctx->pair, W, ctx->b, ctx->D, ctx->U, ctx->Je, ctx->part);
     finalize_linearize_kernel<<<1, kThreads, 0, ctx->stream>>>(nb, ctx->part, ctx->lin);
     ctx->launches += 2;
@@ -1202,7 +1202,7 @@ extern "C" int dsc_profile_kernels(dsc_ctx* ctx, const dsc_weights* w, int warm,
     });
     if (s) return s;
     s = time_it(DSC_K_LINEARIZE, [&]() {
-        linearize_ell_kernel<<<grid_tiles(ctx, n, 1), kEllThreads, kWinBytes, ctx->stream>>>(n, ctx->P, ctx->Q, ctx->uv, ctx->dm, ctx->isg, ctx->sliceptr,
+        linearize_ell_kernel<<<grid_tiles(ctx, n, 1), kLinThreads, kWinBytes, ctx->stream>>>(n, ctx->P, ctx->Q, ctx->uv, ctx->dm, ctx->isg, ctx->sliceptr,
                                                                                        ctx->ecol, ctx->ewgt, ctx->Gcur, ctx->pair, W, ctx->b, ctx->D,
                                                                                        ctx->U, ctx->Je, ctx->part);
     });

@@ -10,6 +10,10 @@ namespace dsc {
 
 constexpr size_t kWinBytes = sizeof(double4) * 3 * kSortGroup;      // X1 | X2 | Q windows
 constexpr int kEllThreads = 256;
+#ifndef DSC_LIN_THREADS
+#define DSC_LIN_THREADS 256
+#endif
+constexpr int kLinThreads = DSC_LIN_THREADS;
 
 struct Window { const double4* x1; const double4* x2; const double4* q; int v0, nv; };
 
@@ -37,6 +41,20 @@ DSC_D void fetch_quat(const Window& w, const double* __restrict__ Q, int j, doub
     const double4 u = jl < (unsigned)w.nv ? w.q[jl] : ldg256(reinterpret_cast<const double4*>(Q) + (size_t)j);
     qj[0] = u.x; qj[1] = u.y; qj[2] = u.z; qj[3] = u.w;
 }
+// Column index and weight of a row's ELL slots, fetched one column ahead of their use so that the load latency
+// overlaps the previous edge's arithmetic.
+struct SlotStream {
+    const int* ecol; const double* ewgt; int b1, lane, jn; double wn;
+    DSC_D SlotStream(const int* __restrict__ ec, const double* __restrict__ ew, int b0, int b1_, int lane_)
+        : ecol(ec), ewgt(ew), b1(b1_), lane(lane_), jn(0), wn(0.0) {
+        if (b0 < b1) { jn = __ldg(ecol + (size_t)b0 * 32 + lane); wn = __ldg(ewgt + (size_t)b0 * 32 + lane); }
+    }
+    DSC_D void next(int bk, int& j, double& w) {
+        j = jn; w = wn;
+        if (bk + 1 < b1) { jn = __ldg(ecol + (size_t)(bk + 1) * 32 + lane); wn = __ldg(ewgt + (size_t)(bk + 1) * 32 + lane); }
+    }
+};
+
 // warp sum of K per-lane values into a per-warp shared accumulator row (lane 0 adds)
 template <int K>
 DSC_D void warp_accumulate(const double (&v)[K], double* wacc) {
@@ -70,10 +88,11 @@ rotations_ell_kernel(int n, const double* __restrict__ P, const int* __restrict_
 #pragma unroll
             for (int k = 0; k < 9; ++k) S[k] = 0.0;
             int deg = 0;
+            SlotStream slots(ecol, ewgt, b0, b1, lane);
             for (int bk = b0; bk < b1; ++bk) {
-                const int j = __ldg(ecol + (size_t)bk * 32 + lane);
+                int j; double wv;
+                slots.next(bk, j, wv);
                 if (j == i) continue;
-                const double wv = __ldg(ewgt + (size_t)bk * 32 + lane);
                 P8 Pj;
                 fetch_point(win, P, n, j, Pj);
                 const D3 d1 = Pi.a - Pj.a, d2 = Pi.b - Pj.b;
@@ -133,10 +152,11 @@ cost_ell_kernel(int n, const double* __restrict__ P, const double* __restrict__ 
             const int sl = (v0 >> 5) + ls;
             const int b0 = __ldg(sliceptr + sl), b1 = __ldg(sliceptr + sl + 1);
             double ea = 0.0;
+            SlotStream slots(ecol, ewgt, b0, b1, lane);
             for (int bk = b0; bk < b1; ++bk) {
-                const int j = __ldg(ecol + (size_t)bk * 32 + lane);
+                int j; double wv;
+                slots.next(bk, j, wv);
                 if (j == i) continue;
-                const double wv = __ldg(ewgt + (size_t)bk * 32 + lane);
                 P8 Pj;
                 double qj[4];
                 fetch_point(win, P, n, j, Pj);
@@ -166,7 +186,7 @@ cost_ell_kernel(int n, const double* __restrict__ P, const double* __restrict__ 
 // ELL slots (coalesced).  Global rows: T_g gradient from the per-row sum Bg_i = sum_j 2 W e_ij g_ij (the directed
 // twins carry the same e and g):  b_w = -2 sum_i X1_i x Bg_i,  b_v = 2 sum_i Bg_i;  C_TT = sum_dir W gT gT^T.
 // part[grid][kLinPart]: chi2[3], max diag, bg[8], C_TT packed (21), C_ss (2)  -- reduced by finalize_linearize_kernel.
-__global__ void __launch_bounds__(kEllThreads, 1)
+__global__ void __launch_bounds__(kLinThreads, 1)
 linearize_ell_kernel(int n, const double* __restrict__ P, const double* __restrict__ Q, const float4* __restrict__ uv,
                      const double2* __restrict__ dm, const float2* __restrict__ isg, const int* __restrict__ sliceptr,
                      const int* __restrict__ ecol, const double* __restrict__ ewgt, const Globals* __restrict__ Gp,
@@ -174,8 +194,8 @@ linearize_ell_kernel(int n, const double* __restrict__ P, const double* __restri
                      double* __restrict__ b, double* __restrict__ D, double* __restrict__ U, double* __restrict__ Je,
                      double* __restrict__ part) {
     extern __shared__ double4 sw[];
-    __shared__ double wacc[kEllThreads / 32][kLinPart];
-    __shared__ double wmax[kEllThreads / 32];
+    __shared__ double wacc[kLinThreads / 32][kLinPart];
+    __shared__ double wmax[kLinThreads / 32];
     __shared__ Globals G;
     if (threadIdx.x == 0) G = *Gp;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
@@ -201,10 +221,11 @@ linearize_ell_kernel(int n, const double* __restrict__ P, const double* __restri
             for (int k = 0; k < 6; ++k) gb[k] = 0.0;
 #pragma unroll
             for (int k = 0; k < 21; ++k) { Dk[k] = 0.0; cT[k] = 0.0; }
+            SlotStream slots(ecol, ewgt, b0, b1, lane);
             for (int bk = b0; bk < b1; ++bk) {
-                const int j = __ldg(ecol + (size_t)bk * 32 + lane);
+                int j; double wv;
+                slots.next(bk, j, wv);
                 if (!act || j == i) continue;                  // padding slot: its Je record stays all-zero
-                const double wv = __ldg(ewgt + (size_t)bk * 32 + lane);
                 P8 Pj;
                 double qj[4];
                 fetch_point(win, P, n, j, Pj);
