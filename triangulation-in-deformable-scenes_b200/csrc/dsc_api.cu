@@ -934,6 +934,7 @@ extern "C" int dsc_optimize(dsc_ctx* ctx, const dsc_weights* w, int n_iters, dsc
     double lambda = 0.0, ni = 2.0;
     double current = 0.0;
     bool expect_long = true;
+    const bool early_log = std::getenv("DSC_EARLY_LOG") != nullptr;     // study aid: rho at every pause, predictor off
     int rc = DSC_OK;
     int nbv = grid_threads(ctx, ctx->n);
     CgVecs v = make_vecs(ctx);
@@ -966,7 +967,7 @@ extern "C" int dsc_optimize(dsc_ctx* ctx, const dsc_weights* w, int n_iters, dsc
             for (int level = 0; level <= ctx->early_levels && prc == DSC_OK && !rejected_early; ++level) {
                 const bool last = level == ctx->early_levels;
                 const double tol = last ? ctx->pcg.rtol : ctx->early_rtol[level];
-                if (!last && (!(tol > ctx->pcg.rtol) || !expect_long)) continue;
+                if (!last && (!(tol > ctx->pcg.rtol) || (!expect_long && !early_log))) continue;
                 cudaEventRecord(e_a, ctx->stream);
                 prc = pcg_resume(ctx, W, lambda, tol, &its);
                 cudaEventRecord(e_b, ctx->stream); cudaEventSynchronize(e_b);
@@ -977,6 +978,7 @@ extern "C" int dsc_optimize(dsc_ctx* ctx, const dsc_weights* w, int n_iters, dsc
                 if (rc) break;
                 cudaEventRecord(e_b, ctx->stream); cudaEventSynchronize(e_b);
                 st.trial_ms += ev_ms(e_a, e_b);
+                if (early_log) fprintf(stderr, "[dsc early] it %d trial %d level %d tol %.1e its %d rho %.6e\n", it, q, last ? -1 : level, tol, its, (current - temp) / scale);
                 if (!last && std::isfinite(temp) && (current - temp) / scale < -ctx->early_margin[level]) {
                     rejected_early = true;
                     st.early_rejects++;
