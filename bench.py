@@ -40,7 +40,8 @@ def parse():
     ap.add_argument("--pcg-max-iters", type=int, default=6000)
     ap.add_argument("--early-rtol", type=float, nargs="*", default=[1e-3, 1e-4], help="loose tolerances of the early-reject check (none = off)")
     ap.add_argument("--early-margin", type=float, nargs="*", default=[1.0, 0.5])
-    ap.add_argument("--cpu-sample-n", type=int, default=20000)
+    ap.add_argument("--cpu-sample-n", type=int, default=50000)
+    ap.add_argument("--cpu-impl", choices=["c", "numpy"], default="c", help="CPU legs: compiled C oracle (all cores) or the numpy port")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -162,7 +163,8 @@ def cpu_reference_run(args, steps, warmup):
     """The reference's CPU algorithm (oracle port; the reference itself needs g2o/Eigen/Qhull/Open3D and
     cannot be compiled here) on a bounded sample of the same workload."""
     from oracle import bench_cpu
-    return bench_cpu.run(args.workload, args.cpu_sample_n, args.k, steps, warmup, args.n)
+    return bench_cpu.run(args.workload, args.cpu_sample_n, args.k, steps, warmup, args.n, impl=args.cpu_impl,
+                         pcg_rtol=args.pcg_rtol)
 
 
 # ---------------------------------------------------------------------------------------------- main

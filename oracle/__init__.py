@@ -20,4 +20,9 @@ checked (tests/test_oracle_pins.py): the Hessian structure rule of
 /root/reference/debug.txt, the "pixel sigma ~= 1.0" statistic of the synthetic
 database, closed-form triangulation cases, analytic-vs-central-difference
 Jacobians, monotone cost under accepted steps.
+
+Two independently written restatements live here and are checked against each other
+(tests/test_c_oracle.py): the numpy modules of this package and the plain-C, OpenMP
+oracle/c/dsc_oracle.c (front end: oracle/cport.py; built into oracle/_build/ by
+oracle/c/Makefile), which also serves as the compiled multi-threaded CPU baseline.
 """

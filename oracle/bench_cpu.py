@@ -1,9 +1,12 @@
 """CPU baseline leg of bench.py (oracle = test infrastructure; this is the one place bench.py may
-execute it).  Times the oracle's restatement of arapOptimization -- analytic Jacobians, assembled
-sparse normal equations, direct sparse solve with the 8 global unknowns eliminated (the stand-in for
-g2o's LinearSolverEigen) -- on a bounded sample of the bench workload and extrapolates linearly in
-the number of correspondences to the bench size (optimistic for the CPU: sparse factorisation is
-super-linear).  kind = "port": the reference itself cannot be compiled in this image.
+execute it).  Times the oracle's restatement of arapOptimization on a bounded sample of the bench workload and
+extrapolates linearly in the number of correspondences to the bench size (optimistic for the CPU: both the sparse
+factorisation and the PCG iteration count grow faster than linearly).  Two implementations:
+  impl="c"     oracle/c/dsc_oracle.c: compiled C, OpenMP over all host cores, analytic Jacobians, matrix-free
+               block-Jacobi PCG to the same tolerance as the CUDA path (default);
+  impl="numpy" the numpy port: assembled sparse normal equations + SuperLU direct solve with the 8 global unknowns
+               eliminated (the stand-in for g2o's LinearSolverEigen), one thread.
+kind = "port" for both: the reference itself cannot be compiled in this image.
 """
 import os
 import time
@@ -35,7 +38,7 @@ def build_from_arrays(sc, n_sample, k):
     return p
 
 
-def run(workload, n_sample, k, steps, warmup, n_full, lm_iters=2, sc=None):
+def run(workload, n_sample, k, steps, warmup, n_full, lm_iters=2, sc=None, impl="c", pcg_rtol=1e-10):
     import importlib.util
     import sys
     if sc is None:
@@ -55,21 +58,39 @@ def run(workload, n_sample, k, steps, warmup, n_full, lm_iters=2, sc=None):
         name = sc.get("name", workload)
     p = build_from_arrays(sc, n_sample, k)
     w = edges.Weights(**sc["weights"])
+    cores = os.cpu_count() or 1
+    if impl == "c":
+        from . import cport
+        cport.build()
+        used = cport.threads()
+
+        def one(iters):
+            cp = cport.CProblem(p)
+            t = time.perf_counter()
+            cport.compute_rotations(cp)                      # computeR is part of arapOptimization
+            tr = cport.optimize(cp, w, iters, threads=0, pcg_rtol=pcg_rtol)
+            return len(tr["chi2"]), time.perf_counter() - t, sum(tr["pcg_iters"])
+        how = (f"C oracle (oracle/c/dsc_oracle.c: analytic Jacobians, matrix-free block-Jacobi PCG to rtol {pcg_rtol:g}, "
+               f"OpenMP), {used} threads of {cores} host cores (the reference is single-threaded)")
+    else:
+        used = 1
+
+        def one(iters):
+            t = time.perf_counter()
+            _, tr = lm.optimize(p, w, iters)
+            return len(tr.chi2), time.perf_counter() - t, 0
+        how = f"numpy/scipy port with SuperLU direct solve, 1 thread of {cores} host cores (the reference is single-threaded)"
     for _ in range(warmup):
-        lm.optimize(p, w, 1)
-    t0 = time.perf_counter()
-    its = 0
+        one(1)
+    its, dt, cg = 0, 0.0, 0
     for _ in range(max(1, steps)):
-        _, tr = lm.optimize(p, w, lm_iters)
-        its += len(tr.chi2)
-    dt = time.perf_counter() - t0
+        a, b, c = one(lm_iters)
+        its += a; dt += b; cg += c
     rate_sample = its / dt
     value = rate_sample * p.n / float(n_full)
-    cores = os.cpu_count() or 1
-    cpu = dict(value=value, unit="LM it/s", cores=1, kind="port",
-               sample=f"{its} LM iterations on {p.n} correspondences (k={k}) in {dt:.1f} s = {rate_sample:.3f} it/s, "
-                      f"scaled linearly to {n_full} correspondences; numpy/scipy port with SuperLU direct solve, "
-                      f"1 thread of {cores} host cores (the reference is single-threaded)")
+    cpu = dict(value=value, unit="LM it/s", cores=used, kind="port",
+               sample=f"{its} LM iterations ({cg} PCG iterations) on {p.n} correspondences (k={k}) in {dt:.1f} s = "
+                      f"{rate_sample:.3f} it/s, scaled linearly to {n_full} correspondences; {how}")
     return dict(value=value, ms_per_step=dt * 1e3 / max(1, steps), cpu_baseline=cpu,
                 config=dict(workload=name, correspondences=n_full, k=k, sample_correspondences=p.n,
                             lm_iters_per_step=lm_iters))

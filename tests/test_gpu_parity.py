@@ -363,3 +363,36 @@ def test_gpu_knn_graph_on_a_clustered_tube(pkg, ctx):
     rowptr, col, w = ctx.knn_graph(X, 8)
     r2, c2, _ = wl.knn_graph(X[:, :2].astype(np.float64), 8)
     assert np.array_equal(rowptr, r2) and np.array_equal(col, c2)
+
+
+@pytest.mark.gpu
+def test_lm_matches_the_c_oracle_at_30k(pkg, ctx):
+    """A size the numpy direct solve does not reach comfortably: the CUDA path against the plain-C oracle
+    (oracle/c/dsc_oracle.c, OpenMP PCG), same rotations, PCG rtol 1e-12 on both sides."""
+    from oracle import cport, se3
+    sc = scenes.tube_scene(30011, seed=31, depth_sigma=0.0003)
+    p, keep = scenes.problem_from_scene(sc, "knn", 8, min_cos=0.99999)
+    w = edges.Weights(rep=1.0, arap=1.0e7, depth_sigma=0.0003)
+    _upload(pkg, ctx, p)
+    q = ctx.get_rotations()
+    R = np.stack([se3.quat_to_rot(qi) for qi in q])
+    cp = cport.CProblem(p, rotations=R)
+    cq = cport.CProblem(p)
+    assert cport.compute_rotations(cq) == 0
+    assert np.abs(cq.R - R).max() < 1e-4                      # the C computeR squares the condition number
+    c0, parts = cport.cost(cp, w)
+    g0, gparts = ctx.cost(_w(pkg, w))
+    assert g0 == pytest.approx(c0, rel=1e-11)
+    ctx.set_pcg(rtol=1e-12, max_iters=40000, check_every=64)
+    recs, st = ctx.optimize(_w(pkg, w), 3)
+    out = ctx.download()
+    tr = cport.optimize(cp, w, 3, pcg_rtol=1e-12, pcg_max=40000)
+    assert st.iterations == len(tr["chi2"])
+    for r, c, lam_o, tq in zip(recs, tr["chi2"], tr["lam"], tr["trials"]):
+        assert r.chi2_before == pytest.approx(c, rel=1e-5)
+        assert r.lam == pytest.approx(lam_o, rel=1e-4)
+        assert r.trials == tq
+    assert st.final_chi2 == pytest.approx(tr["final_chi2"], rel=1e-5)
+    scale = np.abs(np.concatenate([cp.X1, cp.X2])).max()
+    assert np.abs(out["X1d"] - cp.X1).max() <= 1e-5 * scale
+    assert np.abs(out["X2d"] - cp.X2).max() <= 1e-5 * scale
