@@ -10,6 +10,7 @@
 #include "dsc_kernels.cuh"
 #include "dsc_kernels_ell.cuh"
 #include "dsc_knn.cuh"
+#include "dsc_graph.cuh"
 
 #include <algorithm>
 #include <chrono>
@@ -63,6 +64,13 @@ struct dsc_ctx {
     int *rowptr = nullptr, *col = nullptr;
     double* wgt = nullptr;
     double* Je = nullptr;                 // per directed edge {u, m, g}
+    // raw (caller order) device copies: the internal order is produced on the device (dsc_graph.cuh)
+    float4* r_uv = nullptr; double2* r_dm = nullptr; float2* r_isg = nullptr;
+    int *g_rp0 = nullptr, *g_col0 = nullptr, *g_inv = nullptr, *g_width = nullptr, *g_sums = nullptr;
+    double* g_w0 = nullptr;
+    unsigned long long *g_key0 = nullptr, *g_key1 = nullptr;
+    void* g_tmp = nullptr;
+    size_t g_ecap = 0, g_ncap = 0, g_tmpcap = 0;
     int* spmv_part = nullptr;                   // [spmv_units + 1] slice ranges = work units of cg_spmv_kernel
     int spmv_units = 0, spmv_cap = 0;
     int *ecol = nullptr, *sliceptr = nullptr;   // sliced ELL of the gather kernels (see dsc_set_graph)
@@ -265,6 +273,9 @@ extern "C" void dsc_destroy(dsc_ctx* ctx) {
     dev_free(ctx->t_uv1); dev_free(ctx->t_uv2); dev_free(ctx->t_d1); dev_free(ctx->t_d2);
     dev_free(ctx->t_X1); dev_free(ctx->t_X2); dev_free(ctx->t_cos); dev_free(ctx->t_valid);
     dev_free(ctx->X1f); dev_free(ctx->X2f); dev_free(ctx->d_perm);
+    dev_free(ctx->r_uv); dev_free(ctx->r_dm); dev_free(ctx->r_isg); dev_free(ctx->g_rp0); dev_free(ctx->g_col0); dev_free(ctx->g_inv);
+    dev_free(ctx->g_width); dev_free(ctx->g_sums); dev_free(ctx->g_w0); dev_free(ctx->g_key0); dev_free(ctx->g_key1);
+    if (ctx->g_tmp) { cudaFree(ctx->g_tmp); ctx->g_tmp = nullptr; }
     dev_free(ctx->P); dev_free(ctx->Ptrial); dev_free(ctx->P0); dev_free(ctx->Q);
     dev_free(ctx->uv); dev_free(ctx->dm); dev_free(ctx->isg);
     dev_free(ctx->rowptr); dev_free(ctx->col); dev_free(ctx->wgt); dev_free(ctx->Je); dev_free(ctx->ecol); dev_free(ctx->ewgt); dev_free(ctx->sliceptr); dev_free(ctx->spmv_part);
@@ -400,32 +411,38 @@ extern "C" int dsc_depth_scale_init(dsc_ctx* ctx, int which, double* scale) {
 }
 
 // ------------------------------------------------------------------ refinement problem
-static int upload_state(dsc_ctx* ctx) {            // (re)build device state from the host copies, in internal order
+// device state in the internal order from the raw (caller order) device copies; perm = ctx->d_perm or identity
+static int build_state(dsc_ctx* ctx) {
     int n = ctx->n;
     if (n == 0) return DSC_OK;
-    const int* pm = ctx->perm.empty() ? nullptr : ctx->perm.data();
+    const int* dp = ctx->perm.empty() ? nullptr : ctx->d_perm;
+    permute_obs_kernel<<<grid_threads(ctx, n), kThreads, 0, ctx->stream>>>(n, dp, ctx->r_uv, ctx->r_dm, ctx->r_isg, ctx->uv, ctx->dm, ctx->isg);
+    init_state_kernel<<<grid_threads(ctx, n), kThreads, 0, ctx->stream>>>(n, ctx->X1f, ctx->X2f, dp, ctx->P0);
+    ctx->launches += 2;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(ctx->P, ctx->P0, sizeof(double) * 8 * n, cudaMemcpyDeviceToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->Gcur, &ctx->g0, sizeof(Globals), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return DSC_OK;
+}
+
+static int upload_state(dsc_ctx* ctx) {            // host copies -> raw device copies (caller order) -> internal order
+    int n = ctx->n;
+    if (n == 0) return DSC_OK;
     CK(pin_reserve(ctx->hs_uv, ctx->hc_uv, (size_t)n)); CK(pin_reserve(ctx->hs_dm, ctx->hc_dm, (size_t)n)); CK(pin_reserve(ctx->hs_isg, ctx->hc_isg, (size_t)n));
     float4* uv = ctx->hs_uv; double2* dm = ctx->hs_dm; float2* sg = ctx->hs_isg;
 #pragma omp parallel for schedule(static)
     for (int i = 0; i < n; ++i) {
-        int s = pm ? pm[i] : i;
-        uv[i] = make_float4(ctx->huv1[2 * s], ctx->huv1[2 * s + 1], ctx->huv2[2 * s], ctx->huv2[2 * s + 1]);
-        dm[i] = make_double2(ctx->hd1[s], ctx->hd2[s]);
-        sg[i] = make_float2(ctx->hisg1[s], ctx->hisg2[s]);
+        uv[i] = make_float4(ctx->huv1[2 * (size_t)i], ctx->huv1[2 * (size_t)i + 1], ctx->huv2[2 * (size_t)i], ctx->huv2[2 * (size_t)i + 1]);
+        dm[i] = make_double2(ctx->hd1[i], ctx->hd2[i]);
+        sg[i] = make_float2(ctx->hisg1[i], ctx->hisg2[i]);
     }
-    CK(cudaMemcpyAsync(ctx->uv, uv, sizeof(float4) * n, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(ctx->dm, dm, sizeof(double2) * n, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(ctx->isg, sg, sizeof(float2) * n, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->r_uv, uv, sizeof(float4) * n, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->r_dm, dm, sizeof(double2) * n, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->r_isg, sg, sizeof(float2) * n, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->X1f, ctx->hX1.data(), sizeof(float) * 3 * n, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->X2f, ctx->hX2.data(), sizeof(float) * 3 * n, cudaMemcpyHostToDevice, ctx->stream));
-    if (pm) CK(cudaMemcpyAsync(ctx->d_perm, pm, sizeof(int) * n, cudaMemcpyHostToDevice, ctx->stream));
-    init_state_kernel<<<grid_threads(ctx, n), kThreads, 0, ctx->stream>>>(n, ctx->X1f, ctx->X2f, pm ? ctx->d_perm : nullptr, ctx->P0);
-    ctx->launches++;
-    CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(ctx->P, ctx->P0, sizeof(double) * 8 * n, cudaMemcpyDeviceToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(ctx->Gcur, &ctx->g0, sizeof(Globals), cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));       // host staging vectors go out of scope
-    return DSC_OK;
+    return build_state(ctx);
 }
 
 extern "C" int dsc_problem_upload(dsc_ctx* ctx, const dsc_pair* pair, int n,
@@ -441,7 +458,7 @@ extern "C" int dsc_problem_upload(dsc_ctx* ctx, const dsc_pair* pair, int n,
         CK(dev_alloc(ctx->X1f, 3 * N)); CK(dev_alloc(ctx->X2f, 3 * N)); CK(dev_alloc(ctx->d_perm, N));
         CK(dev_alloc(ctx->P, 8 * N)); CK(dev_alloc(ctx->Ptrial, 8 * N)); CK(dev_alloc(ctx->P0, 8 * N)); CK(dev_alloc(ctx->Q, 4 * N));
         CK(dev_alloc(ctx->uv, N)); CK(dev_alloc(ctx->dm, N)); CK(dev_alloc(ctx->isg, N));
-        CK(dev_alloc(ctx->rowptr, N + 1));
+        CK(dev_alloc(ctx->r_uv, N)); CK(dev_alloc(ctx->r_dm, N)); CK(dev_alloc(ctx->r_isg, N));
         CK(dev_alloc(ctx->b, 6 * N)); CK(dev_alloc(ctx->D, 21 * 32 * ((N + 31) / 32))); CK(dev_alloc(ctx->U, (size_t)kURec * 32 * ((N + 31) / 32))); CK(dev_alloc(ctx->Minv, 21 * 32 * ((N + 31) / 32)));
         for (auto& v : ctx->vec) CK(dev_alloc(v, 6 * N));
         ctx->cap = n;
@@ -512,67 +529,87 @@ extern "C" int dsc_set_graph(dsc_ctx* ctx, int n, const int32_t* rowptr, const i
                 if (w[order[lo]] != w[e]) return fail(ctx, DSC_ERR_GRAPH, "edge weights are not symmetric");
             }
     }
-    // internal numbering: Morton order of KF1's world (x,y) -- the plane the reference triangulates in
-    std::vector<int> perm(n), inv(n);
-    for (int i = 0; i < n; ++i) perm[i] = i;
-    if (reorder && n > 1) {
+    lap("validate");
+    // ---- raw CSR to the device through pinned staging (the copy of chunk c overlaps the packing of chunk c + 1)
+    if ((size_t)n + 1 > ctx->g_ncap) {
+        size_t N = (size_t)n + 1, NS = ((size_t)n + 31) / 32 + 2;
+        CK(dev_alloc(ctx->g_rp0, N)); CK(dev_alloc(ctx->g_inv, N)); CK(dev_alloc(ctx->g_key0, N)); CK(dev_alloc(ctx->g_key1, N));
+        CK(dev_alloc(ctx->g_width, NS)); CK(dev_alloc(ctx->g_sums, NS / kScanBlock + 2));
+        ctx->g_ncap = N;
+    }
+    if ((size_t)E > ctx->g_ecap) { CK(dev_alloc(ctx->g_col0, (size_t)E)); CK(dev_alloc(ctx->g_w0, (size_t)E)); ctx->g_ecap = (size_t)E; }
+    CK(pin_reserve(ctx->hs_rp, ctx->hc_rp, (size_t)n + 1)); CK(pin_reserve(ctx->hs_cl, ctx->hc_cl, (size_t)E + 1)); CK(pin_reserve(ctx->hs_ww, ctx->hc_ww, (size_t)E + 1));
+    std::memcpy(ctx->hs_rp, rowptr, sizeof(int) * ((size_t)n + 1));
+    CK(cudaMemcpyAsync(ctx->g_rp0, ctx->hs_rp, sizeof(int) * ((size_t)n + 1), cudaMemcpyHostToDevice, ctx->stream));
+    {
+        const long long chunk = 1 << 21;
+        for (long long c0 = 0; c0 < E; c0 += chunk) {
+            const long long c1 = std::min(E, c0 + chunk);
+#pragma omp parallel for schedule(static)
+            for (long long k0 = c0; k0 < c1; k0 += 65536) {
+                const long long k1 = std::min(c1, k0 + 65536);
+                std::memcpy(ctx->hs_cl + k0, col + k0, sizeof(int) * (size_t)(k1 - k0));
+                std::memcpy(ctx->hs_ww + k0, w + k0, sizeof(double) * (size_t)(k1 - k0));
+            }
+            CK(cudaMemcpyAsync(ctx->g_col0 + c0, ctx->hs_cl + c0, sizeof(int) * (size_t)(c1 - c0), cudaMemcpyHostToDevice, ctx->stream));
+            CK(cudaMemcpyAsync(ctx->g_w0 + c0, ctx->hs_ww + c0, sizeof(double) * (size_t)(c1 - c0), cudaMemcpyHostToDevice, ctx->stream));
+        }
+    }
+    lap("csr staging");
+    // ---- internal numbering on the device: Morton order of KF1's world (x, y) -- the plane the reference triangulates
+    // in -- then, for the sliced ELL, a stable sort by degree (descending) inside every group of kSortGroup rows
+    const int nbv = grid_threads(ctx, std::max(n, 1));
+    const bool permuted = reorder && n > 1;
+    if (permuted) {
         float xmin = 1e30f, xmax = -1e30f, ymin = 1e30f, ymax = -1e30f;
+#pragma omp parallel for reduction(min : xmin, ymin) reduction(max : xmax, ymax) schedule(static)
         for (int i = 0; i < n; ++i) {
             float x = ctx->hX1[3 * (size_t)i], y = ctx->hX1[3 * (size_t)i + 1];
             if (std::isfinite(x) && std::isfinite(y)) { xmin = std::min(xmin, x); xmax = std::max(xmax, x); ymin = std::min(ymin, y); ymax = std::max(ymax, y); }
         }
         float sx = xmax > xmin ? 65535.0f / (xmax - xmin) : 0.f, sy = ymax > ymin ? 65535.0f / (ymax - ymin) : 0.f;
-        std::vector<uint64_t> code(n);
-#pragma omp parallel for schedule(static)
-        for (int i = 0; i < n; ++i) {
-            float x = ctx->hX1[3 * (size_t)i], y = ctx->hX1[3 * (size_t)i + 1];
-            uint32_t qx = std::isfinite(x) ? (uint32_t)std::min(65535.0f, std::max(0.0f, (x - xmin) * sx)) : 0u;
-            uint32_t qy = std::isfinite(y) ? (uint32_t)std::min(65535.0f, std::max(0.0f, (y - ymin) * sy)) : 0u;
-            code[i] = ((uint64_t)(part1by1(qx) | (part1by1(qy) << 1)) << 32) | (uint32_t)i;
+        morton_key_kernel<<<nbv, kThreads, 0, ctx->stream>>>(n, ctx->X1f, xmin, sx, ymin, sy, ctx->g_key0);
+        size_t need = 0;
+        CK(cub::DeviceRadixSort::SortKeys(nullptr, need, ctx->g_key0, ctx->g_key1, n, 0, 64, ctx->stream));
+        if (need > ctx->g_tmpcap) {
+            if (ctx->g_tmp) cudaFree(ctx->g_tmp);
+            ctx->g_tmp = nullptr; ctx->g_tmpcap = 0;
+            CK(cudaMalloc(&ctx->g_tmp, need));
+            ctx->g_tmpcap = need;
         }
-        __gnu_parallel::sort(code.begin(), code.end());
-        for (int i = 0; i < n; ++i) perm[i] = (int)(code[i] & 0xffffffffu);
+        CK(cub::DeviceRadixSort::SortKeys(ctx->g_tmp, need, ctx->g_key0, ctx->g_key1, n, 0, 64, ctx->stream));
+        perm_from_key_kernel<<<nbv, kThreads, 0, ctx->stream>>>(n, ctx->g_key1, ctx->d_perm);
+        degree_sort_kernel<<<(n + kSortGroup - 1) / kSortGroup, kSortGroup, 0, ctx->stream>>>(n, ctx->g_rp0, ctx->d_perm);
+        inverse_perm_kernel<<<nbv, kThreads, 0, ctx->stream>>>(n, ctx->d_perm, ctx->g_inv);
+        ctx->launches += 4;
     }
-    if (reorder && n > 1) {
-        // sliced-ELL friendliness: inside every group of kSortGroup Morton-consecutive rows, order by degree
-        // (descending, stable) so that the 32 rows of a warp slice have nearly equal length
-#pragma omp parallel for schedule(static, 16)
-        for (int g0 = 0; g0 < n; g0 += kSortGroup) {
-            int g1 = std::min(n, g0 + kSortGroup);
-            std::stable_sort(perm.begin() + g0, perm.begin() + g1, [&](int a, int b2) {
-                return (rowptr[a + 1] - rowptr[a]) > (rowptr[b2 + 1] - rowptr[b2]);
-            });
-        }
-    }
-    lap("validate+sort");
-    for (int i = 0; i < n; ++i) inv[perm[i]] = i;
-    CK(pin_reserve(ctx->hs_rp, ctx->hc_rp, (size_t)n + 1)); CK(pin_reserve(ctx->hs_cl, ctx->hc_cl, (size_t)E + 1)); CK(pin_reserve(ctx->hs_ww, ctx->hc_ww, (size_t)E + 1));
-    int* rp = ctx->hs_rp; int* cl = ctx->hs_cl; double* ww = ctx->hs_ww;
-    rp[0] = 0;
-    for (int i = 0; i < n; ++i) rp[i + 1] = rp[i] + (rowptr[perm[i] + 1] - rowptr[perm[i]]);
-#pragma omp parallel for schedule(static, 4096)
-    for (int i = 0; i < n; ++i) {
-        int s = perm[i], o = rp[i], deg = rowptr[s + 1] - rowptr[s];
-        for (int k = 0; k < deg; ++k) { cl[o + k] = inv[col[rowptr[s] + k]]; ww[o + k] = w[rowptr[s] + k]; }
-        for (int a = 1; a < deg; ++a) {            // insertion sort of the (short) row by new column index
-            int cj = cl[o + a]; double wj = ww[o + a]; int b2 = a - 1;
-            while (b2 >= 0 && cl[o + b2] > cj) { cl[o + b2 + 1] = cl[o + b2]; ww[o + b2 + 1] = ww[o + b2]; --b2; }
-            cl[o + b2 + 1] = cj; ww[o + b2 + 1] = wj;
-        }
-    }
-    lap("csr permute");
-    // sliced ELL of the PCG operator: slice = 32 consecutive rows (one warp), width = longest row of the slice;
-    // column k of slice s is "block" sliceptr[s] + k: 32 column indices and 9 x 32 Jacobian doubles (Je).
-    // Padding entries point at the row itself and keep an all-zero Jacobian record, so they add exactly 0.
+    const int* dperm = permuted ? ctx->d_perm : nullptr;
+    const int* dinv = permuted ? ctx->g_inv : nullptr;
+    // ---- sliced ELL of the PCG operator and the gather kernels: slice = 32 consecutive rows (one warp), width = longest
+    // row of the slice; column k of slice s is "block" sliceptr[s] + k: 32 column indices, 32 weights and 9 x 32 Jacobian
+    // doubles (Je).  Padding entries point at the row itself and keep an all-zero Jacobian record, so they add exactly 0.
     int nslices = (n + 31) / 32;
+    if (nslices + 1 > ctx->slcap) { CK(dev_alloc(ctx->sliceptr, (size_t)nslices + 1)); ctx->slcap = nslices + 1; }
+    {
+        const int m = nslices + 1, nb = (m + kScanBlock - 1) / kScanBlock;
+        slice_width_kernel<<<std::max(1, std::min(nbv, (nslices + 8) / 8)), kThreads, 0, ctx->stream>>>(n, nslices, dperm, ctx->g_rp0, ctx->g_width);
+        scan_block_kernel<<<nb, kScanBlock, 0, ctx->stream>>>(m, ctx->g_width, ctx->sliceptr, ctx->g_sums);
+        scan_sums_kernel<<<1, kScanBlock, 0, ctx->stream>>>(nb, ctx->g_sums);
+        scan_add_kernel<<<nb, kScanBlock, 0, ctx->stream>>>(m, ctx->sliceptr, ctx->g_sums);
+        ctx->launches += 4;
+    }
+    CK(cudaGetLastError());
     CK(pin_reserve(ctx->hs_sp, ctx->hc_sp, (size_t)nslices + 1));
     int* sp = ctx->hs_sp;
-    sp[0] = 0;
-    for (int sl = 0; sl < nslices; ++sl) {
-        int wmax = 0;
-        for (int i = sl * 32; i < std::min(n, sl * 32 + 32); ++i) wmax = std::max(wmax, rp[i + 1] - rp[i]);
-        sp[sl + 1] = sp[sl] + wmax;
+    CK(cudaMemcpyAsync(sp, ctx->sliceptr, sizeof(int) * ((size_t)nslices + 1), cudaMemcpyDeviceToHost, ctx->stream));
+    if (permuted) {
+        ctx->perm.resize(n);
+        CK(cudaMemcpyAsync(ctx->perm.data(), ctx->d_perm, sizeof(int) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    } else {
+        ctx->perm.clear();
     }
+    CK(cudaStreamSynchronize(ctx->stream));
+    lap("numbering");
     size_t nblk = (size_t)sp[nslices];
     // Work units of the PCG operator (cg_spmv_kernel): full rounds of 16-slice tiles, then the partial last round cut
     // into one equal-work unit per block; a slice costs its ELL blocks (2432 B each) + its 32 rows (256 B each).
@@ -601,81 +638,26 @@ extern "C" int dsc_set_graph(dsc_ctx* ctx, int n, const int32_t* rowptr, const i
         hpart.push_back(nslices);
     }
     ctx->spmv_units = (int)hpart.size() - 1;
-    CK(pin_reserve(ctx->hs_ecol, ctx->hc_ecol, nblk * 32 + 1)); CK(pin_reserve(ctx->hs_ewgt, ctx->hc_ewgt, nblk * 32 + 1));
-    int* ecol = ctx->hs_ecol; double* ewgt = ctx->hs_ewgt;
-    // Slot order inside a row: neighbours inside the row's own tile (the shared-memory window of the gather kernels)
-    // first, halo neighbours last, each part ascending.  Rows of a slice have about the same length, so the halo
-    // gathers (global loads, divergent) concentrate in the last columns of a slice instead of touching every column.
-#pragma omp parallel for schedule(static, 256)
-    for (int sl = 0; sl < nslices; ++sl) {
-        const int width = sp[sl + 1] - sp[sl];
-        for (int l = 0; l < 32; ++l) {
-            const int i = sl * 32 + l;
-            const int deg = i < n ? rp[i + 1] - rp[i] : 0;
-            const int t0 = (i / kSortGroup) * kSortGroup, t1 = t0 + kSortGroup;
-            int k = 0;
-            for (int pass = 0; pass < 2; ++pass)
-                for (int a = 0; a < deg; ++a) {
-                    const int v = cl[rp[i] + a];
-                    const bool inside = v >= t0 && v < t1;
-                    if (inside != (pass == 0)) continue;
-                    ecol[((size_t)sp[sl] + k) * 32 + l] = v;
-                    ewgt[((size_t)sp[sl] + k) * 32 + l] = ww[rp[i] + a];
-                    ++k;
-                }
-            for (; k < width; ++k) {
-                ecol[((size_t)sp[sl] + k) * 32 + l] = i < n ? i : 0;
-                ewgt[((size_t)sp[sl] + k) * 32 + l] = 0.0;
-            }
-        }
-    }
-    if (getenv("DSC_TIMING")) {
-        long long halo_lanes = 0, halo_blocks = 0;
-        for (int sl = 0; sl < nslices; ++sl)
-            for (int k = 0; k < sp[sl + 1] - sp[sl]; ++k) {
-                int any = 0;
-                for (int l = 0; l < 32; ++l) {
-                    int i = sl * 32 + l;
-                    int v = ecol[((size_t)sp[sl] + k) * 32 + l];
-                    int t0 = (i / kSortGroup) * kSortGroup;
-                    if (i < n && (v < t0 || v >= t0 + kSortGroup)) { ++halo_lanes; any = 1; }
-                }
-                halo_blocks += any;
-            }
-        fprintf(stderr, "[dsc] ELL: %zu blocks, %lld with a halo lane, %lld halo lanes of %lld edges\n", nblk, halo_blocks, halo_lanes, (long long)E);
-    }
-    lap("ell build");
-    if (E > ctx->ecap) {
-        CK(dev_alloc(ctx->col, (size_t)E)); CK(dev_alloc(ctx->wgt, (size_t)E));
-        ctx->ecap = E;
-    }
     if ((long long)nblk > ctx->blkcap) {
         CK(dev_alloc(ctx->ecol, nblk * 32)); CK(dev_alloc(ctx->ewgt, nblk * 32)); CK(dev_alloc(ctx->Je, nblk * 288));
         ctx->blkcap = (long long)nblk;
     }
     if ((int)hpart.size() > ctx->spmv_cap) { CK(dev_alloc(ctx->spmv_part, hpart.size())); ctx->spmv_cap = (int)hpart.size(); }
-    if (nslices + 1 > ctx->slcap) { CK(dev_alloc(ctx->sliceptr, (size_t)nslices + 1)); ctx->slcap = nslices + 1; }
     ctx->E = E; ctx->nblk = (long long)nblk;
     ctx->area = area; ctx->ntri = n_triangles;
-    CK(cudaMemcpyAsync(ctx->rowptr, rp, sizeof(int) * (n + 1), cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(ctx->sliceptr, sp, sizeof(int) * (nslices + 1), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->spmv_part, hpart.data(), sizeof(int) * hpart.size(), cudaMemcpyHostToDevice, ctx->stream));
-    if (E > 0) {
-        CK(cudaMemcpyAsync(ctx->col, cl, sizeof(int) * E, cudaMemcpyHostToDevice, ctx->stream));
-        CK(cudaMemcpyAsync(ctx->wgt, ww, sizeof(double) * E, cudaMemcpyHostToDevice, ctx->stream));
-        CK(cudaMemcpyAsync(ctx->ecol, ecol, sizeof(int) * nblk * 32, cudaMemcpyHostToDevice, ctx->stream));
-        CK(cudaMemcpyAsync(ctx->ewgt, ewgt, sizeof(double) * nblk * 32, cudaMemcpyHostToDevice, ctx->stream));
+    if (n > 0 && nblk > 0) {
+        // Slot order inside a row: neighbours inside the row's own tile (the shared-memory window of the gather kernels)
+        // first, halo neighbours last, each part ascending: the halo gathers concentrate in the last columns of a slice.
+        ell_fill_kernel<<<nbv, kThreads, 0, ctx->stream>>>(n, dperm, dinv, ctx->g_rp0, ctx->g_col0, ctx->g_w0, ctx->sliceptr, ctx->ecol, ctx->ewgt);
+        ctx->launches++;
+        CK(cudaGetLastError());
         CK(cudaMemsetAsync(ctx->Je, 0, sizeof(double) * nblk * 288, ctx->stream));
     }
-    CK(cudaStreamSynchronize(ctx->stream));
-    lap("uploads");
-    bool identity = true;
-    for (int i = 0; i < n; ++i) if (perm[i] != i) { identity = false; break; }
-    if (identity) ctx->perm.clear(); else ctx->perm = perm;
     ctx->have_graph = true; ctx->have_rot = false;
     drop_graphs(ctx);
-    int urc = upload_state(ctx);
-    lap("upload_state");
+    int urc = build_state(ctx);                        // (synchronises the stream: hpart may go out of scope)
+    lap("ell + state");
     return urc;
 }
 
