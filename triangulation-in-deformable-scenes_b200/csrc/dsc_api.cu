@@ -53,8 +53,8 @@ struct dsc_ctx {
     long long ntri = 0;
     Globals g0{};                         // uploaded globals
     std::vector<int> perm;                // internal index -> caller index
-    std::vector<float> hX1, hX2, huv1, huv2, hisg1, hisg2;
-    std::vector<double> hd1, hd2;
+    float *hs_x1 = nullptr, *hs_x2 = nullptr;    // pinned copies of the caller's points (caller order)
+    size_t hc_x1 = 0, hc_x2 = 0;
     float *X1f = nullptr, *X2f = nullptr;         // staging (caller order)
     int* d_perm = nullptr;
     double *P = nullptr, *Ptrial = nullptr, *P0 = nullptr, *Q = nullptr;
@@ -287,7 +287,7 @@ extern "C" void dsc_destroy(dsc_ctx* ctx) {
     dev_free(ctx->dpart); dev_free(ctx->bpart);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     for (void* q : {(void*)ctx->hs_rp, (void*)ctx->hs_cl, (void*)ctx->hs_ecol, (void*)ctx->hs_sp, (void*)ctx->hs_ww, (void*)ctx->hs_ewgt,
-                    (void*)ctx->hs_uv, (void*)ctx->hs_dm, (void*)ctx->hs_isg}) if (q) cudaFreeHost(q);
+                    (void*)ctx->hs_uv, (void*)ctx->hs_dm, (void*)ctx->hs_isg, (void*)ctx->hs_x1, (void*)ctx->hs_x2}) if (q) cudaFreeHost(q);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->evA) cudaEventDestroy(ctx->evA);
@@ -426,22 +426,27 @@ static int build_state(dsc_ctx* ctx) {
     return DSC_OK;
 }
 
-static int upload_state(dsc_ctx* ctx) {            // host copies -> raw device copies (caller order) -> internal order
+// caller arrays -> pinned staging (packed, in parallel) -> raw device copies (caller order) -> internal order
+static int upload_state(dsc_ctx* ctx, const float* X1, const float* X2, const float* uv1, const float* uv2, const double* d1,
+                        const double* d2, const float* isg1, const float* isg2) {
     int n = ctx->n;
     if (n == 0) return DSC_OK;
     CK(pin_reserve(ctx->hs_uv, ctx->hc_uv, (size_t)n)); CK(pin_reserve(ctx->hs_dm, ctx->hc_dm, (size_t)n)); CK(pin_reserve(ctx->hs_isg, ctx->hc_isg, (size_t)n));
+    CK(pin_reserve(ctx->hs_x1, ctx->hc_x1, 3 * (size_t)n)); CK(pin_reserve(ctx->hs_x2, ctx->hc_x2, 3 * (size_t)n));
     float4* uv = ctx->hs_uv; double2* dm = ctx->hs_dm; float2* sg = ctx->hs_isg;
+    float *x1 = ctx->hs_x1, *x2 = ctx->hs_x2;
 #pragma omp parallel for schedule(static)
     for (int i = 0; i < n; ++i) {
-        uv[i] = make_float4(ctx->huv1[2 * (size_t)i], ctx->huv1[2 * (size_t)i + 1], ctx->huv2[2 * (size_t)i], ctx->huv2[2 * (size_t)i + 1]);
-        dm[i] = make_double2(ctx->hd1[i], ctx->hd2[i]);
-        sg[i] = make_float2(ctx->hisg1[i], ctx->hisg2[i]);
+        uv[i] = make_float4(uv1[2 * (size_t)i], uv1[2 * (size_t)i + 1], uv2[2 * (size_t)i], uv2[2 * (size_t)i + 1]);
+        dm[i] = make_double2(d1[i], d2[i]);
+        sg[i] = make_float2(isg1 ? isg1[i] : 1.0f, isg2 ? isg2[i] : 1.0f);
+        for (int k = 0; k < 3; ++k) { x1[3 * (size_t)i + k] = X1[3 * (size_t)i + k]; x2[3 * (size_t)i + k] = X2[3 * (size_t)i + k]; }
     }
     CK(cudaMemcpyAsync(ctx->r_uv, uv, sizeof(float4) * n, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->r_dm, dm, sizeof(double2) * n, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->r_isg, sg, sizeof(float2) * n, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(ctx->X1f, ctx->hX1.data(), sizeof(float) * 3 * n, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(ctx->X2f, ctx->hX2.data(), sizeof(float) * 3 * n, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->X1f, x1, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->X2f, x2, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, ctx->stream));
     return build_state(ctx);
 }
 
@@ -465,11 +470,6 @@ extern "C" int dsc_problem_upload(dsc_ctx* ctx, const dsc_pair* pair, int n,
     }
     ctx->n = n;
     fill_pair(pair, ctx->pair);
-    ctx->hX1.assign(X1, X1 + 3 * (size_t)n); ctx->hX2.assign(X2, X2 + 3 * (size_t)n);
-    ctx->huv1.assign(uv1, uv1 + 2 * (size_t)n); ctx->huv2.assign(uv2, uv2 + 2 * (size_t)n);
-    ctx->hd1.assign(depth1, depth1 + n); ctx->hd2.assign(depth2, depth2 + n);
-    if (inv_sigma2_1) ctx->hisg1.assign(inv_sigma2_1, inv_sigma2_1 + n); else ctx->hisg1.assign(n, 1.0f);
-    if (inv_sigma2_2) ctx->hisg2.assign(inv_sigma2_2, inv_sigma2_2 + n); else ctx->hisg2.assign(n, 1.0f);
     Globals g{};
     if (Tg7) {
         double nq = std::sqrt(Tg7[0] * Tg7[0] + Tg7[1] * Tg7[1] + Tg7[2] * Tg7[2] + Tg7[3] * Tg7[3]);
@@ -484,7 +484,7 @@ extern "C" int dsc_problem_upload(dsc_ctx* ctx, const dsc_pair* pair, int n,
     ctx->perm.clear();
     ctx->have_problem = true; ctx->have_graph = false; ctx->have_rot = false;
     drop_graphs(ctx);
-    return upload_state(ctx);
+    return upload_state(ctx, X1, X2, uv1, uv2, depth1, depth2, inv_sigma2_1, inv_sigma2_2);
 }
 
 extern "C" int dsc_set_graph(dsc_ctx* ctx, int n, const int32_t* rowptr, const int32_t* col, const double* w,
@@ -564,7 +564,7 @@ extern "C" int dsc_set_graph(dsc_ctx* ctx, int n, const int32_t* rowptr, const i
         float xmin = 1e30f, xmax = -1e30f, ymin = 1e30f, ymax = -1e30f;
 #pragma omp parallel for reduction(min : xmin, ymin) reduction(max : xmax, ymax) schedule(static)
         for (int i = 0; i < n; ++i) {
-            float x = ctx->hX1[3 * (size_t)i], y = ctx->hX1[3 * (size_t)i + 1];
+            float x = ctx->hs_x1[3 * (size_t)i], y = ctx->hs_x1[3 * (size_t)i + 1];
             if (std::isfinite(x) && std::isfinite(y)) { xmin = std::min(xmin, x); xmax = std::max(xmax, x); ymin = std::min(ymin, y); ymax = std::max(ymax, y); }
         }
         float sx = xmax > xmin ? 65535.0f / (xmax - xmin) : 0.f, sy = ymax > ymin ? 65535.0f / (ymax - ymin) : 0.f;
