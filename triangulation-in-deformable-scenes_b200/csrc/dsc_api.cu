@@ -798,8 +798,7 @@ static int pcg_begin(dsc_ctx* ctx, const WeightsDev& W, double lambda) {
     double* Ginv = ctx->small + 48;
     CK(cudaMemsetAsync(ctx->errflag, 0, sizeof(int), ctx->stream));
     ctl_set_kernel<<<1, 1, 0, ctx->stream>>>(ctx->ctl, lambda, 1, 0.0, 0, 0);
-    precond_kernel<<<nbv, kThreads, 0, ctx->stream>>>(n, ctx->D, lambda, ctx->lin, ctx->Minv, Ginv, ctx->errflag);
-    cg_init_kernel<<<nbv, kThreads, 0, ctx->stream>>>(n, ctx->b, ctx->lin, ctx->Minv, Ginv, v, ctx->gpart[0], ctx->ctl);
+    cg_init_kernel<<<nbv, kThreads, 0, ctx->stream>>>(n, ctx->b, ctx->D, lambda, ctx->lin, ctx->Minv, Ginv, ctx->errflag, v, ctx->gpart[0], ctx->ctl);
     cg_spmv_kernel<<<nbs, kThreads, kSpmvSmem, ctx->stream>>>(n, ctx->P, ctx->Je, ctx->U, ctx->sliceptr, ctx->ecol, ctx->spmv_part, ctx->spmv_units, ctx->Gcur, ctx->pair, W,
                                                      lambda, v.z, v.zg, v.w, ctx->dpart, ctx->bpart, ctx->lin, ctx->ctl);
     ctx->launches += 3;
@@ -1148,8 +1147,7 @@ extern "C" int dsc_profile_kernels(dsc_ctx* ctx, const dsc_weights* w, int warm,
     double* Ginv = ctx->small + 48;
     int nbv = grid_threads(ctx, n), nbs = grid_groups(ctx, n), nbp = grid_spmv(ctx, n);
     CK(cudaMemsetAsync(ctx->errflag, 0, sizeof(int), ctx->stream));
-    precond_kernel<<<nbv, kThreads, 0, ctx->stream>>>(n, ctx->D, lambda, ctx->lin, ctx->Minv, Ginv, ctx->errflag);
-    cg_init_kernel<<<nbv, kThreads, 0, ctx->stream>>>(n, ctx->b, ctx->lin, ctx->Minv, Ginv, v, ctx->gpart[0], ctx->ctl);
+    cg_init_kernel<<<nbv, kThreads, 0, ctx->stream>>>(n, ctx->b, ctx->D, lambda, ctx->lin, ctx->Minv, Ginv, ctx->errflag, v, ctx->gpart[0], ctx->ctl);
     ctx->launches += 2;
     double N = (double)n, E = (double)ctx->E;
     double by[DSC_K_COUNT];
@@ -1158,7 +1156,7 @@ extern "C" int dsc_profile_kernels(dsc_ctx* ctx, const dsc_weights* w, int warm,
     double S = (double)ctx->nblk * 32.0;            // ELL slots (padding included)
     by[DSC_K_LINEARIZE] = 488.0 * N + 12.0 * S + 72.0 * E;   // P Q uv dm isg | ecol ewgt per slot | write b D U, Je per edge
     by[DSC_K_COST] = 136.0 * N + 12.0 * S;         // P Q uv dm isg | ecol ewgt per slot
-    by[DSC_K_PRECOND] = 336.0 * N;                // D -> Minv
+    by[DSC_K_PRECOND] = 480.0 * N;                // preconditioner + PCG start: D b -> Minv r z
     by[DSC_K_APPLY] = 224.0 * N;                  // P x b -> Ptrial
     by[DSC_K_ROTATIONS] = 96.0 * N + 12.0 * S;     // P | ecol ewgt per slot | write Q
     auto time_it = [&](int which, auto&& launch) -> int {
@@ -1179,9 +1177,10 @@ extern "C" int dsc_profile_kernels(dsc_ctx* ctx, const dsc_weights* w, int warm,
     if (s) return s;
     // update: run real CG steps (first=1 keeps beta = 0, so the recurrences stay finite for any reps)
     s = time_it(DSC_K_UPDATE, [&]() {
-        CgControl z{};
+        CgControl z{};                                 // a regular (not first) step: beta ~ 0, all seven vectors read
+        z.lambda = lambda; z.gamma0 = 1e300; z.sc[1].gamma_prev = 1e300; z.sc[1].alpha_prev = 1.0;
         cudaMemcpyAsync(ctx->ctl, &z, sizeof(CgControl), cudaMemcpyHostToDevice, ctx->stream);
-        cg_update_kernel<<<nbv, kThreads, 0, ctx->stream>>>(n, 0, 1, ctx->Minv, Ginv, ctx->lin, lambda, v, ctx->gpart[0], ctx->gpart[1],
+        cg_update_kernel<<<nbv, kThreads, 0, ctx->stream>>>(n, 0, 0, ctx->Minv, Ginv, ctx->lin, lambda, v, ctx->gpart[0], ctx->gpart[1],
                                                            ctx->dpart, ctx->bpart, nbp, ctx->ctl, 0.0);
     });
     if (s) return s;
@@ -1197,7 +1196,7 @@ extern "C" int dsc_profile_kernels(dsc_ctx* ctx, const dsc_weights* w, int warm,
     });
     if (s) return s;
     s = time_it(DSC_K_PRECOND, [&]() {
-        precond_kernel<<<nbv, kThreads, 0, ctx->stream>>>(n, ctx->D, lambda, ctx->lin, ctx->Minv, Ginv, ctx->errflag);
+        cg_init_kernel<<<nbv, kThreads, 0, ctx->stream>>>(n, ctx->b, ctx->D, lambda, ctx->lin, ctx->Minv, Ginv, ctx->errflag, v, ctx->gpart[0], ctx->ctl);
     });
     if (s) return s;
     s = time_it(DSC_K_APPLY, [&]() {

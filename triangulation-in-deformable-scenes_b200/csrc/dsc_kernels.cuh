@@ -398,43 +398,40 @@ template <typename T>
 DSC_D T* blk21(T* base, int i) { return base + ((size_t)(i >> 5) * 21) * 32 + (i & 31); }
 
 // block-Jacobi preconditioner: Minv_i = (D_i + lambda I)^-1 (packed), Ginv = (C + lambda I)^-1
-__global__ void __launch_bounds__(kThreads)
-precond_kernel(int n, const double* __restrict__ D, double lambda, const LinGlobal* __restrict__ lin,
-               double* __restrict__ Minv, double* __restrict__ Ginv, int* __restrict__ err) {
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const double* Dp = blk21(D, i);
-        double A[36], Ai[36];
+DSC_D void precond_block(const double* __restrict__ D, int i, double lambda, double* __restrict__ Minv, int* __restrict__ err,
+                         double (&M)[21]) {
+    const double* Dp = blk21(D, i);
+    double A[36], Ai[36];
 #pragma unroll
-        for (int r = 0; r < 6; ++r)
+    for (int r = 0; r < 6; ++r)
 #pragma unroll
-            for (int c = r; c < 6; ++c) {
-                double v = Dp[pk<6>(r, c) * 32] + (r == c ? lambda : 0.0);
-                A[r * 6 + c] = v; A[c * 6 + r] = v;
-            }
-        if (!spd_inverse<6>(A, Ai)) {
-            atomicExch(err, 1);
-#pragma unroll
-            for (int k = 0; k < 36; ++k) Ai[k] = 0.0;
-#pragma unroll
-            for (int r = 0; r < 6; ++r) Ai[r * 6 + r] = 1.0 / fmax(fabs(A[r * 6 + r]), 1e-300);
+        for (int c = r; c < 6; ++c) {
+            double v = Dp[pk<6>(r, c) * 32] + (r == c ? lambda : 0.0);
+            A[r * 6 + c] = v; A[c * 6 + r] = v;
         }
-        double* Mp = blk21(Minv, i);
+    if (!spd_inverse<6>(A, Ai)) {
+        atomicExch(err, 1);
 #pragma unroll
-        for (int r = 0; r < 6; ++r)
+        for (int k = 0; k < 36; ++k) Ai[k] = 0.0;
 #pragma unroll
-            for (int c = r; c < 6; ++c) Mp[pk<6>(r, c) * 32] = Ai[r * 6 + c];
+        for (int r = 0; r < 6; ++r) Ai[r * 6 + r] = 1.0 / fmax(fabs(A[r * 6 + r]), 1e-300);
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-        double A[64], Ai[64];
-        for (int k = 0; k < 64; ++k) A[k] = lin->C[k];
-        for (int r = 0; r < 8; ++r) A[r * 8 + r] += lambda;
-        if (!spd_inverse<8>(A, Ai)) {
-            atomicExch(err, 1);
-            for (int k = 0; k < 64; ++k) Ai[k] = 0.0;
-            for (int r = 0; r < 8; ++r) Ai[r * 8 + r] = 1.0 / fmax(fabs(A[r * 8 + r]), 1e-300);
-        }
-        for (int k = 0; k < 64; ++k) Ginv[k] = Ai[k];
+    double* Mp = blk21(Minv, i);
+#pragma unroll
+    for (int r = 0; r < 6; ++r)
+#pragma unroll
+        for (int c = r; c < 6; ++c) { M[pk<6>(r, c)] = Ai[r * 6 + c]; Mp[pk<6>(r, c) * 32] = Ai[r * 6 + c]; }
+}
+DSC_D void precond_global(const LinGlobal* __restrict__ lin, double lambda, double* __restrict__ Ginv, int* __restrict__ err) {
+    double A[64], Ai[64];
+    for (int k = 0; k < 64; ++k) A[k] = lin->C[k];
+    for (int r = 0; r < 8; ++r) A[r * 8 + r] += lambda;
+    if (!spd_inverse<8>(A, Ai)) {
+        atomicExch(err, 1);
+        for (int k = 0; k < 64; ++k) Ai[k] = 0.0;
+        for (int r = 0; r < 8; ++r) Ai[r * 8 + r] = 1.0 / fmax(fabs(A[r * 8 + r]), 1e-300);
     }
+    for (int k = 0; k < 64; ++k) Ginv[k] = Ai[k];
 }
 
 DSC_D void apply_minv(const double* __restrict__ Mp, const double* r, double* z) {
@@ -460,25 +457,34 @@ struct CgVecs {
     double *xg, *rg, *zg, *wg, *pg, *sg;    // [8]
 };
 
+// Preconditioner and PCG start in one pass over the rows: Minv = (D + lambda I)^-1, r = b, z = Minv r, gamma partial.
+// x, p and s are not written: the first cg_update (first = 1) treats them as zero.
 __global__ void __launch_bounds__(kThreads)
-cg_init_kernel(int n, const double* __restrict__ b, const LinGlobal* __restrict__ lin, const double* __restrict__ Minv,
-               const double* __restrict__ Ginv, CgVecs v, double* __restrict__ gpart, CgControl* __restrict__ ctl) {
+cg_init_kernel(int n, const double* __restrict__ b, const double* __restrict__ D, double lambda, const LinGlobal* __restrict__ lin,
+               double* __restrict__ Minv, double* __restrict__ Ginv, int* __restrict__ err, CgVecs v, double* __restrict__ gpart,
+               CgControl* __restrict__ ctl) {
     __shared__ double sm[kThreads / 32];
     double g[1] = {0.0};
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        double r[6], z[6];
+        double r[6], z[6], M[21];
         D3 a, c;
         load6(b, i, a, c);
         r[0] = a.x; r[1] = a.y; r[2] = a.z; r[3] = c.x; r[4] = c.y; r[5] = c.z;
-        apply_minv(blk21(Minv, i), r, z);
+        precond_block(D, i, lambda, Minv, err, M);
+#pragma unroll
+        for (int q = 0; q < 6; ++q) {
+            double sacc = 0.0;
+#pragma unroll
+            for (int k = 0; k < 6; ++k) sacc += (q <= k ? M[pk<6>(q, k)] : M[pk<6>(k, q)]) * r[k];
+            z[q] = sacc;
+        }
         store6(v.r, i, a, c);
         store6(v.z, i, d3(z[0], z[1], z[2]), d3(z[3], z[4], z[5]));
-        D3 zero = d3(0, 0, 0);
-        store6(v.x, i, zero, zero); store6(v.p, i, zero, zero); store6(v.s, i, zero, zero);
 #pragma unroll
         for (int k = 0; k < 6; ++k) g[0] += r[k] * z[k];
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
+        precond_global(lin, lambda, Ginv, err);
         for (int a = 0; a < 8; ++a) {
             double s = 0.0;
             for (int c = 0; c < 8; ++c) s += Ginv[a * 8 + c] * lin->bg[c];
@@ -741,11 +747,16 @@ cg_update_kernel(int n, int par, int first, const double* __restrict__ Minv, con
     double g[1] = {0.0};
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         D3 z1, z2, w1, w2, p1, p2, s1, s2, x1, x2, r1, r2;
-        load6(v.z, i, z1, z2); load6(v.w, i, w1, w2); load6(v.p, i, p1, p2);
-        load6(v.s, i, s1, s2); load6(v.x, i, x1, x2); load6(v.r, i, r1, r2);
-        p1 = z1 + beta * p1; p2 = z2 + beta * p2;
-        s1 = w1 + beta * s1; s2 = w2 + beta * s2;
-        x1 = x1 + alpha * p1; x2 = x2 + alpha * p2;
+        load6(v.z, i, z1, z2); load6(v.w, i, w1, w2); load6(v.r, i, r1, r2);
+        if (first) {                                         // x = p = s = 0 (never written by cg_init_kernel)
+            p1 = z1; p2 = z2; s1 = w1; s2 = w2;
+            x1 = alpha * p1; x2 = alpha * p2;
+        } else {
+            load6(v.p, i, p1, p2); load6(v.s, i, s1, s2); load6(v.x, i, x1, x2);
+            p1 = z1 + beta * p1; p2 = z2 + beta * p2;
+            s1 = w1 + beta * s1; s2 = w2 + beta * s2;
+            x1 = x1 + alpha * p1; x2 = x2 + alpha * p2;
+        }
         r1 = r1 - alpha * s1; r2 = r2 - alpha * s2;
         double r[6] = {r1.x, r1.y, r1.z, r2.x, r2.y, r2.z}, zn[6];
         apply_minv(blk21(Minv, i), r, zn);
