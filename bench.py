@@ -40,7 +40,7 @@ def parse():
     ap.add_argument("--pcg-max-iters", type=int, default=6000)
     ap.add_argument("--early-rtol", type=float, nargs="*", default=[1e-3, 1e-4], help="loose tolerances of the early-reject check (none = off)")
     ap.add_argument("--early-margin", type=float, nargs="*", default=[1.0, 0.5])
-    ap.add_argument("--cpu-sample-n", type=int, default=50000)
+    ap.add_argument("--cpu-sample-n", type=int, default=100000)
     ap.add_argument("--cpu-impl", choices=["c", "numpy"], default="c", help="CPU legs: compiled C oracle (all cores) or the numpy port")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
