@@ -173,6 +173,16 @@ int dsc_set_rotations(dsc_ctx* ctx, const double* quat);
 /* back to the uploaded points / scales / T_global (replaces Map::clone() for the weight search) */
 int dsc_reset_state(dsc_ctx* ctx);
 int dsc_set_pcg(dsc_ctx* ctx, const dsc_pcg_params* prm);
+/* Linear solver of the LM step (the reference: g2o LinearSolverEigen, a sparse Cholesky, g2oBundleAdjustment.cc:619-628).
+ * DSC_SOLVER_AUTO (default): dense Cholesky on the device up to DSC_DENSE_AUTO_MAX correspondences (the reference's own
+ * problem sizes, where the PCG is bound by launch latency), PCG above; DSC_SOLVER_PCG / DSC_SOLVER_DENSE force one
+ * (dense: n <= DSC_DENSE_MAX, else DSC_ERR_INVALID_ARG from dsc_optimize). */
+#define DSC_SOLVER_AUTO 0
+#define DSC_SOLVER_PCG 1
+#define DSC_SOLVER_DENSE 2
+#define DSC_DENSE_AUTO_MAX 600
+#define DSC_DENSE_MAX 1000
+int dsc_set_solver(dsc_ctx* ctx, int solver);
 /* Optional (off by default): pause every linear solve at up to 4 loose tolerances rtol_loose[0] > rtol_loose[1] > ...,
  * evaluate the trial step there, and reject it at once when rho < -rho_margin[level]; otherwise resume the same CG.
  * The last pass always runs to the tight tolerance of dsc_set_pcg, so accepted steps are unchanged.  A rejected step

@@ -136,8 +136,9 @@ def test_rotations_cost_gradient_and_operator(pkg, ctx, kind, n):
     np.testing.assert_allclose(y, yo, rtol=1e-9, atol=1e-10 * np.abs(yo).max())
 
 
-def _compare_lm(pkg, ctx, p, w, iters, rtol_cost=1e-5, rtol_pts=1e-5, pcg_rtol=1e-12, reorder=1):
+def _compare_lm(pkg, ctx, p, w, iters, rtol_cost=1e-5, rtol_pts=1e-5, pcg_rtol=1e-12, reorder=1, solver=1):
     _upload(pkg, ctx, p, reorder)
+    ctx.set_solver(solver)                 # 1 = PCG (the 1M path), 2 = dense Cholesky (small problems), 0 = auto
     ctx.set_pcg(rtol=pcg_rtol, max_iters=20000, check_every=64)
     recs, st = ctx.optimize(_w(pkg, w), iters)
     out = ctx.download()
@@ -318,6 +319,7 @@ def test_early_reject_keeps_the_trace(pkg, ctx):
     p, keep = scenes.build_problem(fe["uv1"], fe["uv2"], fe["d1"], fe["d2"], fe["cam"], fe["T1"], fe["T2"])
     w = _w(pkg, edges.Weights(rep=1.0, arap=200000.0, depth_sigma=0.003))
     _upload(pkg, ctx, p)
+    ctx.set_solver(1)                       # the early rejection belongs to the PCG path
     ctx.set_pcg(rtol=1e-12, max_iters=20000, check_every=64)
     r0, s0 = ctx.optimize(w, 25)
     o0 = ctx.download()
@@ -396,3 +398,43 @@ def test_lm_matches_the_c_oracle_at_30k(pkg, ctx):
     scale = np.abs(np.concatenate([cp.X1, cp.X2])).max()
     assert np.abs(out["X1d"] - cp.X1).max() <= 1e-5 * scale
     assert np.abs(out["X2d"] - cp.X2).max() <= 1e-5 * scale
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("solver", [2, 0])
+def test_dense_solver_on_the_reference_sized_problem(pkg, ctx, solver):
+    """Config 1 (120 points, Delaunay mesh): the dense Cholesky path (what DSC_SOLVER_AUTO picks at this size) against
+    the direct-solve oracle -- both factorise the same matrix, as g2o's LinearSolverEigen does."""
+    import os
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "config1_points.npz"))
+    fe = scenes.simulation_frontend(z["original"], z["moved"], (-0.10, 0.02, 0.12), (0.14, 0.01, 0.06))
+    p, keep = scenes.build_problem(fe["uv1"], fe["uv2"], fe["d1"], fe["d2"], fe["cam"], fe["T1"], fe["T2"])
+    w = edges.Weights(rep=1.0, arap=200000.0, depth_sigma=0.003, glob=50.0)
+    recs, st, out = _compare_lm(pkg, ctx, p, w, 25, solver=solver)
+    assert st.total_pcg_iters == 0
+    ctx.set_solver(0)
+
+
+@pytest.mark.gpu
+def test_dense_and_pcg_agree_and_limits(pkg, ctx):
+    sc = scenes.sheet_scene(700, seed=41)
+    p, keep = scenes.problem_from_scene(sc, "knn", 8)
+    w = edges.Weights(rep=1.0, arap=50.0, depth_sigma=0.003)
+    r1, s1, o1 = _compare_lm(pkg, ctx, p, w, 4, solver=1)
+    r2, s2, o2 = _compare_lm(pkg, ctx, p, w, 4, solver=2)
+    assert [r.trials for r in r1] == [r.trials for r in r2]
+    scale = np.abs(o1["X1d"]).max()
+    assert np.abs(o1["X1d"] - o2["X1d"]).max() <= 1e-6 * scale
+    assert s2.total_pcg_iters == 0 and s1.total_pcg_iters > 0
+    # above DSC_DENSE_MAX the dense solver refuses; auto falls back to the PCG
+    sc = scenes.sheet_scene(1300, seed=42)
+    p, keep = scenes.problem_from_scene(sc, "knn", 8)
+    assert p.n > 1000
+    _upload(pkg, ctx, p)
+    ctx.set_solver(2)
+    with pytest.raises(pkg.DscError) as e:
+        ctx.optimize(_w(pkg, w), 1)
+    assert e.value.status == -1
+    ctx.set_solver(0)
+    recs, st = ctx.optimize(_w(pkg, w), 1)
+    assert st.total_pcg_iters > 0

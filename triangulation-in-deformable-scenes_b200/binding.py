@@ -23,7 +23,7 @@ EXPORTS = [
     "dsc_timer_start", "dsc_timer_stop", "dsc_launch_count",
     "dsc_triangulate", "dsc_tri_upload", "dsc_tri_run", "dsc_tri_download", "dsc_depth_scale_init",
     "dsc_problem_upload", "dsc_set_graph", "dsc_compute_rotations", "dsc_get_rotations", "dsc_set_rotations",
-    "dsc_reset_state", "dsc_set_pcg", "dsc_set_early_reject", "dsc_cost", "dsc_optimize", "dsc_download", "dsc_pixel_sigma",
+    "dsc_reset_state", "dsc_set_pcg", "dsc_set_solver", "dsc_set_early_reject", "dsc_cost", "dsc_optimize", "dsc_download", "dsc_pixel_sigma",
     "dsc_debug_linearize", "dsc_debug_matvec", "dsc_profile_kernels", "dsc_profile_triangulate", "dsc_problem_size", "dsc_knn_build", "dsc_knn_download",
 ]
 KERNEL_NAMES = ["cg_spmv", "cg_update", "linearize", "cost", "precond", "apply_update", "rotations"]
@@ -259,6 +259,10 @@ class Context:
 
     def reset_state(self):
         self._ck(self.lib.dsc_reset_state(self.h))
+
+    def set_solver(self, solver=0):
+        """0 auto (dense Cholesky for small problems, PCG above), 1 PCG, 2 dense."""
+        self._ck(self.lib.dsc_set_solver(self.h, int(solver)))
 
     def set_pcg(self, rtol=1e-10, max_iters=4000, check_every=32):
         p = PcgParams(float(rtol), int(max_iters), int(check_every))

@@ -11,6 +11,7 @@
 #include "dsc_kernels_ell.cuh"
 #include "dsc_knn.cuh"
 #include "dsc_graph.cuh"
+#include "dsc_dense.cuh"
 
 #include <algorithm>
 #include <chrono>
@@ -98,6 +99,9 @@ struct dsc_ctx {
     dsc_pcg_params pcg{1e-10, 4000, 32};
     struct IterGraph { cudaGraphExec_t exec = nullptr; const double* P = nullptr; WeightsDev W{}; } graphs[2];   // per state buffer
     bool use_graphs = true;
+    int solver = DSC_SOLVER_AUTO;                    // dense Cholesky for small problems, PCG above (dsc_set_solver)
+    double *dnH = nullptr, *dnA = nullptr, *dn_rhs = nullptr, *dn_sol = nullptr;
+    int dn_cap = 0;
     int early_levels = 0;                            // early rejection of clearly bad LM trials (off by default)
     double early_rtol[4] = {0, 0, 0, 0}, early_margin[4] = {0, 0, 0, 0};
 };
@@ -273,6 +277,7 @@ extern "C" void dsc_destroy(dsc_ctx* ctx) {
     dev_free(ctx->t_uv1); dev_free(ctx->t_uv2); dev_free(ctx->t_d1); dev_free(ctx->t_d2);
     dev_free(ctx->t_X1); dev_free(ctx->t_X2); dev_free(ctx->t_cos); dev_free(ctx->t_valid);
     dev_free(ctx->X1f); dev_free(ctx->X2f); dev_free(ctx->d_perm);
+    dev_free(ctx->dnH); dev_free(ctx->dnA); dev_free(ctx->dn_rhs); dev_free(ctx->dn_sol);
     dev_free(ctx->r_uv); dev_free(ctx->r_dm); dev_free(ctx->r_isg); dev_free(ctx->g_rp0); dev_free(ctx->g_col0); dev_free(ctx->g_inv);
     dev_free(ctx->g_width); dev_free(ctx->g_sums); dev_free(ctx->g_w0); dev_free(ctx->g_key0); dev_free(ctx->g_key1);
     if (ctx->g_tmp) { cudaFree(ctx->g_tmp); ctx->g_tmp = nullptr; }
@@ -721,6 +726,12 @@ extern "C" int dsc_set_pcg(dsc_ctx* ctx, const dsc_pcg_params* prm) {
     return DSC_OK;
 }
 
+extern "C" int dsc_set_solver(dsc_ctx* ctx, int solver) {
+    if (!ctx || solver < DSC_SOLVER_AUTO || solver > DSC_SOLVER_DENSE) return fail(ctx, DSC_ERR_INVALID_ARG, "dsc_set_solver");
+    ctx->solver = solver;
+    return DSC_OK;
+}
+
 extern "C" int dsc_set_early_reject(dsc_ctx* ctx, int n_levels, const double* rtol_loose, const double* rho_margin) {
     if (!ctx || n_levels < 0 || n_levels > 4 || (n_levels > 0 && (!rtol_loose || !rho_margin)))
         return fail(ctx, DSC_ERR_INVALID_ARG, "dsc_set_early_reject");
@@ -883,6 +894,54 @@ static int pcg_resume(dsc_ctx* ctx, const WeightsDev& W, double lambda, double r
     return DSC_OK;
 }
 
+// ---- dense direct solve of small problems (dsc_dense.cuh)
+static bool dense_active(const dsc_ctx* ctx) {
+    return ctx->solver == DSC_SOLVER_DENSE || (ctx->solver == DSC_SOLVER_AUTO && ctx->n <= DSC_DENSE_AUTO_MAX);
+}
+// once per LM iteration: H (dense, lower) and the right-hand side from the linearisation
+static int dense_prepare(dsc_ctx* ctx, const WeightsDev& W) {
+    const int n = ctx->n, m = 6 * n + 8;
+    if (m > ctx->dn_cap) {
+        CK(dev_alloc(ctx->dnH, (size_t)m * m)); CK(dev_alloc(ctx->dnA, (size_t)m * m));
+        CK(dev_alloc(ctx->dn_rhs, (size_t)m)); CK(dev_alloc(ctx->dn_sol, (size_t)m));
+        ctx->dn_cap = m;
+    }
+    CK(cudaMemsetAsync(ctx->dnH, 0, sizeof(double) * (size_t)m * m, ctx->stream));
+    dense_assemble_kernel<<<grid_threads(ctx, n), kThreads, 0, ctx->stream>>>(n, m, ctx->P, ctx->D, ctx->U, ctx->Je, ctx->sliceptr, ctx->ecol,
+                                                                            ctx->Gcur, ctx->pair, W, ctx->lin, ctx->dnH);
+    dense_rhs_kernel<<<grid_threads(ctx, m), kThreads, 0, ctx->stream>>>(n, ctx->b, ctx->lin, ctx->dn_rhs);
+    ctx->launches += 2;
+    CK(cudaGetLastError());
+    return DSC_OK;
+}
+// (H + lambda I) dx = b by a blocked Cholesky; DSC_ERR_PCG_BREAKDOWN when the matrix is not positive definite
+static int dense_solve(dsc_ctx* ctx, double lambda) {
+    const int n = ctx->n, m = 6 * n + 8;
+    CgVecs v = make_vecs(ctx);
+    CK(cudaMemsetAsync(ctx->errflag, 0, sizeof(int), ctx->stream));
+    dense_shift_kernel<<<grid_threads(ctx, (long long)m * m), kThreads, 0, ctx->stream>>>(m, ctx->dnH, lambda, ctx->dnA);
+    ctx->launches++;
+    for (int k0 = 0; k0 < m; k0 += kDenseNB) {
+        const int nb = std::min(kDenseNB, m - k0);
+        const int rest = m - (k0 + nb);
+        dense_panel_kernel<<<std::max(1, (rest + kPanelThreads - 1) / kPanelThreads), kPanelThreads, 0, ctx->stream>>>(m, k0, nb, ctx->dnA, ctx->errflag);
+        ctx->launches++;
+        if (rest > 0) {
+            const int nt = (rest + kDenseNB - 1) / kDenseNB;
+            dense_syrk_kernel<<<dim3(nt, nt), kDenseNB * 8, 0, ctx->stream>>>(m, k0, nb, ctx->dnA);
+            ctx->launches++;
+        }
+    }
+    dense_solve_kernel<<<1, 1024, sizeof(double) * (size_t)m, ctx->stream>>>(m, ctx->dnA, ctx->dn_rhs, ctx->dn_sol);
+    dense_scatter_kernel<<<grid_threads(ctx, m), kThreads, 0, ctx->stream>>>(n, ctx->dn_sol, v.x, v.xg);
+    ctx->launches += 2;
+    CK(cudaGetLastError());
+    int* hp = reinterpret_cast<int*>(ctx->h_pinned + 5 * kMaxBlocks);
+    CK(cudaMemcpyAsync(hp, ctx->errflag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return *hp ? DSC_ERR_PCG_BREAKDOWN : DSC_OK;
+}
+
 // trial state x (+) dx, its robust chi2 and the rho denominator dx.(lambda dx + b) + 1e-3
 static int eval_trial(dsc_ctx* ctx, const WeightsDev& W, double lambda, double* temp, double* scale) {
     int nbv = grid_threads(ctx, ctx->n);
@@ -915,6 +974,8 @@ extern "C" int dsc_optimize(dsc_ctx* ctx, const dsc_weights* w, int n_iters, dsc
     double lambda = 0.0, ni = 2.0;
     double current = 0.0;
     bool expect_long = true;
+    const bool dense = dense_active(ctx);
+    if (dense && ctx->n > DSC_DENSE_MAX) return fail(ctx, DSC_ERR_INVALID_ARG, "dense solver: too many correspondences (DSC_DENSE_MAX)");
     const bool early_log = std::getenv("DSC_EARLY_LOG") != nullptr;     // study aid: rho at every pause, predictor off
     int rc = DSC_OK;
     int nbv = grid_threads(ctx, ctx->n);
@@ -934,11 +995,13 @@ extern "C" int dsc_optimize(dsc_ctx* ctx, const dsc_weights* w, int n_iters, dsc
         double rho = 0.0;
         int q = 0;
         bool accepted = false;
+        if (dense) { rc = dense_prepare(ctx, W); if (rc) break; }
         do {
             int its = 0;
             cudaEventRecord(e_a, ctx->stream);
-            int prc = pcg_begin(ctx, W, lambda);
+            int prc = dense ? dense_solve(ctx, lambda) : pcg_begin(ctx, W, lambda);
             cudaEventRecord(e_b, ctx->stream);
+            if (dense) { cudaEventSynchronize(e_b); st.pcg_ms += ev_ms(e_a, e_b); }
             double temp = std::numeric_limits<double>::max(), scale = 1e-3;
             // Early rejection: the solve is paused at each loose tolerance, the trial is evaluated, and a step that
             // already fails the gain test by that level's margin is rejected without finishing the solve (only the
@@ -948,11 +1011,13 @@ extern "C" int dsc_optimize(dsc_ctx* ctx, const dsc_weights* w, int n_iters, dsc
             for (int level = 0; level <= ctx->early_levels && prc == DSC_OK && !rejected_early; ++level) {
                 const bool last = level == ctx->early_levels;
                 const double tol = last ? ctx->pcg.rtol : ctx->early_rtol[level];
-                if (!last && (!(tol > ctx->pcg.rtol) || (!expect_long && !early_log))) continue;
-                cudaEventRecord(e_a, ctx->stream);
-                prc = pcg_resume(ctx, W, lambda, tol, &its);
-                cudaEventRecord(e_b, ctx->stream); cudaEventSynchronize(e_b);
-                st.pcg_ms += ev_ms(e_a, e_b);
+                if (!last && (dense || !(tol > ctx->pcg.rtol) || (!expect_long && !early_log))) continue;
+                if (!dense) {
+                    cudaEventRecord(e_a, ctx->stream);
+                    prc = pcg_resume(ctx, W, lambda, tol, &its);
+                    cudaEventRecord(e_b, ctx->stream); cudaEventSynchronize(e_b);
+                    st.pcg_ms += ev_ms(e_a, e_b);
+                }
                 if (prc != DSC_OK) break;
                 cudaEventRecord(e_a, ctx->stream);
                 rc = eval_trial(ctx, W, lambda, &temp, &scale);
