@@ -438,3 +438,57 @@ def test_dense_and_pcg_agree_and_limits(pkg, ctx):
     ctx.set_solver(0)
     recs, st = ctx.optimize(_w(pkg, w), 1)
     assert st.total_pcg_iters > 0
+
+
+def _check_linearisation(pkg, ctx, p, w):
+    import scipy.sparse as sp
+    st = edges.state_of(p)
+    chi, parts = edges.total_cost(p, w, st, parts=True)
+    gchi, gparts = ctx.cost(_w(pkg, w))
+    assert gchi == pytest.approx(chi, rel=1e-11)
+    for a, b in zip(gparts, parts):
+        assert a == pytest.approx(b, rel=1e-10)
+    J, wt, e, chi_l = edges.linearize(p, w, st)
+    JW = J.T @ sp.diags(wt)
+    H = (JW @ J).tocsr()
+    b = -(JW @ e)
+    gb, ghd, gchi2 = ctx.debug_linearize(_w(pkg, w))
+    assert gchi2 == pytest.approx(chi, rel=1e-11)
+    np.testing.assert_allclose(gb, b, rtol=1e-9, atol=1e-9 * np.abs(b).max())
+    np.testing.assert_allclose(ghd, H.diagonal(), rtol=1e-9, atol=1e-12 * np.abs(H.diagonal()).max())
+    x = np.random.default_rng(0).standard_normal(H.shape[0])
+    lam = 1e-5 * np.abs(H.diagonal()).max()
+    y = ctx.debug_matvec(_w(pkg, w), lam, x)
+    yo = H @ x + lam * x
+    np.testing.assert_allclose(y, yo, rtol=1e-9, atol=1e-10 * np.abs(yo).max())
+    return wt
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("solver", [1, 2])
+def test_outliers_activate_the_huber_kernel(pkg, ctx, solver):
+    """Gross reprojection outliers (g2o RobustKernelHuber, delta = sqrt(100.991), g2oBundleAdjustment.cc:631,783-785):
+    rho'(chi2) < 1 on those edges must enter the cost, the gradient, the operator and the LM trace."""
+    sc = scenes.sheet_scene(500, seed=51)
+    p, keep = scenes.problem_from_scene(sc, "knn", 8)
+    rng = np.random.default_rng(5)
+    bad = rng.choice(p.n, p.n // 12, replace=False)
+    p.uv1 = p.uv1.copy(); p.uv2 = p.uv2.copy()
+    p.uv1[bad] += rng.uniform(25, 80, (len(bad), 2)).astype(np.float32) * rng.choice([-1, 1], (len(bad), 2)).astype(np.float32)
+    p.uv2[bad[::2]] += np.float32(40.0)
+    w = edges.Weights(rep=1.0, arap=20.0, depth_sigma=0.003)
+    _upload(pkg, ctx, p)
+    wt = _check_linearisation(pkg, ctx, p, w)
+    assert np.count_nonzero(wt[:4 * p.n] < 1.0) >= len(bad)          # the robust weight is active on the outliers
+    _compare_lm(pkg, ctx, p, w, 5, solver=solver)
+
+
+@pytest.mark.gpu
+def test_non_positive_depth_scale_branch(pkg, ctx):
+    """EdgeDepthCorrection multiplies the error by 500 when the scale vertex is <= 0 (g2oTypes.h:400-416)."""
+    sc = scenes.sheet_scene(300, seed=52)
+    p, keep = scenes.problem_from_scene(sc, "knn", 8)
+    p.s1 = -0.7
+    w = edges.Weights(rep=1.0, arap=20.0, depth_sigma=0.05)
+    _upload(pkg, ctx, p)
+    _check_linearisation(pkg, ctx, p, w)
