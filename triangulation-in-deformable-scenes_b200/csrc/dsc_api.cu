@@ -47,7 +47,7 @@ struct dsc_ctx {
 
     // ---- refinement problem
     int n = 0, cap = 0;
-    long long E = 0, ecap = 0;
+    long long E = 0;
     bool have_problem = false, have_graph = false, have_rot = false;
     PairDev pair{};
     double area = 1.0;
@@ -62,8 +62,6 @@ struct dsc_ctx {
     float4* uv = nullptr;
     double2* dm = nullptr;
     float2* isg = nullptr;
-    int *rowptr = nullptr, *col = nullptr;
-    double* wgt = nullptr;
     double* Je = nullptr;                 // per directed edge {u, m, g}
     // raw (caller order) device copies: the internal order is produced on the device (dsc_graph.cuh)
     float4* r_uv = nullptr; double2* r_dm = nullptr; float2* r_isg = nullptr;
@@ -89,10 +87,10 @@ struct dsc_ctx {
     double *gpart[2] = {nullptr, nullptr}, *dpart = nullptr, *bpart = nullptr;
     double* h_pinned = nullptr;           // pinned host scratch
     // pinned, persistent host staging of the graph / observation uploads (grown on demand)
-    int *hs_rp = nullptr, *hs_cl = nullptr, *hs_ecol = nullptr, *hs_sp = nullptr;
-    double *hs_ww = nullptr, *hs_ewgt = nullptr;
+    int *hs_rp = nullptr, *hs_cl = nullptr, *hs_sp = nullptr;
+    double* hs_ww = nullptr;
     float4* hs_uv = nullptr; double2* hs_dm = nullptr; float2* hs_isg = nullptr;
-    size_t hc_rp = 0, hc_cl = 0, hc_ecol = 0, hc_sp = 0, hc_ww = 0, hc_ewgt = 0, hc_uv = 0, hc_dm = 0, hc_isg = 0;
+    size_t hc_rp = 0, hc_cl = 0, hc_sp = 0, hc_ww = 0, hc_uv = 0, hc_dm = 0, hc_isg = 0;
     // ---- kNN graph builder (device CSR of the last dsc_knn_build)
     int knn_n = 0; long long knn_E = 0;
     int *knn_rowptr = nullptr, *knn_col = nullptr;
@@ -167,12 +165,6 @@ int grid_tiles(const dsc_ctx* c, long long n, int per_sm) {  // one block per ti
     long long nb = (n + kSortGroup - 1) / kSortGroup;
     return (int)std::max(1LL, std::min(nb, (long long)c->sms * per_sm));
 }
-int grid_groups(const dsc_ctx* c, long long n) {            // 8-lanes-per-item kernels
-    long long nb = (n + kGroups - 1) / kGroups;
-    long long cap = (long long)c->sms * 8;
-    return (int)std::max(1LL, std::min(nb, cap));
-}
-
 void fill_pair(const dsc_pair* in, PairDev& o) {
     o.cam1.model = in->cam1.model; o.cam2.model = in->cam2.model;
     for (int k = 0; k < 8; ++k) { o.cam1.p[k] = in->cam1.params[k]; o.cam2.p[k] = in->cam2.params[k]; }
@@ -283,7 +275,7 @@ extern "C" void dsc_destroy(dsc_ctx* ctx) {
     if (ctx->g_tmp) { cudaFree(ctx->g_tmp); ctx->g_tmp = nullptr; }
     dev_free(ctx->P); dev_free(ctx->Ptrial); dev_free(ctx->P0); dev_free(ctx->Q);
     dev_free(ctx->uv); dev_free(ctx->dm); dev_free(ctx->isg);
-    dev_free(ctx->rowptr); dev_free(ctx->col); dev_free(ctx->wgt); dev_free(ctx->Je); dev_free(ctx->ecol); dev_free(ctx->ewgt); dev_free(ctx->sliceptr); dev_free(ctx->spmv_part);
+    dev_free(ctx->Je); dev_free(ctx->ecol); dev_free(ctx->ewgt); dev_free(ctx->sliceptr); dev_free(ctx->spmv_part);
     dev_free(ctx->b); dev_free(ctx->D); dev_free(ctx->U); dev_free(ctx->Minv);
     for (auto& v : ctx->vec) dev_free(v);
     dev_free(ctx->knn_rowptr); dev_free(ctx->knn_col);
@@ -291,7 +283,7 @@ extern "C" void dsc_destroy(dsc_ctx* ctx) {
     dev_free(ctx->errflag); dev_free(ctx->part); dev_free(ctx->gpart[0]); dev_free(ctx->gpart[1]);
     dev_free(ctx->dpart); dev_free(ctx->bpart);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
-    for (void* q : {(void*)ctx->hs_rp, (void*)ctx->hs_cl, (void*)ctx->hs_ecol, (void*)ctx->hs_sp, (void*)ctx->hs_ww, (void*)ctx->hs_ewgt,
+    for (void* q : {(void*)ctx->hs_rp, (void*)ctx->hs_cl, (void*)ctx->hs_sp, (void*)ctx->hs_ww,
                     (void*)ctx->hs_uv, (void*)ctx->hs_dm, (void*)ctx->hs_isg, (void*)ctx->hs_x1, (void*)ctx->hs_x2}) if (q) cudaFreeHost(q);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
@@ -1210,7 +1202,7 @@ extern "C" int dsc_profile_kernels(dsc_ctx* ctx, const dsc_weights* w, int warm,
     double lambda = 1e-5 * hl.maxdiag;
     CgVecs v = make_vecs(ctx);
     double* Ginv = ctx->small + 48;
-    int nbv = grid_threads(ctx, n), nbs = grid_groups(ctx, n), nbp = grid_spmv(ctx, n);
+    int nbv = grid_threads(ctx, n), nbp = grid_spmv(ctx, n);
     CK(cudaMemsetAsync(ctx->errflag, 0, sizeof(int), ctx->stream));
     cg_init_kernel<<<nbv, kThreads, 0, ctx->stream>>>(n, ctx->b, ctx->D, lambda, ctx->lin, ctx->Minv, Ginv, ctx->errflag, v, ctx->gpart[0], ctx->ctl);
     ctx->launches += 2;

@@ -29,8 +29,6 @@
 namespace dsc {
 
 constexpr int kThreads = 256;
-constexpr int kLanes = 8;                       // lanes per correspondence
-constexpr int kGroups = kThreads / kLanes;      // correspondences per block-iteration
 constexpr int kMaxBlocks = 2048;
 constexpr int kSortGroup = 512;                 // rows are degree-sorted inside groups of this many (host, dsc_set_graph)
 
@@ -82,12 +80,6 @@ DSC_D D3 qrotT(const double* q, D3 v) {
     D3 qv = d3(-q[0], -q[1], -q[2]);
     D3 t = 2.0 * cross(qv, v);
     return v + q[3] * t + cross(qv, t);
-}
-DSC_D double group_sum(double v) {                  // sum over the 8 lanes of a correspondence
-    v += __shfl_xor_sync(0xffffffffu, v, 4);
-    v += __shfl_xor_sync(0xffffffffu, v, 2);
-    v += __shfl_xor_sync(0xffffffffu, v, 1);
-    return v;
 }
 DSC_D double warp_sum(double v) {
 #pragma unroll
