@@ -219,7 +219,15 @@ def test_error_behaviour(pkg, ctx):
     bad_col[0] = (bad_col[0] + 7) % p.n       # breaks symmetry
     with pytest.raises(pkg.DscError) as e:
         ctx.set_graph(g.rowptr, bad_col, g.w, g.area, g.n_triangles)
-    assert e.value.status == -7
+    assert e.value.status == -7 and "symmetric" in str(e.value)
+    for breaker, word in ((lambda c, ww: c.__setitem__(3, -1), "range"), (lambda c, ww: c.__setitem__(g.rowptr[5], 5), "self loop"),
+                          (lambda c, ww: c.__setitem__(g.rowptr[9] + 1, c[g.rowptr[9]]), "duplicate"),
+                          (lambda c, ww: ww.__setitem__(2, ww[2] + 1.0), "weights")):
+        c2, w2 = g.col.copy(), g.w.copy()
+        breaker(c2, w2)
+        with pytest.raises(pkg.DscError) as e:
+            ctx.set_graph(g.rowptr, c2, w2, g.area, g.n_triangles)
+        assert e.value.status == -7 and word in str(e.value), str(e.value)
     ctx.set_graph(g.rowptr, g.col, g.w, g.area, g.n_triangles)
     ctx.compute_rotations()
     with pytest.raises(pkg.DscError) as e:

@@ -503,30 +503,6 @@ extern "C" int dsc_set_graph(dsc_ctx* ctx, int n, const int32_t* rowptr, const i
     long long E = n > 0 ? rowptr[n] : 0;
     if (rowptr[0] != 0 || E < 0 || (E > 0 && (!col || !w))) return fail(ctx, DSC_ERR_GRAPH, "rowptr");
     for (int i = 0; i < n; ++i) if (rowptr[i + 1] < rowptr[i]) return fail(ctx, DSC_ERR_GRAPH, "rowptr not monotone");
-    // symmetric, in range, no self loops, symmetric weights (the reference's mesh adjacency always is)
-    if (validate) {
-        std::vector<long long> key((size_t)E);
-        for (int i = 0; i < n; ++i)
-            for (int e = rowptr[i]; e < rowptr[i + 1]; ++e) {
-                int j = col[e];
-                if (j < 0 || j >= n || j == i) return fail(ctx, DSC_ERR_GRAPH, "column index out of range or self loop");
-                key[e] = (long long)i * n + j;
-            }
-        std::vector<size_t> order((size_t)E);
-        for (size_t e = 0; e < (size_t)E; ++e) order[e] = e;
-        std::sort(order.begin(), order.end(), [&](size_t a, size_t b2) { return key[a] < key[b2]; });
-        for (size_t k = 1; k < (size_t)E; ++k)
-            if (key[order[k]] == key[order[k - 1]]) return fail(ctx, DSC_ERR_GRAPH, "duplicate edge");
-        for (int i = 0; i < n; ++i)
-            for (int e = rowptr[i]; e < rowptr[i + 1]; ++e) {
-                long long rk = (long long)col[e] * n + i;
-                size_t lo = 0, hi = (size_t)E;
-                while (lo < hi) { size_t mid = (lo + hi) / 2; if (key[order[mid]] < rk) lo = mid + 1; else hi = mid; }
-                if (lo >= (size_t)E || key[order[lo]] != rk) return fail(ctx, DSC_ERR_GRAPH, "graph is not symmetric");
-                if (w[order[lo]] != w[e]) return fail(ctx, DSC_ERR_GRAPH, "edge weights are not symmetric");
-            }
-    }
-    lap("validate");
     // ---- raw CSR to the device through pinned staging (the copy of chunk c overlaps the packing of chunk c + 1)
     if ((size_t)n + 1 > ctx->g_ncap) {
         size_t N = (size_t)n + 1, NS = ((size_t)n + 31) / 32 + 2;
@@ -553,6 +529,19 @@ extern "C" int dsc_set_graph(dsc_ctx* ctx, int n, const int32_t* rowptr, const i
         }
     }
     lap("csr staging");
+    // symmetric, in range, no self loops, no duplicates, symmetric weights (the reference's mesh adjacency always is)
+    if (validate && n > 0) {
+        CK(cudaMemsetAsync(ctx->errflag, 0, sizeof(int), ctx->stream));
+        validate_graph_kernel<<<grid_threads(ctx, n), kThreads, 0, ctx->stream>>>(n, ctx->g_rp0, ctx->g_col0, ctx->g_w0, ctx->errflag);
+        ctx->launches++;
+        int* hp = reinterpret_cast<int*>(ctx->h_pinned + 5 * kMaxBlocks);
+        CK(cudaMemcpyAsync(hp, ctx->errflag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        static const char* const what[] = {"", "graph is not symmetric", "edge weights are not symmetric", "duplicate edge",
+                                           "column index out of range or self loop"};
+        if (*hp) return fail(ctx, DSC_ERR_GRAPH, what[std::min(*hp, 4)]);
+        lap("validate");
+    }
     // ---- internal numbering on the device: Morton order of KF1's world (x, y) -- the plane the reference triangulates
     // in -- then, for the sliced ELL, a stable sort by degree (descending) inside every group of kSortGroup rows
     const int nbv = grid_threads(ctx, std::max(n, 1));

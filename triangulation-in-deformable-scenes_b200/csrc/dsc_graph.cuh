@@ -23,6 +23,28 @@ DSC_HD unsigned part1by1_dev(unsigned v) {
     return v;
 }
 
+// Graph checks of dsc_set_graph (the reference's mesh adjacency always passes them): column in range, no self loop, no
+// duplicate edge, the reverse edge exists and carries the same weight.  err = the largest code found (the more
+// fundamental defect wins): 4 out of range / self loop, 3 duplicate edge, 2 weights not symmetric, 1 not symmetric.
+// Rows need not be sorted.
+__global__ void validate_graph_kernel(int n, const int* __restrict__ rowptr0, const int* __restrict__ col0,
+                                      const double* __restrict__ w0, int* __restrict__ err) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        int code = 0;
+        const int e0 = rowptr0[i], e1 = rowptr0[i + 1];
+        for (int e = e0; e < e1; ++e) {
+            const int j = col0[e];
+            if (j < 0 || j >= n || j == i) { code = max(code, 4); continue; }
+            for (int q = e0; q < e; ++q) if (col0[q] == j) code = max(code, 3);
+            int found = -1;
+            for (int q = rowptr0[j]; q < rowptr0[j + 1]; ++q) if (col0[q] == i) { found = q; break; }
+            if (found < 0) code = max(code, 1);
+            else if (w0[found] != w0[e]) code = max(code, 2);
+        }
+        if (code) atomicMax(err, code);
+    }
+}
+
 // key = morton(x, y) << 32 | caller index  (the same key the host version sorted)
 __global__ void morton_key_kernel(int n, const float* __restrict__ X1 /* [n][3], caller order */, float xmin, float sx,
                                   float ymin, float sy, unsigned long long* __restrict__ key) {
