@@ -108,7 +108,7 @@ def prepare(pkg, ctx, sc, args):
     return prob
 
 
-def upload(ctx, prob, flags=3):
+def upload(ctx, prob, flags=1):
     ctx.problem_upload(prob["pair"], prob["X1"], prob["X2"], prob["uv1"], prob["uv2"], prob["d1"], prob["d2"],
                        scale1=prob["s1"], scale2=prob["s2"])
     ctx.set_graph(prob["rowptr"], prob["col"], prob["w"], prob["area"], prob["ntri"], flags)
