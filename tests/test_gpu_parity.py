@@ -500,3 +500,37 @@ def test_non_positive_depth_scale_branch(pkg, ctx):
     w = edges.Weights(rep=1.0, arap=20.0, depth_sigma=0.05)
     _upload(pkg, ctx, p)
     _check_linearisation(pkg, ctx, p, w)
+
+
+@pytest.mark.gpu
+def test_cluster_pcg_matches_the_per_iteration_kernels(pkg):
+    """Small problems run the whole PCG in one thread-block-cluster launch (dsc_small.cuh); DSC_NO_CLUSTER_PCG=1 keeps
+    the per-iteration kernels of the 1M path.  Same algorithm, different partial-sum partition: the traces agree to
+    rounding, and both agree with the oracle (the other tests)."""
+    import os
+    sc = scenes.tube_scene(2500, seed=61, depth_sigma=0.0003)
+    p, keep = scenes.problem_from_scene(sc, "knn", 8, min_cos=0.99999)
+    w = edges.Weights(rep=1.0, arap=1.0e7, depth_sigma=0.0003)
+    res = []
+    for env in (None, "1"):
+        if env is None:
+            os.environ.pop("DSC_NO_CLUSTER_PCG", None)
+        else:
+            os.environ["DSC_NO_CLUSTER_PCG"] = env
+        try:
+            with pkg.Context(0) as c:
+                _upload(pkg, c, p)
+                c.set_solver(1)
+                c.set_pcg(rtol=1e-12, max_iters=20000, check_every=64)
+                c.set_early_reject((1e-3, 1e-4), (1.0, 0.5))
+                recs, st = c.optimize(_w(pkg, w), 4)
+                res.append((recs, st, c.download()))
+        finally:
+            os.environ.pop("DSC_NO_CLUSTER_PCG", None)
+    (r0, s0, o0), (r1, s1, o1) = res
+    assert s0.kernel_launches < s1.kernel_launches / 5            # one launch per solve instead of two per iteration
+    assert [r.trials for r in r0] == [r.trials for r in r1]
+    for a, b in zip(r0, r1):
+        assert a.chi2_after == pytest.approx(b.chi2_after, rel=1e-9)
+    scale = np.abs(o0["X1d"]).max()
+    assert np.abs(o0["X1d"] - o1["X1d"]).max() <= 1e-8 * scale

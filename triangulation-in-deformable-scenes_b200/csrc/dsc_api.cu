@@ -12,6 +12,7 @@
 #include "dsc_knn.cuh"
 #include "dsc_graph.cuh"
 #include "dsc_dense.cuh"
+#include "dsc_small.cuh"
 
 #include <algorithm>
 #include <chrono>
@@ -97,6 +98,7 @@ struct dsc_ctx {
     dsc_pcg_params pcg{1e-10, 4000, 32};
     struct IterGraph { cudaGraphExec_t exec = nullptr; const double* P = nullptr; WeightsDev W{}; } graphs[2];   // per state buffer
     bool use_graphs = true;
+    int small_cluster = 0;                           // CTAs of the one-launch PCG of small problems (0 = not available)
     int solver = DSC_SOLVER_AUTO;                    // dense Cholesky for small problems, PCG above (dsc_set_solver)
     double *dnH = nullptr, *dnA = nullptr, *dn_rhs = nullptr, *dn_sol = nullptr;
     int dn_cap = 0;
@@ -253,6 +255,11 @@ extern "C" int dsc_create(int device, dsc_ctx** out) {
     if (cudaMallocHost(&ctx->h_pinned, sizeof(double) * kMaxBlocks * kLinPart) != cudaSuccess) return bail(DSC_ERR_ALLOC);
     cudaMemset(ctx->errflag, 0, sizeof(int));
     ctx->use_graphs = std::getenv("DSC_NO_GRAPHS") == nullptr;
+    if (std::getenv("DSC_NO_CLUSTER_PCG") == nullptr) {
+        // the one-launch PCG of small problems needs a cluster of 16 (non-portable) or 8 CTAs of 256 threads
+        ctx->small_cluster = cudaFuncSetAttribute(pcg_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess ? kSmallCluster : 8;
+        cudaGetLastError();
+    }
     if (cudaFuncSetAttribute(rotations_ell_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWinBytes) != cudaSuccess ||
         cudaFuncSetAttribute(cost_ell_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWinBytes) != cudaSuccess ||
         cudaFuncSetAttribute(cg_spmv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSpmvSmem) != cudaSuccess ||
@@ -782,7 +789,40 @@ static int run_linearize(dsc_ctx* ctx, const WeightsDev& W, LinGlobal* hlin) {
 // PCG solve of (H + lambda I) dx = b in two entry points so that a solve can be paused at a loose tolerance,
 // inspected (trial cost) and resumed to the tight one: begin = preconditioner + r0/z0 + first operator
 // application; resume = iterate until sqrt(r.z / r0.z0) <= rtol, breakdown or max_iters.
+static bool small_active(const dsc_ctx* ctx) { return ctx->small_cluster > 0 && ctx->n <= kSmallMaxRows; }
+
+// one launch = the whole solve (or its continuation after a pause) by a single thread-block cluster (dsc_small.cuh)
+static int small_launch(dsc_ctx* ctx, const WeightsDev& W, int fresh) {
+    CgVecs v = make_vecs(ctx);
+    double* Ginv = ctx->small + 48;
+    for (;;) {
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(ctx->small_cluster); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = 0; cfg.stream = ctx->stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = ctx->small_cluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        cudaError_t e = cudaLaunchKernelEx(&cfg, pcg_cluster_kernel, ctx->n, fresh, ctx->pcg.max_iters, (const double*)ctx->P, (const double*)ctx->Je,
+                                           (const double*)ctx->U, (const int*)ctx->sliceptr, (const int*)ctx->ecol, (const Globals*)ctx->Gcur, ctx->pair, W,
+                                           (const double*)ctx->b, (const double*)ctx->D, (const LinGlobal*)ctx->lin, ctx->Minv, Ginv, ctx->errflag, v,
+                                           ctx->gpart[0], ctx->gpart[1], ctx->dpart, ctx->bpart, ctx->ctl);
+        if (e == cudaSuccess) break;
+        cudaGetLastError();
+        if (fresh && ctx->small_cluster > 8) { ctx->small_cluster = 8; continue; }      // 16 CTAs not schedulable here: use the portable size
+        return fail(ctx, DSC_ERR_CUDA, std::string("pcg_cluster_kernel -> ") + cudaGetErrorString(e));
+    }
+    ctx->launches++;
+    return DSC_OK;
+}
+
 static int pcg_begin(dsc_ctx* ctx, const WeightsDev& W, double lambda) {
+    if (small_active(ctx)) {                           // the cluster kernel starts the solve itself
+        CK(cudaMemsetAsync(ctx->errflag, 0, sizeof(int), ctx->stream));
+        ctl_set_kernel<<<1, 1, 0, ctx->stream>>>(ctx->ctl, lambda, 1, 0.0, 0, 0);
+        ctx->launches++;
+        CK(cudaGetLastError());
+        return DSC_OK;
+    }
     int n = ctx->n;
     int nbv = grid_threads(ctx, (long long)n);
     int nbs = grid_spmv(ctx, n);
@@ -840,6 +880,16 @@ static int pcg_resume(dsc_ctx* ctx, const WeightsDev& W, double lambda, double r
     // resuming after a pause (k > 0): the converged latch belongs to the looser tolerance
     ctl_set_kernel<<<1, 1, 0, ctx->stream>>>(ctx->ctl, 0.0, 0, rtol2, 1, k > 0 ? 1 : 0);
     CgControl hc{};
+    if (small_active(ctx)) {
+        int src = small_launch(ctx, W, k == 0 ? 1 : 0);
+        if (src) return src;
+        CgControl* hp = reinterpret_cast<CgControl*>(ctx->h_pinned + 5 * kMaxBlocks);
+        CK(cudaMemcpyAsync(hp, ctx->ctl, sizeof(CgControl), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        hc = *hp;
+        *k_io = hc.iters;
+        return hc.breakdown ? DSC_ERR_PCG_BREAKDOWN : DSC_OK;
+    }
     int poll = std::min(k == 0 ? 18 : 16, ctx->pcg.check_every);   // first poll early (well-damped solves need ~10 iterations): 2 direct + one graph
     while (k < ctx->pcg.max_iters) {
         int chunk = std::min(poll, ctx->pcg.max_iters - k);

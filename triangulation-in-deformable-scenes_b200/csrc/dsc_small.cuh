@@ -1,0 +1,285 @@
+// dsc_small.cuh -- the whole PCG solve of a SMALL problem in ONE launch: a single thread-block cluster runs all
+// iterations, its CTAs meeting at the hardware cluster barrier twice per iteration instead of the host launching two
+// kernels per iteration.  Between the dense path (<= 600 correspondences) and ~16 k correspondences -- the sizes of the
+// reference's real sequences and of config 5's pairs -- a PCG iteration of the large-problem kernels is ~15 us of pure
+// launch / grid-drain latency for ~1 us of work; here it costs two cluster barriers.
+// Same algorithm and the same arithmetic as cg_init / cg_update / cg_spmv (Chronopoulos-Gear PCG, block-Jacobi 6x6 +
+// exact 8x8 preconditioner, the ARAP operator applied from the per-edge Jacobian records); everything the cluster
+// itself writes during the solve is read back with L2 loads (__ldcg), constants with the read-only path.
+#pragma once
+#include <cooperative_groups.h>
+
+#include "dsc_kernels.cuh"
+
+namespace dsc {
+
+namespace cg = cooperative_groups;
+
+constexpr int kSmallMaxRows = 8192;          // above this the per-iteration kernels of the large path are faster (measured)
+constexpr int kSmallBatch = 4;              // ELL columns whose loads are in flight together
+constexpr int kSmallCluster = 16;            // CTAs per cluster (non-portable size; 8 is tried if 16 cannot launch)
+
+DSC_D void load6_l2(const double* V, int i, D3& a, D3& b) {
+    const double2* p = reinterpret_cast<const double2*>(V) + 3 * (size_t)i;
+    const double2 u = __ldcg(p), v = __ldcg(p + 1), w = __ldcg(p + 2);
+    a = d3(u.x, u.y, v.x); b = d3(v.y, w.x, w.y);
+}
+// fixed-order sum of part[0 .. nb) (stride), nb <= kSmallCluster: every thread does it itself
+DSC_D double sum_small(const double* part, int nb, int stride) {
+    double s = 0.0;
+    for (int i = 0; i < nb; ++i) s += __ldcg(part + (size_t)i * stride);
+    return s;
+}
+
+// fresh = 1: start a solve (preconditioner, r = b, z = M^-1 r, first operator application); fresh = 0: resume the solve
+// whose state is in the vectors and in ctl (pause / resume of the early rejection).  Runs until converged
+// (gamma <= rtol2 gamma0), breakdown, or max_iters updates in total.  gpart[2][cs], dpart[cs], bpart[cs][8].
+__global__ void __launch_bounds__(kThreads, 1)
+pcg_cluster_kernel(int n, int fresh, int max_iters, const double* __restrict__ P, const double* __restrict__ Je,
+                   const double* __restrict__ U, const int* __restrict__ sliceptr, const int* __restrict__ ecol,
+                   const Globals* __restrict__ Gp, const __grid_constant__ PairDev pr, const __grid_constant__ WeightsDev W,
+                   const double* __restrict__ b, const double* __restrict__ D, const LinGlobal* __restrict__ lin,
+                   double* Minv, double* Ginv, int* err, CgVecs v, double* gpart0, double* gpart1, double* dpart, double* bpart,
+                   CgControl* ctl) {
+    cg::cluster_group cluster = cg::this_cluster();
+    const int rank = (int)cluster.block_rank(), cs = (int)cluster.num_blocks();
+    __shared__ double sm[9 * (kThreads / 32)];
+    __shared__ double Rg[9];
+    __shared__ double zgs[8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = kThreads / 32;
+    const int nslices = (n + 31) / 32;
+    if (threadIdx.x < 9) Rg[threadIdx.x] = Gp->Rg[threadIdx.x];
+    const double lambda = __ldcg(&ctl->lambda);
+    const double rtol2 = __ldcg(&ctl->rtol2);
+    double* gp[2] = {gpart0, gpart1};
+    __syncthreads();
+
+    // w = (H + lambda I) z and the partial sums of z.w and of the 8 global rows (see cg_spmv_kernel for the formulas)
+    auto spmv = [&]() {
+        if (threadIdx.x < 8) zgs[threadIdx.x] = __ldcg(v.zg + threadIdx.x);
+        __syncthreads();
+        const D3 zw = d3(zgs[0], zgs[1], zgs[2]);
+        const D3 zv2 = d3(2.0 * zgs[3], 2.0 * zgs[4], 2.0 * zgs[5]);
+        double acc[9];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) acc[k] = 0.0;
+        for (int sl = rank * wpb + warp; sl < nslices; sl += cs * wpb) {
+            const int i = sl * 32 + lane;
+            const bool act = i < n;
+            const int ic = act ? i : n - 1;
+            D3 zi1, zi2;
+            load6_l2(v.z, ic, zi1, zi2);
+            const double4 xi = ldg256(reinterpret_cast<const double4*>(P) + ic);
+            const D3 X1i = d3(xi.x, xi.y, xi.z);
+            D3 Am = d3(0, 0, 0), Ag = d3(0, 0, 0), Au = d3(0, 0, 0);
+            const int b0 = __ldg(sliceptr + sl), b1 = __ldg(sliceptr + sl + 1);
+            // kSmallBatch ELL columns at a time: all their index / record loads are issued together, then all their
+            // gathers -- with 8 warps per SM the loop is bound by L2 latency, not by throughput
+            for (int bk = b0; bk < b1; bk += kSmallBatch) {
+                int jq[kSmallBatch];
+                D3 uq[kSmallBatch], mq[kSmallBatch], gq[kSmallBatch];
+#pragma unroll
+                for (int q = 0; q < kSmallBatch; ++q) {
+                    const bool ok = bk + q < b1;
+                    const size_t blk = ok ? (size_t)(bk + q) : (size_t)b0;
+                    const double* jb = Je + blk * 288 + lane;
+                    jq[q] = ok ? __ldg(ecol + blk * 32 + lane) : ic;
+                    const double f = ok ? 1.0 : 0.0;                       // columns past the end contribute exactly 0
+                    uq[q] = f * d3(__ldg(jb), __ldg(jb + 32), __ldg(jb + 64));
+                    mq[q] = f * d3(__ldg(jb + 96), __ldg(jb + 128), __ldg(jb + 160));
+                    gq[q] = f * d3(__ldg(jb + 192), __ldg(jb + 224), __ldg(jb + 256));
+                }
+                D3 zq1[kSmallBatch], zq2[kSmallBatch], xq[kSmallBatch];
+#pragma unroll
+                for (int q = 0; q < kSmallBatch; ++q) {
+                    load6_l2(v.z, jq[q], zq1[q], zq2[q]);
+                    const double4 xj = ldg256(reinterpret_cast<const double4*>(P) + (size_t)jq[q]);
+                    xq[q] = d3(xj.x, xj.y, xj.z);
+                }
+#pragma unroll
+                for (int q = 0; q < kSmallBatch; ++q) {
+                    const D3 S1 = X1i + xq[q];
+                    const D3 t = mul(Rg, zi2 + zq2[q]) - (zi1 + zq1[q]) + cross(zw, S1) - zv2;
+                    const double s = dot(uq[q], zi2 - zq2[q]) - dot(mq[q], zi1 - zq1[q]) + 2.0 * dot(gq[q], t);
+                    const double w2 = 2.0 * W.arap_info * s;
+                    Am = Am + w2 * mq[q]; Ag = Ag + w2 * gq[q]; Au = Au + w2 * uq[q];
+                }
+            }
+            if (act) {
+                const double* Up = U + ((size_t)(i >> 5) * kURec) * 32 + lane;
+                double uu[kURec];
+#pragma unroll
+                for (int k = 0; k < kURec; ++k) uu[k] = __ldg(Up + k * 32);
+                const D3 rg = mulT(Rg, Ag);
+                double out[6] = {-Am.x - 2.0 * Ag.x, -Am.y - 2.0 * Ag.y, -Am.z - 2.0 * Ag.z,
+                                 Au.x + 2.0 * rg.x, Au.y + 2.0 * rg.y, Au.z + 2.0 * rg.z};
+                const double zi[6] = {zi1.x, zi1.y, zi1.z, zi2.x, zi2.y, zi2.z};
+#pragma unroll
+                for (int cam = 0; cam < 2; ++cam) {
+                    const double* R = cam == 0 ? pr.R1 : pr.R2;
+                    const double nz = R[6] * zi[cam * 3] + R[7] * zi[cam * 3 + 1] + R[8] * zi[cam * 3 + 2];
+                    const double kd = uu[12 + cam];
+#pragma unroll
+                    for (int r = 0; r < 3; ++r) {
+                        double sum = 0.0;
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) sum += (r <= c ? uu[cam * 6 + pk<3>(r, c)] : uu[cam * 6 + pk<3>(c, r)]) * zi[cam * 3 + c];
+                        out[cam * 3 + r] += sum + kd * R[6 + r] * zgs[6 + cam];
+                    }
+                    acc[6 + cam] += kd * nz;
+                }
+                double dl = 0.0;
+#pragma unroll
+                for (int k = 0; k < 6; ++k) { out[k] += lambda * zi[k]; dl += zi[k] * out[k]; }
+                acc[8] += dl;
+                const D3 cx = cross(X1i, Ag);
+                acc[0] += 2.0 * cx.x; acc[1] += 2.0 * cx.y; acc[2] += 2.0 * cx.z;
+                acc[3] -= 2.0 * Ag.x; acc[4] -= 2.0 * Ag.y; acc[5] -= 2.0 * Ag.z;
+                store6(v.w, i, d3(out[0], out[1], out[2]), d3(out[3], out[4], out[5]));
+            }
+        }
+        block_reduce<9>(acc, sm);
+        if (threadIdx.x == 0) {
+            double dl = acc[8];
+            for (int k = 0; k < 8; ++k) { bpart[8 * rank + k] = acc[k]; dl += zgs[k] * acc[k]; }
+            if (rank == 0)
+                for (int k = 0; k < 8; ++k) dl += zgs[k] * ((k >= 6 ? lin->C[k * 8 + k] : 0.0) + lambda) * zgs[k];
+            dpart[rank] = dl;
+        }
+    };
+
+    int k = __ldcg(&ctl->iters);                      // updates done so far
+    if (fresh) {
+        // preconditioner + start: Minv, r = b, z = M^-1 r, gamma partial -> gp[0]
+        double g[1] = {0.0};
+        for (int i = rank * kThreads + threadIdx.x; i < n; i += cs * kThreads) {
+            double r[6], z[6], M[21];
+            D3 a, c;
+            load6(b, i, a, c);
+            r[0] = a.x; r[1] = a.y; r[2] = a.z; r[3] = c.x; r[4] = c.y; r[5] = c.z;
+            precond_block(D, i, lambda, Minv, err, M);
+#pragma unroll
+            for (int q = 0; q < 6; ++q) {
+                double sacc = 0.0;
+#pragma unroll
+                for (int t = 0; t < 6; ++t) sacc += (q <= t ? M[pk<6>(q, t)] : M[pk<6>(t, q)]) * r[t];
+                z[q] = sacc;
+            }
+            store6(v.r, i, a, c);
+            store6(v.z, i, d3(z[0], z[1], z[2]), d3(z[3], z[4], z[5]));
+#pragma unroll
+            for (int t = 0; t < 6; ++t) g[0] += r[t] * z[t];
+        }
+        if (rank == 0 && threadIdx.x == 0) {
+            precond_global(lin, lambda, Ginv, err);
+            for (int a = 0; a < 8; ++a) {
+                double s = 0.0;
+                for (int c = 0; c < 8; ++c) s += Ginv[a * 8 + c] * lin->bg[c];
+                v.rg[a] = lin->bg[a]; v.zg[a] = s; v.xg[a] = 0.0; v.pg[a] = 0.0; v.sg[a] = 0.0;
+                g[0] += lin->bg[a] * s;
+            }
+            ctl->iters = 0; ctl->converged = 0; ctl->breakdown = 0;
+            ctl->sc[0].gamma_prev = 1.0; ctl->sc[0].alpha_prev = 1.0;
+            ctl->sc[1].gamma_prev = 1.0; ctl->sc[1].alpha_prev = 1.0;
+        }
+        block_reduce<1>(g, sm);
+        if (threadIdx.x == 0) gp[0][rank] = g[0];
+        k = 0;
+        cluster.sync();
+        spmv();
+        cluster.sync();
+    }
+
+    // iterations: update (Chronopoulos-Gear step), barrier, operator, barrier
+    double gamma0 = fresh ? 0.0 : __ldcg(&ctl->gamma0);
+    double gprev = fresh ? 1.0 : __ldcg(&ctl->sc[(k & 1) ^ 1].gamma_prev);
+    double aprev = fresh ? 1.0 : __ldcg(&ctl->sc[(k & 1) ^ 1].alpha_prev);
+    int converged = 0, breakdown = 0;
+    while (k < max_iters) {
+        const int par = k & 1;
+        const bool first = k == 0;
+        const double gamma = sum_small(gp[par], cs, 1);
+        const double delta = sum_small(dpart, cs, 1);
+        if (first) gamma0 = gamma;
+        if (!first && gamma <= rtol2 * gamma0) { converged = 1; break; }      // the same sums in every thread: uniform
+        const double beta = first ? 0.0 : gamma / gprev;
+        const double denom = first ? delta : delta - beta * gamma / aprev;
+        const double alpha = gamma / denom;
+        if (!(denom > 0.0) || !isfinite(alpha)) { breakdown = 1; break; }
+        double g[1] = {0.0};
+        for (int i = rank * kThreads + threadIdx.x; i < n; i += cs * kThreads) {
+            D3 z1, z2, w1, w2, p1, p2, s1, s2, x1, x2, r1, r2;
+            load6_l2(v.z, i, z1, z2); load6_l2(v.w, i, w1, w2); load6_l2(v.r, i, r1, r2);
+            if (first) {
+                p1 = z1; p2 = z2; s1 = w1; s2 = w2;
+                x1 = alpha * p1; x2 = alpha * p2;
+            } else {
+                load6_l2(v.p, i, p1, p2); load6_l2(v.s, i, s1, s2); load6_l2(v.x, i, x1, x2);
+                p1 = z1 + beta * p1; p2 = z2 + beta * p2;
+                s1 = w1 + beta * s1; s2 = w2 + beta * s2;
+                x1 = x1 + alpha * p1; x2 = x2 + alpha * p2;
+            }
+            r1 = r1 - alpha * s1; r2 = r2 - alpha * s2;
+            double r[6] = {r1.x, r1.y, r1.z, r2.x, r2.y, r2.z}, zn[6], M[21];
+            const double* Mp = blk21(Minv, i);
+#pragma unroll
+            for (int q = 0; q < 21; ++q) M[q] = __ldcg(Mp + q * 32);
+#pragma unroll
+            for (int a = 0; a < 6; ++a) {
+                double sacc = 0.0;
+#pragma unroll
+                for (int c = 0; c < 6; ++c) sacc += (a <= c ? M[pk<6>(a, c)] : M[pk<6>(c, a)]) * r[c];
+                zn[a] = sacc;
+            }
+            store6(v.p, i, p1, p2); store6(v.s, i, s1, s2); store6(v.x, i, x1, x2); store6(v.r, i, r1, r2);
+            store6(v.z, i, d3(zn[0], zn[1], zn[2]), d3(zn[3], zn[4], zn[5]));
+#pragma unroll
+            for (int q = 0; q < 6; ++q) g[0] += r[q] * zn[q];
+        }
+        if (rank == 0) {
+            __shared__ double wg[8], rgn[8];
+            __syncthreads();
+            if (threadIdx.x < 8) {
+                const int q = threadIdx.x;
+                double s = 0.0;
+                for (int c = 0; c < cs; ++c) s += __ldcg(bpart + 8 * c + q);
+                const double d = (q >= 6 ? lin->C[q * 8 + q] : 0.0) + lambda;
+                const double zq = __ldcg(v.zg + q);
+                wg[q] = s + d * zq;
+                const double pg = first ? zq : zq + beta * __ldcg(v.pg + q);
+                const double sg = first ? wg[q] : wg[q] + beta * __ldcg(v.sg + q);
+                v.pg[q] = pg; v.sg[q] = sg;
+                v.xg[q] = (first ? 0.0 : __ldcg(v.xg + q)) + alpha * pg;
+                const double rr = __ldcg(v.rg + q) - alpha * sg;
+                v.rg[q] = rr; rgn[q] = rr;
+            }
+            __syncthreads();
+            if (threadIdx.x < 8) {
+                const int q = threadIdx.x;
+                double s = 0.0;
+                for (int c = 0; c < 8; ++c) s += __ldcg(Ginv + q * 8 + c) * rgn[c];
+                v.zg[q] = s;
+                wg[q] = s * rgn[q];
+            }
+            __syncthreads();
+            if (threadIdx.x == 0)
+                for (int q = 0; q < 8; ++q) g[0] += wg[q];
+        }
+        block_reduce<1>(g, sm);
+        if (threadIdx.x == 0) gp[par ^ 1][rank] = g[0];
+        gprev = gamma; aprev = alpha;
+        ++k;
+        cluster.sync();
+        spmv();
+        cluster.sync();
+    }
+    if (rank == 0 && threadIdx.x == 0) {
+        ctl->iters = k;
+        ctl->gamma0 = gamma0;
+        ctl->sc[(k & 1) ^ 1].gamma_prev = gprev; ctl->sc[(k & 1) ^ 1].alpha_prev = aprev;
+        if (converged) ctl->converged = 1;
+        if (breakdown) ctl->breakdown = 1;
+    }
+}
+
+}  // namespace dsc
