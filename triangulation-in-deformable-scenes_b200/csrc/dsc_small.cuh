@@ -24,10 +24,13 @@ DSC_D void load6_l2(const double* V, int i, D3& a, D3& b) {
     const double2 u = __ldcg(p), v = __ldcg(p + 1), w = __ldcg(p + 2);
     a = d3(u.x, u.y, v.x); b = d3(v.y, w.x, w.y);
 }
-// fixed-order sum of part[0 .. nb) (stride), nb <= kSmallCluster: every thread does it itself
-DSC_D double sum_small(const double* part, int nb, int stride) {
-    double s = 0.0;
-    for (int i = 0; i < nb; ++i) s += __ldcg(part + (size_t)i * stride);
+// sum of part[0 .. nb), nb <= 32, by every warp on its own: lane c loads entry c (one L2 round trip for all of them,
+// a serial loop would pay one per entry), then a fixed butterfly: the same result in every lane of every warp and CTA
+DSC_D double sum_small(const double* part, int nb) {
+    const int lane = threadIdx.x & 31;
+    double s = lane < nb ? __ldcg(part + lane) : 0.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     return s;
 }
 
@@ -198,8 +201,8 @@ pcg_cluster_kernel(int n, int fresh, int max_iters, const double* __restrict__ P
     while (k < max_iters) {
         const int par = k & 1;
         const bool first = k == 0;
-        const double gamma = sum_small(gp[par], cs, 1);
-        const double delta = sum_small(dpart, cs, 1);
+        const double gamma = sum_small(gp[par], cs);
+        const double delta = sum_small(dpart, cs);
         if (first) gamma0 = gamma;
         if (!first && gamma <= rtol2 * gamma0) { converged = 1; break; }      // the same sums in every thread: uniform
         const double beta = first ? 0.0 : gamma / gprev;
@@ -239,10 +242,15 @@ pcg_cluster_kernel(int n, int fresh, int max_iters, const double* __restrict__ P
         if (rank == 0) {
             __shared__ double wg[8], rgn[8];
             __syncthreads();
+            double bsum = 0.0;                          // warp 0: sum over the CTAs of bpart[c][q], q = lane % 8
+            if (warp == 0) {
+                for (int c = lane >> 3; c < cs; c += 4) bsum += __ldcg(bpart + 8 * c + (lane & 7));
+                bsum += __shfl_xor_sync(0xffffffffu, bsum, 8);
+                bsum += __shfl_xor_sync(0xffffffffu, bsum, 16);
+            }
             if (threadIdx.x < 8) {
                 const int q = threadIdx.x;
-                double s = 0.0;
-                for (int c = 0; c < cs; ++c) s += __ldcg(bpart + 8 * c + q);
+                const double s = bsum;
                 const double d = (q >= 6 ? lin->C[q * 8 + q] : 0.0) + lambda;
                 const double zq = __ldcg(v.zg + q);
                 wg[q] = s + d * zq;
