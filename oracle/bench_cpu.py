@@ -88,9 +88,17 @@ def run(workload, n_sample, k, steps, warmup, n_full, lm_iters=2, sc=None, impl=
         its += a; dt += b; cg += c
     rate_sample = its / dt
     value = rate_sample * p.n / float(n_full)
-    cpu = dict(value=value, unit="LM it/s", cores=used, kind="port",
+    # triangulation (K1) on the CPU: the vectorised numpy oracle on the sample's matches, 2 map points per match
+    cam = (camera.KB8, np.asarray(sc["cam"], np.float32))
+    T1, T2 = Pose.from34(sc["T1"]), Pose.from34(sc["T2"])
+    m = min(len(sc["uv1"]), 200000)
+    t = time.perf_counter()
+    triangulate_pairs(sc["uv1"][:m], sc["uv2"][:m], cam, cam, T1, T2, "NRSLAM", "FarPoints", GATE_SIM, sc["min_cos"])
+    tri_rate = 2.0 * m / (time.perf_counter() - t)
+    cpu = dict(value=value, unit="LM it/s", cores=used, kind="port", triangulated_points_per_s=tri_rate,
                sample=f"{its} LM iterations ({cg} PCG iterations) on {p.n} correspondences (k={k}) in {dt:.1f} s = "
-                      f"{rate_sample:.3f} it/s, scaled linearly to {n_full} correspondences; {how}")
+                      f"{rate_sample:.3f} it/s, scaled linearly to {n_full} correspondences; {how}; triangulation: numpy "
+                      f"oracle, {m} matches, 1 thread")
     return dict(value=value, ms_per_step=dt * 1e3 / max(1, steps), cpu_baseline=cpu,
                 config=dict(workload=name, correspondences=n_full, k=k, sample_correspondences=p.n,
                             lm_iters_per_step=lm_iters))

@@ -95,3 +95,23 @@ def test_threads_do_not_change_the_trace(small):
     assert ta["trials"] == tb["trials"]
     for x, y in zip(ta["chi2"], tb["chi2"]):
         assert x == pytest.approx(y, rel=1e-9)
+
+
+def test_huber_branch_matches_numpy():
+    """Gross outliers switch the reprojection edges to the linear branch of the Huber kernel in both restatements."""
+    sc = scenes.sheet_scene(300, seed=23)
+    p, keep = scenes.problem_from_scene(sc, "knn", 8)
+    rng = np.random.default_rng(1)
+    bad = rng.choice(p.n, p.n // 10, replace=False)
+    p.uv1 = p.uv1.copy()
+    p.uv1[bad] += np.float32(45.0)
+    w = edges.Weights(rep=1.0, arap=20.0, depth_sigma=0.003)
+    cp = cport.CProblem(p, rotations=p.R)
+    v, parts = cport.cost(cp, w)
+    ref, rparts = edges.total_cost(p, w, edges.state_of(p), parts=True)
+    assert v == pytest.approx(ref, rel=1e-12)
+    ost, otr = lm.optimize(p, w, 4)
+    tr = cport.optimize(cp, w, 4, pcg_rtol=1e-13)
+    assert tr["trials"] == otr.trials
+    for a, b2 in zip(tr["chi2"], otr.chi2):
+        assert a == pytest.approx(b2, rel=1e-6)
