@@ -58,21 +58,17 @@ __global__ void morton_key_kernel(int n, const float* __restrict__ X1 /* [n][3],
 __global__ void perm_from_key_kernel(int n, const unsigned long long* __restrict__ key, int* __restrict__ perm) {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) perm[i] = (int)(key[i] & 0xffffffffull);
 }
-__global__ void iota_kernel(int n, int* __restrict__ v) {
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) v[i] = i;
-}
 
 // stable sort of perm[g0 .. g0 + kSortGroup) by degree, descending: rank = #(larger degree) + #(equal degree before me)
 __global__ void __launch_bounds__(kSortGroup)
 degree_sort_kernel(int n, const int* __restrict__ rowptr0, int* __restrict__ perm) {
     __shared__ int sdeg[kSortGroup];
-    __shared__ int sprm[kSortGroup];
     const int g0 = blockIdx.x * kSortGroup;
     const int m = min(kSortGroup, n - g0);
     const int t = threadIdx.x;
     int p = 0, d = -1;
     if (t < m) { p = perm[g0 + t]; d = rowptr0[p + 1] - rowptr0[p]; }
-    sdeg[t] = d; sprm[t] = p;
+    sdeg[t] = d;
     __syncthreads();
     if (t < m) {
         int rank = 0;

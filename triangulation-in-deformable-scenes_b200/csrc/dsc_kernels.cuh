@@ -1,28 +1,30 @@
 // dsc_kernels.cuh -- hand-written sm_100a kernels of the deformable two-view hot path.
 //
-// Layout in HBM (n correspondences in the library's internal, space-filling-curve order; E directed
-// neighbour edges in CSR):
+// Layout in HBM (n correspondences in the library's internal order: Morton order of KF1's world (x, y), then a stable
+// degree sort inside groups of kSortGroup rows; E directed neighbour edges as a sliced ELL):
 //   P      double[2][n][4] {X1.xyz, 0} plane then {X2.xyz, 0} plane: 32 B records, one neighbour gather of a
 //                        point = 1 aligned sector (LDG.E.256); the PCG operator only touches the X1 plane
 //   Q      double[n][4]  per-vertex ARAP rotation as unit quaternion (computeR)   32 B = 1 sector
 //   uv     float4[n]     {u1, v1, u2, v2}
 //   dm     double2[n]    depth measurements (KF1, KF2)
 //   isg    float2[n]     KeyFrame::getInvSigma2(octave) of the two observations
-//   U      double[n][16] unary Hessian record {U1[6], U2[6], kd1, kd2, 0, 0}      128 B = 1 line
-//   Je     double[nblk][9][32] sliced ELL of the ARAP Jacobian records {u, m, g}: block b = column k of a 32-row
-//                        slice (b = sliceptr[slice] + k), lane = row inside the slice; ecol int[nblk][32] the neighbour
-//   D      double[n][21] packed upper 6x6 diagonal block of H (block-Jacobi preconditioner source)
-//   Minv   double[n/32][21][32] packed inverse of D + lambda I (slice-major)
+//   sliced ELL: slice = 32 consecutive rows = one warp, lane = row; block b = column k of a slice (b = sliceptr[slice] + k)
+//   ecol   int[nblk][32]         neighbour of the lane's row (own tile first, halo last; padding = the row itself)
+//   ewgt   double[nblk][32]      edge weight (0 on padding)
+//   Je     double[nblk][9][32]   ARAP Jacobian record {u, m, g} of the directed edge, written by the linearisation
+//   U      double[n/32][14][32]  unary Hessian record {U1[6], U2[6], kd1, kd2}, slice-major
+//   D      double[n/32][21][32]  packed upper 6x6 diagonal block of H, slice-major (block-Jacobi preconditioner source)
+//   Minv   double[n/32][21][32]  packed inverse of D + lambda I, slice-major
 //   vectors b, x, r, z, w, p, s: double[n][6] {d/dX1, d/dX2}; the 8 global unknowns
 //   (T_g omega/upsilon, s1, s2) live in separate 8-vectors.
 //
-// Work decomposition of the gather kernels: sliced ELL, one warp per 32-row slice, lane = row (dsc_kernels_ell.cuh);
-// lane l walks the directed edges rowptr[i]+l, +8, ... of vertex i, and the per-vertex sums are
-// combined with warp-shuffle segmented reductions -- no global atomics anywhere.  The neighbour graph
-// is symmetric and the reference adds one EdgeARAP per *directed* pair with identical residual
-// (g2oBundleAdjustment.cc:883-953), so vertex i's row of J^T W J is 2x the sum over its own CSR row.
-// Grid = persistent blocks (multiple of the SM count) with a grid-stride loop; every reduction is
-// two-stage and deterministic (per-block partials, summed in a fixed order by the consumer).
+// Work decomposition: one warp per 32-row slice, lane = row, the row's sums stay in registers (no cross-lane reduction,
+// no global atomics anywhere); a block owns a tile of kSortGroup rows whose points / vectors are staged in shared memory
+// (dsc_kernels_ell.cuh for the gather kernels, cg_spmv_kernel below for the PCG operator).  The neighbour graph is
+// symmetric and the reference adds one EdgeARAP per *directed* pair with identical residual
+// (g2oBundleAdjustment.cc:883-953), so vertex i's row of J^T W J is 2x the sum over its own row.
+// Grids are persistent (multiples of the SM count); every reduction is two-stage and deterministic (per-block
+// partials, summed in a fixed order by the consumer).
 #pragma once
 #include "dsc_math.cuh"
 
@@ -530,10 +532,7 @@ DSC_D void mbar_wait(unsigned long long* bar, unsigned parity) {
                  "}" ::"r"(smem_addr(bar)), "r"(parity) : "memory");
 }
 
-#ifndef DSC_STAGES
-#define DSC_STAGES 3
-#endif
-constexpr int kSpmvStages = DSC_STAGES;                                   // ring depth per warp (ELL blocks in flight)
+constexpr int kSpmvStages = 3;                                   // ring depth per warp (ELL blocks in flight)
 constexpr int kURec = 14;                                        // unary record {U1[6], U2[6], kd1, kd2}, stored [slice][kURec][32]
 constexpr int kSpmvStageBytes = 9 * 32 * 8 + 32 * 4;             // one ELL block: Je[9][32] doubles + ecol[32] ints
 constexpr int kSpmvWinBytes = kSortGroup * (48 + 32);            // z (6 doubles) and X1 (double4) of the tile

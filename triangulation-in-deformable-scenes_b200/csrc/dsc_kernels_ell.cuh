@@ -10,10 +10,7 @@ namespace dsc {
 
 constexpr size_t kWinBytes = sizeof(double4) * 3 * kSortGroup;      // X1 | X2 | Q windows
 constexpr int kEllThreads = 256;
-#ifndef DSC_LIN_THREADS
-#define DSC_LIN_THREADS 256
-#endif
-constexpr int kLinThreads = DSC_LIN_THREADS;
+constexpr int kLinThreads = 256;             // linearise: 234 registers, one block per SM (384 / 512 threads spill and are slower)
 
 struct Window { const double4* x1; const double4* x2; const double4* q; int v0, nv; };
 
