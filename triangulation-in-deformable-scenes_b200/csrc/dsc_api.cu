@@ -99,6 +99,7 @@ struct dsc_ctx {
     struct IterGraph { cudaGraphExec_t exec = nullptr; const double* P = nullptr; WeightsDev W{}; } graphs[2];   // per state buffer
     bool use_graphs = true;
     int small_cluster = 0;                           // CTAs of the one-launch PCG of small problems (0 = not available)
+    int small_max_rows = kSmallMaxRows;              // largest problem that takes that path (DSC_SMALL_MAX_ROWS overrides)
     int solver = DSC_SOLVER_AUTO;                    // dense Cholesky for small problems, PCG above (dsc_set_solver)
     double *dnH = nullptr, *dnA = nullptr, *dn_rhs = nullptr, *dn_sol = nullptr;
     int dn_cap = 0;
@@ -259,6 +260,9 @@ extern "C" int dsc_create(int device, dsc_ctx** out) {
         // the one-launch PCG of small problems needs a cluster of 16 (non-portable) or 8 CTAs of 256 threads
         ctx->small_cluster = cudaFuncSetAttribute(pcg_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess ? kSmallCluster : 8;
         cudaGetLastError();
+        // tuning knobs: cluster size (1..16) and the size limit of the one-launch path
+        if (const char* cs = std::getenv("DSC_CLUSTER")) ctx->small_cluster = std::max(1, std::min(kSmallCluster, std::atoi(cs)));
+        if (const char* mr = std::getenv("DSC_SMALL_MAX_ROWS")) ctx->small_max_rows = std::max(0, std::atoi(mr));
     }
     if (cudaFuncSetAttribute(rotations_ell_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWinBytes) != cudaSuccess ||
         cudaFuncSetAttribute(cost_ell_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWinBytes) != cudaSuccess ||
@@ -789,7 +793,7 @@ static int run_linearize(dsc_ctx* ctx, const WeightsDev& W, LinGlobal* hlin) {
 // PCG solve of (H + lambda I) dx = b in two entry points so that a solve can be paused at a loose tolerance,
 // inspected (trial cost) and resumed to the tight one: begin = preconditioner + r0/z0 + first operator
 // application; resume = iterate until sqrt(r.z / r0.z0) <= rtol, breakdown or max_iters.
-static bool small_active(const dsc_ctx* ctx) { return ctx->small_cluster > 0 && ctx->n <= kSmallMaxRows; }
+static bool small_active(const dsc_ctx* ctx) { return ctx->small_cluster > 0 && ctx->n <= ctx->small_max_rows; }
 
 // one launch = the whole solve (or its continuation after a pause) by a single thread-block cluster (dsc_small.cuh)
 static int small_launch(dsc_ctx* ctx, const WeightsDev& W, int fresh) {
