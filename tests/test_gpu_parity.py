@@ -434,6 +434,22 @@ def test_dense_and_pcg_agree_and_limits(pkg, ctx):
     scale = np.abs(o1["X1d"]).max()
     assert np.abs(o1["X1d"] - o2["X1d"]).max() <= 1e-6 * scale
     assert s2.total_pcg_iters == 0 and s1.total_pcg_iters > 0
+    # the largest size the dense path accepts (DSC_DENSE_MAX = 1000 correspondences)
+    sc = scenes.sheet_scene(1000, seed=43)
+    p, keep = scenes.problem_from_scene(sc, "knn", 8)
+    assert 900 < p.n <= 1000
+    _upload(pkg, ctx, p)
+    ctx.set_solver(2)
+    recs_d, st_d = ctx.optimize(_w(pkg, w), 2)
+    od = ctx.download()
+    ctx.reset_state()
+    ctx.set_solver(1)
+    ctx.set_pcg(rtol=1e-12, max_iters=20000, check_every=64)
+    recs_p, st_p = ctx.optimize(_w(pkg, w), 2)
+    op = ctx.download()
+    assert [r.trials for r in recs_d] == [r.trials for r in recs_p]
+    assert st_d.final_chi2 == pytest.approx(st_p.final_chi2, rel=1e-8)
+    assert np.abs(od["X1d"] - op["X1d"]).max() <= 1e-6 * np.abs(op["X1d"]).max()
     # above DSC_DENSE_MAX the dense solver refuses; auto falls back to the PCG
     sc = scenes.sheet_scene(1300, seed=42)
     p, keep = scenes.problem_from_scene(sc, "knn", 8)

@@ -267,6 +267,7 @@ extern "C" int dsc_create(int device, dsc_ctx** out) {
     if (cudaFuncSetAttribute(rotations_ell_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWinBytes) != cudaSuccess ||
         cudaFuncSetAttribute(cost_ell_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWinBytes) != cudaSuccess ||
         cudaFuncSetAttribute(cg_spmv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSpmvSmem) != cudaSuccess ||
+        cudaFuncSetAttribute(dense_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * kDenseMaxM)) != cudaSuccess ||
         cudaFuncSetAttribute(linearize_ell_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWinBytes) != cudaSuccess) return bail(DSC_ERR_CUDA);
     *out = ctx;
     return DSC_OK;
