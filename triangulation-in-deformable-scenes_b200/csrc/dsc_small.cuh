@@ -47,6 +47,7 @@ pcg_cluster_kernel(int n, int fresh, int max_iters, const double* __restrict__ P
     cg::cluster_group cluster = cg::this_cluster();
     const int rank = (int)cluster.block_rank(), cs = (int)cluster.num_blocks();
     __shared__ double sm[9 * (kThreads / 32)];
+    __shared__ double psum[(kThreads / 32) * 9 * 32];
     __shared__ double Rg[9];
     __shared__ double zgs[8];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = kThreads / 32;
@@ -66,19 +67,30 @@ pcg_cluster_kernel(int n, int fresh, int max_iters, const double* __restrict__ P
         double acc[9];
 #pragma unroll
         for (int k = 0; k < 9; ++k) acc[k] = 0.0;
-        for (int sl = rank * wpb + warp; sl < nslices; sl += cs * wpb) {
-            const int i = sl * 32 + lane;
-            const bool act = i < n;
+        // Slices are dealt to the CTAs in contiguous groups of per_cta.  When a CTA has fewer slices than warps, wps
+        // warps share a slice: part p walks the column batches p, p + wps, ... and the leader (p = 0) adds the partial
+        // sums (through shared memory, in a fixed order) and finishes the rows -- 1000 correspondences are 32 slices
+        // for 128 warps, and the phase is as long as its longest warp.
+        const int per_cta = (nslices + cs - 1) / cs;
+        int wps = 1;
+        while (wps * 2 * per_cta <= wpb) wps *= 2;
+        const int slot = warp / wps, part = warp % wps;
+        for (int s0 = 0; s0 < per_cta; s0 += wpb / wps) {           // (uniform trip count inside the CTA)
+            const int sl = rank * per_cta + s0 + slot;
+            const bool have = s0 + slot < per_cta && sl < nslices;
+            const int slc = have ? sl : 0;
+            const int i = slc * 32 + lane;
+            const bool act = have && i < n;
             const int ic = act ? i : n - 1;
             D3 zi1, zi2;
             load6_l2(v.z, ic, zi1, zi2);
             const double4 xi = ldg256(reinterpret_cast<const double4*>(P) + ic);
             const D3 X1i = d3(xi.x, xi.y, xi.z);
             D3 Am = d3(0, 0, 0), Ag = d3(0, 0, 0), Au = d3(0, 0, 0);
-            const int b0 = __ldg(sliceptr + sl), b1 = __ldg(sliceptr + sl + 1);
+            const int b0 = __ldg(sliceptr + slc), b1 = have ? __ldg(sliceptr + slc + 1) : b0;
             // kSmallBatch ELL columns at a time: all their index / record loads are issued together, then all their
             // gathers -- with 8 warps per SM the loop is bound by L2 latency, not by throughput
-            for (int bk = b0; bk < b1; bk += kSmallBatch) {
+            for (int bk = b0 + part * kSmallBatch; bk < b1; bk += wps * kSmallBatch) {
                 int jq[kSmallBatch];
                 D3 uq[kSmallBatch], mq[kSmallBatch], gq[kSmallBatch];
 #pragma unroll
@@ -108,7 +120,20 @@ pcg_cluster_kernel(int n, int fresh, int max_iters, const double* __restrict__ P
                     Am = Am + w2 * mq[q]; Ag = Ag + w2 * gq[q]; Au = Au + w2 * uq[q];
                 }
             }
-            if (act) {
+            if (wps > 1) {                                          // partial sums of the slice's other warps
+                double* ps = psum + (size_t)warp * 9 * 32 + lane;
+                ps[0] = Am.x; ps[32] = Am.y; ps[64] = Am.z; ps[96] = Ag.x; ps[128] = Ag.y; ps[160] = Ag.z;
+                ps[192] = Au.x; ps[224] = Au.y; ps[256] = Au.z;
+                __syncthreads();
+                if (part == 0)
+                    for (int q = 1; q < wps; ++q) {
+                        const double* pq = psum + (size_t)(warp + q) * 9 * 32 + lane;
+                        Am = Am + d3(pq[0], pq[32], pq[64]); Ag = Ag + d3(pq[96], pq[128], pq[160]);
+                        Au = Au + d3(pq[192], pq[224], pq[256]);
+                    }
+                __syncthreads();
+            }
+            if (act && part == 0) {
                 const double* Up = U + ((size_t)(i >> 5) * kURec) * 32 + lane;
                 double uu[kURec];
 #pragma unroll
