@@ -40,8 +40,7 @@ def parse():
     ap.add_argument("--pcg-max-iters", type=int, default=6000)
     ap.add_argument("--early-rtol", type=float, nargs="*", default=[1e-3, 1e-4], help="loose tolerances of the early-reject check (none = off)")
     ap.add_argument("--early-margin", type=float, nargs="*", default=[1.0, 0.5])
-    ap.add_argument("--cpu-sample-n", type=int, default=100000)
-    ap.add_argument("--cpu-impl", choices=["c", "numpy"], default="c", help="CPU legs: compiled C oracle (all cores) or the numpy port")
+    ap.add_argument("--cpu-budget", type=float, default=900.0, help="--impl reference: wall-time budget of the CPU step in seconds")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -62,23 +61,7 @@ class _stdout_to_stderr:
 
 # ---------------------------------------------------------------------------------------------- workload
 def make_scene(pkg, args, seed):
-    wl = pkg_workloads(pkg)
-    n_gen = int(args.n * 1.08) + 64
-    if args.workload == "drunkard":
-        sc = wl.tube_scene(n_gen, seed=seed, cam=wl.DRUNKARD_CAM, arap=1.0e7, depth_sigma=0.0003, lm_iters=30)
-        name = "config3: Drunkard.yaml-shaped tube, 1 frame pair"
-    elif args.workload == "realcolon":
-        sc = wl.tube_scene(n_gen, seed=seed, cam=wl.REALCOLON_CAM, arap=0.1, depth_sigma=1e-6, lm_iters=30,
-                           scales=(1.0, 1.0))
-        keep = wl.border_mask_keep(sc["uv1"], 1440, 1080) & wl.border_mask_keep(sc["uv2"], 1440, 1080)
-        for key in ("uv1", "uv2", "d1", "d2"):
-            sc[key] = sc[key][keep]
-        name = "config4: Realcolon.yaml-shaped tube + border mask, 1 frame pair"
-    else:
-        sc = wl.sheet_scene(n_gen, seed=seed)
-        name = "config2: Simulation.yaml sheet, 1 frame pair"
-    sc["name"] = name
-    return sc
+    return pkg_workloads(pkg).make_scene(args.workload, args.n, seed)
 
 
 def pkg_workloads(pkg):
@@ -159,12 +142,21 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------- CPU arm
-def cpu_reference_run(args, steps, warmup):
-    """The reference's CPU algorithm (oracle port; the reference itself needs g2o/Eigen/Qhull/Open3D and
-    cannot be compiled here) on a bounded sample of the same workload."""
+def reference_arm(args):
+    """`--impl reference`: the reference's CPU algorithm (oracle port: the reference itself needs g2o / Eigen / Sophus /
+    Qhull / Open3D and cannot be compiled here) on the SAME frame pair, size, iteration count and PCG tolerance as the
+    GPU arm, with g2o's policy (every trial solved to the tolerance), all host threads.  A CPU step takes minutes, so
+    ONE step is timed whatever --steps / --warmup say (echoed in the line; config.steps_timed tells)."""
     from oracle import bench_cpu
-    return bench_cpu.run(args.workload, args.cpu_sample_n, args.k, steps, warmup, args.n, impl=args.cpu_impl,
-                         pcg_rtol=args.pcg_rtol)
+    res = bench_cpu.run_reference(args.workload, args.n, args.k, args.lm_iters, pcg_rtol=args.pcg_rtol, budget_s=args.cpu_budget)
+    cfg = res["config"]
+    cfg.update(parallelism="host cores only (rank 0)", trace=res["trace"])
+    return dict(metric="non-rigid LM iterations/s at 1M correspondences", value=res["value"], unit="LM it/s",
+                n_gpus=args.gpus, steps=args.steps, warmup=args.warmup, ms_per_step=res["ms_per_step"],
+                higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64", data="synthetic",
+                impl="reference", config=cfg, cpu_baseline=res["cpu_baseline"],
+                e2e=dict(value=res["value"], unit="LM it/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+                gpu_launches=0)
 
 
 # ---------------------------------------------------------------------------------------------- main
@@ -175,17 +167,14 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if args.workload == "batch" and args.impl == "ours":
         return main_batch(args, rank, world, local)
+    if args.workload == "batch":                       # the CPU arm of config 5 = one of its pairs
+        args.workload, args.n = "sheet", (args.n if args.n != 1_000_000 else 10_000)
 
     if args.impl == "reference":
         if rank != 0:
             return 0
-        res = cpu_reference_run(args, args.steps, args.warmup)
-        line = dict(metric="non-rigid LM iterations/s at 1M correspondences", value=res["value"], unit="LM it/s",
-                    n_gpus=args.gpus, steps=args.steps, warmup=args.warmup, ms_per_step=res["ms_per_step"],
-                    higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64", data="synthetic",
-                    impl="reference", config=res["config"], cpu_baseline=res["cpu_baseline"],
-                    e2e=dict(value=res["value"], unit="LM it/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
-                    gpu_launches=0)
+        with _stdout_to_stderr():
+            line = reference_arm(args)
         print(json.dumps(line))
         return 0
 
@@ -224,6 +213,7 @@ def main():
     # shortcut is only kept if they are identical, iteration by iteration.
     early = dict(rtol_loose=args.early_rtol, rho_margin=args.early_margin, used=False, trace_identical=None)
     ref_trace = None
+    full_counts = None
     for k in range(args.warmup):
         ctx.reset_state()
         recs, st = ctx.optimize(w, lm_iters)
@@ -231,6 +221,7 @@ def main():
         if k == 0:
             ref_trace = tr
             early["lm_it_per_s_full_solves"] = st.iterations / (st.device_ms * 1e-3)   # first warm-up step, no shortcut
+            full_counts = dict(lm_iters=st.iterations, trials=st.total_trials, pcg_iters=st.total_pcg_iters)
             if len(args.early_rtol) > 0 and args.warmup > 1:
                 ctx.set_early_reject(args.early_rtol, args.early_margin)
                 early["used"] = True
@@ -315,8 +306,10 @@ def main():
         cpu = None
         if not args.no_cpu_baseline and world == 1:
             try:
-                r = cpu_reference_run(args, 1, 0)
-                cpu = r["cpu_baseline"]
+                from oracle import bench_cpu
+                with _stdout_to_stderr():
+                    counts = full_counts or dict(lm_iters=its // args.steps, trials=trials // args.steps, pcg_iters=pcg_its // args.steps)
+                    cpu = bench_cpu.components(sc, prob, sc["weights"], counts, args.pcg_rtol)
             except Exception as ex:      # the baseline is a report, never a gate
                 cpu = dict(value=None, unit="LM it/s", cores=1, kind="port", sample=f"failed: {ex}")
         line = dict(metric="non-rigid LM iterations/s at 1M correspondences", value=value, unit="LM it/s", n_gpus=world,

@@ -10,6 +10,7 @@
  *                           Modules/Mapping/Mapping.cc:294-343 (+ gate :351-364) and
  *                           Modules/Mapping/MonocularMapInitializer.cc:303-368 (+ gates :315-360);
  *                           KannalaBrandt8::unproject/project Modules/Calibration/KannalaBrandt8.cc:32-83
+ *   dsc_triangulate_rays    the same dispatcher with the reference's own argument list (rays, not pixels)
  *   dsc_depth_scale_init    Modules/Map/KeyFrame.cc:131-153 setInitialDepthScaleInSimulationImages
  *   dsc_problem_upload      the Map -> g2o graph gather of arapOptimization,
  *                           Modules/Optimization/g2oBundleAdjustment.cc:640-957
@@ -120,6 +121,8 @@ typedef struct {
     double linearize_ms, pcg_ms, trial_ms;   /* CUDA-event breakdown           */
     int    kernel_launches;
     int    early_rejects;      /* trials rejected at the loose tolerance (dsc_set_early_reject) */
+    int    pcg_unconverged;    /* linear solves that hit max_iters; each is treated as a failed solve (trial rejected,
+                                  lambda grows), as g2o treats a failed factorisation                                */
 } dsc_opt_stats;
 
 /* ---- context --------------------------------------------------------------------------- */
@@ -147,6 +150,11 @@ int dsc_tri_upload(dsc_ctx* ctx, const dsc_pair* pair, int n, const float* uv1, 
                    const float* depth1, const float* depth2);
 int dsc_tri_run(dsc_ctx* ctx, const dsc_tri_params* prm);
 int dsc_tri_download(dsc_ctx* ctx, float* X1, float* X2, uint8_t* valid, float* cos_parallax, int* n_valid);
+/* useTriangulationMethod as the reference declares it (Modules/Utils/Geometry.h:66-69): bearing rays in, no camera
+ * model, no gates (Geometry.cc:216-230 always returns true).  T1w/T2w row-major 3x4 [R|t]; xn1/xn2 [n][3] rays (for
+ * DSC_TRI_DEPTH: camera-frame points at the measured depth, Geometry.cc:189-214); X1/X2 [n][3] world points out. */
+int dsc_triangulate_rays(dsc_ctx* ctx, const float* T1w, const float* T2w, int method, int location, int n,
+                         const float* xn1, const float* xn2, float* X1, float* X2);
 /* mean of depth/z_c over valid points with non-zero depth (KeyFrame.cc:131-153); which = 1|2 */
 int dsc_depth_scale_init(dsc_ctx* ctx, int which, double* scale);
 

@@ -50,7 +50,7 @@ typedef struct {
 } dso_problem;
 
 typedef struct { double rep, arap, depth_sigma; } dso_weights;
-typedef struct { int fd; int threads; double pcg_rtol; int pcg_max; } dso_options;
+typedef struct { int fd; int threads; double pcg_rtol; int pcg_max; double budget_s; /* > 0: stop after the LM iteration in which this much wall time has passed */ } dso_options;
 
 #define FD_DELTA 1e-9
 
@@ -682,7 +682,13 @@ int dso_optimize(dso_problem* p, const dso_weights* w, const dso_options* opt, i
     if (!work || !dx || !T1 || !T2) { free(work); free(dx); free(T1); free(T2); lin_free(&L); return -1; }
     double lambda = 0, ni = 2;
     int it, done = 0;
+#ifdef _OPENMP
+    const double t_start = omp_get_wtime();
+#endif
     for (it = 0; it < iters; ++it) {
+#ifdef _OPENMP
+        if (opt->budget_s > 0 && it > 0 && omp_get_wtime() - t_start > opt->budget_s) break;
+#endif
         linearize(p, w, p->X[0], p->X[1], p->Tg, p->s, opt->fd, &L);
         double current = dso_cost_state(p, w, p->X[0], p->X[1], p->Tg, p->s, NULL);
         if (it == 0) { lambda = 1e-5 * L.maxdiag; ni = 2; }             /* computeLambdaInit, tau = 1e-5 */
@@ -759,6 +765,45 @@ int dso_debug_linearize(dso_problem* p, const dso_weights* w, int fd, double lam
     if (chi2) *chi2 = L.chi2;
     lin_free(&L);
     return 0;
+}
+
+/* Timing aid of bench.py's CPU baseline (wall clock, omp_get_wtime): out[0] = one linearisation + cost evaluation
+ * (what starts every LM iteration), out[1] = one PCG iteration (a solve at lambda = 1e-5 max diag H cut after pcg_reps
+ * iterations, preconditioner set-up excluded by differencing two lengths), out[2] = one cost evaluation (one per LM
+ * trial), out[3] = the block-Jacobi set-up of a solve.  The state of p is not changed. */
+int dso_time_components(dso_problem* p, const dso_weights* w, int threads, int pcg_reps, double* out) {
+#ifdef _OPENMP
+    omp_set_num_threads(threads > 0 ? threads : omp_get_num_procs());
+    lin_t L;
+    if (lin_alloc(&L, p)) { lin_free(&L); return -1; }
+    size_t m = 8 + 6 * (size_t)p->n;
+    double* work = malloc(sizeof(double) * (4 * m + (size_t)(L.E > 0 ? L.E : 1)));
+    double* dx = malloc(sizeof(double) * m);
+    if (!work || !dx) { free(work); free(dx); lin_free(&L); return -1; }
+    double t0 = omp_get_wtime();
+    linearize(p, w, p->X[0], p->X[1], p->Tg, p->s, 0, &L);
+    double c = dso_cost_state(p, w, p->X[0], p->X[1], p->Tg, p->s, NULL);
+    out[0] = omp_get_wtime() - t0;
+    t0 = omp_get_wtime();
+    c += dso_cost_state(p, w, p->X[0], p->X[1], p->Tg, p->s, NULL);
+    out[2] = omp_get_wtime() - t0;
+    double lambda = 1e-5 * L.maxdiag;
+    int its = 0;
+    t0 = omp_get_wtime();
+    solve_pcg(p, &L, lambda, 0.0, 1, dx, &its, work);
+    double t1 = omp_get_wtime() - t0;
+    t0 = omp_get_wtime();
+    solve_pcg(p, &L, lambda, 0.0, 1 + pcg_reps, dx, &its, work);
+    double t2 = omp_get_wtime() - t0;
+    out[1] = (t2 - t1) / (double)pcg_reps;
+    out[3] = t1 - out[1];
+    free(work); free(dx);
+    lin_free(&L);
+    return c == c ? 0 : 1;
+#else
+    (void)p; (void)w; (void)threads; (void)pcg_reps; (void)out;
+    return -2;
+#endif
 }
 
 int dso_threads(void) {

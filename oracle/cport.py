@@ -28,7 +28,7 @@ class _Weights(C.Structure):
 
 
 class _Options(C.Structure):
-    _fields_ = [("fd", C.c_int), ("threads", C.c_int), ("pcg_rtol", C.c_double), ("pcg_max", C.c_int)]
+    _fields_ = [("fd", C.c_int), ("threads", C.c_int), ("pcg_rtol", C.c_double), ("pcg_max", C.c_int), ("budget_s", C.c_double)]
 
 
 def build(force=False):
@@ -50,6 +50,7 @@ def load():
         lib.dso_compute_rotations.argtypes = [C.POINTER(_Problem)]
         lib.dso_optimize.argtypes = [C.POINTER(_Problem), C.POINTER(_Weights), C.POINTER(_Options), C.c_int, C.c_void_p,
                                      C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int)]
+        lib.dso_time_components.argtypes = [C.POINTER(_Problem), C.POINTER(_Weights), C.c_int, C.c_int, C.c_void_p]
         lib.dso_debug_linearize.argtypes = [C.POINTER(_Problem), C.POINTER(_Weights), C.c_int, C.c_double, C.c_void_p,
                                             C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_double)]
         _lib = lib
@@ -140,14 +141,14 @@ def debug_linearize(cp, w, lam, x, fd=False):
     return b, hd, y, chi.value
 
 
-def optimize(cp, w, iters, fd=False, threads=0, pcg_rtol=1e-12, pcg_max=20000):
+def optimize(cp, w, iters, fd=False, threads=0, pcg_rtol=1e-12, pcg_max=20000, budget_s=0.0):
     """Runs LM in place on cp; returns dict(chi2, lam, trials, pcg_iters, final_chi2)."""
     chi2 = np.zeros(iters + 1)
     lam = np.zeros(max(iters, 1))
     trials = np.zeros(max(iters, 1), np.int32)
     its = np.zeros(max(iters, 1), np.int32)
     done = C.c_int(0)
-    opt = _Options(int(fd), int(threads), float(pcg_rtol), int(pcg_max))
+    opt = _Options(int(fd), int(threads), float(pcg_rtol), int(pcg_max), float(budget_s))
     rc = load().dso_optimize(C.byref(cp.c), C.byref(_w(w)), C.byref(opt), int(iters), chi2.ctypes.data, lam.ctypes.data,
                              trials.ctypes.data, its.ctypes.data, C.byref(done))
     if rc:
@@ -155,6 +156,15 @@ def optimize(cp, w, iters, fd=False, threads=0, pcg_rtol=1e-12, pcg_max=20000):
     k = done.value
     return dict(chi2=chi2[:k].tolist(), lam=lam[:k].tolist(), trials=trials[:k].tolist(), pcg_iters=its[:k].tolist(),
                 final_chi2=float(chi2[k]))
+
+
+def time_components(cp, w, pcg_reps=20, threads=0):
+    """seconds of (linearisation + cost, one PCG iteration, one cost evaluation, the preconditioner set-up of a solve)"""
+    out = np.zeros(4)
+    rc = load().dso_time_components(C.byref(cp.c), C.byref(_w(w)), int(threads), int(pcg_reps), out.ctypes.data)
+    if rc < 0:
+        raise MemoryError("dso_time_components")
+    return dict(linearize_s=float(out[0]), pcg_iter_s=float(out[1]), cost_s=float(out[2]), precond_s=float(out[3]))
 
 
 def threads():

@@ -94,8 +94,10 @@ def simulation_poses(C1, C2, moved0):
 
 
 def simulation_frontend(original, moved, C1, C2, cam=SIM_CAM, rep_sigma=1.0, decimals=1,
-                        depth_sigma_mm=3.0, scale_c1=0.4, scale_c2=1.7):
-    """Key points and depth measurements exactly as the reference draws them."""
+                        depth_sigma_mm=3.0, scale_c1=0.4, scale_c2=1.7, model=camera.KB8):
+    """Key points and depth measurements exactly as the reference draws them.  model = camera.KB8 (what HEAD's
+    Settings.cc:43-51 builds) or camera.PINHOLE (what the revision that wrote Data/SinteticDataBase and
+    Data/Experiments used: tests/golden/reference_pins.json reproduces those logs to 6 digits with it)."""
     original, moved = f32(original), f32(moved)
     T1, T2 = simulation_poses(C1, C2, moved[0])
     n = original.shape[0]
@@ -112,8 +114,8 @@ def simulation_frontend(original, moved, C1, C2, cam=SIM_CAM, rep_sigma=1.0, dec
     # createKeyPoints (own generator, default seed)
     g = MinStdRand0()
     dist = NormalFloat(0.0, F(rep_sigma))
-    p1 = camera.kb8_project(cam, c1)
-    p2 = camera.kb8_project(cam, c2)
+    p1 = camera.project(model, cam, c1)
+    p2 = camera.project(model, cam, c2)
     uv1 = np.zeros((n, 2), np.float32)
     uv2 = np.zeros((n, 2), np.float32)
     for i in range(n):
@@ -139,11 +141,11 @@ def load_points_csv(path):
 # ------------------------------------------------------------------ problem assembly
 def build_problem(uv1, uv2, d1, d2, cam, T1, T2, graph_kind="delaunay", k=8, area=None,
                   method="NRSLAM", location="FarPoints", min_cos=0.9998, gate=GATE_SIM,
-                  scale_init=(0.0, 0.0)):
+                  scale_init=(0.0, 0.0), model=camera.KB8):
     """Triangulate (K1), compact away rejected correspondences, build the neighbour graph on
     KF1's points, initial depth scales and per-vertex rotations: everything arapOptimization
     sets up before optimizer.optimize() (g2oBundleAdjustment.cc:640-957)."""
-    camt = (camera.KB8, f32(cam))
+    camt = (model, f32(cam))
     X1, X2, valid, cosp = triangulate_pairs(uv1, uv2, camt, camt, T1, T2, method, location, gate, min_cos,
                                             d1=d1, d2=d2)
     keep = np.nonzero(valid)[0]

@@ -1,0 +1,15 @@
+// API-CONFORMANCE STUB (test infrastructure, tests/test_host_shim.py::test_shim_compiles_against_the_reference_api).
+// Declares ONLY members that the reference declares in Modules/Map/MapPoint.h, with the reference's own signatures
+// (every declaration below is checked, line for line, against that header when /root/reference is present); no bodies.
+// host/Optimization.cc is compiled against this tree with -DDSC_IN_REFERENCE_TREE: anything it calls that the reference
+// does not declare fails that build.
+#pragma once
+#include <Eigen/Core>
+
+class MapPoint {
+public:
+    MapPoint(Eigen::Vector3f& p3d);
+    Eigen::Vector3f getWorldPosition();
+    void setWorldPosition(Eigen::Vector3f& p3d);
+    long unsigned int getId();
+};

@@ -1,0 +1,23 @@
+// API-CONFORMANCE STUB (test infrastructure, tests/test_host_shim.py::test_shim_compiles_against_the_reference_api).
+// Declares ONLY members that the reference declares in Modules/Utils/CommonTypes.h:9-30, with the reference's own signatures
+// (every declaration below is checked, line for line, against that header when /root/reference is present); no bodies.
+// host/Optimization.cc is compiled against this tree with -DDSC_IN_REFERENCE_TREE: anything it calls that the reference
+// does not declare fails that build.
+#pragma once
+#include <memory>
+#include "Map/KeyFrame.h"
+#include "Map/MapPoint.h"
+
+using namespace std;
+
+typedef shared_ptr<MapPoint> MapPoint_;
+typedef shared_ptr<KeyFrame> KeyFrame_;
+
+struct PixelsError {
+    double avgc1;
+    double avgc2;
+    double avg;
+    double desvc1;
+    double desvc2;
+    double desv;
+};

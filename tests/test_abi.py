@@ -45,7 +45,7 @@ def test_struct_sizes_match_header(pkg):
     b = pkg.binding
     assert ctypes.sizeof(b.Camera) == 36 and ctypes.sizeof(b.Pair) == 168
     assert ctypes.sizeof(b.TriParams) == 24 and ctypes.sizeof(b.Weights) == 48
-    assert ctypes.sizeof(b.PcgParams) == 16 and ctypes.sizeof(b.IterRecord) == 40 and ctypes.sizeof(b.OptStats) == 64
+    assert ctypes.sizeof(b.PcgParams) == 16 and ctypes.sizeof(b.IterRecord) == 40 and ctypes.sizeof(b.OptStats) == 72
 
 
 def test_product_does_not_touch_the_oracle():

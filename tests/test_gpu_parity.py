@@ -550,3 +550,162 @@ def test_cluster_pcg_matches_the_per_iteration_kernels(pkg):
         assert a.chi2_after == pytest.approx(b.chi2_after, rel=1e-9)
     scale = np.abs(o0["X1d"]).max()
     assert np.abs(o0["X1d"] - o1["X1d"]).max() <= 1e-8 * scale
+
+
+# ---------------------------------------------------------------------------------------------- reference-held numbers
+def _reference_pins():
+    import json
+    import os
+    gold = os.path.join(os.path.dirname(__file__), "golden")
+    return json.load(open(os.path.join(gold, "reference_pins.json"))), np.load(os.path.join(gold, "reference_pins.npz"))
+
+
+@pytest.mark.gpu
+def test_reference_logs_reproduced_through_the_c_abi(pkg, ctx):
+    """REFERENCE-HELD NUMBERS on the GPU.  The INITIAL MEASUREMENTS of Data/Experiments/**/Experiment.txt (written by
+    the reference right after triangulation; tests/golden/make_reference_pins.py): mean / RMSE 3-D error and pixel
+    sigma of the triangulated map points for the three seed locations, 12 database pairs, 6 printed digits each.
+    The logs were written with the PinHole model, so this is also the PinHole parity test of K1 (unproject),
+    pixel_sigma_kernel (project) and the gates; the CUDA points are compared bit for bit with the oracle's."""
+    from oracle import metrics
+    meta, arr = _reference_pins()
+    checked = 0
+    for m in meta:
+        o, mv = arr[f"o{m['key']}"], arr[f"m{m['key']}"]
+        fe = scenes.simulation_frontend(o, mv, m["C1"], m["C2"], model=camera.PINHOLE)
+        cam = (camera.PINHOLE, fe["cam"])
+        pair = pkg.make_pair(cam, cam, fe["T1"], fe["T2"])
+        for loc, lg in m["logs"].items():
+            X1, X2, valid, cosp, nv = ctx.triangulate(pair, ctx.tri_params("NRSLAM", loc, GATE_SIM, 0.9998), fe["uv1"], fe["uv2"])
+            oX1, oX2, ovalid, ocos = triangulate_pairs(fe["uv1"], fe["uv2"], cam, cam, fe["T1"], fe["T2"], "NRSLAM", loc, GATE_SIM, 0.9998)
+            assert np.array_equal(valid, ovalid) and np.array_equal(X1, oX1) and np.array_equal(X2, oX2) and np.array_equal(cosp, ocos)
+            assert nv == lg["n_mapped"]
+            _, av, rmse = metrics.sim_absolute_map_errors(X1[valid], X2[valid], o[valid], mv[valid])
+            assert av == pytest.approx(lg["av_error"], rel=2e-5), (m["case"], loc)
+            assert rmse == pytest.approx(lg["rmse"], rel=2e-5), (m["case"], loc)
+            # calculatePixelsStandDev on the device (pixel_sigma_kernel) from the float map points
+            k = int(valid.sum())
+            ctx.problem_upload(pair, X1[valid], X2[valid], fe["uv1"][valid], fe["uv2"][valid], np.zeros(k), np.zeros(k))
+            s = ctx.pixel_sigma()
+            if loc != "InRays":
+                assert s[0] == pytest.approx(lg["sigma_c1"], rel=4e-5) and s[1] == pytest.approx(lg["sigma_c2"], rel=4e-5)
+            else:
+                assert s[0] < 1e-4 and s[1] < 1e-4
+            checked += 1
+        # show-solution mode (Data/SinteticDataBase/**/Experiment.txt): ground-truth points as map points
+        ctx.problem_upload(pair, o, mv, fe["uv1"], fe["uv2"], np.zeros(len(o)), np.zeros(len(o)))
+        s = ctx.pixel_sigma()
+        assert s[0] == pytest.approx(m["database"]["sigma_c1"], rel=1e-5) and s[1] == pytest.approx(m["database"]["sigma_c2"], rel=1e-5)
+    assert checked >= 30
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("method,location", [("NRSLAM", "FarPoints"), ("Classic", "InRays"), ("DepthMeasurement", "TwoPoints")])
+def test_pinhole_camera_triangulation(pkg, ctx, method, location):
+    """PinHole::unproject / project (PinHole.cc:25-40) on K1, including the real-image gates with the reprojection check."""
+    sc = scenes.tube_scene(6000, seed=72)
+    cam = (camera.PINHOLE, sc["cam"])
+    c1, c2 = sc["T1"].apply(sc["original"]), sc["T2"].apply(sc["moved"])
+    rng = np.random.default_rng(72)
+    uv1 = (camera.pinhole_project(sc["cam"], c1) + rng.normal(0, 1, (len(c1), 2)).astype(np.float32)).astype(np.float32)
+    uv2 = (camera.pinhole_project(sc["cam"], c2) + rng.normal(0, 1, (len(c1), 2)).astype(np.float32)).astype(np.float32)
+    pair = pkg.make_pair(cam, cam, sc["T1"], sc["T2"])
+    prm = ctx.tri_params(method, location, GATE_REAL, 0.9998, depth_limit=0.3, check_reproj=True)
+    X1, X2, valid, cosp, nv = ctx.triangulate(pair, prm, uv1, uv2, sc["d1"], sc["d2"])
+    oX1, oX2, ovalid, ocos = triangulate_pairs(uv1, uv2, cam, cam, sc["T1"], sc["T2"], method, location, GATE_REAL, 0.9998,
+                                                depth_limit=0.3, check_reproj=True, d1=sc["d1"], d2=sc["d2"])
+    assert 0 < ovalid.sum()
+    if method == "Classic":
+        np.testing.assert_allclose(X1, oX1, rtol=2e-4, atol=2e-6)
+        assert np.mean(valid == ovalid) > 0.999
+    else:
+        assert np.array_equal(valid, ovalid)
+        assert np.array_equal(X1, oX1) and np.array_equal(X2, oX2) and np.array_equal(cosp, ocos)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("solver", [1, 2])
+def test_lm_pinhole_camera(pkg, ctx, solver):
+    """PinHole::project / projectJac (PinHole.cc:25-33,49-62) inside the refinement: cost, gradient, operator and the
+    LM trace against the direct-solve oracle."""
+    sc = scenes.sheet_scene(700, seed=73)
+    n = len(sc["original"])
+    c1, c2 = sc["T1"].apply(sc["original"]), sc["T2"].apply(sc["moved"])
+    rng = np.random.default_rng(73)
+    uv1 = (camera.pinhole_project(sc["cam"], c1) + rng.normal(0, 1, (n, 2)).astype(np.float32)).astype(np.float32)
+    uv2 = (camera.pinhole_project(sc["cam"], c2) + rng.normal(0, 1, (n, 2)).astype(np.float32)).astype(np.float32)
+    p, keep = scenes.build_problem(uv1, uv2, sc["d1"], sc["d2"], sc["cam"], sc["T1"], sc["T2"], graph_kind="knn", k=8,
+                                   area=sc["area"], model=camera.PINHOLE)
+    assert p.cam1[0] == camera.PINHOLE and p.n > 500
+    w = edges.Weights(rep=1.0, arap=50.0, depth_sigma=0.003)
+    _upload(pkg, ctx, p)
+    _check_linearisation(pkg, ctx, p, w)
+    _compare_lm(pkg, ctx, p, w, 4, solver=solver)
+
+
+@pytest.mark.gpu
+def test_triangulate_rays_entry_matches_the_oracle(pkg, ctx):
+    """dsc_triangulate_rays = useTriangulationMethod with the reference's argument list (Geometry.h:66-69): rays, no
+    camera, no gates -- including rays that point backwards (z <= 0), which the pixel entry cannot express."""
+    from oracle import triangulate as otri
+    from oracle.f32 import normalize3
+    sc = scenes.sheet_scene(3000, seed=81)
+    xn1 = normalize3(camera.kb8_unproject(sc["cam"], sc["uv1"]))
+    xn2 = normalize3(camera.kb8_unproject(sc["cam"], sc["uv2"]))
+    xn1[::7] *= np.float32(-1.0)                                   # backwards rays
+    xn2[::11, 2] = np.float32(0.0)
+    for loc_name, loc in otri.LOCATIONS.items():
+        X1, X2 = ctx.triangulate_rays(sc["T1"], sc["T2"], "NRSLAM", loc_name, xn1, xn2)
+        with np.errstate(all="ignore"):
+            oX1, oX2 = otri.triangulate_nrslam(xn1, xn2, sc["T1"], sc["T2"], loc)
+        assert np.array_equal(X1, oX1.astype(np.float32), equal_nan=True) and np.array_equal(X2, oX2.astype(np.float32), equal_nan=True)
+    # DepthMeasurement: the "rays" are camera-frame points at the measured depth (Geometry.cc:189-214)
+    c1, c2 = sc["T1"].apply(sc["original"]), sc["T2"].apply(sc["moved"])
+    X1, X2 = ctx.triangulate_rays(sc["T1"], sc["T2"], "DepthMeasurement", "FarPoints", c1, c2)
+    oX1, oX2 = otri.triangulate_depth(c1, c2, sc["T1"], sc["T2"], otri.LOCATIONS["FarPoints"])
+    assert np.array_equal(X1, oX1.astype(np.float32)) and np.array_equal(X2, oX2.astype(np.float32))
+    # one match, as the host shim calls it
+    X1, X2 = ctx.triangulate_rays(sc["T1"], sc["T2"], "NRSLAM", "InRays", xn1[:1], xn2[:1])
+    assert X1.shape == (1, 3)
+
+
+@pytest.mark.gpu
+def test_dense_solver_is_race_free_under_concurrent_load(pkg):
+    """Round-1 advisor finding: dense_panel_kernel's block 0 overwrote the diagonal block A11 in the launch in which the
+    other blocks still read it.  L11 now goes through a side buffer; with other streams keeping every SM busy (blocks of
+    the panel launch start late and far apart) the dense LM run must stay bit-identical to the quiet one."""
+    import threading
+    sc = scenes.sheet_scene(560, seed=91)
+    p, keep = scenes.problem_from_scene(sc, "knn", 8)
+    w = _w(pkg, edges.Weights(rep=1.0, arap=50.0, depth_sigma=0.003))
+    big = scenes.tube_scene(120000, seed=92, depth_sigma=0.0003)
+    pb, _ = scenes.problem_from_scene(big, "knn", 8, min_cos=0.99999)
+    wb = _w(pkg, edges.Weights(rep=1.0, arap=1.0e7, depth_sigma=0.0003))
+    with pkg.Context(0) as c, pkg.Context(0) as noisy1, pkg.Context(0) as noisy2:
+        _upload(pkg, c, p)
+        c.set_solver(2)
+        recs0, st0 = c.optimize(w, 6)
+        out0 = c.download()
+        stop = threading.Event()
+
+        def hammer(ctx_n):
+            _upload(pkg, ctx_n, pb)
+            ctx_n.set_solver(1)
+            ctx_n.set_pcg(rtol=1e-10, max_iters=300, check_every=64)
+            while not stop.is_set():
+                ctx_n.reset_state()
+                ctx_n.optimize(wb, 1)
+        th = [threading.Thread(target=hammer, args=(x,)) for x in (noisy1, noisy2)]
+        for t in th:
+            t.start()
+        try:
+            for _ in range(8):
+                c.reset_state()
+                recs, st = c.optimize(w, 6)
+                out = c.download()
+                assert [r.chi2_after for r in recs] == [r.chi2_after for r in recs0]
+                assert np.array_equal(out["X1d"], out0["X1d"]) and np.array_equal(out["X2d"], out0["X2d"])
+        finally:
+            stop.set()
+            for t in th:
+                t.join()

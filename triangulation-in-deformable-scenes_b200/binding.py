@@ -21,7 +21,7 @@ LOCATIONS = {"InRays": 0, "TwoPoints": 1, "FarPoints": 2}
 EXPORTS = [
     "dsc_create", "dsc_destroy", "dsc_last_error", "dsc_status_string", "dsc_version", "dsc_synchronize",
     "dsc_timer_start", "dsc_timer_stop", "dsc_launch_count",
-    "dsc_triangulate", "dsc_tri_upload", "dsc_tri_run", "dsc_tri_download", "dsc_depth_scale_init",
+    "dsc_triangulate", "dsc_triangulate_rays", "dsc_tri_upload", "dsc_tri_run", "dsc_tri_download", "dsc_depth_scale_init",
     "dsc_problem_upload", "dsc_set_graph", "dsc_compute_rotations", "dsc_get_rotations", "dsc_set_rotations",
     "dsc_reset_state", "dsc_set_pcg", "dsc_set_solver", "dsc_set_early_reject", "dsc_cost", "dsc_optimize", "dsc_download", "dsc_pixel_sigma",
     "dsc_debug_linearize", "dsc_debug_matvec", "dsc_profile_kernels", "dsc_profile_triangulate", "dsc_problem_size", "dsc_knn_build", "dsc_knn_download",
@@ -59,7 +59,7 @@ class IterRecord(C.Structure):
 class OptStats(C.Structure):
     _fields_ = [("iterations", C.c_int), ("total_trials", C.c_int), ("total_pcg_iters", C.c_int), ("terminated", C.c_int),
                 ("final_chi2", C.c_double), ("device_ms", C.c_double), ("linearize_ms", C.c_double), ("pcg_ms", C.c_double),
-                ("trial_ms", C.c_double), ("kernel_launches", C.c_int), ("early_rejects", C.c_int)]
+                ("trial_ms", C.c_double), ("kernel_launches", C.c_int), ("early_rejects", C.c_int), ("pcg_unconverged", C.c_int)]
 
 
 class DscError(RuntimeError):
@@ -201,6 +201,19 @@ class Context:
                                           _fp(X1), _fp(X2), _fp(valid), _fp(cosp), C.byref(nv)))
         self.tn = n
         return X1, X2, valid.astype(bool), cosp, nv.value
+
+    def triangulate_rays(self, T1w, T2w, method, location, xn1, xn2):
+        """useTriangulationMethod with the reference's argument list: rays in, world points out (no gates)"""
+        xn1, xn2 = _f32(xn1, (-1, 3)), _f32(xn2, (-1, 3))
+        n = xn1.shape[0]
+        T1 = _f32(T1w.as34() if hasattr(T1w, "as34") else T1w, (12,))
+        T2 = _f32(T2w.as34() if hasattr(T2w, "as34") else T2w, (12,))
+        m = METHODS.get(method, 1) if isinstance(method, str) else int(method)
+        loc = LOCATIONS.get(location, 0) if isinstance(location, str) else int(location)
+        X1 = np.empty((n, 3), np.float32)
+        X2 = np.empty((n, 3), np.float32)
+        self._ck(self.lib.dsc_triangulate_rays(self.h, _fp(T1), _fp(T2), m, loc, n, _fp(xn1), _fp(xn2), _fp(X1), _fp(X2)))
+        return X1, X2
 
     def tri_upload(self, pair, uv1, uv2, d1=None, d2=None):
         uv1, uv2 = _f32(uv1, (-1, 2)), _f32(uv2, (-1, 2))

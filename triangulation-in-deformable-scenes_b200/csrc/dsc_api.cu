@@ -27,13 +27,14 @@
 
 using namespace dsc;
 
-#define DSC_VERSION 100
+#define DSC_VERSION 200
 
 struct dsc_ctx {
     int device = 0;
     int sms = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, evA = nullptr, evB = nullptr;
+    cudaEvent_t evo[4] = {nullptr, nullptr, nullptr, nullptr};      // dsc_optimize: begin, end, phase a, phase b
     std::string err;
     long long launches = 0;
 
@@ -101,7 +102,7 @@ struct dsc_ctx {
     int small_cluster = 0;                           // CTAs of the one-launch PCG of small problems (0 = not available)
     int small_max_rows = kSmallMaxRows;              // largest problem that takes that path (DSC_SMALL_MAX_ROWS overrides)
     int solver = DSC_SOLVER_AUTO;                    // dense Cholesky for small problems, PCG above (dsc_set_solver)
-    double *dnH = nullptr, *dnA = nullptr, *dn_rhs = nullptr, *dn_sol = nullptr;
+    double *dnH = nullptr, *dnA = nullptr, *dn_rhs = nullptr, *dn_sol = nullptr, *dn_l11 = nullptr;
     int dn_cap = 0;
     int early_levels = 0;                            // early rejection of clearly bad LM trials (off by default)
     double early_rtol[4] = {0, 0, 0, 0}, early_margin[4] = {0, 0, 0, 0};
@@ -242,6 +243,7 @@ extern "C" int dsc_create(int device, dsc_ctx** out) {
     ctx->sms = prop.multiProcessorCount;
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(DSC_ERR_CUDA);
     cudaEventCreate(&ctx->ev0); cudaEventCreate(&ctx->ev1); cudaEventCreate(&ctx->evA); cudaEventCreate(&ctx->evB);
+    for (auto& e : ctx->evo) if (cudaEventCreate(&e) != cudaSuccess) return bail(DSC_ERR_CUDA);
     if (cudaMalloc(&ctx->Gcur, sizeof(Globals)) != cudaSuccess) return bail(DSC_ERR_ALLOC);
     if (cudaMalloc(&ctx->Gtrial, sizeof(Globals)) != cudaSuccess) return bail(DSC_ERR_ALLOC);
     if (cudaMalloc(&ctx->lin, sizeof(LinGlobal)) != cudaSuccess) return bail(DSC_ERR_ALLOC);
@@ -281,7 +283,7 @@ extern "C" void dsc_destroy(dsc_ctx* ctx) {
     dev_free(ctx->t_uv1); dev_free(ctx->t_uv2); dev_free(ctx->t_d1); dev_free(ctx->t_d2);
     dev_free(ctx->t_X1); dev_free(ctx->t_X2); dev_free(ctx->t_cos); dev_free(ctx->t_valid);
     dev_free(ctx->X1f); dev_free(ctx->X2f); dev_free(ctx->d_perm);
-    dev_free(ctx->dnH); dev_free(ctx->dnA); dev_free(ctx->dn_rhs); dev_free(ctx->dn_sol);
+    dev_free(ctx->dnH); dev_free(ctx->dnA); dev_free(ctx->dn_rhs); dev_free(ctx->dn_sol); dev_free(ctx->dn_l11);
     dev_free(ctx->r_uv); dev_free(ctx->r_dm); dev_free(ctx->r_isg); dev_free(ctx->g_rp0); dev_free(ctx->g_col0); dev_free(ctx->g_inv);
     dev_free(ctx->g_width); dev_free(ctx->g_sums); dev_free(ctx->g_w0); dev_free(ctx->g_key0); dev_free(ctx->g_key1);
     if (ctx->g_tmp) { cudaFree(ctx->g_tmp); ctx->g_tmp = nullptr; }
@@ -301,6 +303,7 @@ extern "C" void dsc_destroy(dsc_ctx* ctx) {
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->evA) cudaEventDestroy(ctx->evA);
     if (ctx->evB) cudaEventDestroy(ctx->evB);
+    for (auto& e : ctx->evo) if (e) cudaEventDestroy(e);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -399,6 +402,41 @@ extern "C" int dsc_triangulate(dsc_ctx* ctx, const dsc_pair* pair, const dsc_tri
     s = dsc_tri_run(ctx, prm);
     if (s) return s;
     return dsc_tri_download(ctx, X1, X2, valid, cos_parallax, n_valid);
+}
+
+extern "C" int dsc_triangulate_rays(dsc_ctx* ctx, const float* T1w, const float* T2w, int method, int location, int n,
+                                    const float* xn1, const float* xn2, float* X1, float* X2) {
+    if (!ctx || !T1w || !T2w || n < 0 || (n > 0 && (!xn1 || !xn2 || !X1 || !X2))) return fail(ctx, DSC_ERR_INVALID_ARG, "dsc_triangulate_rays");
+    if (method < 0 || method > 3 || location < 0 || location > 2) return fail(ctx, DSC_ERR_INVALID_ARG, "triangulation parameters");
+    CK(cudaSetDevice(ctx->device));
+    if (n == 0) return DSC_OK;
+    dsc_pair pr{};
+    std::memcpy(pr.T1w, T1w, sizeof(pr.T1w));
+    std::memcpy(pr.T2w, T2w, sizeof(pr.T2w));
+    PairDev pd{};
+    fill_pair(&pr, pd);
+    if (n > ctx->tcap) {
+        CK(dev_alloc(ctx->t_uv1, (size_t)n)); CK(dev_alloc(ctx->t_uv2, (size_t)n));
+        CK(dev_alloc(ctx->t_d1, (size_t)n)); CK(dev_alloc(ctx->t_d2, (size_t)n));
+        CK(dev_alloc(ctx->t_X1, (size_t)3 * n)); CK(dev_alloc(ctx->t_X2, (size_t)3 * n));
+        CK(dev_alloc(ctx->t_cos, (size_t)n)); CK(dev_alloc(ctx->t_valid, (size_t)n));
+        ctx->tcap = n;
+    }
+    ctx->tn = 0; ctx->t_done = false;                      // the output buffers of the pixel stage are reused: invalidate it
+    float *d_in1 = nullptr, *d_in2 = nullptr;              // stream-ordered staging of the rays
+    CK(cudaMallocAsync(reinterpret_cast<void**>(&d_in1), sizeof(float) * 3 * (size_t)n, ctx->stream));
+    CK(cudaMallocAsync(reinterpret_cast<void**>(&d_in2), sizeof(float) * 3 * (size_t)n, ctx->stream));
+    CK(cudaMemcpyAsync(d_in1, xn1, sizeof(float) * 3 * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(d_in2, xn2, sizeof(float) * 3 * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+    triangulate_rays_kernel<<<grid_threads(ctx, n), kThreads, 0, ctx->stream>>>(n, d_in1, d_in2, pd, method, location, ctx->t_X1, ctx->t_X2);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(X1, ctx->t_X1, sizeof(float) * 3 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(X2, ctx->t_X2, sizeof(float) * 3 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaFreeAsync(d_in1, ctx->stream));
+    CK(cudaFreeAsync(d_in2, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return DSC_OK;
 }
 
 extern "C" int dsc_depth_scale_init(dsc_ctx* ctx, int which, double* scale) {
@@ -846,6 +884,7 @@ static int pcg_begin(dsc_ctx* ctx, const WeightsDev& W, double lambda) {
 // kGraphIters PCG iterations (first = 0, parity starting even) captured once per state buffer and replayed:
 // lambda and the tolerance live in CgControl, every other argument is fixed for the uploaded problem.
 constexpr int kGraphIters = 16;
+constexpr int kPcgUnconverged = 1;       // internal status of pcg_resume: iteration limit reached without convergence
 constexpr int kEarlyWorthIters = 16;     // early-reject pauses are skipped while full solves take no more than this
 static int iteration_graph(dsc_ctx* ctx, const WeightsDev& W, cudaGraphExec_t* out) {
     dsc_ctx::IterGraph* slot = nullptr;
@@ -893,7 +932,7 @@ static int pcg_resume(dsc_ctx* ctx, const WeightsDev& W, double lambda, double r
         CK(cudaStreamSynchronize(ctx->stream));
         hc = *hp;
         *k_io = hc.iters;
-        return hc.breakdown ? DSC_ERR_PCG_BREAKDOWN : DSC_OK;
+        return hc.breakdown ? DSC_ERR_PCG_BREAKDOWN : (hc.converged ? DSC_OK : kPcgUnconverged);
     }
     int poll = std::min(k == 0 ? 18 : 16, ctx->pcg.check_every);   // first poll early (well-damped solves need ~10 iterations): 2 direct + one graph
     while (k < ctx->pcg.max_iters) {
@@ -927,6 +966,7 @@ static int pcg_resume(dsc_ctx* ctx, const WeightsDev& W, double lambda, double r
     }
     *k_io = hc.iters;
     if (hc.breakdown) return DSC_ERR_PCG_BREAKDOWN;
+    if (!hc.converged) return kPcgUnconverged;        // max_iters reached: the caller treats the step as a failed solve
     return DSC_OK;
 }
 
@@ -939,7 +979,7 @@ static int dense_prepare(dsc_ctx* ctx, const WeightsDev& W) {
     const int n = ctx->n, m = 6 * n + 8;
     if (m > ctx->dn_cap) {
         CK(dev_alloc(ctx->dnH, (size_t)m * m)); CK(dev_alloc(ctx->dnA, (size_t)m * m));
-        CK(dev_alloc(ctx->dn_rhs, (size_t)m)); CK(dev_alloc(ctx->dn_sol, (size_t)m));
+        CK(dev_alloc(ctx->dn_rhs, (size_t)m)); CK(dev_alloc(ctx->dn_sol, (size_t)m)); CK(dev_alloc(ctx->dn_l11, (size_t)kDenseNB * kDenseNB));
         ctx->dn_cap = m;
     }
     CK(cudaMemsetAsync(ctx->dnH, 0, sizeof(double) * (size_t)m * m, ctx->stream));
@@ -960,11 +1000,12 @@ static int dense_solve(dsc_ctx* ctx, double lambda) {
     for (int k0 = 0; k0 < m; k0 += kDenseNB) {
         const int nb = std::min(kDenseNB, m - k0);
         const int rest = m - (k0 + nb);
-        dense_panel_kernel<<<std::max(1, (rest + kPanelThreads - 1) / kPanelThreads), kPanelThreads, 0, ctx->stream>>>(m, k0, nb, ctx->dnA, ctx->errflag);
+        const int pblocks = std::max(1, (rest + kPanelThreads - 1) / kPanelThreads);
+        dense_panel_kernel<<<pblocks, kPanelThreads, 0, ctx->stream>>>(m, k0, nb, ctx->dnA, ctx->dn_l11, ctx->errflag);
         ctx->launches++;
-        if (rest > 0) {
+        if (rest > 0) {                                        // (pblocks > 1 implies rest > 0: the copy of L11 always happens)
             const int nt = (rest + kDenseNB - 1) / kDenseNB;
-            dense_syrk_kernel<<<dim3(nt, nt), kDenseNB * 8, 0, ctx->stream>>>(m, k0, nb, ctx->dnA);
+            dense_syrk_kernel<<<dim3(nt, nt), kDenseNB * 8, 0, ctx->stream>>>(m, k0, nb, ctx->dnA, ctx->dn_l11, pblocks > 1 ? 1 : 0);
             ctx->launches++;
         }
     }
@@ -1003,15 +1044,13 @@ extern "C" int dsc_optimize(dsc_ctx* ctx, const dsc_weights* w, int n_iters, dsc
     long long launches0 = ctx->launches;
     if (ctx->n == 0) { if (stats) *stats = st; return DSC_OK; }
     WeightsDev W = make_weights(ctx, w);
-    cudaEvent_t e_begin, e_end, e_a, e_b;
-    cudaEventCreate(&e_begin); cudaEventCreate(&e_end); cudaEventCreate(&e_a); cudaEventCreate(&e_b);
-    auto cleanup = [&]() { cudaEventDestroy(e_begin); cudaEventDestroy(e_end); cudaEventDestroy(e_a); cudaEventDestroy(e_b); };
+    const bool dense = dense_active(ctx);
+    if (dense && ctx->n > DSC_DENSE_MAX) return fail(ctx, DSC_ERR_INVALID_ARG, "dense solver: too many correspondences (DSC_DENSE_MAX)");
+    cudaEvent_t e_begin = ctx->evo[0], e_end = ctx->evo[1], e_a = ctx->evo[2], e_b = ctx->evo[3];
     cudaEventRecord(e_begin, ctx->stream);
     double lambda = 0.0, ni = 2.0;
     double current = 0.0;
     bool expect_long = true;
-    const bool dense = dense_active(ctx);
-    if (dense && ctx->n > DSC_DENSE_MAX) return fail(ctx, DSC_ERR_INVALID_ARG, "dense solver: too many correspondences (DSC_DENSE_MAX)");
     const bool early_log = std::getenv("DSC_EARLY_LOG") != nullptr;     // study aid: rho at every pause, predictor off
     int rc = DSC_OK;
     int nbv = grid_threads(ctx, ctx->n);
@@ -1067,6 +1106,10 @@ extern "C" int dsc_optimize(dsc_ctx* ctx, const dsc_weights* w, int n_iters, dsc
                 }
             }
             if (rc) break;
+            // A solve that hit the iteration limit is a failed solve, as a failed factorisation is for g2o
+            // (OptimizationAlgorithmLevenberg: ok2 == false -> tempChi = max, the trial is rejected and lambda grows);
+            // it is counted in dsc_opt_stats::pcg_unconverged so that it never passes silently.
+            if (prc == kPcgUnconverged) { st.pcg_unconverged++; prc = DSC_ERR_PCG_BREAKDOWN; }
             if (prc != DSC_OK && prc != DSC_ERR_PCG_BREAKDOWN) { rc = prc; break; }
             if (prc == DSC_ERR_PCG_BREAKDOWN) { temp = std::numeric_limits<double>::max(); scale = 1e-3; }
             rec.pcg_iters += its; st.total_pcg_iters += its;
@@ -1099,7 +1142,6 @@ extern "C" int dsc_optimize(dsc_ctx* ctx, const dsc_weights* w, int n_iters, dsc
     st.device_ms = ev_ms(e_begin, e_end);
     st.final_chi2 = current;
     st.kernel_launches = (int)(ctx->launches - launches0);
-    cleanup();
     if (stats) *stats = st;
     return rc;
 }
@@ -1115,9 +1157,9 @@ extern "C" int dsc_download(dsc_ctx* ctx, float* X1, float* X2, double* X1d, dou
     double upd = 0.0;
     if (n > 0) {
         int nb = grid_threads(ctx, n);
-        double *dX1 = nullptr, *dX2 = nullptr;
-        if (X1d) CK(cudaMalloc(&dX1, sizeof(double) * 3 * n));
-        if (X2d) CK(cudaMalloc(&dX2, sizeof(double) * 3 * n));
+        // fp64 copies in the caller's order go through the CG scratch vector w ([n][6] doubles, dead between solves)
+        double* dX1 = X1d ? ctx->vec[3] : nullptr;
+        double* dX2 = X2d ? ctx->vec[3] + 3 * (size_t)n : nullptr;
         export_kernel<<<nb, kThreads, 0, ctx->stream>>>(n, ctx->P, ctx->P0, ctx->perm.empty() ? nullptr : ctx->d_perm,
                                                        ctx->X1f, ctx->X2f, dX1, dX2, ctx->part);
         ctx->launches++;
@@ -1128,8 +1170,6 @@ extern "C" int dsc_download(dsc_ctx* ctx, float* X1, float* X2, double* X1d, dou
         if (X2d) CK(cudaMemcpyAsync(X2d, dX2, sizeof(double) * 3 * n, cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaMemcpyAsync(ctx->h_pinned, ctx->part, sizeof(double) * nb, cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
-        if (dX1) cudaFree(dX1);
-        if (dX2) cudaFree(dX2);
         upd = host_sum(ctx->h_pinned, nb);
     } else CK(cudaStreamSynchronize(ctx->stream));
     if (scales) { scales[0] = g.s1; scales[1] = g.s2; }

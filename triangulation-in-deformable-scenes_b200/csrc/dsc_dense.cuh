@@ -95,11 +95,13 @@ __global__ void dense_shift_kernel(int m, const double* __restrict__ H, double l
 // ---- blocked right-looking Cholesky, lower, in place
 // Panel step k0: every block factors the 32 x 32 diagonal block itself in shared memory (redundantly: cheaper than one
 // more launch), then solves its rows of the panel, L21 = A21 L11^-T (one thread per row, the row kept in shared memory
-// so that all loops stay rolled: straight-line unrolled code of this size is instruction-fetch bound); block 0 writes
-// L11 back and raises fail[0] when a pivot is not positive.
+// so that all loops stay rolled: straight-line unrolled code of this size is instruction-fetch bound); block 0 keeps
+// L11 and raises fail[0] when a pivot is not positive.  Every block READS the unfactored A11 in this launch, so block 0
+// must not overwrite it here unless it is alone: with more than one block L11 goes to the side buffer `L11` and the
+// trailing update of the same step (dense_syrk_kernel, stream-ordered after this launch) copies it into A.
 constexpr int kPanelThreads = 128;
 __global__ void __launch_bounds__(kPanelThreads)
-dense_panel_kernel(int m, int k0, int nb, double* __restrict__ A, int* __restrict__ fail) {
+dense_panel_kernel(int m, int k0, int nb, double* __restrict__ A, double* __restrict__ L11, int* __restrict__ fail) {
     __shared__ double T[kDenseNB][kDenseNB + 1];
     __shared__ double inv[kDenseNB];
     __shared__ double xs[kDenseNB][kPanelThreads];
@@ -125,8 +127,12 @@ dense_panel_kernel(int m, int k0, int nb, double* __restrict__ A, int* __restric
     __syncthreads();
     if (blockIdx.x == 0) {
         if (bad && threadIdx.x == 0) fail[0] = 1;
+        const bool alone = gridDim.x == 1;
         for (int c = tg; c < nb; c += kPanelThreads / kDenseNB)
-            if (tr < nb && tr >= c) A[dense_at(m, k0 + tr, k0 + c)] = T[tr][c];
+            if (tr < nb && tr >= c) {
+                if (alone) A[dense_at(m, k0 + tr, k0 + c)] = T[tr][c];
+                else L11[tr * kDenseNB + c] = T[tr][c];
+            }
     }
     const int row = k0 + nb + blockIdx.x * blockDim.x + threadIdx.x;
     if (row >= m) return;
@@ -139,10 +145,16 @@ dense_panel_kernel(int m, int k0, int nb, double* __restrict__ A, int* __restric
         A[dense_at(m, row, k0 + c)] = sacc;
     }
 }
-// trailing update A22 -= L21 L21^T, lower part, 32 x 32 tile per block
+// trailing update A22 -= L21 L21^T, lower part, 32 x 32 tile per block; block (0, 0) also stores the panel's L11 from
+// the side buffer into A when the panel launch had more than one block (see dense_panel_kernel)
 __global__ void __launch_bounds__(kDenseNB * 8)
-dense_syrk_kernel(int m, int k0, int nb, double* __restrict__ A) {
+dense_syrk_kernel(int m, int k0, int nb, double* __restrict__ A, const double* __restrict__ L11, int copy_l11) {
     const int bi = blockIdx.y, bj = blockIdx.x;
+    if (copy_l11 && bi == 0 && bj == 0)
+        for (int e = threadIdx.x; e < nb * nb; e += blockDim.x) {
+            const int r = e / nb, c = e % nb;
+            if (r >= c) A[dense_at(m, k0 + r, k0 + c)] = L11[r * kDenseNB + c];
+        }
     if (bj > bi) return;
     __shared__ double Li[kDenseNB][kDenseNB + 1], Lj[kDenseNB][kDenseNB + 1];
     const int base = k0 + nb;

@@ -254,6 +254,28 @@ DSC_D void tri_dlt(F3 xn1, F3 xn2, const PoseF& T1, const PoseF& T2, F3& X) {   
     if (x3 != 0.f) X = mk3(fdv(x0, x3), fdv(x1, x3), fdv(x2, x3)); else X = mk3(0.f, 0.f, 0.f);
 }
 
+// useTriangulationMethod (Geometry.cc:216-230) for one match: xn1 / xn2 are the (normalised) bearing rays of the two
+// key points; DepthMeasurement takes the camera-frame points at the measured depth instead (cp1 / cp2).  World points out.
+DSC_D void triangulate_match(const PairDev& pr, int method, int location, F3 xn1, F3 xn2, F3 cp1, F3 cp2, F3& w1, F3& w2) {
+    if (method == 2) {
+        F3 X; tri_dlt(xn1, xn2, pr.T1f, pr.T2f, X);
+        w1 = X; w2 = X;
+        return;
+    }
+    const PoseF T21 = compose(pr.T2f, inverse(pr.T1f));
+    const PoseF Tw2 = inverse(pr.T2f);
+    F3 p1, p2;
+    if (method == 3) {                               // Geometry.cc:189-214
+        F3 point0 = apply(T21, cp1), point1 = cp2;
+        F3 xm = div3(add3(point0, point1), 2.0f);
+        if (location == 1) { p1 = xm; p2 = xm; }
+        else if (location == 2) { p1 = add3(point0, sub3(point0, xm)); p2 = add3(point1, sub3(point1, xm)); }
+        else { p1 = point0; p2 = point1; }
+    } else if (method == 0) tri_classic(xn1, xn2, T21, location, p1, p2);
+    else tri_nrslam(xn1, xn2, T21, location, p1, p2);
+    w1 = apply(Tw2, p1); w2 = apply(Tw2, p2);
+}
+
 __global__ void __launch_bounds__(kThreads)
 triangulate_kernel(int n, const float2* __restrict__ uv1, const float2* __restrict__ uv2,
                    const float* __restrict__ dep1, const float* __restrict__ dep2,
@@ -264,27 +286,14 @@ triangulate_kernel(int n, const float2* __restrict__ uv1, const float2* __restri
         float2 a = uv1[i], b = uv2[i];
         F3 ray1 = cam_unproject(pr.cam1, a.x, a.y), ray2 = cam_unproject(pr.cam2, b.x, b.y);
         F3 xn1 = normalize3(ray1), xn2 = normalize3(ray2);
-        PoseF T21 = compose(pr.T2f, inverse(pr.T1f));
-        PoseF Tw2 = inverse(pr.T2f);
-        F3 w1, w2;
-        if (tp.method == 2) {
-            F3 X; tri_dlt(xn1, xn2, pr.T1f, pr.T2f, X);
-            w1 = X; w2 = X;
-        } else {
-            F3 p1, p2;
-            if (tp.method == 3) {                        // Geometry.cc:189-214
-                float s1 = fdv(dep1[i], ray1.z), s2 = fdv(dep2[i], ray2.z);
-                F3 c1 = mk3(fm(ray1.x, s1), fm(ray1.y, s1), fm(ray1.z, s1));
-                F3 c2 = mk3(fm(ray2.x, s2), fm(ray2.y, s2), fm(ray2.z, s2));
-                F3 point0 = apply(T21, c1), point1 = c2;
-                F3 xm = div3(add3(point0, point1), 2.0f);
-                if (tp.location == 1) { p1 = xm; p2 = xm; }
-                else if (tp.location == 2) { p1 = add3(point0, sub3(point0, xm)); p2 = add3(point1, sub3(point1, xm)); }
-                else { p1 = point0; p2 = point1; }
-            } else if (tp.method == 0) tri_classic(xn1, xn2, T21, tp.location, p1, p2);
-            else tri_nrslam(xn1, xn2, T21, tp.location, p1, p2);
-            w1 = apply(Tw2, p1); w2 = apply(Tw2, p2);
+        F3 cp1 = ray1, cp2 = ray2;
+        if (tp.method == 3) {
+            float s1 = fdv(dep1[i], ray1.z), s2 = fdv(dep2[i], ray2.z);
+            cp1 = mk3(fm(ray1.x, s1), fm(ray1.y, s1), fm(ray1.z, s1));
+            cp2 = mk3(fm(ray2.x, s2), fm(ray2.y, s2), fm(ray2.z, s2));
         }
+        F3 w1, w2;
+        triangulate_match(pr, tp.method, tp.location, xn1, xn2, cp1, cp2, w1, w2);
         F3 c1 = apply(pr.T1f, w1), c2 = apply(pr.T2f, w2);
         F3 r1 = normalize3(rotT(pr.T1f.R, xn1)), r2 = normalize3(rotT(pr.T2f.R, xn2));
         float cp = fdv(dot3(r1, r2), fm(norm3(r1), norm3(r2)));
@@ -312,6 +321,21 @@ triangulate_kernel(int n, const float2* __restrict__ uv1, const float2* __restri
         X2[3 * (size_t)i + 0] = w2.x; X2[3 * (size_t)i + 1] = w2.y; X2[3 * (size_t)i + 2] = w2.z;
         valid[i] = ok ? 1 : 0;
         cosp[i] = cp;
+    }
+}
+
+// useTriangulationMethod on rays the caller already holds (Geometry.h:66-69 takes xn1 / xn2, not pixels): no camera
+// model, no gates -- the reference's function has neither.  xn[n][3] in, X[n][3] out.
+__global__ void __launch_bounds__(kThreads)
+triangulate_rays_kernel(int n, const float* __restrict__ xn1, const float* __restrict__ xn2, const __grid_constant__ PairDev pr,
+                        int method, int location, float* __restrict__ X1, float* __restrict__ X2) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const F3 a = mk3(xn1[3 * (size_t)i], xn1[3 * (size_t)i + 1], xn1[3 * (size_t)i + 2]);
+        const F3 b = mk3(xn2[3 * (size_t)i], xn2[3 * (size_t)i + 1], xn2[3 * (size_t)i + 2]);
+        F3 w1, w2;
+        triangulate_match(pr, method, location, a, b, a, b, w1, w2);
+        X1[3 * (size_t)i + 0] = w1.x; X1[3 * (size_t)i + 1] = w1.y; X1[3 * (size_t)i + 2] = w1.z;
+        X2[3 * (size_t)i + 0] = w2.x; X2[3 * (size_t)i + 1] = w2.y; X2[3 * (size_t)i + 2] = w2.z;
     }
 }
 

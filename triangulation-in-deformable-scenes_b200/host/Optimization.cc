@@ -14,6 +14,9 @@
 
 #include "../../include/dsc.h"
 #include "Mesh.h"
+#ifdef DSC_IN_REFERENCE_TREE
+#include "compat.h"          // only dsc_host::pose34 (the value types come from the real Eigen / Sophus / OpenCV)
+#endif
 
 namespace {
 
@@ -43,10 +46,17 @@ int location_id(const std::string& l) {
     if (l == "FarPoints") return DSC_LOC_FARPOINTS;
     return DSC_LOC_INRAYS;
 }
+// The reference's CameraModel has no model tag: the dynamic type decides (KannalaBrandt8 carries 8 parameters,
+// PinHole 4: Calibration/KannalaBrandt8.h:29-36, PinHole.h:36-46), the parameter count is the fallback.
+int model_id(CameraModel* c) {
+    if (dynamic_cast<KannalaBrandt8*>(c)) return DSC_CAM_KB8;
+    if (dynamic_cast<PinHole*>(c)) return DSC_CAM_PINHOLE;
+    return c->getNumberOfParameters() >= 8 ? DSC_CAM_KB8 : DSC_CAM_PINHOLE;
+}
 dsc_pair make_pair(KeyFrame& k1, KeyFrame& k2) {
     dsc_pair p{};
     auto c1 = k1.getCalibration(), c2 = k2.getCalibration();
-    p.cam1.model = c1->modelId(); p.cam2.model = c2->modelId();
+    p.cam1.model = model_id(c1.get()); p.cam2.model = model_id(c2.get());
     for (int i = 0; i < 8; ++i) {
         p.cam1.params[i] = i < c1->getNumberOfParameters() ? c1->getParameter(i) : 0.f;
         p.cam2.params[i] = i < c2->getNumberOfParameters() ? c2->getParameter(i) : 0.f;
@@ -96,8 +106,51 @@ struct PairProblem {
     double Tg[7];
 };
 
-bool gather_pair(Map* pMap, KeyFrame_ pKF1, ID kf1ID, KeyFrame_ pKF2, ID kf2ID, PairProblem& pp) {
+// The reference reads depths through KeyFrame::getDepthMeasure(x, y, false), which throws when the key frame has no
+// depth image (KeyFrame.cc:181-184) -- the case of the simulation, whose key frames only carry per-key-point depths
+// (SURVEY.md 3.1).  Probed once per key frame with the reference's own call.
+bool has_depth_image(KeyFrame& kf) {
+    if (kf.getKeyPoints().empty()) return false;
+    try {
+        cv::Point2f p = kf.getKeyPoint(0).pt;
+        (void)kf.getDepthMeasure(p.x, p.y, false);
+        return true;
+    } catch (const std::out_of_range&) {
+        return true;                       // an image exists, the probe pixel was outside it
+    } catch (const std::exception&) {
+        return false;
+    }
+}
+
+// What the device holds after the last refinement: lets calculatePixelsStandDev read the statistic without
+// gathering the Map and rebuilding the mesh again (it is valid while the same MapPoints still sit at the written-back
+// positions).
+struct Resident {
+    bool valid = false;
+    Map* map = nullptr;
+    ID kf1 = 0, kf2 = 0;
+    std::vector<MapPoint_> mp1, mp2;
+    std::vector<float> X1, X2;
+} g_res;
+
+bool resident_pair(Map* pMap, KeyFrame_ pKF1, ID kf1ID, KeyFrame_ pKF2, ID kf2ID) {
+    if (!g_res.valid || g_res.map != pMap || g_res.kf1 != kf1ID || g_res.kf2 != kf2ID) return false;
+    auto& v1 = pKF1->getMapPoints();
+    auto& v2 = pKF2->getMapPoints();
+    size_t slots = std::min(v1.size(), v2.size()), both = 0;
+    for (size_t k = 0; k < slots; ++k) both += (v1[k] && v2[k]) ? 1 : 0;
+    if (both < g_res.mp1.size()) return false;
+    for (size_t i = 0; i < g_res.mp1.size(); ++i) {
+        auto a = g_res.mp1[i]->getWorldPosition(), b = g_res.mp2[i]->getWorldPosition();
+        for (int k = 0; k < 3; ++k)
+            if (a[k] != g_res.X1[3 * i + k] || b[k] != g_res.X2[3 * i + k]) return false;
+    }
+    return true;
+}
+
+bool gather_pair(Map* pMap, KeyFrame_ pKF1, ID kf1ID, KeyFrame_ pKF2, ID kf2ID, PairProblem& pp, bool with_mesh = true) {
     pp.kf1 = pKF1; pp.kf2 = pKF2; pp.kf1Id = kf1ID; pp.kf2Id = kf2ID;
+    const bool img1 = has_depth_image(*pKF1), img2 = has_depth_image(*pKF2);
     auto& v1 = pKF1->getMapPoints();
     auto& v2 = pKF2->getMapPoints();
     size_t slots = std::min(v1.size(), v2.size());
@@ -116,10 +169,12 @@ bool gather_pair(Map* pMap, KeyFrame_ pKF1, ID kf1ID, KeyFrame_ pKF2, ID kf2ID, 
         pp.isg1.push_back(pKF1->getInvSigma2(k1.octave));                     // :781
         pp.isg2.push_back(pKF2->getInvSigma2(k2.octave));
         // :816,846 read the depth image; simulated key frames only carry per-key-point depths
-        pp.d1.push_back(pKF1->hasDepthImage() ? pKF1->getDepthMeasure(k1.pt.x, k1.pt.y, false) : (double)pKF1->getDepthMeasure((size_t)i1));
-        pp.d2.push_back(pKF2->hasDepthImage() ? pKF2->getDepthMeasure(k2.pt.x, k2.pt.y, false) : (double)pKF2->getDepthMeasure((size_t)i2));
+        pp.d1.push_back(img1 ? pKF1->getDepthMeasure(k1.pt.x, k1.pt.y, false) : (double)pKF1->getDepthMeasure((size_t)i1));
+        pp.d2.push_back(img2 ? pKF2->getDepthMeasure(k2.pt.x, k2.pt.y, false) : (double)pKF2->getDepthMeasure((size_t)i2));
     }
     int n = (int)pp.mp1.size();
+    se3_to_7(pMap->getGlobalKeyFramesTransformation(kf1ID, kf2ID), pp.Tg);    // :664 (identity the first time)
+    if (!with_mesh) return n > 0;
     if (n < 3) return false;
     // mesh on KF1's positions: 2-D Delaunay of world (x,y), adjacency, cot weights, area (:653-662)
     std::vector<double> xy(2 * (size_t)n);
@@ -130,17 +185,18 @@ bool gather_pair(Map* pMap, KeyFrame_ pKF1, ID kf1ID, KeyFrame_ pKF2, ID kf2ID, 
     }
     auto tri = dsc_host::Delaunay2D::triangulate(xy.data(), n);
     pp.graph = dsc_host::mesh_graph(V, tri, 0.0);
-    se3_to_7(pMap->getGlobalKeyFramesTransformation(kf1ID, kf2ID), pp.Tg);    // :664 (identity the first time)
     return pp.graph.n_triangles > 0 && pp.graph.area > 0.0;
 }
 
-void upload_pair(PairProblem& pp) {
+void upload_pair(PairProblem& pp, bool with_graph = true) {
     dsc_ctx* c = ctx();
+    g_res.valid = false;
     dsc_pair pr = make_pair(*pp.kf1, *pp.kf2);
     int n = (int)pp.mp1.size();
     ck(dsc_problem_upload(c, &pr, n, pp.X1.data(), pp.X2.data(), pp.uv1.data(), pp.uv2.data(), pp.d1.data(), pp.d2.data(),
                           pp.isg1.data(), pp.isg2.data(), pp.kf1->getEstimatedDepthScale(), pp.kf2->getEstimatedDepthScale(), pp.Tg),
        "dsc_problem_upload");
+    if (!with_graph) return;
     ck(dsc_set_graph(c, n, pp.graph.rowptr.data(), pp.graph.col.data(), pp.graph.w.data(), pp.graph.area, pp.graph.n_triangles, 1 | 2),
        "dsc_set_graph");
     ck(dsc_compute_rotations(c), "dsc_compute_rotations");                    // :687-688 computeR
@@ -176,6 +232,8 @@ void write_back(Map* pMap, PairProblem& pp, double* optimizationUpdate) {
     }
     if (optimizationUpdate) *optimizationUpdate += upd;
     pMap->insertGlobalKeyFramesTransformation(0, 1, se3_from_7(Tg));          // :1007 (ids hard-coded upstream)
+    g_res.valid = true; g_res.map = pMap; g_res.kf1 = pp.kf1Id; g_res.kf2 = pp.kf2Id;
+    g_res.mp1 = pp.mp1; g_res.mp2 = pp.mp2; g_res.X1 = std::move(X1); g_res.X2 = std::move(X2);
 }
 
 template <typename F>
@@ -356,24 +414,20 @@ int initializeMapFromMatches(Map& map, KeyFrame_ refKF, KeyFrame_ currKF, const 
 }
 }  // namespace dsc_host
 
+#ifndef DSC_IN_REFERENCE_TREE
 void KeyFrame::setInitialDepthScaleInSimulationImages() {
     throw std::logic_error("use dsc_host::triangulateSimulatedMapPoints: the initial depth scale is reduced on the GPU");
 }
+#endif
 
 bool useTriangulationMethod(const Eigen::Vector3f& xn1, const Eigen::Vector3f& xn2, const Sophus::SE3f& T1w, const Sophus::SE3f& T2w,
                             Eigen::Vector3f& x3D_1, Eigen::Vector3f& x3D_2, std::string TrianMethod, std::string TrianLocation) {
-    // rays in, so the batch kernel is driven through an identity pin-hole: pixel = (x/z, y/z) unprojects to the
-    // same ray direction.  Rays with z <= 0 cannot be expressed that way.
-    if (!(xn1[2] > 0.f) || !(xn2[2] > 0.f)) return false;
-    dsc_pair pr{};
-    pr.cam1.model = pr.cam2.model = DSC_CAM_PINHOLE;
-    pr.cam1.params[0] = pr.cam1.params[1] = pr.cam2.params[0] = pr.cam2.params[1] = 1.f;
-    dsc_host::pose34(T1w, pr.T1w);
-    dsc_host::pose34(T2w, pr.T2w);
-    dsc_tri_params tp{method_id(TrianMethod), location_id(TrianLocation), DSC_GATE_NONE, 1.f, 3.0e38f, 0};
-    float uv1[2] = {xn1[0] / xn1[2], xn1[1] / xn1[2]}, uv2[2] = {xn2[0] / xn2[2], xn2[1] / xn2[2]};
-    float d1 = xn1[2], d2 = xn2[2], X1[3], X2[3];
-    ck(dsc_triangulate(ctx(), &pr, &tp, 1, uv1, uv2, &d1, &d2, X1, X2, nullptr, nullptr, nullptr), "dsc_triangulate");
+    float T1[12], T2[12];
+    dsc_host::pose34(T1w, T1);
+    dsc_host::pose34(T2w, T2);
+    const float a[3] = {xn1[0], xn1[1], xn1[2]}, b[3] = {xn2[0], xn2[1], xn2[2]};
+    float X1[3], X2[3];
+    ck(dsc_triangulate_rays(ctx(), T1, T2, method_id(TrianMethod), location_id(TrianLocation), 1, a, b, X1, X2), "dsc_triangulate_rays");
     x3D_1 = Eigen::Vector3f(X1[0], X1[1], X1[2]);
     x3D_2 = Eigen::Vector3f(X2[0], X2[1], X2[2]);
     return true;                                                               // Geometry.cc:229
@@ -396,10 +450,18 @@ void arapOptimization(Map* pMap, double repBalanceWeight, double globalBalanceWe
 
 void calculatePixelsStandDev(std::shared_ptr<Map> map, PixelsError& pe) {
     for_each_pair(map.get(), [&](KeyFrame_ kf1, ID id1, KeyFrame_ kf2, ID id2) {
-        PairProblem pp;
-        if (!gather_pair(map.get(), kf1, id1, kf2, id2, pp)) return;
-        upload_pair(pp);
+        // The statistic needs the map points and the key points only: when the device still holds this pair's
+        // refinement (the usual call order: arapOptimization, then the statistic), it is read from there; otherwise
+        // points and observations are uploaded without building the mesh.
         double s[2];
+        if (resident_pair(map.get(), kf1, id1, kf2, id2)) {
+            ck(dsc_pixel_sigma(ctx(), s), "dsc_pixel_sigma");
+            pe.desvc1 = s[0]; pe.desvc2 = s[1]; pe.desv = 0.5 * (s[0] + s[1]);
+            return;
+        }
+        PairProblem pp;
+        if (!gather_pair(map.get(), kf1, id1, kf2, id2, pp, /*with_mesh=*/false)) return;
+        upload_pair(pp, /*with_graph=*/false);
         ck(dsc_pixel_sigma(ctx(), s), "dsc_pixel_sigma");
         pe.desvc1 = s[0]; pe.desvc2 = s[1]; pe.desv = 0.5 * (s[0] + s[1]);
     });

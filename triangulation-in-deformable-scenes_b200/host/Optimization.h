@@ -5,13 +5,33 @@
 //   Modules/Utils/Geometry.h:66-69                      useTriangulationMethod
 // so Modules/System/SLAM.cc:127,145, Modules/Optimization/nloptOptimization.cc:20, Modules/Mapping/Mapping.cc:311
 // and Modules/Mapping/MonocularMapInitializer.cc:313 compile against this header unchanged.
+//
+// Two builds of the same sources:
+//   * stand-alone (this image: no Eigen / Sophus / OpenCV): Map.h / Settings.h / compat.h of this directory provide the
+//     data model with the reference's names;
+//   * -DDSC_IN_REFERENCE_TREE: the reference's own headers (Map/Map.h, Map/KeyFrame.h, Calibration/*.h, System/Settings.h,
+//     Utils/CommonTypes.h) are used instead and nothing of that data model is redefined here.  tests/refapi/ holds a
+//     header tree with exactly the reference's declarations of the members this shim calls; the conformance test
+//     compiles Optimization.cc against it.
 #pragma once
 #include <memory>
 #include <string>
 #include <vector>
 
+#ifdef DSC_IN_REFERENCE_TREE
+#include "Calibration/CameraModel.h"
+#include "Calibration/KannalaBrandt8.h"
+#include "Calibration/PinHole.h"
+#include "Map/KeyFrame.h"
+#include "Map/Map.h"
+#include "Map/MapPoint.h"
+#include "System/Settings.h"
+#include "Utils/CommonTypes.h"
+#include "Visualization/MapVisualizer.h"
+#else
 #include "Map.h"
 #include "Settings.h"
+#endif
 
 /* Performs an As-Rigid-As-Possible optimization using arapOptimization inside an external loop that optimizes the
  * balance weights (g2oBundleAdjustment.cc:446-606). */
@@ -22,13 +42,16 @@ void deformationOptimization(std::shared_ptr<Map> pMap, Settings& settings, std:
 void arapOptimization(Map* pMap, double repBalanceWeight, double globalBalanceWeight, double arapBalanceWeight, double alphaWeight,
                       double betaWeight, float DepthError, int nOptIterations, double* optimizationUpdate = nullptr);
 
-/* One correspondence (Geometry.cc:216-230).  Kept for API parity: it launches a 1-element batch; callers with
- * many matches should use triangulateMatches. */
+/* One correspondence (Geometry.cc:216-230), rays in, always true -- as in the reference.  Kept for API parity: it
+ * launches a 1-element batch (dsc_triangulate_rays); callers with many matches should use triangulateMatches. */
 bool useTriangulationMethod(const Eigen::Vector3f& xn1, const Eigen::Vector3f& xn2, const Sophus::SE3f& T1w, const Sophus::SE3f& T2w,
                             Eigen::Vector3f& x3D_1, Eigen::Vector3f& x3D_2, std::string TrianMethod, std::string TrianLocation);
 
-/* Pixel-error standard deviation of the two cameras (Utils/Geometry.cc:370-498). */
+/* Pixel-error standard deviation of the two cameras (Utils/Geometry.cc:370-498).  PixelsError is the reference's
+ * struct (Utils/CommonTypes.h:23-30); it is only defined here when that header is not in the build. */
+#ifndef DSC_IN_REFERENCE_TREE
 struct PixelsError { double avgc1 = 0, avgc2 = 0, avg = 0, desvc1 = 0, desvc2 = 0, desv = 0; };
+#endif
 void calculatePixelsStandDev(std::shared_ptr<Map> Map, PixelsError& pixelsErrors);
 
 namespace dsc_host {

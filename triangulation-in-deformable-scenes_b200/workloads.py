@@ -123,3 +123,26 @@ def knn_graph(xy, k):
     np.add.at(rowptr, ii.astype(np.int64) + 1, 1)
     rowptr = np.cumsum(rowptr).astype(np.int32)
     return rowptr, jj, np.ones(len(jj), np.float64)
+
+
+def make_scene(workload, n, seed=0):
+    """The bench / full-size-parity workloads by name: 'drunkard' (config 3), 'realcolon' (config 4: distorted camera +
+    border mask; build the graph with k = 16), 'sheet' (configs 2 and 5).  Generates ~8 % more matches than n so that
+    n survive the triangulation gates."""
+    n_gen = int(n * 1.08) + 64
+    if workload == "drunkard":
+        sc = tube_scene(n_gen, seed=seed, cam=DRUNKARD_CAM, arap=1.0e7, depth_sigma=0.0003, lm_iters=30)
+        sc["name"] = "config3: Drunkard.yaml-shaped tube, 1 frame pair"
+    elif workload == "realcolon":
+        sc = tube_scene(n_gen, seed=seed, cam=REALCOLON_CAM, arap=0.1, depth_sigma=1e-6, lm_iters=30, scales=(1.0, 1.0))
+        keep = border_mask_keep(sc["uv1"], 1440, 1080) & border_mask_keep(sc["uv2"], 1440, 1080)
+        for key in ("uv1", "uv2", "d1", "d2", "original", "moved"):
+            sc[key] = sc[key][keep]
+        sc["name"] = "config4: Realcolon.yaml-shaped tube + border mask, 1 frame pair"
+    elif workload == "sheet":
+        sc = sheet_scene(n_gen, seed=seed)
+        sc["name"] = "config2: Simulation.yaml sheet, 1 frame pair"
+    else:
+        raise ValueError(f"unknown workload {workload!r}")
+    sc["workload"] = workload
+    return sc
