@@ -34,7 +34,8 @@ def parse():
     ap.add_argument("--k", type=int, default=8)
     ap.add_argument("--workload", default="drunkard", choices=["drunkard", "realcolon", "sheet", "batch"])
     ap.add_argument("--problems", type=int, default=0, help="batch workload: frame-pair problems per GPU (config 5 has 4096 in total)")
-    ap.add_argument("--streams", type=int, default=32, help="batch workload: concurrent contexts (CUDA streams) per GPU")
+    ap.add_argument("--total-problems", type=int, default=0, help="batch workload: strong scaling over this many pairs in total (config 5: 4096)")
+    ap.add_argument("--config5-problems", type=int, default=64, help="frame pairs per GPU of the config-5 sub-record of the default line (0 = skip)")
     ap.add_argument("--lm-iters", type=int, default=0, help="0 = the config's own count")
     ap.add_argument("--pcg-rtol", type=float, default=1e-10)
     ap.add_argument("--pcg-max-iters", type=int, default=6000)
@@ -331,14 +332,131 @@ def main():
     return 0
 
 
-def main_batch(args, rank, world, local):
-    """Config 5: many independent small frame pairs, sharded by problem index (p % world == rank), several
-    contexts (streams) per GPU fed from a work queue.  No collective on the data path."""
+def batch_bytes(prob_sizes, recs, stats):
+    """algorithmic bytes one lm_batch_kernel launch moves (per-phase formulas of the 1M path summed with
+    every pair's own counts): linearise 488 N + 12 S + 72 E per LM iteration; per trial 480 N (preconditioner) + 224 N (trial
+    state) + 136 N + 12 S (cost); per PCG iteration 936 N + 76 S (operator + update)."""
+    total = 0.0
+    for (n, e), st in zip(prob_sizes, stats):
+        s_ = 1.04 * e
+        total += st.iterations * (488.0 * n + 12.0 * s_ + 72.0 * e)
+        total += st.total_trials * (480.0 * n + 224.0 * n + 136.0 * n + 12.0 * s_)
+        total += st.total_pcg_iters * (936.0 * n + 76.0 * s_)
+    return total
+
+
+def run_config5(pkg, args, rank, world, local, dist, per_gpu, n_points, steps, warmup, total=None):
+    """Config 5: independent ~10k-correspondence frame pairs (config-2 generator, seed = problem index), sharded over the
+    ranks by problem index, every rank's share refined by ONE launch of lm_batch_kernel (thread-block clusters take pairs
+    from a device-side queue and run the whole LM loop of a pair).  No data-path collective; one gather of the per-problem
+    results.  total = None: weak scaling (per_gpu pairs on every GPU); total = N: strong scaling (N pairs over all GPUs)."""
     import importlib
-    import queue
+    sh = importlib.import_module(pkg.__name__ + ".sharding")
+    wl = pkg_workloads(pkg)
+    n_problems = total if total else per_gpu * world
+    sb = sh.ShardedBatch(pkg, local, n_problems, world, rank)
+    ctx = pkg.Context(local)
+    a2 = argparse.Namespace(**vars(args))
+    a2.n, a2.workload = n_points, "sheet"
+    t_build = time.perf_counter()
+
+    def problem_of(pidx):
+        sc = wl.make_scene("sheet", n_points, pidx)
+        pr = prepare(pkg, ctx, sc, a2)
+        pr["_sc"] = sc
+        return pr
+    sb.build(problem_of)
+    build_ms = (time.perf_counter() - t_build) * 1e3
+    ctx.close()
+    sc0 = sb.problems[0]["_sc"] if sb.problems else wl.make_scene("sheet", n_points, 0)
+    lm_iters = args.lm_iters or sc0["lm_iters"]
+    w = pkg.make_weights(**sc0["weights"])
+    b = sb.batch
+    b.set_pcg(rtol=args.pcg_rtol, max_iters=args.pcg_max_iters)
+    h2d = sb.upload()
+    sizes = [(len(p["X1"]), len(p["col"])) for p in sb.problems]
+    early = dict(rtol_loose=args.early_rtol, rho_margin=args.early_margin, used=False, trace_identical=None)
+    ref = None
+    for k in range(max(2, warmup)):                      # warm-up 0: every solve to the tolerance; then with early rejection
+        b.reset_state()
+        recs, stats, ms = b.optimize(w, lm_iters)
+        tr = [[(r.chi2_before, r.chi2_after, r.trials, r.accepted) for r in rr] for rr in recs]
+        if k == 0:
+            ref = tr
+            early["lm_it_per_s_full_solves_this_rank"] = sum(s_.iterations for s_ in stats) / (ms * 1e-3)
+            if len(args.early_rtol) > 0:
+                b.set_early_reject(args.early_rtol, args.early_margin)
+                early["used"] = True
+        elif early["used"] and early["trace_identical"] is None:
+            early["trace_identical"] = (tr == ref)
+            if not early["trace_identical"]:
+                b.set_early_reject((), ())
+                early["used"] = False
+
+    def barrier():
+        if dist is not None:
+            import torch
+            dist.barrier()
+            torch.cuda.synchronize()
+    barrier()
+    dev_ms, its, pcg, trials, rejects, nbytes = 0.0, 0, 0, 0, 0, 0.0
+    for _ in range(steps):
+        b.reset_state()
+        recs, stats, ms = b.optimize(w, lm_iters)
+        dev_ms += ms
+        its += sum(s_.iterations for s_ in stats)
+        pcg += sum(s_.total_pcg_iters for s_ in stats)
+        trials += sum(s_.total_trials for s_ in stats)
+        rejects += sum(s_.early_rejects for s_ in stats)
+        nbytes += batch_bytes(sizes, recs, stats)
+    barrier()
+    # end to end: host arrays in (upload + device-side graph set-up), one launch, host arrays out
+    e2e_ms = 0.0
+    for s_ in range(1 + steps):
+        barrier()
+        t1 = time.perf_counter()
+        sb.upload()
+        recs, stats, ms = b.optimize(w, lm_iters)
+        outs = b.download()
+        barrier()
+        if s_ > 0:
+            e2e_ms += (time.perf_counter() - t1) * 1e3
+    d2h = sum(o["X1"].nbytes + o["X2"].nbytes for o in outs)
+    rows = sb.result_rows(stats)
+    dev = f"cuda:{local}" if dist is not None else "cpu"
+    table = sh.gather_by_problem(dist, dev, n_problems, world, rank, rows)          # the one collective: results by problem
+    (dev_ms_max, e2e_ms_max), (its_all, pcg_all, trials_all, bytes_all) = sh.fold(dist, dev, [dev_ms, e2e_ms], [its, pcg, trials, nbytes])
+    info = b.size()
+    sb.close()
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    ach = nbytes / (dev_ms * 1e-3) / 1e9 if dev_ms > 0 else 0.0
+    rate = its_all / (dev_ms_max * 1e-3)
+    return dict(workload="config5: independent config-2 frame pairs (seed = problem index), sharded by problem index, one launch per GPU",
+                problems=n_problems, problems_per_gpu=len(sb.mine), correspondences_per_problem=n_points,
+                directed_edges_per_problem=int(np.mean([e for _, e in sizes])) if sizes else 0, lm_iters_per_problem=lm_iters,
+                scaling="strong" if total else "weak", steps=steps,
+                lm_it_per_s=rate, lm_it_per_s_per_gpu=rate / world, problems_per_s=rate / lm_iters,
+                e2e_lm_it_per_s=(lm_iters * n_problems * steps) / (e2e_ms_max * 1e-3), ms_per_step=dev_ms_max / steps,
+                e2e_ms_per_step=e2e_ms_max / steps, h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(d2h),
+                pcg_iters_per_lm_iter=pcg_all / max(1.0, its_all), lm_trials_per_problem=trials_all / max(1, n_problems * steps),
+                early_reject=early, cluster_ctas=info["cluster_ctas"], clusters_per_gpu=info["clusters"], gpu_launches_per_step=1,
+                roofline=dict(bound="hbm", kernel="lm_batch_kernel", achieved=ach, peak=peak, unit="GB/s", frac=ach / peak,
+                              note="algorithmic bytes of all phases of all pairs of this rank / launch time; a pair's working set "
+                                   "(~18 MB) is L2-resident while its cluster refines it, so the fraction of the HBM peak can exceed 1"),
+                gathered=dict(problems=int(table.shape[0]), final_chi2_sum=float(table[:, 0].sum()), lm_iterations=int(table[:, 1].sum())),
+                host_build_ms_this_rank=build_ms)
+
+
+def main_batch(args, rank, world, local):
+    """`--workload batch`: config 5 as the headline of the line (value = LM iterations/s over all pairs of all GPUs)."""
+    os.environ["OMP_NUM_THREADS"] = str(max(1, (os.cpu_count() or 8) // max(1, world)))
     import __graft_entry__ as g
     pkg = g.package()
-    sh = importlib.import_module(pkg.__name__ + ".sharding")
     dist = None
     if world > 1:
         import torch
@@ -348,91 +466,35 @@ def main_batch(args, rank, world, local):
             dist.init_process_group("nccl", device_id=torch.device("cuda", local))
             dist.barrier()
     n = args.n if args.n != 1_000_000 else 10_000
-    per_gpu = args.problems or 16
-    mine = sh.shard(per_gpu * world, world, rank)
-    args.n, args.workload = n, "sheet"
-    ctxs = [pkg.Context(local) for _ in range(max(1, args.streams))]
-    probs = []
-    for pidx in mine:                                      # host-side synthesis + graph, untimed
-        sc = make_scene(pkg, args, seed=pidx)
-        probs.append((sc, prepare(pkg, ctxs[0], sc, args)))
-    lm_iters = args.lm_iters or probs[0][0]["lm_iters"]
-    w = pkg.make_weights(**probs[0][0]["weights"])
-    for c in ctxs:
-        c.set_pcg(rtol=args.pcg_rtol, max_iters=args.pcg_max_iters, check_every=64)
-        if len(args.early_rtol) > 0:
-            c.set_early_reject(args.early_rtol, args.early_margin)
-
-    def run_all():
-        q = queue.Queue()
-        for pr in probs:
-            q.put(pr)
-        res = [[0.0, 0, 0, 0] for _ in ctxs]               # device ms, LM its, PCG its, launches
-
-        def worker(k):
-            c = ctxs[k]
-            l0 = c.launch_count()
-            while True:
-                try:
-                    sc, prob = q.get_nowait()
-                except queue.Empty:
-                    break
-                upload(c, prob)
-                recs, st = c.optimize(w, lm_iters)
-                c.download(doubles=False)
-                res[k][0] += st.device_ms
-                res[k][1] += st.iterations
-                res[k][2] += st.total_pcg_iters
-            res[k][3] = c.launch_count() - l0
-        th = [threading.Thread(target=worker, args=(k,)) for k in range(len(ctxs))]
-        t0 = time.perf_counter()
-        for t in th:
-            t.start()
-        for t in th:
-            t.join()
-        for c in ctxs:
-            c.synchronize()
-        return res, (time.perf_counter() - t0) * 1e3
-
-    for _ in range(args.warmup):
-        run_all()
     sampler = ClockSampler(local) if rank == 0 else None
-    if dist is not None:
-        import torch
-        dist.barrier()
-        torch.cuda.synchronize()
-    wall, its, pcg, launches = 0.0, 0, 0, 0
-    for _ in range(args.steps):
-        res, ms = run_all()
-        wall += ms
-        its += sum(r[1] for r in res)
-        pcg += sum(r[2] for r in res)
-        launches += sum(r[3] for r in res)
-    if dist is not None:
-        import torch
-        dist.barrier()
-        torch.cuda.synchronize()
+    c5 = run_config5(pkg, args, rank, world, local, dist, args.problems or 128, n, args.steps, args.warmup, total=args.total_problems or None)
     clocks = sampler.stop() if sampler else None
-    (wall,), (its, pcg, launches) = sh.fold(dist, f"cuda:{local}" if dist is not None else "cpu", [wall], [its, pcg, launches])
     if rank == 0:
-        n_c, E = ctxs[0].problem_size()
-        line = dict(metric="non-rigid LM iterations/s, batch of independent 10k-correspondence frame pairs", value=its / (wall * 1e-3),
-                    unit="LM it/s", n_gpus=world, steps=args.steps, warmup=args.warmup, ms_per_step=wall / args.steps,
-                    higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64", data="synthetic",
-                    config=dict(workload="config5: batch of independent config-2 frame pairs, sharded by problem index",
-                                correspondences_per_problem=n_c, directed_edges_per_problem=E, problems_per_gpu=per_gpu,
-                                problems=per_gpu * world, streams_per_gpu=len(ctxs), lm_iters_per_problem=lm_iters,
-                                pcg_rtol=args.pcg_rtol, pcg_iters_per_lm_iter=pcg / max(1, its),
-                                timing="host clock around the synchronised step (concurrent streams), max over ranks; includes "
-                                       "per-problem upload and download", l2="per-problem working set ~10 MB: L2 resident by design"),
-                    e2e=dict(value=its / (wall * 1e-3), unit="LM it/s", h2d_bytes_per_step=int(len(probs) * (n_c * 96 + E * 12)),
-                             d2h_bytes_per_step=int(len(probs) * n_c * 24)),
-                    gpu_launches=int(launches), clocks=clocks, roofline=None, cpu_baseline=None)
+        cpu = None
+        if not args.no_cpu_baseline and world == 1:
+            try:
+                from oracle import bench_cpu
+                with _stdout_to_stderr():
+                    r = bench_cpu.run_reference("sheet", n, args.k, args.lm_iters, pcg_rtol=args.pcg_rtol, budget_s=120.0)
+                cpu = r["cpu_baseline"]
+                cpu["sample"] = "ONE pair of the batch (the CPU refines the pairs one after the other, all threads on each): " + cpu["sample"]
+            except Exception as ex:
+                cpu = dict(value=None, unit="LM it/s", cores=1, kind="port", sample=f"failed: {ex}")
+        line = dict(metric="non-rigid LM iterations/s, batch of independent 10k-correspondence frame pairs", value=c5["lm_it_per_s"],
+                    unit="LM it/s", n_gpus=world, steps=args.steps, warmup=args.warmup, ms_per_step=c5["ms_per_step"],
+                    higher_is_better=True, scaling=c5["scaling"], vs_baseline=None, dtype="f64", data="synthetic",
+                    config=dict(workload=c5["workload"], problems=c5["problems"], problems_per_gpu=c5["problems_per_gpu"],
+                                correspondences_per_problem=c5["correspondences_per_problem"], k=args.k,
+                                lm_iters_per_problem=c5["lm_iters_per_problem"], pcg_rtol=args.pcg_rtol, early_reject=c5["early_reject"],
+                                cluster_ctas=c5["cluster_ctas"], clusters_per_gpu=c5["clusters_per_gpu"],
+                                l2="a pair's working set (~18 MB) is L2-resident by design; the batch of a GPU (~2.3 GB at 128 pairs) is not",
+                                parallelism=f"{world} GPUs x {c5['problems_per_gpu']} pairs, no data-path collective"),
+                    e2e=dict(value=c5["e2e_lm_it_per_s"], unit="LM it/s", h2d_bytes_per_step=c5["h2d_bytes_per_step"],
+                             d2h_bytes_per_step=c5["d2h_bytes_per_step"], ms_per_step=c5["e2e_ms_per_step"]),
+                    gpu_launches=int(args.steps * world), clocks=clocks, roofline=c5["roofline"], cpu_baseline=cpu, config5=c5)
         print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
-    for c in ctxs:
-        c.close()
     return 0
 
 

@@ -234,6 +234,42 @@ int dsc_knn_download(dsc_ctx* ctx, int32_t* rowptr, int32_t* col);
 /* problem size as seen by the library: n correspondences, E directed edges */
 int dsc_problem_size(const dsc_ctx* ctx, long long* n, long long* n_edges);
 
+/* ---- batches of independent frame pairs (BASELINE.json configs[4], and the <= 31 independent
+ * refinements per outer iteration of the weight search, Modules/Optimization/nloptOptimization.cc:5-37) ---------------
+ * Arrays of pair descriptors with prefix offsets: pair p owns correspondences point_offset[p] .. point_offset[p+1] of
+ * the concatenated point arrays (same element layout as dsc_problem_upload) and the directed edges edge_offset[p] ..
+ * edge_offset[p+1] of col / w; rowptr is the concatenation of the pairs' own CSR row pointers (n_p + 1 entries each,
+ * every one starting at 0: pair p's begin at rowptr[point_offset[p] + p]).  dsc_batch_optimize refines ALL pairs in one
+ * kernel launch: thread-block clusters take pairs from a device-side queue and run the whole Levenberg-Marquardt loop
+ * of a pair (the same algorithm as dsc_optimize, PCG linear solves) without returning to the host.  n_weights = 1: one
+ * dsc_weights for every pair; n_weights = n_problems: one each (the weight search).  records[n_problems][n_iters] and
+ * stats[n_problems] may be NULL; device_ms = CUDA-event time of the launch. */
+typedef struct dsc_batch dsc_batch;
+typedef struct {
+    dsc_pair  pair;
+    double    scale1, scale2;      /* initial depth scales                                             */
+    double    Tg7[7];              /* initial T_global (qx qy qz qw tx ty tz); all-zero quaternion = identity */
+    double    area;                /* mesh area                                                        */
+    long long n_triangles;         /* ARAP information = arap * n_triangles^2                          */
+} dsc_batch_pair;
+int  dsc_batch_create(int device, dsc_batch** out);
+void dsc_batch_destroy(dsc_batch* batch);
+const char* dsc_batch_last_error(const dsc_batch* batch);
+int  dsc_batch_upload(dsc_batch* batch, int n_problems, const dsc_batch_pair* pairs, const long long* point_offset,
+                      const float* X1, const float* X2, const float* uv1, const float* uv2,
+                      const double* depth1, const double* depth2, const float* inv_sigma2_1, const float* inv_sigma2_2,
+                      const long long* edge_offset, const int32_t* rowptr, const int32_t* col, const double* w, int reorder);
+int  dsc_batch_set_pcg(dsc_batch* batch, const dsc_pcg_params* prm);
+int  dsc_batch_set_early_reject(dsc_batch* batch, int n_levels, const double* rtol_loose, const double* rho_margin);
+int  dsc_batch_reset_state(dsc_batch* batch);
+int  dsc_batch_optimize(dsc_batch* batch, const dsc_weights* weights, int n_weights, int n_iters, dsc_iter_record* records,
+                        dsc_opt_stats* stats, double* device_ms);
+/* results in the callers' numbering, concatenated like the inputs: X1/X2 [sum n][3] float, scales [n_problems][2],
+ * Tg7 [n_problems][7], update [n_problems] (any may be NULL) */
+int  dsc_batch_download(dsc_batch* batch, float* X1, float* X2, double* scales, double* Tg7, double* update);
+/* pairs uploaded, their correspondences, CTAs per cluster and clusters of the last launch */
+int  dsc_batch_size(const dsc_batch* batch, int* n_problems, long long* n_points, int* cluster_ctas, int* clusters);
+
 #ifdef __cplusplus
 }
 #endif

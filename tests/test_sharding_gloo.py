@@ -20,8 +20,15 @@ mine = sh.shard(37, world, rank)
 gathered = [None] * world
 dist.all_gather_object(gathered, mine)
 times, counts = sh.fold(dist, "cpu", [10.0 * (rank + 1), 5.0], [len(mine), 3])
+# the one collective of the batched path: per-problem result rows -> the table in global problem order on every rank
+import numpy as np
+rows = np.array([[100.0 + p, 2.0 * p] for p in mine])
+table = sh.gather_by_problem(dist, "cpu", 37, world, rank, rows)
+ok = bool(np.array_equal(table[:, 0], 100.0 + np.arange(37)) and np.array_equal(table[:, 1], 2.0 * np.arange(37)))
+oks = [None] * world
+dist.all_gather_object(oks, ok)
 if rank == 0:
-    print(json.dumps(dict(shards=gathered, times=times, counts=counts, rate=sh.throughput(counts[0], times[0]))))
+    print(json.dumps(dict(shards=gathered, times=times, counts=counts, rate=sh.throughput(counts[0], times[0]), gather_ok=oks)))
 dist.destroy_process_group()
 """
 
@@ -47,6 +54,7 @@ def test_two_rank_sharding_and_fold(tmp_path):
     assert js["times"] == [20.0, 5.0]                                     # max over ranks
     assert js["counts"] == [37.0, 6.0]                                    # sum over ranks
     assert js["rate"] == 37 / 0.02
+    assert js["gather_ok"] == [True, True]                                # both ranks hold the table in problem order
 
 
 def test_shard_edge_cases(pkg):
@@ -59,3 +67,9 @@ def test_shard_edge_cases(pkg):
     assert sum(len(sh.shard(4096, 8, r)) for r in range(8)) == 4096
     with pytest.raises(ValueError):
         sh.shard(4, 2, 2)
+    assert [sh.owner(p, 4) for p in (0, 3, 4, 9)] == [(0, 0), (3, 0), (0, 1), (1, 2)]
+    import numpy as np
+    t = sh.gather_by_problem(None, "cpu", 5, 1, 0, np.arange(10.0).reshape(5, 2))        # single process: identity
+    assert np.array_equal(t, np.arange(10.0).reshape(5, 2))
+    with pytest.raises(ValueError):
+        sh.gather_by_problem(None, "cpu", 5, 2, 0, np.zeros((2, 1)))                       # rank 0 of 2 owns 3 of 5

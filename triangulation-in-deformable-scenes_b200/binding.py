@@ -24,6 +24,8 @@ EXPORTS = [
     "dsc_triangulate", "dsc_triangulate_rays", "dsc_tri_upload", "dsc_tri_run", "dsc_tri_download", "dsc_depth_scale_init",
     "dsc_problem_upload", "dsc_set_graph", "dsc_compute_rotations", "dsc_get_rotations", "dsc_set_rotations",
     "dsc_reset_state", "dsc_set_pcg", "dsc_set_solver", "dsc_set_early_reject", "dsc_cost", "dsc_optimize", "dsc_download", "dsc_pixel_sigma",
+    "dsc_batch_create", "dsc_batch_destroy", "dsc_batch_last_error", "dsc_batch_upload", "dsc_batch_set_pcg", "dsc_batch_set_early_reject",
+    "dsc_batch_reset_state", "dsc_batch_optimize", "dsc_batch_download", "dsc_batch_size",
     "dsc_debug_linearize", "dsc_debug_matvec", "dsc_profile_kernels", "dsc_profile_triangulate", "dsc_problem_size", "dsc_knn_build", "dsc_knn_download",
 ]
 KERNEL_NAMES = ["cg_spmv", "cg_update", "linearize", "cost", "precond", "apply_update", "rotations"]
@@ -62,6 +64,11 @@ class OptStats(C.Structure):
                 ("trial_ms", C.c_double), ("kernel_launches", C.c_int), ("early_rejects", C.c_int), ("pcg_unconverged", C.c_int)]
 
 
+class BatchPair(C.Structure):
+    _fields_ = [("pair", Pair), ("scale1", C.c_double), ("scale2", C.c_double), ("Tg7", C.c_double * 7), ("area", C.c_double),
+                ("n_triangles", C.c_longlong)]
+
+
 class DscError(RuntimeError):
     def __init__(self, status, msg):
         super().__init__(f"dsc status {status}: {msg}")
@@ -84,6 +91,8 @@ def load_library(path=None):
     lib.dsc_last_error.restype = C.c_char_p
     lib.dsc_status_string.restype = C.c_char_p
     lib.dsc_destroy.restype = None
+    lib.dsc_batch_last_error.restype = C.c_char_p
+    lib.dsc_batch_destroy.restype = None
     _lib = lib
     return lib
 
@@ -361,3 +370,104 @@ class Context:
         self._ck(self.lib.dsc_knn_download(self.h, _fp(rowptr), _fp(col)))
         col = col[:E.value]
         return rowptr, col, np.ones(E.value, np.float64)
+
+
+class Batch:
+    """One dsc_batch: many independent frame pairs refined by ONE kernel launch (include/dsc.h, dsc_batch_*)."""
+
+    def __init__(self, device=0):
+        self.lib = load_library()
+        self.h = C.c_void_p()
+        st = self.lib.dsc_batch_create(int(device), C.byref(self.h))
+        if st != 0:
+            raise DscError(st, self.lib.dsc_status_string(st).decode())
+        self.np, self.point_offset = 0, np.zeros(1, np.int64)
+
+    def close(self):
+        if getattr(self, "h", None) is not None and self.h:
+            self.lib.dsc_batch_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _ck(self, st):
+        if st != 0:
+            raise DscError(st, self.lib.dsc_batch_last_error(self.h).decode())
+
+    def upload(self, problems, reorder=1):
+        """problems: list of dicts with pair, X1, X2, uv1, uv2, d1, d2, s1, s2, rowptr, col, w, area, ntri (+ optional Tg7,
+        isg1, isg2); packed into the concatenated arrays + prefix offsets the C ABI takes."""
+        n_p = len(problems)
+        pairs = (BatchPair * max(1, n_p))()
+        po, eo = np.zeros(n_p + 1, np.int64), np.zeros(n_p + 1, np.int64)
+        for k, pr in enumerate(problems):
+            pairs[k].pair = pr["pair"]
+            pairs[k].scale1, pairs[k].scale2 = float(pr["s1"]), float(pr["s2"])
+            tg = pr.get("Tg7")
+            for q in range(7):
+                pairs[k].Tg7[q] = float(tg[q]) if tg is not None else 0.0
+            pairs[k].area, pairs[k].n_triangles = float(pr["area"]), int(pr["ntri"])
+            po[k + 1] = po[k] + len(pr["X1"])
+            eo[k + 1] = eo[k] + len(pr["col"])
+
+        def cat(key, dt, shape):
+            if n_p == 0:
+                return np.zeros(tuple(0 if d < 0 else d for d in shape), dt)
+            return np.ascontiguousarray(np.concatenate([np.asarray(pr[key], dt).reshape(shape) for pr in problems]))
+        X1, X2 = cat("X1", np.float32, (-1, 3)), cat("X2", np.float32, (-1, 3))
+        uv1, uv2 = cat("uv1", np.float32, (-1, 2)), cat("uv2", np.float32, (-1, 2))
+        d1, d2 = cat("d1", np.float64, (-1,)), cat("d2", np.float64, (-1,))
+        has_isg = n_p > 0 and all(pr.get("isg1") is not None for pr in problems)
+        s1 = cat("isg1", np.float32, (-1,)) if has_isg else None
+        s2 = cat("isg2", np.float32, (-1,)) if has_isg else None
+        rowptr, col, w = cat("rowptr", np.int32, (-1,)), cat("col", np.int32, (-1,)), cat("w", np.float64, (-1,))
+        self._ck(self.lib.dsc_batch_upload(self.h, n_p, pairs, _fp(po), _fp(X1), _fp(X2), _fp(uv1), _fp(uv2), _fp(d1), _fp(d2),
+                                           _fp(s1), _fp(s2), _fp(eo), _fp(rowptr), _fp(col), _fp(w), int(reorder)))
+        self.np, self.point_offset = n_p, po
+        return int(X1.nbytes + X2.nbytes + uv1.nbytes + uv2.nbytes + d1.nbytes + d2.nbytes + rowptr.nbytes + col.nbytes + w.nbytes)
+
+    def set_pcg(self, rtol=1e-10, max_iters=4000, check_every=32):
+        p = PcgParams(float(rtol), int(max_iters), int(check_every))
+        self._ck(self.lib.dsc_batch_set_pcg(self.h, C.byref(p)))
+
+    def set_early_reject(self, rtol_loose=(1e-3, 1e-4), rho_margin=(1.0, 0.5)):
+        r = np.ascontiguousarray(np.atleast_1d(rtol_loose), np.float64)
+        m = np.ascontiguousarray(np.atleast_1d(rho_margin), np.float64)
+        self._ck(self.lib.dsc_batch_set_early_reject(self.h, len(r), _fp(r), _fp(m)))
+
+    def reset_state(self):
+        self._ck(self.lib.dsc_batch_reset_state(self.h))
+
+    def optimize(self, weights, n_iters):
+        """weights: one Weights (shared) or a list with one per pair -> (records[pair][iteration], stats[pair], device ms)"""
+        ws = weights if isinstance(weights, (list, tuple)) else [weights]
+        warr = (Weights * len(ws))(*ws)
+        recs = (IterRecord * max(1, self.np * max(1, n_iters)))()
+        stats = (OptStats * max(1, self.np))()
+        ms = C.c_double()
+        self._ck(self.lib.dsc_batch_optimize(self.h, warr, len(ws), int(n_iters), recs, stats, C.byref(ms)))
+        out = [[recs[p * n_iters + i] for i in range(stats[p].iterations)] for p in range(self.np)]
+        return out, [stats[p] for p in range(self.np)], ms.value
+
+    def download(self):
+        n = int(self.point_offset[-1])
+        X1, X2 = np.empty((n, 3), np.float32), np.empty((n, 3), np.float32)
+        scales, tg, upd = np.empty((self.np, 2)), np.empty((self.np, 7)), np.empty(self.np)
+        self._ck(self.lib.dsc_batch_download(self.h, _fp(X1), _fp(X2), _fp(scales), _fp(tg), _fp(upd)))
+        po = self.point_offset
+        return [dict(X1=X1[po[p]:po[p + 1]], X2=X2[po[p]:po[p + 1]], scales=scales[p], Tg=tg[p], update=upd[p]) for p in range(self.np)]
+
+    def size(self):
+        a, b, c, d = C.c_int(), C.c_longlong(), C.c_int(), C.c_int()
+        self._ck(self.lib.dsc_batch_size(self.h, C.byref(a), C.byref(b), C.byref(c), C.byref(d)))
+        return dict(problems=a.value, points=b.value, cluster_ctas=c.value, clusters=d.value)

@@ -13,6 +13,7 @@
 #include "dsc_graph.cuh"
 #include "dsc_dense.cuh"
 #include "dsc_small.cuh"
+#include "dsc_batch.cuh"
 
 #include <algorithm>
 #include <chrono>
@@ -1457,5 +1458,253 @@ extern "C" int dsc_knn_download(dsc_ctx* ctx, int32_t* rowptr, int32_t* col) {
     CK(cudaMemcpyAsync(rowptr, ctx->knn_rowptr, sizeof(int) * ((size_t)ctx->knn_n + 1), cudaMemcpyDeviceToHost, ctx->stream));
     if (col && ctx->knn_E > 0) CK(cudaMemcpyAsync(col, ctx->knn_col, sizeof(int) * (size_t)ctx->knn_E, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    return DSC_OK;
+}
+
+// ------------------------------------------------------------------ batched frame pairs (include/dsc.h: dsc_batch_*)
+// One sub-context per pair owns that pair's device buffers (set-up reuses dsc_problem_upload / dsc_set_graph /
+// dsc_compute_rotations); the refinement of ALL pairs is one launch of lm_batch_kernel (dsc_batch.cuh).
+struct dsc_batch {
+    int device = 0, sms = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::string err;
+    std::vector<dsc_ctx*> ctxs;              // grown on demand, reused between uploads
+    int n_problems = 0;
+    std::vector<long long> point_offset;
+    BatchProblem* d_probs = nullptr; BatchIterRec* d_recs = nullptr; BatchResult* d_res = nullptr; int* d_queue = nullptr;
+    double* d_part = nullptr;                // per problem: [kBatchPartStride] linearisation / trial partials
+    size_t probs_cap = 0, recs_cap = 0, part_cap = 0;
+    int cluster = kSmallCluster, n_clusters = 0;
+    dsc_pcg_params pcg{1e-10, 4000, 32};
+    int early_levels = 0;
+    double early_rtol[4] = {0, 0, 0, 0}, early_margin[4] = {0, 0, 0, 0};
+    long long launches = 0;
+};
+
+namespace {
+constexpr int kBatchPartStride = kSmallCluster * (kLinPart + 4);
+int bfail(dsc_batch* b, int code, const std::string& what) {
+    if (b) b->err = std::string(status_str(code)) + ": " + what;
+    return code;
+}
+#define BCK(call)                                                                              \
+    do {                                                                                       \
+        cudaError_t e_ = (call);                                                               \
+        if (e_ != cudaSuccess)                                                                 \
+            return bfail(bt, DSC_ERR_CUDA, std::string(#call) + " -> " + cudaGetErrorString(e_)); \
+    } while (0)
+}  // namespace
+
+extern "C" int dsc_batch_create(int device, dsc_batch** out) {
+    if (!out) return DSC_ERR_INVALID_ARG;
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) return DSC_ERR_NO_DEVICE;
+    if (device < 0 || device >= count) return DSC_ERR_INVALID_ARG;
+    dsc_batch* bt = new dsc_batch();
+    bt->device = device;
+    auto bail = [&](int code) { dsc_batch_destroy(bt); return code; };
+    if (cudaSetDevice(device) != cudaSuccess) return bail(DSC_ERR_CUDA);
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return bail(DSC_ERR_CUDA);
+    bt->sms = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&bt->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(DSC_ERR_CUDA);
+    if (cudaEventCreate(&bt->ev0) != cudaSuccess || cudaEventCreate(&bt->ev1) != cudaSuccess) return bail(DSC_ERR_CUDA);
+    if (cudaFuncSetAttribute(lm_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWinBytes) != cudaSuccess) return bail(DSC_ERR_CUDA);
+    // CTAs per cluster: 16 (non-portable) when the device schedules it, else 8; DSC_BATCH_CLUSTER overrides (1, 2, 4, 8, 16)
+    bt->cluster = cudaFuncSetAttribute(lm_batch_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess ? kSmallCluster : 8;
+    cudaGetLastError();
+    if (const char* cs = std::getenv("DSC_BATCH_CLUSTER")) {
+        int v = std::atoi(cs);
+        if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16) bt->cluster = v;
+    }
+    *out = bt;
+    return DSC_OK;
+}
+
+extern "C" void dsc_batch_destroy(dsc_batch* bt) {
+    if (!bt) return;
+    cudaSetDevice(bt->device);
+    if (bt->stream) cudaStreamSynchronize(bt->stream);
+    for (dsc_ctx* c : bt->ctxs) dsc_destroy(c);
+    dev_free(bt->d_probs); dev_free(bt->d_recs); dev_free(bt->d_res); dev_free(bt->d_queue); dev_free(bt->d_part);
+    if (bt->ev0) cudaEventDestroy(bt->ev0);
+    if (bt->ev1) cudaEventDestroy(bt->ev1);
+    if (bt->stream) cudaStreamDestroy(bt->stream);
+    delete bt;
+}
+
+extern "C" const char* dsc_batch_last_error(const dsc_batch* bt) { return bt ? bt->err.c_str() : "null batch"; }
+
+extern "C" int dsc_batch_size(const dsc_batch* bt, int* n_problems, long long* n_points, int* cluster_ctas, int* clusters) {
+    if (!bt) return DSC_ERR_INVALID_ARG;
+    if (n_problems) *n_problems = bt->n_problems;
+    if (n_points) *n_points = bt->point_offset.empty() ? 0 : bt->point_offset.back();
+    if (cluster_ctas) *cluster_ctas = bt->cluster;
+    if (clusters) *clusters = bt->n_clusters;
+    return DSC_OK;
+}
+
+extern "C" int dsc_batch_set_pcg(dsc_batch* bt, const dsc_pcg_params* prm) {
+    if (!bt || !prm || !(prm->rtol > 0.0) || prm->max_iters < 1) return bfail(bt, DSC_ERR_INVALID_ARG, "dsc_batch_set_pcg");
+    bt->pcg = *prm;
+    return DSC_OK;
+}
+
+extern "C" int dsc_batch_set_early_reject(dsc_batch* bt, int n_levels, const double* rtol_loose, const double* rho_margin) {
+    if (!bt || n_levels < 0 || n_levels > 4 || (n_levels > 0 && (!rtol_loose || !rho_margin)))
+        return bfail(bt, DSC_ERR_INVALID_ARG, "dsc_batch_set_early_reject");
+    for (int l = 0; l < n_levels; ++l)
+        if (!(rtol_loose[l] > 0.0) || !(rho_margin[l] >= 0.0) || (l > 0 && !(rtol_loose[l] < rtol_loose[l - 1])))
+            return bfail(bt, DSC_ERR_INVALID_ARG, "tolerances must be positive and strictly decreasing, margins >= 0");
+    bt->early_levels = n_levels;
+    for (int l = 0; l < n_levels; ++l) { bt->early_rtol[l] = rtol_loose[l]; bt->early_margin[l] = rho_margin[l]; }
+    return DSC_OK;
+}
+
+extern "C" int dsc_batch_upload(dsc_batch* bt, int n_problems, const dsc_batch_pair* pairs, const long long* point_offset,
+                                const float* X1, const float* X2, const float* uv1, const float* uv2,
+                                const double* depth1, const double* depth2, const float* inv_sigma2_1, const float* inv_sigma2_2,
+                                const long long* edge_offset, const int32_t* rowptr, const int32_t* col, const double* w, int reorder) {
+    if (!bt || n_problems < 0 || (n_problems > 0 && (!pairs || !point_offset || !edge_offset || !rowptr)))
+        return bfail(bt, DSC_ERR_INVALID_ARG, "dsc_batch_upload");
+    BCK(cudaSetDevice(bt->device));
+    for (int p = 0; p < n_problems; ++p)
+        if (point_offset[p + 1] < point_offset[p] || edge_offset[p + 1] < edge_offset[p] || point_offset[p + 1] - point_offset[p] > 0x7fffffffLL)
+            return bfail(bt, DSC_ERR_INVALID_ARG, "offsets must be non-decreasing prefix sums");
+    while ((int)bt->ctxs.size() < n_problems) {
+        dsc_ctx* c = nullptr;
+        int st = dsc_create(bt->device, &c);
+        if (st) return bfail(bt, st, "sub-context");
+        bt->ctxs.push_back(c);
+    }
+    bt->n_problems = 0;
+    if (n_problems == 0) bt->point_offset.assign(1, 0LL);
+    else bt->point_offset.assign(point_offset, point_offset + n_problems + 1);
+    for (int p = 0; p < n_problems; ++p) {
+        dsc_ctx* c = bt->ctxs[p];
+        const long long o = point_offset[p], e = edge_offset[p];
+        const int n = (int)(point_offset[p + 1] - o);
+        const dsc_batch_pair& bp = pairs[p];
+        const bool ident = bp.Tg7[0] == 0 && bp.Tg7[1] == 0 && bp.Tg7[2] == 0 && bp.Tg7[3] == 0;
+        int st = dsc_problem_upload(c, &bp.pair, n, X1 + 3 * o, X2 + 3 * o, uv1 + 2 * o, uv2 + 2 * o, depth1 + o, depth2 + o,
+                                    inv_sigma2_1 ? inv_sigma2_1 + o : nullptr, inv_sigma2_2 ? inv_sigma2_2 + o : nullptr,
+                                    bp.scale1, bp.scale2, ident ? nullptr : bp.Tg7);
+        if (!st) st = dsc_set_graph(c, n, rowptr + o + p, col + e, w + e, bp.area, bp.n_triangles, reorder);
+        if (!st) st = dsc_compute_rotations(c);
+        if (st) return bfail(bt, st, "problem " + std::to_string(p) + ": " + c->err);
+    }
+    for (int p = 0; p < n_problems; ++p) BCK(cudaStreamSynchronize(bt->ctxs[p]->stream));
+    bt->n_problems = n_problems;
+    return DSC_OK;
+}
+
+extern "C" int dsc_batch_reset_state(dsc_batch* bt) {
+    if (!bt) return DSC_ERR_INVALID_ARG;
+    for (int p = 0; p < bt->n_problems; ++p) {
+        int st = dsc_reset_state(bt->ctxs[p]);
+        if (st) return bfail(bt, st, bt->ctxs[p]->err);
+    }
+    return DSC_OK;
+}
+
+extern "C" int dsc_batch_optimize(dsc_batch* bt, const dsc_weights* weights, int n_weights, int n_iters, dsc_iter_record* records,
+                                  dsc_opt_stats* stats, double* device_ms) {
+    if (!bt || !weights || n_iters < 0 || (n_weights != 1 && n_weights != bt->n_problems))
+        return bfail(bt, DSC_ERR_INVALID_ARG, "dsc_batch_optimize: one dsc_weights for all pairs or one per pair");
+    BCK(cudaSetDevice(bt->device));
+    const int np = bt->n_problems;
+    if (device_ms) *device_ms = 0.0;
+    if (np == 0) return DSC_OK;
+    if ((size_t)np > bt->probs_cap) {
+        BCK(dev_alloc(bt->d_probs, (size_t)np)); BCK(dev_alloc(bt->d_res, (size_t)np));
+        BCK(dev_alloc(bt->d_queue, (size_t)2 + 4096));
+        bt->probs_cap = (size_t)np;
+    }
+    if ((size_t)np * kBatchPartStride > bt->part_cap) { BCK(dev_alloc(bt->d_part, (size_t)np * kBatchPartStride)); bt->part_cap = (size_t)np * kBatchPartStride; }
+    const size_t nrec = (size_t)np * (size_t)std::max(1, n_iters);
+    if (nrec > bt->recs_cap) { BCK(dev_alloc(bt->d_recs, nrec)); bt->recs_cap = nrec; }
+    std::vector<BatchProblem> hp((size_t)np);
+    for (int p = 0; p < np; ++p) {
+        dsc_ctx* c = bt->ctxs[p];
+        const dsc_weights* w = weights + (n_weights == 1 ? 0 : p);
+        int st = ready(c, w);
+        if (st) return bfail(bt, st, "problem " + std::to_string(p) + ": " + c->err);
+        BatchProblem& B = hp[p];
+        B.n = c->n;
+        B.P = c->P; B.Ptrial = c->Ptrial; B.Q = c->Q;
+        B.uv = c->uv; B.dm = c->dm; B.isg = c->isg;
+        B.sliceptr = c->sliceptr; B.ecol = c->ecol; B.ewgt = c->ewgt;
+        B.Je = c->Je; B.U = c->U; B.D = c->D; B.Minv = c->Minv; B.b = c->b;
+        B.v = make_vecs(c); B.Ginv = c->small + 48;
+        B.G = c->Gcur; B.lin = c->lin; B.err = c->errflag;
+        B.part = bt->d_part + (size_t)p * kBatchPartStride;
+        B.gpart0 = c->gpart[0]; B.gpart1 = c->gpart[1]; B.dpart = c->dpart; B.bpart = c->bpart;
+        B.pair = c->pair; B.W = make_weights(c, w);
+    }
+    BCK(cudaMemcpyAsync(bt->d_probs, hp.data(), sizeof(BatchProblem) * (size_t)np, cudaMemcpyHostToDevice, bt->stream));
+    BCK(cudaMemsetAsync(bt->d_recs, 0, sizeof(BatchIterRec) * nrec, bt->stream));
+    BCK(cudaMemsetAsync(bt->d_res, 0, sizeof(BatchResult) * (size_t)np, bt->stream));
+    BCK(cudaMemsetAsync(bt->d_queue, 0, sizeof(int) * (2 + 4096), bt->stream));
+    BatchParams prm{};
+    prm.n_iters = n_iters; prm.max_pcg = bt->pcg.max_iters; prm.rtol = bt->pcg.rtol; prm.early_levels = bt->early_levels;
+    for (int l = 0; l < 4; ++l) { prm.early_rtol[l] = bt->early_rtol[l]; prm.early_margin[l] = bt->early_margin[l]; }
+    // persistent clusters: as many as the device keeps resident at once (one CTA per SM: 250 registers x 256 threads), at
+    // most one per pair; the queue balances the load
+    cudaLaunchConfig_t cfg{};
+    cudaLaunchAttribute at[1];
+    for (;;) {
+        cfg = cudaLaunchConfig_t{};
+        cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = kWinBytes; cfg.stream = bt->stream;
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = bt->cluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        cfg.gridDim = dim3(bt->cluster);
+        int maxc = 0;
+        cudaError_t e = cudaOccupancyMaxActiveClusters(&maxc, lm_batch_kernel, &cfg);
+        if (e == cudaSuccess && maxc > 0) { bt->n_clusters = std::min(std::min(maxc, np), 4096); break; }
+        cudaGetLastError();
+        if (bt->cluster > 1) { bt->cluster /= 2; continue; }
+        return bfail(bt, DSC_ERR_CUDA, std::string("no cluster configuration of lm_batch_kernel is schedulable: ") + cudaGetErrorString(e));
+    }
+    cfg.gridDim = dim3(bt->n_clusters * bt->cluster);
+    BCK(cudaEventRecord(bt->ev0, bt->stream));
+    BCK(cudaLaunchKernelEx(&cfg, lm_batch_kernel, (const BatchProblem*)bt->d_probs, np, prm, bt->d_queue, bt->d_recs, bt->d_res));
+    BCK(cudaEventRecord(bt->ev1, bt->stream));
+    bt->launches++;
+    std::vector<BatchResult> hr((size_t)np);
+    BCK(cudaMemcpyAsync(hr.data(), bt->d_res, sizeof(BatchResult) * (size_t)np, cudaMemcpyDeviceToHost, bt->stream));
+    if (records && n_iters > 0) {
+        static_assert(sizeof(BatchIterRec) == sizeof(dsc_iter_record), "record layouts must agree");
+        BCK(cudaMemcpyAsync(records, bt->d_recs, sizeof(BatchIterRec) * nrec, cudaMemcpyDeviceToHost, bt->stream));
+    }
+    BCK(cudaStreamSynchronize(bt->stream));
+    float ms = 0.f;
+    BCK(cudaEventElapsedTime(&ms, bt->ev0, bt->ev1));
+    if (device_ms) *device_ms = (double)ms;
+    int rc = DSC_OK;
+    for (int p = 0; p < np; ++p) {
+        const BatchResult& r = hr[p];
+        if (stats) {
+            dsc_opt_stats st{};
+            st.iterations = r.iterations; st.total_trials = r.total_trials; st.total_pcg_iters = r.total_pcg_iters;
+            st.terminated = r.terminated; st.final_chi2 = r.final_chi2; st.early_rejects = r.early_rejects;
+            st.pcg_unconverged = r.pcg_unconverged; st.device_ms = (double)ms; st.kernel_launches = p == 0 ? 1 : 0;
+            stats[p] = st;
+        }
+        if (r.status != 0 && rc == DSC_OK) rc = bfail(bt, r.status, "problem " + std::to_string(p) + ": cost is not finite");
+    }
+    return rc;
+}
+
+extern "C" int dsc_batch_download(dsc_batch* bt, float* X1, float* X2, double* scales, double* Tg7, double* update) {
+    if (!bt) return DSC_ERR_INVALID_ARG;
+    for (int p = 0; p < bt->n_problems; ++p) {
+        const long long o = bt->point_offset[p];
+        int st = dsc_download(bt->ctxs[p], X1 ? X1 + 3 * o : nullptr, X2 ? X2 + 3 * o : nullptr, nullptr, nullptr,
+                              scales ? scales + 2 * (size_t)p : nullptr, Tg7 ? Tg7 + 7 * (size_t)p : nullptr, update ? update + p : nullptr);
+        if (st) return bfail(bt, st, bt->ctxs[p]->err);
+    }
     return DSC_OK;
 }

@@ -128,12 +128,34 @@ DSC_D double4 ldg256(const double4* p) {
     asm("ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w) : "l"(p));
     return r;
 }
+// Load policy of the kernels that exist in two forms.  kRO = true: the data is constant for the whole launch (the
+// per-phase kernels of the 1M path): non-coherent read-only loads.  kRO = false: other CTAs of the SAME launch write the
+// data between cluster barriers (the one-launch LM of the batched path, dsc_batch.cuh): loads that are coherent at L2
+// (ld.global.cg -> LDG.E.ENL2.256.STRONG.GPU), never served from a stale L1 / read-only line.
+template <bool kRO>
+DSC_D double4 ld256(const double4* p) {
+    if (kRO) return ldg256(p);
+    double4 r;
+    asm volatile("ld.global.cg.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w) : "l"(p) : "memory");
+    return r;
+}
+template <bool kRO>
+DSC_D double ld64(const double* p) { return kRO ? __ldg(p) : __ldcg(p); }
 struct P8 { D3 a, b; };                             // X1, X2 of one correspondence
+template <bool kRO = true>
 DSC_D P8 load_P(const double* __restrict__ P, int n, int i) {
     const double4* p = reinterpret_cast<const double4*>(P);
-    double4 u = ldg256(p + (size_t)i), v = ldg256(p + (size_t)n + (size_t)i);
+    double4 u = ld256<kRO>(p + (size_t)i), v = ld256<kRO>(p + (size_t)n + (size_t)i);
     P8 r; r.a = d3(u.x, u.y, u.z); r.b = d3(v.x, v.y, v.z);
     return r;
+}
+template <bool kRO>
+DSC_D void load6_t(const double* V, int i, D3& a, D3& b) {
+    const double2* p = reinterpret_cast<const double2*>(V) + 3 * (size_t)i;
+    double2 u, v, w;
+    if (kRO) { u = p[0]; v = p[1]; w = p[2]; }
+    else { u = __ldcg(p); v = __ldcg(p + 1); w = __ldcg(p + 2); }
+    a = d3(u.x, u.y, v.x); b = d3(v.y, w.x, w.y);
 }
 DSC_D void load6(const double* __restrict__ V, int i, D3& a, D3& b) {
     const double2* p = reinterpret_cast<const double2*>(V) + 3 * (size_t)i;
@@ -416,6 +438,7 @@ template <typename T>
 DSC_D T* blk21(T* base, int i) { return base + ((size_t)(i >> 5) * 21) * 32 + (i & 31); }
 
 // block-Jacobi preconditioner: Minv_i = (D_i + lambda I)^-1 (packed), Ginv = (C + lambda I)^-1
+template <bool kRO = true>
 DSC_D void precond_block(const double* __restrict__ D, int i, double lambda, double* __restrict__ Minv, int* __restrict__ err,
                          double (&M)[21]) {
     const double* Dp = blk21(D, i);
@@ -424,7 +447,7 @@ DSC_D void precond_block(const double* __restrict__ D, int i, double lambda, dou
     for (int r = 0; r < 6; ++r)
 #pragma unroll
         for (int c = r; c < 6; ++c) {
-            double v = Dp[pk<6>(r, c) * 32] + (r == c ? lambda : 0.0);
+            double v = (kRO ? Dp[pk<6>(r, c) * 32] : __ldcg(Dp + pk<6>(r, c) * 32)) + (r == c ? lambda : 0.0);
             A[r * 6 + c] = v; A[c * 6 + r] = v;
         }
     if (!spd_inverse<6>(A, Ai)) {
@@ -440,9 +463,10 @@ DSC_D void precond_block(const double* __restrict__ D, int i, double lambda, dou
 #pragma unroll
         for (int c = r; c < 6; ++c) { M[pk<6>(r, c)] = Ai[r * 6 + c]; Mp[pk<6>(r, c) * 32] = Ai[r * 6 + c]; }
 }
+template <bool kRO = true>
 DSC_D void precond_global(const LinGlobal* __restrict__ lin, double lambda, double* __restrict__ Ginv, int* __restrict__ err) {
     double A[64], Ai[64];
-    for (int k = 0; k < 64; ++k) A[k] = lin->C[k];
+    for (int k = 0; k < 64; ++k) A[k] = kRO ? lin->C[k] : __ldcg(&lin->C[k]);
     for (int r = 0; r < 8; ++r) A[r * 8 + r] += lambda;
     if (!spd_inverse<8>(A, Ai)) {
         atomicExch(err, 1);
@@ -824,34 +848,46 @@ __global__ void ctl_set_kernel(CgControl* ctl, double lambda, int set_lambda, do
 
 // ================================================================== LM trial: x_new = x (+) dx
 // Ptrial = P + dx (points), trial globals = exp(dx_T) * T_g, s + ds; scale partial = sum dx (lambda dx + b)
+template <bool kRO>
+DSC_D double apply_update_rows(int n, int first, int stride, const double* __restrict__ P, const double* __restrict__ x,
+                               const double* __restrict__ b, double lambda, double* __restrict__ Ptrial) {
+    double acc = 0.0;
+    for (int i = first; i < n; i += stride) {
+        D3 x1, x2, b1, b2;
+        load6_t<kRO>(x, i, x1, x2); load6_t<kRO>(b, i, b1, b2);
+        P8 Pi = load_P<kRO>(P, n, i);
+        double4* o = reinterpret_cast<double4*>(Ptrial);
+        o[i] = make_double4(Pi.a.x + x1.x, Pi.a.y + x1.y, Pi.a.z + x1.z, 0.0);
+        o[(size_t)n + i] = make_double4(Pi.b.x + x2.x, Pi.b.y + x2.y, Pi.b.z + x2.z, 0.0);
+        acc += dot(x1, lambda * x1 + b1) + dot(x2, lambda * x2 + b2);
+    }
+    return acc;
+}
+// the 8 global unknowns of the trial state; returns their share of dx.(lambda dx + b)
+DSC_D double apply_update_globals(const Globals& g, const double* xg, const double* bg, double lambda, Globals& o) {
+    double upd[6];
+    for (int k = 0; k < 6; ++k) upd[k] = xg[k];
+    double T[7];
+    se3_oplus(g.Tg, upd, T);
+    for (int k = 0; k < 7; ++k) o.Tg[k] = T[k];
+    o.s1 = g.s1 + xg[6]; o.s2 = g.s2 + xg[7];
+    quat_to_rot(o.Tg, o.Rg);
+    double acc = 0.0;
+    for (int k = 0; k < 8; ++k) acc += xg[k] * (lambda * xg[k] + bg[k]);
+    return acc;
+}
 __global__ void __launch_bounds__(kThreads)
 apply_update_kernel(int n, const double* __restrict__ P, const double* __restrict__ x, const double* __restrict__ xg,
                     const double* __restrict__ b, const LinGlobal* __restrict__ lin, double lambda,
                     const Globals* __restrict__ Gcur, double* __restrict__ Ptrial, Globals* __restrict__ Gtrial,
                     double* __restrict__ part) {
     __shared__ double sm[kThreads / 32];
-    double acc[1] = {0.0};
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        D3 x1, x2, b1, b2;
-        load6(x, i, x1, x2); load6(b, i, b1, b2);
-        P8 Pi = load_P(P, n, i);
-        double4* o = reinterpret_cast<double4*>(Ptrial);
-        o[i] = make_double4(Pi.a.x + x1.x, Pi.a.y + x1.y, Pi.a.z + x1.z, 0.0);
-        o[(size_t)n + i] = make_double4(Pi.b.x + x2.x, Pi.b.y + x2.y, Pi.b.z + x2.z, 0.0);
-        acc[0] += dot(x1, lambda * x1 + b1) + dot(x2, lambda * x2 + b2);
-    }
+    double acc[1];
+    acc[0] = apply_update_rows<true>(n, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x, P, x, b, lambda, Ptrial);
     if (blockIdx.x == 0 && threadIdx.x == 0) {
-        Globals g = *Gcur;
-        double upd[6];
-        for (int k = 0; k < 6; ++k) upd[k] = xg[k];
-        double T[7];
-        se3_oplus(g.Tg, upd, T);
-        Globals o;
-        for (int k = 0; k < 7; ++k) o.Tg[k] = T[k];
-        o.s1 = g.s1 + xg[6]; o.s2 = g.s2 + xg[7];
-        quat_to_rot(o.Tg, o.Rg);
+        Globals g = *Gcur, o;
+        acc[0] += apply_update_globals(g, xg, lin->bg, lambda, o);
         *Gtrial = o;
-        for (int k = 0; k < 8; ++k) acc[0] += xg[k] * (lambda * xg[k] + lin->bg[k]);
     }
     block_reduce<1>(acc, sm);
     if (threadIdx.x == 0) part[blockIdx.x] = acc[0];

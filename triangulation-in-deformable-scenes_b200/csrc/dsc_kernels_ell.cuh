@@ -14,22 +14,25 @@ constexpr int kLinThreads = 256;             // linearise: 234 registers, one bl
 
 struct Window { const double4* x1; const double4* x2; const double4* q; int v0, nv; };
 
+// kRO: load policy of the points (dsc_kernels.cuh, ld256); the rotations Q are constant during a refinement in both forms
+template <bool kRO = true>
 DSC_D void stage_window(double4* sw, const double* __restrict__ P, const double* __restrict__ Q, int n, int v0, int nv, bool with_q) {
     const double4* p = reinterpret_cast<const double4*>(P);
     const double4* q = reinterpret_cast<const double4*>(Q);
     for (int k = threadIdx.x; k < nv; k += blockDim.x) {
-        sw[k] = ldg256(p + (size_t)v0 + k);
-        sw[kSortGroup + k] = ldg256(p + (size_t)n + v0 + k);
+        sw[k] = ld256<kRO>(p + (size_t)v0 + k);
+        sw[kSortGroup + k] = ld256<kRO>(p + (size_t)n + v0 + k);
         if (with_q) sw[2 * kSortGroup + k] = ldg256(q + (size_t)v0 + k);
     }
 }
+template <bool kRO = true>
 DSC_D void fetch_point(const Window& w, const double* __restrict__ P, int n, int j, P8& Pj) {
     const unsigned jl = (unsigned)(j - w.v0);
     double4 a, b;
     if (jl < (unsigned)w.nv) { a = w.x1[jl]; b = w.x2[jl]; }
     else {
-        a = ldg256(reinterpret_cast<const double4*>(P) + (size_t)j);
-        b = ldg256(reinterpret_cast<const double4*>(P) + (size_t)n + (size_t)j);
+        a = ld256<kRO>(reinterpret_cast<const double4*>(P) + (size_t)j);
+        b = ld256<kRO>(reinterpret_cast<const double4*>(P) + (size_t)n + (size_t)j);
     }
     Pj.a = d3(a.x, a.y, a.z); Pj.b = d3(b.x, b.y, b.z);
 }
@@ -123,22 +126,19 @@ DSC_D void unary_cost(const CamF& cam, const double* R, const double* t, D3 X, f
 }
 
 // ------------------------------------------------------------------ K6 cost: part[grid][3]
-__global__ void __launch_bounds__(kEllThreads, 2)
-cost_ell_kernel(int n, const double* __restrict__ P, const double* __restrict__ Q, const float4* __restrict__ uv,
-                const double2* __restrict__ dm, const float2* __restrict__ isg, const int* __restrict__ sliceptr,
-                const int* __restrict__ ecol, const double* __restrict__ ewgt, const Globals* __restrict__ Gp,
-                const __grid_constant__ PairDev pr, const __grid_constant__ WeightsDev W, double* __restrict__ part) {
-    extern __shared__ double4 sw[];
-    __shared__ double sm[3 * (kEllThreads / 32)];
-    __shared__ Globals G;
-    if (threadIdx.x == 0) G = *Gp;
+// The tiles first, first + stride, ... of one block; acc[3] = this thread's share of (reprojection, depth, ARAP) chi2.
+// sw = the block's dynamic shared window (kWinBytes).
+template <bool kRO>
+DSC_D void cost_tiles(int first, int stride, int n, const double* __restrict__ P, const double* __restrict__ Q,
+                      const float4* __restrict__ uv, const double2* __restrict__ dm, const float2* __restrict__ isg,
+                      const int* __restrict__ sliceptr, const int* __restrict__ ecol, const double* __restrict__ ewgt,
+                      const Globals& G, const PairDev& pr, const WeightsDev& W, double4* sw, double (&acc)[3]) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
-    double acc[3] = {0.0, 0.0, 0.0};
     const int ntiles = (n + kSortGroup - 1) / kSortGroup;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    for (int tile = first; tile < ntiles; tile += stride) {
         const int v0 = tile * kSortGroup, nv = min(kSortGroup, n - v0);
         __syncthreads();
-        stage_window(sw, P, Q, n, v0, nv, true);
+        stage_window<kRO>(sw, P, Q, n, v0, nv, true);
         __syncthreads();
         const Window win{sw, sw + kSortGroup, sw + 2 * kSortGroup, v0, nv};
         for (int ls = warp; ls * 32 < nv; ls += wpb) {
@@ -156,7 +156,7 @@ cost_ell_kernel(int n, const double* __restrict__ P, const double* __restrict__ 
                 if (j == i) continue;
                 P8 Pj;
                 double qj[4];
-                fetch_point(win, P, n, j, Pj);
+                fetch_point<kRO>(win, P, n, j, Pj);
                 fetch_quat(win, Q, j, qj);
                 ArapGrad g;
                 arap_edge<false>(Pi, Pj, qi, qj, wv, W.inv_area, G, g);
@@ -174,6 +174,18 @@ cost_ell_kernel(int n, const double* __restrict__ P, const double* __restrict__ 
         }
     }
     __syncthreads();
+}
+__global__ void __launch_bounds__(kEllThreads, 2)
+cost_ell_kernel(int n, const double* __restrict__ P, const double* __restrict__ Q, const float4* __restrict__ uv,
+                const double2* __restrict__ dm, const float2* __restrict__ isg, const int* __restrict__ sliceptr,
+                const int* __restrict__ ecol, const double* __restrict__ ewgt, const Globals* __restrict__ Gp,
+                const __grid_constant__ PairDev pr, const __grid_constant__ WeightsDev W, double* __restrict__ part) {
+    extern __shared__ double4 sw[];
+    __shared__ double sm[3 * (kEllThreads / 32)];
+    __shared__ Globals G;
+    if (threadIdx.x == 0) G = *Gp;
+    double acc[3] = {0.0, 0.0, 0.0};
+    cost_tiles<true>(blockIdx.x, gridDim.x, n, P, Q, uv, dm, isg, sliceptr, ecol, ewgt, G, pr, W, sw, acc);
     block_reduce<3>(acc, sm);
     if (threadIdx.x == 0) { part[3 * blockIdx.x] = acc[0]; part[3 * blockIdx.x + 1] = acc[1]; part[3 * blockIdx.x + 2] = acc[2]; }
 }
@@ -183,26 +195,24 @@ cost_ell_kernel(int n, const double* __restrict__ P, const double* __restrict__ 
 // ELL slots (coalesced).  Global rows: T_g gradient from the per-row sum Bg_i = sum_j 2 W e_ij g_ij (the directed
 // twins carry the same e and g):  b_w = -2 sum_i X1_i x Bg_i,  b_v = 2 sum_i Bg_i;  C_TT = sum_dir W gT gT^T.
 // part[grid][kLinPart]: chi2[3], max diag, bg[8], C_TT packed (21), C_ss (2)  -- reduced by finalize_linearize_kernel.
-__global__ void __launch_bounds__(kLinThreads, 1)
-linearize_ell_kernel(int n, const double* __restrict__ P, const double* __restrict__ Q, const float4* __restrict__ uv,
-                     const double2* __restrict__ dm, const float2* __restrict__ isg, const int* __restrict__ sliceptr,
-                     const int* __restrict__ ecol, const double* __restrict__ ewgt, const Globals* __restrict__ Gp,
-                     const __grid_constant__ PairDev pr, const __grid_constant__ WeightsDev W,
-                     double* __restrict__ b, double* __restrict__ D, double* __restrict__ U, double* __restrict__ Je,
-                     double* __restrict__ part) {
-    extern __shared__ double4 sw[];
+template <bool kRO>
+DSC_D void linearize_tiles(int first, int stride, int n, const double* __restrict__ P, const double* __restrict__ Q,
+                           const float4* __restrict__ uv, const double2* __restrict__ dm, const float2* __restrict__ isg,
+                           const int* __restrict__ sliceptr, const int* __restrict__ ecol, const double* __restrict__ ewgt,
+                           const Globals& G, const PairDev& pr, const WeightsDev& W,
+                           double* __restrict__ b, double* __restrict__ D, double* __restrict__ U, double* __restrict__ Je,
+                           double* __restrict__ part_row /* [kLinPart] of this block */, double4* sw) {
     __shared__ double wacc[kLinThreads / 32][kLinPart];
     __shared__ double wmax[kLinThreads / 32];
-    __shared__ Globals G;
-    if (threadIdx.x == 0) G = *Gp;
+    __syncthreads();                                   // (a previous phase of the same block may still read the scratch)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     for (int k = lane; k < kLinPart; k += 32) wacc[warp][k] = 0.0;
     if (lane == 0) wmax[warp] = 0.0;
     const int ntiles = (n + kSortGroup - 1) / kSortGroup;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    for (int tile = first; tile < ntiles; tile += stride) {
         const int v0 = tile * kSortGroup, nv = min(kSortGroup, n - v0);
         __syncthreads();
-        stage_window(sw, P, Q, n, v0, nv, true);
+        stage_window<kRO>(sw, P, Q, n, v0, nv, true);
         __syncthreads();
         const Window win{sw, sw + kSortGroup, sw + 2 * kSortGroup, v0, nv};
         for (int ls = warp; ls * 32 < nv; ls += wpb) {
@@ -225,7 +235,7 @@ linearize_ell_kernel(int n, const double* __restrict__ P, const double* __restri
                 if (!act || j == i) continue;                  // padding slot: its Je record stays all-zero
                 P8 Pj;
                 double qj[4];
-                fetch_point(win, P, n, j, Pj);
+                fetch_point<kRO>(win, P, n, j, Pj);
                 fetch_quat(win, Q, j, qj);
                 ArapGrad g;
                 arap_edge<true>(Pi, Pj, qi, qj, wv, W.inv_area, G, g);
@@ -336,7 +346,7 @@ linearize_ell_kernel(int n, const double* __restrict__ P, const double* __restri
     }
     __syncthreads();
     if (threadIdx.x == 0) {
-        double* o = part + (size_t)kLinPart * blockIdx.x;
+        double* o = part_row;
         for (int k = 0; k < kLinPart; ++k) {
             double s = 0.0;
             for (int wv = 0; wv < (int)(blockDim.x >> 5); ++wv) s += wacc[wv][k];
@@ -346,6 +356,20 @@ linearize_ell_kernel(int n, const double* __restrict__ P, const double* __restri
         for (int wv = 0; wv < (int)(blockDim.x >> 5); ++wv) m = fmax(m, wmax[wv]);
         o[3] = m;
     }
+}
+
+__global__ void __launch_bounds__(kLinThreads, 1)
+linearize_ell_kernel(int n, const double* __restrict__ P, const double* __restrict__ Q, const float4* __restrict__ uv,
+                     const double2* __restrict__ dm, const float2* __restrict__ isg, const int* __restrict__ sliceptr,
+                     const int* __restrict__ ecol, const double* __restrict__ ewgt, const Globals* __restrict__ Gp,
+                     const __grid_constant__ PairDev pr, const __grid_constant__ WeightsDev W,
+                     double* __restrict__ b, double* __restrict__ D, double* __restrict__ U, double* __restrict__ Je,
+                     double* __restrict__ part) {
+    extern __shared__ double4 sw[];
+    __shared__ Globals G;
+    if (threadIdx.x == 0) G = *Gp;
+    linearize_tiles<true>(blockIdx.x, gridDim.x, n, P, Q, uv, dm, isg, sliceptr, ecol, ewgt, G, pr, W, b, D, U, Je,
+                          part + (size_t)kLinPart * blockIdx.x, sw);
 }
 
 }  // namespace dsc

@@ -1,10 +1,19 @@
-"""Multi-GPU plumbing for the one way this path shards: independent frame-pair problems.
+"""Multi-GPU plumbing for the way this path shards: independent frame-pair problems (BASELINE.json configs[4]).
 
-One process per GPU.  A problem is owned by exactly one rank (static round-robin by problem index, the
-reference has no notion of ranks); there is NO data-path collective.  torch.distributed (NCCL on the GPU box,
-gloo in the CPU tests) is used only for the start barrier and for folding the per-rank timings / counters.
+One process per GPU.  A problem is owned by exactly one rank (static round-robin by problem index: the reference has no
+notion of ranks, and on one GPU the device-side queue of lm_batch_kernel balances the load between clusters); there is
+NO data-path collective -- a frame pair never needs another pair's data.  torch.distributed (NCCL on the GPU box, gloo in
+the CPU tests) carries three things only: the start barrier, the fold of the per-rank timings / counters, and ONE gather
+of the small per-problem results at the end ("one ncclGather / host gather of results").
+
+  shard / owner            problem index <-> rank
+  ShardedBatch             a rank's share of a batch: uploads its pairs into a dsc_batch, refines them with one launch,
+                           hands back per-problem results in GLOBAL problem order after gather_by_problem
+  fold / throughput        max-over-ranks timing, whole-job rate
 """
 import os
+
+import numpy as np
 
 
 def rank_world():
@@ -16,6 +25,11 @@ def shard(n_problems, world, rank):
     if not (0 <= rank < world):
         raise ValueError("rank out of range")
     return list(range(rank, n_problems, world))
+
+
+def owner(p, world):
+    """(rank, position inside that rank's shard) of problem p"""
+    return p % world, p // world
 
 
 def fold(dist, device, times_ms, counters):
@@ -33,3 +47,61 @@ def fold(dist, device, times_ms, counters):
 def throughput(units_all_ranks, max_ms):
     """whole-job rate: units processed by all ranks / slowest rank's time."""
     return units_all_ranks / (max_ms * 1e-3)
+
+
+def gather_by_problem(dist, device, n_problems, world, rank, local_rows):
+    """The one collective of the batched path: every rank contributes a [len(shard), C] float64 block of per-problem
+    results (row k = its k-th problem, i.e. global problem rank + k * world); every rank gets the [n_problems, C] table
+    in global problem order.  One all_gather of equally sized (zero-padded) blocks."""
+    local_rows = np.ascontiguousarray(local_rows, np.float64)
+    if local_rows.ndim == 1:
+        local_rows = local_rows[:, None]
+    mine = shard(n_problems, world, rank)
+    if local_rows.shape[0] != len(mine):
+        raise ValueError(f"rank {rank} owns {len(mine)} problems, got {local_rows.shape[0]} rows")
+    c = local_rows.shape[1]
+    if dist is None or world == 1:
+        return local_rows.copy()
+    import torch
+    per = (n_problems + world - 1) // world
+    block = torch.zeros((per, c), dtype=torch.float64, device=device)
+    if len(mine):
+        block[:len(mine)] = torch.from_numpy(local_rows).to(device)
+    table = torch.empty((world, per, c), dtype=torch.float64, device=device)
+    dist.all_gather_into_tensor(table.view(world * per, c), block)
+    t = table.cpu().numpy()
+    out = np.empty((n_problems, c), np.float64)
+    for p in range(n_problems):
+        r, k = owner(p, world)
+        out[p] = t[r, k]
+    return out
+
+
+class ShardedBatch:
+    """A rank's share of a batch of independent frame pairs.
+
+    problems_of(p) -> problem dict (Batch.upload layout) is called for the problems this rank owns only, so host-side
+    synthesis / loading is sharded too."""
+
+    def __init__(self, pkg, device, n_problems, world, rank):
+        self.pkg, self.n_problems, self.world, self.rank = pkg, n_problems, world, rank
+        self.mine = shard(n_problems, world, rank)
+        self.batch = pkg.Batch(device)
+        self.problems = []
+
+    def build(self, problem_of):
+        self.problems = [problem_of(p) for p in self.mine]
+        return self
+
+    def upload(self):
+        return self.batch.upload(self.problems)
+
+    def optimize(self, weights, n_iters):
+        return self.batch.optimize(weights, n_iters)
+
+    def result_rows(self, stats):
+        """per-problem rows of this rank for gather_by_problem: final chi2, LM iterations, trials, PCG iterations"""
+        return np.array([[s.final_chi2, s.iterations, s.total_trials, s.total_pcg_iters] for s in stats], np.float64).reshape(len(stats), 4)
+
+    def close(self):
+        self.batch.close()
