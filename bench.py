@@ -293,6 +293,14 @@ def main():
                 triangulate=dict(ms=tri["ms"], gbs=tri["bytes"] / (tri["ms"] * 1e-3) / 1e9, frac=tri["bytes"] / (tri["ms"] * 1e-3) / 1e9 / peak,
                                  points_per_s=2.0 * n_tri / (tri["ms"] * 1e-3)))
 
+    # ---- config 5 (batch of independent 10k pairs, sharded by problem index) as a sub-record of the same line at every N
+    c5 = None
+    if args.config5_problems > 0:
+        try:
+            c5 = run_config5(pkg, args, rank, world, local, dist, args.config5_problems, 10_000, 3, 2)
+        except Exception as ex:                       # a sub-record never takes the headline down (all ranks fail alike)
+            c5 = dict(error=str(ex))
+
     # ---- max over ranks, aggregate
     if dist is not None:
         import importlib
@@ -324,7 +332,7 @@ def main():
                              ms_per_step=e2e_ms / args.steps),
                     gpu_launches=int(launches), clocks=clocks, roofline=roof, cpu_baseline=cpu,
                     triangulated_points_per_s=roof["triangulate"]["points_per_s"], knn_graph_build_ms=prob["graph_build_ms"],
-                    cg_iteration_ms=cg_ms, wall_ms_per_step=wall_ms / args.steps)
+                    cg_iteration_ms=cg_ms, wall_ms_per_step=wall_ms / args.steps, config5=c5)
         print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()

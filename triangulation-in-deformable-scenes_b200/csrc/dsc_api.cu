@@ -1512,9 +1512,13 @@ extern "C" int dsc_batch_create(int device, dsc_batch** out) {
     if (cudaStreamCreateWithFlags(&bt->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(DSC_ERR_CUDA);
     if (cudaEventCreate(&bt->ev0) != cudaSuccess || cudaEventCreate(&bt->ev1) != cudaSuccess) return bail(DSC_ERR_CUDA);
     if (cudaFuncSetAttribute(lm_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWinBytes) != cudaSuccess) return bail(DSC_ERR_CUDA);
-    // CTAs per cluster: 16 (non-portable) when the device schedules it, else 8; DSC_BATCH_CLUSTER overrides (1, 2, 4, 8, 16)
-    bt->cluster = cudaFuncSetAttribute(lm_batch_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess ? kSmallCluster : 8;
+    // CTAs per cluster.  Measured on B200 (64 pairs x 10k correspondences, profiles/r02_batch_cluster_sweep.txt): the
+    // rate per SM is the same for 4, 8 and 16 CTAs (the phases are bound by load latency at 8 warps per SM, not by the
+    // barriers), so the size that tiles the 148 SMs best wins: 4 (33 clusters = 132 SMs; 16 CTAs fit 7 times = 112 SMs).
+    // DSC_BATCH_CLUSTER overrides (1, 2, 4, 8, 16; 16 is a non-portable size).
+    cudaFuncSetAttribute(lm_batch_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
     cudaGetLastError();
+    bt->cluster = 4;
     if (const char* cs = std::getenv("DSC_BATCH_CLUSTER")) {
         int v = std::atoi(cs);
         if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16) bt->cluster = v;

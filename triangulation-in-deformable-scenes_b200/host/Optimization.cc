@@ -509,8 +509,19 @@ void deformationOptimization(std::shared_ptr<Map> pMap, Settings& settings, std:
             arapOptimization(pMap.get(), x[0], x[1], x[2], alpha, beta, depthSigma, nOptIterations, &optimizationUpdate);   // :525
             rep = x[0]; glob = x[1]; arap = x[2];
         } else {
-            // "g2oArap", and "twoOptimizations" with weightsSelection "eigen" (Eigen::LevenbergMarquardt over
-            // NumericalDiff, :532-563, unsupported Eigen module): the refinement runs with the configured weights
+            // "g2oArap": the refinement with the configured weights (:566-569).
+            // "twoOptimizations" with weightsSelection "eigen" (:532-563): the reference hands Eigen::LevenbergMarquardt a
+            // functor that declares 2 residuals (EigenOptimization.h:31, Functor<double>(2, 2)) for the 3 unknowns
+            // (rep, global, arap).  Eigen's LevenbergMarquardt::minimizeInit refuses m < n ("if (n <= 0 || m < n || ...)
+            // return ImproperInputParameters", unsupported/Eigen/src/NonLinearOptimization/LevenbergMarquardt.h) before the
+            // first function evaluation, so minimize() returns 0 with x untouched and the reference then runs its "final
+            // optimization with optimized weights" on the CONFIGURED weights.  That is reproduced literally: no search,
+            // the same messages, one refinement.
+            if (sel == "twoOptimizations" && wsel != "nlopt") {
+                std::cout << "Return code: 0" << std::endl;                      // LevenbergMarquardtSpace::ImproperInputParameters
+                std::cout << "\nWEIGHTS OPTIMIZED\nOptimized repBalanceWeight: " << rep << "\nOptimized globalBalanceWeight: " << glob
+                          << "\nOptimized arapBalanceWeight: " << arap << "\n\nFinal optimization with optimized weights:\n" << std::endl;
+            }
             arapOptimization(pMap.get(), rep, glob, arap, alpha, beta, depthSigma, nOptIterations, &optimizationUpdate);
         }
         std::cout << "\nOptimization COMPLETED... " << i << " / " << nOptimizations << " iterations.\nOptimization change: "
