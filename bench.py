@@ -70,7 +70,7 @@ def pkg_workloads(pkg):
     return importlib.import_module(pkg.__name__ + ".workloads")
 
 
-def prepare(pkg, ctx, sc, args):
+def prepare(pkg, ctx, sc, args, pin=False):
     """Triangulate on the GPU, keep exactly n valid correspondences, build the k-NN graph (host, untimed)."""
     wl = pkg_workloads(pkg)
     cam = (0, sc["cam"])
@@ -89,6 +89,17 @@ def prepare(pkg, ctx, sc, args):
     ctx.tri_upload(pair, prob["uv1"], prob["uv2"], prob["d1"].astype(np.float32), prob["d2"].astype(np.float32))
     ctx.tri_run(prm)
     prob["s1"], prob["s2"] = ctx.depth_scale_init(1), ctx.depth_scale_init(2)
+    if pin:
+        # The caller's buffers are page-locked ONCE (a front end keeps its key-point / map-point arrays across frames);
+        # every step's uploads and downloads are then DMA straight from / into them -- inside the timed region.
+        for key in ("X1", "X2", "uv1", "uv2", "d1", "d2", "rowptr", "col", "w"):
+            prob[key] = np.ascontiguousarray(prob[key])
+        pkg.pin_host(*[prob[key] for key in ("X1", "X2", "uv1", "uv2", "d1", "d2", "rowptr", "col", "w")])
+        n = len(idx)
+        prob["out_tri"] = dict(X1=np.empty((n, 3), np.float32), X2=np.empty((n, 3), np.float32), valid=np.empty(n, np.uint8),
+                               cosp=np.empty(n, np.float32))
+        prob["out_opt"] = dict(X1=np.empty((n, 3), np.float32), X2=np.empty((n, 3), np.float32))
+        pkg.pin_host(*prob["out_tri"].values(), *prob["out_opt"].values())
     return prob
 
 
@@ -194,7 +205,7 @@ def main():
             dist.barrier()
     ctx = pkg.Context(local)
     sc = make_scene(pkg, args, seed=rank)
-    prob = prepare(pkg, ctx, sc, args)
+    prob = prepare(pkg, ctx, sc, args, pin=True)
     lm_iters = args.lm_iters or sc["lm_iters"]
     w = pkg.make_weights(**sc["weights"])
     ctx.set_pcg(rtol=args.pcg_rtol, max_iters=args.pcg_max_iters, check_every=64)
@@ -252,16 +263,16 @@ def main():
 
     # ---- end-to-end arm: host buffers in, host buffers out, every step
     h2d = (prob["uv1"].nbytes + prob["uv2"].nbytes) * 2 + prob["X1"].nbytes + prob["X2"].nbytes + prob["d1"].nbytes + \
-        prob["d2"].nbytes + prob["rowptr"].nbytes + prob["col"].nbytes + prob["w"].nbytes + 8 * n
+        prob["d2"].nbytes + prob["rowptr"].nbytes + prob["col"].nbytes + prob["w"].nbytes
     d2h = 2 * 12 * n * 2 + 5 * n + 2 * 12 * n
     e2e_ms = 0.0
     for s in range(1 + args.steps):                       # first pass untimed
         barrier()
         t1 = time.perf_counter()
-        ctx.triangulate(prob["pair"], prob["prm"], prob["uv1"], prob["uv2"])
+        ctx.triangulate(prob["pair"], prob["prm"], prob["uv1"], prob["uv2"], out=prob["out_tri"])
         upload(ctx, prob)
         ctx.optimize(w, lm_iters)
-        out = ctx.download(doubles=False)
+        out = ctx.download(doubles=False, out=prob["out_opt"])
         barrier()
         if s > 0:
             e2e_ms += (time.perf_counter() - t1) * 1e3

@@ -135,6 +135,11 @@ int  dsc_synchronize(dsc_ctx* ctx);
 /* CUDA-event stopwatch on the context's stream (bench.py times kernels with it) */
 int  dsc_timer_start(dsc_ctx* ctx);
 int  dsc_timer_stop(dsc_ctx* ctx, double* ms);
+/* Page-lock caller memory (cudaHostRegister) / undo it.  The upload and download entry points move pinned or registered
+ * caller memory by DMA straight from / to where it lies; pageable memory is staged through a pinned bounce buffer.  No
+ * context needed; registering an already registered range is not an error. */
+int  dsc_pin_host(const void* ptr, size_t bytes);
+int  dsc_unpin_host(const void* ptr);
 /* number of kernels this context has launched so far */
 int  dsc_launch_count(const dsc_ctx* ctx, long long* count);
 

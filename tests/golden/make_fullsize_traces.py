@@ -45,7 +45,7 @@ def main():
     b, hd, y0, chi = cport.debug_linearize(cp, w, 0.0, x)
     lam = 1e-5 * np.abs(hd).max()
     y = y0 + lam * x
-    sel = np.arange(0, p.n, max(1, p.n // 1000))
+    sel = np.arange(0, p.n, max(1, p.n // 250))
     rows = np.concatenate([np.arange(8), (8 + 6 * sel[:, None] + np.arange(6)[None, :]).reshape(-1)])
     out = dict(workload=workload, n=p.n, k=k, seed=0, directed_edges=int(p.graph.n_edges), fingerprint=fullsize.fingerprint(p),
                weights=sc["weights"], s1=p.s1, s2=p.s2, pcg_rtol=1e-12,

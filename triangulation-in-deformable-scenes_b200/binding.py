@@ -20,7 +20,7 @@ LOCATIONS = {"InRays": 0, "TwoPoints": 1, "FarPoints": 2}
 
 EXPORTS = [
     "dsc_create", "dsc_destroy", "dsc_last_error", "dsc_status_string", "dsc_version", "dsc_synchronize",
-    "dsc_timer_start", "dsc_timer_stop", "dsc_launch_count",
+    "dsc_timer_start", "dsc_timer_stop", "dsc_launch_count", "dsc_pin_host", "dsc_unpin_host",
     "dsc_triangulate", "dsc_triangulate_rays", "dsc_tri_upload", "dsc_tri_run", "dsc_tri_download", "dsc_depth_scale_init",
     "dsc_problem_upload", "dsc_set_graph", "dsc_compute_rotations", "dsc_get_rotations", "dsc_set_rotations",
     "dsc_reset_state", "dsc_set_pcg", "dsc_set_solver", "dsc_set_early_reject", "dsc_cost", "dsc_optimize", "dsc_download", "dsc_pixel_sigma",
@@ -119,6 +119,25 @@ def _f64(a, shape=None):
     return a
 
 
+def pin_host(*arrays):
+    """page-lock numpy arrays in place (dsc_pin_host): uploads from them are then plain DMA, no host-side staging"""
+    lib = load_library()
+    for a in arrays:
+        if a is not None and a.nbytes > 0:
+            if not a.flags["C_CONTIGUOUS"]:
+                raise ValueError("pin_host needs C-contiguous arrays")
+            st = lib.dsc_pin_host(C.c_void_p(a.ctypes.data), C.c_size_t(a.nbytes))
+            if st != 0:
+                raise DscError(st, "cudaHostRegister failed")
+
+
+def unpin_host(*arrays):
+    lib = load_library()
+    for a in arrays:
+        if a is not None and a.nbytes > 0:
+            lib.dsc_unpin_host(C.c_void_p(a.ctypes.data))
+
+
 def make_pair(cam1, cam2, T1w, T2w):
     """cam = (model, params[8]); Tcw = 3x4 float32 [R|t] (or an object with .as34())."""
     p = Pair()
@@ -197,14 +216,16 @@ class Context:
         loc = LOCATIONS.get(location, 0) if isinstance(location, str) else int(location)
         return TriParams(m, loc, int(gate), float(min_cos), float(min(depth_limit, 3.0e38)), int(bool(check_reproj)))
 
-    def triangulate(self, pair, prm, uv1, uv2, d1=None, d2=None):
+    def triangulate(self, pair, prm, uv1, uv2, d1=None, d2=None, out=None):
+        """out: optional dict of preallocated (e.g. page-locked) result arrays X1, X2 [n][3] f32, valid [n] u8, cosp [n] f32"""
         uv1, uv2 = _f32(uv1, (-1, 2)), _f32(uv2, (-1, 2))
         n = uv1.shape[0]
         d1, d2 = _f32(d1), _f32(d2)
-        X1 = np.empty((n, 3), np.float32)
-        X2 = np.empty((n, 3), np.float32)
-        valid = np.empty(n, np.uint8)
-        cosp = np.empty(n, np.float32)
+        out = out or {}
+        X1 = out.get("X1") if out.get("X1") is not None else np.empty((n, 3), np.float32)
+        X2 = out.get("X2") if out.get("X2") is not None else np.empty((n, 3), np.float32)
+        valid = out.get("valid") if out.get("valid") is not None else np.empty(n, np.uint8)
+        cosp = out.get("cosp") if out.get("cosp") is not None else np.empty(n, np.float32)
         nv = C.c_int()
         self._ck(self.lib.dsc_triangulate(self.h, C.byref(pair), C.byref(prm), n, _fp(uv1), _fp(uv2), _fp(d1), _fp(d2),
                                           _fp(X1), _fp(X2), _fp(valid), _fp(cosp), C.byref(nv)))
@@ -310,10 +331,12 @@ class Context:
         self._ck(self.lib.dsc_optimize(self.h, C.byref(w), int(n_iters), recs, C.byref(st)))
         return [recs[i] for i in range(st.iterations)], st
 
-    def download(self, doubles=True):
+    def download(self, doubles=True, out=None):
+        """out: optional dict of preallocated (e.g. page-locked) X1, X2 [n][3] f32 result arrays"""
         n = self.n
-        X1 = np.empty((n, 3), np.float32)
-        X2 = np.empty((n, 3), np.float32)
+        out = out or {}
+        X1 = out.get("X1") if out.get("X1") is not None else np.empty((n, 3), np.float32)
+        X2 = out.get("X2") if out.get("X2") is not None else np.empty((n, 3), np.float32)
         X1d = np.empty((n, 3), np.float64) if doubles else None
         X2d = np.empty((n, 3), np.float64) if doubles else None
         scales = np.empty(2, np.float64)

@@ -57,8 +57,11 @@ struct dsc_ctx {
     long long ntri = 0;
     Globals g0{};                         // uploaded globals
     std::vector<int> perm;                // internal index -> caller index
-    float *hs_x1 = nullptr, *hs_x2 = nullptr;    // pinned copies of the caller's points (caller order)
-    size_t hc_x1 = 0, hc_x2 = 0;
+    // pinned bounce buffer of the host -> device copies of PAGEABLE caller memory (two halves, see h2d)
+    unsigned char* bounce[2] = {nullptr, nullptr};
+    cudaEvent_t bounce_ev[2] = {nullptr, nullptr};
+    unsigned bounce_next = 0;
+    float* d_box = nullptr;                       // [4 + 4 * kMaxBlocks] bounding box of KF1's (x, y) + block partials
     float *X1f = nullptr, *X2f = nullptr;         // staging (caller order)
     int* d_perm = nullptr;
     double *P = nullptr, *Ptrial = nullptr, *P0 = nullptr, *Q = nullptr;
@@ -67,7 +70,8 @@ struct dsc_ctx {
     float2* isg = nullptr;
     double* Je = nullptr;                 // per directed edge {u, m, g}
     // raw (caller order) device copies: the internal order is produced on the device (dsc_graph.cuh)
-    float4* r_uv = nullptr; double2* r_dm = nullptr; float2* r_isg = nullptr;
+    float2 *r_uv1 = nullptr, *r_uv2 = nullptr; double *r_d1 = nullptr, *r_d2 = nullptr; float *r_isg1 = nullptr, *r_isg2 = nullptr;
+    bool r_has_isg1 = false, r_has_isg2 = false;
     int *g_rp0 = nullptr, *g_col0 = nullptr, *g_inv = nullptr, *g_width = nullptr, *g_sums = nullptr;
     double* g_w0 = nullptr;
     unsigned long long *g_key0 = nullptr, *g_key1 = nullptr;
@@ -90,10 +94,8 @@ struct dsc_ctx {
     double *gpart[2] = {nullptr, nullptr}, *dpart = nullptr, *bpart = nullptr;
     double* h_pinned = nullptr;           // pinned host scratch
     // pinned, persistent host staging of the graph / observation uploads (grown on demand)
-    int *hs_rp = nullptr, *hs_cl = nullptr, *hs_sp = nullptr;
-    double* hs_ww = nullptr;
-    float4* hs_uv = nullptr; double2* hs_dm = nullptr; float2* hs_isg = nullptr;
-    size_t hc_rp = 0, hc_cl = 0, hc_sp = 0, hc_ww = 0, hc_uv = 0, hc_dm = 0, hc_isg = 0;
+    int* hs_sp = nullptr;
+    size_t hc_sp = 0;
     // ---- kNN graph builder (device CSR of the last dsc_knn_build)
     int knn_n = 0; long long knn_E = 0;
     int *knn_rowptr = nullptr, *knn_col = nullptr;
@@ -154,6 +156,44 @@ cudaError_t pin_reserve(T*& p, size_t& cap, size_t count) {       // pinned host
     cudaError_t e = cudaMallocHost(reinterpret_cast<void**>(&p), want * sizeof(T));
     if (e == cudaSuccess) cap = want;
     return e;
+}
+
+// Host -> device copy of CALLER memory on the context's stream.  Pinned or registered memory (dsc_pin_host,
+// cudaHostRegister, cudaMallocHost) is read by the copy engine where it lies: no staging, no host loop.  Pageable memory
+// goes through the context's pinned bounce buffer in chunks; the parallel memcpy of chunk c + 1 overlaps the DMA of
+// chunk c.  The caller's memory must stay valid until the stream has been synchronised (every upload entry point does).
+constexpr size_t kBounceBytes = (size_t)16 << 20;
+int h2d(dsc_ctx* ctx, void* dst, const void* src, size_t bytes) {
+    if (bytes == 0) return DSC_OK;
+    cudaPointerAttributes at{};
+    const bool pinned = cudaPointerGetAttributes(&at, src) == cudaSuccess && at.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    if (pinned) {
+        CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+        return DSC_OK;
+    }
+    for (int h = 0; h < 2; ++h)
+        if (!ctx->bounce[h]) {
+            CK(cudaMallocHost(reinterpret_cast<void**>(&ctx->bounce[h]), kBounceBytes));
+            CK(cudaEventCreateWithFlags(&ctx->bounce_ev[h], cudaEventDisableTiming));
+        }
+    const unsigned char* s8 = static_cast<const unsigned char*>(src);
+    unsigned char* d8 = static_cast<unsigned char*>(dst);
+    for (size_t off = 0; off < bytes; off += kBounceBytes) {
+        const size_t len = std::min(kBounceBytes, bytes - off);
+        const int h = (int)(ctx->bounce_next++ & 1u);
+        CK(cudaEventSynchronize(ctx->bounce_ev[h]));               // the DMA that last read this half has finished
+        unsigned char* bb = ctx->bounce[h];
+        const long long pieces = (long long)((len + 65535) / 65536);
+#pragma omp parallel for schedule(static)
+        for (long long q = 0; q < pieces; ++q) {
+            const size_t o = (size_t)q * 65536, l = std::min((size_t)65536, len - o);
+            std::memcpy(bb + o, s8 + off + o, l);
+        }
+        CK(cudaMemcpyAsync(d8 + off, bb, len, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaEventRecord(ctx->bounce_ev[h], ctx->stream));
+    }
+    return DSC_OK;
 }
 
 int grid_threads(const dsc_ctx* c, long long n) {           // thread-per-item kernels
@@ -257,6 +297,7 @@ extern "C" int dsc_create(int device, dsc_ctx** out) {
     if (cudaMalloc(&ctx->dpart, sizeof(double) * kMaxBlocks) != cudaSuccess) return bail(DSC_ERR_ALLOC);
     if (cudaMalloc(&ctx->bpart, sizeof(double) * kMaxBlocks * 8) != cudaSuccess) return bail(DSC_ERR_ALLOC);
     if (cudaMallocHost(&ctx->h_pinned, sizeof(double) * kMaxBlocks * kLinPart) != cudaSuccess) return bail(DSC_ERR_ALLOC);
+    if (cudaMalloc(&ctx->d_box, sizeof(float) * (4 + 4 * kMaxBlocks)) != cudaSuccess) return bail(DSC_ERR_ALLOC);
     cudaMemset(ctx->errflag, 0, sizeof(int));
     ctx->use_graphs = std::getenv("DSC_NO_GRAPHS") == nullptr;
     if (std::getenv("DSC_NO_CLUSTER_PCG") == nullptr) {
@@ -285,7 +326,8 @@ extern "C" void dsc_destroy(dsc_ctx* ctx) {
     dev_free(ctx->t_X1); dev_free(ctx->t_X2); dev_free(ctx->t_cos); dev_free(ctx->t_valid);
     dev_free(ctx->X1f); dev_free(ctx->X2f); dev_free(ctx->d_perm);
     dev_free(ctx->dnH); dev_free(ctx->dnA); dev_free(ctx->dn_rhs); dev_free(ctx->dn_sol); dev_free(ctx->dn_l11);
-    dev_free(ctx->r_uv); dev_free(ctx->r_dm); dev_free(ctx->r_isg); dev_free(ctx->g_rp0); dev_free(ctx->g_col0); dev_free(ctx->g_inv);
+    dev_free(ctx->r_uv1); dev_free(ctx->r_uv2); dev_free(ctx->r_d1); dev_free(ctx->r_d2); dev_free(ctx->r_isg1); dev_free(ctx->r_isg2);
+    dev_free(ctx->d_box); dev_free(ctx->g_rp0); dev_free(ctx->g_col0); dev_free(ctx->g_inv);
     dev_free(ctx->g_width); dev_free(ctx->g_sums); dev_free(ctx->g_w0); dev_free(ctx->g_key0); dev_free(ctx->g_key1);
     if (ctx->g_tmp) { cudaFree(ctx->g_tmp); ctx->g_tmp = nullptr; }
     dev_free(ctx->P); dev_free(ctx->Ptrial); dev_free(ctx->P0); dev_free(ctx->Q);
@@ -298,8 +340,8 @@ extern "C" void dsc_destroy(dsc_ctx* ctx) {
     dev_free(ctx->errflag); dev_free(ctx->part); dev_free(ctx->gpart[0]); dev_free(ctx->gpart[1]);
     dev_free(ctx->dpart); dev_free(ctx->bpart);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
-    for (void* q : {(void*)ctx->hs_rp, (void*)ctx->hs_cl, (void*)ctx->hs_sp, (void*)ctx->hs_ww,
-                    (void*)ctx->hs_uv, (void*)ctx->hs_dm, (void*)ctx->hs_isg, (void*)ctx->hs_x1, (void*)ctx->hs_x2}) if (q) cudaFreeHost(q);
+    for (void* q : {(void*)ctx->hs_sp, (void*)ctx->bounce[0], (void*)ctx->bounce[1]}) if (q) cudaFreeHost(q);
+    for (auto& e : ctx->bounce_ev) if (e) cudaEventDestroy(e);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->evA) cudaEventDestroy(ctx->evA);
@@ -307,6 +349,23 @@ extern "C" void dsc_destroy(dsc_ctx* ctx) {
     for (auto& e : ctx->evo) if (e) cudaEventDestroy(e);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
+}
+
+// Page-lock caller memory (cudaHostRegister) so that the upload / download entry points move it by DMA without a host
+// copy.  Worth it for buffers that live across calls (a SLAM front end's key-point / map-point arrays, bench.py's
+// inputs); registering costs about as much as one copy of the buffer.  ptr / bytes as for cudaHostRegister.
+extern "C" int dsc_pin_host(const void* ptr, size_t bytes) {
+    if (!ptr || bytes == 0) return DSC_ERR_INVALID_ARG;
+    cudaError_t e = cudaHostRegister(const_cast<void*>(ptr), bytes, cudaHostRegisterPortable);
+    if (e == cudaErrorHostMemoryAlreadyRegistered) { cudaGetLastError(); return DSC_OK; }
+    if (e != cudaSuccess) { cudaGetLastError(); return DSC_ERR_CUDA; }
+    return DSC_OK;
+}
+extern "C" int dsc_unpin_host(const void* ptr) {
+    if (!ptr) return DSC_ERR_INVALID_ARG;
+    cudaError_t e = cudaHostUnregister(const_cast<void*>(ptr));
+    if (e != cudaSuccess) { cudaGetLastError(); return e == cudaErrorHostMemoryNotRegistered ? DSC_OK : DSC_ERR_CUDA; }
+    return DSC_OK;
 }
 
 extern "C" int dsc_synchronize(dsc_ctx* ctx) {
@@ -464,7 +523,9 @@ static int build_state(dsc_ctx* ctx) {
     int n = ctx->n;
     if (n == 0) return DSC_OK;
     const int* dp = ctx->perm.empty() ? nullptr : ctx->d_perm;
-    permute_obs_kernel<<<grid_threads(ctx, n), kThreads, 0, ctx->stream>>>(n, dp, ctx->r_uv, ctx->r_dm, ctx->r_isg, ctx->uv, ctx->dm, ctx->isg);
+    permute_obs_kernel<<<grid_threads(ctx, n), kThreads, 0, ctx->stream>>>(n, dp, ctx->r_uv1, ctx->r_uv2, ctx->r_d1, ctx->r_d2,
+                                                                          ctx->r_has_isg1 ? ctx->r_isg1 : nullptr, ctx->r_has_isg2 ? ctx->r_isg2 : nullptr,
+                                                                          ctx->uv, ctx->dm, ctx->isg);
     init_state_kernel<<<grid_threads(ctx, n), kThreads, 0, ctx->stream>>>(n, ctx->X1f, ctx->X2f, dp, ctx->P0);
     ctx->launches += 2;
     CK(cudaGetLastError());
@@ -474,27 +535,21 @@ static int build_state(dsc_ctx* ctx) {
     return DSC_OK;
 }
 
-// caller arrays -> pinned staging (packed, in parallel) -> raw device copies (caller order) -> internal order
+// caller arrays -> raw device copies (caller order, copied as they are: h2d) -> internal order (device kernels)
 static int upload_state(dsc_ctx* ctx, const float* X1, const float* X2, const float* uv1, const float* uv2, const double* d1,
                         const double* d2, const float* isg1, const float* isg2) {
-    int n = ctx->n;
+    const size_t n = (size_t)ctx->n;
     if (n == 0) return DSC_OK;
-    CK(pin_reserve(ctx->hs_uv, ctx->hc_uv, (size_t)n)); CK(pin_reserve(ctx->hs_dm, ctx->hc_dm, (size_t)n)); CK(pin_reserve(ctx->hs_isg, ctx->hc_isg, (size_t)n));
-    CK(pin_reserve(ctx->hs_x1, ctx->hc_x1, 3 * (size_t)n)); CK(pin_reserve(ctx->hs_x2, ctx->hc_x2, 3 * (size_t)n));
-    float4* uv = ctx->hs_uv; double2* dm = ctx->hs_dm; float2* sg = ctx->hs_isg;
-    float *x1 = ctx->hs_x1, *x2 = ctx->hs_x2;
-#pragma omp parallel for schedule(static)
-    for (int i = 0; i < n; ++i) {
-        uv[i] = make_float4(uv1[2 * (size_t)i], uv1[2 * (size_t)i + 1], uv2[2 * (size_t)i], uv2[2 * (size_t)i + 1]);
-        dm[i] = make_double2(d1[i], d2[i]);
-        sg[i] = make_float2(isg1 ? isg1[i] : 1.0f, isg2 ? isg2[i] : 1.0f);
-        for (int k = 0; k < 3; ++k) { x1[3 * (size_t)i + k] = X1[3 * (size_t)i + k]; x2[3 * (size_t)i + k] = X2[3 * (size_t)i + k]; }
-    }
-    CK(cudaMemcpyAsync(ctx->r_uv, uv, sizeof(float4) * n, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(ctx->r_dm, dm, sizeof(double2) * n, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(ctx->r_isg, sg, sizeof(float2) * n, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(ctx->X1f, x1, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(ctx->X2f, x2, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, ctx->stream));
+    int rc;
+    if ((rc = h2d(ctx, ctx->r_uv1, uv1, sizeof(float2) * n))) return rc;
+    if ((rc = h2d(ctx, ctx->r_uv2, uv2, sizeof(float2) * n))) return rc;
+    if ((rc = h2d(ctx, ctx->r_d1, d1, sizeof(double) * n))) return rc;
+    if ((rc = h2d(ctx, ctx->r_d2, d2, sizeof(double) * n))) return rc;
+    ctx->r_has_isg1 = isg1 != nullptr; ctx->r_has_isg2 = isg2 != nullptr;
+    if (isg1 && (rc = h2d(ctx, ctx->r_isg1, isg1, sizeof(float) * n))) return rc;
+    if (isg2 && (rc = h2d(ctx, ctx->r_isg2, isg2, sizeof(float) * n))) return rc;
+    if ((rc = h2d(ctx, ctx->X1f, X1, sizeof(float) * 3 * n))) return rc;
+    if ((rc = h2d(ctx, ctx->X2f, X2, sizeof(float) * 3 * n))) return rc;
     return build_state(ctx);
 }
 
@@ -511,7 +566,8 @@ extern "C" int dsc_problem_upload(dsc_ctx* ctx, const dsc_pair* pair, int n,
         CK(dev_alloc(ctx->X1f, 3 * N)); CK(dev_alloc(ctx->X2f, 3 * N)); CK(dev_alloc(ctx->d_perm, N));
         CK(dev_alloc(ctx->P, 8 * N)); CK(dev_alloc(ctx->Ptrial, 8 * N)); CK(dev_alloc(ctx->P0, 8 * N)); CK(dev_alloc(ctx->Q, 4 * N));
         CK(dev_alloc(ctx->uv, N)); CK(dev_alloc(ctx->dm, N)); CK(dev_alloc(ctx->isg, N));
-        CK(dev_alloc(ctx->r_uv, N)); CK(dev_alloc(ctx->r_dm, N)); CK(dev_alloc(ctx->r_isg, N));
+        CK(dev_alloc(ctx->r_uv1, N)); CK(dev_alloc(ctx->r_uv2, N)); CK(dev_alloc(ctx->r_d1, N)); CK(dev_alloc(ctx->r_d2, N));
+        CK(dev_alloc(ctx->r_isg1, N)); CK(dev_alloc(ctx->r_isg2, N));
         CK(dev_alloc(ctx->b, 6 * N)); CK(dev_alloc(ctx->D, 21 * 32 * ((N + 31) / 32))); CK(dev_alloc(ctx->U, (size_t)kURec * 32 * ((N + 31) / 32))); CK(dev_alloc(ctx->Minv, 21 * 32 * ((N + 31) / 32)));
         for (auto& v : ctx->vec) CK(dev_alloc(v, 6 * N));
         ctx->cap = n;
@@ -554,7 +610,7 @@ extern "C" int dsc_set_graph(dsc_ctx* ctx, int n, const int32_t* rowptr, const i
     long long E = n > 0 ? rowptr[n] : 0;
     if (rowptr[0] != 0 || E < 0 || (E > 0 && (!col || !w))) return fail(ctx, DSC_ERR_GRAPH, "rowptr");
     for (int i = 0; i < n; ++i) if (rowptr[i + 1] < rowptr[i]) return fail(ctx, DSC_ERR_GRAPH, "rowptr not monotone");
-    // ---- raw CSR to the device through pinned staging (the copy of chunk c overlaps the packing of chunk c + 1)
+    // ---- raw CSR to the device as it is (h2d: straight from pinned / registered caller memory, else through the bounce buffer)
     if ((size_t)n + 1 > ctx->g_ncap) {
         size_t N = (size_t)n + 1, NS = ((size_t)n + 31) / 32 + 2;
         CK(dev_alloc(ctx->g_rp0, N)); CK(dev_alloc(ctx->g_inv, N)); CK(dev_alloc(ctx->g_key0, N)); CK(dev_alloc(ctx->g_key1, N));
@@ -562,22 +618,11 @@ extern "C" int dsc_set_graph(dsc_ctx* ctx, int n, const int32_t* rowptr, const i
         ctx->g_ncap = N;
     }
     if ((size_t)E > ctx->g_ecap) { CK(dev_alloc(ctx->g_col0, (size_t)E)); CK(dev_alloc(ctx->g_w0, (size_t)E)); ctx->g_ecap = (size_t)E; }
-    CK(pin_reserve(ctx->hs_rp, ctx->hc_rp, (size_t)n + 1)); CK(pin_reserve(ctx->hs_cl, ctx->hc_cl, (size_t)E + 1)); CK(pin_reserve(ctx->hs_ww, ctx->hc_ww, (size_t)E + 1));
-    std::memcpy(ctx->hs_rp, rowptr, sizeof(int) * ((size_t)n + 1));
-    CK(cudaMemcpyAsync(ctx->g_rp0, ctx->hs_rp, sizeof(int) * ((size_t)n + 1), cudaMemcpyHostToDevice, ctx->stream));
     {
-        const long long chunk = 1 << 21;
-        for (long long c0 = 0; c0 < E; c0 += chunk) {
-            const long long c1 = std::min(E, c0 + chunk);
-#pragma omp parallel for schedule(static)
-            for (long long k0 = c0; k0 < c1; k0 += 65536) {
-                const long long k1 = std::min(c1, k0 + 65536);
-                std::memcpy(ctx->hs_cl + k0, col + k0, sizeof(int) * (size_t)(k1 - k0));
-                std::memcpy(ctx->hs_ww + k0, w + k0, sizeof(double) * (size_t)(k1 - k0));
-            }
-            CK(cudaMemcpyAsync(ctx->g_col0 + c0, ctx->hs_cl + c0, sizeof(int) * (size_t)(c1 - c0), cudaMemcpyHostToDevice, ctx->stream));
-            CK(cudaMemcpyAsync(ctx->g_w0 + c0, ctx->hs_ww + c0, sizeof(double) * (size_t)(c1 - c0), cudaMemcpyHostToDevice, ctx->stream));
-        }
+        int rc;
+        if ((rc = h2d(ctx, ctx->g_rp0, rowptr, sizeof(int) * ((size_t)n + 1)))) return rc;
+        if (E > 0 && (rc = h2d(ctx, ctx->g_col0, col, sizeof(int) * (size_t)E))) return rc;
+        if (E > 0 && (rc = h2d(ctx, ctx->g_w0, w, sizeof(double) * (size_t)E))) return rc;
     }
     lap("csr staging");
     // symmetric, in range, no self loops, no duplicates, symmetric weights (the reference's mesh adjacency always is)
@@ -598,14 +643,10 @@ extern "C" int dsc_set_graph(dsc_ctx* ctx, int n, const int32_t* rowptr, const i
     const int nbv = grid_threads(ctx, std::max(n, 1));
     const bool permuted = reorder && n > 1;
     if (permuted) {
-        float xmin = 1e30f, xmax = -1e30f, ymin = 1e30f, ymax = -1e30f;
-#pragma omp parallel for reduction(min : xmin, ymin) reduction(max : xmax, ymax) schedule(static)
-        for (int i = 0; i < n; ++i) {
-            float x = ctx->hs_x1[3 * (size_t)i], y = ctx->hs_x1[3 * (size_t)i + 1];
-            if (std::isfinite(x) && std::isfinite(y)) { xmin = std::min(xmin, x); xmax = std::max(xmax, x); ymin = std::min(ymin, y); ymax = std::max(ymax, y); }
-        }
-        float sx = xmax > xmin ? 65535.0f / (xmax - xmin) : 0.f, sy = ymax > ymin ? 65535.0f / (ymax - ymin) : 0.f;
-        morton_key_kernel<<<nbv, kThreads, 0, ctx->stream>>>(n, ctx->X1f, xmin, sx, ymin, sy, ctx->g_key0);
+        bbox_kernel<<<nbv, kThreads, 0, ctx->stream>>>(n, ctx->X1f, ctx->d_box + 4);
+        bbox_final_kernel<<<1, 32, 0, ctx->stream>>>(nbv, ctx->d_box + 4, ctx->d_box);
+        morton_key_kernel<<<nbv, kThreads, 0, ctx->stream>>>(n, ctx->X1f, ctx->d_box, ctx->g_key0);
+        ctx->launches += 2;
         size_t need = 0;
         CK(cub::DeviceRadixSort::SortKeys(nullptr, need, ctx->g_key0, ctx->g_key1, n, 0, 64, ctx->stream));
         if (need > ctx->g_tmpcap) {

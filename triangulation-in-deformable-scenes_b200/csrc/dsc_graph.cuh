@@ -46,8 +46,42 @@ __global__ void validate_graph_kernel(int n, const int* __restrict__ rowptr0, co
 }
 
 // key = morton(x, y) << 32 | caller index  (the same key the host version sorted)
-__global__ void morton_key_kernel(int n, const float* __restrict__ X1 /* [n][3], caller order */, float xmin, float sx,
-                                  float ymin, float sy, unsigned long long* __restrict__ key) {
+// bounding box of KF1's (x, y) over the finite points: two stages, no host round trip.  part[grid][4] = xmin, xmax,
+// ymin, ymax per block; bbox_final_kernel folds them into box[4] = xmin, sx, ymin, sy (sx = 65535 / extent, 0 if flat).
+__global__ void __launch_bounds__(kThreads)
+bbox_kernel(int n, const float* __restrict__ X1, float* __restrict__ part) {
+    __shared__ float sm[4][kThreads / 32];
+    float v[4] = {1e30f, -1e30f, 1e30f, -1e30f};
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float x = X1[3 * (size_t)i], y = X1[3 * (size_t)i + 1];
+        if (isfinite(x) && isfinite(y)) { v[0] = fminf(v[0], x); v[1] = fmaxf(v[1], x); v[2] = fminf(v[2], y); v[3] = fmaxf(v[3], y); }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        v[0] = fminf(v[0], __shfl_xor_sync(0xffffffffu, v[0], o)); v[1] = fmaxf(v[1], __shfl_xor_sync(0xffffffffu, v[1], o));
+        v[2] = fminf(v[2], __shfl_xor_sync(0xffffffffu, v[2], o)); v[3] = fmaxf(v[3], __shfl_xor_sync(0xffffffffu, v[3], o));
+    }
+    if ((threadIdx.x & 31) == 0) for (int k = 0; k < 4; ++k) sm[k][threadIdx.x >> 5] = v[k];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < kThreads / 32; ++w) {
+            v[0] = fminf(v[0], sm[0][w]); v[1] = fmaxf(v[1], sm[1][w]); v[2] = fminf(v[2], sm[2][w]); v[3] = fmaxf(v[3], sm[3][w]);
+        }
+        for (int k = 0; k < 4; ++k) part[4 * blockIdx.x + k] = v[k];
+    }
+}
+__global__ void bbox_final_kernel(int nb, const float* __restrict__ part, float* __restrict__ box) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    float xmin = 1e30f, xmax = -1e30f, ymin = 1e30f, ymax = -1e30f;
+    for (int b = 0; b < nb; ++b) {
+        xmin = fminf(xmin, part[4 * b]); xmax = fmaxf(xmax, part[4 * b + 1]);
+        ymin = fminf(ymin, part[4 * b + 2]); ymax = fmaxf(ymax, part[4 * b + 3]);
+    }
+    box[0] = xmin; box[1] = xmax > xmin ? __fdiv_rn(65535.0f, __fsub_rn(xmax, xmin)) : 0.f;
+    box[2] = ymin; box[3] = ymax > ymin ? __fdiv_rn(65535.0f, __fsub_rn(ymax, ymin)) : 0.f;
+}
+__global__ void morton_key_kernel(int n, const float* __restrict__ X1 /* [n][3], caller order */, const float* __restrict__ box,
+                                  unsigned long long* __restrict__ key) {
+    const float xmin = box[0], sx = box[1], ymin = box[2], sy = box[3];
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const float x = X1[3 * (size_t)i], y = X1[3 * (size_t)i + 1];
         const unsigned qx = isfinite(x) ? (unsigned)fminf(65535.0f, fmaxf(0.0f, __fmul_rn(__fsub_rn(x, xmin), sx))) : 0u;
@@ -137,12 +171,18 @@ ell_fill_kernel(int n, const int* __restrict__ perm, const int* __restrict__ inv
 }
 
 // observations, depth measurements and inverse variances gathered into the internal order
-__global__ void permute_obs_kernel(int n, const int* __restrict__ perm, const float4* __restrict__ ruv, const double2* __restrict__ rdm,
-                                   const float2* __restrict__ risg, float4* __restrict__ uv, double2* __restrict__ dm,
+// (the raw arrays are the caller's own, copied as they are: uv1 / uv2 [n][2] float, d1 / d2 [n] double, isg1 / isg2 [n]
+// float or NULL = 1; interleaving them for the kernels happens here, on the device, not in a host loop)
+__global__ void permute_obs_kernel(int n, const int* __restrict__ perm, const float2* __restrict__ ruv1, const float2* __restrict__ ruv2,
+                                   const double* __restrict__ rd1, const double* __restrict__ rd2, const float* __restrict__ risg1,
+                                   const float* __restrict__ risg2, float4* __restrict__ uv, double2* __restrict__ dm,
                                    float2* __restrict__ isg) {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const int s = perm ? perm[i] : i;
-        uv[i] = ruv[s]; dm[i] = rdm[s]; isg[i] = risg[s];
+        const float2 a = ruv1[s], b = ruv2[s];
+        uv[i] = make_float4(a.x, a.y, b.x, b.y);
+        dm[i] = make_double2(rd1[s], rd2[s]);
+        isg[i] = make_float2(risg1 ? risg1[s] : 1.0f, risg2 ? risg2[s] : 1.0f);
     }
 }
 
