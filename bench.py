@@ -43,6 +43,7 @@ def parse():
     ap.add_argument("--early-margin", type=float, nargs="*", default=[1.0, 0.5])
     ap.add_argument("--cpu-budget", type=float, default=900.0, help="--impl reference: wall-time budget of the CPU step in seconds")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-fp32", action="store_true", help="skip the fp32-mode sub-record")
     return ap.parse_args()
 
 
@@ -277,6 +278,41 @@ def main():
         if s > 0:
             e2e_ms += (time.perf_counter() - t1) * 1e3
 
+    # ---- fp32 mode (dsc_set_precision): float storage of what the PCG streams + fp64 iterative refinement; same steps,
+    # device-resident, reported next to the fp64 headline with its distance from the fp64 result
+    f32rec = None
+    if not args.no_fp32:
+        try:
+            out64 = ctx.download(doubles=True)
+            sig64 = ctx.pixel_sigma()
+            chi64 = stats_last.final_chi2
+            ctx.set_precision("f32")
+            ms32, its32, pcg32, tr32 = 0.0, 0, 0, None
+            for s in range(1 + args.steps):               # first pass untimed
+                ctx.reset_state()
+                recs, st = ctx.optimize(w, lm_iters)
+                if s == 0:
+                    tr32 = [(r.trials, r.accepted) for r in recs]
+                else:
+                    ms32 += st.device_ms; its32 += st.iterations; pcg32 += st.total_pcg_iters
+            out32 = ctx.download(doubles=True)
+            sig32 = ctx.pixel_sigma()
+            k32 = ctx.profile_kernels(w, warm=3, reps=20)
+            scale = float(np.abs(out64["X1d"]).max())
+            f32rec = dict(lm_it_per_s=its32 / (ms32 * 1e-3), ms_per_step=ms32 / args.steps, pcg_iters_per_lm_iter=pcg32 / max(1, its32),
+                          final_chi2_rel_diff=abs(st.final_chi2 - chi64) / chi64,
+                          points_max_rel_diff=float(max(np.abs(out32["X1d"] - out64["X1d"]).max(), np.abs(out32["X2d"] - out64["X2d"]).max()) / scale),
+                          pixel_sigma_abs_diff_px=[abs(a - b) for a, b in zip(sig32, sig64)],
+                          lm_decisions_identical=(tr32 == [(t[2], t[3]) for t in ref_trace]) if ref_trace else None,
+                          pcg_unconverged=st.pcg_unconverged,
+                          kernels={k: dict(ms=v["ms"], gbs=v["bytes"] / (v["ms"] * 1e-3) / 1e9, bytes=v["bytes"]) for k, v in k32.items()
+                                   if k in ("cg_spmv", "cg_update", "precond", "linearize")},
+                          storage="Je/U/Minv/PCG vectors float; sums, state, cost double; fp64 residual refinement")
+        except Exception as ex:
+            f32rec = dict(error=str(ex))
+        finally:
+            ctx.set_precision("f64")
+
     # ---- kernel roofline (CUDA events on the library's stream) and triangulation throughput
     kern = ctx.profile_kernels(w, warm=3, reps=20)
     ctx.tri_upload(prob["pair"], sc["uv1"], sc["uv2"])
@@ -343,7 +379,7 @@ def main():
                              ms_per_step=e2e_ms / args.steps),
                     gpu_launches=int(launches), clocks=clocks, roofline=roof, cpu_baseline=cpu,
                     triangulated_points_per_s=roof["triangulate"]["points_per_s"], knn_graph_build_ms=prob["graph_build_ms"],
-                    cg_iteration_ms=cg_ms, wall_ms_per_step=wall_ms / args.steps, config5=c5)
+                    cg_iteration_ms=cg_ms, wall_ms_per_step=wall_ms / args.steps, fp32_mode=f32rec, config5=c5)
         print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()

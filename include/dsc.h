@@ -196,6 +196,18 @@ int dsc_set_pcg(dsc_ctx* ctx, const dsc_pcg_params* prm);
 #define DSC_DENSE_AUTO_MAX 600
 #define DSC_DENSE_MAX 1000
 int dsc_set_solver(dsc_ctx* ctx, int solver);
+/* Storage precision of the linear solver (the north_star's second tolerance: "1e-3 px reprojection RMSE in fp32 mode").
+ * DSC_PRECISION_F64 (default): everything double, the 1e-5 parity bar against the direct-solve oracle.
+ * DSC_PRECISION_F32: the data the PCG streams -- the per-edge ARAP Jacobian records, the unary Hessian records, the
+ * block-Jacobi preconditioner and the six PCG vectors -- are STORED as float (half the bytes per PCG iteration); every
+ * sum, dot product, the 8x8 global block, the state (points, scales, T_global), the cost and the LM decisions stay
+ * double, and the reprojection is float32 as in the reference (g2oTypes.h:284-289) in both modes.  An LM step is then an
+ * inexact Newton step (relative error ~1e-6), which moves the per-iteration costs by ~1e-6 relative and the final
+ * reprojection RMSE by far less than 1e-3 px (tests/test_gpu_parity.py).  A mode of the PCG path: the dense and the
+ * one-launch cluster solvers of small problems are not used while it is set.  May be switched between dsc_optimize calls. */
+#define DSC_PRECISION_F64 0
+#define DSC_PRECISION_F32 1
+int dsc_set_precision(dsc_ctx* ctx, int precision);
 /* Optional (off by default): pause every linear solve at up to 4 loose tolerances rtol_loose[0] > rtol_loose[1] > ...,
  * evaluate the trial step there, and reject it at once when rho < -rho_margin[level]; otherwise resume the same CG.
  * The last pass always runs to the tight tolerance of dsc_set_pcg, so accepted steps are unchanged.  A rejected step

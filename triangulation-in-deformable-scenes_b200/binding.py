@@ -23,7 +23,7 @@ EXPORTS = [
     "dsc_timer_start", "dsc_timer_stop", "dsc_launch_count", "dsc_pin_host", "dsc_unpin_host",
     "dsc_triangulate", "dsc_triangulate_rays", "dsc_tri_upload", "dsc_tri_run", "dsc_tri_download", "dsc_depth_scale_init",
     "dsc_problem_upload", "dsc_set_graph", "dsc_compute_rotations", "dsc_get_rotations", "dsc_set_rotations",
-    "dsc_reset_state", "dsc_set_pcg", "dsc_set_solver", "dsc_set_early_reject", "dsc_cost", "dsc_optimize", "dsc_download", "dsc_pixel_sigma",
+    "dsc_reset_state", "dsc_set_pcg", "dsc_set_solver", "dsc_set_precision", "dsc_set_early_reject", "dsc_cost", "dsc_optimize", "dsc_download", "dsc_pixel_sigma",
     "dsc_batch_create", "dsc_batch_destroy", "dsc_batch_last_error", "dsc_batch_upload", "dsc_batch_set_pcg", "dsc_batch_set_early_reject",
     "dsc_batch_reset_state", "dsc_batch_optimize", "dsc_batch_download", "dsc_batch_size",
     "dsc_debug_linearize", "dsc_debug_matvec", "dsc_profile_kernels", "dsc_profile_triangulate", "dsc_problem_size", "dsc_knn_build", "dsc_knn_download",
@@ -310,6 +310,10 @@ class Context:
     def set_pcg(self, rtol=1e-10, max_iters=4000, check_every=32):
         p = PcgParams(float(rtol), int(max_iters), int(check_every))
         self._ck(self.lib.dsc_set_pcg(self.h, C.byref(p)))
+
+    def set_precision(self, precision="f64"):
+        """"f64" (default) or "f32": storage of the data the PCG streams (dsc.h, dsc_set_precision)"""
+        self._ck(self.lib.dsc_set_precision(self.h, {"f64": 0, "f32": 1}.get(precision, precision)))
 
     def set_early_reject(self, rtol_loose=(1e-3, 1e-4), rho_margin=(1.0, 0.5)):
         """levels of (loose tolerance, rho margin); empty sequences switch the shortcut off"""

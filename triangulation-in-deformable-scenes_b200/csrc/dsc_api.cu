@@ -100,13 +100,20 @@ struct dsc_ctx {
     int knn_n = 0; long long knn_E = 0;
     int *knn_rowptr = nullptr, *knn_col = nullptr;
     dsc_pcg_params pcg{1e-10, 4000, 32};
-    struct IterGraph { cudaGraphExec_t exec = nullptr; const double* P = nullptr; WeightsDev W{}; } graphs[2];   // per state buffer
+    struct IterGraph { cudaGraphExec_t exec = nullptr; const double* P = nullptr; WeightsDev W{}; int precision = 0; } graphs[2];   // per state buffer
     bool use_graphs = true;
     int small_cluster = 0;                           // CTAs of the one-launch PCG of small problems (0 = not available)
     int small_max_rows = kSmallMaxRows;              // largest problem that takes that path (DSC_SMALL_MAX_ROWS overrides)
     int solver = DSC_SOLVER_AUTO;                    // dense Cholesky for small problems, PCG above (dsc_set_solver)
     double *dnH = nullptr, *dnA = nullptr, *dn_rhs = nullptr, *dn_sol = nullptr, *dn_l11 = nullptr;
     int dn_cap = 0;
+    int precision = DSC_PRECISION_F64;               // storage of the solver data (dsc_set_precision)
+    // fp32 mode: float copies of what the PCG streams + its six vectors; the double buffers keep serving the residual
+    // of the iterative refinement (X = vec[0], peeked solution = vec[1], operator output = vec[3])
+    float *JeF = nullptr, *UF = nullptr, *MinvF = nullptr, *vecF[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    int f32_cap = 0; long long f32_blkcap = 0;
+    bool f32_fresh = false;                          // JeF's padding slots are all-zero for the current graph
+    struct Refine { int pass_k = 0, total = 0, passes = 0; double gamma0 = 0.0, rho = 1.0; bool have_X = false; } rf;
     int early_levels = 0;                            // early rejection of clearly bad LM trials (off by default)
     double early_rtol[4] = {0, 0, 0, 0}, early_margin[4] = {0, 0, 0, 0};
 };
@@ -246,16 +253,6 @@ WeightsDev make_weights(const dsc_ctx* c, const dsc_weights* w) {
     return o;
 }
 
-// spread the low 16 bits of v so that there is a zero between every bit
-uint32_t part1by1(uint32_t v) {
-    v &= 0x0000ffffu;
-    v = (v | (v << 8)) & 0x00ff00ffu;
-    v = (v | (v << 4)) & 0x0f0f0f0fu;
-    v = (v | (v << 2)) & 0x33333333u;
-    v = (v | (v << 1)) & 0x55555555u;
-    return v;
-}
-
 double host_sum(const double* p, int n, int stride = 1, int off = 0) {
     double s = 0.0;
     for (int i = 0; i < n; ++i) s += p[(size_t)i * stride + off];
@@ -290,7 +287,7 @@ extern "C" int dsc_create(int device, dsc_ctx** out) {
     if (cudaMalloc(&ctx->lin, sizeof(LinGlobal)) != cudaSuccess) return bail(DSC_ERR_ALLOC);
     if (cudaMalloc(&ctx->ctl, sizeof(CgControl)) != cudaSuccess) return bail(DSC_ERR_ALLOC);
     if (cudaMalloc(&ctx->errflag, sizeof(int)) != cudaSuccess) return bail(DSC_ERR_ALLOC);
-    if (cudaMalloc(&ctx->small, sizeof(double) * (6 * 8 + 64)) != cudaSuccess) return bail(DSC_ERR_ALLOC);
+    if (cudaMalloc(&ctx->small, sizeof(double) * (6 * 8 + 64 + 16)) != cudaSuccess) return bail(DSC_ERR_ALLOC);
     if (cudaMalloc(&ctx->part, sizeof(double) * kMaxBlocks * kLinPart) != cudaSuccess) return bail(DSC_ERR_ALLOC);
     if (cudaMalloc(&ctx->gpart[0], sizeof(double) * kMaxBlocks) != cudaSuccess) return bail(DSC_ERR_ALLOC);
     if (cudaMalloc(&ctx->gpart[1], sizeof(double) * kMaxBlocks) != cudaSuccess) return bail(DSC_ERR_ALLOC);
@@ -310,9 +307,11 @@ extern "C" int dsc_create(int device, dsc_ctx** out) {
     }
     if (cudaFuncSetAttribute(rotations_ell_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWinBytes) != cudaSuccess ||
         cudaFuncSetAttribute(cost_ell_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWinBytes) != cudaSuccess ||
-        cudaFuncSetAttribute(cg_spmv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSpmvSmem) != cudaSuccess ||
+        cudaFuncSetAttribute(cg_spmv_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SpmvCfg<double>::kSmem) != cudaSuccess ||
+        cudaFuncSetAttribute(cg_spmv_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SpmvCfg<float>::kSmem) != cudaSuccess ||
+        cudaFuncSetAttribute(linearize_ell_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWinBytes) != cudaSuccess ||
         cudaFuncSetAttribute(dense_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * kDenseMaxM)) != cudaSuccess ||
-        cudaFuncSetAttribute(linearize_ell_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWinBytes) != cudaSuccess) return bail(DSC_ERR_CUDA);
+        cudaFuncSetAttribute(linearize_ell_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWinBytes) != cudaSuccess) return bail(DSC_ERR_CUDA);
     *out = ctx;
     return DSC_OK;
 }
@@ -335,6 +334,8 @@ extern "C" void dsc_destroy(dsc_ctx* ctx) {
     dev_free(ctx->Je); dev_free(ctx->ecol); dev_free(ctx->ewgt); dev_free(ctx->sliceptr); dev_free(ctx->spmv_part);
     dev_free(ctx->b); dev_free(ctx->D); dev_free(ctx->U); dev_free(ctx->Minv);
     for (auto& v : ctx->vec) dev_free(v);
+    for (auto& v : ctx->vecF) dev_free(v);
+    dev_free(ctx->JeF); dev_free(ctx->UF); dev_free(ctx->MinvF);
     dev_free(ctx->knn_rowptr); dev_free(ctx->knn_col);
     dev_free(ctx->small); dev_free(ctx->Gcur); dev_free(ctx->Gtrial); dev_free(ctx->lin); dev_free(ctx->ctl);
     dev_free(ctx->errflag); dev_free(ctx->part); dev_free(ctx->gpart[0]); dev_free(ctx->gpart[1]);
@@ -733,6 +734,7 @@ extern "C" int dsc_set_graph(dsc_ctx* ctx, int n, const int32_t* rowptr, const i
         CK(cudaMemsetAsync(ctx->Je, 0, sizeof(double) * nblk * 288, ctx->stream));
     }
     ctx->have_graph = true; ctx->have_rot = false;
+    ctx->f32_fresh = false;
     drop_graphs(ctx);
     int urc = build_state(ctx);                        // (synchronises the stream: hpart may go out of scope)
     lap("ell + state");
@@ -805,6 +807,13 @@ extern "C" int dsc_set_solver(dsc_ctx* ctx, int solver) {
     return DSC_OK;
 }
 
+extern "C" int dsc_set_precision(dsc_ctx* ctx, int precision) {
+    if (!ctx || (precision != DSC_PRECISION_F64 && precision != DSC_PRECISION_F32)) return fail(ctx, DSC_ERR_INVALID_ARG, "dsc_set_precision");
+    if (precision != ctx->precision) drop_graphs(ctx);
+    ctx->precision = precision;
+    return DSC_OK;
+}
+
 extern "C" int dsc_set_early_reject(dsc_ctx* ctx, int n_levels, const double* rtol_loose, const double* rho_margin) {
     if (!ctx || n_levels < 0 || n_levels > 4 || (n_levels > 0 && (!rtol_loose || !rho_margin)))
         return fail(ctx, DSC_ERR_INVALID_ARG, "dsc_set_early_reject");
@@ -849,17 +858,60 @@ extern "C" int dsc_cost(dsc_ctx* ctx, const dsc_weights* w, double* chi2, double
     return eval_cost(ctx, make_weights(ctx, w), ctx->P, ctx->Gcur, chi2, parts);
 }
 
-static CgVecs make_vecs(dsc_ctx* ctx) {
-    CgVecs v;
-    v.x = ctx->vec[0]; v.r = ctx->vec[1]; v.z = ctx->vec[2]; v.w = ctx->vec[3]; v.p = ctx->vec[4]; v.s = ctx->vec[5];
+// The PCG's data in the two precisions: T = double -> Je, U, Minv, vec[]; T = float -> JeF, UF, MinvF, vecF[] (fp32 mode).
+template <typename T> struct Sel;
+template <> struct Sel<double> {
+    static double* Je(dsc_ctx* c) { return c->Je; } static double* U(dsc_ctx* c) { return c->U; }
+    static double* Minv(dsc_ctx* c) { return c->Minv; } static double* vec(dsc_ctx* c, int k) { return c->vec[k]; }
+};
+template <> struct Sel<float> {
+    static float* Je(dsc_ctx* c) { return c->JeF; } static float* U(dsc_ctx* c) { return c->UF; }
+    static float* Minv(dsc_ctx* c) { return c->MinvF; } static float* vec(dsc_ctx* c, int k) { return c->vecF[k]; }
+};
+template <typename T = double>
+static CgVecsT<T> make_vecs(dsc_ctx* ctx) {
+    CgVecsT<T> v;
+    v.x = Sel<T>::vec(ctx, 0); v.r = Sel<T>::vec(ctx, 1); v.z = Sel<T>::vec(ctx, 2); v.w = Sel<T>::vec(ctx, 3); v.p = Sel<T>::vec(ctx, 4); v.s = Sel<T>::vec(ctx, 5);
     v.xg = ctx->small; v.rg = ctx->small + 8; v.zg = ctx->small + 16; v.wg = ctx->small + 24; v.pg = ctx->small + 32; v.sg = ctx->small + 40;
     return v;
 }
+static bool f32(const dsc_ctx* ctx) { return ctx->precision == DSC_PRECISION_F32; }
+static double* refine_Xg(dsc_ctx* ctx) { return ctx->small + 112; }        // globals of the accumulated solution X (vec[0])
+static double* refine_Xg_peek(dsc_ctx* ctx) { return ctx->small + 120; }   // globals of the peeked solution (vec[1])
+// float buffers of the fp32 mode, (re)allocated for the uploaded problem; JeF's padding records are zeroed once per graph
+static int ensure_f32(dsc_ctx* ctx) {
+    if (!f32(ctx)) return DSC_OK;
+    if (ctx->cap > ctx->f32_cap) {
+        const size_t N = (size_t)ctx->cap, S32 = 32 * ((N + 31) / 32);
+        CK(dev_alloc(ctx->UF, (size_t)kURec * S32)); CK(dev_alloc(ctx->MinvF, 21 * S32));
+        for (auto& v : ctx->vecF) CK(dev_alloc(v, 6 * N + 8));
+        ctx->f32_cap = ctx->cap;
+    }
+    if (ctx->blkcap > ctx->f32_blkcap) {
+        CK(dev_alloc(ctx->JeF, (size_t)ctx->blkcap * 288));
+        ctx->f32_blkcap = ctx->blkcap;
+        ctx->f32_fresh = false;
+    }
+    if (!ctx->f32_fresh && ctx->nblk > 0) {
+        CK(cudaMemsetAsync(ctx->JeF, 0, sizeof(float) * (size_t)ctx->nblk * 288, ctx->stream));
+        drop_graphs(ctx);
+    }
+    ctx->f32_fresh = true;
+    return DSC_OK;
+}
 
+static void launch_linearize(dsc_ctx* ctx, const WeightsDev& W, int nb) {
+    if (f32(ctx))
+        linearize_ell_kernel<true><<<nb, kLinThreads, kWinBytes, ctx->stream>>>(ctx->n, ctx->P, ctx->Q, ctx->uv, ctx->dm, ctx->isg, ctx->sliceptr, ctx->ecol,
+                                                                              ctx->ewgt, ctx->Gcur, ctx->pair, W, ctx->b, ctx->D, ctx->U, ctx->Je, ctx->part, ctx->UF, ctx->JeF);
+    else
+        linearize_ell_kernel<false><<<nb, kLinThreads, kWinBytes, ctx->stream>>>(ctx->n, ctx->P, ctx->Q, ctx->uv, ctx->dm, ctx->isg, ctx->sliceptr, ctx->ecol,
+                                                                               ctx->ewgt, ctx->Gcur, ctx->pair, W, ctx->b, ctx->D, ctx->U, ctx->Je, ctx->part, nullptr, nullptr);
+}
 static int run_linearize(dsc_ctx* ctx, const WeightsDev& W, LinGlobal* hlin) {
     int nb = grid_tiles(ctx, ctx->n, 1);
-    linearize_ell_kernel<<<nb, kLinThreads, kWinBytes, ctx->stream>>>(ctx->n, ctx->P, ctx->Q, ctx->uv, ctx->dm, ctx->isg, ctx->sliceptr, ctx->ecol,
-                                                                    ctx->ewgt, ctx->Gcur, ctx->pair, W, ctx->b, ctx->D, ctx->U, ctx->Je, ctx->part);
+    { int erc = ensure_f32(ctx); if (erc) return erc; }
+    launch_linearize(ctx, W, nb);
     finalize_linearize_kernel<<<1, kThreads, 0, ctx->stream>>>(nb, ctx->part, ctx->lin);
     ctx->launches += 2;
     CK(cudaGetLastError());
@@ -874,7 +926,7 @@ static int run_linearize(dsc_ctx* ctx, const WeightsDev& W, LinGlobal* hlin) {
 // PCG solve of (H + lambda I) dx = b in two entry points so that a solve can be paused at a loose tolerance,
 // inspected (trial cost) and resumed to the tight one: begin = preconditioner + r0/z0 + first operator
 // application; resume = iterate until sqrt(r.z / r0.z0) <= rtol, breakdown or max_iters.
-static bool small_active(const dsc_ctx* ctx) { return ctx->small_cluster > 0 && ctx->n <= ctx->small_max_rows; }
+static bool small_active(const dsc_ctx* ctx) { return ctx->small_cluster > 0 && ctx->n <= ctx->small_max_rows && !f32(ctx); }
 
 // one launch = the whole solve (or its continuation after a pause) by a single thread-block cluster (dsc_small.cuh)
 static int small_launch(dsc_ctx* ctx, const WeightsDev& W, int fresh) {
@@ -900,6 +952,27 @@ static int small_launch(dsc_ctx* ctx, const WeightsDev& W, int fresh) {
     return DSC_OK;
 }
 
+// the three PCG kernels in the context's precision (T = storage type of Je, U, Minv and the vectors)
+template <typename T>
+static void launch_init(dsc_ctx* ctx, double lambda) {
+    cg_init_kernel<T><<<grid_threads(ctx, (long long)ctx->n), kThreads, 0, ctx->stream>>>(ctx->n, ctx->b, ctx->D, lambda, ctx->lin, Sel<T>::Minv(ctx), ctx->small + 48,
+                                                                                       ctx->errflag, make_vecs<T>(ctx), ctx->gpart[0], ctx->ctl);
+}
+// w = (H + lambda I) z in precision T; z / zg / w default to the PCG's own vectors
+template <typename T>
+static void launch_spmv(dsc_ctx* ctx, const WeightsDev& W, double lambda, const CgControl* ctl, const T* z = nullptr, const double* zg = nullptr, T* w = nullptr) {
+    CgVecsT<T> v = make_vecs<T>(ctx);
+    cg_spmv_kernel<T><<<grid_spmv(ctx, ctx->n), kThreads, SpmvCfg<T>::kSmem, ctx->stream>>>(ctx->n, ctx->P, Sel<T>::Je(ctx), Sel<T>::U(ctx), ctx->sliceptr, ctx->ecol, ctx->spmv_part,
+                                                                                         ctx->spmv_units, ctx->Gcur, ctx->pair, W, lambda, z ? z : v.z, zg ? zg : v.zg,
+                                                                                         w ? w : v.w, ctx->dpart, ctx->bpart, ctx->lin, ctl);
+}
+template <typename T>
+static void launch_update(dsc_ctx* ctx, int par, int first, double lambda, int gin, int gout, double rtol2) {
+    cg_update_kernel<T><<<grid_threads(ctx, (long long)ctx->n), kThreads, 0, ctx->stream>>>(ctx->n, par, first, Sel<T>::Minv(ctx), ctx->small + 48, ctx->lin, lambda, make_vecs<T>(ctx),
+                                                                                         ctx->gpart[gin], ctx->gpart[gout], ctx->dpart, ctx->bpart, grid_spmv(ctx, ctx->n),
+                                                                                         ctx->ctl, rtol2);
+}
+
 static int pcg_begin(dsc_ctx* ctx, const WeightsDev& W, double lambda) {
     if (small_active(ctx)) {                           // the cluster kernel starts the solve itself
         CK(cudaMemsetAsync(ctx->errflag, 0, sizeof(int), ctx->stream));
@@ -908,16 +981,10 @@ static int pcg_begin(dsc_ctx* ctx, const WeightsDev& W, double lambda) {
         CK(cudaGetLastError());
         return DSC_OK;
     }
-    int n = ctx->n;
-    int nbv = grid_threads(ctx, (long long)n);
-    int nbs = grid_spmv(ctx, n);
-    CgVecs v = make_vecs(ctx);
-    double* Ginv = ctx->small + 48;
     CK(cudaMemsetAsync(ctx->errflag, 0, sizeof(int), ctx->stream));
     ctl_set_kernel<<<1, 1, 0, ctx->stream>>>(ctx->ctl, lambda, 1, 0.0, 0, 0);
-    cg_init_kernel<<<nbv, kThreads, 0, ctx->stream>>>(n, ctx->b, ctx->D, lambda, ctx->lin, ctx->Minv, Ginv, ctx->errflag, v, ctx->gpart[0], ctx->ctl);
-    cg_spmv_kernel<<<nbs, kThreads, kSpmvSmem, ctx->stream>>>(n, ctx->P, ctx->Je, ctx->U, ctx->sliceptr, ctx->ecol, ctx->spmv_part, ctx->spmv_units, ctx->Gcur, ctx->pair, W,
-                                                     lambda, v.z, v.zg, v.w, ctx->dpart, ctx->bpart, ctx->lin, ctx->ctl);
+    if (f32(ctx)) { launch_init<float>(ctx, lambda); launch_spmv<float>(ctx, W, lambda, ctx->ctl); ctx->rf = dsc_ctx::Refine{}; }
+    else { launch_init<double>(ctx, lambda); launch_spmv<double>(ctx, W, lambda, ctx->ctl); }
     ctx->launches += 3;
     CK(cudaGetLastError());
     return DSC_OK;
@@ -930,55 +997,37 @@ constexpr int kPcgUnconverged = 1;       // internal status of pcg_resume: itera
 constexpr int kEarlyWorthIters = 16;     // early-reject pauses are skipped while full solves take no more than this
 static int iteration_graph(dsc_ctx* ctx, const WeightsDev& W, cudaGraphExec_t* out) {
     dsc_ctx::IterGraph* slot = nullptr;
-    for (auto& g : ctx->graphs) if (g.exec && g.P == ctx->P && std::memcmp(&g.W, &W, sizeof(WeightsDev)) == 0) { *out = g.exec; return DSC_OK; }
+    for (auto& g : ctx->graphs) if (g.exec && g.P == ctx->P && g.precision == ctx->precision && std::memcmp(&g.W, &W, sizeof(WeightsDev)) == 0) { *out = g.exec; return DSC_OK; }
     for (auto& g : ctx->graphs) if (!g.exec || g.P == ctx->P) { slot = &g; break; }
     if (!slot) slot = &ctx->graphs[0];
     if (slot->exec) { cudaGraphExecDestroy(slot->exec); slot->exec = nullptr; }
-    int n = ctx->n, nbv = grid_threads(ctx, (long long)n), nbs = grid_spmv(ctx, n);
-    CgVecs v = make_vecs(ctx);
-    double* Ginv = ctx->small + 48;
     cudaGraph_t graph = nullptr;
     CK(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
     for (int k = 2; k < 2 + kGraphIters; ++k) {
-        cg_update_kernel<<<nbv, kThreads, 0, ctx->stream>>>(n, k & 1, 0, ctx->Minv, Ginv, ctx->lin, 0.0, v, ctx->gpart[k & 1],
-                                                           ctx->gpart[(k + 1) & 1], ctx->dpart, ctx->bpart, nbs, ctx->ctl, 0.0);
-        cg_spmv_kernel<<<nbs, kThreads, kSpmvSmem, ctx->stream>>>(n, ctx->P, ctx->Je, ctx->U, ctx->sliceptr, ctx->ecol, ctx->spmv_part, ctx->spmv_units, ctx->Gcur, ctx->pair, W,
-                                                         0.0, v.z, v.zg, v.w, ctx->dpart, ctx->bpart, ctx->lin, ctx->ctl);
+        if (f32(ctx)) { launch_update<float>(ctx, k & 1, 0, 0.0, k & 1, (k + 1) & 1, 0.0); launch_spmv<float>(ctx, W, 0.0, ctx->ctl); }
+        else { launch_update<double>(ctx, k & 1, 0, 0.0, k & 1, (k + 1) & 1, 0.0); launch_spmv<double>(ctx, W, 0.0, ctx->ctl); }
     }
     cudaError_t e = cudaStreamEndCapture(ctx->stream, &graph);
     if (e != cudaSuccess) return fail(ctx, DSC_ERR_CUDA, std::string("graph capture -> ") + cudaGetErrorString(e));
     e = cudaGraphInstantiate(&slot->exec, graph, 0);
     cudaGraphDestroy(graph);
     if (e != cudaSuccess) { slot->exec = nullptr; return fail(ctx, DSC_ERR_CUDA, std::string("graph instantiate -> ") + cudaGetErrorString(e)); }
-    slot->P = ctx->P; slot->W = W;
+    slot->P = ctx->P; slot->W = W; slot->precision = ctx->precision;
     *out = slot->exec;
     return DSC_OK;
 }
 
-static int pcg_resume(dsc_ctx* ctx, const WeightsDev& W, double lambda, double rtol, int* k_io) {
-    int n = ctx->n;
-    int nbv = grid_threads(ctx, (long long)n);
-    int nbs = grid_spmv(ctx, n);
-    CgVecs v = make_vecs(ctx);
-    double* Ginv = ctx->small + 48;
-    double rtol2 = rtol * rtol;
+// The iteration loop of both precisions: updates k .. (pass-local in the fp32 mode) until the control block reports
+// convergence to rtol (relative to the gamma0 of the running pass), breakdown, or `limit` updates.
+static int pcg_iterate(dsc_ctx* ctx, const WeightsDev& W, double lambda, double rtol, int* k_io, int limit, CgControl* out) {
+    const double rtol2 = rtol * rtol;
     int k = *k_io;
     // resuming after a pause (k > 0): the converged latch belongs to the looser tolerance
     ctl_set_kernel<<<1, 1, 0, ctx->stream>>>(ctx->ctl, 0.0, 0, rtol2, 1, k > 0 ? 1 : 0);
     CgControl hc{};
-    if (small_active(ctx)) {
-        int src = small_launch(ctx, W, k == 0 ? 1 : 0);
-        if (src) return src;
-        CgControl* hp = reinterpret_cast<CgControl*>(ctx->h_pinned + 5 * kMaxBlocks);
-        CK(cudaMemcpyAsync(hp, ctx->ctl, sizeof(CgControl), cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaStreamSynchronize(ctx->stream));
-        hc = *hp;
-        *k_io = hc.iters;
-        return hc.breakdown ? DSC_ERR_PCG_BREAKDOWN : (hc.converged ? DSC_OK : kPcgUnconverged);
-    }
     int poll = std::min(k == 0 ? 18 : 16, ctx->pcg.check_every);   // first poll early (well-damped solves need ~10 iterations): 2 direct + one graph
-    while (k < ctx->pcg.max_iters) {
-        int chunk = std::min(poll, ctx->pcg.max_iters - k);
+    while (k < limit) {
+        int chunk = std::min(poll, limit - k);
         poll = std::min(2 * poll, ctx->pcg.check_every);
         for (int c = 0; c < chunk;) {
             if (ctx->use_graphs && k >= 2 && (k & 1) == 0 && chunk - c >= kGraphIters) {
@@ -990,11 +1039,8 @@ static int pcg_resume(dsc_ctx* ctx, const WeightsDev& W, double lambda, double r
                 ctx->launches += 2 * kGraphIters;
                 continue;
             }
-            cg_update_kernel<<<nbv, kThreads, 0, ctx->stream>>>(n, k & 1, k == 0 ? 1 : 0, ctx->Minv, Ginv, ctx->lin, lambda, v,
-                                                               ctx->gpart[k & 1], ctx->gpart[(k + 1) & 1], ctx->dpart, ctx->bpart, nbs,
-                                                               ctx->ctl, rtol2);
-            cg_spmv_kernel<<<nbs, kThreads, kSpmvSmem, ctx->stream>>>(n, ctx->P, ctx->Je, ctx->U, ctx->sliceptr, ctx->ecol, ctx->spmv_part, ctx->spmv_units, ctx->Gcur, ctx->pair, W,
-                                                             lambda, v.z, v.zg, v.w, ctx->dpart, ctx->bpart, ctx->lin, ctx->ctl);
+            if (f32(ctx)) { launch_update<float>(ctx, k & 1, k == 0 ? 1 : 0, lambda, k & 1, (k + 1) & 1, rtol2); launch_spmv<float>(ctx, W, lambda, ctx->ctl); }
+            else { launch_update<double>(ctx, k & 1, k == 0 ? 1 : 0, lambda, k & 1, (k + 1) & 1, rtol2); launch_spmv<double>(ctx, W, lambda, ctx->ctl); }
             ctx->launches += 2;
             ++k; ++c;
         }
@@ -1007,13 +1053,86 @@ static int pcg_resume(dsc_ctx* ctx, const WeightsDev& W, double lambda, double r
         if (hc.converged || hc.breakdown) break;
     }
     *k_io = hc.iters;
+    *out = hc;
     if (hc.breakdown) return DSC_ERR_PCG_BREAKDOWN;
-    if (!hc.converged) return kPcgUnconverged;        // max_iters reached: the caller treats the step as a failed solve
+    if (!hc.converged) return kPcgUnconverged;        // iteration limit reached: the caller treats the step as a failed solve
     return DSC_OK;
+}
+
+// fp32 mode: mixed-precision iterative refinement.  The float PCG runs in passes; a pass that is asked for more than
+// three digits is followed by a VERIFICATION: X += x_f (double), r = b - (H + lambda I) X with the double operator, and
+// the next pass solves for the correction of that true residual.  The float recursion loses the true residual after a
+// few digits (its attainable accuracy is ~ kappa * 6e-8), the refinement restores it: the returned step satisfies the
+// same tolerance on the TRUE preconditioned residual that the fp64 path reaches on its recursive one.
+constexpr double kRefineInnerFloor = 1e-6;    // digits asked of the first float pass (its recursion follows the true residual that far)
+constexpr double kRefineLaterFloor = 1e-4;    // ... of a later pass: the float rounding of the operator data limits its true gain to 1e-3 .. 1e-4
+constexpr double kRefineTrust = 1e-4;         // a pass that needs no more than this is not verified
+constexpr int kRefineMaxPasses = 16;
+static int pcg_resume_f32(dsc_ctx* ctx, const WeightsDev& W, double lambda, double tol, int* k_io) {
+    dsc_ctx::Refine& rf = ctx->rf;
+    const int n = ctx->n, nbv = grid_threads(ctx, (long long)n), nbs = grid_spmv(ctx, n);
+    CgVecsT<float> vf = make_vecs<float>(ctx);
+    double* X = ctx->vec[0];
+    double* Wd = ctx->vec[3];
+    for (;;) {
+        const double need = tol / rf.rho;                      // reduction of the true residual this call still owes
+        if (need >= 1.0) { *k_io = rf.total + rf.pass_k; return DSC_OK; }
+        const bool trust = need >= kRefineTrust || tol >= 5e-5;   // (the loose levels of the early rejection only need the sign of rho)
+        const double inner = trust ? 0.5 * need : std::max(need, rf.passes == 0 ? kRefineInnerFloor : kRefineLaterFloor);
+        int k = rf.pass_k;
+        if (k == 0 && rf.passes > 0) {                          // first operator application of a restarted pass
+            launch_spmv<float>(ctx, W, lambda, ctx->ctl);
+            ctx->launches++;
+        }
+        CgControl hc{};
+        const int rc = pcg_iterate(ctx, W, lambda, inner, &k, ctx->pcg.max_iters - rf.total, &hc);
+        rf.pass_k = k;
+        *k_io = rf.total + rf.pass_k;
+        if (rf.passes == 0 && k > 0) rf.gamma0 = hc.gamma0;     // preconditioned norm of the right-hand side
+        if (rc != DSC_OK) return rc;
+        if (trust) return DSC_OK;
+        // ---- verification: X += x_f, true residual, restart
+        refine_accumulate_kernel<<<nbv, kThreads, 0, ctx->stream>>>(n, rf.have_X ? X : nullptr, vf.x, X, rf.have_X ? refine_Xg(ctx) : nullptr, vf.xg,
+                                                                   refine_Xg(ctx), rf.pass_k > 0 ? 1 : 0);
+        rf.have_X = true; rf.total += rf.pass_k; rf.pass_k = 0; rf.passes++;
+        launch_spmv<double>(ctx, W, lambda, nullptr, X, refine_Xg(ctx), Wd);
+        cg_restart_kernel<<<nbv, kThreads, 0, ctx->stream>>>(n, ctx->b, Wd, ctx->MinvF, ctx->small + 48, ctx->lin, refine_Xg(ctx), ctx->bpart, nbs, vf, ctx->gpart[0], ctx->ctl);
+        refine_gamma_kernel<<<1, kThreads, 0, ctx->stream>>>(nbv, ctx->gpart[0], ctx->ctl);
+        ctx->launches += 4;
+        CK(cudaGetLastError());
+        CgControl* hp = reinterpret_cast<CgControl*>(ctx->h_pinned + 5 * kMaxBlocks);
+        CK(cudaMemcpyAsync(hp, ctx->ctl, sizeof(CgControl), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        const double rho_new = std::sqrt(hp->gamma_true / rf.gamma0);
+        if (std::getenv("DSC_REFINE_LOG")) std::fprintf(stderr, "[dsc refine] pass %d its %d rho %.3e -> %.3e (tol %.1e)\n", rf.passes, rf.total, rf.rho, rho_new, tol);
+        if (!std::isfinite(rho_new)) return DSC_ERR_PCG_BREAKDOWN;
+        if (rho_new <= tol) { rf.rho = rho_new; return DSC_OK; }
+        if (rf.passes >= kRefineMaxPasses || rho_new > 0.5 * rf.rho) return kPcgUnconverged;   // the refinement stalls: a failed solve
+        rf.rho = rho_new;
+    }
+}
+
+static int pcg_resume(dsc_ctx* ctx, const WeightsDev& W, double lambda, double rtol, int* k_io) {
+    if (f32(ctx)) return pcg_resume_f32(ctx, W, lambda, rtol, k_io);
+    CgControl hc{};
+    if (small_active(ctx)) {
+        // resuming after a pause (k > 0): the converged latch belongs to the looser tolerance
+        ctl_set_kernel<<<1, 1, 0, ctx->stream>>>(ctx->ctl, 0.0, 0, rtol * rtol, 1, *k_io > 0 ? 1 : 0);
+        int src = small_launch(ctx, W, *k_io == 0 ? 1 : 0);
+        if (src) return src;
+        CgControl* hp = reinterpret_cast<CgControl*>(ctx->h_pinned + 5 * kMaxBlocks);
+        CK(cudaMemcpyAsync(hp, ctx->ctl, sizeof(CgControl), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        hc = *hp;
+        *k_io = hc.iters;
+        return hc.breakdown ? DSC_ERR_PCG_BREAKDOWN : (hc.converged ? DSC_OK : kPcgUnconverged);
+    }
+    return pcg_iterate(ctx, W, lambda, rtol, k_io, ctx->pcg.max_iters, &hc);
 }
 
 // ---- dense direct solve of small problems (dsc_dense.cuh)
 static bool dense_active(const dsc_ctx* ctx) {
+    if (f32(ctx)) return false;                            // the fp32 mode is a mode of the PCG path
     return ctx->solver == DSC_SOLVER_DENSE || (ctx->solver == DSC_SOLVER_AUTO && ctx->n <= DSC_DENSE_AUTO_MAX);
 }
 // once per LM iteration: H (dense, lower) and the right-hand side from the linearisation
@@ -1065,8 +1184,16 @@ static int dense_solve(dsc_ctx* ctx, double lambda) {
 static int eval_trial(dsc_ctx* ctx, const WeightsDev& W, double lambda, double* temp, double* scale) {
     int nbv = grid_threads(ctx, ctx->n);
     CgVecs v = make_vecs(ctx);
-    apply_update_kernel<<<nbv, kThreads, 0, ctx->stream>>>(ctx->n, ctx->P, v.x, v.xg, ctx->b, ctx->lin, lambda, ctx->Gcur,
-                                                          ctx->Ptrial, ctx->Gtrial, ctx->part);
+    if (f32(ctx)) {     // the step is X (+ the running correction x_f): peek at it without disturbing the solve
+        const dsc_ctx::Refine& rf = ctx->rf;
+        refine_accumulate_kernel<<<nbv, kThreads, 0, ctx->stream>>>(ctx->n, rf.have_X ? ctx->vec[0] : nullptr, ctx->vecF[0], ctx->vec[1],
+                                                                   rf.have_X ? refine_Xg(ctx) : nullptr, v.xg, refine_Xg_peek(ctx), rf.pass_k > 0 ? 1 : 0);
+        apply_update_kernel<double><<<nbv, kThreads, 0, ctx->stream>>>(ctx->n, ctx->P, ctx->vec[1], refine_Xg_peek(ctx), ctx->b, ctx->lin, lambda, ctx->Gcur,
+                                                                      ctx->Ptrial, ctx->Gtrial, ctx->part);
+        ctx->launches++;
+    } else
+        apply_update_kernel<double><<<nbv, kThreads, 0, ctx->stream>>>(ctx->n, ctx->P, v.x, v.xg, ctx->b, ctx->lin, lambda, ctx->Gcur,
+                                                                      ctx->Ptrial, ctx->Gtrial, ctx->part);
     ctx->launches++;
     CK(cudaMemcpyAsync(ctx->h_pinned + 3 * kMaxBlocks, ctx->part, sizeof(double) * nbv, cudaMemcpyDeviceToHost, ctx->stream));
     int rc = eval_cost(ctx, W, ctx->Ptrial, ctx->Gtrial, temp, nullptr);
@@ -1279,21 +1406,25 @@ extern "C" int dsc_debug_matvec(dsc_ctx* ctx, const dsc_weights* w, double lambd
     if (s) return s;
     CgVecs v = make_vecs(ctx);
     std::vector<double> hz(6 * (size_t)n);
+    std::vector<float> hzf(f32(ctx) ? 6 * (size_t)n : 0);
     for (int i = 0; i < n; ++i) {
         size_t sidx = ctx->perm.empty() ? (size_t)i : (size_t)ctx->perm[i];
         for (int k = 0; k < 6; ++k) hz[6 * (size_t)i + k] = x[8 + 6 * sidx + k];
     }
-    if (n) CK(cudaMemcpyAsync(v.z, hz.data(), sizeof(double) * 6 * n, cudaMemcpyHostToDevice, ctx->stream));
+    for (size_t k = 0; k < hzf.size(); ++k) hzf[k] = (float)hz[k];
+    if (n && f32(ctx)) CK(cudaMemcpyAsync(ctx->vecF[2], hzf.data(), sizeof(float) * 6 * n, cudaMemcpyHostToDevice, ctx->stream));
+    else if (n) CK(cudaMemcpyAsync(v.z, hz.data(), sizeof(double) * 6 * n, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(v.zg, x, sizeof(double) * 8, cudaMemcpyHostToDevice, ctx->stream));
     int nbs = grid_spmv(ctx, n);
-    cg_spmv_kernel<<<nbs, kThreads, kSpmvSmem, ctx->stream>>>(n, ctx->P, ctx->Je, ctx->U, ctx->sliceptr, ctx->ecol, ctx->spmv_part, ctx->spmv_units, ctx->Gcur, ctx->pair, W,
-                                                     lambda, v.z, v.zg, v.w, ctx->dpart, ctx->bpart, ctx->lin, nullptr);
+    if (f32(ctx)) launch_spmv<float>(ctx, W, lambda, nullptr); else launch_spmv<double>(ctx, W, lambda, nullptr);
     ctx->launches++;
     CK(cudaGetLastError());
     std::vector<double> hw(6 * (size_t)n), hbp(8 * (size_t)nbs);
-    if (n) CK(cudaMemcpyAsync(hw.data(), v.w, sizeof(double) * 6 * n, cudaMemcpyDeviceToHost, ctx->stream));
+    if (n && f32(ctx)) CK(cudaMemcpyAsync(hzf.data(), ctx->vecF[3], sizeof(float) * 6 * n, cudaMemcpyDeviceToHost, ctx->stream));
+    else if (n) CK(cudaMemcpyAsync(hw.data(), v.w, sizeof(double) * 6 * n, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaMemcpyAsync(hbp.data(), ctx->bpart, sizeof(double) * 8 * nbs, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    for (size_t k = 0; k < hzf.size(); ++k) hw[k] = (double)hzf[k];
     for (int k = 0; k < 8; ++k) {
         double sum = 0.0;
         for (int bk = 0; bk < nbs; ++bk) sum += hbp[8 * (size_t)bk + k];
@@ -1327,19 +1458,20 @@ extern "C" int dsc_profile_kernels(dsc_ctx* ctx, const dsc_weights* w, int warm,
     if (s) return s;
     double lambda = 1e-5 * hl.maxdiag;
     CgVecs v = make_vecs(ctx);
-    double* Ginv = ctx->small + 48;
-    int nbv = grid_threads(ctx, n), nbp = grid_spmv(ctx, n);
+    int nbv = grid_threads(ctx, n);
+    const bool lo = f32(ctx);
+    const double tb = lo ? 4.0 : 8.0;              // bytes per stored solver value
     CK(cudaMemsetAsync(ctx->errflag, 0, sizeof(int), ctx->stream));
-    cg_init_kernel<<<nbv, kThreads, 0, ctx->stream>>>(n, ctx->b, ctx->D, lambda, ctx->lin, ctx->Minv, Ginv, ctx->errflag, v, ctx->gpart[0], ctx->ctl);
+    if (lo) launch_init<float>(ctx, lambda); else launch_init<double>(ctx, lambda);
     ctx->launches += 2;
     double N = (double)n, E = (double)ctx->E;
     double by[DSC_K_COUNT];
-    by[DSC_K_SPMV] = 240.0 * N + 76.0 * (double)ctx->nblk * 32.0;   // X1(32) z(48) U(112) | ELL blocks: col(4) Je(72) per slot (padding included) | write w
-    by[DSC_K_UPDATE] = 696.0 * N;                 // read z w p s x r Minv, write p s x r z
     double S = (double)ctx->nblk * 32.0;            // ELL slots (padding included)
-    by[DSC_K_LINEARIZE] = 488.0 * N + 12.0 * S + 72.0 * E;   // P Q uv dm isg | ecol ewgt per slot | write b D U, Je per edge
+    by[DSC_K_SPMV] = (32.0 + 26.0 * tb) * N + (4.0 + 9.0 * tb) * S;   // X1(32) | z(6) U(14) w(6) values | ELL blocks: col(4) + Je(9 values) per slot (padding included)
+    by[DSC_K_UPDATE] = 87.0 * tb * N;             // read z w p s x r (36 values) + Minv (21), write p s x r z (30)
+    by[DSC_K_LINEARIZE] = (488.0 + (lo ? 56.0 : 0.0)) * N + 12.0 * S + (72.0 + (lo ? 36.0 : 0.0)) * E;   // P Q uv dm isg | ecol ewgt per slot | write b D U, Je per edge (+ the float copies in the fp32 mode)
     by[DSC_K_COST] = 136.0 * N + 12.0 * S;         // P Q uv dm isg | ecol ewgt per slot
-    by[DSC_K_PRECOND] = 480.0 * N;                // preconditioner + PCG start: D b -> Minv r z
+    by[DSC_K_PRECOND] = (48.0 + 168.0 + 33.0 * tb) * N;   // preconditioner + PCG start: b D -> Minv (21 values) r z (12)
     by[DSC_K_APPLY] = 224.0 * N;                  // P x b -> Ptrial
     by[DSC_K_ROTATIONS] = 96.0 * N + 12.0 * S;     // P | ecol ewgt per slot | write Q
     auto time_it = [&](int which, auto&& launch) -> int {
@@ -1354,8 +1486,7 @@ extern "C" int dsc_profile_kernels(dsc_ctx* ctx, const dsc_weights* w, int warm,
         return DSC_OK;
     };
     s = time_it(DSC_K_SPMV, [&]() {
-        cg_spmv_kernel<<<nbp, kThreads, kSpmvSmem, ctx->stream>>>(n, ctx->P, ctx->Je, ctx->U, ctx->sliceptr, ctx->ecol, ctx->spmv_part, ctx->spmv_units, ctx->Gcur, ctx->pair, W,
-                                                         lambda, v.z, v.zg, v.w, ctx->dpart, ctx->bpart, ctx->lin, nullptr);
+        if (lo) launch_spmv<float>(ctx, W, lambda, nullptr); else launch_spmv<double>(ctx, W, lambda, nullptr);
     });
     if (s) return s;
     // update: run real CG steps (first=1 keeps beta = 0, so the recurrences stay finite for any reps)
@@ -1363,14 +1494,11 @@ extern "C" int dsc_profile_kernels(dsc_ctx* ctx, const dsc_weights* w, int warm,
         CgControl z{};                                 // a regular (not first) step: beta ~ 0, all seven vectors read
         z.lambda = lambda; z.gamma0 = 1e300; z.sc[1].gamma_prev = 1e300; z.sc[1].alpha_prev = 1.0;
         cudaMemcpyAsync(ctx->ctl, &z, sizeof(CgControl), cudaMemcpyHostToDevice, ctx->stream);
-        cg_update_kernel<<<nbv, kThreads, 0, ctx->stream>>>(n, 0, 0, ctx->Minv, Ginv, ctx->lin, lambda, v, ctx->gpart[0], ctx->gpart[1],
-                                                           ctx->dpart, ctx->bpart, nbp, ctx->ctl, 0.0);
+        if (lo) launch_update<float>(ctx, 0, 0, lambda, 0, 1, 0.0); else launch_update<double>(ctx, 0, 0, lambda, 0, 1, 0.0);
     });
     if (s) return s;
     s = time_it(DSC_K_LINEARIZE, [&]() {
-        linearize_ell_kernel<<<grid_tiles(ctx, n, 1), kLinThreads, kWinBytes, ctx->stream>>>(n, ctx->P, ctx->Q, ctx->uv, ctx->dm, ctx->isg, ctx->sliceptr,
-                                                                                       ctx->ecol, ctx->ewgt, ctx->Gcur, ctx->pair, W, ctx->b, ctx->D,
-                                                                                       ctx->U, ctx->Je, ctx->part);
+        launch_linearize(ctx, W, grid_tiles(ctx, n, 1));
     });
     if (s) return s;
     s = time_it(DSC_K_COST, [&]() {
@@ -1379,12 +1507,12 @@ extern "C" int dsc_profile_kernels(dsc_ctx* ctx, const dsc_weights* w, int warm,
     });
     if (s) return s;
     s = time_it(DSC_K_PRECOND, [&]() {
-        cg_init_kernel<<<nbv, kThreads, 0, ctx->stream>>>(n, ctx->b, ctx->D, lambda, ctx->lin, ctx->Minv, Ginv, ctx->errflag, v, ctx->gpart[0], ctx->ctl);
+        if (lo) launch_init<float>(ctx, lambda); else launch_init<double>(ctx, lambda);
     });
     if (s) return s;
     s = time_it(DSC_K_APPLY, [&]() {
-        apply_update_kernel<<<nbv, kThreads, 0, ctx->stream>>>(n, ctx->P, v.x, v.xg, ctx->b, ctx->lin, lambda, ctx->Gcur,
-                                                              ctx->Ptrial, ctx->Gtrial, ctx->gpart[0]);
+        apply_update_kernel<double><<<nbv, kThreads, 0, ctx->stream>>>(n, ctx->P, v.x, v.xg, ctx->b, ctx->lin, lambda, ctx->Gcur,
+                                                                      ctx->Ptrial, ctx->Gtrial, ctx->gpart[0]);
     });
     if (s) return s;
     double* Qtmp = ctx->vec[3];                    // scratch: do not disturb the real rotations

@@ -70,6 +70,7 @@ struct CgControl {
     int iters;
     int converged;
     int breakdown;
+    double gamma_true;   // fp32 mode: r.M^-1 r of the true (double) residual at the last restart (refine_gamma_kernel)
 };
 
 // ------------------------------------------------------------------ helpers
@@ -165,6 +166,21 @@ DSC_D void load6(const double* __restrict__ V, int i, D3& a, D3& b) {
 DSC_D void store6(double* __restrict__ V, int i, D3 a, D3 b) {
     double2* p = reinterpret_cast<double2*>(V) + 3 * (size_t)i;
     p[0] = make_double2(a.x, a.y); p[1] = make_double2(a.z, b.x); p[2] = make_double2(b.y, b.z);
+}
+// float storage of the solver vectors (dsc_set_precision, DSC_PRECISION_F32): the same records in 24 bytes; every
+// value is widened on load and all arithmetic (sums, dot products, the 8x8 global block) stays double
+template <bool kRO>
+DSC_D void load6_t(const float* V, int i, D3& a, D3& b) {
+    const float2* p = reinterpret_cast<const float2*>(V) + 3 * (size_t)i;
+    float2 u, v, w;
+    if (kRO) { u = p[0]; v = p[1]; w = p[2]; }
+    else { u = __ldcg(p); v = __ldcg(p + 1); w = __ldcg(p + 2); }
+    a = d3((double)u.x, (double)u.y, (double)v.x); b = d3((double)v.y, (double)w.x, (double)w.y);
+}
+DSC_D void load6(const float* __restrict__ V, int i, D3& a, D3& b) { load6_t<true>(V, i, a, b); }
+DSC_D void store6(float* __restrict__ V, int i, D3 a, D3 b) {
+    float2* p = reinterpret_cast<float2*>(V) + 3 * (size_t)i;
+    p[0] = make_float2((float)a.x, (float)a.y); p[1] = make_float2((float)a.z, (float)b.x); p[2] = make_float2((float)b.y, (float)b.z);
 }
 DSC_D void load_q(const double* __restrict__ Q, int i, double* q) {
     const double4* p = reinterpret_cast<const double4*>(Q) + (size_t)i;
@@ -438,8 +454,8 @@ template <typename T>
 DSC_D T* blk21(T* base, int i) { return base + ((size_t)(i >> 5) * 21) * 32 + (i & 31); }
 
 // block-Jacobi preconditioner: Minv_i = (D_i + lambda I)^-1 (packed), Ginv = (C + lambda I)^-1
-template <bool kRO = true>
-DSC_D void precond_block(const double* __restrict__ D, int i, double lambda, double* __restrict__ Minv, int* __restrict__ err,
+template <bool kRO = true, typename T = double>
+DSC_D void precond_block(const double* __restrict__ D, int i, double lambda, T* __restrict__ Minv, int* __restrict__ err,
                          double (&M)[21]) {
     const double* Dp = blk21(D, i);
     double A[36], Ai[36];
@@ -457,11 +473,14 @@ DSC_D void precond_block(const double* __restrict__ D, int i, double lambda, dou
 #pragma unroll
         for (int r = 0; r < 6; ++r) Ai[r * 6 + r] = 1.0 / fmax(fabs(A[r * 6 + r]), 1e-300);
     }
-    double* Mp = blk21(Minv, i);
+    T* Mp = blk21(Minv, i);
 #pragma unroll
     for (int r = 0; r < 6; ++r)
 #pragma unroll
-        for (int c = r; c < 6; ++c) { M[pk<6>(r, c)] = Ai[r * 6 + c]; Mp[pk<6>(r, c) * 32] = Ai[r * 6 + c]; }
+        for (int c = r; c < 6; ++c) {
+            const T stored = (T)Ai[r * 6 + c];           // the preconditioner the iterations will apply is the STORED one
+            M[pk<6>(r, c)] = (double)stored; Mp[pk<6>(r, c) * 32] = stored;
+        }
 }
 template <bool kRO = true>
 DSC_D void precond_global(const LinGlobal* __restrict__ lin, double lambda, double* __restrict__ Ginv, int* __restrict__ err) {
@@ -476,10 +495,11 @@ DSC_D void precond_global(const LinGlobal* __restrict__ lin, double lambda, doub
     for (int k = 0; k < 64; ++k) Ginv[k] = Ai[k];
 }
 
-DSC_D void apply_minv(const double* __restrict__ Mp, const double* r, double* z) {
+template <typename T>
+DSC_D void apply_minv(const T* __restrict__ Mp, const double* r, double* z) {
     double M[21];
 #pragma unroll
-    for (int k = 0; k < 21; ++k) M[k] = Mp[k * 32];
+    for (int k = 0; k < 21; ++k) M[k] = (double)Mp[k * 32];
 #pragma unroll
     for (int a = 0; a < 6; ++a) {
         double s = 0.0;
@@ -494,16 +514,19 @@ DSC_D void apply_minv(const double* __restrict__ Mp, const double* r, double* z)
 //   beta = gamma/gamma_prev ; alpha = gamma / (delta - beta gamma / alpha_prev)
 //   p = z + beta p ; s = w + beta s ; x += alpha p ; r -= alpha s
 // Two kernels per iteration (update, spmv); all scalars stay on the device.
-struct CgVecs {
-    double *x, *r, *z, *w, *p, *s;          // [n][6]
+template <typename T>
+struct CgVecsT {
+    T *x, *r, *z, *w, *p, *s;               // [n][6]   (T = float in the fp32 mode: 24-byte records)
     double *xg, *rg, *zg, *wg, *pg, *sg;    // [8]
 };
+using CgVecs = CgVecsT<double>;
 
 // Preconditioner and PCG start in one pass over the rows: Minv = (D + lambda I)^-1, r = b, z = Minv r, gamma partial.
 // x, p and s are not written: the first cg_update (first = 1) treats them as zero.
+template <typename T>
 __global__ void __launch_bounds__(kThreads)
 cg_init_kernel(int n, const double* __restrict__ b, const double* __restrict__ D, double lambda, const LinGlobal* __restrict__ lin,
-               double* __restrict__ Minv, double* __restrict__ Ginv, int* __restrict__ err, CgVecs v, double* __restrict__ gpart,
+               T* __restrict__ Minv, double* __restrict__ Ginv, int* __restrict__ err, CgVecsT<T> v, double* __restrict__ gpart,
                CgControl* __restrict__ ctl) {
     __shared__ double sm[kThreads / 32];
     double g[1] = {0.0};
@@ -511,14 +534,15 @@ cg_init_kernel(int n, const double* __restrict__ b, const double* __restrict__ D
         double r[6], z[6], M[21];
         D3 a, c;
         load6(b, i, a, c);
+        if (sizeof(T) == 4) { a = d3((float)a.x, (float)a.y, (float)a.z); c = d3((float)c.x, (float)c.y, (float)c.z); }   // r as stored
         r[0] = a.x; r[1] = a.y; r[2] = a.z; r[3] = c.x; r[4] = c.y; r[5] = c.z;
-        precond_block(D, i, lambda, Minv, err, M);
+        precond_block<true, T>(D, i, lambda, Minv, err, M);
 #pragma unroll
         for (int q = 0; q < 6; ++q) {
             double sacc = 0.0;
 #pragma unroll
             for (int k = 0; k < 6; ++k) sacc += (q <= k ? M[pk<6>(q, k)] : M[pk<6>(k, q)]) * r[k];
-            z[q] = sacc;
+            z[q] = sizeof(T) == 4 ? (double)(float)sacc : sacc;
         }
         store6(v.r, i, a, c);
         store6(v.z, i, d3(z[0], z[1], z[2]), d3(z[3], z[4], z[5]));
@@ -580,26 +604,37 @@ DSC_D void mbar_wait(unsigned long long* bar, unsigned parity) {
                  "}" ::"r"(smem_addr(bar)), "r"(parity) : "memory");
 }
 
-constexpr int kSpmvStages = 3;                                   // ring depth per warp (ELL blocks in flight)
 constexpr int kURec = 14;                                        // unary record {U1[6], U2[6], kd1, kd2}, stored [slice][kURec][32]
-constexpr int kSpmvStageBytes = 9 * 32 * 8 + 32 * 4;             // one ELL block: Je[9][32] doubles + ecol[32] ints
-constexpr int kSpmvWinBytes = kSortGroup * (48 + 32);            // z (6 doubles) and X1 (double4) of the tile
-constexpr int kSpmvSmem = kSpmvWinBytes + (kThreads / 32) * kSpmvStages * kSpmvStageBytes;
+// Per storage type T of the operator data (Je, U) and of the vectors (double, or float in the fp32 mode): ring depth per
+// warp (ELL blocks in flight: the float blocks are half as large, so more of them keep the same bytes in flight), bytes
+// of one ELL block (Je[9][32] + ecol[32] ints), window bytes (z: 6 T per row, X1: double4 per row).
+template <typename T> struct SpmvCfg {
+    static constexpr int kStages = sizeof(T) == 8 ? 3 : 6;
+    static constexpr int kJeBytes = 9 * 32 * (int)sizeof(T);
+    static constexpr int kStageBytes = kJeBytes + 32 * 4;
+    static constexpr int kZRow = 6 * (int)sizeof(T);
+    static constexpr int kWinBytes = kSortGroup * (kZRow + 32);
+    static constexpr int kSmem = kWinBytes + (kThreads / 32) * kStages * kStageBytes;
+};
+constexpr int kSpmvSmem = SpmvCfg<double>::kSmem;
 
+template <typename T>
 __global__ void __launch_bounds__(kThreads, 2)
-cg_spmv_kernel(int n, const double* __restrict__ P, const double* __restrict__ Je, const double* __restrict__ U,
+cg_spmv_kernel(int n, const double* __restrict__ P, const T* __restrict__ Je, const T* __restrict__ U,
                const int* __restrict__ sliceptr, const int* __restrict__ ecol, const int* __restrict__ part, int nunits,
                const Globals* __restrict__ Gp, const __grid_constant__ PairDev pr, const __grid_constant__ WeightsDev W,
-               double lambda, const double* __restrict__ z, const double* __restrict__ zg, double* __restrict__ w,
+               double lambda, const T* __restrict__ z, const double* __restrict__ zg, T* __restrict__ w,
                double* __restrict__ dpart, double* __restrict__ bpart,
                const LinGlobal* __restrict__ lin, const CgControl* __restrict__ ctl) {
+    constexpr int kSpmvStages = SpmvCfg<T>::kStages, kSpmvStageBytes = SpmvCfg<T>::kStageBytes, kSpmvWinBytes = SpmvCfg<T>::kWinBytes;
+    constexpr int kJeBytes = SpmvCfg<T>::kJeBytes, kZRow = SpmvCfg<T>::kZRow;
     extern __shared__ __align__(128) unsigned char dyn[];
     __shared__ double sm[9 * (kThreads / 32)];
     __shared__ double Rg[9];
     __shared__ double zgs[8];
     __shared__ unsigned long long bars[(kThreads / 32) * kSpmvStages + 1];
-    double2* sz = reinterpret_cast<double2*>(dyn);                               // z of the tile: 3 double2 per row
-    double4* sx = reinterpret_cast<double4*>(dyn + kSortGroup * 48);             // X1 of the tile
+    const T* sz = reinterpret_cast<const T*>(dyn);                               // z of the tile: 6 T per row
+    double4* sx = reinterpret_cast<double4*>(dyn + kSortGroup * kZRow);          // X1 of the tile
     if (ctl && (ctl->converged || ctl->breakdown)) return;   // flags are only written by an EARLIER launch
     if (ctl) lambda = ctl->lambda;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -649,13 +684,16 @@ cg_spmv_kernel(int n, const double* __restrict__ P, const double* __restrict__ J
             unsigned char* dst = ring + (slot % kSpmvStages) * kSpmvStageBytes;
             unsigned long long* bar = rbar + (slot % kSpmvStages);
             mbar_expect_tx(bar, kSpmvStageBytes);
-            bulk_load(dst, Je + (size_t)bk * 288, 2304, bar);
-            bulk_load(dst + 2304, ecol + (size_t)bk * 32, 128, bar);
+            bulk_load(dst, Je + (size_t)bk * 288, kJeBytes, bar);
+            bulk_load(dst + kJeBytes, ecol + (size_t)bk * 32, 128, bar);
         };
         __syncthreads();                               // everyone is done with the previous window
         if (threadIdx.x == 0) {
-            mbar_expect_tx(wbar, (unsigned)nv * 80u);
-            bulk_load(sz, z + 6 * (size_t)v0, (unsigned)nv * 48u, wbar);
+            // (bulk copies move multiples of 16 bytes: an odd number of 24-byte float rows is rounded up; the vector
+            // buffers are allocated for doubles, so the 8 extra bytes exist)
+            const unsigned zbytes = ((unsigned)nv * (unsigned)kZRow + 15u) & ~15u;
+            mbar_expect_tx(wbar, zbytes + (unsigned)nv * 32u);
+            bulk_load(dyn, z + 6 * (size_t)v0, zbytes, wbar);
             bulk_load(sx, reinterpret_cast<const double4*>(P) + v0, (unsigned)nv * 32u, wbar);
         }
         if (lane == 0)
@@ -670,8 +708,8 @@ cg_spmv_kernel(int n, const double* __restrict__ P, const double* __restrict__ J
         const int i = v0 + il;
         const bool act = il < nv;
         const int ilc = act ? il : nv - 1;
-        const double2 a0 = sz[3 * ilc], a1 = sz[3 * ilc + 1], a2 = sz[3 * ilc + 2];
-        const D3 zi1 = d3(a0.x, a0.y, a1.x), zi2 = d3(a1.y, a2.x, a2.y);
+        D3 zi1, zi2;
+        load6(sz, ilc, zi1, zi2);
         const double4 xi = sx[ilc];
         const D3 X1i = d3(xi.x, xi.y, xi.z);
         D3 Am = d3(0, 0, 0), Ag = d3(0, 0, 0), Au = d3(0, 0, 0);
@@ -679,16 +717,15 @@ cg_spmv_kernel(int n, const double* __restrict__ P, const double* __restrict__ J
             const unsigned st = cons % kSpmvStages;
             mbar_wait(rbar + st, (cons / kSpmvStages) & 1u);
             const unsigned char* sb = ring + st * kSpmvStageBytes;
-            const double* jb = reinterpret_cast<const double*>(sb) + lane;
-            const int j = reinterpret_cast<const int*>(sb + 2304)[lane];
-            const D3 u = d3(jb[0], jb[32], jb[64]);
-            const D3 m = d3(jb[96], jb[128], jb[160]);
-            const D3 g = d3(jb[192], jb[224], jb[256]);
+            const T* jb = reinterpret_cast<const T*>(sb) + lane;
+            const int j = reinterpret_cast<const int*>(sb + kJeBytes)[lane];
+            const D3 u = d3((double)jb[0], (double)jb[32], (double)jb[64]);
+            const D3 m = d3((double)jb[96], (double)jb[128], (double)jb[160]);
+            const D3 g = d3((double)jb[192], (double)jb[224], (double)jb[256]);
             D3 zj1, zj2, X1j;
             const unsigned jl = (unsigned)(j - v0);
             if (jl < (unsigned)nv) {
-                const double2 c0 = sz[3 * jl], c1 = sz[3 * jl + 1], c2 = sz[3 * jl + 2];
-                zj1 = d3(c0.x, c0.y, c1.x); zj2 = d3(c1.y, c2.x, c2.y);
+                load6(sz, (int)jl, zj1, zj2);
                 const double4 xj = sx[jl];
                 X1j = d3(xj.x, xj.y, xj.z);
             } else {
@@ -710,10 +747,10 @@ cg_spmv_kernel(int n, const double* __restrict__ P, const double* __restrict__ J
         }
         if (act) {
             // output rows: [-Am - 2 Ag | Au + 2 Rg^T Ag] + U z + kd n z_s + lambda z
-            const double* Up = U + ((size_t)(i >> 5) * kURec) * 32 + lane;
+            const T* Up = U + ((size_t)(i >> 5) * kURec) * 32 + lane;
             double uu[kURec];
 #pragma unroll
-            for (int k = 0; k < kURec; ++k) uu[k] = __ldg(Up + k * 32);
+            for (int k = 0; k < kURec; ++k) uu[k] = (double)__ldg(Up + k * 32);
             const D3 rg = mulT(Rg, Ag);
             double out[6] = {-Am.x - 2.0 * Ag.x, -Am.y - 2.0 * Ag.y, -Am.z - 2.0 * Ag.z,
                              Au.x + 2.0 * rg.x, Au.y + 2.0 * rg.y, Au.z + 2.0 * rg.z};
@@ -734,7 +771,11 @@ cg_spmv_kernel(int n, const double* __restrict__ P, const double* __restrict__ J
             }
             double dl = 0.0;
 #pragma unroll
-            for (int k = 0; k < 6; ++k) { out[k] += lambda * zi[k]; dl += zi[k] * out[k]; }
+            for (int k = 0; k < 6; ++k) {
+                out[k] += lambda * zi[k];
+                if (sizeof(T) == 4) out[k] = (double)(float)out[k];   // z.w of the w the update kernel will read
+                dl += zi[k] * out[k];
+            }
             acc[8] += dl;
             // T_g rows (the directed twins carry the same s_e and g): omega 2 (X1i x Ag), upsilon -2 Ag
             const D3 cx = cross(X1i, Ag);
@@ -756,9 +797,10 @@ cg_spmv_kernel(int n, const double* __restrict__ P, const double* __restrict__ J
 }
 
 // One CG step.  par = iteration parity (double-buffered scalars and gamma partials).
+template <typename T>
 __global__ void __launch_bounds__(kThreads)
-cg_update_kernel(int n, int par, int first, const double* __restrict__ Minv, const double* __restrict__ Ginv,
-                 const LinGlobal* __restrict__ lin, double lambda, CgVecs v,
+cg_update_kernel(int n, int par, int first, const T* __restrict__ Minv, const double* __restrict__ Ginv,
+                 const LinGlobal* __restrict__ lin, double lambda, CgVecsT<T> v,
                  const double* __restrict__ gpart_in, double* __restrict__ gpart_out,
                  const double* __restrict__ dpart, const double* __restrict__ bpart, int nspmv,
                  CgControl* __restrict__ ctl, double rtol2) {
@@ -797,8 +839,15 @@ cg_update_kernel(int n, int par, int first, const double* __restrict__ Minv, con
             x1 = x1 + alpha * p1; x2 = x2 + alpha * p2;
         }
         r1 = r1 - alpha * s1; r2 = r2 - alpha * s2;
+        if (sizeof(T) == 4) {                                // continue from the residual as it is stored
+            r1 = d3((float)r1.x, (float)r1.y, (float)r1.z); r2 = d3((float)r2.x, (float)r2.y, (float)r2.z);
+        }
         double r[6] = {r1.x, r1.y, r1.z, r2.x, r2.y, r2.z}, zn[6];
         apply_minv(blk21(Minv, i), r, zn);
+        if (sizeof(T) == 4) {
+#pragma unroll
+            for (int k = 0; k < 6; ++k) zn[k] = (double)(float)zn[k];     // gamma = r.z of the stored z
+        }
         store6(v.p, i, p1, p2); store6(v.s, i, s1, s2); store6(v.x, i, x1, x2); store6(v.r, i, r1, r2);
         store6(v.z, i, d3(zn[0], zn[1], zn[2]), d3(zn[3], zn[4], zn[5]));
 #pragma unroll
@@ -839,6 +888,78 @@ cg_update_kernel(int n, int par, int first, const double* __restrict__ Minv, con
     if (threadIdx.x == 0) gpart_out[blockIdx.x] = g[0];
 }
 
+// ------------------------------------------------------------------ fp32 mode: mixed-precision iterative refinement
+// The float PCG (cg_*_kernel<float>) solves for a CORRECTION; the solution itself and the residual it restarts from are
+// double:   X += x_f ;  r = b - (H + lambda I) X  (double operator, cg_spmv_kernel<double>) ;  solve (H + lambda I) e = r ...
+// X <- base + x_f (base = nullptr: X <- x_f); the 8 globals alike.  Also used to peek at the running solution for a
+// trial evaluation without disturbing the solve (out != base).
+__global__ void __launch_bounds__(kThreads)
+refine_accumulate_kernel(int n, const double* base, const float* __restrict__ xf, double* out,
+                         const double* baseg, const double* __restrict__ xg, double* outg, int add_xf) {     // (out may be base)
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        D3 a = d3(0, 0, 0), c = d3(0, 0, 0), u = d3(0, 0, 0), v = d3(0, 0, 0);
+        if (base) load6(base, i, a, c);
+        if (add_xf) load6(xf, i, u, v);
+        store6(out, i, a + u, c + v);
+    }
+    if (blockIdx.x == 0 && threadIdx.x < 8) outg[threadIdx.x] = (baseg ? baseg[threadIdx.x] : 0.0) + (add_xf ? xg[threadIdx.x] : 0.0);
+}
+// Restart of the float PCG from the TRUE residual: r = b - Wd, where Wd = (H + lambda I) X was just applied in double
+// (bpart: the block partials of its global rows); z = Minv r; gamma partial (double, from the unrounded r and z); the
+// float vectors r, z are what the iterations continue from; x, p, s are treated as zero by the first update.
+__global__ void __launch_bounds__(kThreads)
+cg_restart_kernel(int n, const double* __restrict__ b, const double* __restrict__ Wd, const float* __restrict__ Minv,
+                  const double* __restrict__ Ginv, const LinGlobal* __restrict__ lin, const double* __restrict__ Xg,
+                  const double* __restrict__ bpart, int nspmv, CgVecsT<float> v, double* __restrict__ gpart, CgControl* __restrict__ ctl) {
+    __shared__ double sm[kThreads / 32];
+    double g[1] = {0.0};
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        D3 b1, b2, w1, w2;
+        load6(b, i, b1, b2); load6(Wd, i, w1, w2);
+        const D3 r1 = b1 - w1, r2 = b2 - w2;
+        const double r[6] = {r1.x, r1.y, r1.z, r2.x, r2.y, r2.z};
+        double z[6];
+        apply_minv(blk21(Minv, i), r, z);
+        store6(v.r, i, r1, r2);
+        store6(v.z, i, d3(z[0], z[1], z[2]), d3(z[3], z[4], z[5]));
+#pragma unroll
+        for (int k = 0; k < 6; ++k) g[0] += r[k] * z[k];
+    }
+    if (blockIdx.x == 0) {
+        __shared__ double rgn[8];
+        __syncthreads();
+        if (threadIdx.x < 8) {
+            const int k = threadIdx.x;
+            double s = 0.0;
+            for (int bk = 0; bk < nspmv; ++bk) s += bpart[8 * (size_t)bk + k];
+            const double d = (k >= 6 ? lin->C[k * 8 + k] : 0.0) + ctl->lambda;
+            rgn[k] = lin->bg[k] - (s + d * Xg[k]);
+            v.rg[k] = rgn[k]; v.xg[k] = 0.0; v.pg[k] = 0.0; v.sg[k] = 0.0;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int a = 0; a < 8; ++a) {
+                double s = 0.0;
+                for (int c = 0; c < 8; ++c) s += Ginv[a * 8 + c] * rgn[c];
+                v.zg[a] = s;
+                g[0] += rgn[a] * s;
+            }
+            ctl->iters = 0; ctl->converged = 0;
+            ctl->sc[0].gamma_prev = 1.0; ctl->sc[0].alpha_prev = 1.0;
+            ctl->sc[1].gamma_prev = 1.0; ctl->sc[1].alpha_prev = 1.0;
+        }
+    }
+    block_reduce<1>(g, sm);
+    if (threadIdx.x == 0) gpart[blockIdx.x] = g[0];
+}
+// gamma_true = fixed-order sum of the restart's partials, left in the control block for the host
+__global__ void __launch_bounds__(kThreads)
+refine_gamma_kernel(int nb, const double* __restrict__ gpart, CgControl* __restrict__ ctl) {
+    __shared__ double sm[kThreads / 32];
+    const double g = sum_partials(gpart, nb, 1, sm);
+    if (threadIdx.x == 0) ctl->gamma_true = g;
+}
+
 // host -> CgControl without a (pageable, stream-serialising) memcpy: one thread writes the fields that are >= 0 / set
 __global__ void ctl_set_kernel(CgControl* ctl, double lambda, int set_lambda, double rtol2, int set_rtol, int clear_converged) {
     if (set_lambda) ctl->lambda = lambda;
@@ -848,8 +969,8 @@ __global__ void ctl_set_kernel(CgControl* ctl, double lambda, int set_lambda, do
 
 // ================================================================== LM trial: x_new = x (+) dx
 // Ptrial = P + dx (points), trial globals = exp(dx_T) * T_g, s + ds; scale partial = sum dx (lambda dx + b)
-template <bool kRO>
-DSC_D double apply_update_rows(int n, int first, int stride, const double* __restrict__ P, const double* __restrict__ x,
+template <bool kRO, typename T = double>
+DSC_D double apply_update_rows(int n, int first, int stride, const double* __restrict__ P, const T* __restrict__ x,
                                const double* __restrict__ b, double lambda, double* __restrict__ Ptrial) {
     double acc = 0.0;
     for (int i = first; i < n; i += stride) {
@@ -876,14 +997,15 @@ DSC_D double apply_update_globals(const Globals& g, const double* xg, const doub
     for (int k = 0; k < 8; ++k) acc += xg[k] * (lambda * xg[k] + bg[k]);
     return acc;
 }
+template <typename T>
 __global__ void __launch_bounds__(kThreads)
-apply_update_kernel(int n, const double* __restrict__ P, const double* __restrict__ x, const double* __restrict__ xg,
+apply_update_kernel(int n, const double* __restrict__ P, const T* __restrict__ x, const double* __restrict__ xg,
                     const double* __restrict__ b, const LinGlobal* __restrict__ lin, double lambda,
                     const Globals* __restrict__ Gcur, double* __restrict__ Ptrial, Globals* __restrict__ Gtrial,
                     double* __restrict__ part) {
     __shared__ double sm[kThreads / 32];
     double acc[1];
-    acc[0] = apply_update_rows<true>(n, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x, P, x, b, lambda, Ptrial);
+    acc[0] = apply_update_rows<true, T>(n, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x, P, x, b, lambda, Ptrial);
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         Globals g = *Gcur, o;
         acc[0] += apply_update_globals(g, xg, lin->bg, lambda, o);

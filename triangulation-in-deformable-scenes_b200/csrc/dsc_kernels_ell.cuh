@@ -195,13 +195,16 @@ cost_ell_kernel(int n, const double* __restrict__ P, const double* __restrict__ 
 // ELL slots (coalesced).  Global rows: T_g gradient from the per-row sum Bg_i = sum_j 2 W e_ij g_ij (the directed
 // twins carry the same e and g):  b_w = -2 sum_i X1_i x Bg_i,  b_v = 2 sum_i Bg_i;  C_TT = sum_dir W gT gT^T.
 // part[grid][kLinPart]: chi2[3], max diag, bg[8], C_TT packed (21), C_ss (2)  -- reduced by finalize_linearize_kernel.
-template <bool kRO>
+// kDual: the fp32 mode of the solver (dsc_set_precision) -- the records the PCG streams are ALSO written as float
+// (UF, JeF: same layouts, 4-byte values); the double copies serve the fp64 residual of the iterative refinement.
+template <bool kRO, bool kDual = false>
 DSC_D void linearize_tiles(int first, int stride, int n, const double* __restrict__ P, const double* __restrict__ Q,
                            const float4* __restrict__ uv, const double2* __restrict__ dm, const float2* __restrict__ isg,
                            const int* __restrict__ sliceptr, const int* __restrict__ ecol, const double* __restrict__ ewgt,
                            const Globals& G, const PairDev& pr, const WeightsDev& W,
                            double* __restrict__ b, double* __restrict__ D, double* __restrict__ U, double* __restrict__ Je,
-                           double* __restrict__ part_row /* [kLinPart] of this block */, double4* sw) {
+                           double* __restrict__ part_row /* [kLinPart] of this block */, double4* sw,
+                           float* __restrict__ UF = nullptr, float* __restrict__ JeF = nullptr) {
     __shared__ double wacc[kLinThreads / 32][kLinPart];
     __shared__ double wmax[kLinThreads / 32];
     __syncthreads();                                   // (a previous phase of the same block may still read the scratch)
@@ -242,6 +245,11 @@ DSC_D void linearize_tiles(int first, int stride, int n, const double* __restric
                 double* jb = Je + (size_t)bk * 288 + lane;
                 jb[0] = g.u.x; jb[32] = g.u.y; jb[64] = g.u.z; jb[96] = g.m.x; jb[128] = g.m.y; jb[160] = g.m.z;
                 jb[192] = g.g.x; jb[224] = g.g.y; jb[256] = g.g.z;
+                if (kDual) {
+                    float* jf = JeF + (size_t)bk * 288 + lane;
+                    jf[0] = (float)g.u.x; jf[32] = (float)g.u.y; jf[64] = (float)g.u.z; jf[96] = (float)g.m.x; jf[128] = (float)g.m.y;
+                    jf[160] = (float)g.m.z; jf[192] = (float)g.g.x; jf[224] = (float)g.g.y; jf[256] = (float)g.g.z;
+                }
                 const double gi[6] = {g.gi1.x, g.gi1.y, g.gi1.z, g.gi2.x, g.gi2.y, g.gi2.z};
                 const double gt[6] = {g.gw.x, g.gw.y, g.gw.z, g.gv.x, g.gv.y, g.gv.z};
                 const double we = W.arap_info * g.e;
@@ -329,6 +337,11 @@ DSC_D void linearize_tiles(int first, int stride, int n, const double* __restric
                 double* Up = U + ((size_t)(i >> 5) * kURec) * 32 + (i & 31);     // slice-major: component k of 32 rows is one 256 B line pair
 #pragma unroll
                 for (int k = 0; k < kURec; ++k) Up[k * 32] = Urec[k];
+                if (kDual) {
+                    float* Uf = UF + ((size_t)(i >> 5) * kURec) * 32 + (i & 31);
+#pragma unroll
+                    for (int k = 0; k < kURec; ++k) Uf[k * 32] = (float)Urec[k];
+                }
 #pragma unroll
                 for (int r = 0; r < 6; ++r) mx = fmax(mx, fabs(Dk[pk<6>(r, r)]));
                 glob[2] = chi_a;
@@ -358,18 +371,19 @@ DSC_D void linearize_tiles(int first, int stride, int n, const double* __restric
     }
 }
 
+template <bool kDual>
 __global__ void __launch_bounds__(kLinThreads, 1)
 linearize_ell_kernel(int n, const double* __restrict__ P, const double* __restrict__ Q, const float4* __restrict__ uv,
                      const double2* __restrict__ dm, const float2* __restrict__ isg, const int* __restrict__ sliceptr,
                      const int* __restrict__ ecol, const double* __restrict__ ewgt, const Globals* __restrict__ Gp,
                      const __grid_constant__ PairDev pr, const __grid_constant__ WeightsDev W,
                      double* __restrict__ b, double* __restrict__ D, double* __restrict__ U, double* __restrict__ Je,
-                     double* __restrict__ part) {
+                     double* __restrict__ part, float* __restrict__ UF, float* __restrict__ JeF) {
     extern __shared__ double4 sw[];
     __shared__ Globals G;
     if (threadIdx.x == 0) G = *Gp;
-    linearize_tiles<true>(blockIdx.x, gridDim.x, n, P, Q, uv, dm, isg, sliceptr, ecol, ewgt, G, pr, W, b, D, U, Je,
-                          part + (size_t)kLinPart * blockIdx.x, sw);
+    linearize_tiles<true, kDual>(blockIdx.x, gridDim.x, n, P, Q, uv, dm, isg, sliceptr, ecol, ewgt, G, pr, W, b, D, U, Je,
+                                 part + (size_t)kLinPart * blockIdx.x, sw, UF, JeF);
 }
 
 }  // namespace dsc

@@ -1,0 +1,115 @@
+// dsc_shard.cuh -- ONE frame pair over several GPUs (second row): the correspondences are sharded by
+// contiguous ranges of tiles of the internal (Morton) order, one process per GPU, every exchange fused into the
+// producing / consuming kernels over NVLink peer memory -- no collective library call anywhere on the solve path.
+//
+// Every rank holds the whole pair (same upload, same deterministic set-up, hence the same internal numbering and the
+// same sliced ELL) but computes only the rows [row_begin[rank], row_begin[rank + 1]).  What crosses NVLink:
+//   * halo rows: a row whose neighbour lives on another rank is PUSHED by its owner into that rank's local buffer with
+//     remote stores from inside the kernel that produces it (z of the PCG: cg_init / cg_update; trial state: apply_update),
+//     so every consumer kernel (cg_spmv, cost, linearise) reads local memory only;
+//   * partial sums (PCG scalars gamma / delta + the 8 global rows; linearisation and cost partials): the last block of the
+//     producing kernel to finish folds the block partials of its rank in a fixed order and stores the rank's totals into
+//     every rank's mailbox; consumers add the G mailbox entries in rank order -> the same bits on every rank, every run;
+//   * flags: a message is complete when its flag (a sequence number, release / acquire at system scope) has arrived;
+//     consumer kernels wait for it in their prologue.  All ranks run the same kernel sequence (every decision is taken
+//     from the same totals), so message n of a class on one rank pairs with message n of that class on every other.
+// Mailbox slots and the z buffers are double-buffered by message parity: a producer can only be one message ahead of
+// the slowest consumer (it needs that consumer's next message to proceed), so parity n is never overwritten while read.
+// Waits are bounded (a rank that died must not hang the others): on a time-out the error word is set and the kernels run
+// to completion on whatever they have; the host reports DSC_ERR_SHARD.
+#pragma once
+#include <cuda_runtime.h>
+
+namespace dsc {
+
+constexpr int kMaxShards = 8;
+constexpr int kMboxDoubles = 48;             // doubles per message slot
+enum ShardClass { SF_Z = 0 /* z pushed + gamma */, SF_S = 1 /* operator partials */, SF_P = 2 /* trial state pushed */,
+                  SF_L = 3 /* linearisation partials */, SF_C = 4 /* cost + scale partials */, SF_A = 5 /* final all-gather */,
+                  SF_COUNT = 6 };
+
+struct ShardDev {
+    int rank, world;
+    int row_begin[kMaxShards + 1];               // multiples of the tile size, row_begin[world] = n
+    double* Pbuf[2][kMaxShards];                 // the two state buffers of every rank (peer-mapped; [.][rank] is local)
+    double* zbuf[2][kMaxShards];                 // PCG vector z by message parity
+    double* mbox[kMaxShards];                    // [SF_COUNT][2][world][kMboxDoubles]
+    unsigned long long* flags[kMaxShards];       // [SF_COUNT][world]
+    unsigned long long* sent;                    // local [SF_COUNT]: messages this rank has sent per class
+    unsigned int* ticket;                        // local [SF_COUNT]: blocks that have finished (last-block election)
+    const unsigned char* exportmask;             // local [n]: bit q = rank q holds row i as a halo row
+    int* error;                                  // local: set by a wait that timed out
+    long long spin_limit;                        // clock64 ticks a wait may take
+};
+
+__device__ __forceinline__ unsigned long long shard_ld_flag(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void shard_st_flag(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ double* shard_slot(const ShardDev& S, int dst, int cls, unsigned long long seq, int src) {
+    return S.mbox[dst] + (((size_t)cls * 2 + (size_t)(seq & 1ull)) * S.world + src) * kMboxDoubles;
+}
+
+// Block-wide: returns when message `seq` of class cls from EVERY rank has arrived here (or the wait timed out).
+__device__ __forceinline__ void shard_wait(const ShardDev& S, int cls, unsigned long long seq) {
+    if ((int)threadIdx.x < S.world) {
+        const unsigned long long* f = S.flags[S.rank] + (size_t)cls * S.world + threadIdx.x;
+        const long long t0 = clock64();
+        while (shard_ld_flag(f) < seq) {
+            if (clock64() - t0 > S.spin_limit) { atomicExch(S.error, 1); break; }
+            __nanosleep(64);
+        }
+    }
+    __syncthreads();
+}
+__device__ __forceinline__ unsigned long long shard_sent(const ShardDev& S, int cls) {
+    return *reinterpret_cast<volatile unsigned long long*>(S.sent + cls);
+}
+
+// Last-block election of a producer kernel: every block calls this after its global writes (block partials, remote
+// stores); exactly one block -- the last to arrive -- gets true, with all other blocks' writes visible to it.
+__device__ __forceinline__ bool shard_last_block(const ShardDev& S, int cls) {
+    __shared__ int last;
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int t = atomicAdd(S.ticket + cls, 1u);
+        last = (t == gridDim.x - 1) ? 1 : 0;
+        if (last) S.ticket[cls] = 0;                              // ready for the next launch
+    }
+    __syncthreads();
+    if (last) __threadfence_system();
+    return last != 0;
+}
+
+// Called by the elected block: message (vals[0 .. count), count <= kMboxDoubles, may be 0) to every rank, then the flag.
+__device__ __forceinline__ void shard_send(const ShardDev& S, int cls, const double* vals, int count) {
+    const unsigned long long seq = shard_sent(S, cls) + 1ull;
+    for (int k = threadIdx.x; k < count * S.world; k += blockDim.x) {
+        const int dst = k / count, e = k % count;
+        shard_slot(S, dst, cls, seq, S.rank)[e] = vals[e];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if ((int)threadIdx.x < S.world) shard_st_flag(S.flags[threadIdx.x] + (size_t)cls * S.world + S.rank, seq);
+    if (threadIdx.x == 0) *reinterpret_cast<volatile unsigned long long*>(S.sent + cls) = seq;
+    __syncthreads();
+}
+
+// Sum over the ranks, in rank order, of entry e of message `seq` of class cls (after shard_wait): same bits everywhere.
+__device__ __forceinline__ double shard_total(const ShardDev& S, int cls, unsigned long long seq, int e) {
+    double s = 0.0;
+    for (int r = 0; r < S.world; ++r) s += __ldcg(shard_slot(S, S.rank, cls, seq, r) + e);
+    return s;
+}
+__device__ __forceinline__ double shard_max(const ShardDev& S, int cls, unsigned long long seq, int e) {
+    double s = 0.0;
+    for (int r = 0; r < S.world; ++r) s = fmax(s, __ldcg(shard_slot(S, S.rank, cls, seq, r) + e));
+    return s;
+}
+
+}  // namespace dsc
