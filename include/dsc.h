@@ -52,7 +52,8 @@ typedef enum {
     DSC_ERR_NONFINITE = -5,      /* cost became NaN/inf                                      */
     DSC_ERR_PCG_BREAKDOWN = -6,  /* p.Ap <= 0 or non-finite inside the linear solve          */
     DSC_ERR_GRAPH = -7,          /* neighbour graph is not symmetric / has bad indices       */
-    DSC_ERR_ALLOC = -8
+    DSC_ERR_ALLOC = -8,
+    DSC_ERR_SHARD = -9           /* point-sharded pair: a peer rank did not answer in time   */
 } dsc_status;
 
 /* camera models: Modules/Calibration/{KannalaBrandt8,PinHole}.cc */
@@ -286,6 +287,30 @@ int  dsc_batch_optimize(dsc_batch* batch, const dsc_weights* weights, int n_weig
 int  dsc_batch_download(dsc_batch* batch, float* X1, float* X2, double* scales, double* Tg7, double* update);
 /* pairs uploaded, their correspondences, CTAs per cluster and clusters of the last launch */
 int  dsc_batch_size(const dsc_batch* batch, int* n_problems, long long* n_points, int* cluster_ctas, int* clusters);
+
+/* ---- ONE frame pair over several GPUs (second row: "point-sharded edge evaluation with an allreduce of
+ * the small reduced system over NVLink"; the graph it partitions is the one of g2oBundleAdjustment.cc:883-953) ------------
+ * One process per GPU, one context per process.  Every rank uploads the SAME pair and graph and calls the SAME sequence
+ * of entry points (dsc_problem_upload, dsc_set_graph, dsc_compute_rotations, dsc_optimize, dsc_download, ...); the
+ * library splits the correspondences into contiguous ranges of tiles of its internal (space-filling-curve) order, each
+ * rank linearises / solves / evaluates its own range, and everything that crosses NVLink is written by the kernels
+ * themselves into peer-mapped memory: halo rows of the PCG vector z and of the trial state are pushed by their owners,
+ * the PCG scalars and the 8 global rows are exchanged by the last block of the producing kernel (no collective library
+ * call on the solve path; sums over the ranks are taken in rank order, so every rank and every run sees the same bits).
+ *   dsc_shard_init     before dsc_problem_upload: allocates the rank's exchange arena for up to max_points
+ *                      correspondences and returns its 64-byte inter-process handle (cudaIpcMemHandle_t);
+ *   dsc_shard_attach   handles[world][64] of all ranks, in rank order (exchange them with any host-side all-gather);
+ *   dsc_shard_partition  the row partition the library uses (pure host function): sliceptr[nslices + 1] of the sliced ELL
+ *                      -> row_begin[world + 1], multiples of 512 rows, equal work per rank;
+ *   dsc_shard_info     rank, world, own row range (internal numbering), own rows that are halo rows of a peer.
+ * A rank that waits for a peer longer than a few seconds gives up: the entry point returns DSC_ERR_SHARD.
+ * fp64 PCG path only (DSC_PRECISION_F32 and the dense / one-launch solvers are refused on a sharded context). */
+#define DSC_SHARD_HANDLE_BYTES 64
+#define DSC_SHARD_MAX_RANKS 8
+int dsc_shard_init(dsc_ctx* ctx, int rank, int world, int max_points, void* handle_out);
+int dsc_shard_attach(dsc_ctx* ctx, const void* handles);
+int dsc_shard_partition(const int32_t* sliceptr, int nslices, int world, int32_t* row_begin);
+int dsc_shard_info(const dsc_ctx* ctx, int* rank, int* world, int* row_begin, int* row_end, long long* halo_rows);
 
 #ifdef __cplusplus
 }

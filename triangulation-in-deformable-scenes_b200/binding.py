@@ -26,6 +26,7 @@ EXPORTS = [
     "dsc_reset_state", "dsc_set_pcg", "dsc_set_solver", "dsc_set_precision", "dsc_set_early_reject", "dsc_cost", "dsc_optimize", "dsc_download", "dsc_pixel_sigma",
     "dsc_batch_create", "dsc_batch_destroy", "dsc_batch_last_error", "dsc_batch_upload", "dsc_batch_set_pcg", "dsc_batch_set_early_reject",
     "dsc_batch_reset_state", "dsc_batch_optimize", "dsc_batch_download", "dsc_batch_size",
+    "dsc_shard_init", "dsc_shard_attach", "dsc_shard_partition", "dsc_shard_info",
     "dsc_debug_linearize", "dsc_debug_matvec", "dsc_profile_kernels", "dsc_profile_triangulate", "dsc_problem_size", "dsc_knn_build", "dsc_knn_download",
 ]
 KERNEL_NAMES = ["cg_spmv", "cg_update", "linearize", "cost", "precond", "apply_update", "rotations"]
@@ -311,6 +312,23 @@ class Context:
         p = PcgParams(float(rtol), int(max_iters), int(check_every))
         self._ck(self.lib.dsc_set_pcg(self.h, C.byref(p)))
 
+    # ---- point-sharded pair (dsc.h: dsc_shard_*): this context is one rank of ONE frame pair
+    def shard_init(self, rank, world, max_points):
+        """-> the 64-byte inter-process handle of this rank's exchange arena"""
+        h = np.zeros(64, np.uint8)
+        self._ck(self.lib.dsc_shard_init(self.h, int(rank), int(world), int(max_points), _fp(h)))
+        return h
+
+    def shard_attach(self, handles):
+        """handles: [world][64] uint8, rank order (every rank's shard_init result)"""
+        hs = np.ascontiguousarray(handles, np.uint8)
+        self._ck(self.lib.dsc_shard_attach(self.h, _fp(hs)))
+
+    def shard_info(self):
+        r, w, b, e, hl = C.c_int(), C.c_int(), C.c_int(), C.c_int(), C.c_longlong()
+        self._ck(self.lib.dsc_shard_info(self.h, C.byref(r), C.byref(w), C.byref(b), C.byref(e), C.byref(hl)))
+        return dict(rank=r.value, world=w.value, row_begin=b.value, row_end=e.value, halo_rows=hl.value)
+
     def set_precision(self, precision="f64"):
         """"f64" (default) or "f32": storage of the data the PCG streams (dsc.h, dsc_set_precision)"""
         self._ck(self.lib.dsc_set_precision(self.h, {"f64": 0, "f32": 1}.get(precision, precision)))
@@ -397,6 +415,16 @@ class Context:
         self._ck(self.lib.dsc_knn_download(self.h, _fp(rowptr), _fp(col)))
         col = col[:E.value]
         return rowptr, col, np.ones(E.value, np.float64)
+
+
+def shard_partition(sliceptr, world):
+    """dsc_shard_partition: row_begin[world + 1] of the library's row partition for a sliced ELL (pure host function)"""
+    sp = np.ascontiguousarray(sliceptr, np.int32)
+    rb = np.zeros(world + 1, np.int32)
+    st = load_library().dsc_shard_partition(_fp(sp), len(sp) - 1, int(world), _fp(rb))
+    if st != 0:
+        raise DscError(st, "dsc_shard_partition")
+    return rb
 
 
 class Batch:

@@ -14,6 +14,7 @@
 #include "dsc_dense.cuh"
 #include "dsc_small.cuh"
 #include "dsc_batch.cuh"
+#include "dsc_shard_kernels.cuh"
 
 #include <algorithm>
 #include <chrono>
@@ -114,6 +115,17 @@ struct dsc_ctx {
     int f32_cap = 0; long long f32_blkcap = 0;
     bool f32_fresh = false;                          // JeF's padding slots are all-zero for the current graph
     struct Refine { int pass_k = 0, total = 0, passes = 0; double gamma0 = 0.0, rho = 1.0; bool have_X = false; } rf;
+    // ---- point-sharded pair (dsc_shard_init / dsc_shard_attach, dsc_shard.cuh): this context is ONE rank of a frame pair
+    bool sharded = false, sh_attached = false;
+    ShardDev sh{};                                   // device-visible descriptor (peer-mapped buffers of every rank)
+    unsigned char* sh_arena = nullptr;               // local arena: Pbuf[2] | zbuf[2] | mailboxes | flags (exported by IPC)
+    void* sh_peer[kMaxShards] = {};                  // peers' arenas as mapped here
+    int sh_cap = 0;                                  // correspondences the arena was sized for
+    int* sh_part = nullptr; int sh_units = 0, sh_partcap = 0;    // work units of cg_spmv over the rank's own slices
+    unsigned char* sh_mask = nullptr;                // [cap] export mask
+    double* sh_out = nullptr;                        // [kMboxDoubles] result of the last shard_allreduce_kernel
+    int* sh_err = nullptr;
+    long long sh_halo_rows = 0;                      // own rows that at least one peer holds as halo rows
     int early_levels = 0;                            // early rejection of clearly bad LM trials (off by default)
     double early_rtol[4] = {0, 0, 0, 0}, early_margin[4] = {0, 0, 0, 0};
 };
@@ -131,6 +143,7 @@ const char* status_str(int s) {
         case DSC_ERR_PCG_BREAKDOWN: return "PCG breakdown";
         case DSC_ERR_GRAPH: return "neighbour graph invalid (must be symmetric, in range, no self loops)";
         case DSC_ERR_ALLOC: return "allocation failed";
+        case DSC_ERR_SHARD: return "point-sharded pair: a peer rank did not answer (or the sharding set-up is incomplete)";
     }
     return "unknown";
 }
@@ -238,6 +251,33 @@ void fill_pair(const dsc_pair* in, PairDev& o) {
     }
 }
 
+// Work units of cg_spmv_kernel over the slices [s0, s1) (s0 a tile boundary): full rounds of 16-slice tiles, then the
+// partial last round cut into one equal-work unit per block (a unit may be empty: the kernel skips it).
+constexpr double kRowCost = 32.0 * 256.0 / 2432.0;             // the 32 rows of a slice in units of one ELL block
+std::vector<int> spmv_units_of(const int* sp, int s0, int s1, int nbs) {
+    std::vector<int> hpart;
+    const int tsl = kSortGroup / 32;
+    const int ntiles = (s1 - s0 + tsl - 1) / tsl;
+    const int full = (ntiles / nbs) * nbs;                     // tiles in complete rounds
+    for (int t = 0; t < full; ++t) hpart.push_back(s0 + t * tsl);
+    int sl = std::min(s1, s0 + full * tsl);
+    if (sl < s1) {
+        const double total = (double)(sp[s1] - sp[sl]) + kRowCost * (s1 - sl);
+        double acc = 0.0;
+        for (int b = 0; b < nbs; ++b) {
+            hpart.push_back(sl);
+            const double target = total * (b + 1) / nbs;
+            while (sl < s1) {
+                const double c = (sp[sl + 1] - sp[sl]) + kRowCost;
+                if (acc + 0.5 * c > target) break;
+                acc += c; ++sl;
+            }
+        }
+    }
+    hpart.push_back(s1);
+    return hpart;
+}
+
 void drop_graphs(dsc_ctx* c) {
     for (auto& g : c->graphs) { if (g.exec) cudaGraphExecDestroy(g.exec); g.exec = nullptr; g.P = nullptr; }
 }
@@ -309,6 +349,7 @@ extern "C" int dsc_create(int device, dsc_ctx** out) {
         cudaFuncSetAttribute(cost_ell_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWinBytes) != cudaSuccess ||
         cudaFuncSetAttribute(cg_spmv_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SpmvCfg<double>::kSmem) != cudaSuccess ||
         cudaFuncSetAttribute(cg_spmv_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SpmvCfg<float>::kSmem) != cudaSuccess ||
+        cudaFuncSetAttribute(cg_spmv_kernel<double, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SpmvCfg<double>::kSmem) != cudaSuccess ||
         cudaFuncSetAttribute(linearize_ell_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWinBytes) != cudaSuccess ||
         cudaFuncSetAttribute(dense_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * kDenseMaxM)) != cudaSuccess ||
         cudaFuncSetAttribute(linearize_ell_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWinBytes) != cudaSuccess) return bail(DSC_ERR_CUDA);
@@ -321,6 +362,13 @@ extern "C" void dsc_destroy(dsc_ctx* ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     drop_graphs(ctx);
+    if (ctx->sharded) {                                // P, Ptrial and z live in the exported arena; peers' arenas are unmapped
+        ctx->P = nullptr; ctx->Ptrial = nullptr; ctx->vec[2] = nullptr;
+        for (int q = 0; q < kMaxShards; ++q) if (ctx->sh_peer[q]) cudaIpcCloseMemHandle(ctx->sh_peer[q]);
+        if (ctx->sh_arena) cudaFree(ctx->sh_arena);
+        if (ctx->sh.sent) cudaFree(ctx->sh.sent);
+        dev_free(ctx->sh_part); dev_free(ctx->sh_mask); dev_free(ctx->sh_out); dev_free(ctx->sh_err);
+    }
     dev_free(ctx->t_uv1); dev_free(ctx->t_uv2); dev_free(ctx->t_d1); dev_free(ctx->t_d2);
     dev_free(ctx->t_X1); dev_free(ctx->t_X2); dev_free(ctx->t_cos); dev_free(ctx->t_valid);
     dev_free(ctx->X1f); dev_free(ctx->X2f); dev_free(ctx->d_perm);
@@ -562,15 +610,17 @@ extern "C" int dsc_problem_upload(dsc_ctx* ctx, const dsc_pair* pair, int n,
     if (!ctx || !pair || n < 0 || (n > 0 && (!X1 || !X2 || !uv1 || !uv2 || !depth1 || !depth2)))
         return fail(ctx, DSC_ERR_INVALID_ARG, "dsc_problem_upload");
     CK(cudaSetDevice(ctx->device));
+    if (ctx->sharded && n > ctx->sh_cap) return fail(ctx, DSC_ERR_INVALID_ARG, "more correspondences than dsc_shard_init was sized for");
     if (n > ctx->cap) {
         size_t N = (size_t)n;
         CK(dev_alloc(ctx->X1f, 3 * N)); CK(dev_alloc(ctx->X2f, 3 * N)); CK(dev_alloc(ctx->d_perm, N));
-        CK(dev_alloc(ctx->P, 8 * N)); CK(dev_alloc(ctx->Ptrial, 8 * N)); CK(dev_alloc(ctx->P0, 8 * N)); CK(dev_alloc(ctx->Q, 4 * N));
+        if (!ctx->sharded) { CK(dev_alloc(ctx->P, 8 * N)); CK(dev_alloc(ctx->Ptrial, 8 * N)); }      // (sharded: in the exported arena)
+        CK(dev_alloc(ctx->P0, 8 * N)); CK(dev_alloc(ctx->Q, 4 * N));
         CK(dev_alloc(ctx->uv, N)); CK(dev_alloc(ctx->dm, N)); CK(dev_alloc(ctx->isg, N));
         CK(dev_alloc(ctx->r_uv1, N)); CK(dev_alloc(ctx->r_uv2, N)); CK(dev_alloc(ctx->r_d1, N)); CK(dev_alloc(ctx->r_d2, N));
         CK(dev_alloc(ctx->r_isg1, N)); CK(dev_alloc(ctx->r_isg2, N));
         CK(dev_alloc(ctx->b, 6 * N)); CK(dev_alloc(ctx->D, 21 * 32 * ((N + 31) / 32))); CK(dev_alloc(ctx->U, (size_t)kURec * 32 * ((N + 31) / 32))); CK(dev_alloc(ctx->Minv, 21 * 32 * ((N + 31) / 32)));
-        for (auto& v : ctx->vec) CK(dev_alloc(v, 6 * N));
+        for (int k = 0; k < 6; ++k) if (!(ctx->sharded && k == 2)) CK(dev_alloc(ctx->vec[k], 6 * N));
         ctx->cap = n;
     }
     ctx->n = n;
@@ -590,6 +640,150 @@ extern "C" int dsc_problem_upload(dsc_ctx* ctx, const dsc_pair* pair, int n,
     ctx->have_problem = true; ctx->have_graph = false; ctx->have_rot = false;
     drop_graphs(ctx);
     return upload_state(ctx, X1, X2, uv1, uv2, depth1, depth2, inv_sigma2_1, inv_sigma2_2);
+}
+
+// ------------------------------------------------------------------ point-sharded pair: set-up (dsc_shard.cuh)
+// Row partition: contiguous tile ranges of (nearly) equal work -- ELL blocks + rows, the cost model of the operator.
+extern "C" int dsc_shard_partition(const int32_t* sliceptr, int nslices, int world, int32_t* row_begin) {
+    if (!sliceptr || !row_begin || nslices < 0 || world < 1 || world > kMaxShards) return DSC_ERR_INVALID_ARG;
+    const int tsl = kSortGroup / 32;
+    const int ntiles = (nslices + tsl - 1) / tsl;
+    auto cost_to = [&](int tile) {                             // work of tiles [0, tile)
+        const int sl = std::min(nslices, tile * tsl);
+        return (double)sliceptr[sl] + kRowCost * sl;
+    };
+    const double total = cost_to(ntiles);
+    row_begin[0] = 0;
+    int t = 0;
+    for (int r = 1; r < world; ++r) {
+        const double target = total * r / world;
+        while (t < ntiles && cost_to(t + 1) - 0.5 * (cost_to(t + 1) - cost_to(t)) <= target) ++t;
+        row_begin[r] = t * kSortGroup;
+    }
+    row_begin[world] = nslices * 32;                           // (clamped to n by the caller)
+    for (int r = 1; r <= world; ++r) row_begin[r] = std::max(row_begin[r], row_begin[r - 1]);
+    return DSC_OK;
+}
+
+static size_t shard_align(size_t x) { return (x + 255) & ~(size_t)255; }
+struct ShardLayout { size_t P[2], z[2], mbox, flags, total; };
+static ShardLayout shard_layout(int cap, int world) {
+    ShardLayout L{};
+    size_t off = 0;
+    const size_t N = (size_t)cap;
+    for (int k = 0; k < 2; ++k) { L.P[k] = off; off = shard_align(off + sizeof(double) * 8 * N); }
+    for (int k = 0; k < 2; ++k) { L.z[k] = off; off = shard_align(off + sizeof(double) * 6 * N); }
+    L.mbox = off; off = shard_align(off + sizeof(double) * SF_COUNT * 2 * world * kMboxDoubles);
+    L.flags = off; off = shard_align(off + sizeof(unsigned long long) * SF_COUNT * world);
+    L.total = off;
+    return L;
+}
+
+extern "C" int dsc_shard_init(dsc_ctx* ctx, int rank, int world, int max_points, void* handle_out) {
+    if (!ctx || !handle_out || world < 1 || world > kMaxShards || rank < 0 || rank >= world || max_points < 1)
+        return fail(ctx, DSC_ERR_INVALID_ARG, "dsc_shard_init");
+    if (ctx->sharded || ctx->have_problem) return fail(ctx, DSC_ERR_STATE, "dsc_shard_init: call it once, before dsc_problem_upload");
+    static_assert(sizeof(cudaIpcMemHandle_t) == DSC_SHARD_HANDLE_BYTES, "handle size");
+    CK(cudaSetDevice(ctx->device));
+    const ShardLayout L = shard_layout(max_points, world);
+    CK(cudaMalloc(reinterpret_cast<void**>(&ctx->sh_arena), L.total));
+    CK(cudaMemset(ctx->sh_arena, 0, L.total));
+    unsigned long long* sent = nullptr; unsigned int* ticket = nullptr;
+    CK(cudaMalloc(reinterpret_cast<void**>(&sent), sizeof(unsigned long long) * SF_COUNT + sizeof(unsigned int) * SF_COUNT));
+    CK(cudaMemset(sent, 0, sizeof(unsigned long long) * SF_COUNT + sizeof(unsigned int) * SF_COUNT));
+    ticket = reinterpret_cast<unsigned int*>(sent + SF_COUNT);
+    CK(dev_alloc(ctx->sh_mask, (size_t)max_points)); CK(dev_alloc(ctx->sh_out, (size_t)kMboxDoubles)); CK(dev_alloc(ctx->sh_err, (size_t)1));
+    CK(cudaMemset(ctx->sh_mask, 0, (size_t)max_points));
+    CK(cudaMemset(ctx->sh_err, 0, sizeof(int)));
+    CK(cudaDeviceSynchronize());
+    cudaIpcMemHandle_t h;
+    CK(cudaIpcGetMemHandle(&h, ctx->sh_arena));
+    std::memcpy(handle_out, &h, sizeof(h));
+    dev_free(ctx->P); dev_free(ctx->Ptrial); dev_free(ctx->vec[2]);
+    ctx->P = reinterpret_cast<double*>(ctx->sh_arena + L.P[0]);
+    ctx->Ptrial = reinterpret_cast<double*>(ctx->sh_arena + L.P[1]);
+    ctx->vec[2] = reinterpret_cast<double*>(ctx->sh_arena + L.z[0]);
+    ctx->cap = 0;                                              // every other buffer is (re)allocated by the next upload
+    ShardDev& S = ctx->sh;
+    S = ShardDev{};
+    S.rank = rank; S.world = world;
+    S.sent = sent; S.ticket = ticket; S.exportmask = ctx->sh_mask; S.error = ctx->sh_err;
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, ctx->device));
+    const char* lim = std::getenv("DSC_SHARD_TIMEOUT_S");
+    S.spin_limit = (long long)((lim ? std::atof(lim) : 5.0) * 1e3 * (double)prop.clockRate);       // clockRate is in kHz
+    ctx->sh_cap = max_points;
+    ctx->sharded = true; ctx->sh_attached = false;
+    return DSC_OK;
+}
+
+extern "C" int dsc_shard_attach(dsc_ctx* ctx, const void* handles) {
+    if (!ctx || !handles) return fail(ctx, DSC_ERR_INVALID_ARG, "dsc_shard_attach");
+    if (!ctx->sharded || ctx->sh_attached) return fail(ctx, DSC_ERR_STATE, "dsc_shard_attach: after dsc_shard_init, once");
+    CK(cudaSetDevice(ctx->device));
+    ShardDev& S = ctx->sh;
+    const ShardLayout L = shard_layout(ctx->sh_cap, S.world);
+    for (int q = 0; q < S.world; ++q) {
+        unsigned char* base = ctx->sh_arena;
+        if (q != S.rank) {
+            cudaIpcMemHandle_t h;
+            std::memcpy(&h, static_cast<const unsigned char*>(handles) + (size_t)q * DSC_SHARD_HANDLE_BYTES, sizeof(h));
+            void* mapped = nullptr;
+            cudaError_t e = cudaIpcOpenMemHandle(&mapped, h, cudaIpcMemLazyEnablePeerAccess);
+            if (e != cudaSuccess) return fail(ctx, DSC_ERR_CUDA, std::string("cudaIpcOpenMemHandle (rank ") + std::to_string(q) + ") -> " + cudaGetErrorString(e));
+            ctx->sh_peer[q] = mapped;
+            base = static_cast<unsigned char*>(mapped);
+        }
+        for (int k = 0; k < 2; ++k) {
+            S.Pbuf[k][q] = reinterpret_cast<double*>(base + L.P[k]);
+            S.zbuf[k][q] = reinterpret_cast<double*>(base + L.z[k]);
+        }
+        S.mbox[q] = reinterpret_cast<double*>(base + L.mbox);
+        S.flags[q] = reinterpret_cast<unsigned long long*>(base + L.flags);
+    }
+    ctx->sh_attached = true;
+    return DSC_OK;
+}
+
+extern "C" int dsc_shard_info(const dsc_ctx* ctx, int* rank, int* world, int* row_begin, int* row_end, long long* halo_rows) {
+    if (!ctx || !ctx->sharded) return DSC_ERR_INVALID_ARG;
+    if (rank) *rank = ctx->sh.rank;
+    if (world) *world = ctx->sh.world;
+    if (row_begin) *row_begin = ctx->sh.row_begin[ctx->sh.rank];
+    if (row_end) *row_end = ctx->sh.row_begin[ctx->sh.rank + 1];
+    if (halo_rows) *halo_rows = ctx->sh_halo_rows;
+    return DSC_OK;
+}
+
+// after the sliced ELL exists: the row partition, the rank's work units of the operator, the export mask
+static int shard_setup_graph(dsc_ctx* ctx, const int* sp, int nslices) {
+    if (!ctx->sh_attached) return fail(ctx, DSC_ERR_SHARD, "dsc_shard_attach has not been called");
+    ShardDev& S = ctx->sh;
+    int rb[kMaxShards + 1];
+    dsc_shard_partition(sp, nslices, S.world, rb);
+    for (int r = 0; r <= S.world; ++r) S.row_begin[r] = std::min(rb[r], ctx->n);
+    const int r0 = S.row_begin[S.rank], r1 = S.row_begin[S.rank + 1];
+    const int s0 = r0 / 32, s1 = (r1 + 31) / 32;
+    std::vector<int> hpart = spmv_units_of(sp, s0, s1, grid_spmv(ctx, std::max(1, r1 - r0)));
+    ctx->sh_units = (int)hpart.size() - 1;
+    if ((int)hpart.size() > ctx->sh_partcap) { CK(dev_alloc(ctx->sh_part, hpart.size())); ctx->sh_partcap = (int)hpart.size(); }
+    CK(cudaMemcpyAsync(ctx->sh_part, hpart.data(), sizeof(int) * hpart.size(), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemsetAsync(ctx->sh_mask, 0, (size_t)ctx->n, ctx->stream));
+    if (r1 > r0) {
+        shard_exportmask_kernel<<<grid_threads(ctx, r1 - r0), 256, 0, ctx->stream>>>(S, ctx->n, ctx->sliceptr, ctx->ecol, ctx->sh_mask);
+        ctx->launches++;
+    }
+    CK(cudaGetLastError());
+    std::vector<unsigned char> hm((size_t)ctx->n);
+    if (ctx->n) CK(cudaMemcpyAsync(hm.data(), ctx->sh_mask, (size_t)ctx->n, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    long long halo = 0;
+    for (unsigned char m : hm) halo += m ? 1 : 0;
+    ctx->sh_halo_rows = halo;
+    // the trial buffer of every rank starts as a copy of the state: rows nobody pushes (not in any halo) stay valid
+    if (ctx->n) CK(cudaMemcpyAsync(ctx->Ptrial, ctx->P, sizeof(double) * 8 * ctx->n, cudaMemcpyDeviceToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return DSC_OK;
 }
 
 extern "C" int dsc_set_graph(dsc_ctx* ctx, int n, const int32_t* rowptr, const int32_t* col, const double* w,
@@ -693,29 +887,7 @@ extern "C" int dsc_set_graph(dsc_ctx* ctx, int n, const int32_t* rowptr, const i
     // Work units of the PCG operator (cg_spmv_kernel): full rounds of 16-slice tiles, then the partial last round cut
     // into one equal-work unit per block; a slice costs its ELL blocks (2432 B each) + its 32 rows (256 B each).
     int nbs = grid_spmv(ctx, n);
-    std::vector<int> hpart;
-    {
-        const int tsl = kSortGroup / 32;
-        const int ntiles = (nslices + tsl - 1) / tsl;
-        const int full = (ntiles / nbs) * nbs;                 // tiles in complete rounds
-        for (int t = 0; t < full; ++t) hpart.push_back(t * tsl);
-        int sl = std::min(nslices, full * tsl);
-        if (sl < nslices) {
-            const double row_cost = 32.0 * 256.0 / 2432.0;
-            const double total = (double)(sp[nslices] - sp[sl]) + row_cost * (nslices - sl);
-            double acc = 0.0;
-            for (int b = 0; b < nbs; ++b) {                     // a unit may be empty (the kernel skips it)
-                hpart.push_back(sl);
-                const double target = total * (b + 1) / nbs;
-                while (sl < nslices) {
-                    const double c = (sp[sl + 1] - sp[sl]) + row_cost;
-                    if (acc + 0.5 * c > target) break;
-                    acc += c; ++sl;
-                }
-            }
-        }
-        hpart.push_back(nslices);
-    }
+    std::vector<int> hpart = spmv_units_of(sp, 0, nslices, nbs);
     ctx->spmv_units = (int)hpart.size() - 1;
     if ((long long)nblk > ctx->blkcap) {
         CK(dev_alloc(ctx->ecol, nblk * 32)); CK(dev_alloc(ctx->ewgt, nblk * 32)); CK(dev_alloc(ctx->Je, nblk * 288));
@@ -738,6 +910,7 @@ extern "C" int dsc_set_graph(dsc_ctx* ctx, int n, const int32_t* rowptr, const i
     drop_graphs(ctx);
     int urc = build_state(ctx);                        // (synchronises the stream: hpart may go out of scope)
     lap("ell + state");
+    if (urc == DSC_OK && ctx->sharded) urc = shard_setup_graph(ctx, sp, nslices);
     return urc;
 }
 
@@ -832,16 +1005,52 @@ static int ready(dsc_ctx* ctx, const dsc_weights* w) {
         return fail(ctx, DSC_ERR_STATE, "need dsc_problem_upload, dsc_set_graph and rotations first");
     if (!(w->depth_sigma > 0.f) || !std::isfinite(w->depth_sigma))
         return fail(ctx, DSC_ERR_INVALID_ARG, "depth_sigma must be finite and > 0 (the reference divides by it, g2oBundleAdjustment.cc:824)");
+    if (ctx->sharded) {
+        if (!ctx->sh_attached) return fail(ctx, DSC_ERR_SHARD, "dsc_shard_attach has not been called");
+        if (ctx->precision != DSC_PRECISION_F64) return fail(ctx, DSC_ERR_INVALID_ARG, "a sharded context runs the fp64 PCG path only");
+        if (ctx->solver == DSC_SOLVER_DENSE) return fail(ctx, DSC_ERR_INVALID_ARG, "a sharded context runs the PCG path only");
+    }
+    return DSC_OK;
+}
+
+// ---- point-sharded pair: helpers of the solve path
+static int shard_tile0(const dsc_ctx* ctx) { return ctx->sh.row_begin[ctx->sh.rank] / kSortGroup; }
+static int shard_tile1(const dsc_ctx* ctx) { return (ctx->sh.row_begin[ctx->sh.rank + 1] + kSortGroup - 1) / kSortGroup; }
+static int shard_rows(const dsc_ctx* ctx) { return ctx->sh.row_begin[ctx->sh.rank + 1] - ctx->sh.row_begin[ctx->sh.rank]; }
+static int shard_pidx(const dsc_ctx* ctx, const double* P) { return P == ctx->sh.Pbuf[0][ctx->sh.rank] ? 0 : 1; }
+// sum (entry maxidx: maximum) over the blocks of this rank and over the ranks -> ctx->sh_out[count]
+static void shard_allreduce(dsc_ctx* ctx, int cls, const double* part, int nb, int stride, int count, int maxidx = -1) {
+    shard_allreduce_kernel<<<1, 256, 0, ctx->stream>>>(ctx->sh, cls, part, nb, stride, count, maxidx, ctx->sh_out);
+    ctx->launches++;
+}
+// DSC_ERR_SHARD if a wait on a peer has timed out (call after a stream synchronisation point is acceptable)
+static int shard_check(dsc_ctx* ctx) {
+    if (!ctx->sharded) return DSC_OK;
+    int* hp = reinterpret_cast<int*>(ctx->h_pinned + 7 * kMaxBlocks);
+    CK(cudaMemcpyAsync(hp, ctx->sh_err, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (*hp) return fail(ctx, DSC_ERR_SHARD, "a peer rank did not answer within the time limit (DSC_SHARD_TIMEOUT_S)");
     return DSC_OK;
 }
 
 static int eval_cost(dsc_ctx* ctx, const WeightsDev& W, const double* P, const Globals* G, double* chi2, double* parts) {
     int nb = grid_tiles(ctx, ctx->n, 2);
-    cost_ell_kernel<<<nb, kEllThreads, kWinBytes, ctx->stream>>>(ctx->n, P, ctx->Q, ctx->uv, ctx->dm, ctx->isg, ctx->sliceptr, ctx->ecol,
-                                                               ctx->ewgt, G, ctx->pair, W, ctx->part);
-    ctx->launches++;
-    CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(ctx->h_pinned, ctx->part, sizeof(double) * 3 * nb, cudaMemcpyDeviceToHost, ctx->stream));
+    if (ctx->sharded) {                                  // the rank's tiles, then the totals over the ranks (one "block" of 3)
+        nb = std::max(1, std::min(shard_tile1(ctx) - shard_tile0(ctx), ctx->sms * 2));
+        cost_ell_kernel<<<nb, kEllThreads, kWinBytes, ctx->stream>>>(ctx->n, P, ctx->Q, ctx->uv, ctx->dm, ctx->isg, ctx->sliceptr, ctx->ecol,
+                                                                   ctx->ewgt, G, ctx->pair, W, ctx->part, shard_tile0(ctx), shard_tile1(ctx));
+        shard_allreduce(ctx, SF_C, ctx->part, nb, 3, 3);
+        ctx->launches++;
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(ctx->h_pinned, ctx->sh_out, sizeof(double) * 3, cudaMemcpyDeviceToHost, ctx->stream));
+        nb = 1;
+    } else {
+        cost_ell_kernel<<<nb, kEllThreads, kWinBytes, ctx->stream>>>(ctx->n, P, ctx->Q, ctx->uv, ctx->dm, ctx->isg, ctx->sliceptr, ctx->ecol,
+                                                                   ctx->ewgt, G, ctx->pair, W, ctx->part, 0, -1);
+        ctx->launches++;
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(ctx->h_pinned, ctx->part, sizeof(double) * 3 * nb, cudaMemcpyDeviceToHost, ctx->stream));
+    }
     CK(cudaStreamSynchronize(ctx->stream));
     double p0 = host_sum(ctx->h_pinned, nb, 3, 0), p1 = host_sum(ctx->h_pinned, nb, 3, 1), p2 = host_sum(ctx->h_pinned, nb, 3, 2);
     if (parts) { parts[0] = p0; parts[1] = p1; parts[2] = p2; }
@@ -855,7 +1064,8 @@ extern "C" int dsc_cost(dsc_ctx* ctx, const dsc_weights* w, double* chi2, double
     if (!chi2) return DSC_ERR_INVALID_ARG;
     CK(cudaSetDevice(ctx->device));
     if (ctx->n == 0) { *chi2 = 0.0; if (parts) parts[0] = parts[1] = parts[2] = 0.0; return DSC_OK; }
-    return eval_cost(ctx, make_weights(ctx, w), ctx->P, ctx->Gcur, chi2, parts);
+    int rc = eval_cost(ctx, make_weights(ctx, w), ctx->P, ctx->Gcur, chi2, parts);
+    return rc ? rc : shard_check(ctx);
 }
 
 // The PCG's data in the two precisions: T = double -> Je, U, Minv, vec[]; T = float -> JeF, UF, MinvF, vecF[] (fp32 mode).
@@ -901,18 +1111,26 @@ static int ensure_f32(dsc_ctx* ctx) {
 }
 
 static void launch_linearize(dsc_ctx* ctx, const WeightsDev& W, int nb) {
+    const int t0 = ctx->sharded ? shard_tile0(ctx) : 0, t1 = ctx->sharded ? shard_tile1(ctx) : -1;
     if (f32(ctx))
         linearize_ell_kernel<true><<<nb, kLinThreads, kWinBytes, ctx->stream>>>(ctx->n, ctx->P, ctx->Q, ctx->uv, ctx->dm, ctx->isg, ctx->sliceptr, ctx->ecol,
-                                                                              ctx->ewgt, ctx->Gcur, ctx->pair, W, ctx->b, ctx->D, ctx->U, ctx->Je, ctx->part, ctx->UF, ctx->JeF);
+                                                                              ctx->ewgt, ctx->Gcur, ctx->pair, W, ctx->b, ctx->D, ctx->U, ctx->Je, ctx->part, ctx->UF, ctx->JeF, t0, t1);
     else
         linearize_ell_kernel<false><<<nb, kLinThreads, kWinBytes, ctx->stream>>>(ctx->n, ctx->P, ctx->Q, ctx->uv, ctx->dm, ctx->isg, ctx->sliceptr, ctx->ecol,
-                                                                               ctx->ewgt, ctx->Gcur, ctx->pair, W, ctx->b, ctx->D, ctx->U, ctx->Je, ctx->part, nullptr, nullptr);
+                                                                               ctx->ewgt, ctx->Gcur, ctx->pair, W, ctx->b, ctx->D, ctx->U, ctx->Je, ctx->part, nullptr, nullptr, t0, t1);
 }
 static int run_linearize(dsc_ctx* ctx, const WeightsDev& W, LinGlobal* hlin) {
     int nb = grid_tiles(ctx, ctx->n, 1);
     { int erc = ensure_f32(ctx); if (erc) return erc; }
-    launch_linearize(ctx, W, nb);
-    finalize_linearize_kernel<<<1, kThreads, 0, ctx->stream>>>(nb, ctx->part, ctx->lin);
+    if (ctx->sharded) {                                  // the rank's tiles; totals over the ranks = one "block" of partials
+        nb = std::max(1, std::min(shard_tile1(ctx) - shard_tile0(ctx), ctx->sms));
+        launch_linearize(ctx, W, nb);
+        shard_allreduce(ctx, SF_L, ctx->part, nb, kLinPart, kLinPart, 3);
+        finalize_linearize_kernel<<<1, kThreads, 0, ctx->stream>>>(1, ctx->sh_out, ctx->lin);
+    } else {
+        launch_linearize(ctx, W, nb);
+        finalize_linearize_kernel<<<1, kThreads, 0, ctx->stream>>>(nb, ctx->part, ctx->lin);
+    }
     ctx->launches += 2;
     CK(cudaGetLastError());
     LinGlobal* hp = reinterpret_cast<LinGlobal*>(ctx->h_pinned + 6 * kMaxBlocks);
@@ -926,7 +1144,7 @@ static int run_linearize(dsc_ctx* ctx, const WeightsDev& W, LinGlobal* hlin) {
 // PCG solve of (H + lambda I) dx = b in two entry points so that a solve can be paused at a loose tolerance,
 // inspected (trial cost) and resumed to the tight one: begin = preconditioner + r0/z0 + first operator
 // application; resume = iterate until sqrt(r.z / r0.z0) <= rtol, breakdown or max_iters.
-static bool small_active(const dsc_ctx* ctx) { return ctx->small_cluster > 0 && ctx->n <= ctx->small_max_rows && !f32(ctx); }
+static bool small_active(const dsc_ctx* ctx) { return ctx->small_cluster > 0 && ctx->n <= ctx->small_max_rows && !f32(ctx) && !ctx->sharded; }
 
 // one launch = the whole solve (or its continuation after a pause) by a single thread-block cluster (dsc_small.cuh)
 static int small_launch(dsc_ctx* ctx, const WeightsDev& W, int fresh) {
@@ -964,13 +1182,26 @@ static void launch_spmv(dsc_ctx* ctx, const WeightsDev& W, double lambda, const 
     CgVecsT<T> v = make_vecs<T>(ctx);
     cg_spmv_kernel<T><<<grid_spmv(ctx, ctx->n), kThreads, SpmvCfg<T>::kSmem, ctx->stream>>>(ctx->n, ctx->P, Sel<T>::Je(ctx), Sel<T>::U(ctx), ctx->sliceptr, ctx->ecol, ctx->spmv_part,
                                                                                          ctx->spmv_units, ctx->Gcur, ctx->pair, W, lambda, z ? z : v.z, zg ? zg : v.zg,
-                                                                                         w ? w : v.w, ctx->dpart, ctx->bpart, ctx->lin, ctl);
+                                                                                         w ? w : v.w, ctx->dpart, ctx->bpart, ctx->lin, ctl, ShardDev{});
 }
 template <typename T>
 static void launch_update(dsc_ctx* ctx, int par, int first, double lambda, int gin, int gout, double rtol2) {
     cg_update_kernel<T><<<grid_threads(ctx, (long long)ctx->n), kThreads, 0, ctx->stream>>>(ctx->n, par, first, Sel<T>::Minv(ctx), ctx->small + 48, ctx->lin, lambda, make_vecs<T>(ctx),
                                                                                          ctx->gpart[gin], ctx->gpart[gout], ctx->dpart, ctx->bpart, grid_spmv(ctx, ctx->n),
                                                                                          ctx->ctl, rtol2);
+}
+
+// point-sharded pair: the same three launches over the rank's rows; zpar = parity of the z buffer the launch reads
+static void shard_launch_spmv(dsc_ctx* ctx, const WeightsDev& W, double lambda, int zpar) {
+    CgVecs v = make_vecs(ctx);
+    const int nbs = grid_spmv(ctx, std::max(1, shard_rows(ctx)));
+    cg_spmv_kernel<double, true><<<nbs, kThreads, SpmvCfg<double>::kSmem, ctx->stream>>>(ctx->n, ctx->P, ctx->Je, ctx->U, ctx->sliceptr, ctx->ecol, ctx->sh_part, ctx->sh_units,
+                                                                                      ctx->Gcur, ctx->pair, W, lambda, ctx->sh.zbuf[zpar][ctx->sh.rank], v.zg, v.w,
+                                                                                      ctx->dpart, ctx->bpart, ctx->lin, ctx->ctl, ctx->sh);
+}
+static void shard_launch_update(dsc_ctx* ctx, int k, int first) {
+    shard_cg_update_kernel<<<grid_threads(ctx, std::max(1, shard_rows(ctx))), kThreads, 0, ctx->stream>>>(ctx->sh, ctx->n, k & 1, first, ctx->Minv, ctx->small + 48, ctx->lin,
+                                                                                                      make_vecs(ctx), k & 1, ctx->gpart[(k + 1) & 1], ctx->ctl);
 }
 
 static int pcg_begin(dsc_ctx* ctx, const WeightsDev& W, double lambda) {
@@ -983,7 +1214,11 @@ static int pcg_begin(dsc_ctx* ctx, const WeightsDev& W, double lambda) {
     }
     CK(cudaMemsetAsync(ctx->errflag, 0, sizeof(int), ctx->stream));
     ctl_set_kernel<<<1, 1, 0, ctx->stream>>>(ctx->ctl, lambda, 1, 0.0, 0, 0);
-    if (f32(ctx)) { launch_init<float>(ctx, lambda); launch_spmv<float>(ctx, W, lambda, ctx->ctl); ctx->rf = dsc_ctx::Refine{}; }
+    if (ctx->sharded) {
+        shard_cg_init_kernel<<<grid_threads(ctx, std::max(1, shard_rows(ctx))), kThreads, 0, ctx->stream>>>(ctx->sh, ctx->n, ctx->b, ctx->D, lambda, ctx->lin, ctx->Minv, ctx->small + 48,
+                                                                                                        ctx->errflag, make_vecs(ctx), 0, ctx->gpart[0], ctx->ctl);
+        shard_launch_spmv(ctx, W, lambda, 0);
+    } else if (f32(ctx)) { launch_init<float>(ctx, lambda); launch_spmv<float>(ctx, W, lambda, ctx->ctl); ctx->rf = dsc_ctx::Refine{}; }
     else { launch_init<double>(ctx, lambda); launch_spmv<double>(ctx, W, lambda, ctx->ctl); }
     ctx->launches += 3;
     CK(cudaGetLastError());
@@ -1004,7 +1239,8 @@ static int iteration_graph(dsc_ctx* ctx, const WeightsDev& W, cudaGraphExec_t* o
     cudaGraph_t graph = nullptr;
     CK(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
     for (int k = 2; k < 2 + kGraphIters; ++k) {
-        if (f32(ctx)) { launch_update<float>(ctx, k & 1, 0, 0.0, k & 1, (k + 1) & 1, 0.0); launch_spmv<float>(ctx, W, 0.0, ctx->ctl); }
+        if (ctx->sharded) { shard_launch_update(ctx, k, 0); shard_launch_spmv(ctx, W, 0.0, (k + 1) & 1); }
+        else if (f32(ctx)) { launch_update<float>(ctx, k & 1, 0, 0.0, k & 1, (k + 1) & 1, 0.0); launch_spmv<float>(ctx, W, 0.0, ctx->ctl); }
         else { launch_update<double>(ctx, k & 1, 0, 0.0, k & 1, (k + 1) & 1, 0.0); launch_spmv<double>(ctx, W, 0.0, ctx->ctl); }
     }
     cudaError_t e = cudaStreamEndCapture(ctx->stream, &graph);
@@ -1039,7 +1275,8 @@ static int pcg_iterate(dsc_ctx* ctx, const WeightsDev& W, double lambda, double 
                 ctx->launches += 2 * kGraphIters;
                 continue;
             }
-            if (f32(ctx)) { launch_update<float>(ctx, k & 1, k == 0 ? 1 : 0, lambda, k & 1, (k + 1) & 1, rtol2); launch_spmv<float>(ctx, W, lambda, ctx->ctl); }
+            if (ctx->sharded) { shard_launch_update(ctx, k, k == 0 ? 1 : 0); shard_launch_spmv(ctx, W, lambda, (k + 1) & 1); }
+            else if (f32(ctx)) { launch_update<float>(ctx, k & 1, k == 0 ? 1 : 0, lambda, k & 1, (k + 1) & 1, rtol2); launch_spmv<float>(ctx, W, lambda, ctx->ctl); }
             else { launch_update<double>(ctx, k & 1, k == 0 ? 1 : 0, lambda, k & 1, (k + 1) & 1, rtol2); launch_spmv<double>(ctx, W, lambda, ctx->ctl); }
             ctx->launches += 2;
             ++k; ++c;
@@ -1132,7 +1369,7 @@ static int pcg_resume(dsc_ctx* ctx, const WeightsDev& W, double lambda, double r
 
 // ---- dense direct solve of small problems (dsc_dense.cuh)
 static bool dense_active(const dsc_ctx* ctx) {
-    if (f32(ctx)) return false;                            // the fp32 mode is a mode of the PCG path
+    if (f32(ctx) || ctx->sharded) return false;            // the fp32 mode and the point-sharded pair are modes of the PCG path
     return ctx->solver == DSC_SOLVER_DENSE || (ctx->solver == DSC_SOLVER_AUTO && ctx->n <= DSC_DENSE_AUTO_MAX);
 }
 // once per LM iteration: H (dense, lower) and the right-hand side from the linearisation
@@ -1184,6 +1421,18 @@ static int dense_solve(dsc_ctx* ctx, double lambda) {
 static int eval_trial(dsc_ctx* ctx, const WeightsDev& W, double lambda, double* temp, double* scale) {
     int nbv = grid_threads(ctx, ctx->n);
     CgVecs v = make_vecs(ctx);
+    if (ctx->sharded) {  // own rows + halo rows into the peers' trial buffers; the exchange publishes them and sums the scale
+        nbv = grid_threads(ctx, std::max(1, shard_rows(ctx)));
+        shard_apply_update_kernel<<<nbv, kThreads, 0, ctx->stream>>>(ctx->sh, ctx->n, ctx->P, v.x, v.xg, ctx->b, ctx->lin, lambda, ctx->Gcur,
+                                                                    shard_pidx(ctx, ctx->Ptrial), ctx->Gtrial, ctx->part);
+        shard_allreduce(ctx, SF_P, ctx->part, nbv, 1, 1);
+        ctx->launches++;
+        CK(cudaMemcpyAsync(ctx->h_pinned + 3 * kMaxBlocks, ctx->sh_out, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        int rc = eval_cost(ctx, W, ctx->Ptrial, ctx->Gtrial, temp, nullptr);
+        if (rc) return rc;
+        *scale = ctx->h_pinned[3 * kMaxBlocks] + 1e-3;
+        return DSC_OK;
+    }
     if (f32(ctx)) {     // the step is X (+ the running correction x_f): peek at it without disturbing the solve
         const dsc_ctx::Refine& rf = ctx->rf;
         refine_accumulate_kernel<<<nbv, kThreads, 0, ctx->stream>>>(ctx->n, rf.have_X ? ctx->vec[0] : nullptr, ctx->vecF[0], ctx->vec[1],
@@ -1312,7 +1561,18 @@ extern "C" int dsc_optimize(dsc_ctx* ctx, const dsc_weights* w, int n_iters, dsc
     st.final_chi2 = current;
     st.kernel_launches = (int)(ctx->launches - launches0);
     if (stats) *stats = st;
+    if (rc == DSC_OK) rc = shard_check(ctx);
     return rc;
+}
+
+// point-sharded pair: every rank's own rows of the state into every rank's copy, so that what follows sees the whole pair
+static int shard_sync_state(dsc_ctx* ctx) {
+    if (!ctx->sharded || !ctx->sh_attached || !ctx->have_graph || ctx->n == 0) return DSC_OK;
+    shard_allgather_state_kernel<<<grid_threads(ctx, std::max(1, shard_rows(ctx))), 256, 0, ctx->stream>>>(ctx->sh, ctx->n, shard_pidx(ctx, ctx->P));
+    ctx->launches++;
+    shard_allreduce(ctx, SF_A, ctx->part, 1, 1, 1);          // (the value is irrelevant: its flag publishes the rows)
+    CK(cudaGetLastError());
+    return shard_check(ctx);
 }
 
 extern "C" int dsc_download(dsc_ctx* ctx, float* X1, float* X2, double* X1d, double* X2d,
@@ -1324,6 +1584,7 @@ extern "C" int dsc_download(dsc_ctx* ctx, float* X1, float* X2, double* X1d, dou
     Globals g;
     CK(cudaMemcpyAsync(&g, ctx->Gcur, sizeof(Globals), cudaMemcpyDeviceToHost, ctx->stream));
     double upd = 0.0;
+    { int src = shard_sync_state(ctx); if (src) return src; }
     if (n > 0) {
         int nb = grid_threads(ctx, n);
         // fp64 copies in the caller's order go through the CG scratch vector w ([n][6] doubles, dead between solves)
@@ -1353,6 +1614,7 @@ extern "C" int dsc_pixel_sigma(dsc_ctx* ctx, double* sigma) {
     CK(cudaSetDevice(ctx->device));
     int n = ctx->n;
     if (n == 0) { sigma[0] = sigma[1] = std::numeric_limits<double>::quiet_NaN(); return DSC_OK; }
+    { int src = shard_sync_state(ctx); if (src) return src; }
     int nb = grid_threads(ctx, n);
     pixel_sigma_kernel<<<nb, kThreads, 0, ctx->stream>>>(n, ctx->P, ctx->uv, ctx->pair, ctx->part);
     ctx->launches++;
@@ -1370,6 +1632,7 @@ extern "C" int dsc_pixel_sigma(dsc_ctx* ctx, double* sigma) {
 extern "C" int dsc_debug_linearize(dsc_ctx* ctx, const dsc_weights* w, double* b, double* hdiag, double* chi2) {
     int s = ready(ctx, w);
     if (s) return s;
+    if (ctx->sharded) return fail(ctx, DSC_ERR_STATE, "test hook: not on a sharded context");
     CK(cudaSetDevice(ctx->device));
     int n = ctx->n;
     WeightsDev W = make_weights(ctx, w);
@@ -1397,6 +1660,7 @@ extern "C" int dsc_debug_linearize(dsc_ctx* ctx, const dsc_weights* w, double* b
 extern "C" int dsc_debug_matvec(dsc_ctx* ctx, const dsc_weights* w, double lambda, const double* x, double* y) {
     int s = ready(ctx, w);
     if (s) return s;
+    if (ctx->sharded) return fail(ctx, DSC_ERR_STATE, "test hook: not on a sharded context");
     if (!x || !y) return DSC_ERR_INVALID_ARG;
     CK(cudaSetDevice(ctx->device));
     int n = ctx->n;
@@ -1449,6 +1713,7 @@ extern "C" int dsc_profile_kernels(dsc_ctx* ctx, const dsc_weights* w, int warm,
     int s = ready(ctx, w);
     if (s) return s;
     if (!ms || reps < 1 || warm < 0) return DSC_ERR_INVALID_ARG;
+    if (ctx->sharded) return fail(ctx, DSC_ERR_STATE, "per-kernel timing: not on a sharded context");
     CK(cudaSetDevice(ctx->device));
     int n = ctx->n;
     if (n == 0) return fail(ctx, DSC_ERR_STATE, "empty problem");
@@ -1503,7 +1768,7 @@ extern "C" int dsc_profile_kernels(dsc_ctx* ctx, const dsc_weights* w, int warm,
     if (s) return s;
     s = time_it(DSC_K_COST, [&]() {
         cost_ell_kernel<<<grid_tiles(ctx, n, 2), kEllThreads, kWinBytes, ctx->stream>>>(n, ctx->P, ctx->Q, ctx->uv, ctx->dm, ctx->isg, ctx->sliceptr, ctx->ecol,
-                                                                                  ctx->ewgt, ctx->Gcur, ctx->pair, W, ctx->part);
+                                                                                  ctx->ewgt, ctx->Gcur, ctx->pair, W, ctx->part, 0, -1);
     });
     if (s) return s;
     s = time_it(DSC_K_PRECOND, [&]() {

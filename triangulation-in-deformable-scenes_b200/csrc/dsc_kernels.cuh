@@ -27,6 +27,7 @@
 // partials, summed in a fixed order by the consumer).
 #pragma once
 #include "dsc_math.cuh"
+#include "dsc_shard.cuh"
 
 namespace dsc {
 
@@ -618,14 +619,17 @@ template <typename T> struct SpmvCfg {
 };
 constexpr int kSpmvSmem = SpmvCfg<double>::kSmem;
 
-template <typename T>
+// kShard: one rank of a point-sharded pair (dsc_shard.cuh) -- the work units cover the rank's own slices only, z holds
+// the halo rows the peers pushed (waited for in the prologue), and the LAST block of the launch to finish sends the
+// rank's totals of z.w and of the 8 global rows to every rank.
+template <typename T, bool kShard = false>
 __global__ void __launch_bounds__(kThreads, 2)
 cg_spmv_kernel(int n, const double* __restrict__ P, const T* __restrict__ Je, const T* __restrict__ U,
                const int* __restrict__ sliceptr, const int* __restrict__ ecol, const int* __restrict__ part, int nunits,
                const Globals* __restrict__ Gp, const __grid_constant__ PairDev pr, const __grid_constant__ WeightsDev W,
                double lambda, const T* __restrict__ z, const double* __restrict__ zg, T* __restrict__ w,
                double* __restrict__ dpart, double* __restrict__ bpart,
-               const LinGlobal* __restrict__ lin, const CgControl* __restrict__ ctl) {
+               const LinGlobal* __restrict__ lin, const CgControl* __restrict__ ctl, const __grid_constant__ ShardDev S) {
     constexpr int kSpmvStages = SpmvCfg<T>::kStages, kSpmvStageBytes = SpmvCfg<T>::kStageBytes, kSpmvWinBytes = SpmvCfg<T>::kWinBytes;
     constexpr int kJeBytes = SpmvCfg<T>::kJeBytes, kZRow = SpmvCfg<T>::kZRow;
     extern __shared__ __align__(128) unsigned char dyn[];
@@ -637,6 +641,7 @@ cg_spmv_kernel(int n, const double* __restrict__ P, const T* __restrict__ Je, co
     double4* sx = reinterpret_cast<double4*>(dyn + kSortGroup * kZRow);          // X1 of the tile
     if (ctl && (ctl->converged || ctl->breakdown)) return;   // flags are only written by an EARLIER launch
     if (ctl) lambda = ctl->lambda;
+    if (kShard) shard_wait(S, SF_Z, shard_sent(S, SF_Z));    // the peers' halo rows of z have arrived
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int wpb = kThreads / 32;
     if (threadIdx.x < 9) Rg[threadIdx.x] = Gp->Rg[threadIdx.x];
@@ -790,9 +795,21 @@ cg_spmv_kernel(int n, const double* __restrict__ P, const T* __restrict__ Je, co
     if (threadIdx.x == 0) {
         double dl = acc[8];
         for (int k = 0; k < 8; ++k) { bpart[8 * (size_t)blockIdx.x + k] = acc[k]; dl += zgs[k] * acc[k]; }
-        if (blockIdx.x == 0)     // diagonal of the global rows that is not inside the edge sums: (C_ss + lambda)
+        if (blockIdx.x == 0 && (!kShard || S.rank == 0))     // diagonal of the global rows that is not inside the edge sums: (C_ss + lambda)
             for (int k = 0; k < 8; ++k) dl += zgs[k] * ((k >= 6 ? lin->C[k * 8 + k] : 0.0) + lambda) * zgs[k];
         dpart[blockIdx.x] = dl;
+    }
+    if (kShard) {
+        __shared__ double tot[9];
+        if (!shard_last_block(S, SF_S)) return;
+        for (int e = warp; e < 9; e += wpb) {              // fixed-order totals of dpart[grid] and bpart[grid][8]
+            double v = 0.0;
+            for (int i = lane; i < (int)gridDim.x; i += 32) v += e == 0 ? __ldcg(dpart + i) : __ldcg(bpart + 8 * (size_t)i + (e - 1));
+            v = warp_sum(v);
+            if (lane == 0) tot[e] = v;
+        }
+        __syncthreads();
+        shard_send(S, SF_S, tot, 9);
     }
 }
 

@@ -132,10 +132,11 @@ template <bool kRO>
 DSC_D void cost_tiles(int first, int stride, int n, const double* __restrict__ P, const double* __restrict__ Q,
                       const float4* __restrict__ uv, const double2* __restrict__ dm, const float2* __restrict__ isg,
                       const int* __restrict__ sliceptr, const int* __restrict__ ecol, const double* __restrict__ ewgt,
-                      const Globals& G, const PairDev& pr, const WeightsDev& W, double4* sw, double (&acc)[3]) {
+                      const Globals& G, const PairDev& pr, const WeightsDev& W, double4* sw, double (&acc)[3],
+                      int tile0 = 0, int tile1 = -1 /* tiles [tile0, tile1): the rank's share of a point-sharded pair */) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
-    const int ntiles = (n + kSortGroup - 1) / kSortGroup;
-    for (int tile = first; tile < ntiles; tile += stride) {
+    const int ntiles = tile1 < 0 ? (n + kSortGroup - 1) / kSortGroup : tile1;
+    for (int tile = tile0 + first; tile < ntiles; tile += stride) {
         const int v0 = tile * kSortGroup, nv = min(kSortGroup, n - v0);
         __syncthreads();
         stage_window<kRO>(sw, P, Q, n, v0, nv, true);
@@ -179,13 +180,14 @@ __global__ void __launch_bounds__(kEllThreads, 2)
 cost_ell_kernel(int n, const double* __restrict__ P, const double* __restrict__ Q, const float4* __restrict__ uv,
                 const double2* __restrict__ dm, const float2* __restrict__ isg, const int* __restrict__ sliceptr,
                 const int* __restrict__ ecol, const double* __restrict__ ewgt, const Globals* __restrict__ Gp,
-                const __grid_constant__ PairDev pr, const __grid_constant__ WeightsDev W, double* __restrict__ part) {
+                const __grid_constant__ PairDev pr, const __grid_constant__ WeightsDev W, double* __restrict__ part,
+                int tile0, int tile1) {
     extern __shared__ double4 sw[];
     __shared__ double sm[3 * (kEllThreads / 32)];
     __shared__ Globals G;
     if (threadIdx.x == 0) G = *Gp;
     double acc[3] = {0.0, 0.0, 0.0};
-    cost_tiles<true>(blockIdx.x, gridDim.x, n, P, Q, uv, dm, isg, sliceptr, ecol, ewgt, G, pr, W, sw, acc);
+    cost_tiles<true>(blockIdx.x, gridDim.x, n, P, Q, uv, dm, isg, sliceptr, ecol, ewgt, G, pr, W, sw, acc, tile0, tile1);
     block_reduce<3>(acc, sm);
     if (threadIdx.x == 0) { part[3 * blockIdx.x] = acc[0]; part[3 * blockIdx.x + 1] = acc[1]; part[3 * blockIdx.x + 2] = acc[2]; }
 }
@@ -204,15 +206,15 @@ DSC_D void linearize_tiles(int first, int stride, int n, const double* __restric
                            const Globals& G, const PairDev& pr, const WeightsDev& W,
                            double* __restrict__ b, double* __restrict__ D, double* __restrict__ U, double* __restrict__ Je,
                            double* __restrict__ part_row /* [kLinPart] of this block */, double4* sw,
-                           float* __restrict__ UF = nullptr, float* __restrict__ JeF = nullptr) {
+                           float* __restrict__ UF = nullptr, float* __restrict__ JeF = nullptr, int tile0 = 0, int tile1 = -1) {
     __shared__ double wacc[kLinThreads / 32][kLinPart];
     __shared__ double wmax[kLinThreads / 32];
     __syncthreads();                                   // (a previous phase of the same block may still read the scratch)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     for (int k = lane; k < kLinPart; k += 32) wacc[warp][k] = 0.0;
     if (lane == 0) wmax[warp] = 0.0;
-    const int ntiles = (n + kSortGroup - 1) / kSortGroup;
-    for (int tile = first; tile < ntiles; tile += stride) {
+    const int ntiles = tile1 < 0 ? (n + kSortGroup - 1) / kSortGroup : tile1;
+    for (int tile = tile0 + first; tile < ntiles; tile += stride) {
         const int v0 = tile * kSortGroup, nv = min(kSortGroup, n - v0);
         __syncthreads();
         stage_window<kRO>(sw, P, Q, n, v0, nv, true);
@@ -378,12 +380,12 @@ linearize_ell_kernel(int n, const double* __restrict__ P, const double* __restri
                      const int* __restrict__ ecol, const double* __restrict__ ewgt, const Globals* __restrict__ Gp,
                      const __grid_constant__ PairDev pr, const __grid_constant__ WeightsDev W,
                      double* __restrict__ b, double* __restrict__ D, double* __restrict__ U, double* __restrict__ Je,
-                     double* __restrict__ part, float* __restrict__ UF, float* __restrict__ JeF) {
+                     double* __restrict__ part, float* __restrict__ UF, float* __restrict__ JeF, int tile0, int tile1) {
     extern __shared__ double4 sw[];
     __shared__ Globals G;
     if (threadIdx.x == 0) G = *Gp;
     linearize_tiles<true, kDual>(blockIdx.x, gridDim.x, n, P, Q, uv, dm, isg, sliceptr, ecol, ewgt, G, pr, W, b, D, U, Je,
-                                 part + (size_t)kLinPart * blockIdx.x, sw, UF, JeF);
+                                 part + (size_t)kLinPart * blockIdx.x, sw, UF, JeF, tile0, tile1);
 }
 
 }  // namespace dsc

@@ -7,9 +7,11 @@
 //   * halo rows: a row whose neighbour lives on another rank is PUSHED by its owner into that rank's local buffer with
 //     remote stores from inside the kernel that produces it (z of the PCG: cg_init / cg_update; trial state: apply_update),
 //     so every consumer kernel (cg_spmv, cost, linearise) reads local memory only;
-//   * partial sums (PCG scalars gamma / delta + the 8 global rows; linearisation and cost partials): the last block of the
-//     producing kernel to finish folds the block partials of its rank in a fixed order and stores the rank's totals into
-//     every rank's mailbox; consumers add the G mailbox entries in rank order -> the same bits on every rank, every run;
+//   * partial sums: the rank's total (its block partials folded in a fixed order) goes into every rank's mailbox and
+//     consumers add the G mailbox entries in rank order -> the same bits on every rank, every run.  Inside the PCG loop
+//     (gamma from cg_init / cg_update; delta + the 8 global rows from cg_spmv) the LAST BLOCK of the producing kernel to
+//     finish does that, so an iteration stays two launches; the per-trial sums (linearisation, trial scale, cost) take
+//     a one-block exchange kernel (shard_allreduce_kernel), whose flag also publishes the halo rows its predecessor pushed;
 //   * flags: a message is complete when its flag (a sequence number, release / acquire at system scope) has arrived;
 //     consumer kernels wait for it in their prologue.  All ranks run the same kernel sequence (every decision is taken
 //     from the same totals), so message n of a class on one rank pairs with message n of that class on every other.
@@ -60,6 +62,7 @@ __device__ __forceinline__ void shard_wait(const ShardDev& S, int cls, unsigned 
         const unsigned long long* f = S.flags[S.rank] + (size_t)cls * S.world + threadIdx.x;
         const long long t0 = clock64();
         while (shard_ld_flag(f) < seq) {
+            if (*reinterpret_cast<volatile int*>(S.error)) break;                 // a wait has already timed out: do not wait again
             if (clock64() - t0 > S.spin_limit) { atomicExch(S.error, 1); break; }
             __nanosleep(64);
         }
@@ -110,6 +113,70 @@ __device__ __forceinline__ double shard_max(const ShardDev& S, int cls, unsigned
     double s = 0.0;
     for (int r = 0; r < S.world; ++r) s = fmax(s, __ldcg(shard_slot(S, S.rank, cls, seq, r) + e));
     return s;
+}
+
+// One-block exchange: the rank's total of `count` per-block partials part[nb][stride] (entry maxidx: maximum instead of
+// sum) -> every rank's mailbox -> wait for all ranks -> out[count] = totals over the ranks (rank order).  Launched right
+// after the kernel that wrote `part`; the flag it raises also tells the peers that the halo rows that kernel pushed into
+// their buffers are complete (stream order + the system-scope fence of the pushing threads).
+__global__ void __launch_bounds__(256)
+shard_allreduce_kernel(const __grid_constant__ ShardDev S, int cls, const double* __restrict__ part, int nb, int stride, int count,
+                       int maxidx, double* __restrict__ out) {
+    __shared__ double vals[kMboxDoubles];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int e = warp; e < count; e += (int)(blockDim.x >> 5)) {        // one warp per entry, fixed order
+        double v = 0.0;
+        for (int i = lane; i < nb; i += 32) {
+            const double x = part[(size_t)i * stride + e];
+            v = e == maxidx ? fmax(v, x) : v + x;
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            const double y = __shfl_xor_sync(0xffffffffu, v, o);
+            v = e == maxidx ? fmax(v, y) : v + y;
+        }
+        if (lane == 0) vals[e] = v;
+    }
+    __syncthreads();
+    shard_send(S, cls, vals, count);
+    const unsigned long long seq = shard_sent(S, cls);
+    shard_wait(S, cls, seq);
+    for (int e = threadIdx.x; e < count; e += blockDim.x) out[e] = e == maxidx ? shard_max(S, cls, seq, e) : shard_total(S, cls, seq, e);
+}
+
+// the ranks that hold row i as a halo row: bit q set <=> a neighbour of row i is owned by rank q != owner(i)
+__global__ void __launch_bounds__(256)
+shard_exportmask_kernel(const __grid_constant__ ShardDev S, int n, const int* __restrict__ sliceptr, const int* __restrict__ ecol,
+                        unsigned char* __restrict__ mask) {
+    const int r0 = S.row_begin[S.rank], r1 = S.row_begin[S.rank + 1];
+    for (int i = r0 + blockIdx.x * blockDim.x + threadIdx.x; i < r1; i += gridDim.x * blockDim.x) {
+        const int sl = i >> 5, lane = i & 31;
+        unsigned m = 0;
+        for (int bk = sliceptr[sl]; bk < sliceptr[sl + 1]; ++bk) {
+            const int j = ecol[(size_t)bk * 32 + lane];
+            if (j >= r0 && j < r1) continue;
+            int q = 0;
+            while (q + 1 < S.world && j >= S.row_begin[q + 1]) ++q;
+            m |= 1u << q;
+        }
+        mask[i] = (unsigned char)m;
+    }
+}
+
+// final all-gather of the state: every rank pushes its own rows of P (both planes) to all peers (shard_allreduce_kernel
+// of the update norm follows and publishes them)
+__global__ void __launch_bounds__(256)
+shard_allgather_state_kernel(const __grid_constant__ ShardDev S, int n, int pidx) {
+    const int r0 = S.row_begin[S.rank], r1 = S.row_begin[S.rank + 1];
+    const double4* src = reinterpret_cast<const double4*>(S.Pbuf[pidx][S.rank]);
+    for (int i = r0 + blockIdx.x * blockDim.x + threadIdx.x; i < r1; i += gridDim.x * blockDim.x) {
+        const double4 a = src[i], b = src[(size_t)n + i];
+        for (int q = 0; q < S.world; ++q) {
+            if (q == S.rank) continue;
+            double4* dst = reinterpret_cast<double4*>(S.Pbuf[pidx][q]);
+            dst[i] = a; dst[(size_t)n + i] = b;
+        }
+    }
+    __threadfence_system();
 }
 
 }  // namespace dsc

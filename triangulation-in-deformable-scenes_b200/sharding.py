@@ -1,4 +1,7 @@
-"""Multi-GPU plumbing for the way this path shards: independent frame-pair problems (BASELINE.json configs[4]).
+"""Multi-GPU plumbing for the two ways this path shards: independent frame-pair problems (BASELINE.json
+configs[4], below) and ONE frame pair split by points over the GPUs (ShardedPair at the end of this file: the data plane
+is inside the library -- kernels writing peer-mapped memory over NVLink; torch.distributed only carries the 64-byte
+memory handles once, at set-up).
 
 One process per GPU.  A problem is owned by exactly one rank (static round-robin by problem index: the reference has no
 notion of ranks, and on one GPU the device-side queue of lm_batch_kernel balances the load between clusters); there is
@@ -105,3 +108,40 @@ class ShardedBatch:
 
     def close(self):
         self.batch.close()
+
+
+# ---------------------------------------------------------------------------------------------- one pair over several GPUs
+def exchange_handles(dist, device, handle, world, rank):
+    """all-gather of the ranks' 64-byte arena handles -> [world][64] uint8 in rank order (the only use of torch.distributed
+    by the point-sharded path)."""
+    handle = np.ascontiguousarray(handle, np.uint8).reshape(-1)
+    if dist is None or world == 1:
+        return handle[None, :].copy()
+    import torch
+    mine = torch.from_numpy(handle.copy()).to(device)
+    table = torch.empty((world, handle.size), dtype=torch.uint8, device=device)
+    dist.all_gather_into_tensor(table.view(-1), mine)
+    out = table.cpu().numpy()
+    if not np.array_equal(out[rank], handle):
+        raise RuntimeError("handle exchange: own handle came back changed")
+    return out
+
+
+class ShardedPair:
+    """One rank of a frame pair split by points (dsc.h: dsc_shard_*).  Every rank builds it with the same problem; after
+    attach() the Context is used exactly like a single-GPU one (problem_upload, set_graph, compute_rotations, optimize,
+    download): every rank gets the same records and, after download, the whole refined pair."""
+
+    def __init__(self, pkg, device, max_points, dist=None, world=1, rank=0, torch_device=None):
+        self.pkg, self.world, self.rank = pkg, world, rank
+        self.ctx = pkg.Context(device)
+        handle = self.ctx.shard_init(rank, world, max_points)
+        self.handles = exchange_handles(dist, torch_device or f"cuda:{device}", handle, world, rank)
+        self.ctx.shard_attach(self.handles)
+        if dist is not None and world > 1:
+            dist.barrier()                                  # every arena is mapped everywhere before anyone writes
+
+    def close(self, dist=None):
+        if dist is not None and self.world > 1:
+            dist.barrier()                                  # nobody writes into an arena that is about to be freed
+        self.ctx.close()
