@@ -44,6 +44,7 @@ def parse():
     ap.add_argument("--cpu-budget", type=float, default=900.0, help="--impl reference: wall-time budget of the CPU step in seconds")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-fp32", action="store_true", help="skip the fp32-mode sub-record")
+    ap.add_argument("--no-point-sharded", action="store_true", help="N > 1: skip the one-pair-over-all-GPUs sub-record")
     return ap.parse_args()
 
 
@@ -348,6 +349,14 @@ def main():
         except Exception as ex:                       # a sub-record never takes the headline down (all ranks fail alike)
             c5 = dict(error=str(ex))
 
+    # ---- ONE pair over all N GPUs (point-sharded): rank 0's frame pair refined by all ranks together
+    ps = None
+    if world > 1 and not args.no_point_sharded:
+        try:
+            ps = run_point_sharded(pkg, args, rank, world, local, dist, max(2, args.steps // 2), lm_iters, w)
+        except Exception as ex:
+            ps = dict(error=str(ex))
+
     # ---- max over ranks, aggregate
     if dist is not None:
         import importlib
@@ -380,11 +389,67 @@ def main():
                     gpu_launches=int(launches), clocks=clocks, roofline=roof, cpu_baseline=cpu,
                     triangulated_points_per_s=roof["triangulate"]["points_per_s"], knn_graph_build_ms=prob["graph_build_ms"],
                     cg_iteration_ms=cg_ms, wall_ms_per_step=wall_ms / args.steps, fp32_mode=f32rec, config5=c5)
+        if ps is not None:
+            if "error" not in ps:
+                ps["speedup_vs_one_gpu"] = ps["lm_it_per_s"] / (value / world)      # the same pair, same LM trace, on ONE of these GPUs
+                ps["strong_scaling_efficiency"] = ps["speedup_vs_one_gpu"] / world
+            line["point_sharded"] = ps
         print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
     ctx.close()
     return 0
+
+
+def run_point_sharded(pkg, args, rank, world, local, dist, steps, lm_iters, w):
+    """Strong scaling of ONE frame pair (the workload's pair of seed 0, i.e. rank 0's pair of the headline) over all N GPUs:
+    dsc_shard_* -- every rank uploads the same pair and refines its own range of tiles; halo rows and PCG scalars cross
+    NVLink inside the kernels.  Timed like the headline: device-resident, barrier + synchronize, max over ranks."""
+    import importlib
+    import torch
+    sh = importlib.import_module(pkg.__name__ + ".sharding")
+    sc = make_scene(pkg, args, seed=0)
+    c0 = pkg.Context(local)
+    prob = prepare(pkg, c0, sc, args)
+    c0.close()
+    sp = sh.ShardedPair(pkg, local, len(prob["X1"]), dist, world, rank)
+    ctx = sp.ctx
+    ctx.set_pcg(rtol=args.pcg_rtol, max_iters=args.pcg_max_iters, check_every=64)
+    upload(ctx, prob)
+    ref = None
+    early_ok = None
+    for k in range(2):                                   # warm-up 0: every solve to the tolerance; 1: with the early rejection
+        ctx.reset_state()
+        recs, st = ctx.optimize(w, lm_iters)
+        tr = [(r.chi2_before, r.chi2_after, r.trials, r.accepted) for r in recs]
+        if k == 0:
+            ref = tr
+            if len(args.early_rtol) > 0:
+                ctx.set_early_reject(args.early_rtol, args.early_margin)
+        else:
+            early_ok = (tr == ref)
+            if not early_ok:
+                ctx.set_early_reject((), ())
+    dist.barrier(); torch.cuda.synchronize(); ctx.synchronize()
+    ms, its, pcg = 0.0, 0, 0
+    for _ in range(steps):
+        ctx.reset_state()
+        recs, st = ctx.optimize(w, lm_iters)
+        ms += st.device_ms; its += st.iterations; pcg += st.total_pcg_iters
+    dist.barrier(); torch.cuda.synchronize()
+    info = ctx.shard_info()
+    (ms_max,), (halo, rows) = sh.fold(dist, f"cuda:{local}", [ms], [info["halo_rows"], info["row_end"] - info["row_begin"]])
+    finals = [None] * world
+    dist.all_gather_object(finals, (st.final_chi2, [r.trials for r in recs]))
+    sp.close(dist)
+    return dict(workload=sc["name"] + ", ONE pair over all GPUs", n_gpus=world, steps=steps, lm_iters_per_step=lm_iters, scaling="strong",
+                lm_it_per_s=its / (ms_max * 1e-3), ms_per_step=ms_max / steps, pcg_iters_per_lm_iter=pcg / max(1, its),
+                halo_rows_all_ranks=int(halo), rows_all_ranks=int(rows),
+                nvlink_bytes_per_pcg_iteration=int(halo) * 48 + world * world * 80,
+                nvlink_bytes_per_trial=int(halo) * 64 + world * world * (8 + 24),
+                exchange="halo rows pushed by the producing kernel into peer-mapped memory; scalars + 8 global rows by its last block; no collective call",
+                all_ranks_same_bits=all(f == finals[0] for f in finals), early_reject_trace_identical=early_ok,
+                final_chi2=st.final_chi2)
 
 
 def batch_bytes(prob_sizes, recs, stats):

@@ -802,12 +802,16 @@ cg_spmv_kernel(int n, const double* __restrict__ P, const T* __restrict__ Je, co
     if (kShard) {
         __shared__ double tot[9];
         if (!shard_last_block(S, SF_S)) return;
-        for (int e = warp; e < 9; e += wpb) {              // fixed-order totals of dpart[grid] and bpart[grid][8]
-            double v = 0.0;
-            for (int i = lane; i < (int)gridDim.x; i += 32) v += e == 0 ? __ldcg(dpart + i) : __ldcg(bpart + 8 * (size_t)i + (e - 1));
-            v = warp_sum(v);
-            if (lane == 0) tot[e] = v;
+        double t9[9];                                      // fixed-order totals of dpart[grid] and bpart[grid][8], all threads loading
+#pragma unroll
+        for (int e = 0; e < 9; ++e) t9[e] = 0.0;
+        for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x) {
+            t9[0] += __ldcg(dpart + i);
+#pragma unroll
+            for (int e = 1; e < 9; ++e) t9[e] += __ldcg(bpart + 8 * (size_t)i + (e - 1));
         }
+        block_reduce<9>(t9, sm);
+        if (threadIdx.x == 0) for (int e = 0; e < 9; ++e) tot[e] = t9[e];
         __syncthreads();
         shard_send(S, SF_S, tot, 9);
     }

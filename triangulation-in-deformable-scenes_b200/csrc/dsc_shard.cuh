@@ -75,17 +75,18 @@ __device__ __forceinline__ unsigned long long shard_sent(const ShardDev& S, int 
 
 // Last-block election of a producer kernel: every block calls this after its global writes (block partials, remote
 // stores); exactly one block -- the last to arrive -- gets true, with all other blocks' writes visible to it.
-__device__ __forceinline__ bool shard_last_block(const ShardDev& S, int cls) {
+// pushed: some thread of this block has stored into a PEER's memory (halo rows) -- its stores get a system-scope fence
+// before the ticket; a block that only wrote local memory (its partials) needs the cheaper device-scope one.
+__device__ __forceinline__ bool shard_last_block(const ShardDev& S, int cls, bool pushed = false) {
     __shared__ int last;
-    __threadfence_system();
-    __syncthreads();
+    const int any = __syncthreads_or(pushed ? 1 : 0);  // (also orders the block's writes before thread 0's fence: cumulativity)
     if (threadIdx.x == 0) {
+        if (any) __threadfence_system(); else __threadfence();
         const unsigned int t = atomicAdd(S.ticket + cls, 1u);
         last = (t == gridDim.x - 1) ? 1 : 0;
-        if (last) S.ticket[cls] = 0;                              // ready for the next launch
+        if (last) { S.ticket[cls] = 0; __threadfence(); }         // ready for the next launch; acquire side of the election
     }
     __syncthreads();
-    if (last) __threadfence_system();
     return last != 0;
 }
 
@@ -96,7 +97,9 @@ __device__ __forceinline__ void shard_send(const ShardDev& S, int cls, const dou
         const int dst = k / count, e = k % count;
         shard_slot(S, dst, cls, seq, S.rank)[e] = vals[e];
     }
-    __threadfence_system();
+    // ONE system-scope release for the whole message: the barrier orders the block's stores (and, through the election,
+    // every other block's) before the release stores of the flags -- a system-scope fence costs ~10 us on this machine,
+    // and this block is the serial tail of the launch
     __syncthreads();
     if ((int)threadIdx.x < S.world) shard_st_flag(S.flags[threadIdx.x] + (size_t)cls * S.world + S.rank, seq);
     if (threadIdx.x == 0) *reinterpret_cast<volatile unsigned long long*>(S.sent + cls) = seq;

@@ -15,16 +15,17 @@ DSC_D void shard_push6(const ShardDev& S, double* const* bufs, unsigned mask, in
 // the rank's total of count per-block partials part[grid][count] (fixed order) -> every rank's mailbox; called by all
 // blocks after their partial has been written, the last block to arrive does the work
 template <int kCount>
-DSC_D void shard_finish(const ShardDev& S, int cls, const double* part) {
+DSC_D void shard_finish(const ShardDev& S, int cls, const double* part, double* smem /* [kCount][kThreads / 32] */, bool pushed) {
     __shared__ double tot[kCount];
-    if (!shard_last_block(S, cls)) return;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int e = warp; e < kCount; e += (int)(blockDim.x >> 5)) {
-        double v = 0.0;
-        for (int i = lane; i < (int)gridDim.x; i += 32) v += __ldcg(part + (size_t)i * kCount + e);
-        v = warp_sum(v);
-        if (lane == 0) tot[e] = v;
-    }
+    if (!shard_last_block(S, cls, pushed)) return;
+    double t[kCount];
+#pragma unroll
+    for (int e = 0; e < kCount; ++e) t[e] = 0.0;
+    for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x)           // (every thread loads: a handful of L2 round trips in all)
+#pragma unroll
+        for (int e = 0; e < kCount; ++e) t[e] += __ldcg(part + (size_t)i * kCount + e);
+    block_reduce<kCount>(t, smem);
+    if (threadIdx.x == 0) for (int e = 0; e < kCount; ++e) tot[e] = t[e];
     __syncthreads();
     shard_send(S, cls, tot, kCount);
 }
@@ -40,6 +41,7 @@ shard_cg_init_kernel(const __grid_constant__ ShardDev S, int n, const double* __
     double* const* zpeer = S.zbuf[zpar];
     const int r0 = S.row_begin[S.rank], r1 = S.row_begin[S.rank + 1];
     double g[1] = {0.0};
+    bool pushed = false;
     for (int i = r0 + blockIdx.x * blockDim.x + threadIdx.x; i < r1; i += gridDim.x * blockDim.x) {
         double r[6], z[6], M[21];
         D3 a, c;
@@ -56,7 +58,9 @@ shard_cg_init_kernel(const __grid_constant__ ShardDev S, int n, const double* __
         const D3 z1 = d3(z[0], z[1], z[2]), z2 = d3(z[3], z[4], z[5]);
         store6(v.r, i, a, c);
         store6(zout, i, z1, z2);
-        shard_push6(S, zpeer, S.exportmask[i], i, z1, z2);
+        const unsigned em = S.exportmask[i];
+        pushed |= em != 0;
+        shard_push6(S, zpeer, em, i, z1, z2);
 #pragma unroll
         for (int k = 0; k < 6; ++k) g[0] += r[k] * z[k];
     }
@@ -74,12 +78,12 @@ shard_cg_init_kernel(const __grid_constant__ ShardDev S, int n, const double* __
     }
     block_reduce<1>(g, sm);
     if (threadIdx.x == 0) gpart[blockIdx.x] = g[0];
-    shard_finish<1>(S, SF_Z, gpart);
+    shard_finish<1>(S, SF_Z, gpart, sm, pushed);
 }
 
 // One CG step over the rank's rows.  z is double-buffered by iteration parity: read from zbuf[zpar], written (own rows
 // locally, halo rows into the peers) to zbuf[zpar ^ 1].
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 3)
 shard_cg_update_kernel(const __grid_constant__ ShardDev S, int n, int par, int first, const double* __restrict__ Minv,
                        const double* __restrict__ Ginv, const LinGlobal* __restrict__ lin, CgVecs v, int zpar,
                        double* __restrict__ gpart_out, CgControl* __restrict__ ctl) {
@@ -109,6 +113,7 @@ shard_cg_update_kernel(const __grid_constant__ ShardDev S, int n, int par, int f
     double* const* zpeer = S.zbuf[zpar ^ 1];
     const int r0 = S.row_begin[S.rank], r1 = S.row_begin[S.rank + 1];
     double g[1] = {0.0};
+    bool pushed = false;
     for (int i = r0 + blockIdx.x * blockDim.x + threadIdx.x; i < r1; i += gridDim.x * blockDim.x) {
         D3 z1, z2, w1, w2, p1, p2, s1, s2, x1, x2, r1v, r2v;
         load6(zin, i, z1, z2); load6(v.w, i, w1, w2); load6(v.r, i, r1v, r2v);
@@ -127,7 +132,9 @@ shard_cg_update_kernel(const __grid_constant__ ShardDev S, int n, int par, int f
         const D3 zn1 = d3(zn[0], zn[1], zn[2]), zn2 = d3(zn[3], zn[4], zn[5]);
         store6(v.p, i, p1, p2); store6(v.s, i, s1, s2); store6(v.x, i, x1, x2); store6(v.r, i, r1v, r2v);
         store6(zout, i, zn1, zn2);
-        shard_push6(S, zpeer, S.exportmask[i], i, zn1, zn2);
+        const unsigned em = S.exportmask[i];
+        pushed |= em != 0;
+        shard_push6(S, zpeer, em, i, zn1, zn2);
 #pragma unroll
         for (int k = 0; k < 6; ++k) g[0] += r[k] * zn[k];
     }
@@ -163,7 +170,7 @@ shard_cg_update_kernel(const __grid_constant__ ShardDev S, int n, int par, int f
     }
     block_reduce<1>(g, sm);
     if (threadIdx.x == 0) gpart_out[blockIdx.x] = g[0];
-    shard_finish<1>(S, SF_Z, gpart_out);
+    shard_finish<1>(S, SF_Z, gpart_out, sm, pushed);
 }
 
 // trial state of the rank's rows (+ halo rows into the peers' trial buffers Pbuf[pidx]); part[grid]: partial of
