@@ -25,6 +25,10 @@ import numpy as np
 rows = np.array([[100.0 + p, 2.0 * p] for p in mine])
 table = sh.gather_by_problem(dist, "cpu", 37, world, rank, rows)
 ok = bool(np.array_equal(table[:, 0], 100.0 + np.arange(37)) and np.array_equal(table[:, 1], 2.0 * np.arange(37)))
+# the one use of torch.distributed by the point-sharded pair: the all-gather of the ranks' 64-byte arena handles
+handle = (np.arange(64) * (rank + 3) % 251).astype(np.uint8)
+table = sh.exchange_handles(dist, "cpu", handle, world, rank)
+ok = ok and table.shape == (world, 64) and all(np.array_equal(table[r], (np.arange(64) * (r + 3) % 251).astype(np.uint8)) for r in range(world))
 oks = [None] * world
 dist.all_gather_object(oks, ok)
 if rank == 0:
@@ -73,3 +77,23 @@ def test_shard_edge_cases(pkg):
     assert np.array_equal(t, np.arange(10.0).reshape(5, 2))
     with pytest.raises(ValueError):
         sh.gather_by_problem(None, "cpu", 5, 2, 0, np.zeros((2, 1)))                       # rank 0 of 2 owns 3 of 5
+
+
+def test_point_shard_partition_is_tile_aligned_balanced_and_complete(pkg):
+    """dsc_shard_partition (pure host function of the C ABI): the row partition of a point-sharded pair"""
+    import numpy as np
+    import pytest
+    rng = np.random.default_rng(0)
+    for nslices, world in ((1, 1), (5, 2), (16, 4), (1000, 8), (31250, 8), (31250, 3)):
+        width = rng.integers(6, 14, nslices)
+        sp = np.concatenate([[0], np.cumsum(width)]).astype(np.int32)
+        rb = pkg.shard_partition(sp, world)
+        assert rb[0] == 0 and rb[-1] == nslices * 32 and np.all(np.diff(rb) >= 0)
+        assert np.all((rb % 512 == 0) | (rb == nslices * 32))                  # tile boundaries (or the end: a rank may be empty)
+        if nslices >= 64 * world:                                              # enough tiles: the ranks' work differs by less than 2 tiles
+            cost = lambda a, b: (sp[min(nslices, b // 32)] - sp[a // 32]) + 3.37 * (min(nslices, b // 32) - a // 32)
+            work = [cost(rb[r], rb[r + 1]) for r in range(world)]
+            tile = 16 * (width.mean() + 3.37)
+            assert max(work) - min(work) <= 2.5 * tile
+    with pytest.raises(pkg.DscError):
+        pkg.shard_partition(np.zeros(3, np.int32), 9)                          # more ranks than DSC_SHARD_MAX_RANKS

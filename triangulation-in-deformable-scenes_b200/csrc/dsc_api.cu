@@ -658,7 +658,7 @@ extern "C" int dsc_shard_partition(const int32_t* sliceptr, int nslices, int wor
     for (int r = 1; r < world; ++r) {
         const double target = total * r / world;
         while (t < ntiles && cost_to(t + 1) - 0.5 * (cost_to(t + 1) - cost_to(t)) <= target) ++t;
-        row_begin[r] = t * kSortGroup;
+        row_begin[r] = std::min(t * kSortGroup, nslices * 32);
     }
     row_begin[world] = nslices * 32;                           // (clamped to n by the caller)
     for (int r = 1; r <= world; ++r) row_begin[r] = std::max(row_begin[r], row_begin[r - 1]);
