@@ -249,6 +249,21 @@ int dsc_profile_triangulate(dsc_ctx* ctx, const dsc_tri_params* prm, int warm, i
  * reports the number of directed edges; dsc_knn_download copies rowptr[n+1] / col[E] out (feed them to dsc_set_graph). */
 int dsc_knn_build(dsc_ctx* ctx, int n, const float* X, int k, long long* n_edges);
 int dsc_knn_download(dsc_ctx* ctx, int32_t* rowptr, int32_t* col);
+/* The reference's own neighbour graph on the GPU (Modules/Utils/Geometry.cc:272-368: ComputeDelaunayTriangulation3D -- the 2-D
+ * Delaunay triangulation of the points' world (x, y), Qhull "d Qbb Qt" --, TriangleMesh adjacency, ComputeEdgeWeightsCot, mesh
+ * area and triangle count, g2oBundleAdjustment.cc:657-662,942-946).  Every point clips its own Voronoi cell from the points
+ * around it (uniform grid, ring by ring, certified by the security radius); the ~sqrt(n) cells that reach outside the point
+ * cloud are finished in a second pass (n_second_pass reports how many); the thin triangles along the convex hull are kept, as
+ * Qhull keeps them (the host triangulator host/Mesh.h loses the thinnest to its finite super triangle).  Rows ascending; w = mean over the adjacent
+ * triangles of the cotangent of the opposite angle, clamped to >= min_weight; area in 3-D.  DSC_ERR_GRAPH on inputs this
+ * construction does not handle (a cell with more than 32 vertices: e.g. many co-circular points).
+ *   dsc_delaunay_build / dsc_delaunay_download   stand-alone, X[n][3] host floats -> CSR (feed it to dsc_set_graph)
+ *   dsc_set_graph_delaunay                       the graph of the UPLOADED problem (its KF1 points), built and installed on
+ *                                                the device: replaces host mesh + dsc_set_graph; reorder as for dsc_set_graph */
+int dsc_delaunay_build(dsc_ctx* ctx, int n, const float* X, double min_weight, long long* n_edges, long long* n_triangles, double* area,
+                       long long* n_second_pass);
+int dsc_delaunay_download(dsc_ctx* ctx, int32_t* rowptr, int32_t* col, double* w);
+int dsc_set_graph_delaunay(dsc_ctx* ctx, double min_weight, int reorder, double* area, long long* n_triangles, long long* n_edges);
 /* problem size as seen by the library: n correspondences, E directed edges */
 int dsc_problem_size(const dsc_ctx* ctx, long long* n, long long* n_edges);
 

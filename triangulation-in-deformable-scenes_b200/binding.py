@@ -28,6 +28,7 @@ EXPORTS = [
     "dsc_batch_reset_state", "dsc_batch_optimize", "dsc_batch_download", "dsc_batch_size",
     "dsc_shard_init", "dsc_shard_attach", "dsc_shard_partition", "dsc_shard_info",
     "dsc_debug_linearize", "dsc_debug_matvec", "dsc_profile_kernels", "dsc_profile_triangulate", "dsc_problem_size", "dsc_knn_build", "dsc_knn_download",
+    "dsc_delaunay_build", "dsc_delaunay_download", "dsc_set_graph_delaunay",
 ]
 KERNEL_NAMES = ["cg_spmv", "cg_update", "linearize", "cost", "precond", "apply_update", "rotations"]
 
@@ -415,6 +416,28 @@ class Context:
         self._ck(self.lib.dsc_knn_download(self.h, _fp(rowptr), _fp(col)))
         col = col[:E.value]
         return rowptr, col, np.ones(E.value, np.float64)
+
+
+    def delaunay_graph(self, X, min_weight=0.0):
+        """the reference's neighbour graph built on the GPU (dsc_delaunay_build): 2-D Delaunay of (x, y), cot weights
+        -> (rowptr, col, w, area, n_triangles, cells finished in the second pass)"""
+        X = _f32(X, (-1, 3))
+        n = X.shape[0]
+        E, T, U = C.c_longlong(), C.c_longlong(), C.c_longlong()
+        area = C.c_double()
+        self._ck(self.lib.dsc_delaunay_build(self.h, n, _fp(X), C.c_double(min_weight), C.byref(E), C.byref(T), C.byref(area), C.byref(U)))
+        rowptr = np.empty(n + 1, np.int32)
+        col = np.empty(max(E.value, 1), np.int32)
+        w = np.empty(max(E.value, 1), np.float64)
+        self._ck(self.lib.dsc_delaunay_download(self.h, _fp(rowptr), _fp(col), _fp(w)))
+        return rowptr, col[:E.value], w[:E.value], area.value, T.value, U.value
+
+    def set_graph_delaunay(self, min_weight=0.0, reorder=1):
+        """Delaunay graph of the uploaded problem's KF1 points, built and installed on the device -> (area, n_triangles, E)"""
+        area = C.c_double()
+        T, E = C.c_longlong(), C.c_longlong()
+        self._ck(self.lib.dsc_set_graph_delaunay(self.h, C.c_double(min_weight), int(reorder), C.byref(area), C.byref(T), C.byref(E)))
+        return area.value, T.value, E.value
 
 
 def shard_partition(sliceptr, world):

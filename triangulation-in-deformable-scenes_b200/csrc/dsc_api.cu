@@ -10,6 +10,7 @@
 #include "dsc_kernels.cuh"
 #include "dsc_kernels_ell.cuh"
 #include "dsc_knn.cuh"
+#include "dsc_delaunay.cuh"
 #include "dsc_graph.cuh"
 #include "dsc_dense.cuh"
 #include "dsc_small.cuh"
@@ -97,6 +98,10 @@ struct dsc_ctx {
     // pinned, persistent host staging of the graph / observation uploads (grown on demand)
     int* hs_sp = nullptr;
     size_t hc_sp = 0;
+    // ---- Delaunay graph builder (device CSR of the last dsc_delaunay_build / dsc_set_graph_delaunay)
+    int dl_n = 0; long long dl_E = 0, dl_ntri = 0; double dl_area = 0.0;
+    int *dl_rowptr = nullptr, *dl_col = nullptr; double* dl_w = nullptr;
+    long long dl_uncertified = 0;
     // ---- kNN graph builder (device CSR of the last dsc_knn_build)
     int knn_n = 0; long long knn_E = 0;
     int *knn_rowptr = nullptr, *knn_col = nullptr;
@@ -385,6 +390,7 @@ extern "C" void dsc_destroy(dsc_ctx* ctx) {
     for (auto& v : ctx->vecF) dev_free(v);
     dev_free(ctx->JeF); dev_free(ctx->UF); dev_free(ctx->MinvF);
     dev_free(ctx->knn_rowptr); dev_free(ctx->knn_col);
+    dev_free(ctx->dl_rowptr); dev_free(ctx->dl_col); dev_free(ctx->dl_w);
     dev_free(ctx->small); dev_free(ctx->Gcur); dev_free(ctx->Gtrial); dev_free(ctx->lin); dev_free(ctx->ctl);
     dev_free(ctx->errflag); dev_free(ctx->part); dev_free(ctx->gpart[0]); dev_free(ctx->gpart[1]);
     dev_free(ctx->dpart); dev_free(ctx->bpart);
@@ -786,26 +792,7 @@ static int shard_setup_graph(dsc_ctx* ctx, const int* sp, int nslices) {
     return DSC_OK;
 }
 
-extern "C" int dsc_set_graph(dsc_ctx* ctx, int n, const int32_t* rowptr, const int32_t* col, const double* w,
-                             double area, long long n_triangles, int reorder) {
-    if (!ctx || !rowptr || n < 0) return fail(ctx, DSC_ERR_INVALID_ARG, "dsc_set_graph");
-    if (!ctx->have_problem || n != ctx->n) return fail(ctx, DSC_ERR_STATE, "dsc_set_graph: upload a problem of the same size first");
-    const bool validate = !(reorder & 2);
-    reorder &= 1;
-    const bool timing = std::getenv("DSC_TIMING") != nullptr;
-    auto t_last = std::chrono::steady_clock::now();
-    auto lap = [&](const char* what) {
-        if (!timing) return;
-        auto t = std::chrono::steady_clock::now();
-        std::fprintf(stderr, "[dsc_set_graph] %-18s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(t - t_last).count());
-        t_last = t;
-    };
-    if (!(area > 0.0) || n_triangles < 0) return fail(ctx, DSC_ERR_INVALID_ARG, "area must be > 0, n_triangles >= 0");
-    CK(cudaSetDevice(ctx->device));
-    long long E = n > 0 ? rowptr[n] : 0;
-    if (rowptr[0] != 0 || E < 0 || (E > 0 && (!col || !w))) return fail(ctx, DSC_ERR_GRAPH, "rowptr");
-    for (int i = 0; i < n; ++i) if (rowptr[i + 1] < rowptr[i]) return fail(ctx, DSC_ERR_GRAPH, "rowptr not monotone");
-    // ---- raw CSR to the device as it is (h2d: straight from pinned / registered caller memory, else through the bounce buffer)
+static int reserve_graph(dsc_ctx* ctx, int n, long long E) {
     if ((size_t)n + 1 > ctx->g_ncap) {
         size_t N = (size_t)n + 1, NS = ((size_t)n + 31) / 32 + 2;
         CK(dev_alloc(ctx->g_rp0, N)); CK(dev_alloc(ctx->g_inv, N)); CK(dev_alloc(ctx->g_key0, N)); CK(dev_alloc(ctx->g_key1, N));
@@ -813,13 +800,19 @@ extern "C" int dsc_set_graph(dsc_ctx* ctx, int n, const int32_t* rowptr, const i
         ctx->g_ncap = N;
     }
     if ((size_t)E > ctx->g_ecap) { CK(dev_alloc(ctx->g_col0, (size_t)E)); CK(dev_alloc(ctx->g_w0, (size_t)E)); ctx->g_ecap = (size_t)E; }
-    {
-        int rc;
-        if ((rc = h2d(ctx, ctx->g_rp0, rowptr, sizeof(int) * ((size_t)n + 1)))) return rc;
-        if (E > 0 && (rc = h2d(ctx, ctx->g_col0, col, sizeof(int) * (size_t)E))) return rc;
-        if (E > 0 && (rc = h2d(ctx, ctx->g_w0, w, sizeof(double) * (size_t)E))) return rc;
-    }
-    lap("csr staging");
+    return DSC_OK;
+}
+
+// the rest of dsc_set_graph once the raw CSR (caller numbering) is on the device in g_rp0 / g_col0 / g_w0
+static int set_graph_tail(dsc_ctx* ctx, int n, long long E, double area, long long n_triangles, int reorder, bool validate, bool timing) {
+    auto t_last = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) {
+        if (!timing) return;
+        auto t = std::chrono::steady_clock::now();
+        std::fprintf(stderr, "[dsc_set_graph] %-18s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(t - t_last).count());
+        t_last = t;
+    };
+
     // symmetric, in range, no self loops, no duplicates, symmetric weights (the reference's mesh adjacency always is)
     if (validate && n > 0) {
         CK(cudaMemsetAsync(ctx->errflag, 0, sizeof(int), ctx->stream));
@@ -912,6 +905,205 @@ extern "C" int dsc_set_graph(dsc_ctx* ctx, int n, const int32_t* rowptr, const i
     lap("ell + state");
     if (urc == DSC_OK && ctx->sharded) urc = shard_setup_graph(ctx, sp, nslices);
     return urc;
+}
+
+
+extern "C" int dsc_set_graph(dsc_ctx* ctx, int n, const int32_t* rowptr, const int32_t* col, const double* w,
+                             double area, long long n_triangles, int reorder) {
+    if (!ctx || !rowptr || n < 0) return fail(ctx, DSC_ERR_INVALID_ARG, "dsc_set_graph");
+    if (!ctx->have_problem || n != ctx->n) return fail(ctx, DSC_ERR_STATE, "dsc_set_graph: upload a problem of the same size first");
+    const bool validate = !(reorder & 2);
+    reorder &= 1;
+    const bool timing = std::getenv("DSC_TIMING") != nullptr;
+    auto t_last = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) {
+        if (!timing) return;
+        auto t = std::chrono::steady_clock::now();
+        std::fprintf(stderr, "[dsc_set_graph] %-18s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(t - t_last).count());
+        t_last = t;
+    };
+    if (!(area > 0.0) || n_triangles < 0) return fail(ctx, DSC_ERR_INVALID_ARG, "area must be > 0, n_triangles >= 0");
+    CK(cudaSetDevice(ctx->device));
+    long long E = n > 0 ? rowptr[n] : 0;
+    if (rowptr[0] != 0 || E < 0 || (E > 0 && (!col || !w))) return fail(ctx, DSC_ERR_GRAPH, "rowptr");
+    for (int i = 0; i < n; ++i) if (rowptr[i + 1] < rowptr[i]) return fail(ctx, DSC_ERR_GRAPH, "rowptr not monotone");
+    // ---- raw CSR to the device as it is (h2d: straight from pinned / registered caller memory, else through the bounce buffer)
+    { int rrc = reserve_graph(ctx, n, E); if (rrc) return rrc; }
+    {
+        int rc;
+        if ((rc = h2d(ctx, ctx->g_rp0, rowptr, sizeof(int) * ((size_t)n + 1)))) return rc;
+        if (E > 0 && (rc = h2d(ctx, ctx->g_col0, col, sizeof(int) * (size_t)E))) return rc;
+        if (E > 0 && (rc = h2d(ctx, ctx->g_w0, w, sizeof(double) * (size_t)E))) return rc;
+    }
+    lap("csr staging");
+    return set_graph_tail(ctx, n, E, area, n_triangles, reorder, validate, timing);
+}
+
+// ------------------------------------------------------------------ Delaunay graph on the GPU (dsc_delaunay.cuh)
+// dX: device float [n][3]; leaves the CSR (caller numbering, rows ascending) in ctx->dl_*.
+static int delaunay_build_device(dsc_ctx* ctx, int n, const float* dX, double min_weight) {
+    dev_free(ctx->dl_rowptr); dev_free(ctx->dl_col); dev_free(ctx->dl_w);
+    ctx->dl_n = n; ctx->dl_E = 0; ctx->dl_ntri = 0; ctx->dl_area = 0.0; ctx->dl_uncertified = 0;
+    CK(dev_alloc(ctx->dl_rowptr, (size_t)n + 2));
+    CK(cudaMemsetAsync(ctx->dl_rowptr, 0, sizeof(int) * ((size_t)n + 2), ctx->stream));
+    if (n < 3) { CK(cudaStreamSynchronize(ctx->stream)); return DSC_OK; }
+    // bounding box of (x, y) (two-stage device reduction, folded on the host) -> grid and the three ghost vertices
+    const int nbv = grid_threads(ctx, n);
+    bbox_kernel<<<nbv, kThreads, 0, ctx->stream>>>(n, dX, ctx->d_box + 4);
+    ctx->launches++;
+    float* hb = reinterpret_cast<float*>(ctx->h_pinned);
+    CK(cudaMemcpyAsync(hb, ctx->d_box + 4, sizeof(float) * 4 * nbv, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    double x0 = 1e300, x1 = -1e300, y0 = 1e300, y1 = -1e300;
+    for (int b = 0; b < nbv; ++b) {
+        x0 = std::min(x0, (double)hb[4 * b]); x1 = std::max(x1, (double)hb[4 * b + 1]);
+        y0 = std::min(y0, (double)hb[4 * b + 2]); y1 = std::max(y1, (double)hb[4 * b + 3]);
+    }
+    const double wdt = x1 - x0, hgt = y1 - y0, dm = std::max(wdt, hgt);
+    if (!(dm > 0.0) || !std::isfinite(dm)) return fail(ctx, DSC_ERR_INVALID_ARG, "Delaunay: the points have no extent in (x, y) or are not finite");
+    KnnGrid g{x0, y0, 1.0, 1, 1};
+    {
+        double cell = std::sqrt(std::max(wdt, 1e-300) * std::max(hgt, 1e-300) / std::max(1.0, n / 2.0));
+        cell = std::max(cell, std::max(wdt, hgt) / 4096.0);
+        g.inv_cell = 1.0 / cell;
+        g.nx = std::max(1, (int)std::ceil(wdt / cell) + 1);
+        g.ny = std::max(1, (int)std::ceil(hgt / cell) + 1);
+    }
+    const int ncells = g.nx * g.ny, m = std::max(ncells, n) + 1;
+    int *cell = nullptr, *cnt = nullptr, *start = nullptr, *cursor = nullptr, *order = nullptr, *sums = nullptr, *star = nullptr, *deg = nullptr,
+        *flag = nullptr, *isu = nullptr, *pos = nullptr, *list = nullptr, *slot = nullptr, *extra = nullptr, *nextra = nullptr, *rowdeg = nullptr;
+    auto release = [&]() {
+        for (int** q : {&cell, &cnt, &start, &cursor, &order, &sums, &star, &deg, &flag, &isu, &pos, &list, &slot, &extra, &nextra, &rowdeg}) dev_free(*q);
+    };
+    auto scan = [&](int count, const int* in, int* out) {      // exclusive scan of count ints
+        int nb = (count + kScanBlock - 1) / kScanBlock;
+        scan_block_kernel<<<nb, kScanBlock, 0, ctx->stream>>>(count, in, out, sums);
+        scan_sums_kernel<<<1, kScanBlock, 0, ctx->stream>>>(nb, sums);
+        scan_add_kernel<<<nb, kScanBlock, 0, ctx->stream>>>(count, out, sums);
+        ctx->launches += 3;
+    };
+    cudaError_t e = cudaSuccess;
+    if ((e = dev_alloc(cell, (size_t)n)) || (e = dev_alloc(cnt, (size_t)m)) || (e = dev_alloc(start, (size_t)m)) || (e = dev_alloc(cursor, (size_t)m)) ||
+        (e = dev_alloc(order, (size_t)n)) || (e = dev_alloc(sums, (size_t)(m / kScanBlock + 2))) || (e = dev_alloc(star, (size_t)n * kDlMaxV)) ||
+        (e = dev_alloc(deg, (size_t)n)) || (e = dev_alloc(flag, (size_t)n)) || (e = dev_alloc(isu, (size_t)n + 1)) || (e = dev_alloc(pos, (size_t)n + 1)) ||
+        (e = dev_alloc(slot, (size_t)n)) || (e = dev_alloc(nextra, (size_t)n)) || (e = dev_alloc(rowdeg, (size_t)n + 1))) {
+        release();
+        return fail(ctx, DSC_ERR_ALLOC, cudaGetErrorString(e));
+    }
+    auto bail = [&](int code, const char* what) { release(); return fail(ctx, code, what); };
+    CK(cudaMemsetAsync(cnt, 0, sizeof(int) * m, ctx->stream));
+    CK(cudaMemsetAsync(cursor, 0, sizeof(int) * m, ctx->stream));
+    knn_cell_kernel<<<nbv, kThreads, 0, ctx->stream>>>(n, dX, g, cell, cnt);
+    scan(ncells, cnt, start);
+    knn_scatter_kernel<<<nbv, kThreads, 0, ctx->stream>>>(n, cell, start, cursor, order);
+    const double box = std::ldexp(dm, 40);                     // "the whole plane": 2^40 x the extent of the point cloud
+    // ---- pass one: every cell from the points around it
+    delaunay_cells_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(n, dX, g, start, order, ncells, box, nullptr, 0, nullptr, nullptr, star, deg, flag);
+    // ---- the uncertified points, in index order
+    delaunay_flag_kernel<<<nbv, kThreads, 0, ctx->stream>>>(n, flag, isu);
+    CK(cudaMemsetAsync(isu + n, 0, sizeof(int), ctx->stream));
+    scan(n + 1, isu, pos);
+    ctx->launches += 4;
+    int nu = 0;
+    CK(cudaMemcpyAsync(&nu, pos + n, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (cudaGetLastError() != cudaSuccess) return bail(DSC_ERR_CUDA, "Delaunay pass one");
+    ctx->dl_uncertified = nu;
+    if (nu > 0) {
+        // ---- pass two: finish them from the certified points that list them and from each other
+        if ((e = dev_alloc(list, (size_t)nu)) || (e = dev_alloc(extra, (size_t)nu * kDlMaxExtra))) { release(); return fail(ctx, DSC_ERR_ALLOC, cudaGetErrorString(e)); }
+        CK(cudaMemsetAsync(nextra, 0, sizeof(int) * n, ctx->stream));
+        delaunay_compact_kernel<<<nbv, kThreads, 0, ctx->stream>>>(n, isu, pos, list, slot);
+        delaunay_extra_kernel<<<nbv, kThreads, 0, ctx->stream>>>(n, star, deg, flag, slot, extra, nextra);
+        delaunay_sort_extra_kernel<<<grid_threads(ctx, nu), kThreads, 0, ctx->stream>>>(nu, list, extra, nextra);
+        delaunay_cells_kernel<<<(nu + 127) / 128, 128, 0, ctx->stream>>>(n, dX, g, start, order, ncells, box, list, nu, extra, nextra, star, deg, flag);
+        delaunay_flag_kernel<<<nbv, kThreads, 0, ctx->stream>>>(n, flag, isu);
+        scan(n + 1, isu, pos);
+        ctx->launches += 5;
+        int bad = 0;
+        CK(cudaMemcpyAsync(&bad, pos + n, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        if (bad > 0) return bail(DSC_ERR_GRAPH, "Delaunay: a cell has more than 32 vertices or more than 96 certified neighbours (degenerate input: use the host mesh)");
+    }
+    // ---- rows: degrees + triangle count + area, scan, fill (ascending, cot weights)
+    delaunay_edges_kernel<<<nbv, kThreads, 0, ctx->stream>>>(n, dX, star, deg, min_weight, 0, nullptr, rowdeg, nullptr, nullptr, ctx->part);
+    CK(cudaMemsetAsync(rowdeg + n, 0, sizeof(int), ctx->stream));
+    scan(n + 1, rowdeg, ctx->dl_rowptr);
+    ctx->launches++;
+    int E = 0;
+    CK(cudaMemcpyAsync(&E, ctx->dl_rowptr + n, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->h_pinned, ctx->part, sizeof(double) * 2 * nbv, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->dl_ntri = (long long)host_sum(ctx->h_pinned, nbv, 2, 0);
+    ctx->dl_area = host_sum(ctx->h_pinned, nbv, 2, 1);
+    if ((e = dev_alloc(ctx->dl_col, (size_t)std::max(E, 1))) || (e = dev_alloc(ctx->dl_w, (size_t)std::max(E, 1)))) { release(); return fail(ctx, DSC_ERR_ALLOC, cudaGetErrorString(e)); }
+    delaunay_edges_kernel<<<nbv, kThreads, 0, ctx->stream>>>(n, dX, star, deg, min_weight, 1, ctx->dl_rowptr, nullptr, ctx->dl_col, ctx->dl_w, nullptr);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(ctx->stream));
+    release();
+    ctx->dl_E = E;
+    return DSC_OK;
+}
+
+extern "C" int dsc_delaunay_build(dsc_ctx* ctx, int n, const float* X, double min_weight, long long* n_edges, long long* n_triangles, double* area,
+                                  long long* n_second_pass) {
+    if (!ctx || n < 0 || (n > 0 && !X)) return fail(ctx, DSC_ERR_INVALID_ARG, "dsc_delaunay_build");
+    CK(cudaSetDevice(ctx->device));
+    float* dX = nullptr;
+    if (n > 0) {
+        CK(cudaMalloc(reinterpret_cast<void**>(&dX), sizeof(float) * 3 * (size_t)n));
+        int rc = h2d(ctx, dX, X, sizeof(float) * 3 * (size_t)n);
+        if (rc) { cudaFree(dX); return rc; }
+    }
+    int rc = delaunay_build_device(ctx, n, dX, min_weight);
+    if (dX) cudaFree(dX);
+    if (rc) return rc;
+    if (n_edges) *n_edges = ctx->dl_E;
+    if (n_triangles) *n_triangles = ctx->dl_ntri;
+    if (area) *area = ctx->dl_area;
+    if (n_second_pass) *n_second_pass = ctx->dl_uncertified;
+    return DSC_OK;
+}
+
+extern "C" int dsc_delaunay_download(dsc_ctx* ctx, int32_t* rowptr, int32_t* col, double* w) {
+    if (!ctx || !rowptr) return DSC_ERR_INVALID_ARG;
+    if (!ctx->dl_rowptr) return fail(ctx, DSC_ERR_STATE, "dsc_delaunay_download before dsc_delaunay_build");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpyAsync(rowptr, ctx->dl_rowptr, sizeof(int) * ((size_t)ctx->dl_n + 1), cudaMemcpyDeviceToHost, ctx->stream));
+    if (col && ctx->dl_E) CK(cudaMemcpyAsync(col, ctx->dl_col, sizeof(int) * (size_t)ctx->dl_E, cudaMemcpyDeviceToHost, ctx->stream));
+    if (w && ctx->dl_E) CK(cudaMemcpyAsync(w, ctx->dl_w, sizeof(double) * (size_t)ctx->dl_E, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return DSC_OK;
+}
+
+// The reference's graph for the uploaded problem, built where the problem lies: Delaunay of the KF1 map points' world (x, y)
+// (extractPositions + ComputeDelaunayTriangulation3D), cot weights, area, triangle count -> the same set-up as dsc_set_graph.
+extern "C" int dsc_set_graph_delaunay(dsc_ctx* ctx, double min_weight, int reorder, double* area, long long* n_triangles, long long* n_edges) {
+    if (!ctx) return DSC_ERR_INVALID_ARG;
+    if (!ctx->have_problem) return fail(ctx, DSC_ERR_STATE, "dsc_set_graph_delaunay: upload a problem first");
+    CK(cudaSetDevice(ctx->device));
+    const bool timing = std::getenv("DSC_TIMING") != nullptr;
+    auto t0 = std::chrono::steady_clock::now();
+    const int n = ctx->n;
+    int rc = delaunay_build_device(ctx, n, ctx->X1f, min_weight);
+    if (rc) return rc;
+    if (!(ctx->dl_area > 0.0)) return fail(ctx, DSC_ERR_GRAPH, "Delaunay: the mesh has no area (fewer than 3 points, or all collinear)");
+    if ((rc = reserve_graph(ctx, n, ctx->dl_E))) return rc;
+    CK(cudaMemcpyAsync(ctx->g_rp0, ctx->dl_rowptr, sizeof(int) * ((size_t)n + 1), cudaMemcpyDeviceToDevice, ctx->stream));
+    if (ctx->dl_E) {
+        CK(cudaMemcpyAsync(ctx->g_col0, ctx->dl_col, sizeof(int) * (size_t)ctx->dl_E, cudaMemcpyDeviceToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->g_w0, ctx->dl_w, sizeof(double) * (size_t)ctx->dl_E, cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    if (timing) {
+        CK(cudaStreamSynchronize(ctx->stream));
+        std::fprintf(stderr, "[dsc_set_graph_delaunay] mesh %8.2f ms (%lld second-pass cells)\n",
+                     std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(), ctx->dl_uncertified);
+    }
+    if (area) *area = ctx->dl_area;
+    if (n_triangles) *n_triangles = ctx->dl_ntri;
+    if (n_edges) *n_edges = ctx->dl_E;
+    return set_graph_tail(ctx, n, ctx->dl_E, ctx->dl_area, ctx->dl_ntri, reorder & 1, !(reorder & 2), timing);
 }
 
 extern "C" int dsc_compute_rotations(dsc_ctx* ctx) {

@@ -382,18 +382,37 @@ int initializeMapFromMatches(Map& map, KeyFrame_ refKF, KeyFrame_ currKF, const 
     if (par.empty()) return 0;
     std::sort(par.begin(), par.end());                                        // MonocularMapInitializer.cc:375-386
     float cosp = par[std::min<size_t>(50, par.size() - 1)];
-    if (parallaxDegrees) *parallaxDegrees = std::acos(cosp) * (float)(180.0 / M_PI);
+    if (cosp < 0.f || cosp > 1.f) return 0;                                    // :379-382 "Parallax must be between 0 and 1"
+    const float degrees50 = std::acos(cosp) * (float)(180.0 / M_PI);
+    if (parallaxDegrees) *parallaxDegrees = degrees50;
+    // the initialiser's acceptance test (:389; Mapping.cc:60 passes Triangulation.minCos as fMinParallax): a pair the
+    // reference refuses to initialise from creates nothing here either
+    if (!(par.size() >= 25 && degrees50 > settings.getMinCos())) return 0;
     Sophus::SE3f T1w = refKF->getPose(), T2w = currKF->getPose();
+    auto usable = [&](size_t i, cv::Point2f& x1, cv::Point2f& x2) {
+        if (!r.valid[i]) return false;
+        x1 = refKF->getKeyPoint(i).pt; x2 = currKF->getKeyPoint((size_t)matches[i]).pt;
+        double d1 = refKF->getDepthMeasure(x1.x, x1.y), d2 = currKF->getDepthMeasure(x2.x, x2.y);
+        if (d1 <= 0.0 || d2 <= 0.0) return false;                             // Mapping.cc:194-200
+        if (x1.x <= 0.1 || x1.x >= 1500 || x1.y <= 0.1 || x1.y >= 1500) return false;
+        if (x2.x <= 0.1 || x2.x >= 1500 || x2.y <= 0.1 || x2.y >= 1500) return false;
+        return true;
+    };
+    // The initial depth scales are means over the points whose parallax exceeds the setting (:211-254); with no such point
+    // the reference divides by zero and refines with a NaN scale.  Refused here: nothing is created.
+    {
+        size_t n_scale = 0;
+        cv::Point2f x1, x2;
+        for (size_t i = 0; i < r.valid.size(); ++i)
+            if (usable(i, x1, x2) && std::acos(r.cosParallax[i]) * (float)(180.0 / M_PI) > settings.getMinCos()) ++n_scale;
+        if (n_scale == 0) return 0;
+    }
     int created = 0;
     double scale1 = 0, scale2 = 0;
     float n_points = 0;
     for (size_t i = 0; i < r.valid.size(); ++i) {
-        if (!r.valid[i]) continue;
-        cv::Point2f x1 = refKF->getKeyPoint(i).pt, x2 = currKF->getKeyPoint((size_t)matches[i]).pt;
-        double d1 = refKF->getDepthMeasure(x1.x, x1.y), d2 = currKF->getDepthMeasure(x2.x, x2.y);
-        if (d1 <= 0.0 || d2 <= 0.0) continue;                                 // Mapping.cc:194-200
-        if (x1.x <= 0.1 || x1.x >= 1500 || x1.y <= 0.1 || x1.y >= 1500) continue;
-        if (x2.x <= 0.1 || x2.x >= 1500 || x2.y <= 0.1 || x2.y >= 1500) continue;
+        cv::Point2f x1, x2;
+        if (!usable(i, x1, x2)) continue;
         MapPoint_ a(new MapPoint(r.x3D_1[i])), b(new MapPoint(r.x3D_2[i]));
         map.insertMapPoint(a); map.insertMapPoint(b);
         map.addObservation(refKF->getId(), a->getId(), i);                    // :205-209
