@@ -5,6 +5,7 @@
 
 #include <algorithm>
 #include <array>
+#include <chrono>
 #include <cmath>
 #include <cstdlib>
 #include <fstream>
@@ -22,6 +23,8 @@ namespace {
 
 dsc_ctx* g_ctx = nullptr;
 std::vector<dsc_host::LmRecord> g_trace;
+dsc_host::PhaseTimes g_times;
+double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 dsc_pcg_params g_pcg{1e-10, 6000, 64};
 
 dsc_ctx* ctx() {
@@ -148,6 +151,9 @@ bool resident_pair(Map* pMap, KeyFrame_ pKF1, ID kf1ID, KeyFrame_ pKF2, ID kf2ID
     return true;
 }
 
+bool host_mesh_forced() { return std::getenv("DSC_HOST_MESH") != nullptr; }
+bool host_mesh(PairProblem& pp);
+
 bool gather_pair(Map* pMap, KeyFrame_ pKF1, ID kf1ID, KeyFrame_ pKF2, ID kf2ID, PairProblem& pp, bool with_mesh = true) {
     pp.kf1 = pKF1; pp.kf2 = pKF2; pp.kf1Id = kf1ID; pp.kf2Id = kf2ID;
     const bool img1 = has_depth_image(*pKF1), img2 = has_depth_image(*pKF2);
@@ -176,7 +182,15 @@ bool gather_pair(Map* pMap, KeyFrame_ pKF1, ID kf1ID, KeyFrame_ pKF2, ID kf2ID, 
     se3_to_7(pMap->getGlobalKeyFramesTransformation(kf1ID, kf2ID), pp.Tg);    // :664 (identity the first time)
     if (!with_mesh) return n > 0;
     if (n < 3) return false;
-    // mesh on KF1's positions: 2-D Delaunay of world (x,y), adjacency, cot weights, area (:653-662)
+    // mesh on KF1's positions: 2-D Delaunay of world (x,y), adjacency, cot weights, area (:653-662) -- built on the
+    // device from the uploaded points (dsc_set_graph_delaunay, upload_pair); the host triangulator below only serves
+    // DSC_HOST_MESH=1 and inputs the device construction refuses (DSC_ERR_GRAPH: e.g. many co-circular points)
+    if (!host_mesh_forced()) return true;
+    return host_mesh(pp);
+}
+
+bool host_mesh(PairProblem& pp) {
+    const int n = (int)pp.mp1.size();
     std::vector<double> xy(2 * (size_t)n);
     std::vector<std::array<double, 3>> V(n);
     for (int i = 0; i < n; ++i) {
@@ -188,7 +202,8 @@ bool gather_pair(Map* pMap, KeyFrame_ pKF1, ID kf1ID, KeyFrame_ pKF2, ID kf2ID, 
     return pp.graph.n_triangles > 0 && pp.graph.area > 0.0;
 }
 
-void upload_pair(PairProblem& pp, bool with_graph = true) {
+// false: the pair has no mesh (fewer than 3 points, all collinear) -- the caller skips it, as gather_pair's callers do
+bool upload_pair(PairProblem& pp, bool with_graph = true) {
     dsc_ctx* c = ctx();
     g_res.valid = false;
     dsc_pair pr = make_pair(*pp.kf1, *pp.kf2);
@@ -196,11 +211,25 @@ void upload_pair(PairProblem& pp, bool with_graph = true) {
     ck(dsc_problem_upload(c, &pr, n, pp.X1.data(), pp.X2.data(), pp.uv1.data(), pp.uv2.data(), pp.d1.data(), pp.d2.data(),
                           pp.isg1.data(), pp.isg2.data(), pp.kf1->getEstimatedDepthScale(), pp.kf2->getEstimatedDepthScale(), pp.Tg),
        "dsc_problem_upload");
-    if (!with_graph) return;
-    ck(dsc_set_graph(c, n, pp.graph.rowptr.data(), pp.graph.col.data(), pp.graph.w.data(), pp.graph.area, pp.graph.n_triangles, 1 | 2),
-       "dsc_set_graph");
+    if (!with_graph) return true;
+    bool on_device = !host_mesh_forced();
+    if (on_device) {
+        int st = dsc_set_graph_delaunay(c, 0.0, 1, nullptr, nullptr, nullptr);
+        if (st == DSC_ERR_GRAPH) {                         // degenerate for the device construction: the host triangulator decides
+            on_device = false;
+            if (!host_mesh(pp)) return false;
+        } else ck(st, "dsc_set_graph_delaunay");
+    }
+    if (!on_device)
+        ck(dsc_set_graph(c, n, pp.graph.rowptr.data(), pp.graph.col.data(), pp.graph.w.data(), pp.graph.area, pp.graph.n_triangles, 1 | 2),
+           "dsc_set_graph");
     ck(dsc_compute_rotations(c), "dsc_compute_rotations");                    // :687-688 computeR
     ck(dsc_set_pcg(c, &g_pcg), "dsc_set_pcg");
+    // Early rejection of clearly bad LM trials (dsc.h): same trace, same result (tests/test_gpu_parity.py), 7x fewer PCG
+    // iterations on large pairs.  DSC_NO_EARLY_REJECT=1 runs every solve to the tolerance, as g2o does.
+    static const double rt[2] = {1e-3, 1e-4}, mg[2] = {1.0, 0.5};
+    ck(dsc_set_early_reject(c, std::getenv("DSC_NO_EARLY_REJECT") ? 0 : 2, rt, mg), "dsc_set_early_reject");
+    return true;
 }
 
 dsc_weights weights(double rep, double glob, double arap, double alpha, double beta, float depthError) {
@@ -316,6 +345,7 @@ double nelder_mead(std::vector<double>& x, const std::vector<double>& lb, const 
 namespace dsc_host {
 const std::vector<LmRecord>& lastTrace() { return g_trace; }
 void setSolver(double rtol, int maxIters) { g_pcg.rtol = rtol; g_pcg.max_iters = maxIters; }
+const PhaseTimes& lastPhaseTimes() { return g_times; }
 
 TriangulationResult triangulateMatches(KeyFrame& refKF, KeyFrame& currKF, const std::vector<int>& matches, const std::string& method,
                                        const std::string& location, int gate, float minCos, float depthLimit, bool checkReprojection) {
@@ -460,10 +490,17 @@ void arapOptimization(Map* pMap, double repBalanceWeight, double globalBalanceWe
     // (the main loops stop after the first mapped pair), so pairs are refined one after the other here.
     for_each_pair(pMap, [&](KeyFrame_ kf1, ID id1, KeyFrame_ kf2, ID id2) {
         PairProblem pp;
+        double t0 = now_ms();
         if (!gather_pair(pMap, kf1, id1, kf2, id2, pp)) return;
-        upload_pair(pp);
+        double t1 = now_ms();
+        if (!upload_pair(pp)) return;
+        dsc_synchronize(ctx());
+        double t2 = now_ms();
         run_lm(w, nOptIterations);
+        double t3 = now_ms();
         write_back(pMap, pp, optimizationUpdate);
+        double t4 = now_ms();
+        g_times = dsc_host::PhaseTimes{t1 - t0, t2 - t1, t3 - t2, t4 - t3, (long long)pp.mp1.size()};
     });
 }
 
@@ -510,7 +547,7 @@ void deformationOptimization(std::shared_ptr<Map> pMap, Settings& settings, std:
                 if (uploaded) return;
                 PairProblem pp;
                 if (!gather_pair(pMap.get(), kf1, id1, kf2, id2, pp)) return;
-                upload_pair(pp);
+                if (!upload_pair(pp)) return;
                 uploaded = true;
             });
             if (uploaded) {

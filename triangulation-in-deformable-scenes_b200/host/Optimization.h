@@ -88,6 +88,11 @@ int initializeMapFromMatches(Map& map, KeyFrame_ refKF, KeyFrame_ currKF, const 
 struct LmRecord { double chi2_before, chi2_after, lambda; int trials, accepted, pcg_iters; };
 const std::vector<LmRecord>& lastTrace();
 
+/* Wall-clock phases of the last arapOptimization call (last key-frame pair): Map -> arrays, upload + mesh + graph set-up +
+ * rotations (device), the LM iterations, download + Map write-back. */
+struct PhaseTimes { double gather_ms, setup_ms, lm_ms, writeback_ms; long long correspondences; };
+const PhaseTimes& lastPhaseTimes();
+
 /* PCG controls of the linear solve (defaults rtol 1e-10, 6000 iterations). */
 void setSolver(double rtol, int maxIters);
 

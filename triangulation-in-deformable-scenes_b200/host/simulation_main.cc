@@ -2,7 +2,10 @@
 // SLAM::loadPoints / setCameraPoses / getSimulatedDepthMeasurements / createKeyPoints / processSimulatedImage
 // (Modules/System/SLAM.cc:133-148,172-351) restated without OpenCV/Pangolin.  Prints one JSON object with the
 // triangulation, the LM trace of the last arapOptimization call and the final state.
-//   dsc_simulation <settings.yaml> <original_points.csv> <moved_points.csv> [--single]
+//   dsc_simulation <settings.yaml> <original_points.csv> <moved_points.csv> [--single] [--time]
+// --time: instead of the points, the wall-clock phases of the run (triangulation + Map building, then the phases of
+// arapOptimization through the reference-facing call: Map gather, device set-up incl. the Delaunay mesh, LM, write-back)
+#include <chrono>
 #include <cstdio>
 #include <fstream>
 #include <iostream>
@@ -37,7 +40,9 @@ static Eigen::Matrix3f lookAt(const Eigen::Vector3f& c, const Eigen::Vector3f& t
 
 int main(int argc, char** argv) {
     if (argc < 4) { std::fprintf(stderr, "usage: %s settings.yaml original.csv moved.csv [--single]\n", argv[0]); return 2; }
-    bool single = argc > 4 && std::string(argv[4]) == "--single";
+    bool single = false, timed = false;
+    for (int a = 4; a < argc; ++a) { single |= std::string(argv[a]) == "--single"; timed |= std::string(argv[a]) == "--time"; }
+    auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     try {
         Settings settings(argv[1]);
         auto original = loadCsv(argv[2]), moved = loadCsv(argv[3]);
@@ -76,20 +81,34 @@ int main(int argc, char** argv) {
         auto pMap = std::make_shared<Map>();
         pMap->insertKeyFrame(refKF); pMap->insertKeyFrame(currKF);
         // processSimulatedImage (SLAM.cc:133-148)
+        const double t_tri0 = now();
         int nMPs = dsc_host::triangulateSimulatedMapPoints(*pMap, refKF, currKF, settings.getTrianMethod(), settings.getTrianLocation(), settings.getMinCos());
         std::vector<Eigen::Vector3f> tri1, tri2;
         for (size_t i = 0; i < n; ++i) if (refKF->getMapPoint(i)) { tri1.push_back(refKF->getMapPoint(i)->getWorldPosition()); tri2.push_back(currKF->getMapPoint(i)->getWorldPosition()); }
         double s1_0 = refKF->getEstimatedDepthScale(), s2_0 = currKF->getEstimatedDepthScale();
         std::shared_ptr<MapVisualizer> vis = std::make_shared<MapVisualizer>();
-        dsc_host::setSolver(1e-12, 20000);
+        const double t_tri1 = now();
+        if (timed) dsc_host::setSolver(1e-10, 6000); else dsc_host::setSolver(1e-12, 20000);
         double update = 0;
+        const double t_opt0 = now();
         if (single)
             arapOptimization(pMap.get(), settings.getOptRepWeight(), settings.getOptGlobalWeight(), settings.getOptArapWeight(), settings.getOptAlphaWeight(),
                              settings.getOptBetaWeight(), settings.getSimulatedDepthWeight() / 1000, settings.getnOptIterations(), &update);
         else
             deformationOptimization(pMap, settings, vis, original, moved);
+        const double t_opt1 = now();
         PixelsError pe;
         calculatePixelsStandDev(pMap, pe);
+        if (timed) {
+            auto& ph = dsc_host::lastPhaseTimes();
+            auto& tr = dsc_host::lastTrace();
+            std::printf("{\"n\": %zu, \"map_points\": %d, \"correspondences\": %lld, \"lm_iterations\": %zu, \"triangulate_and_map_ms\": %.3f, "
+                        "\"optimization_call_ms\": %.3f, \"gather_ms\": %.3f, \"device_setup_ms\": %.3f, \"lm_ms\": %.3f, \"writeback_ms\": %.3f, "
+                        "\"final_chi2\": %.17g, \"sigma_c1\": %.9g, \"sigma_c2\": %.9g}\n",
+                        n, nMPs, ph.correspondences, tr.size(), t_tri1 - t_tri0, t_opt1 - t_opt0, ph.gather_ms, ph.setup_ms, ph.lm_ms, ph.writeback_ms,
+                        tr.empty() ? 0.0 : tr.back().chi2_after, pe.desvc1, pe.desvc2);
+            return 0;
+        }
         std::printf("{\"n\": %zu, \"map_points\": %d, \"s1_init\": %.17g, \"s2_init\": %.17g, \"update\": %.17g, \"sigma_c1\": %.17g, \"sigma_c2\": %.17g,\n",
                     n, nMPs, s1_0, s2_0, update, pe.desvc1, pe.desvc2);
         std::printf(" \"s1\": %.17g, \"s2\": %.17g, \"uv1_sum\": %.17g, \"d1_sum\": %.17g,\n", refKF->getEstimatedDepthScale(), currKF->getEstimatedDepthScale(),
