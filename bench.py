@@ -45,6 +45,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-fp32", action="store_true", help="skip the fp32-mode sub-record")
     ap.add_argument("--no-point-sharded", action="store_true", help="N > 1: skip the one-pair-over-all-GPUs sub-record")
+    ap.add_argument("--no-shim-e2e", action="store_true", help="skip the arapOptimization-through-the-C++-shim sub-record")
+    ap.add_argument("--shim-points", type=int, default=1_000_000, help="points of the shim sub-record's sheet scene")
     return ap.parse_args()
 
 
@@ -341,6 +343,18 @@ def main():
                 triangulate=dict(ms=tri["ms"], gbs=tri["bytes"] / (tri["ms"] * 1e-3) / 1e9, frac=tri["bytes"] / (tri["ms"] * 1e-3) / 1e9 / peak,
                                  points_per_s=2.0 * n_tri / (tri["ms"] * 1e-3)))
 
+    # ---- the reference-facing call: arapOptimization(Map*, ...) through the C++ shim (Map gather, Delaunay mesh on the GPU,
+    # LM, Map write-back), the flow of Execution/simulation.cc on a sheet scene of the headline's size
+    shim = None
+    if world == 1 and not args.no_shim_e2e:
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "profiles"))
+            import shim_e2e
+            with _stdout_to_stderr():
+                shim = shim_e2e.run(min(n, args.shim_points), reps=1)
+        except Exception as ex:
+            shim = dict(error=str(ex)[-400:])
+
     # ---- config 5 (batch of independent 10k pairs, sharded by problem index) as a sub-record of the same line at every N
     c5 = None
     if args.config5_problems > 0:
@@ -388,7 +402,7 @@ def main():
                              ms_per_step=e2e_ms / args.steps),
                     gpu_launches=int(launches), clocks=clocks, roofline=roof, cpu_baseline=cpu,
                     triangulated_points_per_s=roof["triangulate"]["points_per_s"], knn_graph_build_ms=prob["graph_build_ms"],
-                    cg_iteration_ms=cg_ms, wall_ms_per_step=wall_ms / args.steps, fp32_mode=f32rec, config5=c5)
+                    cg_iteration_ms=cg_ms, wall_ms_per_step=wall_ms / args.steps, fp32_mode=f32rec, reference_api_e2e=shim, config5=c5)
         if ps is not None:
             if "error" not in ps:
                 ps["speedup_vs_one_gpu"] = ps["lm_it_per_s"] / (value / world)      # the same pair, same LM trace, on ONE of these GPUs

@@ -3,7 +3,7 @@
 Execution/simulation.cc (host/simulation_main.cc --single --time) on the sheet scene -- key points and depths simulated like
 SLAM.cc does, triangulation + Map building, then ONE arapOptimization call: Map gather, device set-up (upload, Delaunay
 mesh + cot weights on the GPU, renumbering, ELL, rotations), LM iterations, write-back into the Map.
-usage: python profiles/shim_e2e.py [n ...]      (default 100000 1000000)"""
+usage: python profiles/shim_e2e.py [n ...]      (default 100000 1000000; SHIM_HOST_MESH=1: the host triangulator instead)"""
 import importlib
 import json
 import os
@@ -15,34 +15,42 @@ import time
 import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, ROOT)
-import __graft_entry__ as g  # noqa: E402
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
 
-pkg = g.package()
-wl = importlib.import_module(pkg.__name__ + ".workloads")
-exe = os.path.join(ROOT, "triangulation-in-deformable-scenes_b200", "lib", "dsc_simulation")
-yaml = open(os.path.join(ROOT, "tests", "golden", "Simulation_b200.yaml")).read().replace(
-    "Optimization.numberOfIterations: 6", "Optimization.numberOfIterations: 25")
-sizes = [int(a) for a in sys.argv[1:]] or [100_000, 1_000_000]
-out = []
-with tempfile.TemporaryDirectory() as tmp:
-    yp = os.path.join(tmp, "sim.yaml")
-    open(yp, "w").write(yaml)
-    for n in sizes:
+
+def run(n, host_mesh=False, lm_iters=25, reps=2, timeout=600):
+    """one timed run of dsc_simulation --single --time on the n-point sheet scene (the last of `reps` runs is reported)"""
+    import __graft_entry__ as g
+    pkg = g.package()
+    wl = importlib.import_module(pkg.__name__ + ".workloads")
+    exe = os.path.join(ROOT, "triangulation-in-deformable-scenes_b200", "lib", "dsc_simulation")
+    yaml = open(os.path.join(ROOT, "tests", "golden", "Simulation_b200.yaml")).read().replace(
+        "Optimization.numberOfIterations: 6", f"Optimization.numberOfIterations: {lm_iters}")
+    with tempfile.TemporaryDirectory() as tmp:
+        yp, po, pm = os.path.join(tmp, "sim.yaml"), os.path.join(tmp, "o.csv"), os.path.join(tmp, "m.csv")
+        open(yp, "w").write(yaml)
         sc = wl.sheet_scene(n, seed=0)
-        po, pm = os.path.join(tmp, f"o{n}.csv"), os.path.join(tmp, f"m{n}.csv")
         np.savetxt(po, sc["original"], fmt="%.9g")
         np.savetxt(pm, sc["moved"], fmt="%.9g")
-        for rep in range(2):                              # second run: page cache and driver warm
+        env = dict(os.environ, **({"DSC_HOST_MESH": "1"} if host_mesh else {}))
+        for _ in range(reps):                              # the last run has the page cache and the driver warm
             t0 = time.perf_counter()
-            r = subprocess.run([exe, yp, po, pm, "--single", "--time"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True,
-                               env=dict(os.environ, **({"DSC_HOST_MESH": "1"} if os.environ.get("SHIM_HOST_MESH") else {})))
+            r = subprocess.run([exe, yp, po, pm, "--single", "--time"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=env,
+                               timeout=timeout)
             wall = time.perf_counter() - t0
             if r.returncode != 0:
-                raise SystemExit(r.stderr[-2000:])
-        rec = json.loads(r.stdout.strip().splitlines()[-1])
-        rec["process_wall_s"] = wall
-        rec["lm_it_per_s_through_the_shim"] = rec["lm_iterations"] / (rec["optimization_call_ms"] * 1e-3)
-        rec["mesh"] = "host Bowyer-Watson (DSC_HOST_MESH=1)" if os.environ.get("SHIM_HOST_MESH") else "GPU (dsc_set_graph_delaunay)"
-        out.append(rec)
-        print(json.dumps(rec), flush=True)
+                raise RuntimeError(r.stderr[-2000:])
+    if os.environ.get("DSC_TIMING"):
+        sys.stderr.write(r.stderr[-4000:])
+    rec = json.loads(r.stdout.strip().splitlines()[-1])
+    rec["process_wall_s"] = wall
+    rec["lm_it_per_s"] = rec["lm_iterations"] / (rec["optimization_call_ms"] * 1e-3)
+    rec["mesh"] = "host Bowyer-Watson (DSC_HOST_MESH=1)" if host_mesh else "GPU (dsc_set_graph_delaunay)"
+    rec["workload"] = f"sheet scene (config-2 generator), {n} points, Simulation.yaml cameras, reference mesh (2-D Delaunay + cot weights), {lm_iters} LM iterations"
+    return rec
+
+
+if __name__ == "__main__":
+    for n in ([int(a) for a in sys.argv[1:]] or [100_000, 1_000_000]):
+        print(json.dumps(run(n, host_mesh=bool(os.environ.get("SHIM_HOST_MESH")))), flush=True)

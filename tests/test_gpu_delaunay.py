@@ -53,6 +53,77 @@ def test_delaunay_edge_cases(pkg, ctx):
         ctx.delaunay_graph(np.zeros((5, 3), np.float32))
 
 
+def test_coincident_points_get_no_vertex(pkg, ctx):
+    """two points with the same (x, y) (different z): the later one is left out of the mesh, as Qhull and the host triangulator
+    leave it out; everything else is the triangulation of the distinct locations"""
+    V = _points("normal", 4000, 11)
+    twins = [(17, 2500), (300, 301), (5, 3999)]
+    for a, b in twins:
+        V[b, :2] = V[a, :2]
+    rowptr, col, w, area, ntri, ns = ctx.delaunay_graph(V)
+    deg = np.diff(rowptr)
+    keep = np.ones(len(V), bool)
+    keep[[b for _, b in twins]] = False
+    assert np.all(deg[~keep] == 0) and np.all(deg[keep] > 0)
+    g = ograph.delaunay_graph(V[keep].astype(np.float64))
+    new_of_old = np.cumsum(keep) - 1
+    old_of_new = np.nonzero(keep)[0]
+    assert ntri == g.n_triangles
+    assert np.array_equal(deg[keep], np.diff(g.rowptr)) and np.array_equal(new_of_old[col], g.col)
+    np.testing.assert_allclose(w, g.w, rtol=1e-12, atol=1e-14)
+    assert np.array_equal(old_of_new[g.col], col)
+
+
+def _exact_flip_verdicts(V, rp_a, col_a, only_a):
+    """for every edge (p, q) of mesh A that mesh B lacks: the sign of the EXACT in-circle determinant (rational arithmetic on the
+    float32 coordinates) of p, q and the two apexes A gives the edge; > 0: the edge is not locally Delaunay"""
+    from fractions import Fraction as Fr
+    P = lambda i: (Fr(float(V[i, 0])), Fr(float(V[i, 1])))
+    nb = lambda i: set(col_a[rp_a[i]:rp_a[i + 1]].tolist())
+    out = []
+    for p, q in only_a:
+        (px, py), (qx, qy) = P(p), P(q)
+        side = lambda r: (qx - px) * (P(r)[1] - py) - (qy - py) * (P(r)[0] - px)
+        com = nb(p) & nb(q)
+        left, right = [r for r in com if side(r) > 0], [r for r in com if side(r) < 0]
+        worst = None
+        for r in left:
+            for t in right:
+                (dx, dy) = P(t)
+                a, b, c = [(x - dx, y - dy) for x, y in (P(p), P(q), P(r))]
+                det = ((a[0] ** 2 + a[1] ** 2) * (b[0] * c[1] - c[0] * b[1]) - (b[0] ** 2 + b[1] ** 2) * (a[0] * c[1] - c[0] * a[1])
+                       + (c[0] ** 2 + c[1] ** 2) * (a[0] * b[1] - b[0] * a[1]))
+                # p, q, r counter-clockwise  =>  det > 0 iff t is strictly inside their circle
+                worst = det if worst is None else max(worst, det)
+        out.append(worst)
+    return out
+
+
+def test_far_outliers_do_not_decide_the_grid(pkg, ctx):
+    """badly triangulated matches far from everything else: the search grid follows mean +- 4 sigma and the mesh stays the
+    Delaunay triangulation.  With points 3000 sigma away Qhull itself (floating-point lifting, 'Qbb' scaling) flips a handful of
+    nearly co-circular quads the wrong way; wherever the two meshes differ the EXACT in-circle test decides: every edge only
+    the device has is locally Delaunay, every edge only Qhull has is not."""
+    V = _points("normal", 30000, 12)
+    V[:5, :2] = np.array([[40.0, 3.0], [-25.0, -60.0], [0.5, 90.0], [70.0, -70.0], [-90.0, 0.1]], np.float32)
+    n = len(V)
+    g = ograph.delaunay_graph(V.astype(np.float64))
+    rowptr, col, w, area, ntri, ns = ctx.delaunay_graph(V)
+    assert ntri == g.n_triangles and len(col) == len(g.col)
+    edges_of = lambda rp, c: set(zip(np.repeat(np.arange(n), np.diff(rp)).tolist(), np.asarray(c).tolist()))
+    mine, qh = edges_of(rowptr, col), edges_of(g.rowptr, g.col)
+    only_mine = sorted(e for e in mine - qh if e[0] < e[1])
+    only_qh = sorted(e for e in qh - mine if e[0] < e[1])
+    assert len(only_mine) == len(only_qh) <= 1e-3 * n                                      # diagonal flips of single quads
+    assert all(d is not None and d < 0 for d in _exact_flip_verdicts(V, rowptr, col, only_mine))
+    assert all(d is not None and d > 0 for d in _exact_flip_verdicts(V, g.rowptr, g.col, only_qh))
+    # the same cloud without the outliers' influence on Qhull's scaling: bit-exact as everywhere else
+    W = V[5:]
+    g2 = ograph.delaunay_graph(W.astype(np.float64))
+    rowptr2, col2, *_ = ctx.delaunay_graph(W)
+    assert np.array_equal(rowptr2, g2.rowptr) and np.array_equal(col2, g2.col)
+
+
 def test_refinement_on_the_gpu_built_mesh_matches_the_oracle(pkg, ctx):
     """config 1's flow with the graph built on the device: same LM trace as the oracle on its Qhull mesh"""
     from oracle import lm
@@ -83,6 +154,11 @@ def test_delaunay_1m_timing(pkg, ctx):
     rowptr, col, w, area, ntri, nsecond = ctx.delaunay_graph(V)
     ms = (time.perf_counter() - t0) * 1e3
     n = len(V)
-    assert ntri > 1.9 * n and len(col) == 2 * (ntri + (len(col) // 2 - ntri)) and nsecond < 40 * np.sqrt(n)
-    hull = len(col) // 2 - (3 * ntri - len(col) // 2)        # Euler: E = 3T + h - ... for a triangulated disc: h = 3V - 3 - E
+    assert ntri > 1.9 * n and nsecond < 40 * np.sqrt(n)
+    row = np.repeat(np.arange(n), np.diff(rowptr))
+    key = row.astype(np.int64) * n + col
+    rev = col.astype(np.int64) * n + row
+    assert np.array_equal(np.sort(key), np.sort(rev))                                      # symmetric
+    assert np.array_equal(w[np.argsort(key)], w[np.argsort(rev)])                          # ... with the same bits both ways
+    assert ntri == len(col) // 2 - n + 1                                                   # Euler, triangulated disc: T = E - V + 1
     print(f"[delaunay 1M] {ms:.1f} ms incl. upload/download; {ntri} triangles, {len(col) // 2} edges, {nsecond} second-pass cells")

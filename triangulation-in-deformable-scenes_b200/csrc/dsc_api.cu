@@ -961,19 +961,48 @@ static int delaunay_build_device(dsc_ctx* ctx, int n, const float* dX, double mi
     }
     const double wdt = x1 - x0, hgt = y1 - y0, dm = std::max(wdt, hgt);
     if (!(dm > 0.0) || !std::isfinite(dm)) return fail(ctx, DSC_ERR_INVALID_ARG, "Delaunay: the points have no extent in (x, y) or are not finite");
-    KnnGrid g{x0, y0, 1.0, 1, 1};
+    // the search grid covers mean +- 4 sigma of the points (clipped to the bounding box): a handful of far outliers --
+    // badly triangulated matches -- must not decide the cell size.  Points outside fall into the border cells (the ring
+    // walk's distance bound stays valid for them; a query point outside is simply left to the second pass).
+    double gx0 = x0, gx1 = x1, gy0 = y0, gy1 = y1;
     {
-        double cell = std::sqrt(std::max(wdt, 1e-300) * std::max(hgt, 1e-300) / std::max(1.0, n / 2.0));
-        cell = std::max(cell, std::max(wdt, hgt) / 4096.0);
+        const double mcx = 0.5 * (x0 + x1), mcy = 0.5 * (y0 + y1);
+        delaunay_moments_kernel<<<nbv, kThreads, 0, ctx->stream>>>(n, dX, mcx, mcy, ctx->part);
+        ctx->launches++;
+        CK(cudaMemcpyAsync(ctx->h_pinned, ctx->part, sizeof(double) * 4 * nbv, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        double mo[4];
+        for (int k = 0; k < 4; ++k) mo[k] = host_sum(ctx->h_pinned, nbv, 4, k);
+        const double mx = mo[0] / n, my = mo[1] / n;
+        const double sx = std::sqrt(std::max(0.0, mo[2] / n - mx * mx)), sy = std::sqrt(std::max(0.0, mo[3] / n - my * my));
+        if (sx > 0.0 && std::isfinite(sx)) { gx0 = std::max(x0, mcx + mx - 4.0 * sx); gx1 = std::min(x1, mcx + mx + 4.0 * sx); }
+        if (sy > 0.0 && std::isfinite(sy)) { gy0 = std::max(y0, mcy + my - 4.0 * sy); gy1 = std::min(y1, mcy + my + 4.0 * sy); }
+    }
+    KnnGrid g{gx0, gy0, 1.0, 1, 1};
+    {
+        const double gw = gx1 - gx0, ghh = gy1 - gy0;
+        double cell = std::sqrt(std::max(gw, 1e-300) * std::max(ghh, 1e-300) / std::max(1.0, n / 2.0));
+        cell = std::max(cell, std::max(gw, ghh) / 4096.0);
         g.inv_cell = 1.0 / cell;
-        g.nx = std::max(1, (int)std::ceil(wdt / cell) + 1);
-        g.ny = std::max(1, (int)std::ceil(hgt / cell) + 1);
+        g.nx = std::max(1, (int)std::ceil(gw / cell) + 1);
+        g.ny = std::max(1, (int)std::ceil(ghh / cell) + 1);
     }
     const int ncells = g.nx * g.ny, m = std::max(ncells, n) + 1;
     int *cell = nullptr, *cnt = nullptr, *start = nullptr, *cursor = nullptr, *order = nullptr, *sums = nullptr, *star = nullptr, *deg = nullptr,
         *flag = nullptr, *isu = nullptr, *pos = nullptr, *list = nullptr, *slot = nullptr, *extra = nullptr, *nextra = nullptr, *rowdeg = nullptr;
+    unsigned char* dup = nullptr;
     auto release = [&]() {
         for (int** q : {&cell, &cnt, &start, &cursor, &order, &sums, &star, &deg, &flag, &isu, &pos, &list, &slot, &extra, &nextra, &rowdeg}) dev_free(*q);
+        dev_free(dup);
+    };
+    const bool timing = std::getenv("DSC_TIMING") != nullptr;
+    auto t_last = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) {
+        if (!timing) return;
+        cudaStreamSynchronize(ctx->stream);
+        auto t = std::chrono::steady_clock::now();
+        std::fprintf(stderr, "[dsc_delaunay] %-18s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(t - t_last).count());
+        t_last = t;
     };
     auto scan = [&](int count, const int* in, int* out) {      // exclusive scan of count ints
         int nb = (count + kScanBlock - 1) / kScanBlock;
@@ -986,7 +1015,7 @@ static int delaunay_build_device(dsc_ctx* ctx, int n, const float* dX, double mi
     if ((e = dev_alloc(cell, (size_t)n)) || (e = dev_alloc(cnt, (size_t)m)) || (e = dev_alloc(start, (size_t)m)) || (e = dev_alloc(cursor, (size_t)m)) ||
         (e = dev_alloc(order, (size_t)n)) || (e = dev_alloc(sums, (size_t)(m / kScanBlock + 2))) || (e = dev_alloc(star, (size_t)n * kDlMaxV)) ||
         (e = dev_alloc(deg, (size_t)n)) || (e = dev_alloc(flag, (size_t)n)) || (e = dev_alloc(isu, (size_t)n + 1)) || (e = dev_alloc(pos, (size_t)n + 1)) ||
-        (e = dev_alloc(slot, (size_t)n)) || (e = dev_alloc(nextra, (size_t)n)) || (e = dev_alloc(rowdeg, (size_t)n + 1))) {
+        (e = dev_alloc(slot, (size_t)n)) || (e = dev_alloc(nextra, (size_t)n)) || (e = dev_alloc(rowdeg, (size_t)n + 1)) || (e = dev_alloc(dup, (size_t)n))) {
         release();
         return fail(ctx, DSC_ERR_ALLOC, cudaGetErrorString(e));
     }
@@ -996,9 +1025,13 @@ static int delaunay_build_device(dsc_ctx* ctx, int n, const float* dX, double mi
     knn_cell_kernel<<<nbv, kThreads, 0, ctx->stream>>>(n, dX, g, cell, cnt);
     scan(ncells, cnt, start);
     knn_scatter_kernel<<<nbv, kThreads, 0, ctx->stream>>>(n, cell, start, cursor, order);
+    delaunay_duplicates_kernel<<<nbv, kThreads, 0, ctx->stream>>>(n, dX, g, start, order, ncells, dup);
+    ctx->launches++;
+    lap("grid");
     const double box = std::ldexp(dm, 40);                     // "the whole plane": 2^40 x the extent of the point cloud
     // ---- pass one: every cell from the points around it
-    delaunay_cells_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(n, dX, g, start, order, ncells, box, nullptr, 0, nullptr, nullptr, star, deg, flag);
+    delaunay_cells_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(n, dX, g, start, order, ncells, box, dup, nullptr, 0, nullptr, nullptr, star, deg, flag);
+    lap("cells, pass one");
     // ---- the uncertified points, in index order
     delaunay_flag_kernel<<<nbv, kThreads, 0, ctx->stream>>>(n, flag, isu);
     CK(cudaMemsetAsync(isu + n, 0, sizeof(int), ctx->stream));
@@ -1016,7 +1049,8 @@ static int delaunay_build_device(dsc_ctx* ctx, int n, const float* dX, double mi
         delaunay_compact_kernel<<<nbv, kThreads, 0, ctx->stream>>>(n, isu, pos, list, slot);
         delaunay_extra_kernel<<<nbv, kThreads, 0, ctx->stream>>>(n, star, deg, flag, slot, extra, nextra);
         delaunay_sort_extra_kernel<<<grid_threads(ctx, nu), kThreads, 0, ctx->stream>>>(nu, list, extra, nextra);
-        delaunay_cells_kernel<<<(nu + 127) / 128, 128, 0, ctx->stream>>>(n, dX, g, start, order, ncells, box, list, nu, extra, nextra, star, deg, flag);
+        delaunay_cells_kernel<<<(nu + 127) / 128, 128, 0, ctx->stream>>>(n, dX, g, start, order, ncells, box, dup, list, nu, extra, nextra, star, deg, flag);
+        lap("cells, pass two");
         delaunay_flag_kernel<<<nbv, kThreads, 0, ctx->stream>>>(n, flag, isu);
         scan(n + 1, isu, pos);
         ctx->launches += 5;
@@ -1041,6 +1075,7 @@ static int delaunay_build_device(dsc_ctx* ctx, int n, const float* dX, double mi
     ctx->launches++;
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(ctx->stream));
+    lap("rows");
     release();
     ctx->dl_E = E;
     return DSC_OK;

@@ -100,11 +100,12 @@ DSC_D void dl_clip(DlCell& c, double qx, double qy, int id) {
 // 1 certified, 0 not, 2 overflow.
 __global__ void __launch_bounds__(128)
 delaunay_cells_kernel(int n, const float* __restrict__ X, KnnGrid g, const int* __restrict__ start, const int* __restrict__ order, int ncells,
-                      double box, const int* __restrict__ list, int nlist, const int* __restrict__ extra,
+                      double box, const unsigned char* __restrict__ dup, const int* __restrict__ list, int nlist, const int* __restrict__ extra,
                       const int* __restrict__ nextra, int* __restrict__ star, int* __restrict__ deg, int* __restrict__ flag) {
     const int total = list ? nlist : n;
     for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
         const int i = list ? list[t] : order[t];          // pass one walks the points in cell order: neighbouring threads search the same cells
+        if (dup[i]) { deg[i] = 0; flag[i] = 1; continue; } // no vertex of the mesh
         const double xi = (double)X[3 * (size_t)i], yi = (double)X[3 * (size_t)i + 1];
         const int cx = min(g.nx - 1, max(0, (int)((xi - g.x0) * g.inv_cell)));
         const int cy = min(g.ny - 1, max(0, (int)((yi - g.y0) * g.inv_cell)));
@@ -130,7 +131,7 @@ delaunay_cells_kernel(int n, const float* __restrict__ X, KnnGrid g, const int* 
                     const int e1 = cc + 1 < ncells ? start[cc + 1] : n;
                     for (int e = start[cc]; e < e1; ++e) {
                         const int j = order[e];
-                        if (j != i) dl_clip(c, (double)X[3 * (size_t)j] - xi, (double)X[3 * (size_t)j + 1] - yi, j);
+                        if (j != i && !dup[j]) dl_clip(c, (double)X[3 * (size_t)j] - xi, (double)X[3 * (size_t)j + 1] - yi, j);
                     }
                     if (r == 0) break;
                 }
@@ -144,7 +145,7 @@ delaunay_cells_kernel(int n, const float* __restrict__ X, KnnGrid g, const int* 
             }
             for (int k = 0; k < nlist; ++k) {
                 const int j = list[k];
-                if (j != i) dl_clip(c, (double)X[3 * (size_t)j] - xi, (double)X[3 * (size_t)j + 1] - yi, j);
+                if (j != i && !dup[j]) dl_clip(c, (double)X[3 * (size_t)j] - xi, (double)X[3 * (size_t)j + 1] - yi, j);
             }
             certified = nextra[i] <= kDlMaxExtra;
         }
@@ -154,6 +155,40 @@ delaunay_cells_kernel(int n, const float* __restrict__ X, KnnGrid g, const int* 
         deg[i] = c.m;
         flag[i] = c.overflow ? 2 : (certified ? 1 : 0);
     }
+}
+
+// Points with the same (x, y) as a point of smaller index are DUPLICATES: like Qhull and the host triangulator, the mesh
+// has one vertex per location -- a duplicate gets no cell and is nobody's generator.  Coincident points share a grid cell.
+__global__ void delaunay_duplicates_kernel(int n, const float* __restrict__ X, KnnGrid g, const int* __restrict__ start,
+                                           const int* __restrict__ order, int ncells, unsigned char* __restrict__ dup) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float xf = X[3 * (size_t)i], yf = X[3 * (size_t)i + 1];
+        const int cx = min(g.nx - 1, max(0, (int)(((double)xf - g.x0) * g.inv_cell)));
+        const int cy = min(g.ny - 1, max(0, (int)(((double)yf - g.y0) * g.inv_cell)));
+        const int cc = cy * g.nx + cx;
+        const int e1 = cc + 1 < ncells ? start[cc + 1] : n;
+        unsigned char d = 0;
+        for (int e = start[cc]; e < e1; ++e) {
+            const int j = order[e];
+            if (j < i && X[3 * (size_t)j] == xf && X[3 * (size_t)j + 1] == yf) { d = 1; break; }
+        }
+        dup[i] = d;
+    }
+}
+
+// first and second moments of (x, y): the grid is laid over mean +- 4 sigma (inside the bounding box), so a few far
+// outliers -- badly triangulated points -- cannot blow the cells up; points outside fall into the border cells.
+// part[grid][4] = sum x, sum y, sum x^2, sum y^2
+__global__ void __launch_bounds__(kThreads)
+delaunay_moments_kernel(int n, const float* __restrict__ X, double cx, double cy, double* __restrict__ part) {
+    __shared__ double sm[4 * (kThreads / 32)];
+    double a[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const double x = (double)X[3 * (size_t)i] - cx, y = (double)X[3 * (size_t)i + 1] - cy;
+        a[0] += x; a[1] += y; a[2] += x * x; a[3] += y * y;
+    }
+    block_reduce<4>(a, sm);
+    if (threadIdx.x == 0) for (int k = 0; k < 4; ++k) part[4 * (size_t)blockIdx.x + k] = a[k];
 }
 
 // certified point p lists uncertified u  =>  p is a candidate for u's cell.  slot[u] = position of u in the list of
