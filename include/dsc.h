@@ -295,6 +295,11 @@ int  dsc_batch_upload(dsc_batch* batch, int n_problems, const dsc_batch_pair* pa
 int  dsc_batch_set_pcg(dsc_batch* batch, const dsc_pcg_params* prm);
 int  dsc_batch_set_early_reject(dsc_batch* batch, int n_levels, const double* rtol_loose, const double* rho_margin);
 int  dsc_batch_reset_state(dsc_batch* batch);
+/* the next launches (optimize / reset_state / pixel_sigma) work on pairs [0, n_active) only; -1 = all.  The weight search
+ * keeps K replicas of one pair resident and refines as many as a Nelder-Mead step has candidate weights. */
+int  dsc_batch_set_active(dsc_batch* batch, int n_active);
+/* calculatePixelsStandDev (Modules/Utils/Geometry.cc:370-498) of every active pair's current state: sigma[n_active][2] */
+int  dsc_batch_pixel_sigma(dsc_batch* batch, double* sigma);
 int  dsc_batch_optimize(dsc_batch* batch, const dsc_weights* weights, int n_weights, int n_iters, dsc_iter_record* records,
                         dsc_opt_stats* stats, double* device_ms);
 /* results in the callers' numbering, concatenated like the inputs: X1/X2 [sum n][3] float, scales [n_problems][2],

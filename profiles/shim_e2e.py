@@ -46,6 +46,9 @@ def run(n, host_mesh=False, lm_iters=25, reps=2, timeout=600):
     rec = json.loads(r.stdout.strip().splitlines()[-1])
     rec["process_wall_s"] = wall
     rec["lm_it_per_s"] = rec["lm_iterations"] / (rec["optimization_call_ms"] * 1e-3)
+    sc = rec.get("second_call") or {}
+    if sc.get("optimization_call_ms"):          # the outer loop's next arapOptimization call: context warm (buffers, kernels loaded)
+        sc["lm_it_per_s"] = sc["lm_iterations"] / (sc["optimization_call_ms"] * 1e-3)
     rec["mesh"] = "host Bowyer-Watson (DSC_HOST_MESH=1)" if host_mesh else "GPU (dsc_set_graph_delaunay)"
     rec["workload"] = f"sheet scene (config-2 generator), {n} points, Simulation.yaml cameras, reference mesh (2-D Delaunay + cot weights), {lm_iters} LM iterations"
     return rec

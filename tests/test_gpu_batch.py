@@ -144,3 +144,47 @@ def test_batch_edge_cases(pkg):
                 assert np.array_equal(outs[k]["X1"], outs[0]["X1"])
     r1, s1, o1 = _single(pkg, p, w, 3)
     assert ref == pytest.approx([x.chi2_after for x in r1], rel=1e-7)
+
+
+def test_weight_search_candidates_refined_together_match_the_oracle(pkg):
+    """the outer objective (nloptOptimization.cc:5-37) of the weights a Nelder-Mead search visits, (a) by the
+    oracle one refinement at a time, (b) on the device with the K replicas of the pair resident in one dsc_batch, as many of them
+    refined per launch as there are candidates (dsc_batch_set_active / dsc_batch_pixel_sigma).  Same evaluations, same order."""
+    from oracle import outer
+    sc = scenes.sheet_scene(400, seed=7)
+    p, _ = scenes.problem_from_scene(sc, "delaunay", 8)
+    iters, sigma_d = 4, 0.003
+    x0, lb, ub = [1.0, 50.0, 2.0e5], [1.0, 50.0, 1e-5], [1.0, 50.0, 1e7]          # Simulation.yaml:88-93: a 1-D search over arap
+    fo = lambda y: outer.outer_objective(p, y[0], y[1], y[2], sigma_d, iters)
+    xo, fbest_o, log_o = outer.nelder_mead(fo, x0, lb, ub, 0.15, 0.15, 7)
+    K = 4
+    with pkg.Batch(0) as b:
+        b.upload([_problem_dict(pkg, p) for _ in range(K)])
+        b.set_pcg(rtol=1e-12, max_iters=20000)
+
+        def many(cands):
+            b.set_active(len(cands))
+            b.reset_state()
+            b.optimize([pkg.make_weights(y[0], y[2], sigma_d, glob=y[1]) for y in cands], iters)
+            s = b.pixel_sigma()
+            return [float(np.log(s[k, 0]) ** 2 + np.log(s[k, 1]) ** 2) for k in range(len(cands))]
+        # the weights the oracle's search visited, four at a time: one launch per group
+        xs = [e[0] for e in log_o]
+        fg = []
+        for at in range(0, len(xs), K):
+            fg += many(xs[at:at + K])
+        np.testing.assert_allclose(fg, [e[1] for e in log_o], rtol=2e-5)
+        # and the search itself on device values: the same walk
+        xg, fbest_g, log_g = outer.nelder_mead(lambda y: many([y])[0], x0, lb, ub, 0.15, 0.15, 7)
+        assert len(log_g) == len(log_o)
+        np.testing.assert_allclose([e[0] for e in log_g], xs, rtol=1e-12)
+        assert xg == pytest.approx(xo, rel=1e-12) and fbest_g == pytest.approx(fbest_o, rel=2e-5)
+        # a subset launch leaves the other replicas alone
+        b.set_active(-1)
+        b.reset_state()
+        b.set_active(1)
+        b.optimize([pkg.make_weights(1.0, 2.0e5, sigma_d, glob=50.0)], iters)
+        b.set_active(-1)
+        s = b.pixel_sigma()
+        assert s[1, 0] == s[2, 0] == s[3, 0] and s[0, 0] != s[1, 0]
+        assert s[1, 0] == pytest.approx(scenes.pixel_sigma(p.cam1, p.T1, p.X1, p.uv1), rel=1e-9)

@@ -102,6 +102,80 @@ def test_simulation_flow_single_call_matches_oracle():
     np.testing.assert_allclose(chi, tr.chi2, rtol=5e-2)            # different key-point rounding => loose; exact parity is in test_gpu_parity
 
 
+def _shim_nm(lib, fn, x0, lb, ub, xtol_rel, xtol_abs, maxeval, speculative):
+    dim = len(x0)
+    arr = lambda v: np.ascontiguousarray(v, np.float64)
+    x0, lb, ub = arr(x0), arr(lb), arr(ub)
+    xout, fout, log, launches = np.zeros(dim), ctypes.c_double(), np.zeros((maxeval + 8, dim + 1)), ctypes.c_int()
+    ptr = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    used = lib.dsch_nelder_mead(fn, dim, ptr(x0), ptr(lb), ptr(ub), ctypes.c_double(xtol_rel), ctypes.c_double(xtol_abs), maxeval, int(speculative),
+                                ptr(xout), ctypes.byref(fout), ptr(log), log.shape[0], ctypes.byref(launches))
+    return xout, fout.value, log[:used], launches.value
+
+
+@pytest.mark.parametrize("case", ["weights-1d", "weights-3d", "rosenbrock", "maxeval-cut"])
+def test_weight_search_nelder_mead_matches_the_oracle_in_both_modes(case):
+    """the shim's Nelder-Mead (stand-in for nlopt LN_NELDERMEAD, g2oBundleAdjustment.cc:491-515) against the oracle's separate
+    restatement: the same evaluations in the same order -- also when the candidates of a step are evaluated together, which
+    then takes fewer launches"""
+    from oracle import outer
+    lib = _host()
+    if case == "weights-1d":       # the shipped YAMLs: rep and global fixed, arap in [1e-5, 1e7] (Simulation.yaml:88-93)
+        fn, x0, lb, ub, tol, me = 0, [1.0, 50.0, 2e5], [1.0, 50.0, 1e-5], [1.0, 50.0, 1e7], 1e-3, 60
+    elif case == "weights-3d":
+        fn, x0, lb, ub, tol, me = 0, [3.0, 50.0, 2e3], [1e-2, 1.0, 1e-1], [1e3, 1e4, 1e6], 1e-4, 200
+    elif case == "rosenbrock":
+        fn, x0, lb, ub, tol, me = 1, [-1.2, 1.0], [-2.0, -2.0], [2.0, 2.0], 1e-6, 400
+    else:
+        fn, x0, lb, ub, tol, me = 0, [3.0, 50.0, 2e3], [1e-2, 1.0, 1e-1], [1e3, 1e4, 1e6], 1e-9, 17
+    dim = len(x0)
+    f = (lambda y: 100.0 * (y[1] - y[0] ** 2) ** 2 + (1.0 - y[0]) ** 2) if fn == 1 else (lambda y: sum((np.log10(y[k]) - (k + 1)) ** 2 for k in range(dim)))
+    xo, fo, logo = outer.nelder_mead(f, x0, lb, ub, tol, tol, me)
+    runs = {spec: _shim_nm(lib, fn, x0, lb, ub, tol, tol, me, spec) for spec in (False, True)}
+    for spec, (x, fbest, log, launches) in runs.items():
+        assert len(log) == len(logo) <= me
+        np.testing.assert_allclose(log[:, :dim], np.array([e[0] for e in logo]), rtol=1e-13, atol=0)
+        np.testing.assert_allclose(log[:, dim], np.array([e[1] for e in logo]), rtol=1e-9, atol=1e-300)
+        np.testing.assert_allclose(x, xo, rtol=1e-13)
+        assert fbest == pytest.approx(fo, rel=1e-9, abs=1e-300)
+    assert runs[False][3] == len(logo)                           # one launch per evaluation
+    if len(logo) > 8:
+        assert runs[True][3] < 0.8 * runs[False][3]              # a step's candidates share a launch
+    if case == "rosenbrock":
+        assert fo < 1e-8
+
+
+@pytest.mark.gpu
+def test_weight_search_modes_walk_the_same_simplices():
+    """deformationOptimization with weightsSelection nlopt (config 1): the candidates of a Nelder-Mead step refined together
+    on the batched path (default), one at a time on the batched path, and one at a time on the main context (the round-1
+    path) evaluate the same weights in the same order and end at the same weights"""
+    exe = os.path.join(LIB, "dsc_simulation")
+    outs = {}
+    for mode in ("", "sequential", "single"):
+        env = dict(os.environ)
+        env.pop("DSC_WEIGHT_SEARCH", None)
+        if mode:
+            env["DSC_WEIGHT_SEARCH"] = mode
+        out = subprocess.run([exe, os.path.join(GOLD, "Simulation_b200.yaml"), os.path.join(GOLD, "config1_original.csv"),
+                              os.path.join(GOLD, "config1_moved.csv")], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=env)
+        assert out.returncode == 0, out.stderr
+        xs = [float(l.split("ARAP:")[1]) for l in out.stdout.splitlines() if l.startswith("Current x values")]
+        fs = [float(l.split(":")[1]) for l in out.stdout.splitlines() if l.startswith("error:")]
+        launches = [int(l.split(" in ")[1].split()[0]) for l in out.stdout.splitlines() if l.startswith("Weight search:")]
+        js = json.loads(out.stdout[out.stdout.rindex('{"n"'):])
+        outs[mode] = (xs, fs, launches, js)
+    xs0, fs0, l0, js0 = outs[""]
+    assert len(xs0) >= 6 and len(fs0) == len(xs0)
+    for mode in ("sequential", "single"):
+        xs, fs, l, js = outs[mode]
+        np.testing.assert_allclose(xs, xs0, rtol=1e-5)            # printed with 6 digits
+        np.testing.assert_allclose(fs, fs0, rtol=1e-4 if mode == "single" else 1e-5)
+        assert sum(l) == len(xs)                                  # one launch per evaluation
+        assert js["sigma_c1"] == pytest.approx(js0["sigma_c1"], rel=1e-6) and js["s1"] == pytest.approx(js0["s1"], rel=1e-6)
+    assert sum(l0) < len(xs0)                                     # fewer launches than evaluations
+
+
 @pytest.mark.gpu
 def test_simulation_flow_outer_loop_runs():
     exe = os.path.join(LIB, "dsc_simulation")

@@ -25,7 +25,7 @@ EXPORTS = [
     "dsc_problem_upload", "dsc_set_graph", "dsc_compute_rotations", "dsc_get_rotations", "dsc_set_rotations",
     "dsc_reset_state", "dsc_set_pcg", "dsc_set_solver", "dsc_set_precision", "dsc_set_early_reject", "dsc_cost", "dsc_optimize", "dsc_download", "dsc_pixel_sigma",
     "dsc_batch_create", "dsc_batch_destroy", "dsc_batch_last_error", "dsc_batch_upload", "dsc_batch_set_pcg", "dsc_batch_set_early_reject",
-    "dsc_batch_reset_state", "dsc_batch_optimize", "dsc_batch_download", "dsc_batch_size",
+    "dsc_batch_reset_state", "dsc_batch_set_active", "dsc_batch_pixel_sigma", "dsc_batch_optimize", "dsc_batch_download", "dsc_batch_size",
     "dsc_shard_init", "dsc_shard_attach", "dsc_shard_partition", "dsc_shard_info",
     "dsc_debug_linearize", "dsc_debug_matvec", "dsc_profile_kernels", "dsc_profile_triangulate", "dsc_problem_size", "dsc_knn_build", "dsc_knn_download",
     "dsc_delaunay_build", "dsc_delaunay_download", "dsc_set_graph_delaunay",
@@ -525,6 +525,17 @@ class Batch:
 
     def reset_state(self):
         self._ck(self.lib.dsc_batch_reset_state(self.h))
+
+    def set_active(self, n_active=-1):
+        """the next optimize / reset_state / pixel_sigma work on pairs [0, n_active) only (-1: all)"""
+        self._ck(self.lib.dsc_batch_set_active(self.h, int(n_active)))
+        self.active = int(n_active)
+
+    def pixel_sigma(self):
+        k = self.np if getattr(self, "active", -1) < 0 else min(self.active, self.np)
+        out = np.empty((max(1, k), 2))
+        self._ck(self.lib.dsc_batch_pixel_sigma(self.h, _fp(out)))
+        return out[:k]
 
     def optimize(self, weights, n_iters):
         """weights: one Weights (shared) or a list with one per pair -> (records[pair][iteration], stats[pair], device ms)"""

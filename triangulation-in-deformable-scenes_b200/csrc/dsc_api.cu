@@ -101,10 +101,15 @@ struct dsc_ctx {
     // ---- Delaunay graph builder (device CSR of the last dsc_delaunay_build / dsc_set_graph_delaunay)
     int dl_n = 0; long long dl_E = 0, dl_ntri = 0; double dl_area = 0.0;
     int *dl_rowptr = nullptr, *dl_col = nullptr; double* dl_w = nullptr;
+    float* dl_X = nullptr; size_t dl_xcap = 0;
+    size_t dl_cap = 0;                               // points the three arrays are sized for (a planar mesh has < 6 n directed edges)
     long long dl_uncertified = 0;
+    // grow-only device workspace of the graph builders (carved per call: no cudaMalloc / cudaFree on a warm context)
+    unsigned char* ws = nullptr; size_t ws_cap = 0, ws_off = 0;
     // ---- kNN graph builder (device CSR of the last dsc_knn_build)
     int knn_n = 0; long long knn_E = 0;
     int *knn_rowptr = nullptr, *knn_col = nullptr;
+    size_t knn_cap_n = 0, knn_cap_e = 0;
     dsc_pcg_params pcg{1e-10, 4000, 32};
     struct IterGraph { cudaGraphExec_t exec = nullptr; const double* P = nullptr; WeightsDev W{}; int precision = 0; } graphs[2];   // per state buffer
     bool use_graphs = true;
@@ -173,6 +178,7 @@ cudaError_t dev_alloc(T*& p, size_t count) {
 }
 template <typename T>
 void dev_free(T*& p) { if (p) { cudaFree(p); p = nullptr; } }
+inline size_t ws_round(size_t bytes) { return (bytes + 255) & ~(size_t)255; }
 template <typename T>
 cudaError_t pin_reserve(T*& p, size_t& cap, size_t count) {       // pinned host buffer with at least `count` elements
     if (count <= cap) return cudaSuccess;
@@ -390,7 +396,7 @@ extern "C" void dsc_destroy(dsc_ctx* ctx) {
     for (auto& v : ctx->vecF) dev_free(v);
     dev_free(ctx->JeF); dev_free(ctx->UF); dev_free(ctx->MinvF);
     dev_free(ctx->knn_rowptr); dev_free(ctx->knn_col);
-    dev_free(ctx->dl_rowptr); dev_free(ctx->dl_col); dev_free(ctx->dl_w);
+    dev_free(ctx->dl_rowptr); dev_free(ctx->dl_col); dev_free(ctx->dl_w); dev_free(ctx->ws); dev_free(ctx->dl_X);
     dev_free(ctx->small); dev_free(ctx->Gcur); dev_free(ctx->Gtrial); dev_free(ctx->lin); dev_free(ctx->ctl);
     dev_free(ctx->errflag); dev_free(ctx->part); dev_free(ctx->gpart[0]); dev_free(ctx->gpart[1]);
     dev_free(ctx->dpart); dev_free(ctx->bpart);
@@ -939,12 +945,36 @@ extern "C" int dsc_set_graph(dsc_ctx* ctx, int n, const int32_t* rowptr, const i
     return set_graph_tail(ctx, n, E, area, n_triangles, reorder, validate, timing);
 }
 
+// Grow-only device workspace of the graph builders: one allocation, carved per call (ws_begin, ws_take...).  A warm context
+// builds a graph without a single cudaMalloc / cudaFree (each costs 0.1 - 10 ms and serialises the device).
+static cudaError_t ws_begin(dsc_ctx* ctx, size_t bytes) {
+    ctx->ws_off = 0;
+    if (bytes <= ctx->ws_cap) return cudaSuccess;
+    if (ctx->ws) { cudaFree(ctx->ws); ctx->ws = nullptr; ctx->ws_cap = 0; }
+    const size_t want = bytes + bytes / 8;
+    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&ctx->ws), want);
+    if (e == cudaSuccess) ctx->ws_cap = want;
+    return e;
+}
+template <typename T>
+static T* ws_take(dsc_ctx* ctx, size_t count) {
+    T* p = reinterpret_cast<T*>(ctx->ws + ctx->ws_off);
+    ctx->ws_off += ws_round(count * sizeof(T));
+    return p;
+}
+
 // ------------------------------------------------------------------ Delaunay graph on the GPU (dsc_delaunay.cuh)
 // dX: device float [n][3]; leaves the CSR (caller numbering, rows ascending) in ctx->dl_*.
 static int delaunay_build_device(dsc_ctx* ctx, int n, const float* dX, double min_weight) {
-    dev_free(ctx->dl_rowptr); dev_free(ctx->dl_col); dev_free(ctx->dl_w);
     ctx->dl_n = n; ctx->dl_E = 0; ctx->dl_ntri = 0; ctx->dl_area = 0.0; ctx->dl_uncertified = 0;
-    CK(dev_alloc(ctx->dl_rowptr, (size_t)n + 2));
+    if (!ctx->dl_rowptr || (size_t)n > ctx->dl_cap) {          // grow-only: row pointers + the < 6 n directed edges of a planar mesh
+        const size_t cap = (size_t)n + (size_t)n / 8 + 16;
+        ctx->dl_cap = 0;
+        CK(dev_alloc(ctx->dl_rowptr, cap + 2));
+        CK(dev_alloc(ctx->dl_col, 6 * cap));
+        CK(dev_alloc(ctx->dl_w, 6 * cap));
+        ctx->dl_cap = cap;
+    }
     CK(cudaMemsetAsync(ctx->dl_rowptr, 0, sizeof(int) * ((size_t)n + 2), ctx->stream));
     if (n < 3) { CK(cudaStreamSynchronize(ctx->stream)); return DSC_OK; }
     // bounding box of (x, y) (two-stage device reduction, folded on the host) -> grid and the three ghost vertices
@@ -988,13 +1018,26 @@ static int delaunay_build_device(dsc_ctx* ctx, int n, const float* dX, double mi
         g.ny = std::max(1, (int)std::ceil(ghh / cell) + 1);
     }
     const int ncells = g.nx * g.ny, m = std::max(ncells, n) + 1;
-    int *cell = nullptr, *cnt = nullptr, *start = nullptr, *cursor = nullptr, *order = nullptr, *sums = nullptr, *star = nullptr, *deg = nullptr,
-        *flag = nullptr, *isu = nullptr, *pos = nullptr, *list = nullptr, *slot = nullptr, *extra = nullptr, *nextra = nullptr, *rowdeg = nullptr;
-    unsigned char* dup = nullptr;
-    auto release = [&]() {
-        for (int** q : {&cell, &cnt, &start, &cursor, &order, &sums, &star, &deg, &flag, &isu, &pos, &list, &slot, &extra, &nextra, &rowdeg}) dev_free(*q);
-        dev_free(dup);
-    };
+    // every work array comes out of the context's grow-only workspace
+    const size_t nsums = (size_t)(m / kScanBlock + 2);
+    {
+        size_t need = 0;
+        for (size_t c : {(size_t)n, (size_t)m, (size_t)m, (size_t)m, (size_t)n, nsums, (size_t)n * kDlMaxV, (size_t)n, (size_t)n, (size_t)n + 1, (size_t)n + 1,
+                         (size_t)n, (size_t)n, (size_t)n + 1})
+            need += ws_round(c * sizeof(int));
+        need += ws_round((size_t)n);
+        need += ws_round(sizeof(int) * (size_t)kDlWsSecond) + ws_round(sizeof(int) * (size_t)kDlWsSecond * kDlMaxExtra);
+        cudaError_t e = ws_begin(ctx, need);
+        if (e != cudaSuccess) return fail(ctx, DSC_ERR_ALLOC, cudaGetErrorString(e));
+    }
+    int *cell = ws_take<int>(ctx, n), *cnt = ws_take<int>(ctx, m), *start = ws_take<int>(ctx, m), *cursor = ws_take<int>(ctx, m),
+        *order = ws_take<int>(ctx, n), *sums = ws_take<int>(ctx, nsums), *star = ws_take<int>(ctx, (size_t)n * kDlMaxV), *deg = ws_take<int>(ctx, n),
+        *flag = ws_take<int>(ctx, n), *isu = ws_take<int>(ctx, (size_t)n + 1), *pos = ws_take<int>(ctx, (size_t)n + 1), *slot = ws_take<int>(ctx, n),
+        *nextra = ws_take<int>(ctx, n), *rowdeg = ws_take<int>(ctx, (size_t)n + 1);
+    unsigned char* dup = ws_take<unsigned char>(ctx, n);
+    // second pass only: room for kDlWsSecond uncertified cells (the rim: ~2 sqrt(n)) is part of the workspace, more is allocated
+    int *list = ws_take<int>(ctx, kDlWsSecond), *extra = ws_take<int>(ctx, (size_t)kDlWsSecond * kDlMaxExtra), *list_own = nullptr, *extra_own = nullptr;
+    auto release = [&]() { dev_free(list_own); dev_free(extra_own); };
     const bool timing = std::getenv("DSC_TIMING") != nullptr;
     auto t_last = std::chrono::steady_clock::now();
     auto lap = [&](const char* what) {
@@ -1012,13 +1055,6 @@ static int delaunay_build_device(dsc_ctx* ctx, int n, const float* dX, double mi
         ctx->launches += 3;
     };
     cudaError_t e = cudaSuccess;
-    if ((e = dev_alloc(cell, (size_t)n)) || (e = dev_alloc(cnt, (size_t)m)) || (e = dev_alloc(start, (size_t)m)) || (e = dev_alloc(cursor, (size_t)m)) ||
-        (e = dev_alloc(order, (size_t)n)) || (e = dev_alloc(sums, (size_t)(m / kScanBlock + 2))) || (e = dev_alloc(star, (size_t)n * kDlMaxV)) ||
-        (e = dev_alloc(deg, (size_t)n)) || (e = dev_alloc(flag, (size_t)n)) || (e = dev_alloc(isu, (size_t)n + 1)) || (e = dev_alloc(pos, (size_t)n + 1)) ||
-        (e = dev_alloc(slot, (size_t)n)) || (e = dev_alloc(nextra, (size_t)n)) || (e = dev_alloc(rowdeg, (size_t)n + 1)) || (e = dev_alloc(dup, (size_t)n))) {
-        release();
-        return fail(ctx, DSC_ERR_ALLOC, cudaGetErrorString(e));
-    }
     auto bail = [&](int code, const char* what) { release(); return fail(ctx, code, what); };
     CK(cudaMemsetAsync(cnt, 0, sizeof(int) * m, ctx->stream));
     CK(cudaMemsetAsync(cursor, 0, sizeof(int) * m, ctx->stream));
@@ -1044,7 +1080,10 @@ static int delaunay_build_device(dsc_ctx* ctx, int n, const float* dX, double mi
     ctx->dl_uncertified = nu;
     if (nu > 0) {
         // ---- pass two: finish them from the certified points that list them and from each other
-        if ((e = dev_alloc(list, (size_t)nu)) || (e = dev_alloc(extra, (size_t)nu * kDlMaxExtra))) { release(); return fail(ctx, DSC_ERR_ALLOC, cudaGetErrorString(e)); }
+        if (nu > kDlWsSecond) {
+            if ((e = dev_alloc(list_own, (size_t)nu)) || (e = dev_alloc(extra_own, (size_t)nu * kDlMaxExtra))) { release(); return fail(ctx, DSC_ERR_ALLOC, cudaGetErrorString(e)); }
+            list = list_own; extra = extra_own;
+        }
         CK(cudaMemsetAsync(nextra, 0, sizeof(int) * n, ctx->stream));
         delaunay_compact_kernel<<<nbv, kThreads, 0, ctx->stream>>>(n, isu, pos, list, slot);
         delaunay_extra_kernel<<<nbv, kThreads, 0, ctx->stream>>>(n, star, deg, flag, slot, extra, nextra);
@@ -1070,7 +1109,7 @@ static int delaunay_build_device(dsc_ctx* ctx, int n, const float* dX, double mi
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->dl_ntri = (long long)host_sum(ctx->h_pinned, nbv, 2, 0);
     ctx->dl_area = host_sum(ctx->h_pinned, nbv, 2, 1);
-    if ((e = dev_alloc(ctx->dl_col, (size_t)std::max(E, 1))) || (e = dev_alloc(ctx->dl_w, (size_t)std::max(E, 1)))) { release(); return fail(ctx, DSC_ERR_ALLOC, cudaGetErrorString(e)); }
+    if ((size_t)E > 6 * ctx->dl_cap) { release(); return fail(ctx, DSC_ERR_GRAPH, "Delaunay: more than 6 n directed edges (not a planar mesh)"); }
     delaunay_edges_kernel<<<nbv, kThreads, 0, ctx->stream>>>(n, dX, star, deg, min_weight, 1, ctx->dl_rowptr, nullptr, ctx->dl_col, ctx->dl_w, nullptr);
     ctx->launches++;
     CK(cudaGetLastError());
@@ -1085,14 +1124,13 @@ extern "C" int dsc_delaunay_build(dsc_ctx* ctx, int n, const float* X, double mi
                                   long long* n_second_pass) {
     if (!ctx || n < 0 || (n > 0 && !X)) return fail(ctx, DSC_ERR_INVALID_ARG, "dsc_delaunay_build");
     CK(cudaSetDevice(ctx->device));
-    float* dX = nullptr;
-    if (n > 0) {
-        CK(cudaMalloc(reinterpret_cast<void**>(&dX), sizeof(float) * 3 * (size_t)n));
-        int rc = h2d(ctx, dX, X, sizeof(float) * 3 * (size_t)n);
-        if (rc) { cudaFree(dX); return rc; }
+    if (n > 0 && (size_t)n > ctx->dl_xcap) {                    // grow-only staging of the caller's points
+        ctx->dl_xcap = 0;
+        CK(dev_alloc(ctx->dl_X, 3 * ((size_t)n + (size_t)n / 8 + 16)));
+        ctx->dl_xcap = (size_t)n + (size_t)n / 8 + 16;
     }
-    int rc = delaunay_build_device(ctx, n, dX, min_weight);
-    if (dX) cudaFree(dX);
+    if (n > 0) { int rc = h2d(ctx, ctx->dl_X, X, sizeof(float) * 3 * (size_t)n); if (rc) return rc; }
+    int rc = delaunay_build_device(ctx, n, ctx->dl_X, min_weight);
     if (rc) return rc;
     if (n_edges) *n_edges = ctx->dl_E;
     if (n_triangles) *n_triangles = ctx->dl_ntri;
@@ -2043,17 +2081,24 @@ extern "C" int dsc_profile_triangulate(dsc_ctx* ctx, const dsc_tri_params* prm, 
 extern "C" int dsc_knn_build(dsc_ctx* ctx, int n, const float* X, int k, long long* n_edges) {
     if (!ctx || n < 0 || (n > 0 && !X) || k < 1 || k > kKnnMax) return fail(ctx, DSC_ERR_INVALID_ARG, "dsc_knn_build");
     CK(cudaSetDevice(ctx->device));
-    dev_free(ctx->knn_rowptr); dev_free(ctx->knn_col);
     ctx->knn_n = n; ctx->knn_E = 0;
     if (n_edges) *n_edges = 0;
-    CK(dev_alloc(ctx->knn_rowptr, (size_t)n + 1));
+    if (!ctx->knn_rowptr || (size_t)n > ctx->knn_cap_n) {
+        const size_t cap = (size_t)n + (size_t)n / 8 + 16;
+        ctx->knn_cap_n = 0;
+        CK(dev_alloc(ctx->knn_rowptr, cap + 1));
+        ctx->knn_cap_n = cap;
+    }
     if (n == 0) { CK(cudaMemset(ctx->knn_rowptr, 0, sizeof(int))); return DSC_OK; }
     double x0 = 1e300, x1 = -1e300, y0 = 1e300, y1 = -1e300;
+    int bad = 0;
+#pragma omp parallel for reduction(min : x0, y0) reduction(max : x1, y1) reduction(| : bad) schedule(static)
     for (int i = 0; i < n; ++i) {
         double x = X[3 * (size_t)i], y = X[3 * (size_t)i + 1];
-        if (!std::isfinite(x) || !std::isfinite(y)) return fail(ctx, DSC_ERR_INVALID_ARG, "dsc_knn_build: non-finite coordinate");
+        if (!std::isfinite(x) || !std::isfinite(y)) { bad |= 1; continue; }
         x0 = std::min(x0, x); x1 = std::max(x1, x); y0 = std::min(y0, y); y1 = std::max(y1, y);
     }
+    if (bad) return fail(ctx, DSC_ERR_INVALID_ARG, "dsc_knn_build: non-finite coordinate");
     double w = x1 - x0, h = y1 - y0;
     KnnGrid g{x0, y0, 1.0, 1, 1};
     if (w > 0 || h > 0) {
@@ -2064,9 +2109,18 @@ extern "C" int dsc_knn_build(dsc_ctx* ctx, int n, const float* X, int k, long lo
         g.ny = std::max(1, (int)std::ceil(h / cell) + 1);
     }
     int ncells = g.nx * g.ny;
-    float* dX = nullptr;
-    int *cell = nullptr, *cnt = nullptr, *start = nullptr, *cursor = nullptr, *order = nullptr, *nbr = nullptr, *sums = nullptr, *deg = nullptr;
-    auto release = [&]() { dev_free(dX); dev_free(cell); dev_free(cnt); dev_free(start); dev_free(cursor); dev_free(order); dev_free(nbr); dev_free(sums); dev_free(deg); };
+    auto release = [&]() {};
+    int m = std::max(ncells, n) + 1;
+    const size_t nsums = (size_t)(m / kScanBlock + 2);
+    {
+        size_t need = ws_round(sizeof(float) * 3 * (size_t)n);
+        for (size_t c : {(size_t)n, (size_t)m, (size_t)m, (size_t)m, (size_t)n, (size_t)n * k, nsums, (size_t)n + 1}) need += ws_round(c * sizeof(int));
+        cudaError_t e = ws_begin(ctx, need);
+        if (e != cudaSuccess) return fail(ctx, DSC_ERR_ALLOC, cudaGetErrorString(e));
+    }
+    float* dX = ws_take<float>(ctx, 3 * (size_t)n);
+    int *cell = ws_take<int>(ctx, n), *cnt = ws_take<int>(ctx, m), *start = ws_take<int>(ctx, m), *cursor = ws_take<int>(ctx, m), *order = ws_take<int>(ctx, n),
+        *nbr = ws_take<int>(ctx, (size_t)n * k), *sums = ws_take<int>(ctx, nsums), *deg = ws_take<int>(ctx, (size_t)n + 1);
     auto scan = [&](int m, const int* in, int* out) -> int {      // exclusive scan of m ints
         int nb = (m + kScanBlock - 1) / kScanBlock;
         scan_block_kernel<<<nb, kScanBlock, 0, ctx->stream>>>(m, in, out, sums);
@@ -2075,16 +2129,9 @@ extern "C" int dsc_knn_build(dsc_ctx* ctx, int n, const float* X, int k, long lo
         ctx->launches += 3;
         return DSC_OK;
     };
-    int m = std::max(ncells, n) + 1;
     cudaError_t e = cudaSuccess;
-    if ((e = dev_alloc(dX, 3 * (size_t)n)) || (e = dev_alloc(cell, (size_t)n)) || (e = dev_alloc(cnt, (size_t)m)) || (e = dev_alloc(start, (size_t)m)) ||
-        (e = dev_alloc(cursor, (size_t)m)) || (e = dev_alloc(order, (size_t)n)) || (e = dev_alloc(nbr, (size_t)n * k)) ||
-        (e = dev_alloc(sums, (size_t)(m / kScanBlock + 2))) || (e = dev_alloc(deg, (size_t)n + 1))) {
-        release();
-        return fail(ctx, DSC_ERR_ALLOC, cudaGetErrorString(e));
-    }
     int nbt = grid_threads(ctx, n);
-    CK(cudaMemcpyAsync(dX, X, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, ctx->stream));
+    { int rc = h2d(ctx, dX, X, sizeof(float) * 3 * (size_t)n); if (rc) return rc; }
     CK(cudaMemsetAsync(cnt, 0, sizeof(int) * m, ctx->stream));
     CK(cudaMemsetAsync(cursor, 0, sizeof(int) * m, ctx->stream));
     knn_cell_kernel<<<nbt, kThreads, 0, ctx->stream>>>(n, dX, g, cell, cnt);
@@ -2099,7 +2146,12 @@ extern "C" int dsc_knn_build(dsc_ctx* ctx, int n, const float* X, int k, long lo
     int E = 0;
     CK(cudaMemcpyAsync(&E, ctx->knn_rowptr + n, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    if ((e = dev_alloc(ctx->knn_col, (size_t)std::max(E, 1)))) { release(); return fail(ctx, DSC_ERR_ALLOC, cudaGetErrorString(e)); }
+    if (!ctx->knn_col || (size_t)E > ctx->knn_cap_e) {
+        const size_t cap = (size_t)E + (size_t)E / 8 + 16;
+        ctx->knn_cap_e = 0;
+        if ((e = dev_alloc(ctx->knn_col, cap))) { release(); return fail(ctx, DSC_ERR_ALLOC, cudaGetErrorString(e)); }
+        ctx->knn_cap_e = cap;
+    }
     CK(cudaMemsetAsync(cursor, 0, sizeof(int) * m, ctx->stream));
     knn_fill_kernel<<<nbt, kThreads, 0, ctx->stream>>>(n, k, nbr, ctx->knn_rowptr, cursor, ctx->knn_col);
     knn_sortrows_kernel<<<nbt, kThreads, 0, ctx->stream>>>(n, ctx->knn_rowptr, ctx->knn_col);
@@ -2132,6 +2184,7 @@ struct dsc_batch {
     std::string err;
     std::vector<dsc_ctx*> ctxs;              // grown on demand, reused between uploads
     int n_problems = 0;
+    int n_active = -1;                       // dsc_batch_set_active: the launch refines pairs [0, n_active) (-1: all)
     std::vector<long long> point_offset;
     BatchProblem* d_probs = nullptr; BatchIterRec* d_recs = nullptr; BatchResult* d_res = nullptr; int* d_queue = nullptr;
     double* d_part = nullptr;                // per problem: [kBatchPartStride] linearisation / trial partials
@@ -2149,6 +2202,7 @@ int bfail(dsc_batch* b, int code, const std::string& what) {
     if (b) b->err = std::string(status_str(code)) + ": " + what;
     return code;
 }
+int batch_active(const dsc_batch* b) { return b->n_active >= 0 ? std::min(b->n_active, b->n_problems) : b->n_problems; }
 #define BCK(call)                                                                              \
     do {                                                                                       \
         cudaError_t e_ = (call);                                                               \
@@ -2262,12 +2316,30 @@ extern "C" int dsc_batch_upload(dsc_batch* bt, int n_problems, const dsc_batch_p
     }
     for (int p = 0; p < n_problems; ++p) BCK(cudaStreamSynchronize(bt->ctxs[p]->stream));
     bt->n_problems = n_problems;
+    bt->n_active = -1;
+    return DSC_OK;
+}
+
+extern "C" int dsc_batch_set_active(dsc_batch* bt, int n_active) {
+    if (!bt) return DSC_ERR_INVALID_ARG;
+    bt->n_active = n_active;
+    return DSC_OK;
+}
+
+// calculatePixelsStandDev of every active pair (the weight search's objective): sigma[p][2]
+extern "C" int dsc_batch_pixel_sigma(dsc_batch* bt, double* sigma) {
+    if (!bt || !sigma) return DSC_ERR_INVALID_ARG;
+    const int np = batch_active(bt);
+    for (int p = 0; p < np; ++p) {
+        int st = dsc_pixel_sigma(bt->ctxs[p], sigma + 2 * (size_t)p);
+        if (st) return bfail(bt, st, bt->ctxs[p]->err);
+    }
     return DSC_OK;
 }
 
 extern "C" int dsc_batch_reset_state(dsc_batch* bt) {
     if (!bt) return DSC_ERR_INVALID_ARG;
-    for (int p = 0; p < bt->n_problems; ++p) {
+    for (int p = 0; p < batch_active(bt); ++p) {
         int st = dsc_reset_state(bt->ctxs[p]);
         if (st) return bfail(bt, st, bt->ctxs[p]->err);
     }
@@ -2276,10 +2348,11 @@ extern "C" int dsc_batch_reset_state(dsc_batch* bt) {
 
 extern "C" int dsc_batch_optimize(dsc_batch* bt, const dsc_weights* weights, int n_weights, int n_iters, dsc_iter_record* records,
                                   dsc_opt_stats* stats, double* device_ms) {
-    if (!bt || !weights || n_iters < 0 || (n_weights != 1 && n_weights != bt->n_problems))
-        return bfail(bt, DSC_ERR_INVALID_ARG, "dsc_batch_optimize: one dsc_weights for all pairs or one per pair");
+    if (!bt) return DSC_ERR_INVALID_ARG;
+    const int np = batch_active(bt);
+    if (!weights || n_iters < 0 || (n_weights != 1 && n_weights != np && n_weights != bt->n_problems))
+        return bfail(bt, DSC_ERR_INVALID_ARG, "dsc_batch_optimize: one dsc_weights for all pairs or one per (active) pair");
     BCK(cudaSetDevice(bt->device));
-    const int np = bt->n_problems;
     if (device_ms) *device_ms = 0.0;
     if (np == 0) return DSC_OK;
     if ((size_t)np > bt->probs_cap) {

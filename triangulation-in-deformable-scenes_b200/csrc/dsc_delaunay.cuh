@@ -22,6 +22,7 @@ namespace dsc {
 constexpr int kDlMaxV = 32;                 // polygon vertices / star size a cell may reach
 constexpr int kDlRingCap = 10;              // rings of grid cells a first-pass cell may visit before it is left to pass two
 constexpr int kDlMaxExtra = 96;             // certified neighbours handed to an uncertified point
+constexpr int kDlWsSecond = 32768;          // second-pass cells the context's workspace has room for (more: allocated on the spot)
 
 struct DlCell {
     double vx[kDlMaxV], vy[kDlMaxV];        // vertices, counter-clockwise, relative to the cell's point

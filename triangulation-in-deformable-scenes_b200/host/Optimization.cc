@@ -3,6 +3,7 @@
 // happens here; there is no CPU fallback (a missing GPU throws).
 #include "Optimization.h"
 
+#include <exception>
 #include <algorithm>
 #include <array>
 #include <chrono>
@@ -106,6 +107,7 @@ struct PairProblem {
     std::vector<float> X1, X2, uv1, uv2, isg1, isg2;
     std::vector<double> d1, d2;
     dsc_host::Graph graph;
+    long long mesh_edges = -1;           // >= 0: the mesh was built on the device (graph.rowptr / col / w are empty)
     double Tg[7];
 };
 
@@ -160,24 +162,54 @@ bool gather_pair(Map* pMap, KeyFrame_ pKF1, ID kf1ID, KeyFrame_ pKF2, ID kf2ID, 
     auto& v1 = pKF1->getMapPoints();
     auto& v2 = pKF2->getMapPoints();
     size_t slots = std::min(v1.size(), v2.size());
-    for (size_t mpIndex = 0; mpIndex < slots; ++mpIndex) {
-        MapPoint_ a = v1[mpIndex], b = v2[mpIndex];
-        if (!a || !b) continue;                                               // :728-729
-        int i1 = pMap->isMapPointInKeyFrame(a->getId(), kf1ID);               // :765-768
-        int i2 = pMap->isMapPointInKeyFrame(b->getId(), kf2ID);
-        if (i1 < 0 || i2 < 0) continue;
-        cv::KeyPoint k1 = pKF1->getKeyPoint((size_t)i1), k2 = pKF2->getKeyPoint((size_t)i2);
-        auto p1 = a->getWorldPosition(), p2 = b->getWorldPosition();
-        pp.mp1.push_back(a); pp.mp2.push_back(b);
-        for (int k = 0; k < 3; ++k) { pp.X1.push_back(p1[k]); pp.X2.push_back(p2[k]); }
-        pp.uv1.push_back(k1.pt.x); pp.uv1.push_back(k1.pt.y);
-        pp.uv2.push_back(k2.pt.x); pp.uv2.push_back(k2.pt.y);
-        pp.isg1.push_back(pKF1->getInvSigma2(k1.octave));                     // :781
-        pp.isg2.push_back(pKF2->getInvSigma2(k2.octave));
-        // :816,846 read the depth image; simulated key frames only carry per-key-point depths
-        pp.d1.push_back(img1 ? pKF1->getDepthMeasure(k1.pt.x, k1.pt.y, false) : (double)pKF1->getDepthMeasure((size_t)i1));
-        pp.d2.push_back(img2 ? pKF2->getDepthMeasure(k2.pt.x, k2.pt.y, false) : (double)pKF2->getDepthMeasure((size_t)i2));
+    // Pass 1 (threads): which slots take part and where their observations are -- read-only look-ups in the Map.
+    // Pass 2 (threads): the SoA arrays, every correspondence at its final position (the order of the serial loop).
+    std::vector<int> o1(slots), o2(slots);
+    const long long nslots = (long long)slots;
+#pragma omp parallel for schedule(static)
+    for (long long mpIndex = 0; mpIndex < nslots; ++mpIndex) {
+        const MapPoint_& a = v1[mpIndex];
+        const MapPoint_& b = v2[mpIndex];
+        int i1 = -1, i2 = -1;
+        if (a && b) {                                                         // :728-729
+            i1 = pMap->isMapPointInKeyFrame(a->getId(), kf1ID);               // :765-768
+            i2 = pMap->isMapPointInKeyFrame(b->getId(), kf2ID);
+        }
+        o1[mpIndex] = (i1 < 0 || i2 < 0) ? -1 : i1;
+        o2[mpIndex] = i2;
     }
+    std::vector<size_t> at(slots + 1, 0);
+    for (size_t k = 0; k < slots; ++k) at[k + 1] = at[k] + (o1[k] >= 0 ? 1 : 0);
+    const size_t cnt = at[slots];
+    pp.mp1.resize(cnt); pp.mp2.resize(cnt);
+    pp.X1.resize(3 * cnt); pp.X2.resize(3 * cnt); pp.uv1.resize(2 * cnt); pp.uv2.resize(2 * cnt);
+    pp.isg1.resize(cnt); pp.isg2.resize(cnt); pp.d1.resize(cnt); pp.d2.resize(cnt);
+    std::exception_ptr thrown;
+#pragma omp parallel for schedule(static)
+    for (long long mpIndex = 0; mpIndex < nslots; ++mpIndex) {
+        if (o1[mpIndex] < 0) continue;
+        try {
+            const size_t q = at[mpIndex];
+            const int i1 = o1[mpIndex], i2 = o2[mpIndex];
+            const MapPoint_& a = v1[mpIndex];
+            const MapPoint_& b = v2[mpIndex];
+            cv::KeyPoint k1 = pKF1->getKeyPoint((size_t)i1), k2 = pKF2->getKeyPoint((size_t)i2);
+            auto p1 = a->getWorldPosition(), p2 = b->getWorldPosition();
+            pp.mp1[q] = a; pp.mp2[q] = b;
+            for (int k = 0; k < 3; ++k) { pp.X1[3 * q + k] = p1[k]; pp.X2[3 * q + k] = p2[k]; }
+            pp.uv1[2 * q] = k1.pt.x; pp.uv1[2 * q + 1] = k1.pt.y;
+            pp.uv2[2 * q] = k2.pt.x; pp.uv2[2 * q + 1] = k2.pt.y;
+            pp.isg1[q] = pKF1->getInvSigma2(k1.octave);                       // :781
+            pp.isg2[q] = pKF2->getInvSigma2(k2.octave);
+            // :816,846 read the depth image; simulated key frames only carry per-key-point depths
+            pp.d1[q] = img1 ? pKF1->getDepthMeasure(k1.pt.x, k1.pt.y, false) : (double)pKF1->getDepthMeasure((size_t)i1);
+            pp.d2[q] = img2 ? pKF2->getDepthMeasure(k2.pt.x, k2.pt.y, false) : (double)pKF2->getDepthMeasure((size_t)i2);
+        } catch (...) {
+#pragma omp critical
+            if (!thrown) thrown = std::current_exception();
+        }
+    }
+    if (thrown) std::rethrow_exception(thrown);
     int n = (int)pp.mp1.size();
     se3_to_7(pMap->getGlobalKeyFramesTransformation(kf1ID, kf2ID), pp.Tg);    // :664 (identity the first time)
     if (!with_mesh) return n > 0;
@@ -214,7 +246,10 @@ bool upload_pair(PairProblem& pp, bool with_graph = true) {
     if (!with_graph) return true;
     bool on_device = !host_mesh_forced();
     if (on_device) {
-        int st = dsc_set_graph_delaunay(c, 0.0, 1, nullptr, nullptr, nullptr);
+        long long ntri = 0, ne = 0;
+        int st = dsc_set_graph_delaunay(c, 0.0, 1, &pp.graph.area, &ntri, &ne);
+        pp.graph.n_triangles = ntri;
+        pp.mesh_edges = ne;
         if (st == DSC_ERR_GRAPH) {                         // degenerate for the device construction: the host triangulator decides
             on_device = false;
             if (!host_mesh(pp)) return false;
@@ -254,7 +289,8 @@ void write_back(Map* pMap, PairProblem& pp, double* optimizationUpdate) {
     ck(dsc_download(ctx(), X1.data(), X2.data(), nullptr, nullptr, scales, Tg, &upd), "dsc_download");
     pp.kf1->setEstimatedDepthScale(scales[0]);                                // :967-972
     pp.kf2->setEstimatedDepthScale(scales[1]);
-    for (int i = 0; i < n; ++i) {                                             // :978-990
+#pragma omp parallel for schedule(static)
+    for (int i = 0; i < n; ++i) {                                             // :978-990 (distinct MapPoints: independent writes)
         Eigen::Vector3f a(X1[3 * i], X1[3 * i + 1], X1[3 * i + 2]), b(X2[3 * i], X2[3 * i + 1], X2[3 * i + 2]);
         pp.mp1[i]->setWorldPosition(a);
         pp.mp2[i]->setWorldPosition(b);
@@ -262,8 +298,68 @@ void write_back(Map* pMap, PairProblem& pp, double* optimizationUpdate) {
     if (optimizationUpdate) *optimizationUpdate += upd;
     pMap->insertGlobalKeyFramesTransformation(0, 1, se3_from_7(Tg));          // :1007 (ids hard-coded upstream)
     g_res.valid = true; g_res.map = pMap; g_res.kf1 = pp.kf1Id; g_res.kf2 = pp.kf2Id;
-    g_res.mp1 = pp.mp1; g_res.mp2 = pp.mp2; g_res.X1 = std::move(X1); g_res.X2 = std::move(X2);
+    g_res.mp1 = std::move(pp.mp1); g_res.mp2 = std::move(pp.mp2); g_res.X1 = std::move(X1); g_res.X2 = std::move(X2);   // pp ends here
 }
+
+// The weight search's refinements on the batched path: K replicas of the gathered pair (same initial state, mesh and
+// rotations) stay resident in one dsc_batch; a Nelder-Mead step refines as many of them as it has candidate weights in
+// ONE launch and reads their pixel sigmas (nloptOptimization.cc:5-37 per candidate).  Pairs above kSearchBatchMax
+// correspondences fill the GPU on their own: they keep the sequential path on the main context.
+constexpr int kSearchReplicas = 4;
+constexpr size_t kSearchBatchMax = 32768;
+struct SearchBatch {
+    dsc_batch* bt = nullptr;
+    ~SearchBatch() { if (bt) dsc_batch_destroy(bt); }
+    void bck(int st, const char* what) { if (st != DSC_OK) throw std::runtime_error(std::string(what) + ": " + dsc_batch_last_error(bt)); }
+    void upload(PairProblem& pp) {
+        const int K = kSearchReplicas, n = (int)pp.mp1.size();
+        std::vector<int32_t> rp, col;
+        std::vector<double> w;
+        if (pp.mesh_edges >= 0) {                                   // the mesh lies on the device: fetch its CSR once
+            rp.resize((size_t)n + 1); col.resize((size_t)pp.mesh_edges); w.resize((size_t)pp.mesh_edges);
+            ck(dsc_delaunay_download(ctx(), rp.data(), col.data(), w.data()), "dsc_delaunay_download");
+        } else { rp = pp.graph.rowptr; col = pp.graph.col; w = pp.graph.w; }
+        const size_t E = col.size();
+        int dev = 0;
+        if (const char* d = std::getenv("DSC_DEVICE")) dev = std::atoi(d);
+        if (!bt && dsc_batch_create(dev, &bt) != DSC_OK) throw std::runtime_error("dsc_batch_create failed");
+        std::vector<dsc_batch_pair> pairs(K);
+        std::vector<long long> po(K + 1), eo(K + 1);
+        auto rep = [&](auto& v) { auto one = v; v.reserve(one.size() * K); for (int k = 1; k < K; ++k) v.insert(v.end(), one.begin(), one.end()); };
+        std::vector<float> X1 = pp.X1, X2 = pp.X2, uv1 = pp.uv1, uv2 = pp.uv2, i1 = pp.isg1, i2 = pp.isg2;
+        std::vector<double> d1 = pp.d1, d2 = pp.d2;
+        rep(X1); rep(X2); rep(uv1); rep(uv2); rep(i1); rep(i2); rep(d1); rep(d2); rep(rp); rep(col); rep(w);
+        for (int k = 0; k < K; ++k) {
+            pairs[k].pair = make_pair(*pp.kf1, *pp.kf2);
+            pairs[k].scale1 = pp.kf1->getEstimatedDepthScale(); pairs[k].scale2 = pp.kf2->getEstimatedDepthScale();
+            for (int q = 0; q < 7; ++q) pairs[k].Tg7[q] = pp.Tg[q];
+            pairs[k].area = pp.graph.area; pairs[k].n_triangles = pp.graph.n_triangles;
+            po[k] = (long long)k * n; eo[k] = (long long)k * (long long)E;
+        }
+        po[K] = (long long)K * n; eo[K] = (long long)K * (long long)E;
+        bck(dsc_batch_upload(bt, K, pairs.data(), po.data(), X1.data(), X2.data(), uv1.data(), uv2.data(), d1.data(), d2.data(), i1.data(), i2.data(),
+                             eo.data(), rp.data(), col.data(), w.data(), 1), "dsc_batch_upload");
+        bck(dsc_batch_set_pcg(bt, &g_pcg), "dsc_batch_set_pcg");
+        static const double rt[2] = {1e-3, 1e-4}, mg[2] = {1.0, 0.5};
+        bck(dsc_batch_set_early_reject(bt, std::getenv("DSC_NO_EARLY_REJECT") ? 0 : 2, rt, mg), "dsc_batch_set_early_reject");
+    }
+    // objective (ln sigma_C1)^2 + (ln sigma_C2)^2 of every candidate (rep, global, arap), refined together
+    std::vector<double> evaluate(const std::vector<std::vector<double>>& cand, double alpha, double beta, float depthSigma, int nIter) {
+        std::vector<double> out;
+        for (size_t at = 0; at < cand.size(); at += kSearchReplicas) {
+            const int m = (int)std::min((size_t)kSearchReplicas, cand.size() - at);
+            std::vector<dsc_weights> w(m);
+            for (int k = 0; k < m; ++k) w[k] = weights(cand[at + k][0], cand[at + k][1], cand[at + k][2], alpha, beta, depthSigma);
+            std::vector<double> sg(2 * (size_t)m);
+            bck(dsc_batch_set_active(bt, m), "dsc_batch_set_active");
+            bck(dsc_batch_reset_state(bt), "dsc_batch_reset_state");
+            bck(dsc_batch_optimize(bt, w.data(), m, nIter, nullptr, nullptr, nullptr), "dsc_batch_optimize");
+            bck(dsc_batch_pixel_sigma(bt, sg.data()), "dsc_batch_pixel_sigma");
+            for (int k = 0; k < m; ++k) out.push_back(std::pow(std::log(sg[2 * k]), 2) + std::pow(std::log(sg[2 * k + 1]), 2));
+        }
+        return out;
+    }
+};
 
 template <typename F>
 void for_each_pair(Map* pMap, F&& f) {                                        // :640-645 (pKF1 = k2, pKF2 = k1)
@@ -276,18 +372,35 @@ void for_each_pair(Map* pMap, F&& f) {                                        //
 // nlopt::opt(nlopt::LN_NELDERMEAD, 3) (g2oBundleAdjustment.cc:491-515).  NLopt is absent and unpinned; restated:
 // fixed coordinates (lb == ub) are eliminated, initial step = NLopt's default rule, standard coefficients
 // (1, 2, 0.5, 0.5), points clamped to the box, stop on xtol_rel / xtol_abs of the simplex or maxeval.
+//
+// The objective is handed over as evalMany(points) -> values: the refinements of one Nelder-Mead step are independent
+// given the same initial state, so with `speculative` the step's candidates -- reflection,
+// expansion, outside and inside contraction -- are refined TOGETHER (one launch of the batched path), and the d shrink
+// points likewise.  The decisions read the values in the order of the sequential algorithm, and only the evaluations that
+// algorithm would have made count towards maxeval and appear in `consumed`: both modes walk the same simplices.
+struct NmEval { std::vector<double> x; double f; };
 template <typename F>
 double nelder_mead(std::vector<double>& x, const std::vector<double>& lb, const std::vector<double>& ub, double xtol_rel,
-                   double xtol_abs, int maxeval, F&& f) {
+                   double xtol_abs, int maxeval, bool speculative, F&& evalMany, std::vector<NmEval>* consumed = nullptr,
+                   int* launches = nullptr) {
+    using Pt = std::vector<double>;
     std::vector<int> freeIdx;
     for (size_t i = 0; i < x.size(); ++i) if (ub[i] > lb[i]) freeIdx.push_back((int)i);
-    int evals = 0;
-    auto eval = [&](const std::vector<double>& y) { std::vector<double> full = x; for (size_t k = 0; k < freeIdx.size(); ++k) full[freeIdx[k]] = y[k]; ++evals; return f(full); };
     for (size_t i = 0; i < x.size(); ++i) x[i] = std::min(ub[i], std::max(lb[i], x[i]));
-    size_t d = freeIdx.size();
-    if (d == 0) return f(x);
-    std::vector<std::vector<double>> S(d + 1, std::vector<double>(d));
-    std::vector<double> fv(d + 1);
+    const size_t d = freeIdx.size();
+    int evals = 0, nlaunch = 0;
+    auto full = [&](const Pt& y) { Pt f = x; for (size_t k = 0; k < d; ++k) f[freeIdx[k]] = y[k]; return f; };
+    auto run = [&](const std::vector<Pt>& ys) {                // one launch: all of ys
+        std::vector<Pt> fs;
+        for (auto& y : ys) fs.push_back(full(y));
+        ++nlaunch;
+        return evalMany(fs);
+    };
+    auto consume = [&](const Pt& y, double f) { ++evals; if (consumed) consumed->push_back({full(y), f}); return f; };
+    const double inf = std::numeric_limits<double>::infinity();
+    if (d == 0) { double f = run({Pt{}})[0]; consume(Pt{}, f); if (launches) *launches = nlaunch; return f; }
+    std::vector<Pt> S(d + 1, Pt(d));
+    std::vector<double> fv(d + 1, inf);
     for (size_t k = 0; k < d; ++k) S[0][k] = x[freeIdx[k]];
     for (size_t k = 0; k < d; ++k) {
         int i = freeIdx[k];
@@ -298,8 +411,13 @@ double nelder_mead(std::vector<double>& x, const std::vector<double>& lb, const 
         S[k + 1] = S[0];
         S[k + 1][k] = (S[0][k] + step <= ub[i]) ? S[0][k] + step : S[0][k] - step;
     }
-    auto clamp = [&](std::vector<double>& y) { for (size_t k = 0; k < d; ++k) y[k] = std::min(ub[freeIdx[k]], std::max(lb[freeIdx[k]], y[k])); };
-    for (size_t k = 0; k <= d && evals < maxeval; ++k) fv[k] = eval(S[k]);
+    auto clamp = [&](Pt& y) { for (size_t k = 0; k < d; ++k) y[k] = std::min(ub[freeIdx[k]], std::max(lb[freeIdx[k]], y[k])); };
+    {   // the initial simplex: d + 1 independent refinements
+        size_t m = std::min(d + 1, (size_t)std::max(0, maxeval));
+        std::vector<Pt> ys(S.begin(), S.begin() + m);
+        if (speculative) { auto f = run(ys); for (size_t k = 0; k < m; ++k) fv[k] = consume(S[k], f[k]); }
+        else for (size_t k = 0; k < m; ++k) fv[k] = consume(S[k], run({S[k]})[0]);
+    }
     while (evals < maxeval) {
         std::vector<size_t> o(d + 1);
         for (size_t k = 0; k <= d; ++k) o[k] = k;
@@ -312,30 +430,42 @@ double nelder_mead(std::vector<double>& x, const std::vector<double>& lb, const 
             if (mx - mn > xtol_abs && mx - mn > xtol_rel * std::fabs(S[lo][k])) conv = false;
         }
         if (conv) break;
-        std::vector<double> c(d, 0.0);
+        Pt c(d, 0.0);
         for (size_t j = 0; j <= d; ++j) if (j != hi) for (size_t k = 0; k < d; ++k) c[k] += S[j][k] / d;
-        auto along = [&](double t) { std::vector<double> y(d); for (size_t k = 0; k < d; ++k) y[k] = c[k] + t * (S[hi][k] - c[k]); clamp(y); return y; };
-        std::vector<double> xr = along(-1.0);
-        double fr = eval(xr);
+        auto along = [&](double t) { Pt y(d); for (size_t k = 0; k < d; ++k) y[k] = c[k] + t * (S[hi][k] - c[k]); clamp(y); return y; };
+        const Pt xr = along(-1.0), xe = along(-2.0), xco = along(-0.5), xci = along(0.5);
+        std::vector<double> spec;                                // values of {xr, xe, xco, xci} when refined together
+        if (speculative) spec = run({xr, xe, xco, xci});
+        auto value = [&](int which, const Pt& y) { return consume(y, speculative ? spec[which] : run({y})[0]); };
+        const double fr = value(0, xr);
         if (fr < fv[lo]) {
-            std::vector<double> xe = along(-2.0);
-            double fe = evals < maxeval ? eval(xe) : std::numeric_limits<double>::infinity();
+            const double fe = evals < maxeval ? value(1, xe) : inf;
             if (fe < fr) { S[hi] = xe; fv[hi] = fe; } else { S[hi] = xr; fv[hi] = fr; }
-        } else if (fr < fv[nhi] || d == 1 && fr < fv[hi]) {
+        } else if (fr < fv[nhi] || (d == 1 && fr < fv[hi])) {
             S[hi] = xr; fv[hi] = fr;
         } else {
-            std::vector<double> xc = along(fr < fv[hi] ? -0.5 : 0.5);
-            double fc = evals < maxeval ? eval(xc) : std::numeric_limits<double>::infinity();
+            const bool outside = fr < fv[hi];
+            const Pt& xc = outside ? xco : xci;
+            const double fc = evals < maxeval ? value(outside ? 2 : 3, xc) : inf;
             if (fc < std::min(fr, fv[hi])) { S[hi] = xc; fv[hi] = fc; }
-            else {
-                for (size_t j = 0; j <= d && evals < maxeval; ++j)
-                    if (j != lo) { for (size_t k = 0; k < d; ++k) S[j][k] = S[lo][k] + 0.5 * (S[j][k] - S[lo][k]); fv[j] = eval(S[j]); }
+            else {                                               // shrink towards the best vertex: d independent refinements
+                std::vector<size_t> js;
+                for (size_t j = 0; j <= d; ++j) if (j != lo) js.push_back(j);
+                size_t m = std::min(js.size(), (size_t)std::max(0, maxeval - evals));
+                for (size_t q = 0; q < m; ++q) for (size_t k = 0; k < d; ++k) S[js[q]][k] = S[lo][k] + 0.5 * (S[js[q]][k] - S[lo][k]);
+                if (speculative && m > 0) {
+                    std::vector<Pt> ys;
+                    for (size_t q = 0; q < m; ++q) ys.push_back(S[js[q]]);
+                    auto f = run(ys);
+                    for (size_t q = 0; q < m; ++q) fv[js[q]] = consume(S[js[q]], f[q]);
+                } else for (size_t q = 0; q < m; ++q) fv[js[q]] = consume(S[js[q]], run({S[js[q]]})[0]);
             }
         }
     }
     size_t best = 0;
     for (size_t k = 1; k <= d; ++k) if (fv[k] < fv[best]) best = k;
     for (size_t k = 0; k < d; ++k) x[freeIdx[k]] = S[best][k];
+    if (launches) *launches = nlaunch;
     return fv[best];
 }
 
@@ -498,9 +628,10 @@ void arapOptimization(Map* pMap, double repBalanceWeight, double globalBalanceWe
         double t2 = now_ms();
         run_lm(w, nOptIterations);
         double t3 = now_ms();
+        const long long npts = (long long)pp.mp1.size();
         write_back(pMap, pp, optimizationUpdate);
         double t4 = now_ms();
-        g_times = dsc_host::PhaseTimes{t1 - t0, t2 - t1, t3 - t2, t4 - t3, (long long)pp.mp1.size()};
+        g_times = dsc_host::PhaseTimes{t1 - t0, t2 - t1, t3 - t2, t4 - t3, npts};
     });
 }
 
@@ -543,22 +674,42 @@ void deformationOptimization(std::shared_ptr<Map> pMap, Settings& settings, std:
             std::vector<double> lb = {settings.getNloptRepLowerBound(), settings.getNloptGlobalLowerBound(), settings.getNloptArapLowerBound()};
             std::vector<double> ub = {settings.getNloptRepUpperBound(), settings.getNloptGlobalUpperBound(), settings.getNloptArapUpperBound()};
             bool uploaded = false;
+            PairProblem pp;
             for_each_pair(pMap.get(), [&](KeyFrame_ kf1, ID id1, KeyFrame_ kf2, ID id2) {
                 if (uploaded) return;
-                PairProblem pp;
-                if (!gather_pair(pMap.get(), kf1, id1, kf2, id2, pp)) return;
-                if (!upload_pair(pp)) return;
+                PairProblem cand;
+                if (!gather_pair(pMap.get(), kf1, id1, kf2, id2, cand)) return;
+                if (!upload_pair(cand)) return;
+                pp = std::move(cand);
                 uploaded = true;
             });
             if (uploaded) {
+                // DSC_WEIGHT_SEARCH=sequential: one refinement at a time; =single: additionally on the main context
+                // (the round-1 path).  Default: the step's candidates together on the batched path.
+                const char* mode = std::getenv("DSC_WEIGHT_SEARCH");
+                const bool on_batch = pp.mp1.size() <= kSearchBatchMax && !(mode && std::string(mode) == "single");
+                const bool speculative = on_batch && !(mode && std::string(mode) == "sequential");
+                SearchBatch sb;
+                if (on_batch) sb.upload(pp);
+                std::vector<NmEval> log;
+                int launches = 0;
                 double minf = nelder_mead(x, lb, ub, settings.getNloptRelTolerance(), settings.getNloptAbsTolerance(),
-                                          settings.getNloptnOptimizations(), [&](const std::vector<double>& y) {
-                                              ck(dsc_reset_state(ctx()), "dsc_reset_state");
-                                              run_lm(weights(y[0], y[1], y[2], alpha, beta, depthSigma), nOptIterations);
-                                              double s[2];
-                                              ck(dsc_pixel_sigma(ctx(), s), "dsc_pixel_sigma");
-                                              return std::pow(std::log(s[0]), 2) + std::pow(std::log(s[1]), 2);
-                                          });
+                                          settings.getNloptnOptimizations(), speculative, [&](const std::vector<std::vector<double>>& ys) {
+                                              if (on_batch) return sb.evaluate(ys, alpha, beta, depthSigma, nOptIterations);
+                                              std::vector<double> f;
+                                              for (auto& y : ys) {
+                                                  ck(dsc_reset_state(ctx()), "dsc_reset_state");
+                                                  run_lm(weights(y[0], y[1], y[2], alpha, beta, depthSigma), nOptIterations);
+                                                  double sg[2];
+                                                  ck(dsc_pixel_sigma(ctx(), sg), "dsc_pixel_sigma");
+                                                  f.push_back(std::pow(std::log(sg[0]), 2) + std::pow(std::log(sg[1]), 2));
+                                              }
+                                              return f;
+                                          }, &log, &launches);
+                for (auto& e : log)                                            // outerObjective's own lines, in its order
+                    std::cout << "Current x values. Reprojection: " << e.x[0] << ", Global T: " << e.x[1] << ", ARAP: " << e.x[2] << "\nerror: " << e.f << "\n";
+                std::cout << "Weight search: " << log.size() << " objective evaluations in " << launches << " launches ("
+                          << (speculative ? "candidates of a step refined together" : on_batch ? "one at a time, batched path" : "one at a time") << ")\n";
                 std::cout << "\nWEIGHTS OPTIMIZED\nOptimized repBalanceWeight: " << x[0] << "\nOptimized globalBalanceWeight: " << x[1]
                           << "\nOptimized arapBalanceWeight: " << x[2] << "\nFinal minimized ABSOLUTE error: " << minf << std::endl;
             }
@@ -606,4 +757,32 @@ extern "C" int dsch_mesh_graph(int n, const double* xyz, int ntri, const int* tr
     for (int e = 0; e < E && e < max_e; ++e) { col[e] = g.col[e]; w[e] = g.w[e]; }
     *area = g.area;
     return E;
+}
+
+// Nelder-Mead on analytic objectives, both ways of evaluating a step (tests/test_host_shim.py): log[k] = (x[dim], f) of the
+// k-th evaluation the sequential algorithm makes.  fn 0: sum_k (log10 x_k - (k + 1))^2;  fn 1: Rosenbrock (dim 2).
+extern "C" int dsch_nelder_mead(int fn, int dim, const double* x0, const double* lb, const double* ub, double xtol_rel, double xtol_abs,
+                                int maxeval, int speculative, double* xout, double* fout, double* log, int maxlog, int* launches) {
+    std::vector<double> x(x0, x0 + dim), l(lb, lb + dim), u(ub, ub + dim);
+    auto f = [&](const std::vector<double>& y) {
+        if (fn == 1) return 100.0 * std::pow(y[1] - y[0] * y[0], 2) + std::pow(1.0 - y[0], 2);
+        double a = 0.0;
+        for (int k = 0; k < dim; ++k) a += std::pow(std::log10(y[k]) - (k + 1), 2);
+        return a;
+    };
+    std::vector<NmEval> used;
+    int nl = 0;
+    double best = nelder_mead(x, l, u, xtol_rel, xtol_abs, maxeval, speculative != 0, [&](const std::vector<std::vector<double>>& ys) {
+        std::vector<double> v;
+        for (auto& y : ys) v.push_back(f(y));
+        return v;
+    }, &used, &nl);
+    for (int k = 0; k < dim; ++k) xout[k] = x[k];
+    *fout = best;
+    if (launches) *launches = nl;
+    for (size_t e = 0; e < used.size() && (int)e < maxlog; ++e) {
+        for (int k = 0; k < dim; ++k) log[e * (dim + 1) + k] = used[e].x[k];
+        log[e * (dim + 1) + dim] = used[e].f;
+    }
+    return (int)used.size();
 }
