@@ -1184,7 +1184,7 @@ extern "C" int dsc_compute_rotations(dsc_ctx* ctx) {
     if (!ctx->have_graph) return fail(ctx, DSC_ERR_STATE, "dsc_compute_rotations before dsc_set_graph");
     CK(cudaSetDevice(ctx->device));
     if (ctx->n > 0) {
-        rotations_ell_kernel<<<grid_tiles(ctx, ctx->n, 2), kEllThreads, kWinBytes, ctx->stream>>>(ctx->n, ctx->P, ctx->sliceptr, ctx->ecol, ctx->ewgt, ctx->Q);
+        rotations_ell_kernel<<<grid_tiles(ctx, ctx->n, DSC_ROT_BLOCKS), kEllThreads, kWinBytes, ctx->stream>>>(ctx->n, ctx->P, ctx->sliceptr, ctx->ecol, ctx->ewgt, ctx->Q);
         ctx->launches++;
         CK(cudaGetLastError());
     }
@@ -1299,9 +1299,9 @@ static int shard_check(dsc_ctx* ctx) {
 }
 
 static int eval_cost(dsc_ctx* ctx, const WeightsDev& W, const double* P, const Globals* G, double* chi2, double* parts) {
-    int nb = grid_tiles(ctx, ctx->n, 2);
+    int nb = grid_tiles(ctx, ctx->n, DSC_COST_BLOCKS);
     if (ctx->sharded) {                                  // the rank's tiles, then the totals over the ranks (one "block" of 3)
-        nb = std::max(1, std::min(shard_tile1(ctx) - shard_tile0(ctx), ctx->sms * 2));
+        nb = std::max(1, std::min(shard_tile1(ctx) - shard_tile0(ctx), ctx->sms * DSC_COST_BLOCKS));
         cost_ell_kernel<<<nb, kEllThreads, kWinBytes, ctx->stream>>>(ctx->n, P, ctx->Q, ctx->uv, ctx->dm, ctx->isg, ctx->sliceptr, ctx->ecol,
                                                                    ctx->ewgt, G, ctx->pair, W, ctx->part, shard_tile0(ctx), shard_tile1(ctx));
         shard_allreduce(ctx, SF_C, ctx->part, nb, 3, 3);
@@ -2032,7 +2032,7 @@ extern "C" int dsc_profile_kernels(dsc_ctx* ctx, const dsc_weights* w, int warm,
     });
     if (s) return s;
     s = time_it(DSC_K_COST, [&]() {
-        cost_ell_kernel<<<grid_tiles(ctx, n, 2), kEllThreads, kWinBytes, ctx->stream>>>(n, ctx->P, ctx->Q, ctx->uv, ctx->dm, ctx->isg, ctx->sliceptr, ctx->ecol,
+        cost_ell_kernel<<<grid_tiles(ctx, n, DSC_COST_BLOCKS), kEllThreads, kWinBytes, ctx->stream>>>(n, ctx->P, ctx->Q, ctx->uv, ctx->dm, ctx->isg, ctx->sliceptr, ctx->ecol,
                                                                                   ctx->ewgt, ctx->Gcur, ctx->pair, W, ctx->part, 0, -1);
     });
     if (s) return s;
@@ -2047,7 +2047,7 @@ extern "C" int dsc_profile_kernels(dsc_ctx* ctx, const dsc_weights* w, int warm,
     if (s) return s;
     double* Qtmp = ctx->vec[3];                    // scratch: do not disturb the real rotations
     s = time_it(DSC_K_ROTATIONS, [&]() {
-        rotations_ell_kernel<<<grid_tiles(ctx, n, 2), kEllThreads, kWinBytes, ctx->stream>>>(n, ctx->P, ctx->sliceptr, ctx->ecol, ctx->ewgt, Qtmp);
+        rotations_ell_kernel<<<grid_tiles(ctx, n, DSC_ROT_BLOCKS), kEllThreads, kWinBytes, ctx->stream>>>(n, ctx->P, ctx->sliceptr, ctx->ecol, ctx->ewgt, Qtmp);
     });
     if (s) return s;
     if (bytes) for (int k = 0; k < DSC_K_COUNT; ++k) bytes[k] = by[k];

@@ -66,7 +66,13 @@ DSC_D void warp_accumulate(const double (&v)[K], double* wacc) {
 }
 
 // ------------------------------------------------------------------ K7 computeR (Geometry.cc:549-604)
-__global__ void __launch_bounds__(kEllThreads, 2)
+#ifndef DSC_ROT_BLOCKS
+#define DSC_ROT_BLOCKS 3      // 78 registers: three blocks per SM (measured: 204 -> 162 us at 1M; four spill)
+#endif
+#ifndef DSC_COST_BLOCKS
+#define DSC_COST_BLOCKS 2     // (three: 185 -> 169 us at 1M but 28 -> 31 us at 100k; four spill)
+#endif
+__global__ void __launch_bounds__(kEllThreads, DSC_ROT_BLOCKS)
 rotations_ell_kernel(int n, const double* __restrict__ P, const int* __restrict__ sliceptr, const int* __restrict__ ecol,
                      const double* __restrict__ ewgt, double* __restrict__ Q) {
     extern __shared__ double4 sw[];
@@ -176,7 +182,7 @@ DSC_D void cost_tiles(int first, int stride, int n, const double* __restrict__ P
     }
     __syncthreads();
 }
-__global__ void __launch_bounds__(kEllThreads, 2)
+__global__ void __launch_bounds__(kEllThreads, DSC_COST_BLOCKS)
 cost_ell_kernel(int n, const double* __restrict__ P, const double* __restrict__ Q, const float4* __restrict__ uv,
                 const double2* __restrict__ dm, const float2* __restrict__ isg, const int* __restrict__ sliceptr,
                 const int* __restrict__ ecol, const double* __restrict__ ewgt, const Globals* __restrict__ Gp,
