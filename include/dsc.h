@@ -308,6 +308,31 @@ int  dsc_batch_download(dsc_batch* batch, float* X1, float* X2, double* scales, 
 /* pairs uploaded, their correspondences, CTAs per cluster and clusters of the last launch */
 int  dsc_batch_size(const dsc_batch* batch, int* n_problems, long long* n_points, int* cluster_ctas, int* clusters);
 
+/* ---- classic bundle adjustment: bundleAdjustment / poseOnlyOptimization / localBundleAdjustment of
+ * Modules/Optimization/g2oBundleAdjustment.cc:38-444 -- key-frame poses (g2o::VertexSE3Expmap, Tcw), map points
+ * (VertexSBAPointXYZ, marginalised: BlockSolver_6_3) and reprojection edges (EdgeSE3ProjectXYZ / ...OnlyPose, g2oTypes.h:150-228)
+ * with information invSigma2 * I and an optional Huber kernel.  Levenberg-Marquardt as g2o runs it; the points are
+ * eliminated by a Schur complement summed on the device, the reduced camera system (6 x free poses) is factorised on the
+ * host.  poses7: [n_poses][7] = unit quaternion (x y z w) + translation of Tcw; pose_fixed: setFixed(true) (key frame id 0,
+ * the fixed key frames of the local map); points_fixed != 0: the points are constants of the edges (pose-only).
+ *   dsc_ba_set_levels   active[n_obs] != 0: edge at level 0 (optimised), 0: level 1 (left out); NULL = all at level 0
+ *   dsc_ba_optimize     optimizer.optimize(n_iters); huber_delta <= 0: no robust kernel (setRobustKernel(0))
+ *   dsc_ba_edge_chi2    e->chi2() and e->isDepthPositive() of every edge at the current estimate (any level)
+ *   dsc_ba_set_poses    setEstimate of every pose (poseOnlyOptimization restarts each round from the frame's pose) */
+typedef struct dsc_ba dsc_ba;
+int  dsc_ba_create(int device, dsc_ba** out);
+void dsc_ba_destroy(dsc_ba* ba);
+const char* dsc_ba_last_error(const dsc_ba* ba);
+int  dsc_ba_upload(dsc_ba* ba, int n_poses, const double* poses7, const uint8_t* pose_fixed, const dsc_camera* cams, int n_points,
+                   const double* X, int points_fixed, long long n_obs, const int32_t* obs_pose, const int32_t* obs_point,
+                   const float* obs_uv, const float* obs_inv_sigma2);
+int  dsc_ba_set_poses(dsc_ba* ba, const double* poses7);
+int  dsc_ba_set_levels(dsc_ba* ba, const uint8_t* active);
+int  dsc_ba_optimize(dsc_ba* ba, int n_iters, double huber_delta, dsc_iter_record* records, dsc_opt_stats* stats);
+int  dsc_ba_edge_chi2(dsc_ba* ba, double* chi2, uint8_t* depth_positive);
+int  dsc_ba_download(dsc_ba* ba, double* poses7, double* X);
+int  dsc_ba_launch_count(const dsc_ba* ba, long long* count);
+
 /* ---- ONE frame pair over several GPUs (second row: "point-sharded edge evaluation with an allreduce of
  * the small reduced system over NVLink"; the graph it partitions is the one of g2oBundleAdjustment.cc:883-953) ------------
  * One process per GPU, one context per process.  Every rank uploads the SAME pair and graph and calls the SAME sequence

@@ -6,4 +6,4 @@ optimisation-call API).  `binding` is the ctypes face used by tests/ and bench.p
 The directory name is not a Python identifier; load it with `__graft_entry__.package()`.
 """
 from . import binding  # noqa: F401
-from .binding import Context, Batch, pin_host, unpin_host, make_pair, make_weights, load_library, DscError, shard_partition  # noqa: F401
+from .binding import Context, Batch, BundleAdjuster, pin_host, unpin_host, make_pair, make_weights, load_library, DscError, shard_partition  # noqa: F401

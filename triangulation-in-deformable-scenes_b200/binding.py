@@ -29,6 +29,8 @@ EXPORTS = [
     "dsc_shard_init", "dsc_shard_attach", "dsc_shard_partition", "dsc_shard_info",
     "dsc_debug_linearize", "dsc_debug_matvec", "dsc_profile_kernels", "dsc_profile_triangulate", "dsc_problem_size", "dsc_knn_build", "dsc_knn_download",
     "dsc_delaunay_build", "dsc_delaunay_download", "dsc_set_graph_delaunay",
+    "dsc_ba_create", "dsc_ba_destroy", "dsc_ba_last_error", "dsc_ba_upload", "dsc_ba_set_poses", "dsc_ba_set_levels", "dsc_ba_optimize",
+    "dsc_ba_edge_chi2", "dsc_ba_download", "dsc_ba_launch_count",
 ]
 KERNEL_NAMES = ["cg_spmv", "cg_update", "linearize", "cost", "precond", "apply_update", "rotations"]
 
@@ -95,6 +97,8 @@ def load_library(path=None):
     lib.dsc_destroy.restype = None
     lib.dsc_batch_last_error.restype = C.c_char_p
     lib.dsc_batch_destroy.restype = None
+    lib.dsc_ba_last_error.restype = C.c_char_p
+    lib.dsc_ba_destroy.restype = None
     _lib = lib
     return lib
 
@@ -560,3 +564,83 @@ class Batch:
         a, b, c, d = C.c_int(), C.c_longlong(), C.c_int(), C.c_int()
         self._ck(self.lib.dsc_batch_size(self.h, C.byref(a), C.byref(b), C.byref(c), C.byref(d)))
         return dict(problems=a.value, points=b.value, cluster_ctas=c.value, clusters=d.value)
+
+
+class BundleAdjuster:
+    """dsc_ba_*: the classic bundle-adjustment paths (g2oBundleAdjustment.cc:38-444) -- poses, points, reprojection edges."""
+
+    def __init__(self, device=0):
+        self.lib = load_library()
+        self.h = C.c_void_p()
+        st = self.lib.dsc_ba_create(int(device), C.byref(self.h))
+        if st != 0:
+            raise DscError(st, self.lib.dsc_status_string(st).decode())
+        self.K = self.M = self.O = 0
+
+    def close(self):
+        if self.h:
+            self.lib.dsc_ba_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, st):
+        if st != 0:
+            raise DscError(st, self.lib.dsc_ba_last_error(self.h).decode())
+
+    def upload(self, poses7, pose_fixed, cams, X, obs_pose, obs_point, obs_uv, obs_isg=None, points_fixed=False):
+        """poses7 (K,7) q xyzw + t of Tcw; cams: list of (model, params[8]); X (M,3); observations (pose, point, uv, invSigma2)"""
+        p7 = np.ascontiguousarray(poses7, np.float64).reshape(-1, 7)
+        self.K, X = len(p7), np.ascontiguousarray(X, np.float64).reshape(-1, 3)
+        self.M = len(X)
+        fx = np.ascontiguousarray(np.asarray(pose_fixed, bool).astype(np.uint8))
+        carr = (Camera * self.K)()
+        for k, (model, params) in enumerate(cams):
+            carr[k].model = int(model)
+            for q in range(8):
+                carr[k].params[q] = float(params[q])
+        op, oj = np.ascontiguousarray(obs_pose, np.int32), np.ascontiguousarray(obs_point, np.int32)
+        uv = np.ascontiguousarray(obs_uv, np.float32).reshape(-1, 2)
+        isg = None if obs_isg is None else np.ascontiguousarray(obs_isg, np.float32)
+        self.O = len(op)
+        self._ck(self.lib.dsc_ba_upload(self.h, self.K, _fp(p7), _fp(fx), carr, self.M, _fp(X), int(bool(points_fixed)), C.c_longlong(self.O),
+                                        _fp(op), _fp(oj), _fp(uv), _fp(isg)))
+
+    def set_poses(self, poses7):
+        p7 = np.ascontiguousarray(poses7, np.float64).reshape(-1, 7)
+        self._ck(self.lib.dsc_ba_set_poses(self.h, _fp(p7)))
+
+    def set_levels(self, active=None):
+        a = None if active is None else np.ascontiguousarray(np.asarray(active, bool).astype(np.uint8))
+        self._ck(self.lib.dsc_ba_set_levels(self.h, _fp(a)))
+
+    def optimize(self, n_iters, huber_delta=0.0):
+        recs = (IterRecord * max(1, n_iters))()
+        st = OptStats()
+        self._ck(self.lib.dsc_ba_optimize(self.h, int(n_iters), C.c_double(huber_delta), recs, C.byref(st)))
+        return [recs[i] for i in range(st.iterations)], st
+
+    def edge_chi2(self):
+        chi2, pos = np.empty(max(1, self.O)), np.empty(max(1, self.O), np.uint8)
+        self._ck(self.lib.dsc_ba_edge_chi2(self.h, _fp(chi2), _fp(pos)))
+        return chi2[:self.O], pos[:self.O].astype(bool)
+
+    def download(self):
+        p7, X = np.empty((self.K, 7)), np.empty((max(1, self.M), 3))
+        self._ck(self.lib.dsc_ba_download(self.h, _fp(p7), _fp(X)))
+        return p7, X[:self.M]
+
+    def launch_count(self):
+        c = C.c_longlong()
+        self._ck(self.lib.dsc_ba_launch_count(self.h, C.byref(c)))
+        return c.value

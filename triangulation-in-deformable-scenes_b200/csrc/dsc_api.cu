@@ -2446,3 +2446,6 @@ extern "C" int dsc_batch_download(dsc_batch* bt, float* X1, float* X2, double* s
     }
     return DSC_OK;
 }
+
+// ------------------------------------------------------------------ classic bundle adjustment (include/dsc.h: dsc_ba_*)
+#include "dsc_ba_api.cuh"
