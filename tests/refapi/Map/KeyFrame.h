@@ -15,6 +15,7 @@
 class KeyFrame {
 public:
     Sophus::SE3f getPose();
+    void setPose(Sophus::SE3f& Tcw);
     cv::KeyPoint getKeyPoint(size_t idx);
     std::vector<cv::KeyPoint>& getKeyPoints();
     std::vector<float>& getDepthMeasurements();

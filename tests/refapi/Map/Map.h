@@ -5,6 +5,7 @@
 // does not declare fails that build.
 #pragma once
 #include <memory>
+#include <set>
 #include <unordered_map>
 #include "Map/KeyFrame.h"
 #include "Map/MapPoint.h"
@@ -14,7 +15,11 @@ typedef long unsigned int ID;
 class Map {
 public:
     void insertMapPoint(std::shared_ptr<MapPoint> pMP);
+    std::shared_ptr<KeyFrame> getKeyFrame(ID id);
     void addObservation(ID kfId, ID mpId, size_t idx);
+    void removeObservation(ID kfId, ID mpId);
+    void getLocalMapOfKeyFrame(ID kfId, std::set<ID>& sLocalMapPointsIds, std::set<ID>& sLocalKeyFramesIds, std::set<ID>& sLocalFixedKeyFramesIds);
+    void checkKeyFrame(ID kfId);
     std::unordered_map<ID,std::shared_ptr<MapPoint>>& getMapPoints();
     std::unordered_map<ID,std::shared_ptr<KeyFrame>>& getKeyFrames();
     int isMapPointInKeyFrame(ID mp, ID kf);

@@ -163,3 +163,79 @@ def test_bundle_adjustment_two_views_200k_points(pkg):
         assert all(b2 <= a * (1 + 1e-12) for a, b2 in zip(chi, chi[1:])) and chi[-1] < 0.5 * chi[0]
         print(f"[ba 200k points, 2 views, {len(p.obs_pose)} observations] 10 LM iterations {ms:.1f} ms ({st.device_ms:.1f} ms on the device), "
               f"{st.total_trials} trials, {st.kernel_launches} launches, chi2 {chi[0]:.4e} -> {chi[-1]:.4e}")
+
+
+# ---------------------------------------------------------------- the reference's entry points through the C++ shim
+def _shim_flow(mode, p, octave, curr=0, min_common=0.0):
+    import ctypes
+    import os
+    import __graft_entry__ as g
+    lib_dir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "triangulation-in-deformable-scenes_b200", "lib")
+    g.build()
+    ctypes.CDLL(os.path.join(lib_dir, "libdsc_b200.so"), mode=ctypes.RTLD_GLOBAL)
+    lib = ctypes.CDLL(os.path.join(lib_dir, "libdsc_host.so"))
+    K, M, O = len(p.poses), len(p.X), len(p.obs_pose)
+    pose34 = np.zeros((K, 12), np.float32)
+    for k, T in enumerate(p.poses):
+        pose34[k] = np.concatenate([T.R(), T.t[:, None]], 1).astype(np.float32).reshape(-1)
+    ptr = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    cam8 = np.ascontiguousarray(p.cams[0][1], np.float32)
+    X = np.ascontiguousarray(p.X, np.float32)
+    op, oj = np.ascontiguousarray(p.obs_pose, np.int32), np.ascontiguousarray(p.obs_point, np.int32)
+    uv, oc = np.ascontiguousarray(p.obs_uv, np.float32), np.ascontiguousarray(octave, np.int32)
+    p7, Xo, rem, ng = np.zeros((K, 7)), np.zeros((M, 3), np.float32), np.zeros(O, np.uint8), ctypes.c_int()
+    rc = lib.dsch_ba_flow(mode, K, ptr(pose34), ptr(cam8), M, ptr(X), O, ptr(op), ptr(oj), ptr(uv), ptr(oc), curr, ctypes.c_float(min_common),
+                          ptr(p7), ptr(Xo), ptr(rem), ctypes.byref(ng))
+    assert rc == 0
+    return p7, Xo, rem.astype(bool), ng.value
+
+
+def _as_the_map_holds_it(p):
+    """the Map stores float poses and float points, g2o starts from their casts: the oracle gets the same starting values"""
+    from oracle.f32 import Pose
+    from oracle.se3 import SE3
+    octave = np.where(np.isclose(p.obs_isg, 1.0), 0, 1)
+    isg = np.where(octave == 0, np.float32(1.0), np.float32(1.0) / (np.float32(1.2) * np.float32(1.2))).astype(np.float64)
+    poses = [SE3.from_pose32(Pose(T.R().astype(np.float32), T.t.astype(np.float32))) for T in p.poses]
+    q = oba.BaProblem(poses=poses, pose_fixed=p.pose_fixed, cams=p.cams, X=p.X.astype(np.float32).astype(np.float64), obs_pose=p.obs_pose,
+                      obs_point=p.obs_point, obs_uv=p.obs_uv, obs_isg=isg, points_fixed=p.points_fixed)
+    return q, octave
+
+
+def test_shim_bundle_adjustment_and_local_bundle_adjustment(pkg):
+    """bundleAdjustment(Map*) and localBundleAdjustment(Map*, id) of host/Optimization.cc on a Map of 4 key frames: poses (written
+    back as float), points (float) and the observations taken out of the map against the oracle's flows"""
+    p, octave = _as_the_map_holds_it(oba.make_scene(350, 4, seed=13, outliers=20))
+    def same_up_to_scale(p7, X, oposes, oX):
+        # only key frame 0 is fixed: the scale of a monocular reconstruction is a gauge freedom along which 20 LM iterations
+        # drift by a factor that depends on the last bits -- rotations, and translations / points after normalising the scale
+        s, so = np.linalg.norm(X - X.mean(0)), np.linalg.norm(oX - oX.mean(0))
+        np.testing.assert_allclose(X / s, oX / so, rtol=0, atol=2e-4)
+        for k, T in enumerate(oposes):
+            np.testing.assert_allclose(p7[k][:4], T.as7()[:4], rtol=0, atol=2e-4)
+            np.testing.assert_allclose(p7[k][4:] / s, T.as7()[4:] / so, rtol=0, atol=2e-4)
+    oposes, oX, otr = oba.bundle_adjustment(p)
+    p7, X, removed, _ = _shim_flow(0, p, octave)
+    assert not removed.any()
+    same_up_to_scale(p7, X, oposes, oX)
+    # local map of key frame 1: every key frame shares points with it, so all four are local (none fixed but key frame 0)
+    oposes, oX, oremoved, _ = oba.local_bundle_adjustment(p)
+    p7, X, removed, _ = _shim_flow(1, p, octave, curr=1, min_common=0.0)
+    assert np.array_equal(removed, oremoved) and removed.sum() >= 20
+    same_up_to_scale(p7, X, oposes, oX)
+
+
+def test_shim_pose_only_optimization(pkg):
+    s = oba.make_scene(300, 2, seed=17, outliers=0, point_noise=0.0002)
+    m = s.obs_pose == 1
+    uv = s.obs_uv[m].copy()
+    rng = np.random.default_rng(1)
+    bad = rng.choice(len(uv), 35, replace=False)
+    uv[bad] += rng.normal(0, 30.0, (35, 2)).astype(np.float32)
+    p = oba.BaProblem(poses=[s.poses[1]], pose_fixed=np.array([False]), cams=[s.cams[1]], X=s.X[s.obs_point[m]], obs_pose=np.zeros(m.sum(), int),
+                      obs_point=np.arange(m.sum()), obs_uv=uv, obs_isg=s.obs_isg[m], points_fixed=True)
+    p, octave = _as_the_map_holds_it(p)
+    opose, oinl, ongood = oba.pose_only_optimization(p)
+    p7, _, removed, ngood = _shim_flow(2, p, octave)
+    assert ngood == ongood and np.array_equal(~removed, oinl) and 250 <= ngood <= 270
+    np.testing.assert_allclose(p7[0], opose.as7(), rtol=0, atol=1e-5)

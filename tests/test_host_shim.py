@@ -301,7 +301,7 @@ def test_refapi_declarations_are_the_references_own():
     def norm(s):
         return re.sub(r"\s+", " ", s).strip()
     checked = 0
-    for sub in ("Map", "Calibration", "System", "Utils", "Visualization"):
+    for sub in ("Map", "Mapping", "Calibration", "System", "Utils", "Visualization"):
         for f in sorted(os.listdir(os.path.join(REFAPI, sub))):
             ref = open(os.path.join(REF_MODULES, sub, f)).read()
             ref_lines = {norm(l) for l in ref.splitlines()}

@@ -3,6 +3,7 @@
 //   Modules/Map/MapPoint.h, Modules/Map/KeyFrame.h:29-233, Modules/Map/Map.h:38-224 (+ Map.cc:30-58,257-264,323-343)
 // Image-side members (descriptors, grids, pyramids' images, covisibility) are out of scope.
 #pragma once
+#include <set>
 #include <cmath>
 #include <memory>
 #include <stdexcept>
@@ -91,6 +92,7 @@ public:
     Eigen::Vector3f getWorldPosition() { return position3D_; }
     void setWorldPosition(Eigen::Vector3f& p3d) { position3D_ = p3d; }
     long unsigned int getId() { return id_; }
+    static void restartIds() { nNextId_ = 0; }          // (tests: the ids of a fresh process)
 private:
     Eigen::Vector3f position3D_;
     long unsigned int id_;
@@ -149,6 +151,7 @@ public:
     float getInvSigma2(int octave) { return vInvSigma2_[octave]; }
     int getNumberOfScales() { return (int)vInvSigma2_.size(); }
     void setInitialDepthScaleInSimulationImages();      // KeyFrame.cc:131-153 (runs on the GPU, see Optimization.cc)
+    static void restartIds() { nNextId_ = 0; }          // (tests: the ids of a fresh process -- key frame 0 is the fixed one)
 private:
     std::vector<cv::KeyPoint> vKeys_;
     std::vector<MapPoint_> vMapPoints_;
@@ -173,7 +176,36 @@ public:
     void insertKeyFrame(KeyFrame_ pKF) { mKeyFrames_[pKF->getId()] = pKF; }
     KeyFrame_ getKeyFrame(ID id) { auto it = mKeyFrames_.find(id); return it == mKeyFrames_.end() ? nullptr : it->second; }
     MapPoint_ getMapPoint(ID id) { auto it = mMapPoints_.find(id); return it == mMapPoints_.end() ? nullptr : it->second; }
-    void addObservation(ID kfId, ID mpId, size_t idx) { mKeyFrameObs_[kfId][mpId] = idx; mMapPointObs_[mpId][kfId] = idx; }
+    // Map.cc:100-127: observation tables + covisibility counts
+    void addObservation(ID kfId, ID mpId, size_t idx) {
+        mKeyFrameObs_[kfId][mpId] = idx; mMapPointObs_[mpId][kfId] = idx;
+        for (auto& kv : mMapPointObs_[mpId]) {
+            if (kv.first == kfId) continue;
+            mCovisibilityGraph_[kfId][kv.first]++; mCovisibilityGraph_[kv.first][kfId]++;
+        }
+    }
+    // Map.cc:134-149
+    void removeObservation(ID kfId, ID mpId) {
+        mKeyFrameObs_[kfId].erase(mpId); mMapPointObs_[mpId].erase(kfId);
+        for (auto& kv : mMapPointObs_[mpId]) { mCovisibilityGraph_[kfId][kv.first]--; mCovisibilityGraph_[kv.first][kfId]--; }
+    }
+    void checkKeyFrame(ID) {}                      // Map.h:142: debug only, its body is commented out upstream
+    void setMinCommonObs(float v) { minCommonObs_ = v; }
+    // Map.cc:178-209: the key frame, its covisible key frames (more than minCommonObs shared points), the points they
+    // see, and -- fixed -- every other key frame that sees one of those points
+    void getLocalMapOfKeyFrame(ID kfId, std::set<ID>& sLocalMapPointsIds, std::set<ID>& sLocalKeyFramesIds, std::set<ID>& sLocalFixedKeyFramesIds) {
+        std::set<ID> sAllKFs;
+        sLocalKeyFramesIds.insert(kfId);
+        for (auto& kv : mKeyFrameObs_[kfId]) sLocalMapPointsIds.insert(kv.first);
+        for (auto& kv : mCovisibilityGraph_[kfId])
+            if (kv.second > minCommonObs_) {
+                sLocalKeyFramesIds.insert(kv.first);
+                for (auto& ob : mKeyFrameObs_[kv.first]) sLocalMapPointsIds.insert(ob.first);
+            }
+        for (ID mp : sLocalMapPointsIds) for (auto& kv : mMapPointObs_[mp]) sAllKFs.insert(kv.first);
+        sLocalFixedKeyFramesIds.clear();
+        for (ID k : sAllKFs) if (!sLocalKeyFramesIds.count(k)) sLocalFixedKeyFramesIds.insert(k);
+    }
     std::unordered_map<ID, MapPoint_>& getMapPoints() { return mMapPoints_; }
     std::unordered_map<ID, KeyFrame_>& getKeyFrames() { return mKeyFrames_; }
     // Map.cc:257-264: index of the key point observing mp in kf, or -1
@@ -206,6 +238,7 @@ public:
             m->mKeyFrames_[kv.first] = c;
         }
         m->mKeyFrameObs_ = mKeyFrameObs_; m->mMapPointObs_ = mMapPointObs_; m->mGTransformation_ = mGTransformation_;
+        m->mCovisibilityGraph_ = mCovisibilityGraph_; m->minCommonObs_ = minCommonObs_;
         return m;
     }
 private:
@@ -213,6 +246,33 @@ private:
     std::unordered_map<ID, KeyFrame_> mKeyFrames_;
     std::unordered_map<ID, std::unordered_map<ID, size_t>> mKeyFrameObs_, mMapPointObs_;
     std::unordered_map<ID, std::unordered_map<ID, Sophus::SE3f>> mGTransformation_;
+    std::unordered_map<ID, std::unordered_map<ID, int>> mCovisibilityGraph_;
+    float minCommonObs_ = 0.f;
+};
+
+// ------------------------------------------------------------------ Frame (Mapping/Frame.h:38-233): what poseOnlyOptimization touches
+class Frame {
+public:
+    Frame(const std::vector<cv::KeyPoint>& keys, const Sophus::SE3f& Tcw, std::shared_ptr<CameraModel> calib, int nScales = 8, float scaleFactor = 1.2f)
+        : vKeys_(keys), Tcw_(Tcw), calibration_(calib) {
+        vMapPoints_.assign(keys.size(), nullptr);
+        vInvSigma2_.resize(nScales);
+        float s = 1.0f;
+        for (int i = 0; i < nScales; ++i) { vInvSigma2_[i] = 1.0f / (s * s); s *= scaleFactor; }
+    }
+    void setPose(Sophus::SE3f& Tcw) { Tcw_ = Tcw; }
+    const Sophus::SE3f getPose() const { return Tcw_; }
+    cv::KeyPoint getKeyPoint(const size_t idx) { return vKeys_[idx]; }
+    std::vector<std::shared_ptr<MapPoint>>& getMapPoints() { return vMapPoints_; }
+    void setMapPoint(size_t idx, std::shared_ptr<MapPoint> pMP) { vMapPoints_[idx] = pMP; }
+    std::shared_ptr<CameraModel> getCalibration() { return calibration_; }
+    float getInvSigma2(int octave) { return vInvSigma2_[octave]; }
+private:
+    std::vector<cv::KeyPoint> vKeys_;
+    std::vector<MapPoint_> vMapPoints_;
+    Sophus::SE3f Tcw_;
+    std::shared_ptr<CameraModel> calibration_;
+    std::vector<float> vInvSigma2_;
 };
 
 // Visualisation is out of scope: the optimisation entry point keeps the parameter and calls update().

@@ -12,7 +12,9 @@
 #include <fstream>
 #include <iostream>
 #include <limits>
+#include <set>
 #include <stdexcept>
+#include <unordered_map>
 
 #include "../../include/dsc.h"
 #include "Mesh.h"
@@ -738,6 +740,180 @@ void deformationOptimization(std::shared_ptr<Map> pMap, Settings& settings, std:
     if (mapVisualizer) mapVisualizer->update(drawRays);
 }
 
+// ------------------------------------------------------------------ classic bundle adjustment (g2oBundleAdjustment.cc:38-444) on dsc_ba_*
+namespace {
+dsc_camera ba_camera(CameraModel* c) {
+    dsc_camera o{};
+    o.model = model_id(c);
+    for (int i = 0; i < 8; ++i) o.params[i] = i < c->getNumberOfParameters() ? c->getParameter(i) : 0.f;
+    return o;
+}
+const double kHuber2D = (double)(float)std::sqrt(5.99);                        // const float thHuber2D = sqrt(5.99)
+struct BaHandle {
+    dsc_ba* h = nullptr;
+    BaHandle() {
+        int dev = 0;
+        if (const char* d = std::getenv("DSC_DEVICE")) dev = std::atoi(d);
+        int st = dsc_ba_create(dev, &h);
+        if (st != DSC_OK) throw std::runtime_error(std::string("dsc_ba_create: ") + dsc_status_string(st) + " (there is no CPU fallback)");
+    }
+    ~BaHandle() { if (h) dsc_ba_destroy(h); }
+    void ck(int st, const char* what) { if (st != DSC_OK) throw std::runtime_error(std::string(what) + ": " + dsc_ba_last_error(h)); }
+};
+// vertices and edges of bundleAdjustment / localBundleAdjustment in the reference's creation order
+struct BaGraph {
+    std::vector<KeyFrame_> kfs;                 // poses: optimised key frames first, then the fixed ones
+    std::vector<ID> kfIds;
+    std::vector<uint8_t> fixed;
+    std::vector<MapPoint_> mps;
+    std::unordered_map<MapPoint*, int> mpIndex;
+    std::vector<int32_t> obsPose, obsPoint;
+    std::vector<float> uv, isg;
+    std::vector<size_t> obsSlot;                // vMpInKf
+    void addKeyFrame(KeyFrame_ kf, ID id, bool fix, const std::set<ID>* onlyPoints) {
+        const int k = (int)kfs.size();
+        kfs.push_back(kf); kfIds.push_back(id); fixed.push_back(fix ? 1 : 0);
+        auto& vMPs = kf->getMapPoints();
+        for (size_t i = 0; i < vMPs.size(); ++i) {
+            MapPoint_ mp = vMPs[i];
+            if (!mp) continue;
+            if (onlyPoints && !onlyPoints->count(mp->getId())) continue;   // :381 fixed key frames: local points only
+            auto it = mpIndex.find(mp.get());
+            int j;
+            if (it == mpIndex.end()) {
+                if (onlyPoints) continue;                                   // (:383 asserts the point is already a vertex)
+                j = (int)mps.size(); mps.push_back(mp); mpIndex[mp.get()] = j;
+            } else j = it->second;
+            cv::KeyPoint kp = kf->getKeyPoint(i);
+            obsPose.push_back(k); obsPoint.push_back(j); obsSlot.push_back(i);
+            uv.push_back(kp.pt.x); uv.push_back(kp.pt.y);
+            isg.push_back(kf->getInvSigma2(kp.octave));
+        }
+    }
+    void upload(BaHandle& b) {
+        std::vector<double> p7(7 * kfs.size()), X(3 * mps.size());
+        std::vector<dsc_camera> cams(kfs.size());
+        for (size_t k = 0; k < kfs.size(); ++k) { se3_to_7(kfs[k]->getPose(), p7.data() + 7 * k); cams[k] = ba_camera(kfs[k]->getCalibration().get()); }
+        for (size_t j = 0; j < mps.size(); ++j) { auto p = mps[j]->getWorldPosition(); for (int c = 0; c < 3; ++c) X[3 * j + c] = (double)p[c]; }
+        b.ck(dsc_ba_upload(b.h, (int)kfs.size(), p7.data(), fixed.data(), cams.data(), (int)mps.size(), X.data(), 0, (long long)obsPose.size(),
+                           obsPose.data(), obsPoint.data(), uv.data(), isg.data()), "dsc_ba_upload");
+    }
+    void writeBack(BaHandle& b) {                                               // :126-140, :429-443
+        std::vector<double> p7(7 * kfs.size()), X(3 * mps.size());
+        b.ck(dsc_ba_download(b.h, p7.data(), X.data()), "dsc_ba_download");
+        for (size_t k = 0; k < kfs.size(); ++k) {
+            if (fixed[k] && kfIds[k] != 0) continue;                           // fixed key frames of the local map are not written
+            Sophus::SE3f T = se3_from_7(p7.data() + 7 * k);
+            kfs[k]->setPose(T);
+        }
+        for (size_t j = 0; j < mps.size(); ++j) {
+            Eigen::Vector3f p((float)X[3 * j], (float)X[3 * j + 1], (float)X[3 * j + 2]);
+            mps[j]->setWorldPosition(p);
+        }
+    }
+};
+}  // namespace
+
+void bundleAdjustment(Map* pMap) {
+    BaGraph g;
+    for (auto& kv : pMap->getKeyFrames()) g.addKeyFrame(kv.second, kv.first, kv.second->getId() == 0, nullptr);   // :63-118
+    if (g.kfs.empty()) return;
+    BaHandle b;
+    g.upload(b);
+    b.ck(dsc_ba_optimize(b.h, 20, kHuber2D, nullptr, nullptr), "dsc_ba_optimize");                              // :122-123
+    g.writeBack(b);
+}
+
+void localBundleAdjustment(Map* pMap, ID currKeyFrameId) {
+    std::set<ID> sLocalMapPoints, sLocalKeyFrames, sFixedKeyFrames;
+    pMap->getLocalMapOfKeyFrame(currKeyFrameId, sLocalMapPoints, sLocalKeyFrames, sFixedKeyFrames);              // :252
+    BaGraph g;
+    for (ID id : sLocalKeyFrames) { KeyFrame_ kf = pMap->getKeyFrame(id); g.addKeyFrame(kf, id, kf->getId() == 0, nullptr); }      // :280-344
+    for (ID id : sFixedKeyFrames) g.addKeyFrame(pMap->getKeyFrame(id), id, true, &sLocalMapPoints);                                // :347-398
+    if (g.kfs.empty()) return;
+    BaHandle b;
+    g.upload(b);
+    const size_t O = g.obsPose.size();
+    std::vector<double> chiA(O), chiB(O);
+    std::vector<uint8_t> posA(O), posB(O), active(O);
+    b.ck(dsc_ba_optimize(b.h, 5, kHuber2D, nullptr, nullptr), "dsc_ba_optimize");                               // :401-402
+    b.ck(dsc_ba_edge_chi2(b.h, chiA.data(), posA.data()), "dsc_ba_edge_chi2");
+    for (size_t e = 0; e < O; ++e) active[e] = (chiA[e] > 5.991 || !posA[e]) ? 0 : 1;                             // :405-413 (+ every kernel off)
+    b.ck(dsc_ba_set_levels(b.h, active.data()), "dsc_ba_set_levels");
+    b.ck(dsc_ba_optimize(b.h, 10, 0.0, nullptr, nullptr), "dsc_ba_optimize");                                   // :415-416
+    b.ck(dsc_ba_edge_chi2(b.h, chiB.data(), posB.data()), "dsc_ba_edge_chi2");
+    for (size_t e = 0; e < O; ++e) {                                                                              // :419-428
+        // a level-1 edge was not evaluated by the second run: its chi2() is the one it was classified with
+        const double chi = active[e] ? chiB[e] : chiA[e];
+        if (chi > 5.991 || !posB[e]) {
+            const ID kfId = g.kfIds[(size_t)g.obsPose[e]], mpId = g.mps[(size_t)g.obsPoint[e]]->getId();
+            pMap->getKeyFrame(kfId)->setMapPoint(g.obsSlot[e], nullptr);
+            pMap->removeObservation(kfId, mpId);
+            pMap->checkKeyFrame(kfId);
+        }
+    }
+    g.writeBack(b);
+}
+
+int poseOnlyOptimization(Frame& currFrame) {
+    auto& vMapPoints = currFrame.getMapPoints();
+    std::vector<size_t> slot;
+    std::vector<int32_t> obsPose, obsPoint;
+    std::vector<float> uv, isg;
+    std::vector<double> X;
+    for (size_t i = 0; i < vMapPoints.size(); ++i) {                                                              // :168-197
+        MapPoint_ mp = vMapPoints[i];
+        if (!mp) continue;
+        cv::KeyPoint kp = currFrame.getKeyPoint(i);
+        auto p = mp->getWorldPosition();
+        obsPose.push_back(0); obsPoint.push_back((int32_t)slot.size()); slot.push_back(i);
+        uv.push_back(kp.pt.x); uv.push_back(kp.pt.y);
+        isg.push_back(currFrame.getInvSigma2(kp.octave));
+        for (int c = 0; c < 3; ++c) X.push_back((double)p[c]);
+    }
+    const size_t O = slot.size();
+    double start7[7];
+    se3_to_7(currFrame.getPose(), start7);
+    dsc_camera cam = ba_camera(currFrame.getCalibration().get());
+    uint8_t notFixed = 0;
+    BaHandle b;
+    b.ck(dsc_ba_upload(b.h, 1, start7, &notFixed, &cam, (int)O, X.data(), /*points_fixed=*/1, (long long)O, obsPose.data(), obsPoint.data(), uv.data(),
+                       isg.data()), "dsc_ba_upload");
+    // vInlier is indexed by key-point slot upstream (size = all slots, false where there is no map point)
+    std::vector<bool> vInlier(vMapPoints.size(), false);
+    for (size_t e = 0; e < O; ++e) vInlier[slot[e]] = true;
+    std::vector<uint8_t> level0(O, 1);
+    std::vector<double> stored(O), fresh(O);
+    b.ck(dsc_ba_edge_chi2(b.h, stored.data(), nullptr), "dsc_ba_edge_chi2");
+    double delta = kHuber2D;
+    for (int round = 0; round < 4; ++round) {                                                                     // :199-228
+        b.ck(dsc_ba_set_poses(b.h, start7), "dsc_ba_set_poses");                                               // every round restarts from fPose
+        b.ck(dsc_ba_set_levels(b.h, level0.data()), "dsc_ba_set_levels");
+        b.ck(dsc_ba_optimize(b.h, 10, delta, nullptr, nullptr), "dsc_ba_optimize");
+        b.ck(dsc_ba_edge_chi2(b.h, fresh.data(), nullptr), "dsc_ba_edge_chi2");
+        // `if(!vInlier[mpIndex]) e->computeError();` with mpIndex = the ROUND number (:209-210): edges at level 1 keep
+        // the error of their last evaluation unless the flag of key point #round happens to be false
+        const bool refreshAll = (size_t)round < vInlier.size() && !vInlier[(size_t)round];
+        for (size_t e = 0; e < O; ++e) {
+            if (level0[e] || refreshAll) stored[e] = fresh[e];
+            const bool in = !(stored[e] > 5.991);
+            vInlier[slot[e]] = in;
+            level0[e] = in ? 1 : 0;
+        }
+        if (round == 2) delta = 0.0;                                                                              // :222-224 setRobustKernel(0)
+    }
+    int nGood = 0;
+    for (size_t i = 0; i < vInlier.size(); ++i) {                                                                 // :231-239
+        if (!vInlier[i]) currFrame.setMapPoint(i, nullptr);
+        else nGood++;
+    }
+    double p7[7];
+    b.ck(dsc_ba_download(b.h, p7, nullptr), "dsc_ba_download");
+    Sophus::SE3f T = se3_from_7(p7);
+    currFrame.setPose(T);
+    return nGood;
+}
+
 // ------------------------------------------------------------------ C hooks for the tests (ctypes)
 extern "C" int dsch_delaunay(int n, const double* xy, int* tri_out, int max_tri) {
     auto tri = dsc_host::Delaunay2D::triangulate(xy, n);
@@ -786,3 +962,66 @@ extern "C" int dsch_nelder_mead(int fn, int dim, const double* x0, const double*
     }
     return (int)used.size();
 }
+
+#ifndef DSC_IN_REFERENCE_TREE
+// The classic bundle-adjustment entry points on a Map built from arrays (tests/test_gpu_ba.py): mode 0 bundleAdjustment, 1
+// localBundleAdjustment(curr), 2 poseOnlyOptimization of a Frame with the pose and observations of pose 0.  pose34: [K][12]
+// float [R|t]; X: [M][3] float; observations (pose, point, uv, octave).  Out: poses as 7 doubles of the written-back float
+// poses, points, per observation whether its map point was taken out of its key frame / frame, mode 2: the inlier count.
+extern "C" int dsch_ba_flow(int mode, int K, const float* pose34, const float* cam8, int M, const float* X, int O, const int* obs_pose,
+                            const int* obs_point, const float* obs_uv, const int* obs_octave, int curr, float minCommonObs, double* pose7_out,
+                            float* X_out, unsigned char* removed_out, int* n_good) {
+    try {
+        KeyFrame::restartIds(); MapPoint::restartIds();
+        std::vector<float> cp(cam8, cam8 + 8);
+        auto calib = std::make_shared<KannalaBrandt8>(cp);
+        auto poseOf = [&](int k) {
+            Eigen::Matrix3f R;
+            for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) R(r, c) = pose34[12 * k + 4 * r + c];
+            return Sophus::SE3f(R, Eigen::Vector3f(pose34[12 * k + 3], pose34[12 * k + 7], pose34[12 * k + 11]));
+        };
+        std::vector<MapPoint_> mps(M);
+        for (int j = 0; j < M; ++j) { Eigen::Vector3f p(X[3 * j], X[3 * j + 1], X[3 * j + 2]); mps[j] = std::make_shared<MapPoint>(p); }
+        std::vector<std::vector<int>> obsOf(K);
+        for (int e = 0; e < O; ++e) obsOf[obs_pose[e]].push_back(e);
+        auto keysOf = [&](int k) {
+            std::vector<cv::KeyPoint> keys;
+            for (int e : obsOf[k]) { cv::KeyPoint kp(cv::Point2f(obs_uv[2 * e], obs_uv[2 * e + 1]), 1.0f); kp.octave = obs_octave[e]; keys.push_back(kp); }
+            return keys;
+        };
+        if (n_good) *n_good = 0;
+        if (mode == 2) {
+            Frame f(keysOf(0), poseOf(0), calib);
+            for (size_t s = 0; s < obsOf[0].size(); ++s) f.setMapPoint(s, mps[obs_point[obsOf[0][s]]]);
+            int ng = poseOnlyOptimization(f);
+            if (n_good) *n_good = ng;
+            se3_to_7(f.getPose(), pose7_out);
+            for (size_t s = 0; s < obsOf[0].size(); ++s) removed_out[obsOf[0][s]] = f.getMapPoints()[s] ? 0 : 1;
+            return 0;
+        }
+        Map map;
+        map.setMinCommonObs(minCommonObs);
+        std::vector<KeyFrame_> kfs(K);
+        for (int j = 0; j < M; ++j) map.insertMapPoint(mps[j]);
+        for (int k = 0; k < K; ++k) {
+            kfs[k] = std::make_shared<KeyFrame>(keysOf(k), poseOf(k), calib);
+            map.insertKeyFrame(kfs[k]);
+            for (size_t s = 0; s < obsOf[k].size(); ++s) {
+                MapPoint_ mp = mps[obs_point[obsOf[k][s]]];
+                kfs[k]->setMapPoint(s, mp);
+                map.addObservation(kfs[k]->getId(), mp->getId(), s);
+            }
+        }
+        if (mode == 0) bundleAdjustment(&map); else localBundleAdjustment(&map, kfs[curr]->getId());
+        for (int k = 0; k < K; ++k) {
+            se3_to_7(kfs[k]->getPose(), pose7_out + 7 * k);
+            for (size_t s = 0; s < obsOf[k].size(); ++s) removed_out[obsOf[k][s]] = kfs[k]->getMapPoints()[s] ? 0 : 1;
+        }
+        for (int j = 0; j < M; ++j) { auto p = mps[j]->getWorldPosition(); for (int c = 0; c < 3; ++c) X_out[3 * j + c] = p[c]; }
+        return 0;
+    } catch (const std::exception& ex) {
+        std::cerr << "dsch_ba_flow: " << ex.what() << std::endl;
+        return 1;
+    }
+}
+#endif

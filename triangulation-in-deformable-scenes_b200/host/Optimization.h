@@ -25,6 +25,7 @@
 #include "Map/KeyFrame.h"
 #include "Map/Map.h"
 #include "Map/MapPoint.h"
+#include "Mapping/Frame.h"
 #include "System/Settings.h"
 #include "Utils/CommonTypes.h"
 #include "Visualization/MapVisualizer.h"
@@ -32,6 +33,14 @@
 #include "Map.h"
 #include "Settings.h"
 #endif
+
+/* The classic bundle-adjustment paths (g2oBundleAdjustment.h:36-47, bodies g2oBundleAdjustment.cc:38-444), on dsc_ba_*:
+ * full BA of every key frame and map point (key frame 0 fixed, 20 iterations, Huber sqrt(5.99));  pose-only optimisation of a
+ * frame (four rounds of ten iterations, inliers re-classified at chi2 5.991; returns the number of inliers, outliers lose their
+ * map point);  BA of the local map of a key frame (5 robust + 10 plain iterations, outlier observations removed from the map). */
+void bundleAdjustment(Map* pMap);
+int poseOnlyOptimization(Frame& currFrame);
+void localBundleAdjustment(Map* pMap, ID currKeyFrameId);
 
 /* Performs an As-Rigid-As-Possible optimization using arapOptimization inside an external loop that optimizes the
  * balance weights (g2oBundleAdjustment.cc:446-606). */
