@@ -45,6 +45,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-fp32", action="store_true", help="skip the fp32-mode sub-record")
     ap.add_argument("--no-point-sharded", action="store_true", help="N > 1: skip the one-pair-over-all-GPUs sub-record")
+    ap.add_argument("--no-classic-ba", action="store_true", help="skip the classic bundle-adjustment sub-record (SURVEY 8f-4)")
+    ap.add_argument("--ba-points", type=int, default=1_000_000, help="map points of the classic-BA sub-record (two views)")
     ap.add_argument("--no-shim-e2e", action="store_true", help="skip the arapOptimization-through-the-C++-shim sub-record")
     ap.add_argument("--shim-points", type=int, default=1_000_000, help="points of the shim sub-record's sheet scene")
     return ap.parse_args()
@@ -355,6 +357,14 @@ def main():
         except Exception as ex:
             shim = dict(error=str(ex)[-400:])
 
+    # ---- classic bundle adjustment: two views, --ba-points map points, the reference's bundleAdjustment settings
+    cba = None
+    if world == 1 and not args.no_classic_ba:
+        try:
+            cba = run_classic_ba(pkg, args, peak)
+        except Exception as ex:
+            cba = dict(error=str(ex)[-400:])
+
     # ---- config 5 (batch of independent 10k pairs, sharded by problem index) as a sub-record of the same line at every N
     c5 = None
     if args.config5_problems > 0:
@@ -402,7 +412,7 @@ def main():
                              ms_per_step=e2e_ms / args.steps),
                     gpu_launches=int(launches), clocks=clocks, roofline=roof, cpu_baseline=cpu,
                     triangulated_points_per_s=roof["triangulate"]["points_per_s"], knn_graph_build_ms=prob["graph_build_ms"],
-                    cg_iteration_ms=cg_ms, wall_ms_per_step=wall_ms / args.steps, fp32_mode=f32rec, reference_api_e2e=shim, config5=c5)
+                    cg_iteration_ms=cg_ms, wall_ms_per_step=wall_ms / args.steps, fp32_mode=f32rec, reference_api_e2e=shim, classic_ba=cba, config5=c5)
         if ps is not None:
             if "error" not in ps:
                 ps["speedup_vs_one_gpu"] = ps["lm_it_per_s"] / (value / world)      # the same pair, same LM trace, on ONE of these GPUs
@@ -584,6 +594,66 @@ def run_config5(pkg, args, rank, world, local, dist, per_gpu, n_points, steps, w
                                    "(~18 MB) is L2-resident while its cluster refines it, so the fraction of the HBM peak can exceed 1"),
                 gathered=dict(problems=int(table.shape[0]), final_chi2_sum=float(table[:, 0].sum()), lm_iterations=int(table[:, 1].sum())),
                 host_build_ms_this_rank=build_ms)
+
+
+def run_classic_ba(pkg, args, peak):
+    """bundleAdjustment's optimisation (g2oBundleAdjustment.cc:38-141: Huber sqrt(5.99), 20 LM iterations) on two views of
+    --ba-points map points: LM iterations/s resident and from host arrays, bytes of the run against the measured HBM peak, and the
+    numpy oracle (full-system sparse solve, one core) on a bounded sample of the same scene."""
+    import importlib
+    wl = importlib.import_module(pkg.__name__ + ".workloads")
+    n = int(args.ba_points)
+    sc = wl.ba_scene(n, 2, seed=0)
+    huber = float(np.float32(np.sqrt(5.99)))
+    iters = 20
+    with pkg.BundleAdjuster(0) as b:
+        def upload():
+            b.upload(sc["poses7"], sc["pose_fixed"], sc["cams"], sc["X"], sc["obs_pose"], sc["obs_point"], sc["obs_uv"], sc["obs_isg"])
+        upload()
+        b.optimize(iters, huber)                                   # warm-up (kernel loading)
+        res, e2e = [], []
+        for _ in range(3):
+            t0 = time.perf_counter()
+            upload()
+            recs, st = b.optimize(iters, huber)                    # (device_ms: CUDA events around the LM run, inputs resident)
+            p7, X = b.download()
+            e2e.append((time.perf_counter() - t0) * 1e3)
+            res.append((st.device_ms, st.iterations, st.total_trials, st.kernel_launches, recs[0].chi2_before, st.final_chi2))
+        ms, its, trials, launches, chi0, chi1 = res[-1]
+        ms = float(np.median([r[0] for r in res]))
+    O = len(sc["obs_pose"])
+    # algorithmic bytes: linearise once per iteration (X 32 + Hll 48 + bl 24 per point, 17 in + 360 out per observation), per trial the
+    # Schur pass (444 per diagonal entry: one per point seen from the free view), the back-substitution (136 per point + 148 per
+    # observation) and the cost (32 per point + 17 per observation)
+    by = its * (104.0 * n + 377.0 * O) + trials * (444.0 * n + 136.0 * n + 148.0 * O + 32.0 * n + 17.0 * O)
+    rec = dict(workload=f"bundleAdjustment: 2 key frames x {n} map points ({O} observations), key frame 0 fixed, Huber sqrt(5.99), {iters} LM iterations, "
+                        "points marginalised (Schur complement on the device)",
+               lm_it_per_s=its / (ms * 1e-3), ms_per_run=ms, lm_iterations=int(its), trials=int(trials), gpu_launches_per_run=int(launches),
+               e2e=dict(lm_it_per_s=its / (float(np.median(e2e)) * 1e-3), ms_per_run=float(np.median(e2e)),
+                        h2d_bytes=int(sc["X"].nbytes + sc["obs_uv"].nbytes + sc["obs_pose"].nbytes + sc["obs_point"].nbytes + sc["obs_isg"].nbytes),
+                        d2h_bytes=int(sc["X"].nbytes), note="upload (observation sort and Schur entry list on the host) + optimize + download"),
+               chi2=[float(chi0), float(chi1)],
+               roofline=dict(bound="hbm", achieved=by / (ms * 1e-3) / 1e9, peak=peak, unit="GB/s", frac=by / (ms * 1e-3) / 1e9 / peak,
+                             note="algorithmic bytes of every kernel of the run / device time of the run (host round trips of the LM loop included)"))
+    if not args.no_cpu_baseline:
+        try:
+            sys.path.insert(0, ROOT)
+            from oracle import ba as oba
+            from oracle.se3 import SE3
+            m = min(n, 20_000)
+            small = wl.ba_scene(m, 2, seed=0)
+            prob = oba.BaProblem(poses=[SE3.from7(q) for q in small["poses7"]], pose_fixed=small["pose_fixed"], cams=small["cams"], X=small["X"],
+                                 obs_pose=small["obs_pose"], obs_point=small["obs_point"], obs_uv=small["obs_uv"], obs_isg=small["obs_isg"].astype(np.float64))
+            t0 = time.perf_counter()
+            _, _, tr = oba.optimize(prob, 3, robust=True)
+            dt = time.perf_counter() - t0
+            done = len(tr["trials"])
+            rec["cpu_baseline"] = dict(value=done / dt * (m / n), unit="LM it/s", cores=1, kind="port",
+                                       sample=f"oracle/ba.py (numpy + scipy sparse direct solve of the full system) on {m} of the {n} points, {done} LM "
+                                              f"iterations in {dt:.1f} s, scaled linearly to {n} points")
+        except Exception as ex:
+            rec["cpu_baseline"] = dict(error=str(ex)[-200:])
+    return rec
 
 
 def main_batch(args, rank, world, local):

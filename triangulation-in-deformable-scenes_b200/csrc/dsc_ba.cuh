@@ -5,7 +5,8 @@
 // Layout: the observations are sorted by map point (CSR pt_ptr): one thread owns a point, walks its observations and keeps
 // the point's 3x3 block in registers.  Per observation the linearisation stores the pose-side blocks
 //   A = w Jp^T Jp (21, packed), g = -w Jp^T e (6), W = w Jp^T Jx (6x3)
-// and per point Hll (6, packed) and bl (3).  The reduced camera system S = Hpp - Hpl (Hll + lambda)^-1 Hlp is summed over
+// (component-major: block component c of observation o at [c * O + o], so the threads of a warp -- consecutive points, whose
+// observations are consecutive -- write and read consecutive addresses) and per point Hll (6, packed) and bl (3).  The reduced camera system S = Hpp - Hpl (Hll + lambda)^-1 Hlp is summed over
 // "entries": pairs of observations of the same point seen from free poses a <= b, sorted by (a, b) on the host, cut into
 // chunks of one block each -- every sum is a fixed-order two-stage reduction (no atomics), the per-chunk partials are
 // folded in order on the host, which also factorises the small system (6 x free poses).
@@ -68,7 +69,7 @@ __global__ void __launch_bounds__(kThreads)
 ba_linearize_kernel(int M, const int* __restrict__ pt_ptr, const int* __restrict__ ob_pose, const float2* __restrict__ ob_uv,
                     const float* __restrict__ ob_isg, const unsigned char* __restrict__ ob_act, const double4* __restrict__ X,
                     const BaPose* __restrict__ poses, const CamF* __restrict__ cams, const unsigned char* __restrict__ pose_free,
-                    double delta, int points_fixed, double* __restrict__ Hll, double* __restrict__ bl, double* __restrict__ W,
+                    double delta, int points_fixed, size_t O, double* __restrict__ Hll, double* __restrict__ bl, double* __restrict__ W,
                     double* __restrict__ A, double* __restrict__ g, double* __restrict__ part) {
     __shared__ double sm[2 * (kThreads / 32)];
     double acc[1] = {0.0};
@@ -78,9 +79,9 @@ ba_linearize_kernel(int M, const int* __restrict__ pt_ptr, const int* __restrict
         const D3 Xw = d3(x4.x, x4.y, x4.z);
         double h[6] = {0, 0, 0, 0, 0, 0}, b3[3] = {0, 0, 0};
         for (int o = pt_ptr[j]; o < pt_ptr[j + 1]; ++o) {
-            double* Wo = W + 18 * (size_t)o;
-            double* Ao = A + 21 * (size_t)o;
-            double* go = g + 6 * (size_t)o;
+            double* Wo = W + (size_t)o;                 // component c at Wo[c * O]
+            double* Ao = A + (size_t)o;
+            double* go = g + (size_t)o;
             const int k = ob_pose[o];
             const bool live = ob_act[o] != 0;
             const bool fr = live && pose_free[k] != 0;
@@ -103,10 +104,10 @@ ba_linearize_kernel(int M, const int* __restrict__ pt_ptr, const int* __restrict
 #pragma unroll
             for (int r = 0; r < 6; ++r) {
 #pragma unroll
-                for (int c = r; c < 6; ++c) Ao[q++] = fr ? w * (Jp[r] * Jp[c] + Jp[6 + r] * Jp[6 + c]) : 0.0;
-                go[r] = fr ? -w * (Jp[r] * e[0] + Jp[6 + r] * e[1]) : 0.0;
+                for (int c = r; c < 6; ++c) Ao[(size_t)(q++) * O] = fr ? w * (Jp[r] * Jp[c] + Jp[6 + r] * Jp[6 + c]) : 0.0;
+                go[(size_t)r * O] = fr ? -w * (Jp[r] * e[0] + Jp[6 + r] * e[1]) : 0.0;
 #pragma unroll
-                for (int c = 0; c < 3; ++c) Wo[r * 3 + c] = fr && !points_fixed ? w * (Jp[r] * Jx[c] + Jp[6 + r] * Jx[3 + c]) : 0.0;
+                for (int c = 0; c < 3; ++c) Wo[(size_t)(r * 3 + c) * O] = fr && !points_fixed ? w * (Jp[r] * Jx[c] + Jp[6 + r] * Jx[3 + c]) : 0.0;
             }
         }
 #pragma unroll
@@ -135,7 +136,7 @@ __global__ void __launch_bounds__(kThreads)
 ba_schur_kernel(const BaEntryChunk* __restrict__ chunks, const int* __restrict__ en_a, const int* __restrict__ en_b,
                 const int* __restrict__ en_pt, const double* __restrict__ Hll, const double* __restrict__ bl,
                 const double* __restrict__ W, const double* __restrict__ A, const double* __restrict__ g, double lambda,
-                int with_points, double* __restrict__ part) {
+                int with_points, size_t O, double* __restrict__ part) {
     __shared__ double sm[kBaDiag * (kThreads / 32)];
     const BaEntryChunk ch = chunks[blockIdx.x];
     double acc[kBaDiag];
@@ -145,7 +146,9 @@ ba_schur_kernel(const BaEntryChunk* __restrict__ chunks, const int* __restrict__
         const int oa = en_a[t], ob = en_b[t], j = en_pt[t];
         double Hi[6] = {0, 0, 0, 0, 0, 0};
         if (with_points) ba_inv3(Hll + 6 * (size_t)j, lambda, Hi);
-        const double* Wa = W + 18 * (size_t)oa;
+        double Wa[18];
+#pragma unroll
+        for (int c = 0; c < 18; ++c) Wa[c] = W[(size_t)c * O + oa];
         double WH[18];                                   // W_a Hinv (6x3)
 #pragma unroll
         for (int r = 0; r < 6; ++r) {
@@ -153,12 +156,10 @@ ba_schur_kernel(const BaEntryChunk* __restrict__ chunks, const int* __restrict__
             WH[r * 3] = v.x; WH[r * 3 + 1] = v.y; WH[r * 3 + 2] = v.z;
         }
         if (ch.diag) {
-            const double* Ao = A + 21 * (size_t)oa;
-            const double* go = g + 6 * (size_t)oa;
 #pragma unroll
-            for (int k = 0; k < 21; ++k) acc[k] += Ao[k];
+            for (int k = 0; k < 21; ++k) acc[k] += A[(size_t)k * O + oa];
 #pragma unroll
-            for (int k = 0; k < 6; ++k) acc[21 + k] += go[k];
+            for (int k = 0; k < 6; ++k) acc[21 + k] += g[(size_t)k * O + oa];
             int q = 27;
 #pragma unroll
             for (int r = 0; r < 6; ++r)
@@ -168,7 +169,9 @@ ba_schur_kernel(const BaEntryChunk* __restrict__ chunks, const int* __restrict__
 #pragma unroll
             for (int r = 0; r < 6; ++r) acc[48 + r] += WH[r * 3] * b3[0] + WH[r * 3 + 1] * b3[1] + WH[r * 3 + 2] * b3[2];
         } else {
-            const double* Wb = W + 18 * (size_t)ob;
+            double Wb[18];
+#pragma unroll
+            for (int c = 0; c < 18; ++c) Wb[c] = W[(size_t)c * O + ob];
 #pragma unroll
             for (int r = 0; r < 6; ++r)
 #pragma unroll
@@ -184,7 +187,7 @@ ba_schur_kernel(const BaEntryChunk* __restrict__ chunks, const int* __restrict__
 __global__ void __launch_bounds__(kThreads)
 ba_backsub_kernel(int M, const int* __restrict__ pt_ptr, const int* __restrict__ ob_pose, const double4* __restrict__ X,
                   const double* __restrict__ Hll, const double* __restrict__ bl, const double* __restrict__ W,
-                  const double* __restrict__ dP /*[K][6]*/, double lambda, int points_fixed, double4* __restrict__ Xt,
+                  const double* __restrict__ dP /*[K][6]*/, double lambda, int points_fixed, size_t O, double4* __restrict__ Xt,
                   double* __restrict__ part) {
     __shared__ double sm[kThreads / 32];
     double acc[1] = {0.0};
@@ -195,10 +198,12 @@ ba_backsub_kernel(int M, const int* __restrict__ pt_ptr, const int* __restrict__
             D3 r = d3(bl[3 * (size_t)j], bl[3 * (size_t)j + 1], bl[3 * (size_t)j + 2]);
             const D3 b3 = r;
             for (int o = pt_ptr[j]; o < pt_ptr[j + 1]; ++o) {
-                const double* Wo = W + 18 * (size_t)o;
+                const double* Wo = W + (size_t)o;
                 const double* dp = dP + 6 * (size_t)ob_pose[o];
 #pragma unroll
-                for (int q = 0; q < 6; ++q) { r.x -= Wo[q * 3] * dp[q]; r.y -= Wo[q * 3 + 1] * dp[q]; r.z -= Wo[q * 3 + 2] * dp[q]; }
+                for (int q = 0; q < 6; ++q) {
+                    r.x -= Wo[(size_t)(q * 3) * O] * dp[q]; r.y -= Wo[(size_t)(q * 3 + 1) * O] * dp[q]; r.z -= Wo[(size_t)(q * 3 + 2) * O] * dp[q];
+                }
             }
             double Hi[6];
             ba_inv3(Hll + 6 * (size_t)j, lambda, Hi);

@@ -30,6 +30,7 @@ struct dsc_ba {
     double *d_Hll = nullptr, *d_bl = nullptr, *d_W = nullptr, *d_A = nullptr, *d_g = nullptr, *d_part = nullptr, *d_dP = nullptr, *d_chi = nullptr;
     dsc::BaEntryChunk* d_chunks = nullptr;
     size_t part_cap = 0;
+    size_t capK = 0, capM = 0, capO = 0, capE = 0, capC = 0;   // grow-only capacities (no cudaMalloc / cudaFree on a warm handle)
     std::vector<double> h_part;
     long long launches = 0;
 };
@@ -180,7 +181,14 @@ extern "C" int dsc_ba_upload(dsc_ba* ba, int n_poses, const double* poses7, cons
                 ents.push_back({opose[(size_t)s], opose[(size_t)t], s, t, j});
             }
         }
-    std::stable_sort(ents.begin(), ents.end(), [](const Ent& x, const Ent& y) { return x.a != y.a ? x.a < y.a : x.b < y.b; });
+    {   // stable counting sort by (a, b): the entries of a segment stay in point order
+        std::vector<size_t> start((size_t)K * K + 1, 0);
+        for (const Ent& e : ents) start[(size_t)e.a * K + e.b + 1]++;
+        for (size_t q = 0; q < (size_t)K * K; ++q) start[q + 1] += start[q];
+        std::vector<Ent> sorted(ents.size());
+        for (const Ent& e : ents) sorted[start[(size_t)e.a * K + e.b]++] = e;
+        ents.swap(sorted);
+    }
     ba->E = (long long)ents.size();
     std::vector<int> ea(ents.size()), eb(ents.size()), ept(ents.size());
     ba->chunks.clear(); ba->chunk_a.clear(); ba->chunk_b.clear();
@@ -197,15 +205,32 @@ extern "C" int dsc_ba_upload(dsc_ba* ba, int n_poses, const double* poses7, cons
     // ---- device buffers
     const size_t Os = (size_t)std::max<long long>(O, 1), Ms = (size_t)std::max(M, 1), Es = std::max<size_t>(ents.size(), 1);
     const size_t nch = std::max<size_t>(ba->chunks.size(), 1);
-    ACK(dev_alloc(ba->d_pose, (size_t)K)); ACK(dev_alloc(ba->d_pose_t, (size_t)K)); ACK(dev_alloc(ba->d_cam, (size_t)K));
-    ACK(dev_alloc(ba->d_free, (size_t)K)); ACK(dev_alloc(ba->d_act, Os)); ACK(dev_alloc(ba->d_pos, Os)); ACK(dev_alloc(ba->d_chi, Os));
-    ACK(dev_alloc(ba->d_X, Ms)); ACK(dev_alloc(ba->d_Xt, Ms)); ACK(dev_alloc(ba->d_ptr, (size_t)M + 1)); ACK(dev_alloc(ba->d_opose, Os));
-    ACK(dev_alloc(ba->d_orig, Os)); ACK(dev_alloc(ba->d_uv, Os)); ACK(dev_alloc(ba->d_isg, Os));
-    ACK(dev_alloc(ba->d_ea, Es)); ACK(dev_alloc(ba->d_eb, Es)); ACK(dev_alloc(ba->d_ept, Es)); ACK(dev_alloc(ba->d_chunks, nch));
-    ACK(dev_alloc(ba->d_Hll, 6 * Ms)); ACK(dev_alloc(ba->d_bl, 3 * Ms)); ACK(dev_alloc(ba->d_W, 18 * Os)); ACK(dev_alloc(ba->d_A, 21 * Os));
-    ACK(dev_alloc(ba->d_g, 6 * Os)); ACK(dev_alloc(ba->d_dP, 6 * (size_t)K));
-    ba->part_cap = std::max<size_t>(nch * dsc::kBaDiag, (size_t)ba->sms * 8 * 2 + 16);
-    ACK(dev_alloc(ba->d_part, ba->part_cap));
+    if ((size_t)K > ba->capK) {
+        ACK(dev_alloc(ba->d_pose, (size_t)K)); ACK(dev_alloc(ba->d_pose_t, (size_t)K)); ACK(dev_alloc(ba->d_cam, (size_t)K));
+        ACK(dev_alloc(ba->d_free, (size_t)K)); ACK(dev_alloc(ba->d_dP, 6 * (size_t)K));
+        ba->capK = (size_t)K;
+    }
+    if (Ms > ba->capM) {
+        const size_t c = Ms + Ms / 8;
+        ACK(dev_alloc(ba->d_X, c)); ACK(dev_alloc(ba->d_Xt, c)); ACK(dev_alloc(ba->d_ptr, c + 1)); ACK(dev_alloc(ba->d_Hll, 6 * c)); ACK(dev_alloc(ba->d_bl, 3 * c));
+        ba->capM = c;
+    }
+    if (Os > ba->capO) {
+        const size_t c = Os + Os / 8;
+        ACK(dev_alloc(ba->d_act, c)); ACK(dev_alloc(ba->d_pos, c)); ACK(dev_alloc(ba->d_chi, c)); ACK(dev_alloc(ba->d_opose, c)); ACK(dev_alloc(ba->d_orig, c));
+        ACK(dev_alloc(ba->d_uv, c)); ACK(dev_alloc(ba->d_isg, c)); ACK(dev_alloc(ba->d_W, 18 * c)); ACK(dev_alloc(ba->d_A, 21 * c)); ACK(dev_alloc(ba->d_g, 6 * c));
+        ba->capO = c;
+    }
+    if (Es > ba->capE) {
+        const size_t c = Es + Es / 8;
+        ACK(dev_alloc(ba->d_ea, c)); ACK(dev_alloc(ba->d_eb, c)); ACK(dev_alloc(ba->d_ept, c));
+        ba->capE = c;
+    }
+    if (nch > ba->capC) { ACK(dev_alloc(ba->d_chunks, nch + nch / 8)); ba->capC = nch + nch / 8; }
+    {
+        const size_t want = std::max<size_t>(nch * dsc::kBaDiag, (size_t)ba->sms * 8 * 2 + 16);
+        if (want > ba->part_cap) { ACK(dev_alloc(ba->d_part, want + want / 8)); ba->part_cap = want + want / 8; }
+    }
     ba->h_part.assign(ba->part_cap, 0.0);
     std::vector<dsc::CamF> hc((size_t)K);
     std::vector<unsigned char> hf((size_t)K);
@@ -298,7 +323,7 @@ extern "C" int dsc_ba_optimize(dsc_ba* ba, int n_iters, double huber_delta, dsc_
     for (int it = 0; it < n_iters; ++it) {
         // ---- linearise at the current estimate
         dsc::ba_linearize_kernel<<<nbm, dsc::kThreads, 0, ba->stream>>>(M, ba->d_ptr, ba->d_opose, ba->d_uv, ba->d_isg, ba->d_act, ba->d_X, ba->d_pose,
-                                                                     ba->d_cam, ba->d_free, delta, pf, ba->d_Hll, ba->d_bl, ba->d_W, ba->d_A, ba->d_g, ba->d_part);
+                                                                     ba->d_cam, ba->d_free, delta, pf, (size_t)std::max<long long>(ba->O, 1), ba->d_Hll, ba->d_bl, ba->d_W, ba->d_A, ba->d_g, ba->d_part);
         ba->launches++;
         ACK(cudaGetLastError());
         ACK(cudaMemcpyAsync(ba->h_part.data(), ba->d_part, sizeof(double) * 2 * (size_t)nbm, cudaMemcpyDeviceToHost, ba->stream));
@@ -315,7 +340,7 @@ extern "C" int dsc_ba_optimize(dsc_ba* ba, int n_iters, double huber_delta, dsc_
             bool ok = true;
             if (nch > 0) {
                 dsc::ba_schur_kernel<<<nch, dsc::kThreads, 0, ba->stream>>>(ba->d_chunks, ba->d_ea, ba->d_eb, ba->d_ept, ba->d_Hll, ba->d_bl, ba->d_W, ba->d_A, ba->d_g,
-                                                                         lambda, pf ? 0 : 1, ba->d_part);
+                                                                         lambda, pf ? 0 : 1, (size_t)std::max<long long>(ba->O, 1), ba->d_part);
                 ba->launches++;
                 ACK(cudaGetLastError());
                 ACK(cudaMemcpyAsync(ba->h_part.data(), ba->d_part, sizeof(double) * (size_t)nch * dsc::kBaDiag, cudaMemcpyDeviceToHost, ba->stream));
@@ -368,7 +393,7 @@ extern "C" int dsc_ba_optimize(dsc_ba* ba, int n_iters, double huber_delta, dsc_
                 }
                 ACK(cudaMemcpyAsync(ba->d_dP, dP.data(), sizeof(double) * dP.size(), cudaMemcpyHostToDevice, ba->stream));
                 dsc::ba_backsub_kernel<<<nbm, dsc::kThreads, 0, ba->stream>>>(M, ba->d_ptr, ba->d_opose, ba->d_X, ba->d_Hll, ba->d_bl, ba->d_W, ba->d_dP, lambda, pf,
-                                                                           ba->d_Xt, ba->d_part);
+                                                                           (size_t)std::max<long long>(ba->O, 1), ba->d_Xt, ba->d_part);
                 ba->launches++;
                 ACK(cudaGetLastError());
                 ACK(cudaMemcpyAsync(ba->h_part.data(), ba->d_part, sizeof(double) * (size_t)nbm, cudaMemcpyDeviceToHost, ba->stream));

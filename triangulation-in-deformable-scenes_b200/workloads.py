@@ -146,3 +146,41 @@ def make_scene(workload, n, seed=0):
         raise ValueError(f"unknown workload {workload!r}")
     sc["workload"] = workload
     return sc
+
+
+def _rodrigues(w):
+    w = np.asarray(w, np.float64)
+    th = np.linalg.norm(w)
+    K = np.array([[0, -w[2], w[1]], [w[2], 0, -w[0]], [-w[1], w[0], 0]])
+    if th < 1e-12:
+        return np.eye(3) + K
+    return np.eye(3) + np.sin(th) / th * K + (1 - np.cos(th)) / (th * th) * (K @ K)
+
+
+def _quat_of(R):
+    w = np.sqrt(max(0.0, 1.0 + R[0, 0] + R[1, 1] + R[2, 2])) / 2      # small rotations only: w > 0
+    return np.array([(R[2, 1] - R[1, 2]) / (4 * w), (R[0, 2] - R[2, 0]) / (4 * w), (R[1, 0] - R[0, 1]) / (4 * w), w])
+
+
+def ba_scene(n_points, n_views=2, seed=0, cam=SIM_CAM, px_sigma=1.0, pose_noise=0.003, point_noise=0.001):
+    """Classic bundle adjustment: n_views key frames looking at a sheet of n_points map points, every point seen
+    from every view; noisy key points (1 px, one decimal), perturbed poses (key frame 0 exact and fixed) and points."""
+    rng = np.random.default_rng(seed)
+    X = np.stack([rng.normal(0, 0.05, n_points), rng.normal(0, 0.05, n_points), rng.normal(0.35, 0.02, n_points)], 1)
+    poses7, obs_pose, obs_point, uv = [], [], [], []
+    for k in range(n_views):
+        R = _rodrigues(rng.normal(0, 0.05, 3) * (k > 0))
+        t = np.array([0.04 * k, 0.01 * k, 0.005 * k])
+        pr = kb8_project64(cam, X @ R.T + t)
+        uv.append(np.round((pr + rng.normal(0, px_sigma, pr.shape)) * 10) / 10)
+        obs_pose.append(np.full(n_points, k, np.int32))
+        obs_point.append(np.arange(n_points, dtype=np.int32))
+        if k > 0:
+            R = _rodrigues(rng.normal(0, pose_noise, 3)) @ R
+            t = t + rng.normal(0, pose_noise, 3)
+        poses7.append(np.concatenate([_quat_of(R), t]))
+    fixed = np.zeros(n_views, bool)
+    fixed[0] = True
+    return dict(poses7=np.array(poses7), pose_fixed=fixed, cams=[(0, np.asarray(cam, np.float32))] * n_views,
+                X=X + rng.normal(0, point_noise, X.shape), obs_pose=np.concatenate(obs_pose), obs_point=np.concatenate(obs_point),
+                obs_uv=np.concatenate(uv).astype(np.float32), obs_isg=np.ones(n_views * n_points, np.float32))
