@@ -153,34 +153,51 @@ extern "C" int dsc_ba_upload(dsc_ba* ba, int n_poses, const double* poses7, cons
     {
         std::vector<int> cur(ptr.begin(), ptr.end() - 1);
         for (long long o = 0; o < O; ++o) ba->perm[(size_t)cur[obs_point[o]]++] = (int)o;
+#pragma omp parallel for schedule(static)
         for (int j = 0; j < M; ++j)
-            std::sort(ba->perm.begin() + ptr[j], ba->perm.begin() + ptr[(size_t)j + 1],
-                      [&](int a, int b) { return obs_pose[a] != obs_pose[b] ? obs_pose[a] < obs_pose[b] : a < b; });
+            if (ptr[(size_t)j + 1] - ptr[j] > 1)
+                std::sort(ba->perm.begin() + ptr[j], ba->perm.begin() + ptr[(size_t)j + 1],
+                          [&](int a, int b) { return obs_pose[a] != obs_pose[b] ? obs_pose[a] < obs_pose[b] : a < b; });
     }
     std::vector<int> opose((size_t)O);
     std::vector<float2> uv((size_t)O);
     std::vector<float> isg((size_t)O);
+#pragma omp parallel for schedule(static)
     for (long long s = 0; s < O; ++s) {
         const int o = ba->perm[(size_t)s];
         opose[(size_t)s] = obs_pose[o];
         uv[(size_t)s] = make_float2(obs_uv[2 * (size_t)o], obs_uv[2 * (size_t)o + 1]);
         isg[(size_t)s] = obs_inv_sigma2 ? obs_inv_sigma2[o] : 1.0f;
     }
-    for (int j = 0; j < M; ++j)
-        for (int s = ptr[j] + 1; s < ptr[(size_t)j + 1]; ++s)
-            if (opose[(size_t)s] == opose[(size_t)s - 1]) return bafail(ba, DSC_ERR_INVALID_ARG, "a point is observed twice from the same pose");
-    // ---- entries of the reduced system: pairs (a <= b) of observations of one point from FREE poses, sorted by (a, b)
+    // ---- entries of the reduced system: pairs (a <= b) of observations of one point from FREE poses, sorted by (a, b);
+    // counted per point, placed by a prefix sum (threads), then a stable counting sort by pair
     struct Ent { int a, b, oa, ob, pt; };
-    std::vector<Ent> ents;
-    for (int j = 0; j < M; ++j)
+    std::vector<size_t> eoff((size_t)M + 1, 0);
+    int twice = 0;
+#pragma omp parallel for schedule(static) reduction(| : twice)
+    for (int j = 0; j < M; ++j) {
+        size_t f = 0;
+        for (int s = ptr[j]; s < ptr[(size_t)j + 1]; ++s) {
+            if (s > ptr[j] && opose[(size_t)s] == opose[(size_t)s - 1]) twice |= 1;
+            if (!ba->fixed[opose[(size_t)s]]) ++f;
+        }
+        eoff[(size_t)j + 1] = ba->points_fixed ? f : f * (f + 1) / 2;
+    }
+    if (twice) return bafail(ba, DSC_ERR_INVALID_ARG, "a point is observed twice from the same pose");
+    for (int j = 0; j < M; ++j) eoff[(size_t)j + 1] += eoff[j];
+    std::vector<Ent> ents(eoff[M]);
+#pragma omp parallel for schedule(static)
+    for (int j = 0; j < M; ++j) {
+        size_t at = eoff[j];
         for (int s = ptr[j]; s < ptr[(size_t)j + 1]; ++s) {
             if (ba->fixed[opose[(size_t)s]]) continue;
             for (int t = s; t < ptr[(size_t)j + 1]; ++t) {
                 if (ba->fixed[opose[(size_t)t]]) continue;
                 if (t > s && ba->points_fixed) continue;            // no coupling between poses without free points
-                ents.push_back({opose[(size_t)s], opose[(size_t)t], s, t, j});
+                ents[at++] = Ent{opose[(size_t)s], opose[(size_t)t], s, t, j};
             }
         }
+    }
     {   // stable counting sort by (a, b): the entries of a segment stay in point order
         std::vector<size_t> start((size_t)K * K + 1, 0);
         for (const Ent& e : ents) start[(size_t)e.a * K + e.b + 1]++;
@@ -201,7 +218,8 @@ extern "C" int dsc_ba_upload(dsc_ba* ba, int n_poses, const double* poses7, cons
         }
         e = f;
     }
-    for (size_t e = 0; e < ents.size(); ++e) { ea[e] = ents[e].oa; eb[e] = ents[e].ob; ept[e] = ents[e].pt; }
+#pragma omp parallel for schedule(static)
+    for (long long e = 0; e < (long long)ents.size(); ++e) { ea[(size_t)e] = ents[(size_t)e].oa; eb[(size_t)e] = ents[(size_t)e].ob; ept[(size_t)e] = ents[(size_t)e].pt; }
     // ---- device buffers
     const size_t Os = (size_t)std::max<long long>(O, 1), Ms = (size_t)std::max(M, 1), Es = std::max<size_t>(ents.size(), 1);
     const size_t nch = std::max<size_t>(ba->chunks.size(), 1);
@@ -240,6 +258,7 @@ extern "C" int dsc_ba_upload(dsc_ba* ba, int n_poses, const double* poses7, cons
         hf[k] = ba->fixed[k] ? 0 : 1;
     }
     std::vector<double4> hx((size_t)M);
+#pragma omp parallel for schedule(static)
     for (int j = 0; j < M; ++j) hx[j] = make_double4(X[3 * (size_t)j], X[3 * (size_t)j + 1], X[3 * (size_t)j + 2], 0.0);
     ACK(cudaMemcpyAsync(ba->d_cam, hc.data(), sizeof(dsc::CamF) * (size_t)K, cudaMemcpyHostToDevice, ba->stream));
     ACK(cudaMemcpyAsync(ba->d_free, hf.data(), (size_t)K, cudaMemcpyHostToDevice, ba->stream));
