@@ -5,8 +5,10 @@
 // Layout: the observations are sorted by map point (CSR pt_ptr): one thread owns a point, walks its observations and keeps
 // the point's 3x3 block in registers.  Per observation the linearisation stores the pose-side blocks
 //   A = w Jp^T Jp (21, packed), g = -w Jp^T e (6), W = w Jp^T Jx (6x3)
-// (component-major: block component c of observation o at [c * O + o], so the threads of a warp -- consecutive points, whose
-// observations are consecutive -- write and read consecutive addresses) and per point Hll (6, packed) and bl (3).  The reduced camera system S = Hpp - Hpl (Hll + lambda)^-1 Hlp is summed over
+// (component-major and RANK-major: component c of the s-th observation of point j lives at [c * O + slot], slot = ob_slot[o] =
+// first slot of rank s + the number of earlier points with more than s observations -- the threads of a warp, consecutive
+// points at the same rank, write whole 32-byte sectors in one instruction; interleaving the ranks left half-written sectors
+// in L2 long enough to be evicted: 2.1x the algorithmic DRAM traffic) and per point Hll (6, packed) and bl (3).  The reduced camera system S = Hpp - Hpl (Hll + lambda)^-1 Hlp is summed over
 // "entries": pairs of observations of the same point seen from free poses a <= b, sorted by (a, b) on the host, cut into
 // chunks of one block each -- every sum is a fixed-order two-stage reduction (no atomics), the per-chunk partials are
 // folded in order on the host, which also factorises the small system (6 x free poses).
@@ -67,9 +69,9 @@ DSC_D void ba_edge(const CamF& cam, const BaPose& T, D3 X, float u, float v, dou
 // per point: Hll, bl; per observation: A, g, W.  part[grid][2] = {sum of robust chi2, max diagonal of Hll}
 __global__ void __launch_bounds__(kThreads)
 ba_linearize_kernel(int M, const int* __restrict__ pt_ptr, const int* __restrict__ ob_pose, const float2* __restrict__ ob_uv,
-                    const float* __restrict__ ob_isg, const unsigned char* __restrict__ ob_act, const double4* __restrict__ X,
-                    const BaPose* __restrict__ poses, const CamF* __restrict__ cams, const unsigned char* __restrict__ pose_free,
-                    double delta, int points_fixed, size_t O, double* __restrict__ Hll, double* __restrict__ bl, double* __restrict__ W,
+                    const float* __restrict__ ob_isg, const unsigned char* __restrict__ ob_act, const int* __restrict__ ob_slot,
+                    const double4* __restrict__ X, const BaPose* __restrict__ poses, const CamF* __restrict__ cams,
+                    const unsigned char* __restrict__ pose_free, double delta, int points_fixed, size_t O, double* __restrict__ Hll, double* __restrict__ bl, double* __restrict__ W,
                     double* __restrict__ A, double* __restrict__ g, double* __restrict__ part) {
     __shared__ double sm[2 * (kThreads / 32)];
     double acc[1] = {0.0};
@@ -79,9 +81,10 @@ ba_linearize_kernel(int M, const int* __restrict__ pt_ptr, const int* __restrict
         const D3 Xw = d3(x4.x, x4.y, x4.z);
         double h[6] = {0, 0, 0, 0, 0, 0}, b3[3] = {0, 0, 0};
         for (int o = pt_ptr[j]; o < pt_ptr[j + 1]; ++o) {
-            double* Wo = W + (size_t)o;                 // component c at Wo[c * O]
-            double* Ao = A + (size_t)o;
-            double* go = g + (size_t)o;
+            const size_t sl = (size_t)ob_slot[o];
+            double* Wo = W + sl;                        // component c at Wo[c * O]
+            double* Ao = A + sl;
+            double* go = g + sl;
             const int k = ob_pose[o];
             const bool live = ob_act[o] != 0;
             const bool fr = live && pose_free[k] != 0;
@@ -131,7 +134,7 @@ ba_linearize_kernel(int M, const int* __restrict__ pt_ptr, const int* __restrict
     }
 }
 
-// one block per chunk of entries; part[chunk][kBaDiag]
+// one block per chunk of entries (en_a / en_b: storage slots of the two observations); part[chunk][kBaDiag]
 __global__ void __launch_bounds__(kThreads)
 ba_schur_kernel(const BaEntryChunk* __restrict__ chunks, const int* __restrict__ en_a, const int* __restrict__ en_b,
                 const int* __restrict__ en_pt, const double* __restrict__ Hll, const double* __restrict__ bl,
@@ -185,7 +188,7 @@ ba_schur_kernel(const BaEntryChunk* __restrict__ chunks, const int* __restrict__
 
 // dx_l = (Hll + lambda)^-1 (bl - sum_o W_o^T dp[pose(o)]);  Xt = X + dx_l;  part[grid] = sum dx_l . (lambda dx_l + bl)
 __global__ void __launch_bounds__(kThreads)
-ba_backsub_kernel(int M, const int* __restrict__ pt_ptr, const int* __restrict__ ob_pose, const double4* __restrict__ X,
+ba_backsub_kernel(int M, const int* __restrict__ pt_ptr, const int* __restrict__ ob_pose, const int* __restrict__ ob_slot, const double4* __restrict__ X,
                   const double* __restrict__ Hll, const double* __restrict__ bl, const double* __restrict__ W,
                   const double* __restrict__ dP /*[K][6]*/, double lambda, int points_fixed, size_t O, double4* __restrict__ Xt,
                   double* __restrict__ part) {
@@ -198,7 +201,7 @@ ba_backsub_kernel(int M, const int* __restrict__ pt_ptr, const int* __restrict__
             D3 r = d3(bl[3 * (size_t)j], bl[3 * (size_t)j + 1], bl[3 * (size_t)j + 2]);
             const D3 b3 = r;
             for (int o = pt_ptr[j]; o < pt_ptr[j + 1]; ++o) {
-                const double* Wo = W + (size_t)o;
+                const double* Wo = W + (size_t)ob_slot[o];
                 const double* dp = dP + 6 * (size_t)ob_pose[o];
 #pragma unroll
                 for (int q = 0; q < 6; ++q) {

@@ -24,7 +24,7 @@ struct dsc_ba {
     dsc::CamF* d_cam = nullptr;
     unsigned char *d_free = nullptr, *d_act = nullptr, *d_pos = nullptr;
     double4 *d_X = nullptr, *d_Xt = nullptr;
-    int *d_ptr = nullptr, *d_opose = nullptr, *d_orig = nullptr, *d_ea = nullptr, *d_eb = nullptr, *d_ept = nullptr;
+    int *d_ptr = nullptr, *d_opose = nullptr, *d_orig = nullptr, *d_slot = nullptr, *d_ea = nullptr, *d_eb = nullptr, *d_ept = nullptr;
     float2* d_uv = nullptr;
     float* d_isg = nullptr;
     double *d_Hll = nullptr, *d_bl = nullptr, *d_W = nullptr, *d_A = nullptr, *d_g = nullptr, *d_part = nullptr, *d_dP = nullptr, *d_chi = nullptr;
@@ -106,7 +106,7 @@ extern "C" void dsc_ba_destroy(dsc_ba* ba) {
     if (!ba) return;
     cudaSetDevice(ba->device);
     dev_free(ba->d_pose); dev_free(ba->d_pose_t); dev_free(ba->d_cam); dev_free(ba->d_free); dev_free(ba->d_act); dev_free(ba->d_pos);
-    dev_free(ba->d_X); dev_free(ba->d_Xt); dev_free(ba->d_ptr); dev_free(ba->d_opose); dev_free(ba->d_orig); dev_free(ba->d_ea);
+    dev_free(ba->d_X); dev_free(ba->d_Xt); dev_free(ba->d_ptr); dev_free(ba->d_opose); dev_free(ba->d_orig); dev_free(ba->d_slot); dev_free(ba->d_ea);
     dev_free(ba->d_eb); dev_free(ba->d_ept); dev_free(ba->d_uv); dev_free(ba->d_isg); dev_free(ba->d_Hll); dev_free(ba->d_bl);
     dev_free(ba->d_W); dev_free(ba->d_A); dev_free(ba->d_g); dev_free(ba->d_part); dev_free(ba->d_dP); dev_free(ba->d_chi); dev_free(ba->d_chunks);
     if (ba->ev0) cudaEventDestroy(ba->ev0);
@@ -169,6 +169,20 @@ extern "C" int dsc_ba_upload(dsc_ba* ba, int n_poses, const double* poses7, cons
         uv[(size_t)s] = make_float2(obs_uv[2 * (size_t)o], obs_uv[2 * (size_t)o + 1]);
         isg[(size_t)s] = obs_inv_sigma2 ? obs_inv_sigma2[o] : 1.0f;
     }
+    // ---- storage slots of the per-observation blocks, rank-major: all first observations in point order, then all second ones, ...
+    std::vector<int> slot((size_t)O);
+    {
+        int maxdeg = 0;
+        for (int j = 0; j < M; ++j) maxdeg = std::max(maxdeg, ptr[(size_t)j + 1] - ptr[j]);
+        std::vector<long long> rank_count((size_t)maxdeg + 1, 0);
+        for (int j = 0; j < M; ++j) rank_count[(size_t)(ptr[(size_t)j + 1] - ptr[j])]++;       // points of each degree
+        std::vector<long long> rank_base((size_t)maxdeg + 1, 0);                              // first slot of rank s
+        long long alive = M - rank_count[0], at = 0;
+        for (int sdx = 0; sdx < maxdeg; ++sdx) { rank_base[sdx] = at; at += alive; alive -= rank_count[(size_t)sdx + 1]; }
+        std::vector<long long> next(rank_base.begin(), rank_base.end());
+        for (int j = 0; j < M; ++j)
+            for (int sdx = 0; sdx < ptr[(size_t)j + 1] - ptr[j]; ++sdx) slot[(size_t)ptr[j] + sdx] = (int)next[sdx]++;
+    }
     // ---- entries of the reduced system: pairs (a <= b) of observations of one point from FREE poses, sorted by (a, b);
     // counted per point, placed by a prefix sum (threads), then a stable counting sort by pair
     struct Ent { int a, b, oa, ob, pt; };
@@ -219,7 +233,7 @@ extern "C" int dsc_ba_upload(dsc_ba* ba, int n_poses, const double* poses7, cons
         e = f;
     }
 #pragma omp parallel for schedule(static)
-    for (long long e = 0; e < (long long)ents.size(); ++e) { ea[(size_t)e] = ents[(size_t)e].oa; eb[(size_t)e] = ents[(size_t)e].ob; ept[(size_t)e] = ents[(size_t)e].pt; }
+    for (long long e = 0; e < (long long)ents.size(); ++e) { ea[(size_t)e] = slot[(size_t)ents[(size_t)e].oa]; eb[(size_t)e] = slot[(size_t)ents[(size_t)e].ob]; ept[(size_t)e] = ents[(size_t)e].pt; }
     // ---- device buffers
     const size_t Os = (size_t)std::max<long long>(O, 1), Ms = (size_t)std::max(M, 1), Es = std::max<size_t>(ents.size(), 1);
     const size_t nch = std::max<size_t>(ba->chunks.size(), 1);
@@ -235,7 +249,7 @@ extern "C" int dsc_ba_upload(dsc_ba* ba, int n_poses, const double* poses7, cons
     }
     if (Os > ba->capO) {
         const size_t c = Os + Os / 8;
-        ACK(dev_alloc(ba->d_act, c)); ACK(dev_alloc(ba->d_pos, c)); ACK(dev_alloc(ba->d_chi, c)); ACK(dev_alloc(ba->d_opose, c)); ACK(dev_alloc(ba->d_orig, c));
+        ACK(dev_alloc(ba->d_act, c)); ACK(dev_alloc(ba->d_pos, c)); ACK(dev_alloc(ba->d_chi, c)); ACK(dev_alloc(ba->d_opose, c)); ACK(dev_alloc(ba->d_orig, c)); ACK(dev_alloc(ba->d_slot, c));
         ACK(dev_alloc(ba->d_uv, c)); ACK(dev_alloc(ba->d_isg, c)); ACK(dev_alloc(ba->d_W, 18 * c)); ACK(dev_alloc(ba->d_A, 21 * c)); ACK(dev_alloc(ba->d_g, 6 * c));
         ba->capO = c;
     }
@@ -267,6 +281,7 @@ extern "C" int dsc_ba_upload(dsc_ba* ba, int n_poses, const double* poses7, cons
     if (O) {
         ACK(cudaMemcpyAsync(ba->d_opose, opose.data(), sizeof(int) * (size_t)O, cudaMemcpyHostToDevice, ba->stream));
         ACK(cudaMemcpyAsync(ba->d_orig, ba->perm.data(), sizeof(int) * (size_t)O, cudaMemcpyHostToDevice, ba->stream));
+        ACK(cudaMemcpyAsync(ba->d_slot, slot.data(), sizeof(int) * (size_t)O, cudaMemcpyHostToDevice, ba->stream));
         ACK(cudaMemcpyAsync(ba->d_uv, uv.data(), sizeof(float2) * (size_t)O, cudaMemcpyHostToDevice, ba->stream));
         ACK(cudaMemcpyAsync(ba->d_isg, isg.data(), sizeof(float) * (size_t)O, cudaMemcpyHostToDevice, ba->stream));
         ACK(cudaMemsetAsync(ba->d_act, 1, (size_t)O, ba->stream));
@@ -341,7 +356,7 @@ extern "C" int dsc_ba_optimize(dsc_ba* ba, int n_iters, double huber_delta, dsc_
     std::vector<double> Hpp((size_t)n * n), bp((size_t)n), S((size_t)n * n), rhs((size_t)n), WHW((size_t)n * n), WHb((size_t)n);
     for (int it = 0; it < n_iters; ++it) {
         // ---- linearise at the current estimate
-        dsc::ba_linearize_kernel<<<nbm, dsc::kThreads, 0, ba->stream>>>(M, ba->d_ptr, ba->d_opose, ba->d_uv, ba->d_isg, ba->d_act, ba->d_X, ba->d_pose,
+        dsc::ba_linearize_kernel<<<nbm, dsc::kThreads, 0, ba->stream>>>(M, ba->d_ptr, ba->d_opose, ba->d_uv, ba->d_isg, ba->d_act, ba->d_slot, ba->d_X, ba->d_pose,
                                                                      ba->d_cam, ba->d_free, delta, pf, (size_t)std::max<long long>(ba->O, 1), ba->d_Hll, ba->d_bl, ba->d_W, ba->d_A, ba->d_g, ba->d_part);
         ba->launches++;
         ACK(cudaGetLastError());
@@ -411,7 +426,7 @@ extern "C" int dsc_ba_optimize(dsc_ba* ba, int n_iters, double huber_delta, dsc_
                     dsc::se3_oplus(ba->pose7.data() + 7 * (size_t)k, dp.data() + c0, trial7.data() + 7 * (size_t)k);
                 }
                 ACK(cudaMemcpyAsync(ba->d_dP, dP.data(), sizeof(double) * dP.size(), cudaMemcpyHostToDevice, ba->stream));
-                dsc::ba_backsub_kernel<<<nbm, dsc::kThreads, 0, ba->stream>>>(M, ba->d_ptr, ba->d_opose, ba->d_X, ba->d_Hll, ba->d_bl, ba->d_W, ba->d_dP, lambda, pf,
+                dsc::ba_backsub_kernel<<<nbm, dsc::kThreads, 0, ba->stream>>>(M, ba->d_ptr, ba->d_opose, ba->d_slot, ba->d_X, ba->d_Hll, ba->d_bl, ba->d_W, ba->d_dP, lambda, pf,
                                                                            (size_t)std::max<long long>(ba->O, 1), ba->d_Xt, ba->d_part);
                 ba->launches++;
                 ACK(cudaGetLastError());
