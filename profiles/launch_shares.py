@@ -12,10 +12,10 @@ k, v = h.index("Kernel Name"), h.index("Metric Value")
 names = [r[k].split("(")[0].replace("dsc::", "").split("<")[0] for r in rows[1:]]
 times = [float(r[v].replace(",", "")) for r in rows[1:]]
 per_step = int(sys.argv[2]) if len(sys.argv) > 2 else 30
-lin = [i for i, n in enumerate(names) if n == "linearize_ell_kernel"]
+lin = [i for i, n in enumerate(names) if "linearize_ell_kernel" in n]
 start = lin[-per_step] if len(lin) >= per_step else 0
-# the step ends with the write-back (export_kernel) that follows it
-end = next((i for i in range(lin[-1], len(names)) if names[i] == "export_kernel"), len(names) - 1) + 1
+# the step ends with the write-back (export_kernel) that follows it, if that was captured too
+end = next((i for i in range(lin[-1] if lin else 0, len(names)) if "export_kernel" in names[i]), len(names) - 1) + 1
 agg = collections.OrderedDict()
 for n, t in zip(names[start:end], times[start:end]):
     a = agg.setdefault(n, [0, 0.0])
