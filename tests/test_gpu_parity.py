@@ -519,12 +519,14 @@ def test_non_positive_depth_scale_branch(pkg, ctx):
 
 
 @pytest.mark.gpu
-def test_cluster_pcg_matches_the_per_iteration_kernels(pkg):
-    """Small problems run the whole PCG in one thread-block-cluster launch (dsc_small.cuh); DSC_NO_CLUSTER_PCG=1 keeps
-    the per-iteration kernels of the 1M path.  Same algorithm, different partial-sum partition: the traces agree to
-    rounding, and both agree with the oracle (the other tests)."""
+@pytest.mark.parametrize("n", [2500, 13000])
+def test_cluster_pcg_matches_the_per_iteration_kernels(pkg, n):
+    """Small problems run the whole PCG in one launch (dsc_small.cuh): a thread-block cluster up to 3 k correspondences, a
+    cooperative launch over all SMs with grid barriers up to 120 k; DSC_NO_CLUSTER_PCG=1 keeps the per-iteration kernels of
+    the 1M path.  Same algorithm, different partial-sum partition: the traces agree to rounding, and both agree with the
+    oracle (the other tests)."""
     import os
-    sc = scenes.tube_scene(2500, seed=61, depth_sigma=0.0003)
+    sc = scenes.tube_scene(n, seed=61, depth_sigma=0.0003)
     p, keep = scenes.problem_from_scene(sc, "knn", 8, min_cos=0.99999)
     w = edges.Weights(rep=1.0, arap=1.0e7, depth_sigma=0.0003)
     res = []

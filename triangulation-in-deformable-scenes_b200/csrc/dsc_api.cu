@@ -115,6 +115,8 @@ struct dsc_ctx {
     bool use_graphs = true;
     int small_cluster = 0;                           // CTAs of the one-launch PCG of small problems (0 = not available)
     int small_max_rows = kSmallMaxRows;              // largest problem that takes that path (DSC_SMALL_MAX_ROWS overrides)
+    int grid_max_rows = 0;                           // above small_max_rows and up to this: the same solve by a cooperative launch over all SMs (0 = off)
+    int grid_blocks = 0;
     int solver = DSC_SOLVER_AUTO;                    // dense Cholesky for small problems, PCG above (dsc_set_solver)
     double *dnH = nullptr, *dnA = nullptr, *dn_rhs = nullptr, *dn_sol = nullptr, *dn_l11 = nullptr;
     int dn_cap = 0;
@@ -355,6 +357,15 @@ extern "C" int dsc_create(int device, dsc_ctx** out) {
         // tuning knobs: cluster size (1..16) and the size limit of the one-launch path
         if (const char* cs = std::getenv("DSC_CLUSTER")) ctx->small_cluster = std::max(1, std::min(kSmallCluster, std::atoi(cs)));
         if (const char* mr = std::getenv("DSC_SMALL_MAX_ROWS")) ctx->small_max_rows = std::max(0, std::atoi(mr));
+        // grid-wide variant: needs cooperative launch; one CTA per SM (254 registers x 256 threads)
+        int coop = 0, per_sm = 0;
+        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device);
+        if (coop && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pcg_grid_kernel, kThreads, 0) == cudaSuccess && per_sm > 0) {
+            ctx->grid_blocks = ctx->sms * per_sm;
+            ctx->grid_max_rows = kGridMaxRows;
+            if (const char* gr = std::getenv("DSC_GRID_MAX_ROWS")) ctx->grid_max_rows = std::max(0, std::atoi(gr));
+        }
+        cudaGetLastError();
     }
     if (cudaFuncSetAttribute(rotations_ell_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWinBytes) != cudaSuccess ||
         cudaFuncSetAttribute(cost_ell_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWinBytes) != cudaSuccess ||
@@ -1409,12 +1420,31 @@ static int run_linearize(dsc_ctx* ctx, const WeightsDev& W, LinGlobal* hlin) {
 // PCG solve of (H + lambda I) dx = b in two entry points so that a solve can be paused at a loose tolerance,
 // inspected (trial cost) and resumed to the tight one: begin = preconditioner + r0/z0 + first operator
 // application; resume = iterate until sqrt(r.z / r0.z0) <= rtol, breakdown or max_iters.
-static bool small_active(const dsc_ctx* ctx) { return ctx->small_cluster > 0 && ctx->n <= ctx->small_max_rows && !f32(ctx) && !ctx->sharded; }
+static bool grid_pcg(const dsc_ctx* ctx) { return ctx->grid_blocks > 0 && ctx->n > ctx->small_max_rows && ctx->n <= ctx->grid_max_rows; }
+static bool small_active(const dsc_ctx* ctx) {
+    return !f32(ctx) && !ctx->sharded && ((ctx->small_cluster > 0 && ctx->n <= ctx->small_max_rows) || grid_pcg(ctx));
+}
 
 // one launch = the whole solve (or its continuation after a pause) by a single thread-block cluster (dsc_small.cuh)
 static int small_launch(dsc_ctx* ctx, const WeightsDev& W, int fresh) {
     CgVecs v = make_vecs(ctx);
     double* Ginv = ctx->small + 48;
+    if (grid_pcg(ctx)) {                                  // the whole device, grid barriers (pcg_grid_kernel)
+        int n = ctx->n, mi = ctx->pcg.max_iters;
+        const double *P = ctx->P, *Je = ctx->Je, *U = ctx->U, *b = ctx->b, *D = ctx->D;
+        const int *sp = ctx->sliceptr, *ec = ctx->ecol;
+        const Globals* G = ctx->Gcur;
+        const LinGlobal* lin = ctx->lin;
+        PairDev pr = ctx->pair;
+        WeightsDev Wc = W;
+        void* args[] = {&n, &fresh, &mi, &P, &Je, &U, &sp, &ec, &G, &pr, &Wc, &b, &D, &lin, &ctx->Minv, &Ginv, &ctx->errflag, &v,
+                        &ctx->gpart[0], &ctx->gpart[1], &ctx->dpart, &ctx->bpart, &ctx->ctl};
+        const int blocks = std::min(ctx->grid_blocks, std::max(1, (n + 31) / 32));
+        cudaError_t e = cudaLaunchCooperativeKernel((const void*)pcg_grid_kernel, dim3(blocks), dim3(kThreads), args, 0, ctx->stream);
+        if (e != cudaSuccess) return fail(ctx, DSC_ERR_CUDA, std::string("pcg_grid_kernel -> ") + cudaGetErrorString(e));
+        ctx->launches++;
+        return DSC_OK;
+    }
     for (;;) {
         cudaLaunchConfig_t cfg{};
         cfg.gridDim = dim3(ctx->small_cluster); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = 0; cfg.stream = ctx->stream;

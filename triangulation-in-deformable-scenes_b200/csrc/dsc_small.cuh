@@ -18,16 +18,18 @@ namespace dsc {
 
 namespace cg = cooperative_groups;
 
-constexpr int kSmallMaxRows = 8192;          // above this the per-iteration kernels of the large path are faster (measured)
+constexpr int kGridMaxRows = 120000;             // the grid-wide one-launch solve (pcg_grid_kernel) up to this many rows (0 = off; DSC_GRID_MAX_ROWS)
+constexpr int kSmallMaxRows = 3072;          // above this the grid-wide variant is faster (measured: 2 k 223 vs 217 LM it/s, 4 k 96 vs 103, 8 k 168 vs 244)
 constexpr int kSmallBatch = 4;              // ELL columns whose loads are in flight together
 constexpr int kSmallCluster = 16;            // CTAs per cluster (non-portable size; 8 is tried if 16 cannot launch)
 
 DSC_D void load6_l2(const double* V, int i, D3& a, D3& b) { load6_t<false>(V, i, a, b); }
-// sum of part[0 .. nb), nb <= 32, by every warp on its own: lane c loads entry c (one L2 round trip for all of them,
+// sum of part[0 .. nb) by every warp on its own: lane c loads entry c (one L2 round trip for all of them,
 // a serial loop would pay one per entry), then a fixed butterfly: the same result in every lane of every warp and CTA
 DSC_D double sum_small(const double* part, int nb) {
     const int lane = threadIdx.x & 31;
     double s = lane < nb ? __ldcg(part + lane) : 0.0;
+    for (int i = lane + 32; i < nb; i += 32) s += __ldcg(part + i);     // (the grid-wide variant has one partial per SM)
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     return s;
@@ -174,8 +176,8 @@ DSC_D void cluster_spmv(int rank, int cs, const ClusterPcgArgs& A, const double*
 }
 
 // start of a solve: preconditioner, r = b, z = M^-1 r, gamma partial, first operator application
-template <bool kRO>
-DSC_D void cluster_pcg_begin(cg::cluster_group& cluster, const ClusterPcgArgs& A, const double* Rg, const PairDev& pr,
+template <bool kRO, typename Group>
+DSC_D void cluster_pcg_begin(Group& cluster, const ClusterPcgArgs& A, const double* Rg, const PairDev& pr,
                              const WeightsDev& W, double lambda, ClusterPcgState& st) {
     __shared__ double sm[kThreads / 32];
     const int rank = (int)cluster.block_rank(), cs = (int)cluster.num_blocks();
@@ -220,8 +222,8 @@ DSC_D void cluster_pcg_begin(cg::cluster_group& cluster, const ClusterPcgArgs& A
 
 // iterations: update (Chronopoulos-Gear step), barrier, operator, barrier -- until gamma <= rtol2 gamma0 (converged),
 // breakdown, or max_iters updates in total.  Resumable: call again with a tighter rtol2 to continue the same solve.
-template <bool kRO>
-DSC_D void cluster_pcg_run(cg::cluster_group& cluster, const ClusterPcgArgs& A, const double* Rg, const PairDev& pr,
+template <bool kRO, typename Group>
+DSC_D void cluster_pcg_run(Group& cluster, const ClusterPcgArgs& A, const double* Rg, const PairDev& pr,
                            const WeightsDev& W, double lambda, double rtol2, int max_iters, ClusterPcgState& st) {
     __shared__ double sm[kThreads / 32];
     __shared__ double wg[8], rgn[8];
@@ -345,6 +347,44 @@ pcg_cluster_kernel(int n, int fresh, int max_iters, const double* __restrict__ P
     cluster_pcg_run<true>(cluster, A, Rg, pr, W, lambda, rtol2, max_iters, st);
     // every CTA has read the control block before any CTA can get here (at least one cluster barrier lies between)
     if (cluster.block_rank() == 0 && threadIdx.x == 0) {
+        ctl->iters = st.k;
+        ctl->gamma0 = st.gamma0;
+        ctl->sc[(st.k & 1) ^ 1].gamma_prev = st.gprev; ctl->sc[(st.k & 1) ^ 1].alpha_prev = st.aprev;
+        ctl->converged = st.converged;
+        ctl->breakdown = st.breakdown;
+    }
+}
+
+// The same solve by the WHOLE device: a cooperative launch of one CTA per SM, grid barriers instead of cluster barriers.
+// For pairs between the cluster path and a few hundred thousand correspondences an iteration of the per-iteration kernels
+// is two launches of ~20-30 us each whose duration is latency, not bandwidth; here it is two grid barriers.
+__global__ void __launch_bounds__(kThreads, 1)
+pcg_grid_kernel(int n, int fresh, int max_iters, const double* __restrict__ P, const double* __restrict__ Je,
+                const double* __restrict__ U, const int* __restrict__ sliceptr, const int* __restrict__ ecol,
+                const Globals* __restrict__ Gp, const __grid_constant__ PairDev pr, const __grid_constant__ WeightsDev W,
+                const double* __restrict__ b, const double* __restrict__ D, const LinGlobal* __restrict__ lin,
+                double* Minv, double* Ginv, int* err, CgVecs v, double* gpart0, double* gpart1, double* dpart, double* bpart,
+                CgControl* ctl) {
+    cg::grid_group grid = cg::this_grid();
+    __shared__ double Rg[9];
+    if (threadIdx.x < 9) Rg[threadIdx.x] = Gp->Rg[threadIdx.x];
+    const double lambda = __ldcg(&ctl->lambda);
+    const double rtol2 = __ldcg(&ctl->rtol2);
+    __syncthreads();
+    ClusterPcgArgs A{n, P, Je, U, sliceptr, ecol, b, D, lin, Minv, Ginv, err, v, gpart0, gpart1, dpart, bpart};
+    ClusterPcgState st;
+    if (fresh) {
+        cluster_pcg_begin<true>(grid, A, Rg, pr, W, lambda, st);
+    } else {
+        st.k = __ldcg(&ctl->iters);
+        st.gamma0 = __ldcg(&ctl->gamma0);
+        st.gprev = __ldcg(&ctl->sc[(st.k & 1) ^ 1].gamma_prev);
+        st.aprev = __ldcg(&ctl->sc[(st.k & 1) ^ 1].alpha_prev);
+        st.converged = 0; st.breakdown = 0;
+        grid.sync();                                   // every CTA has read the control block before rank 0 may rewrite it below
+    }
+    cluster_pcg_run<true>(grid, A, Rg, pr, W, lambda, rtol2, max_iters, st);
+    if (grid.block_rank() == 0 && threadIdx.x == 0) {
         ctl->iters = st.k;
         ctl->gamma0 = st.gamma0;
         ctl->sc[(st.k & 1) ^ 1].gamma_prev = st.gprev; ctl->sc[(st.k & 1) ^ 1].alpha_prev = st.aprev;
