@@ -148,15 +148,13 @@ def test_weight_search_nelder_mead_matches_the_oracle_in_both_modes(case):
 @pytest.mark.gpu
 def test_weight_search_modes_walk_the_same_simplices():
     """deformationOptimization with weightsSelection nlopt (config 1): the candidates of a Nelder-Mead step refined together
-    on the batched path (default), one at a time on the batched path, and one at a time on the main context (the round-1
+    on the batched path (DSC_WEIGHT_SEARCH=batch; the default for 601 .. 4096 correspondences), one at a time on the batched path, and one at a time on the main context (the round-1
     path) evaluate the same weights in the same order and end at the same weights"""
     exe = os.path.join(LIB, "dsc_simulation")
     outs = {}
-    for mode in ("", "sequential", "single"):
+    for mode in ("batch", "sequential", "single"):
         env = dict(os.environ)
-        env.pop("DSC_WEIGHT_SEARCH", None)
-        if mode:
-            env["DSC_WEIGHT_SEARCH"] = mode
+        env["DSC_WEIGHT_SEARCH"] = mode
         out = subprocess.run([exe, os.path.join(GOLD, "Simulation_b200.yaml"), os.path.join(GOLD, "config1_original.csv"),
                               os.path.join(GOLD, "config1_moved.csv")], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=env)
         assert out.returncode == 0, out.stderr
@@ -165,7 +163,7 @@ def test_weight_search_modes_walk_the_same_simplices():
         launches = [int(l.split(" in ")[1].split()[0]) for l in out.stdout.splitlines() if l.startswith("Weight search:")]
         js = json.loads(out.stdout[out.stdout.rindex('{"n"'):])
         outs[mode] = (xs, fs, launches, js)
-    xs0, fs0, l0, js0 = outs[""]
+    xs0, fs0, l0, js0 = outs["batch"]
     assert len(xs0) >= 6 and len(fs0) == len(xs0)
     for mode in ("sequential", "single"):
         xs, fs, l, js = outs[mode]

@@ -2220,6 +2220,8 @@ struct dsc_batch {
     double* d_part = nullptr;                // per problem: [kBatchPartStride] linearisation / trial partials
     size_t probs_cap = 0, recs_cap = 0, part_cap = 0;
     int cluster = kSmallCluster, n_clusters = 0;
+    int last_cluster = 0;                    // CTAs per cluster of the last launch (few pairs get larger clusters)
+    bool cluster_forced = false;             // DSC_BATCH_CLUSTER
     dsc_pcg_params pcg{1e-10, 4000, 32};
     int early_levels = 0;
     double early_rtol[4] = {0, 0, 0, 0}, early_margin[4] = {0, 0, 0, 0};
@@ -2266,7 +2268,7 @@ extern "C" int dsc_batch_create(int device, dsc_batch** out) {
     bt->cluster = 4;
     if (const char* cs = std::getenv("DSC_BATCH_CLUSTER")) {
         int v = std::atoi(cs);
-        if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16) bt->cluster = v;
+        if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16) { bt->cluster = v; bt->cluster_forced = true; }
     }
     *out = bt;
     return DSC_OK;
@@ -2290,7 +2292,7 @@ extern "C" int dsc_batch_size(const dsc_batch* bt, int* n_problems, long long* n
     if (!bt) return DSC_ERR_INVALID_ARG;
     if (n_problems) *n_problems = bt->n_problems;
     if (n_points) *n_points = bt->point_offset.empty() ? 0 : bt->point_offset.back();
-    if (cluster_ctas) *cluster_ctas = bt->cluster;
+    if (cluster_ctas) *cluster_ctas = bt->last_cluster ? bt->last_cluster : bt->cluster;
     if (clusters) *clusters = bt->n_clusters;
     return DSC_OK;
 }
@@ -2422,21 +2424,25 @@ extern "C" int dsc_batch_optimize(dsc_batch* bt, const dsc_weights* weights, int
     // most one per pair; the queue balances the load
     cudaLaunchConfig_t cfg{};
     cudaLaunchAttribute at[1];
+    // A few pairs (the weight search: up to four replicas) would leave most SMs idle with 4 CTAs each: larger clusters then
+    int cl = bt->cluster;
+    if (!bt->cluster_forced) while (cl < kSmallCluster && np * cl * 2 <= bt->sms) cl *= 2;
     for (;;) {
         cfg = cudaLaunchConfig_t{};
         cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = kWinBytes; cfg.stream = bt->stream;
         at[0].id = cudaLaunchAttributeClusterDimension;
-        at[0].val.clusterDim.x = bt->cluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        at[0].val.clusterDim.x = cl; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
         cfg.attrs = at; cfg.numAttrs = 1;
-        cfg.gridDim = dim3(bt->cluster);
+        cfg.gridDim = dim3(cl);
         int maxc = 0;
         cudaError_t e = cudaOccupancyMaxActiveClusters(&maxc, lm_batch_kernel, &cfg);
         if (e == cudaSuccess && maxc > 0) { bt->n_clusters = std::min(std::min(maxc, np), 4096); break; }
         cudaGetLastError();
-        if (bt->cluster > 1) { bt->cluster /= 2; continue; }
+        if (cl > 1) { cl /= 2; bt->cluster = std::min(bt->cluster, cl); continue; }
         return bfail(bt, DSC_ERR_CUDA, std::string("no cluster configuration of lm_batch_kernel is schedulable: ") + cudaGetErrorString(e));
     }
-    cfg.gridDim = dim3(bt->n_clusters * bt->cluster);
+    bt->last_cluster = cl;
+    cfg.gridDim = dim3(bt->n_clusters * cl);
     BCK(cudaEventRecord(bt->ev0, bt->stream));
     BCK(cudaLaunchKernelEx(&cfg, lm_batch_kernel, (const BatchProblem*)bt->d_probs, np, prm, bt->d_queue, bt->d_recs, bt->d_res));
     BCK(cudaEventRecord(bt->ev1, bt->stream));

@@ -305,10 +305,9 @@ void write_back(Map* pMap, PairProblem& pp, double* optimizationUpdate) {
 
 // The weight search's refinements on the batched path: K replicas of the gathered pair (same initial state, mesh and
 // rotations) stay resident in one dsc_batch; a Nelder-Mead step refines as many of them as it has candidate weights in
-// ONE launch and reads their pixel sigmas (nloptOptimization.cc:5-37 per candidate).  Pairs above kSearchBatchMax
-// correspondences fill the GPU on their own: they keep the sequential path on the main context.
+// ONE launch and reads their pixel sigmas (nloptOptimization.cc:5-37 per candidate).  Selected by DSC_WEIGHT_SEARCH=batch
+// (see deformationOptimization): on one GPU the sequential search on the main context measured faster.
 constexpr int kSearchReplicas = 4;
-constexpr size_t kSearchBatchMax = 32768;
 struct SearchBatch {
     dsc_batch* bt = nullptr;
     ~SearchBatch() { if (bt) dsc_batch_destroy(bt); }
@@ -686,10 +685,13 @@ void deformationOptimization(std::shared_ptr<Map> pMap, Settings& settings, std:
                 uploaded = true;
             });
             if (uploaded) {
-                // DSC_WEIGHT_SEARCH=sequential: one refinement at a time; =single: additionally on the main context
-                // (the round-1 path).  Default: the step's candidates together on the batched path.
+                // Default (= DSC_WEIGHT_SEARCH=single): one refinement at a time on the main context -- on ONE GPU a refinement
+                // already has the whole device (dense factorisation up to 600 correspondences, one-launch solves above), and it
+                // measured fastest at every size tried.  DSC_WEIGHT_SEARCH=batch: the candidates of a step
+                // together as replicas on the batched path (the arrangement for spare SMs / more GPUs; same walk, tested);
+                // =sequential: one at a time on the batched path.
                 const char* mode = std::getenv("DSC_WEIGHT_SEARCH");
-                const bool on_batch = pp.mp1.size() <= kSearchBatchMax && !(mode && std::string(mode) == "single");
+                const bool on_batch = mode && (std::string(mode) == "batch" || std::string(mode) == "sequential");
                 const bool speculative = on_batch && !(mode && std::string(mode) == "sequential");
                 SearchBatch sb;
                 if (on_batch) sb.upload(pp);
