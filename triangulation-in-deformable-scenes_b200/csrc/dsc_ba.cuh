@@ -186,14 +186,16 @@ ba_schur_kernel(const BaEntryChunk* __restrict__ chunks, const int* __restrict__
         for (int k = 0; k < kBaDiag; ++k) part[(size_t)kBaDiag * blockIdx.x + k] = acc[k];
 }
 
-// dx_l = (Hll + lambda)^-1 (bl - sum_o W_o^T dp[pose(o)]);  Xt = X + dx_l;  part[grid] = sum dx_l . (lambda dx_l + bl)
+// dx_l = (Hll + lambda)^-1 (bl - sum_o W_o^T dp[pose(o)]);  Xt = X + dx_l;  and, in the same pass, the trial's cost at the
+// trial poses: part[grid][2] = {sum dx_l . (lambda dx_l + bl), activeRobustChi2(Xt, poses_t)}
 __global__ void __launch_bounds__(kThreads)
 ba_backsub_kernel(int M, const int* __restrict__ pt_ptr, const int* __restrict__ ob_pose, const int* __restrict__ ob_slot, const double4* __restrict__ X,
                   const double* __restrict__ Hll, const double* __restrict__ bl, const double* __restrict__ W,
                   const double* __restrict__ dP /*[K][6]*/, double lambda, int points_fixed, size_t O, double4* __restrict__ Xt,
-                  double* __restrict__ part) {
-    __shared__ double sm[kThreads / 32];
-    double acc[1] = {0.0};
+                  const float2* __restrict__ ob_uv, const float* __restrict__ ob_isg, const unsigned char* __restrict__ ob_act,
+                  const BaPose* __restrict__ poses_t, const CamF* __restrict__ cams, double delta, double* __restrict__ part) {
+    __shared__ double sm[2 * (kThreads / 32)];
+    double acc[2] = {0.0, 0.0};
     for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < M; j += gridDim.x * blockDim.x) {
         const double4 x4 = X[j];
         D3 dx = d3(0, 0, 0);
@@ -213,10 +215,23 @@ ba_backsub_kernel(int M, const int* __restrict__ pt_ptr, const int* __restrict__
             dx = ba_sym3_mul(Hi, r);
             acc[0] += dx.x * (lambda * dx.x + b3.x) + dx.y * (lambda * dx.y + b3.y) + dx.z * (lambda * dx.z + b3.z);
         }
-        Xt[j] = make_double4(x4.x + dx.x, x4.y + dx.y, x4.z + dx.z, 0.0);
+        const D3 Xn = d3(x4.x + dx.x, x4.y + dx.y, x4.z + dx.z);
+        Xt[j] = make_double4(Xn.x, Xn.y, Xn.z, 0.0);
+        for (int o = pt_ptr[j]; o < pt_ptr[j + 1]; ++o) {
+            if (!ob_act[o]) continue;
+            const int k = ob_pose[o];
+            const float2 uv = ob_uv[o];
+            double e0, e1;
+            F3 xcf;
+            reproj_residual(cams[k], poses_t[k].R, poses_t[k].t, Xn, uv.x, uv.y, e0, e1, xcf);
+            const double chi2 = (double)ob_isg[o] * (e0 * e0 + e1 * e1);
+            double rho0 = chi2, rho1;
+            if (delta > 0.0) huber(chi2, delta, rho0, rho1);
+            acc[1] += rho0;
+        }
     }
-    block_reduce<1>(acc, sm);
-    if (threadIdx.x == 0) part[blockIdx.x] = acc[0];
+    block_reduce<2>(acc, sm);
+    if (threadIdx.x == 0) { part[2 * blockIdx.x] = acc[0]; part[2 * blockIdx.x + 1] = acc[1]; }
 }
 
 // activeRobustChi2 of a state: part[grid]

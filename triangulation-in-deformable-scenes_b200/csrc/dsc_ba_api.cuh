@@ -32,6 +32,8 @@ struct dsc_ba {
     size_t part_cap = 0;
     size_t capK = 0, capM = 0, capO = 0, capE = 0, capC = 0;   // grow-only capacities (no cudaMalloc / cudaFree on a warm handle)
     std::vector<double> h_part;
+    std::vector<dsc::BaPose> h_pose[2];
+    unsigned h_pose_next = 0;
     long long launches = 0;
 };
 
@@ -55,10 +57,12 @@ int ba_grid(const dsc_ba* b, long long n) {
     return (int)std::max(1LL, std::min((n + dsc::kThreads - 1) / dsc::kThreads, (long long)b->sms * 8));
 }
 int ba_upload_poses(dsc_ba* ba, const std::vector<double>& p7, dsc::BaPose* dst) {
-    std::vector<dsc::BaPose> hp((size_t)ba->K);
+    // (a copy from pageable memory is staged before the call returns; the staging vector is a member and is only rewritten
+    // by the next call, which the stream-ordered consumers of this one precede)
+    std::vector<dsc::BaPose>& hp = ba->h_pose[ba->h_pose_next++ & 1];
+    hp.resize((size_t)ba->K);
     for (int k = 0; k < ba->K; ++k) ba_pose_to_dev(p7.data() + 7 * (size_t)k, hp[k]);
     ACK(cudaMemcpyAsync(dst, hp.data(), sizeof(dsc::BaPose) * (size_t)ba->K, cudaMemcpyHostToDevice, ba->stream));
-    ACK(cudaStreamSynchronize(ba->stream));       // (hp is a local)
     return DSC_OK;
 }
 // in-place Cholesky solve of the dense SPD system A x = b (row-major n x n); false if A is not positive definite
@@ -426,17 +430,18 @@ extern "C" int dsc_ba_optimize(dsc_ba* ba, int n_iters, double huber_delta, dsc_
                     dsc::se3_oplus(ba->pose7.data() + 7 * (size_t)k, dp.data() + c0, trial7.data() + 7 * (size_t)k);
                 }
                 ACK(cudaMemcpyAsync(ba->d_dP, dP.data(), sizeof(double) * dP.size(), cudaMemcpyHostToDevice, ba->stream));
-                dsc::ba_backsub_kernel<<<nbm, dsc::kThreads, 0, ba->stream>>>(M, ba->d_ptr, ba->d_opose, ba->d_slot, ba->d_X, ba->d_Hll, ba->d_bl, ba->d_W, ba->d_dP, lambda, pf,
-                                                                           (size_t)std::max<long long>(ba->O, 1), ba->d_Xt, ba->d_part);
-                ba->launches++;
-                ACK(cudaGetLastError());
-                ACK(cudaMemcpyAsync(ba->h_part.data(), ba->d_part, sizeof(double) * (size_t)nbm, cudaMemcpyDeviceToHost, ba->stream));
-                ACK(cudaStreamSynchronize(ba->stream));
-                scale = sp + host_sum(ba->h_part.data(), nbm) + 1e-3;
                 int rc = ba_upload_poses(ba, trial7, ba->d_pose_t);
                 if (rc) return rc;
-                rc = ba_cost(ba, ba->d_Xt, ba->d_pose_t, delta, &temp);
-                if (rc) return rc;
+                // back-substitution of the points and the trial's cost in one pass
+                dsc::ba_backsub_kernel<<<nbm, dsc::kThreads, 0, ba->stream>>>(M, ba->d_ptr, ba->d_opose, ba->d_slot, ba->d_X, ba->d_Hll, ba->d_bl, ba->d_W, ba->d_dP, lambda, pf,
+                                                                           (size_t)std::max<long long>(ba->O, 1), ba->d_Xt, ba->d_uv, ba->d_isg, ba->d_act, ba->d_pose_t,
+                                                                           ba->d_cam, delta, ba->d_part);
+                ba->launches++;
+                ACK(cudaGetLastError());
+                ACK(cudaMemcpyAsync(ba->h_part.data(), ba->d_part, sizeof(double) * 2 * (size_t)nbm, cudaMemcpyDeviceToHost, ba->stream));
+                ACK(cudaStreamSynchronize(ba->stream));
+                scale = sp + host_sum(ba->h_part.data(), nbm, 2, 0) + 1e-3;
+                temp = host_sum(ba->h_part.data(), nbm, 2, 1);
                 if (!std::isfinite(temp)) temp = std::numeric_limits<double>::max();
             }
             rho = (current - temp) / scale;
