@@ -86,6 +86,8 @@ struct dsc_ctx {
     long long nblk = 0, blkcap = 0;
     int slcap = 0;
     double *b = nullptr, *D = nullptr, *U = nullptr, *Minv = nullptr;
+    float* MinvS = nullptr;                      // float copy of the preconditioner blocks the fp64 per-iteration kernels stream (DSC_MINV_F64=1: double)
+    bool minv_float = true;
     double* vec[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // x r z w p s
     double* small = nullptr;              // 6 x 8 global vectors + Ginv(64)
     Globals *Gcur = nullptr, *Gtrial = nullptr;
@@ -350,6 +352,7 @@ extern "C" int dsc_create(int device, dsc_ctx** out) {
     if (cudaMalloc(&ctx->d_box, sizeof(float) * (4 + 4 * kMaxBlocks)) != cudaSuccess) return bail(DSC_ERR_ALLOC);
     cudaMemset(ctx->errflag, 0, sizeof(int));
     ctx->use_graphs = std::getenv("DSC_NO_GRAPHS") == nullptr;
+    ctx->minv_float = std::getenv("DSC_MINV_F64") == nullptr;
     if (std::getenv("DSC_NO_CLUSTER_PCG") == nullptr) {
         // the one-launch PCG of small problems needs a cluster of 16 (non-portable) or 8 CTAs of 256 threads
         ctx->small_cluster = cudaFuncSetAttribute(pcg_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess ? kSmallCluster : 8;
@@ -402,7 +405,7 @@ extern "C" void dsc_destroy(dsc_ctx* ctx) {
     dev_free(ctx->P); dev_free(ctx->Ptrial); dev_free(ctx->P0); dev_free(ctx->Q);
     dev_free(ctx->uv); dev_free(ctx->dm); dev_free(ctx->isg);
     dev_free(ctx->Je); dev_free(ctx->ecol); dev_free(ctx->ewgt); dev_free(ctx->sliceptr); dev_free(ctx->spmv_part);
-    dev_free(ctx->b); dev_free(ctx->D); dev_free(ctx->U); dev_free(ctx->Minv);
+    dev_free(ctx->b); dev_free(ctx->D); dev_free(ctx->U); dev_free(ctx->Minv); dev_free(ctx->MinvS);
     for (auto& v : ctx->vec) dev_free(v);
     for (auto& v : ctx->vecF) dev_free(v);
     dev_free(ctx->JeF); dev_free(ctx->UF); dev_free(ctx->MinvF);
@@ -642,7 +645,7 @@ extern "C" int dsc_problem_upload(dsc_ctx* ctx, const dsc_pair* pair, int n,
         CK(dev_alloc(ctx->uv, N)); CK(dev_alloc(ctx->dm, N)); CK(dev_alloc(ctx->isg, N));
         CK(dev_alloc(ctx->r_uv1, N)); CK(dev_alloc(ctx->r_uv2, N)); CK(dev_alloc(ctx->r_d1, N)); CK(dev_alloc(ctx->r_d2, N));
         CK(dev_alloc(ctx->r_isg1, N)); CK(dev_alloc(ctx->r_isg2, N));
-        CK(dev_alloc(ctx->b, 6 * N)); CK(dev_alloc(ctx->D, 21 * 32 * ((N + 31) / 32))); CK(dev_alloc(ctx->U, (size_t)kURec * 32 * ((N + 31) / 32))); CK(dev_alloc(ctx->Minv, 21 * 32 * ((N + 31) / 32)));
+        CK(dev_alloc(ctx->b, 6 * N)); CK(dev_alloc(ctx->D, 21 * 32 * ((N + 31) / 32))); CK(dev_alloc(ctx->U, (size_t)kURec * 32 * ((N + 31) / 32))); CK(dev_alloc(ctx->Minv, 21 * 32 * ((N + 31) / 32))); CK(dev_alloc(ctx->MinvS, 21 * 32 * ((N + 31) / 32)));
         for (int k = 0; k < 6; ++k) if (!(ctx->sharded && k == 2)) CK(dev_alloc(ctx->vec[k], 6 * N));
         ctx->cap = n;
     }
@@ -1468,6 +1471,11 @@ static int small_launch(dsc_ctx* ctx, const WeightsDev& W, int fresh) {
 // the three PCG kernels in the context's precision (T = storage type of Je, U, Minv and the vectors)
 template <typename T>
 static void launch_init(dsc_ctx* ctx, double lambda) {
+    if (sizeof(T) == 8 && ctx->minv_float) {
+        cg_init_kernel<double, float><<<grid_threads(ctx, (long long)ctx->n), kThreads, 0, ctx->stream>>>(ctx->n, ctx->b, ctx->D, lambda, ctx->lin, ctx->MinvS, ctx->small + 48,
+                                                                                                       ctx->errflag, make_vecs<double>(ctx), ctx->gpart[0], ctx->ctl);
+        return;
+    }
     cg_init_kernel<T><<<grid_threads(ctx, (long long)ctx->n), kThreads, 0, ctx->stream>>>(ctx->n, ctx->b, ctx->D, lambda, ctx->lin, Sel<T>::Minv(ctx), ctx->small + 48,
                                                                                        ctx->errflag, make_vecs<T>(ctx), ctx->gpart[0], ctx->ctl);
 }
@@ -1481,6 +1489,12 @@ static void launch_spmv(dsc_ctx* ctx, const WeightsDev& W, double lambda, const 
 }
 template <typename T>
 static void launch_update(dsc_ctx* ctx, int par, int first, double lambda, int gin, int gout, double rtol2) {
+    if (sizeof(T) == 8 && ctx->minv_float) {
+        cg_update_kernel<double, float><<<grid_threads(ctx, (long long)ctx->n), kThreads, 0, ctx->stream>>>(ctx->n, par, first, ctx->MinvS, ctx->small + 48, ctx->lin, lambda,
+                                                                                                         make_vecs<double>(ctx), ctx->gpart[gin], ctx->gpart[gout], ctx->dpart,
+                                                                                                         ctx->bpart, grid_spmv(ctx, ctx->n), ctx->ctl, rtol2);
+        return;
+    }
     cg_update_kernel<T><<<grid_threads(ctx, (long long)ctx->n), kThreads, 0, ctx->stream>>>(ctx->n, par, first, Sel<T>::Minv(ctx), ctx->small + 48, ctx->lin, lambda, make_vecs<T>(ctx),
                                                                                          ctx->gpart[gin], ctx->gpart[gout], ctx->dpart, ctx->bpart, grid_spmv(ctx, ctx->n),
                                                                                          ctx->ctl, rtol2);
@@ -2028,10 +2042,11 @@ extern "C" int dsc_profile_kernels(dsc_ctx* ctx, const dsc_weights* w, int warm,
     double by[DSC_K_COUNT];
     double S = (double)ctx->nblk * 32.0;            // ELL slots (padding included)
     by[DSC_K_SPMV] = (32.0 + 26.0 * tb) * N + (4.0 + 9.0 * tb) * S;   // X1(32) | z(6) U(14) w(6) values | ELL blocks: col(4) + Je(9 values) per slot (padding included)
-    by[DSC_K_UPDATE] = 87.0 * tb * N;             // read z w p s x r (36 values) + Minv (21), write p s x r z (30)
+    const double mb = (lo || ctx->minv_float) ? 4.0 : 8.0;   // bytes per stored preconditioner value (float also in the fp64 mode)
+    by[DSC_K_UPDATE] = (66.0 * tb + 21.0 * mb) * N;   // read z w p s x r (36 values) + Minv (21), write p s x r z (30)
     by[DSC_K_LINEARIZE] = (488.0 + (lo ? 56.0 : 0.0)) * N + 12.0 * S + (72.0 + (lo ? 36.0 : 0.0)) * E;   // P Q uv dm isg | ecol ewgt per slot | write b D U, Je per edge (+ the float copies in the fp32 mode)
     by[DSC_K_COST] = 136.0 * N + 12.0 * S;         // P Q uv dm isg | ecol ewgt per slot
-    by[DSC_K_PRECOND] = (48.0 + 168.0 + 33.0 * tb) * N;   // preconditioner + PCG start: b D -> Minv (21 values) r z (12)
+    by[DSC_K_PRECOND] = (48.0 + 168.0 + 12.0 * tb + 21.0 * mb) * N;   // preconditioner + PCG start: b D -> Minv (21 values) r z (12)
     by[DSC_K_APPLY] = 224.0 * N;                  // P x b -> Ptrial
     by[DSC_K_ROTATIONS] = 96.0 * N + 12.0 * S;     // P | ecol ewgt per slot | write Q
     auto time_it = [&](int which, auto&& launch) -> int {

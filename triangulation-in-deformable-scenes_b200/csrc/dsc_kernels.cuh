@@ -524,10 +524,12 @@ using CgVecs = CgVecsT<double>;
 
 // Preconditioner and PCG start in one pass over the rows: Minv = (D + lambda I)^-1, r = b, z = Minv r, gamma partial.
 // x, p and s are not written: the first cg_update (first = 1) treats them as zero.
-template <typename T>
+// TM: storage type of the preconditioner blocks (float also in the fp64 mode: any fixed SPD M is a valid preconditioner, the
+// iterations apply the STORED one, and 84 instead of 168 bytes per row and iteration are streamed)
+template <typename T, typename TM = T>
 __global__ void __launch_bounds__(kThreads)
 cg_init_kernel(int n, const double* __restrict__ b, const double* __restrict__ D, double lambda, const LinGlobal* __restrict__ lin,
-               T* __restrict__ Minv, double* __restrict__ Ginv, int* __restrict__ err, CgVecsT<T> v, double* __restrict__ gpart,
+               TM* __restrict__ Minv, double* __restrict__ Ginv, int* __restrict__ err, CgVecsT<T> v, double* __restrict__ gpart,
                CgControl* __restrict__ ctl) {
     __shared__ double sm[kThreads / 32];
     double g[1] = {0.0};
@@ -537,7 +539,7 @@ cg_init_kernel(int n, const double* __restrict__ b, const double* __restrict__ D
         load6(b, i, a, c);
         if (sizeof(T) == 4) { a = d3((float)a.x, (float)a.y, (float)a.z); c = d3((float)c.x, (float)c.y, (float)c.z); }   // r as stored
         r[0] = a.x; r[1] = a.y; r[2] = a.z; r[3] = c.x; r[4] = c.y; r[5] = c.z;
-        precond_block<true, T>(D, i, lambda, Minv, err, M);
+        precond_block<true, TM>(D, i, lambda, Minv, err, M);
 #pragma unroll
         for (int q = 0; q < 6; ++q) {
             double sacc = 0.0;
@@ -818,9 +820,9 @@ cg_spmv_kernel(int n, const double* __restrict__ P, const T* __restrict__ Je, co
 }
 
 // One CG step.  par = iteration parity (double-buffered scalars and gamma partials).
-template <typename T>
+template <typename T, typename TM = T>
 __global__ void __launch_bounds__(kThreads)
-cg_update_kernel(int n, int par, int first, const T* __restrict__ Minv, const double* __restrict__ Ginv,
+cg_update_kernel(int n, int par, int first, const TM* __restrict__ Minv, const double* __restrict__ Ginv,
                  const LinGlobal* __restrict__ lin, double lambda, CgVecsT<T> v,
                  const double* __restrict__ gpart_in, double* __restrict__ gpart_out,
                  const double* __restrict__ dpart, const double* __restrict__ bpart, int nspmv,
