@@ -315,6 +315,7 @@ int  dsc_batch_size(const dsc_batch* batch, int* n_problems, long long* n_points
  * eliminated by a Schur complement summed on the device, the reduced camera system (6 x free poses) is factorised on the
  * host.  poses7: [n_poses][7] = unit quaternion (x y z w) + translation of Tcw; pose_fixed: setFixed(true) (key frame id 0,
  * the fixed key frames of the local map); points_fixed != 0: the points are constants of the edges (pose-only).
+ * At most 512 free poses (the reduced system is dense on the host); a point may be observed once per pose.
  *   dsc_ba_set_levels   active[n_obs] != 0: edge at level 0 (optimised), 0: level 1 (left out); NULL = all at level 0
  *   dsc_ba_optimize     optimizer.optimize(n_iters); huber_delta <= 0: no robust kernel (setRobustKernel(0))
  *   dsc_ba_edge_chi2    e->chi2() and e->isDepthPositive() of every edge at the current estimate (any level)

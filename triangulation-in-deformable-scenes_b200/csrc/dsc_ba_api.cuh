@@ -38,6 +38,7 @@ struct dsc_ba {
 };
 
 namespace {
+constexpr int kBaMaxFreePoses = 512;
 int bafail(dsc_ba* b, int code, const std::string& what) {
     if (b) b->err = std::string(status_str(code)) + ": " + what;
     return code;
@@ -149,6 +150,10 @@ extern "C" int dsc_ba_upload(dsc_ba* ba, int n_poses, const double* poses7, cons
         ba->fixed[k] = pose_fixed && pose_fixed[k] ? 1 : 0;
         if (!ba->fixed[k]) ba->free_col[k] = 6 * ba->Kf++;
     }
+    // the reduced camera system is folded and factorised on the host (dense, 6 x free poses): fine for the local maps of the
+    // reference (a handful of key frames), refused beyond kBaMaxFreePoses rather than silently taking minutes per trial
+    if (ba->Kf > kBaMaxFreePoses)
+        return bafail(ba, DSC_ERR_INVALID_ARG, "more than " + std::to_string(kBaMaxFreePoses) + " free poses: the host factorisation of the reduced system is not meant for that");
     // ---- observations sorted by (point, pose): CSR over the points
     std::vector<int> ptr((size_t)M + 1, 0);
     for (long long o = 0; o < O; ++o) ptr[(size_t)obs_point[o] + 1]++;
@@ -203,6 +208,7 @@ extern "C" int dsc_ba_upload(dsc_ba* ba, int n_poses, const double* poses7, cons
     }
     if (twice) return bafail(ba, DSC_ERR_INVALID_ARG, "a point is observed twice from the same pose");
     for (int j = 0; j < M; ++j) eoff[(size_t)j + 1] += eoff[j];
+    if (eoff[M] > (size_t)0x7fffffff) return bafail(ba, DSC_ERR_INVALID_ARG, "too many observation pairs for 32-bit entry indices");
     std::vector<Ent> ents(eoff[M]);
 #pragma omp parallel for schedule(static)
     for (int j = 0; j < M; ++j) {
