@@ -21,6 +21,10 @@ checked (tests/test_oracle_pins.py): the Hessian structure rule of
 database, closed-form triangulation cases, analytic-vs-central-difference
 Jacobians, monotone cost under accepted steps.
 
+Round 2 added oracle/outer.py (the Nelder-Mead weight search of deformationOptimization and its objective;
+NLopt absent and unpinned: parity unpinned) and oracle/ba.py (bundleAdjustment / localBundleAdjustment /
+poseOnlyOptimization, g2oBundleAdjustment.cc:38-444; no executable of the reference calls them: parity unpinned).
+
 Two independently written restatements live here and are checked against each other
 (tests/test_c_oracle.py): the numpy modules of this package and the plain-C, OpenMP
 oracle/c/dsc_oracle.c (front end: oracle/cport.py; built into oracle/_build/ by

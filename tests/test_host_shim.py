@@ -102,6 +102,37 @@ def test_simulation_flow_single_call_matches_oracle():
     np.testing.assert_allclose(chi, tr.chi2, rtol=5e-2)            # different key-point rounding => loose; exact parity is in test_gpu_parity
 
 
+def test_local_map_of_a_key_frame():
+    """Map::getLocalMapOfKeyFrame (Map.cc:178-209) of the shim's Map: the key frame, its covisible key frames (more than
+    minCommonObs shared points), the points they see, and -- fixed -- every other key frame that sees one of those points;
+    against a direct restatement on observation sets, before and after removeObservation"""
+    lib = _host()
+    rng = np.random.default_rng(3)
+    K, M = 6, 60
+    sees = [set(rng.choice(M, size=rng.integers(8, 25), replace=False).tolist()) for _ in range(K)]
+    sees[4] = set(sorted(sees[0])[:2]) | set(sorted(set(range(M)) - sees[0])[:2])        # shares exactly 2 points with key frame 0
+    obs = [(k, j) for k in range(K) for j in sorted(sees[k])]
+    ok, oj = np.array([o[0] for o in obs], np.int32), np.array([o[1] for o in obs], np.int32)
+    ptr = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+
+    def expected(sees, curr, min_common):
+        lkf = {curr} | {k for k in range(K) if k != curr and len(sees[k] & sees[curr]) > min_common}
+        lmp = set().union(*[sees[k] for k in lkf])
+        fkf = {k for k in range(K) if k not in lkf and sees[k] & lmp}
+        return lkf, fkf, lmp
+    for curr, min_common, remove in ((0, 2.0, []), (0, 1.0, []), (3, 4.0, list(range(0, len(obs), 5)))):
+        cur = [set(s) for s in sees]
+        for r in remove:
+            cur[obs[r][0]].discard(obs[r][1])
+        rem = np.array(remove, np.int32)
+        lk, fk, lm = np.zeros(K, np.uint8), np.zeros(K, np.uint8), np.zeros(M, np.uint8)
+        assert lib.dsch_local_map(K, M, len(obs), ptr(ok), ptr(oj), len(remove), ptr(rem) if len(remove) else None, curr, ctypes.c_float(min_common),
+                                  ptr(lk), ptr(fk), ptr(lm)) == 0
+        elk, efk, elm = expected(cur, curr, min_common)
+        assert set(np.nonzero(lk)[0]) == elk and set(np.nonzero(fk)[0]) == efk and set(np.nonzero(lm)[0]) == elm
+    assert 4 not in expected(sees, 0, 2.0)[0] and 4 in expected(sees, 0, 1.0)[0]
+
+
 def _shim_nm(lib, fn, x0, lb, ub, xtol_rel, xtol_abs, maxeval, speculative):
     dim = len(x0)
     arr = lambda v: np.ascontiguousarray(v, np.float64)

@@ -1027,3 +1027,33 @@ extern "C" int dsch_ba_flow(int mode, int K, const float* pose34, const float* c
     }
 }
 #endif
+
+#ifndef DSC_IN_REFERENCE_TREE
+// Map::getLocalMapOfKeyFrame / addObservation / removeObservation of host/Map.h on a Map given as observation lists
+// (tests/test_host_shim.py, CPU): obs = (key frame index, map point index); out_* are 0/1 flags per key frame / point.
+extern "C" int dsch_local_map(int K, int M, int O, const int* obs_kf, const int* obs_mp, int n_remove, const int* remove_obs, int curr, float minCommonObs,
+                              unsigned char* local_kf, unsigned char* fixed_kf, unsigned char* local_mp) {
+    KeyFrame::restartIds(); MapPoint::restartIds();
+    Map map;
+    map.setMinCommonObs(minCommonObs);
+    std::vector<float> cp = {500.f, 500.f, 320.f, 240.f, 0.f, 0.f, 0.f, 0.f};
+    auto calib = std::make_shared<KannalaBrandt8>(cp);
+    std::vector<KeyFrame_> kfs(K);
+    std::vector<MapPoint_> mps(M);
+    for (int j = 0; j < M; ++j) { Eigen::Vector3f p(0.f, 0.f, 1.f); mps[j] = std::make_shared<MapPoint>(p); map.insertMapPoint(mps[j]); }
+    std::vector<int> slots(K, 0);
+    for (int e = 0; e < O; ++e) slots[obs_kf[e]]++;
+    for (int k = 0; k < K; ++k) {
+        kfs[k] = std::make_shared<KeyFrame>(std::vector<cv::KeyPoint>((size_t)slots[k]), Sophus::SE3f(), calib);
+        map.insertKeyFrame(kfs[k]);
+    }
+    std::vector<int> next(K, 0);
+    for (int e = 0; e < O; ++e) map.addObservation(kfs[obs_kf[e]]->getId(), mps[obs_mp[e]]->getId(), (size_t)next[obs_kf[e]]++);
+    for (int r = 0; r < n_remove; ++r) map.removeObservation(kfs[obs_kf[remove_obs[r]]]->getId(), mps[obs_mp[remove_obs[r]]]->getId());
+    std::set<ID> lmp, lkf, fkf;
+    map.getLocalMapOfKeyFrame(kfs[curr]->getId(), lmp, lkf, fkf);
+    for (int k = 0; k < K; ++k) { local_kf[k] = lkf.count(kfs[k]->getId()) ? 1 : 0; fixed_kf[k] = fkf.count(kfs[k]->getId()) ? 1 : 0; }
+    for (int j = 0; j < M; ++j) local_mp[j] = lmp.count(mps[j]->getId()) ? 1 : 0;
+    return 0;
+}
+#endif
