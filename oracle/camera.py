@@ -29,6 +29,29 @@ def kb8_project(P, Xc):
     return np.stack([u, v], axis=-1)
 
 
+def kb8_project_double_trig(P, Xc):
+    """The OTHER reading of KannalaBrandt8.cc:47-48: `cos(psi)` / `sin(psi)` taken as ::cos(double) / ::sin(double) -- the float
+    product fx * r promoted to double, multiplied, cx added in double, the sum rounded to float on assignment.  Not what
+    libstdc++ resolves the unqualified call to (its <cmath> / <math.h> put the float overloads of std::cos into the global
+    namespace, so `cos(float)` is cosf and kb8_project above is the reading); kept to MEASURE the difference
+    (tests/test_oracle_pins.py::test_kb8_cos_overload_reading)."""
+    P = f32(P)
+    Xc = f32(Xc)
+    x, y, z = Xc[..., 0], Xc[..., 1], Xc[..., 2]
+    theta = emu(np.arctan2, emu(np.sqrt, x * x + y * y), z)
+    psi = emu(np.arctan2, y, x)
+    theta2 = theta * theta
+    theta3 = theta * theta2
+    theta5 = theta3 * theta2
+    theta7 = theta5 * theta2
+    theta9 = theta7 * theta2
+    r = (((theta + P[4] * theta3) + P[5] * theta5) + P[6] * theta7) + P[7] * theta9
+    psd = psi.astype(np.float64)
+    u = ((P[0] * r).astype(np.float64) * np.cos(psd) + np.float64(P[2])).astype(np.float32)
+    v = ((P[1] * r).astype(np.float64) * np.sin(psd) + np.float64(P[3])).astype(np.float32)
+    return np.stack([u, v], axis=-1)
+
+
 def kb8_unproject(P, uv):
     """KannalaBrandt8.cc:51-83.  <=10 Newton steps on theta, tol 1e-6 (KannalaBrandt8.h:29).
 

@@ -48,6 +48,28 @@ def test_sigma_database_pin():
         assert scenes.pixel_sigma((camera.KB8, fk["cam"]), fk["T1"], o, fk["uv1"]) == pytest.approx(m["database"]["sigma_c1"], rel=2e-2)
 
 
+def test_kb8_cos_overload_reading():
+    """KannalaBrandt8.cc:47-48 calls unqualified cos(psi) / sin(psi) on a float.  With libstdc++ that is
+    cosf (the float overload), which the oracle and the CUDA path restate (trig rounded to float, float product); the other
+    reading -- ::cos(double), product and sum in double, one rounding -- is restated next to it.  No reference-held number can
+    tell them apart (the logs that pin the oracle were written with PinHole intrinsics), so the difference is MEASURED: the
+    two readings differ in a minority of pixels, by one float ulp of the pixel coordinate at most a few times 1e-5 px -- seven
+    orders below the 1 px key-point noise, invisible to every parity bar except bit-exactness."""
+    rng = np.random.default_rng(0)
+    for cam in (scenes.SIM_CAM, scenes.REALCOLON_CAM):
+        Xc = np.stack([rng.normal(0, 0.08, 200000), rng.normal(0, 0.06, 200000), rng.uniform(0.1, 0.5, 200000)], 1).astype(np.float32)
+        a = camera.kb8_project(cam, Xc).astype(np.float64)
+        b = camera.kb8_project_double_trig(cam, Xc).astype(np.float64)
+        d = np.abs(a - b)
+        ulp = np.spacing(np.abs(a).astype(np.float32)).astype(np.float64)
+        assert d.max() <= 2.0 * ulp.max() and d.max() < 2.5e-4                # never more than two ulps of a ~1000 px coordinate
+        frac = float((d > 0).mean())
+        assert 0.02 < frac < 0.6                                              # a real difference, in a minority of coordinates
+        obs = a + rng.normal(0, 1.0, a.shape)
+        sig = lambda p: np.sqrt(((obs - p) ** 2).mean(0)).mean()
+        assert abs(sig(a) - sig(b)) <= 1e-6 * sig(a)                          # the pixel-sigma statistic cannot see it
+
+
 def test_triangulation_reproduces_the_reference_logs():
     """REFERENCE-HELD NUMBERS.  The INITIAL MEASUREMENTS blocks of Data/Experiments/**/Experiment.txt were written by
     the reference right after triangulation: mean / RMSE 3-D error (Measurements.cc:8-98) and the pixel sigma of the
